@@ -1,0 +1,149 @@
+// Shared device/host helpers for the tdanet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/tdanet_b200.h"
+
+namespace td {
+
+// ----------------------------------------------------------------------------- host side
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+int fail(int code, const char* fmt, ...);
+
+#define TD_CUDA(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return td::fail(TDANET_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                      __FILE__, __LINE__);                                               \
+  } while (0)
+
+#define TD_REQUIRE(cond, ...)                                                            \
+  do {                                                                                   \
+    if (!(cond)) return td::fail(TDANET_EINVAL, __VA_ARGS__);                            \
+  } while (0)
+
+// Every kernel launch goes through this so that tdanet_launch_count() is honest.
+#define TD_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
+  do {                                                                                   \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+    td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t _e = cudaPeekAtLastError();                                              \
+    if (_e != cudaSuccess)                                                               \
+      return td::fail(TDANET_ECUDA, "launch of %s failed: %s", #kernel, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- device side
+constexpr float kEpsGLN = 1e-8f;
+constexpr float kEpsLN = 1e-5f;
+
+// V consecutive channels held by one thread (V = 2 or 4)
+template <int V>
+struct vf {
+  float v[V];
+  __device__ __forceinline__ float& operator[](int i) { return v[i]; }
+  __device__ __forceinline__ const float& operator[](int i) const { return v[i]; }
+};
+
+template <int V>
+__device__ __forceinline__ vf<V> vzero() {
+  vf<V> r;
+#pragma unroll
+  for (int i = 0; i < V; ++i) r.v[i] = 0.f;
+  return r;
+}
+
+template <int V>
+__device__ __forceinline__ vf<V> vload(const float* __restrict__ p) {
+  vf<V> r;
+  if constexpr (V == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (V == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+
+template <int V>
+__device__ __forceinline__ void vstore(float* __restrict__ p, const vf<V>& r) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else if constexpr (V == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
+  } else {
+    *p = r.v[0];
+  }
+}
+
+// fire-and-forget vector reduction into global memory (red.global.add.v{2,4}.f32 on sm_90+)
+template <int V>
+__device__ __forceinline__ void vred_add(float* p, const vf<V>& r) {
+  if constexpr (V == 4) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+                 "f"(r.v[2]), "f"(r.v[3])
+                 : "memory");
+  } else if constexpr (V == 2) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]) : "memory");
+  } else {
+    atomicAdd(p, r.v[0]);
+  }
+}
+
+// round-to-nearest (ties away) to TF32: what producers of GEMM-only operands store in TF32 mode so
+// that the tensor core's truncation of the low 13 mantissa bits is exact
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+template <int V>
+__device__ __forceinline__ void vround_tf32(vf<V>& r) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) r.v[i] = tf32_rna(r.v[i]);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float preluf_(float x, float a) { return x >= 0.f ? x : a * x; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of two doubles; result valid in every thread.  `sh` needs 2*32 doubles.
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* sh) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();  // protect sh against a previous use
+  if (l == 0) { sh[w] = a; sh[32 + w] = b; }
+  __syncthreads();
+  a = 0.0; b = 0.0;
+  for (int i = 0; i < nw; ++i) { a += sh[i]; b += sh[32 + i]; }
+}
+
+// index of the source row for F.interpolate(mode="nearest"): min(floor(dst * fl32(in/out)), in-1)
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_len) {
+  int s = (int)floorf((float)dst * scale);
+  return s < in_len - 1 ? s : in_len - 1;
+}
+static inline float nearest_scale(int in_len, int out_len) { return (float)in_len / (float)out_len; }
+
+}  // namespace td

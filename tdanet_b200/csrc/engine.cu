@@ -1,0 +1,506 @@
+// Host-side orchestration of one TDANet forward pass: workspace planning and the launch sequence.
+//
+// Replaces the Python control flow of TDANet*.forward / Recurrent.forward / UConvBlock.forward
+// (TDANet_best.py:342-399, 482-521; TDANet.py:586-636, 769-785, 869-909; TDANet_mult_tes.py:391-434,
+// 540-579).  Everything between two GlobLN-delimited tensors is one launch; see DESIGN.md for the
+// stage list and the bytes each stage moves.
+#include "kernels.h"
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace td {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+size_t pit_scratch_floats(int B);
+
+// ----------------------------------------------------------------------------- plan
+struct Named {
+  std::string name;
+  size_t off;  // bytes
+  int64_t dims[3];
+};
+
+struct Plan {
+  int B, T, Tp, rest;
+  int depth, L[TDANET_MAX_DEPTH], Lb;
+  size_t bytes = 0;
+  std::vector<Named> named;
+  // activations
+  size_t enc, x0, u[2], proj, spp[TDANET_MAX_DEPTH], expanded[TDANET_MAX_DEPTH];
+  size_t ga_in, attn_in, qkv, attn_ctx, attn_out, ga_mid, fc1, ffn_dw, fc2, ga_out;
+  size_t pool_dw[TDANET_MAX_DEPTH], pool_pw[TDANET_MAX_DEPTH];
+  size_t masked;
+  // coefficient tables
+  size_t enc_coef, proj_coef, spp_coef[TDANET_MAX_DEPTH], fc1_coef, fc2_coef, inj_coef[TDANET_MAX_DEPTH],
+      la_coef[TDANET_MAX_DEPTH], pool_coef[TDANET_MAX_DEPTH];
+  // statistics arena (zeroed once per block)
+  size_t stats_begin, stats_end;
+  size_t st_enc, st_proj, st_fc1, st_fc2, st_pool[TDANET_MAX_DEPTH];       // double [B,2]
+  size_t st_spp[TDANET_MAX_DEPTH], st_g, st_la_l[TDANET_MAX_DEPTH], st_la_g[TDANET_MAX_DEPTH];  // float
+  // TF32 auxiliary weight copies
+  size_t aux_proj, aux_res, aux_in, aux_out, aux_fc1, aux_fc2, aux_pool[TDANET_MAX_DEPTH];
+
+  size_t take(size_t nbytes) {
+    size_t o = bytes;
+    bytes += (nbytes + 255) / 256 * 256;
+    return o;
+  }
+  size_t act(const char* name, int64_t L_, int64_t C_) {
+    size_t o = take((size_t)B * L_ * C_ * sizeof(float));
+    if (name) named.push_back({name, o, {B, L_, C_}});
+    return o;
+  }
+};
+
+static int check_config(const tdanet_config_t* c) {
+  TD_REQUIRE(c != nullptr, "config is NULL");
+  TD_REQUIRE(c->variant >= TDANET_BEST && c->variant <= TDANET_MULTRES, "unknown variant %d", c->variant);
+  TD_REQUIRE(c->depth >= 2 && c->depth <= TDANET_MAX_DEPTH, "upsampling_depth %d outside [2, %d]", c->depth, TDANET_MAX_DEPTH);
+  TD_REQUIRE(c->num_blocks >= 1, "num_blocks %d", c->num_blocks);
+  TD_REQUIRE(c->out_channels > 0 && c->out_channels % 16 == 0, "out_channels %d must be a multiple of 16", c->out_channels);
+  TD_REQUIRE(c->in_channels > 0 && c->in_channels % 16 == 0, "in_channels %d must be a multiple of 16", c->in_channels);
+  TD_REQUIRE(c->n_head > 0 && c->in_channels % c->n_head == 0, "in_channels %d not divisible by n_head %d", c->in_channels, c->n_head);
+  TD_REQUIRE(c->enc_kernel > 0 && c->enc_kernel % 4 == 0 && c->enc_stride == c->enc_kernel / 4, "encoder window %d / hop %d", c->enc_kernel, c->enc_stride);
+  TD_REQUIRE(c->num_sources == 2 || c->num_sources == 3, "num_sources %d", c->num_sources);
+  TD_REQUIRE(c->gemm_mode >= TDANET_GEMM_FP32 && c->gemm_mode <= TDANET_GEMM_TF32X3, "gemm_mode %d", c->gemm_mode);
+  if (c->variant == TDANET_MULTRES) {
+    TD_REQUIRE(c->enc_convs >= 1 && c->enc_convs <= TDANET_MAX_ENC && c->out_channels % c->enc_convs == 0,
+               "MULTRES: out_channels %d not divisible by kernels %d", c->out_channels, c->enc_convs);
+    TD_REQUIRE(c->n_basis == c->out_channels, "MULTRES: n_basis %d != out_channels %d", c->n_basis, c->out_channels);
+  } else {
+    TD_REQUIRE(c->enc_convs == 1, "enc_convs %d", c->enc_convs);
+    TD_REQUIRE(c->n_basis == c->enc_kernel / 2 + 1, "n_basis %d != K/2+1", c->n_basis);
+  }
+  return 0;
+}
+
+static int make_plan(const tdanet_config_t* c, int B, int T, Plan& p) {
+  if (int e = check_config(c)) return e;
+  TD_REQUIRE(B > 0 && T > 0, "batch %d / n_samples %d", B, T);
+  const int K = c->enc_kernel, S = c->enc_stride, C = c->in_channels, cc = c->out_channels;
+  p.B = B;
+  p.T = T;
+  // pad_input (TDANet_best.py:465-479)
+  p.rest = K - (S + T % K) % K;
+  p.Tp = T + p.rest + 2 * (K - S);
+  p.depth = c->depth;
+  p.L[0] = p.Tp / S + 1;  // Conv1d(k, stride S, padding k/2), k even
+  for (int k = 1; k < c->depth; ++k) p.L[k] = (p.L[k - 1] - 1) / 2 + 1;
+  p.Lb = p.L[c->depth - 1];
+  const int L0 = p.L[0], Lb = p.Lb, Nb = c->n_basis;
+  char nm[32];
+
+  p.enc = p.act("enc", L0, Nb);
+  p.x0 = p.act("x0", L0, cc);
+  p.u[0] = p.act("u0", L0, cc);
+  p.u[1] = p.act("u1", L0, cc);
+  p.proj = p.act("proj", L0, C);
+  for (int k = 0; k < c->depth; ++k) {
+    snprintf(nm, sizeof nm, "spp%d", k);
+    p.spp[k] = p.act(nm, p.L[k], C);
+  }
+  for (int k = 0; k < c->depth - 1; ++k) {
+    snprintf(nm, sizeof nm, "expanded%d", k);
+    p.expanded[k] = p.act(nm, p.L[k], C);
+  }
+  p.ga_in = p.act("ga_in", Lb, C);
+  p.attn_in = p.act("attn_in", Lb, C);
+  p.qkv = p.act("qkv", Lb, 3 * C);
+  p.attn_ctx = p.act("attn_ctx", Lb, C);
+  p.attn_out = p.act("attn_out", Lb, C);
+  p.ga_mid = p.act("ga_mid", Lb, C);
+  p.fc1 = p.act("fc1", Lb, 2 * C);
+  p.ffn_dw = p.act("ffn_dw", Lb, 2 * C);
+  p.fc2 = p.act("fc2", Lb, C);
+  p.ga_out = p.act("ga_out", Lb, C);
+  if (c->variant == TDANET_FORK)
+    for (int k = 0; k < c->depth; ++k) {
+      snprintf(nm, sizeof nm, "pool_dw%d", k);
+      p.pool_dw[k] = p.act(nm, Lb, C);
+      snprintf(nm, sizeof nm, "pool_pw%d", k);
+      p.pool_pw[k] = p.act(nm, Lb, C);
+    }
+  p.masked = p.act("masked", L0, c->num_sources * Nb);
+
+  auto tab = [&](int planes, int ch) { return p.take((size_t)B * planes * ch * sizeof(float)); };
+  p.enc_coef = tab(2, Nb);
+  p.proj_coef = tab(2, C);
+  p.fc1_coef = tab(2, 2 * C);
+  p.fc2_coef = tab(2, C);
+  for (int k = 0; k < c->depth; ++k) {
+    p.spp_coef[k] = tab(2, C);
+    p.inj_coef[k] = tab(6, C);
+    p.la_coef[k] = tab(6, C);
+    p.pool_coef[k] = tab(2, C);
+  }
+  p.stats_begin = p.bytes;
+  auto dstat = [&]() { return p.take((size_t)B * 2 * sizeof(double)); };
+  p.st_enc = dstat();
+  p.st_proj = dstat();
+  p.st_fc1 = dstat();
+  p.st_fc2 = dstat();
+  for (int k = 0; k < c->depth; ++k) {
+    p.st_pool[k] = dstat();
+    p.st_spp[k] = tab(2, C);
+    p.st_la_l[k] = tab(2, C);
+    p.st_la_g[k] = tab(4, C);
+  }
+  p.st_g = tab(2, C);
+  p.stats_end = p.bytes;
+
+  auto wbuf = [&](size_t n) { return p.take(n * sizeof(float)); };
+  p.aux_proj = wbuf((size_t)C * cc);
+  p.aux_res = wbuf((size_t)cc * C);
+  p.aux_in = wbuf((size_t)3 * C * C);
+  p.aux_out = wbuf((size_t)C * C);
+  p.aux_fc1 = wbuf((size_t)2 * C * C);
+  p.aux_fc2 = wbuf((size_t)2 * C * C);
+  for (int k = 0; k < c->depth; ++k) p.aux_pool[k] = c->variant == TDANET_FORK ? wbuf((size_t)C * C) : 0;
+  // "block_out" aliases the u buffer the last block writes
+  p.named.push_back({"block_out", p.u[(c->num_blocks - 1) & 1], {B, L0, cc}});
+  p.named.push_back({"u", p.u[(c->num_blocks & 1)], {B, L0, cc}});
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- forward
+struct Ctx {
+  const tdanet_config_t* c;
+  const tdanet_weights_t* w;
+  const Plan* p;
+  char* ws;
+  cudaStream_t st;
+  // producers of GEMM-only operands store TF32-rounded values when the tensor-core path is on
+  int rnd() const { return c->gemm_mode != TDANET_GEMM_FP32; }
+  template <class T = float>
+  T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
+};
+
+static int gemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
+  if (x.c->gemm_mode == TDANET_GEMM_FP32) return launch_gemm_simt(g, x.st);
+  g.W_aux = x.at(aux_off);
+  return launch_gemm_tc(g, x.c->gemm_mode, x.st);
+}
+
+static int prepare_weights(const Ctx& x) {
+  const tdanet_config_t* c = x.c;
+  if (c->gemm_mode == TDANET_GEMM_FP32) return 0;
+  const size_t C = c->in_channels, cc = c->out_channels;
+  const int m = c->gemm_mode;
+  if (int e = launch_tf32_prepare(x.w->proj.w, x.at(x.p->aux_proj), C * cc, m, x.st)) return e;
+  if (int e = launch_tf32_prepare(x.w->res_w, x.at(x.p->aux_res), C * cc, m, x.st)) return e;
+  if (int e = launch_tf32_prepare(x.w->in_proj_w, x.at(x.p->aux_in), 3 * C * C, m, x.st)) return e;
+  if (int e = launch_tf32_prepare(x.w->out_proj_w, x.at(x.p->aux_out), C * C, m, x.st)) return e;
+  if (int e = launch_tf32_prepare(x.w->fc1.w, x.at(x.p->aux_fc1), 2 * C * C, m, x.st)) return e;
+  if (int e = launch_tf32_prepare(x.w->fc2.w, x.at(x.p->aux_fc2), 2 * C * C, m, x.st)) return e;
+  if (c->variant == TDANET_FORK)
+    for (int k = 0; k < c->depth; ++k)
+      if (int e = launch_tf32_prepare(x.w->conv_pool[k].pw_w, x.at(x.p->aux_pool[k]), C * C, m, x.st)) return e;
+  return 0;
+}
+
+static SrcDesc plain_src(const float* x, int L) { return SrcDesc{x, L, nullptr, nullptr, nullptr, 0, 0.f}; }
+static SrcDesc affine_src(const float* x, int L, const float* coef, const float* slope = nullptr) {
+  return SrcDesc{x, L, coef, slope, nullptr, 0, 0.f};
+}
+
+// The bottom-scale block: GA / GlobalAttention (TDANet_best.py:254-264)
+static int global_attention(const Ctx& x) {
+  const tdanet_config_t* c = x.c;
+  const tdanet_weights_t* w = x.w;
+  const Plan& p = *x.p;
+  const int B = p.B, C = c->in_channels, Lb = p.Lb;
+  const bool time_axis = c->variant == TDANET_MULTRES;
+  const int group = c->attn_group > 0 ? c->attn_group : B;
+  TD_REQUIRE(time_axis || B % group == 0, "batch %d is not a multiple of attn_group %d", B, group);
+  TD_REQUIRE(w->pe_rows >= Lb, "positional encoding has %d rows, need %d", w->pe_rows, Lb);
+
+  // attn_in_norm + positional encoding
+  if (int e = launch_ln_pe(x.at(p.ga_in), w->ln1_w, w->ln1_b, w->pe, x.at(p.attn_in), B, Lb, C, x.rnd(), x.st)) return e;
+  GemmArgs g{};
+  g.A = x.at(p.attn_in); g.W = w->in_proj_w; g.bias = w->in_proj_b; g.D = x.at(p.qkv);
+  g.B = B; g.L = Lb; g.N = 3 * C; g.K = C; g.epi = EPI_BIAS;
+  if (int e = gemm(x, g, p.aux_in)) return e;
+  if (int e = launch_attention(x.at(p.qkv), x.at(p.attn_ctx), B, Lb, C, c->n_head, group, time_axis, x.rnd(), x.st)) return e;
+  g = GemmArgs{};
+  g.A = x.at(p.attn_ctx); g.W = w->out_proj_w; g.bias = w->out_proj_b; g.D = x.at(p.attn_out);
+  g.B = B; g.L = Lb; g.N = C; g.K = C; g.epi = EPI_BIAS;
+  if (int e = gemm(x, g, p.aux_out)) return e;
+  // x + LayerNorm(out + dropout(out))  [BEST/FORK]   |   x + LayerNorm(pe_in + out)  [MULTRES]
+  if (int e = launch_ln_residual(x.at(p.attn_out), x.at(p.attn_in), x.at(p.ga_in), w->ln2_w, w->ln2_b,
+                                 x.at(p.ga_mid), !time_axis, B, Lb, C, x.st)) return e;
+  // FFN: fc1 (1x1, no bias) -> gLN -> dw k5 + bias -> ReLU -> fc2 (1x1, no bias) -> gLN
+  g = GemmArgs{};
+  g.A = x.at(p.ga_mid); g.W = w->fc1.w; g.bias = nullptr; g.D = x.at(p.fc1);
+  g.B = B; g.L = Lb; g.N = 2 * C; g.K = C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_fc1);
+  if (int e = gemm(x, g, p.aux_fc1)) return e;
+  if (int e = launch_coef_item(x.at<double>(p.st_fc1), (double)Lb * 2 * C, w->fc1.gamma, w->fc1.beta,
+                               x.at(p.fc1_coef), B, 2 * C, x.st)) return e;
+  DwArgs d{};
+  d.src = affine_src(x.at(p.fc1), Lb, x.at(p.fc1_coef));
+  d.kind = SRC_AFFINE; d.B = B; d.C = 2 * C; d.Lout = Lb; d.stride = 1; d.nw = 1;
+  d.w[0] = w->ffn_dw_w; d.bias[0] = w->ffn_dw_b; d.out = x.at(p.ffn_dw); d.relu = 1; d.round_out = x.rnd();
+  if (int e = launch_dw5(d, x.st)) return e;
+  g = GemmArgs{};
+  g.A = x.at(p.ffn_dw); g.W = w->fc2.w; g.bias = nullptr; g.D = x.at(p.fc2);
+  g.B = B; g.L = Lb; g.N = C; g.K = 2 * C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_fc2);
+  if (int e = gemm(x, g, p.aux_fc2)) return e;
+  if (int e = launch_coef_item(x.at<double>(p.st_fc2), (double)Lb * C, w->fc2.gamma, w->fc2.beta,
+                               x.at(p.fc2_coef), B, C, x.st)) return e;
+  // global_f = x + gLN(fc2); BEST also needs its per-channel sums for the closed-form loc_glo_fus
+  return launch_affine_residual(x.at(p.fc2), x.at(p.fc2_coef), x.at(p.ga_mid), x.at(p.ga_out),
+                                c->variant == TDANET_BEST ? x.at(p.st_g) : nullptr, B, Lb, C, x.st);
+}
+
+// One UConvBlock (TDANet_best.py:342-380) including the concat_block that feeds the next one.
+static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
+  const tdanet_config_t* c = x.c;
+  const tdanet_weights_t* w = x.w;
+  const Plan& p = *x.p;
+  const int B = p.B, C = c->in_channels, cc = c->out_channels, depth = c->depth, Lb = p.Lb;
+  TD_CUDA(cudaMemsetAsync(x.ws + p.st_proj, 0, p.stats_end - p.st_proj, x.st));
+
+  // proj_1x1: 1x1 conv c -> C (+bias); GlobLN + PReLU are applied by the consumer on load
+  GemmArgs g{};
+  g.A = in; g.W = w->proj.w; g.bias = w->proj.b; g.D = x.at(p.proj);
+  g.B = B; g.L = p.L[0]; g.N = C; g.K = cc; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_proj);
+  if (int e = gemm(x, g, p.aux_proj)) return e;
+  if (int e = launch_coef_item(x.at<double>(p.st_proj), (double)p.L[0] * C, w->proj.gamma, w->proj.beta,
+                               x.at(p.proj_coef), B, C, x.st)) return e;
+  // spp_dw[0..depth-1]: depthwise k5 (stride 1, then 2), raw output + per-channel sums
+  for (int k = 0; k < depth; ++k) {
+    DwArgs d{};
+    if (k == 0) {
+      d.src = affine_src(x.at(p.proj), p.L[0], x.at(p.proj_coef), w->proj_prelu);
+      d.kind = SRC_AFFINE_PRELU;
+    } else {
+      d.src = affine_src(x.at(p.spp[k - 1]), p.L[k - 1], x.at(p.spp_coef[k - 1]));
+      d.kind = SRC_AFFINE;
+    }
+    d.B = B; d.C = C; d.Lout = p.L[k]; d.stride = k == 0 ? 1 : 2; d.nw = 1;
+    d.w[0] = w->spp_dw[k].w; d.bias[0] = w->spp_dw[k].b; d.out = x.at(p.spp[k]); d.stats = x.at(p.st_spp[k]);
+    if (int e = launch_dw5(d, x.st)) return e;
+    if (int e = launch_coef_chan(x.at(p.st_spp[k]), (size_t)2 * C, p.L[k], w->spp_dw[k].gamma, w->spp_dw[k].beta,
+                                 x.at(p.spp_coef[k]), B, C, x.st)) return e;
+  }
+  // global feature at the bottom scale
+  PoolArgs pa{};
+  pa.n = depth; pa.B = B; pa.C = C; pa.Lb = Lb; pa.out = x.at(p.ga_in);
+  if (c->variant == TDANET_FORK) {
+    // conv_pool[depth-1-k](spp[k]): dw (k = 2s+1, stride s = 2^(depth-1-k)) -> 1x1 -> gLN; summed
+    for (int k = 0; k < depth; ++k) {
+      const int j = depth - 1 - k, s = 1 << j, ks = j == 0 ? 5 : 2 * s + 1;
+      const tdanet_sepconvnorm_t& q = w->conv_pool[j];
+      if (int e = launch_dw_generic(affine_src(x.at(p.spp[k]), p.L[k], x.at(p.spp_coef[k])), SRC_AFFINE, B, C, Lb,
+                                    ks, s, q.dw_w, q.dw_b, x.at(p.pool_dw[k]), x.rnd(), x.st)) return e;
+      g = GemmArgs{};
+      g.A = x.at(p.pool_dw[k]); g.W = q.pw_w; g.bias = q.pw_b; g.D = x.at(p.pool_pw[k]);
+      g.B = B; g.L = Lb; g.N = C; g.K = C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_pool[k]);
+      if (int e = gemm(x, g, p.aux_pool[j])) return e;
+      if (int e = launch_coef_item(x.at<double>(p.st_pool[k]), (double)Lb * C, q.gamma, q.beta, x.at(p.pool_coef[k]),
+                                   B, C, x.st)) return e;
+      pa.x[k] = x.at(p.pool_pw[k]); pa.coef[k] = x.at(p.pool_coef[k]); pa.L[k] = Lb;
+    }
+    if (int e = launch_affine_sum(pa, x.st)) return e;
+  } else {
+    for (int k = 0; k < depth; ++k) { pa.x[k] = x.at(p.spp[k]); pa.coef[k] = x.at(p.spp_coef[k]); pa.L[k] = p.L[k]; }
+    if (int e = launch_pool_sum(pa, x.st)) return e;
+  }
+  if (int e = global_attention(x)) return e;
+
+  // injection of the global feature: never materialised, recomputed on load by the LA kernels
+  const int inj_kind = c->variant == TDANET_BEST ? SRC_INJECT_GATE : SRC_INJECT_ADD;
+  const float* gf = x.at(p.ga_out);
+  auto inj_src = [&](int k) {
+    SrcDesc s{};
+    s.x = x.at(p.spp[k]); s.L = p.L[k];
+    s.coef = c->variant == TDANET_BEST ? x.at(p.inj_coef[k]) : x.at(p.spp_coef[k]);
+    s.g = gf; s.Lg = Lb; s.gscale = nearest_scale(Lb, p.L[k]);
+    return s;
+  };
+  if (c->variant == TDANET_BEST)
+    for (int k = 0; k < depth; ++k)
+      if (int e = launch_coef_inject_gate(x.at(p.st_spp[k]), (size_t)2 * C, p.L[k], &w->spp_dw[k], x.at(p.st_g), Lb,
+                                          &w->loc_glo_fus[k], x.at(p.inj_coef[k]), B, C, x.st)) return e;
+  // top-down fusion: last_layer[i](x_fused[i], i == depth-2 ? x_fused[i-1] : expanded)
+  for (int i = depth - 2; i >= 0; --i) {
+    const tdanet_la_t& la = w->last_layer[i];
+    SrcDesc loc = inj_src(i), glo;
+    int gkind;
+    if (i == depth - 2) {
+      glo = inj_src((i - 1 + depth) % depth);  // python x_fused[i-1]: the finer neighbour (or [-1])
+      gkind = inj_kind;
+    } else {
+      glo = plain_src(x.at(p.expanded[i + 1]), p.L[i + 1]);
+      gkind = SRC_PLAIN;
+    }
+    DwArgs d{};
+    d.src = loc; d.kind = inj_kind; d.B = B; d.C = C; d.Lout = loc.L; d.stride = 1; d.nw = 1;
+    d.w[0] = la.local_embedding.w; d.stats = x.at(p.st_la_l[i]);
+    if (int e = launch_dw5(d, x.st)) return e;
+    d = DwArgs{};
+    d.src = glo; d.kind = gkind; d.B = B; d.C = C; d.Lout = glo.L; d.stride = 1; d.nw = 2;
+    d.w[0] = la.global_act.w; d.w[1] = la.global_embedding.w; d.stats = x.at(p.st_la_g[i]);
+    if (int e = launch_dw5(d, x.st)) return e;
+    if (int e = launch_coef_la(x.at(p.st_la_l[i]), loc.L, x.at(p.st_la_g[i]), glo.L, &la, x.at(p.la_coef[i]), B, C, x.st)) return e;
+    LaArgs l{};
+    l.loc = loc; l.glo = glo; l.lkind = inj_kind; l.gkind = gkind; l.B = B; l.C = C;
+    l.wl = la.local_embedding.w; l.wa = la.global_act.w; l.we = la.global_embedding.w;
+    l.coef = x.at(p.la_coef[i]); l.out = x.at(p.expanded[i]); l.scale = nearest_scale(glo.L, loc.L);
+    l.round_out = i == 0 && x.rnd();  // expanded[0] only feeds res_conv
+    if (int e = launch_la_combine(l, x.st)) return e;
+  }
+  // res_conv + residual (+ concat_block for the next iteration)
+  g = GemmArgs{};
+  g.A = x.at(p.expanded[0]); g.W = w->res_w; g.bias = w->res_b; g.D = out;
+  g.B = B; g.L = p.L[0]; g.N = cc; g.K = C; g.epi = EPI_RESIDUAL;
+  g.resid = in; g.mix = x.at(p.x0); g.cw = w->concat_w; g.cb = w->concat_b; g.cslope = w->concat_prelu; g.last = last;
+  return gemm(x, g, p.aux_res);
+}
+
+static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const float* wav, int B, int T,
+                   float* est, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  Plan p;
+  if (int e = make_plan(c, B, T, p)) return e;
+  TD_REQUIRE(w && wav && est && workspace, "NULL argument");
+  if (ws_bytes < p.bytes) return fail(TDANET_ENOSPACE, "workspace has %zu bytes, need %zu", ws_bytes, p.bytes);
+  TD_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  Ctx x{c, w, &p, (char*)workspace, st};
+  const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
+
+  TD_CUDA(cudaMemsetAsync(x.ws + p.st_enc, 0, p.st_proj - p.st_enc, st));
+  if (int e = prepare_weights(x)) return e;
+  // encoder (+ pad_input folded into the indexing) and its GlobLN statistics
+  EncArgs ea{};
+  ea.wav = wav; ea.B = B; ea.T = T; ea.K = K; ea.S = S; ea.front_pad = K - S; ea.Tp = p.Tp;
+  ea.nconv = c->enc_convs; ea.ch_per_conv = Nb / c->enc_convs; ea.Nb = Nb; ea.L0 = L0;
+  for (int k = 0; k < c->enc_convs; ++k) { ea.w[k] = w->enc_w[k]; ea.ks[k] = (k + 1) * K; }
+  ea.out = x.at(p.enc); ea.stats = x.at<double>(p.st_enc);
+  if (int e = launch_encoder(ea, st)) return e;
+  if (int e = launch_coef_item(x.at<double>(p.st_enc), (double)L0 * Nb, w->ln_gamma, w->ln_beta, x.at(p.enc_coef), B, Nb, st)) return e;
+  if (c->variant == TDANET_MULTRES) {
+    if (int e = launch_affine(x.at(p.enc), x.at(p.enc_coef), x.at(p.x0), B, L0, Nb, st)) return e;
+  } else {
+    if (int e = launch_bottleneck(x.at(p.enc), x.at(p.enc_coef), w->bottleneck_w, w->bottleneck_b, x.at(p.x0), B, L0, Nb, cc, st)) return e;
+  }
+  // Recurrent: num_blocks iterations of one shared UConvBlock
+  for (int blk = 0; blk < c->num_blocks; ++blk) {
+    const float* in = blk == 0 ? x.at(p.x0) : x.at(p.u[(blk - 1) & 1]);
+    if (int e = uconv_block(x, in, x.at(p.u[blk & 1]), blk == c->num_blocks - 1)) return e;
+  }
+  // mask_net (PReLU -> 1x1) -> ReLU -> * encoder output, then decoder + crop
+  GemmArgs g{};
+  g.A = x.at(p.u[(c->num_blocks - 1) & 1]); g.W = w->mask_w; g.bias = w->mask_b; g.D = x.at(p.masked);
+  g.B = B; g.L = L0; g.N = c->num_sources * Nb; g.K = cc; g.epi = EPI_MASK; g.a_slope = w->mask_prelu;
+  g.enc = x.at(p.enc); g.Nb = Nb;
+  if (int e = launch_gemm_simt(g, st)) return e;
+  return launch_decoder(x.at(p.masked), w->dec_w, est, B, L0, Nb, c->num_sources, K, S, T, st);
+}
+
+}  // namespace td
+
+// ============================================================================= C ABI
+using namespace td;
+
+extern "C" {
+
+int tdanet_abi_version(void) { return TDANET_ABI_VERSION; }
+
+int tdanet_abi_sizes(size_t* config_bytes, size_t* weights_bytes) {
+  if (config_bytes) *config_bytes = sizeof(tdanet_config_t);
+  if (weights_bytes) *weights_bytes = sizeof(tdanet_weights_t);
+  return 0;
+}
+
+const char* tdanet_last_error(void) { return g_err; }
+
+uint64_t tdanet_launch_count(void) { return g_launches.load(); }
+
+int tdanet_device_supported(int dev) {
+  cudaDeviceProp prop;
+  TD_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(TDANET_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+  return 0;
+}
+
+int tdanet_workspace_bytes(const tdanet_config_t* cfg, int batch, int n_samples, size_t* bytes) {
+  Plan p;
+  if (int e = make_plan(cfg, batch, n_samples, p)) return e;
+  TD_REQUIRE(bytes != nullptr, "bytes is NULL");
+  *bytes = p.bytes;
+  return 0;
+}
+
+int tdanet_latent_lengths(const tdanet_config_t* cfg, int n_samples, int32_t* lengths, int32_t* padded_len, int32_t* rest) {
+  Plan p;
+  if (int e = make_plan(cfg, 1, n_samples, p)) return e;
+  if (lengths) for (int k = 0; k < cfg->depth; ++k) lengths[k] = p.L[k];
+  if (padded_len) *padded_len = p.Tp;
+  if (rest) *rest = p.rest;
+  return 0;
+}
+
+int tdanet_workspace_tensor(const tdanet_config_t* cfg, int batch, int n_samples, const char* name,
+                            size_t* byte_offset, int64_t dims[3]) {
+  Plan p;
+  if (int e = make_plan(cfg, batch, n_samples, p)) return e;
+  TD_REQUIRE(name != nullptr, "name is NULL");
+  for (auto it = p.named.rbegin(); it != p.named.rend(); ++it)
+    if (it->name == name) {
+      if (byte_offset) *byte_offset = it->off;
+      if (dims) { dims[0] = it->dims[0]; dims[1] = it->dims[1]; dims[2] = it->dims[2]; }
+      return 0;
+    }
+  return fail(TDANET_EINVAL, "unknown workspace tensor '%s'", name);
+}
+
+int tdanet_forward(const tdanet_config_t* cfg, const tdanet_weights_t* w, const float* wav, int batch,
+                   int n_samples, float* est, void* workspace, size_t workspace_bytes, tdanet_stream_t stream) {
+  return forward(cfg, w, wav, batch, n_samples, est, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t tdanet_gemm_workspace_bytes(int N, int K) { return ((size_t)N * K * sizeof(float) + 255) / 256 * 256; }
+
+int tdanet_gemm(int gemm_mode, const float* A, const float* W, const float* bias, float* D, int batch,
+                int rows_per_item, int N, int K, double* stats, void* workspace, size_t workspace_bytes,
+                tdanet_stream_t stream) {
+  TD_REQUIRE(A && W && D, "NULL argument");
+  GemmArgs g{};
+  g.A = A; g.W = W; g.bias = bias; g.D = D; g.B = batch; g.L = rows_per_item; g.N = N; g.K = K;
+  g.stats = stats; g.epi = EPI_BIAS;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gemm_mode == TDANET_GEMM_FP32) return launch_gemm_simt(g, st);
+  TD_REQUIRE(gemm_mode == TDANET_GEMM_TF32 || gemm_mode == TDANET_GEMM_TF32X3, "gemm_mode %d", gemm_mode);
+  if (workspace_bytes < tdanet_gemm_workspace_bytes(N, K))
+    return fail(TDANET_ENOSPACE, "gemm workspace has %zu bytes, need %zu", workspace_bytes, tdanet_gemm_workspace_bytes(N, K));
+  if (int e = launch_tf32_prepare(W, (float*)workspace, (size_t)N * K, gemm_mode, st)) return e;
+  g.W_aux = (const float*)workspace;
+  return launch_gemm_tc(g, gemm_mode, st);
+}
+
+size_t tdanet_pit_loss_scratch_bytes(int batch, int n_src) {
+  (void)n_src;
+  return pit_scratch_floats(batch) * sizeof(float);
+}
+
+int tdanet_pit_loss(const float* est, const float* tgt, int batch, int n_src, int n_samples, int sdr_type,
+                    int threshold_byloss, float* loss, float* pw, int32_t* perm, float* grad_est,
+                    void* scratch, size_t scratch_bytes, tdanet_stream_t stream) {
+  TD_REQUIRE(est && tgt && loss && scratch, "NULL argument");
+  if (scratch_bytes < tdanet_pit_loss_scratch_bytes(batch, n_src))
+    return fail(TDANET_ENOSPACE, "pit_loss scratch has %zu bytes, need %zu", scratch_bytes, tdanet_pit_loss_scratch_bytes(batch, n_src));
+  return launch_pit_loss(est, tgt, batch, n_src, n_samples, sdr_type, threshold_byloss, loss, pw, perm,
+                         grad_est, scratch, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// Waveform front end and back end: pad_input + encoder Conv1d (+GlobLN statistics), bottleneck,
+// decoder ConvTranspose1d + crop.
+//
+// Reference: TDANet_best.py:465-479 (pad_input), :430-438/:497 (encoder), :441-444/:502-503 (ln,
+// bottleneck), :453-461/:511-518 (decoder + crop); TDANet_mult_tes.py:317-342 (ConvEncoder).
+#include "kernels.h"
+
+namespace td {
+
+// ----------------------------------------------------------------------------- encoder
+// out[b, t, n] = sum_j w_k[n', j] * xp[t*S + j - ks_k/2], xp = zero-padded input of pad_input.
+// The padding is never materialised: xp[p] = wav[p - front_pad] inside [0, T), else 0.
+__global__ void __launch_bounds__(256) encoder_kernel(EncArgs a, int rows_per_cta, int ksmax) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, a.L0 - t0);
+  const int span = (rows_per_cta - 1) * a.S + ksmax;
+  float* xs = sm;         // [span]
+  float* ws = sm + span;  // per conv: [ch_per_conv][ks_k + 1]
+  const int wstart = t0 * a.S - ksmax / 2;
+  const float* wav = a.wav + (size_t)b * a.T;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const int p = wstart + i;
+    const int q = p - a.front_pad;
+    xs[i] = (p >= 0 && p < a.Tp && q >= 0 && q < a.T) ? __ldg(wav + q) : 0.f;
+  }
+  int woff[TDANET_MAX_ENC];
+  {
+    int off = 0;
+    for (int k = 0; k < a.nconv; ++k) {
+      woff[k] = off;
+      const int ks = a.ks[k];
+      for (int i = threadIdx.x; i < a.ch_per_conv * ks; i += blockDim.x)
+        ws[off + (i / ks) * (ks + 1) + (i % ks)] = __ldg(a.w[k] + i);
+      off += a.ch_per_conv * (ks + 1);
+    }
+  }
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  float* out = a.out + ((size_t)b * a.L0 + t0) * a.Nb;
+  for (int idx = threadIdx.x; idx < rows * a.Nb; idx += blockDim.x) {
+    const int r = idx / a.Nb, n = idx % a.Nb;
+    const int k = n / a.ch_per_conv, nn = n % a.ch_per_conv;
+    const int ks = a.ks[k];
+    const float* wr = ws + woff[k] + nn * (ks + 1);
+    const float* xr = xs + r * a.S + (ksmax - ks) / 2;
+    float acc = 0.f;
+    for (int j = 0; j < ks; ++j) acc = fmaf(wr[j], xr[j], acc);
+    out[idx] = acc;
+    s1 += acc;
+    s2 = fmaf(acc, acc, s2);
+  }
+  __shared__ double red[64];
+  double d1 = s1, d2 = s2;
+  block_sum2(d1, d2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(a.stats + 2 * b, d1);
+    atomicAdd(a.stats + 2 * b + 1, d2);
+  }
+}
+
+int launch_encoder(const EncArgs& a, cudaStream_t st) {
+  int ksmax = 0, wfloats = 0;
+  for (int k = 0; k < a.nconv; ++k) {
+    TD_REQUIRE(a.ks[k] % 2 == 0, "encoder: window %d must be even", a.ks[k]);
+    ksmax = a.ks[k] > ksmax ? a.ks[k] : ksmax;
+    wfloats += a.ch_per_conv * (a.ks[k] + 1);
+  }
+  const int rows = 32;
+  const size_t smem = ((size_t)(rows - 1) * a.S + ksmax + wfloats) * sizeof(float);
+  TD_REQUIRE(smem <= 200 * 1024, "encoder: %zu bytes of shared memory needed", smem);
+  if (smem > 48 * 1024)
+    TD_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(a.L0, rows), 1, a.B);
+  TD_LAUNCH(encoder_kernel, grid, 256, smem, st, a, rows, ksmax);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- bottleneck
+// x0 = Conv1d(Nb -> c, k=1)(GlobLN(enc)); the normalisation is folded into the weights per item.
+__global__ void __launch_bounds__(256) bottleneck_kernel(const float* __restrict__ enc,
+                                                         const float* __restrict__ coef,
+                                                         const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         float* __restrict__ out, int L0, int Nb, int c,
+                                                         int rows_per_cta) {
+  extern __shared__ float sm[];
+  float* wf = sm;                   // [c][Nb+1]  folded weights (+1: odd stride, no bank conflicts)
+  float* bf = wf + c * (Nb + 1);    // [c]
+  float* es = bf + c;               // [rows][Nb]
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, L0 - t0);
+  const float* sc = coef + (size_t)b * 2 * Nb;
+  const float* sh = sc + Nb;
+  for (int i = threadIdx.x; i < c * Nb; i += blockDim.x) {
+    const int o = i / Nb, n = i % Nb;
+    wf[o * (Nb + 1) + n] = __ldg(w + i) * __ldg(sc + n);
+  }
+  for (int o = threadIdx.x; o < c; o += blockDim.x) {
+    float acc = __ldg(bias + o);
+    for (int n = 0; n < Nb; ++n) acc = fmaf(__ldg(w + o * Nb + n), __ldg(sh + n), acc);
+    bf[o] = acc;
+  }
+  const float* e = enc + ((size_t)b * L0 + t0) * Nb;
+  for (int i = threadIdx.x; i < rows * Nb; i += blockDim.x) es[i] = __ldg(e + i);
+  __syncthreads();
+  float* op = out + ((size_t)b * L0 + t0) * c;
+  for (int idx = threadIdx.x; idx < rows * c; idx += blockDim.x) {
+    const int r = idx / c, o = idx % c;
+    const float* wr = wf + o * (Nb + 1);
+    const float* er = es + r * Nb;
+    float acc = bf[o];
+    for (int n = 0; n < Nb; ++n) acc = fmaf(wr[n], er[n], acc);
+    op[idx] = acc;
+  }
+}
+
+int launch_bottleneck(const float* enc, const float* coef, const float* w, const float* bias,
+                      float* out, int B, int L0, int Nb, int c, cudaStream_t st) {
+  const int rows = 32;
+  const size_t smem = ((size_t)c * (Nb + 1) + c + (size_t)rows * Nb) * sizeof(float);
+  TD_REQUIRE(smem <= 200 * 1024, "bottleneck: %zu bytes of shared memory needed", smem);
+  if (smem > 48 * 1024)
+    TD_CUDA(cudaFuncSetAttribute(bottleneck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(L0, rows), 1, B);
+  TD_LAUNCH(bottleneck_kernel, grid, 256, smem, st, enc, coef, w, bias, out, L0, Nb, c, rows);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- decoder
+// ConvTranspose1d(n_src*Nb -> n_src, k=K, stride=S=K/4, padding=K/2, no bias) followed by the crop
+// [K-S : -(rest+K-S)].  With n the index in the un-cropped output and u = (n + K/2)/S,
+// r = (n + K/2) % S:    out[o, n] = sum_{m<4} sum_ci M[u-m, ci] * W[ci, o, r + m*S].
+// A thread owns one phase r and four consecutive hops for every source, so each weight load feeds
+// four outputs and each frame value feeds up to four taps.
+template <int NS>
+__global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ masked,
+                                                      const float* __restrict__ w,
+                                                      float* __restrict__ est, int L0, int CI, int K,
+                                                      int S, int T, int hops_per_cta) {
+  extern __shared__ float ms[];  // [hops_per_cta + 3][CI]
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.x * hops_per_cta;  // first hop (n / S) of this CTA
+  const int f0 = h0 + 2 - 3;                 // first frame needed: u - 3 with u = h0 + 2
+  const int nfr = hops_per_cta + 3;
+  for (int i = threadIdx.x; i < nfr * CI; i += blockDim.x) {
+    const int f = f0 + i / CI;
+    ms[i] = (f >= 0 && f < L0) ? __ldg(masked + ((size_t)b * L0 + f) * CI + i % CI) : 0.f;
+  }
+  __syncthreads();
+  const int r = threadIdx.x % S;
+  const int qg = threadIdx.x / S;
+  if (qg * 4 >= hops_per_cta) return;
+  float acc[NS][4];
+#pragma unroll
+  for (int o = 0; o < NS; ++o)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[o][q] = 0.f;
+  // frames used by this thread: local index qg*4 + {0..6}  (u_q - m = h0 + qg*4 + q + 2 - m)
+  const float* mrow = ms + (size_t)(qg * 4) * CI;
+  for (int ci = 0; ci < CI; ++ci) {
+    float fr[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) fr[i] = mrow[i * CI + ci];
+#pragma unroll
+    for (int o = 0; o < NS; ++o) {
+      const float* wp = w + ((size_t)ci * NS + o) * K + r;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float wv = __ldg(wp + m * S);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[o][q] = fmaf(fr[q + 3 - m], wv, acc[o][q]);
+      }
+    }
+  }
+  const int crop = K - S;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int n = (h0 + qg * 4 + q) * S + r - crop;
+    if (n >= 0 && n < T) {
+#pragma unroll
+      for (int o = 0; o < NS; ++o) est[((size_t)b * NS + o) * T + n] = acc[o][q];
+    }
+  }
+}
+
+int launch_decoder(const float* masked, const float* w, float* est, int B, int L0, int Nb, int n_src,
+                   int K, int S, int T, cudaStream_t st) {
+  TD_REQUIRE(K == 4 * S, "decoder: window %d must be 4 hops of %d", K, S);
+  TD_REQUIRE(S <= 64, "decoder: hop %d too large", S);
+  const int CI = n_src * Nb;
+  int hops = (256 / S) * 4;  // every thread of a 256-thread CTA owns 4 hops of one phase
+  if (hops > 64) hops = 64;
+  const int threads = S * (hops / 4);
+  const size_t smem = (size_t)(hops + 3) * CI * sizeof(float);
+  const int total_hops = cdiv(K - S + T, S);
+  dim3 grid(cdiv(total_hops, hops), 1, B);
+  if (n_src == 2) {
+    if (smem > 48 * 1024)
+      TD_CUDA(cudaFuncSetAttribute(decoder_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TD_LAUNCH((decoder_kernel<2>), grid, threads, smem, st, masked, w, est, L0, CI, K, S, T, hops);
+  } else if (n_src == 3) {
+    if (smem > 48 * 1024)
+      TD_CUDA(cudaFuncSetAttribute(decoder_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TD_LAUNCH((decoder_kernel<3>), grid, threads, smem, st, masked, w, est, L0, CI, K, S, T, hops);
+  } else {
+    return fail(TDANET_EUNSUPPORTED, "decoder: num_sources=%d (2 or 3 supported)", n_src);
+  }
+  return 0;
+}
+
+}  // namespace td

@@ -1,0 +1,413 @@
+// tcgen05 / TMEM / TMA GEMM (kind::tf32) for the 1x1 convolutions and attention / FFN projections:
+//   D[b, r, n] = sum_k A[b, r, k] * W[n, k]  (+ epilogue shared with gemm_simt.cu)
+//
+// Both operands are K-major (activations are channels-last, Conv1d / Linear weights are [N, K]), so
+// TMA loads 128-byte-swizzled [rows x 32 fp32] boxes that tcgen05.mma consumes in place; the tensor
+// core reads fp32 bits as TF32.  Persistent, warp-specialised CTA (one per SM):
+//   warp 0      TMA producer        (one elected lane)
+//   warp 1      TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> bias / residual / statistics
+//               -> st.global.  The accumulator is double-buffered in TMEM so the epilogue of tile i
+//               overlaps the loads and MMAs of tile i+1.
+// A-tiles are 128 rows of ONE batch item (3-D tensor map, rows past the item are zero-filled by TMA)
+// so that the GlobLN statistics of the epilogue never straddle items.
+//
+// Accuracy modes: TDANET_GEMM_TF32  : W pre-rounded to TF32 (RN), one MMA pass.
+//                 TDANET_GEMM_TF32X3: W used as is (tensor core truncates = W_hi) plus a second pass
+//                                     over W_lo = W - trunc(W); A is taken as stored in both.
+#include "kernels.h"
+#include "gemm_epilogue.cuh"
+#include <cuda.h>
+
+namespace td {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // fp32 elements = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must fault (and be reported by the next CUDA call), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, M=128, K=8 (tf32)
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane i of the quarter)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major: 1) |
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// sm_100 UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) /* D = F32 */ | (2u << 7) /* A = TF32 */ | (2u << 10) /* B = TF32 */ |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+  int BN;        // columns per tile (multiple of 16, <= 256)
+  int stages;    // smem pipeline depth
+  int tiles_m;   // row tiles per batch item
+  int tiles_n;
+  int total;     // tiles in the launch
+  int nsplit;    // 1: W only, 2: W then W_lo
+  uint32_t tmem_cols;
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+               const __grid_constant__ CUtensorMap mapW2, GemmArgs a, TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages] x { A 16 KB | W BN*128 B | (W_lo) } then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = TC_BM * TC_BK * 4;
+  const uint32_t w_bytes = (uint32_t)p.BN * TC_BK * 4;
+  const uint32_t stage_bytes = a_bytes + w_bytes * p.nsplit;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* acc_full = bars + 2 * p.stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = a.K / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full + s, 1);
+      mbar_init(acc_empty + s, 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
+        const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
+        const int b = mt / p.tiles_m, r0 = (mt % p.tiles_m) * TC_BM, n0 = nt * p.BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(full + stage, stage_bytes);
+          tma_load_3d(sa, &mapA, full + stage, kb * TC_BK, r0, b);
+          tma_load_2d(sa + a_bytes, &mapW, full + stage, kb * TC_BK, n0);
+          if (p.nsplit == 2) tma_load_2d(sa + a_bytes + w_bytes, &mapW2, full + stage, kb * TC_BK, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
+      mbar_wait(acc_empty + acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full + stage, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t da = make_smem_desc(sa), dw = make_smem_desc(sa + a_bytes), dw2 = make_smem_desc(sa + a_bytes + w_bytes);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            tc_mma_tf32(tmem_d, da + 2 * k, dw + 2 * k, p.idesc, (kb | k) != 0);
+            if (p.nsplit == 2) tc_mma_tf32(tmem_d, da + 2 * k, dw2 + 2 * k, p.idesc, 1);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) tc_commit(empty + stage);  // frees the smem stage once the MMAs have read it
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) tc_commit(acc_full + acc);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================================================================== epilogue (4 warps)
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32) are visible to this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
+      const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
+      const int b = mt / p.tiles_m, r0 = (mt % p.tiles_m) * TC_BM, n0 = nt * p.BN;
+      const int r = r0 + quarter * 32 + lane;
+      const bool row_ok = r < a.L;
+      Epilogue ep(a, b);
+      float s1 = 0.f, s2 = 0.f;
+      mbar_wait(acc_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        float v[32];
+        const int ncol = min(32, p.BN - c0);  // BN is a multiple of 16
+        if (ncol == 32) tc_ld32(taddr + c0, v); else tc_ld16(taddr + c0, v);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncol) {
+              float q[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+              ep.apply4(r, n0 + c0 + j, q, s1, s2);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + acc);
+      if (a.stats) {
+        const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
+        if (lane == 0) {
+          atomicAdd(a.stats + 2 * b, d1);
+          atomicAdd(a.stats + 2 * b + 1, d2);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const float* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(TDANET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[3], gstride[2];
+  cuuint32_t bdim[3], estr[3] = {1, 1, 1};
+  uint64_t stride = sizeof(float);
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    stride *= dims[i];
+    if (i < rank - 1) gstride[i] = stride;
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, gdim, gstride, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TDANET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+bool gemm_tc_supported(const GemmArgs& a) {
+  if (a.K % TC_BK != 0 || a.N % 16 != 0 || a.a_slope != nullptr) return false;
+  if (a.N > 128 && a.N % 128 != 0) return false;
+  if (((uintptr_t)a.A & 15) || ((uintptr_t)a.W & 15)) return false;
+  return true;
+}
+
+int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
+  // Shapes the tensor-core tiling cannot express (K not a multiple of 32, N not a multiple of 16,
+  // an A-operand transform) run on the CUDA-core kernel of this library.
+  if (!gemm_tc_supported(a)) return launch_gemm_simt(a, st);
+  TD_REQUIRE(a.W_aux != nullptr, "gemm_tc: prepared weights missing");
+  static int num_sms = 0;
+  static bool attr_set = false;
+  if (!num_sms) {
+    int dev = 0;
+    TD_CUDA(cudaGetDevice(&dev));
+    TD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  TcParams p{};
+  p.nsplit = mode == TDANET_GEMM_TF32X3 ? 2 : 1;
+  p.BN = a.N % 256 == 0 && p.nsplit == 1 ? 256 : (a.N >= 128 ? 128 : a.N);
+  p.tiles_m = cdiv(a.L, TC_BM);
+  p.tiles_n = a.N / p.BN;
+  p.total = a.B * p.tiles_m * p.tiles_n;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * p.BN)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.idesc = make_idesc(TC_BM, p.BN);
+  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 4 + (size_t)p.BN * TC_BK * 4 * p.nsplit;
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return fail(TDANET_EUNSUPPORTED, "gemm_tc: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
+
+  CUtensorMap mapA, mapW, mapW2;
+  const uint64_t dA[3] = {(uint64_t)a.K, (uint64_t)a.L, (uint64_t)a.B};
+  const uint32_t bA[3] = {TC_BK, TC_BM, 1};
+  const uint64_t dW[2] = {(uint64_t)a.K, (uint64_t)a.N};
+  const uint32_t bW[2] = {TC_BK, (uint32_t)p.BN};
+  if (int e = encode_map(&mapA, a.A, 3, dA, bA)) return e;
+  // TF32: the rounded copy is the operand.  TF32X3: W itself (hi) and the prepared remainder (lo).
+  if (int e = encode_map(&mapW, p.nsplit == 2 ? a.W : a.W_aux, 2, dW, bW)) return e;
+  if (int e = encode_map(&mapW2, a.W_aux, 2, dW, bW)) return e;
+
+  if (!attr_set) {
+    TD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  const int grid = p.total < num_sms ? p.total : num_sms;
+  TD_LAUNCH(gemm_tc_kernel, grid, TC_THREADS, smem, st, mapA, mapW, mapW2, a, p);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- weight preparation
+__global__ void tf32_prepare_kernel(const float* __restrict__ w, float* __restrict__ aux, size_t n, int mode) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = w[i];
+  if (mode == TDANET_GEMM_TF32) {
+    aux[i] = tf32_rna(x);
+  } else {
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // what the tensor core sees
+    aux[i] = x - hi;
+  }
+}
+
+int launch_tf32_prepare(const float* w, float* aux, size_t n, int mode, cudaStream_t st) {
+  TD_LAUNCH(tf32_prepare_kernel, (unsigned)((n + 255) / 256), 256, 0, st, w, aux, n, mode);
+  return 0;
+}
+
+}  // namespace td

@@ -1,0 +1,167 @@
+// Internal launcher interface between the engine (engine.cu) and the kernel files.
+// All tensors are fp32 device pointers, activations channels-last [B, L, C].
+#pragma once
+#include "common.cuh"
+
+namespace td {
+
+// ------------------------------------------------------------------ sources (normalise-on-load)
+// How a consumer kernel reads one row of a [B, L, C] activation.
+enum SrcKind {
+  SRC_PLAIN = 0,         // x
+  SRC_AFFINE = 1,        // x*scale + shift                    coef planes [B,2,C]
+  SRC_AFFINE_PRELU = 2,  // prelu(x*scale + shift, *slope)
+  SRC_INJECT_GATE = 3,   // (al*x+bl) * sigmoid(aa*g[j]+ba) + (ae*g[j]+be), j = nearest(t)  coef [B,6,C]
+  SRC_INJECT_ADD = 4     // (a*x+b) + g[j]                                                  coef [B,2,C]
+};
+
+struct SrcDesc {
+  const float* x;      // [B, L, C]
+  int L;
+  const float* coef;   // [B, planes, C] or nullptr
+  const float* slope;  // PReLU slope (1 element) or nullptr
+  const float* g;      // injected global feature [B, Lg, C] or nullptr
+  int Lg;
+  float gscale;        // fl32(Lg / L)
+};
+
+// ------------------------------------------------------------------ dwconv.cu
+// Depthwise k=5 pad=2 conv over time (stride 1 or 2), NW weight sets sharing one input.
+//   w[i]: [C,1,5]  bias[i]: [C] or null
+//   out : [B, Lout, C] (only NW==1) or null;  relu applied to the stored value if `relu`
+//   stats: [B, NW, 2, C] per-channel sum / sum of squares of the (pre-relu) conv output, or null
+struct DwArgs {
+  SrcDesc src;
+  int kind;  // SrcKind
+  int B, C, Lout, stride, nw;
+  const float* w[2];
+  const float* bias[2];
+  float* out;
+  float* stats;
+  int relu;
+  int round_out;  // store TF32-rounded values (output only feeds a tensor-core GEMM)
+};
+int launch_dw5(const DwArgs& a, cudaStream_t st);
+
+// Generic depthwise conv (any odd k, any stride), plain/affine source, writes out, no stats.
+int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int ks, int stride,
+                      const float* w, const float* bias, float* out, int round_out, cudaStream_t st);
+
+// LA combine (TDANet_best.py:277-292 with the three GlobLN folded into coef tables):
+//   out[t] = (cL.s*dw_l(xl)[t] + cL.h) * sigmoid(cA.s*dw_a(xg)[j] + cA.h) + (cE.s*dw_e(xg)[j] + cE.h)
+//   j = nearest(t; Lg -> Ll)
+struct LaArgs {
+  SrcDesc loc, glo;
+  int lkind, gkind;
+  int B, C;
+  const float *wl, *wa, *we;  // [C,1,5]
+  const float* coef;          // [B, 6, C] : sL hL sA hA sE hE
+  float* out;                 // [B, Ll, C]
+  float scale;                // fl32(Lg / Ll)
+  int round_out;
+};
+int launch_la_combine(const LaArgs& a, cudaStream_t st);
+
+// ------------------------------------------------------------------ coef.cu
+// GlobLN coefficients from per-item (sum, sumsq) in double: scale=gamma*r, shift=beta-gamma*mu*r
+int launch_coef_item(const double* stats, double count, const float* gamma, const float* beta,
+                     float* coef, int B, int C, cudaStream_t st);
+// ... from per-channel stats [B, 2, C] (float), `rows` rows per channel
+int launch_coef_chan(const float* chstats, size_t item_stride, int rows, const float* gamma,
+                     const float* beta, float* coef, int B, int C, cudaStream_t st);
+// LA (k=5) coefficients: three per-channel stat sets -> [B,6,C]
+//   stats_l: [B,1,2,C] over Ll rows; stats_g: [B,2,2,C] (global_act, global_embedding) over Lg rows
+int launch_coef_la(const float* stats_l, int Ll, const float* stats_g, int Lg, const tdanet_la_t* la,
+                   float* coef, int B, int C, cudaStream_t st);
+// BEST loc_glo_fus (k=1 LA) closed form -> SRC_INJECT_GATE table [B,6,C] for one scale
+//   spp_stats: per-channel stats [B,2,C] of the raw spp_dw[k] output (rows Lk), spp: its GlobLN
+//   g_stats:   per-channel stats [B,2,C] of global_f (rows Lg)
+int launch_coef_inject_gate(const float* spp_stats, size_t spp_item_stride, int Lk,
+                            const tdanet_convnorm_t* spp, const float* g_stats, int Lg,
+                            const tdanet_la_t* la, float* coef, int B, int C, cudaStream_t st);
+
+// ------------------------------------------------------------------ bottom.cu
+// sum_k adaptive_avg_pool(affine_k(x_k)) -> out [B, Lb, C]
+struct PoolArgs {
+  int n;
+  const float* x[TDANET_MAX_DEPTH];
+  const float* coef[TDANET_MAX_DEPTH];  // [B,2,C]
+  int L[TDANET_MAX_DEPTH];
+  int B, C, Lb;
+  float* out;
+};
+int launch_pool_sum(const PoolArgs& a, cudaStream_t st);
+// fork: out = sum_k affine_k(x_k), all [B, Lb, C]
+int launch_affine_sum(const PoolArgs& a, cudaStream_t st);
+// y = LayerNorm_C(x)*w + b + pe[t]      x,y [B, L, C]
+int launch_ln_pe(const float* x, const float* w, const float* b, const float* pe, float* y, int B,
+                 int L, int C, int round_out, cudaStream_t st);
+// multi-head attention core on packed qkv [B*L, 3C]; ctx [B*L, C]
+//   time_axis=0: sequence = the `group` batch items sharing a time index; 1: sequence = time
+int launch_attention(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
+                     int time_axis, int round_out, cudaStream_t st);
+// y = resid + LayerNorm_C(post)*w + b ; post = 2*a (doubled=1) or xin + a (doubled=0)
+int launch_ln_residual(const float* a, const float* xin, const float* resid, const float* w,
+                       const float* b, float* y, int doubled, int B, int L, int C, cudaStream_t st);
+// y = resid + (x*scale + shift) with coef [B,2,C]; optional per-channel stats of y -> [B,2,C]
+int launch_affine_residual(const float* x, const float* coef, const float* resid, float* y,
+                           float* chstats, int B, int L, int C, cudaStream_t st);
+// y = x*scale + shift
+int launch_affine(const float* x, const float* coef, float* y, int B, int L, int C, cudaStream_t st);
+
+// ------------------------------------------------------------------ frontend.cu
+struct EncArgs {
+  const float* wav;  // [B, T]
+  int B, T;
+  int K, S, front_pad, Tp;  // Tp: length after pad_input
+  int nconv;                // 1 or MULTRES kernels
+  const float* w[TDANET_MAX_ENC];
+  int ks[TDANET_MAX_ENC];
+  int ch_per_conv, Nb, L0;
+  float* out;     // [B, L0, Nb]
+  double* stats;  // [B,2]
+};
+int launch_encoder(const EncArgs& a, cudaStream_t st);
+// x0[b,t,:] = Wb . (enc*scale+shift) + bb     enc [B,L0,Nb], coef [B,2,Nb], out [B,L0,c]
+int launch_bottleneck(const float* enc, const float* coef, const float* w, const float* bias,
+                      float* out, int B, int L0, int Nb, int c, cudaStream_t st);
+// decoder ConvTranspose1d + crop: masked [B, L0, n_src*Nb] -> est [B, n_src, T]
+int launch_decoder(const float* masked, const float* w, float* est, int B, int L0, int Nb,
+                   int n_src, int K, int S, int T, cudaStream_t st);
+
+// ------------------------------------------------------------------ gemm_simt.cu / gemm_tc.cu
+enum GemmEpi {
+  EPI_BIAS = 0,       // D = acc + bias
+  EPI_RESIDUAL = 1,   // y = acc + bias + resid ; D = last ? y : prelu(cw*(mix+y)+cb, *cslope)
+  EPI_MASK = 2        // D = relu(acc + bias) * enc[b, r, n mod Nb]
+};
+struct GemmArgs {
+  const float* A;  // [B, L, K]
+  const float* W;  // [N, K]
+  const float* bias;
+  float* D;        // [B, L, N]
+  int B, L, N, K;
+  double* stats;   // [B,2] or null (sum, sumsq of D over valid rows)
+  int epi;
+  // A-operand transform: prelu(A, *a_slope) if non-null (mask_net.0)
+  const float* a_slope;
+  // EPI_RESIDUAL
+  const float *resid, *mix, *cw, *cb, *cslope;
+  int last;
+  // EPI_MASK
+  const float* enc;
+  int Nb;
+  // tensor-core path: weight split prepared by prepare_tf32_weights (lo part / rounded copy)
+  const float* W_aux;
+};
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
+int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st);
+// aux[i] = mode==TF32 ? rna_tf32(w[i]) : w[i] - trunc_tf32(w[i])
+int launch_tf32_prepare(const float* w, float* aux, size_t n, int mode, cudaStream_t st);
+
+// ------------------------------------------------------------------ loss.cu
+int launch_pit_loss(const float* est, const float* tgt, int B, int n_src, int T, int sdr_type,
+                    int threshold, float* loss, float* pw, int32_t* perm, float* grad,
+                    void* scratch, cudaStream_t st);
+
+}  // namespace td

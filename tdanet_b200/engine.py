@@ -1,0 +1,246 @@
+"""Host-side driver of the C-ABI library: packs a module's parameters into `tdanet_weights_t`,
+owns the workspace, enqueues `tdanet_forward` on the current CUDA stream, and (optionally) replays
+the whole forward as one CUDA graph.
+
+PyTorch is used for device memory and streams only; every kernel is in csrc/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Config, Weights, check
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+        raise _lib.TdanetError(
+            f"parameter must be a contiguous fp32 CUDA tensor (got {t.dtype}, {t.device}); "
+            "move the model with .cuda() - there is no CPU path")
+    return t.data_ptr()
+
+
+class SeparationEngine:
+    """One model configuration bound to the CUDA library.
+
+    variant        "best" | "fork" | "multres" (TDANetBest / TDANet / TDANetMultRes)
+    gemm_mode      "fp32" (CUDA cores, exact parity) | "tf32" (tcgen05) | "tf32x3" (tcgen05, split weights)
+    """
+
+    def __init__(self, variant: str, out_channels: int, in_channels: int, num_blocks: int, depth: int,
+                 enc_kernel: int, n_basis: int, num_sources: int, enc_convs: int = 1, n_head: int = 8,
+                 gemm_mode: str = "tf32"):
+        self.variant = variant
+        self.cfg = Config(
+            variant=_lib.VARIANTS[variant], out_channels=out_channels, in_channels=in_channels,
+            num_blocks=num_blocks, depth=depth, enc_kernel=enc_kernel, enc_stride=enc_kernel // 4,
+            n_basis=n_basis, num_sources=num_sources, enc_convs=enc_convs, n_head=n_head,
+            gemm_mode=_lib.GEMM_MODES[gemm_mode], attn_group=0)
+        self._ws: Dict[torch.device, torch.Tensor] = {}
+        self._graphs: Dict[Tuple, Tuple] = {}
+        self._keep = None  # tensors referenced by the packed weight struct
+
+    # ------------------------------------------------------------------ configuration
+    @property
+    def gemm_mode(self) -> str:
+        return {v: k for k, v in _lib.GEMM_MODES.items()}[self.cfg.gemm_mode]
+
+    @gemm_mode.setter
+    def gemm_mode(self, mode: str) -> None:
+        self.cfg.gemm_mode = _lib.GEMM_MODES[mode]
+        self._graphs.clear()
+
+    def latent_lengths(self, n_samples: int):
+        lens = (C.c_int32 * _lib.MAX_DEPTH)()
+        tp, rest = C.c_int32(), C.c_int32()
+        check(_lib.load().tdanet_latent_lengths(C.byref(self.cfg), n_samples, C.byref(lens), C.byref(tp), C.byref(rest)))
+        return list(lens[: self.cfg.depth]), tp.value, rest.value
+
+    # ------------------------------------------------------------------ weights
+    def pack(self, sd: Dict[str, torch.Tensor]) -> Weights:
+        """state_dict (reference key names) -> tdanet_weights_t of device pointers."""
+        v, d = self.variant, self.cfg.depth
+        gk, bk = ("gamma", "beta") if v == "best" else ("weight", "bias")
+        w = Weights()
+        keep = []
+
+        def P(key, optional=False):
+            t = sd.get(key)
+            if t is None:
+                if optional:
+                    return None
+                raise KeyError(f"state_dict has no '{key}'")
+            keep.append(t)
+            return _ptr(t)
+
+        def convnorm(dst, prefix, bias):
+            dst.w = P(f"{prefix}.conv.weight")
+            dst.b = P(f"{prefix}.conv.bias") if bias else None
+            dst.gamma = P(f"{prefix}.norm.{gk}")
+            dst.beta = P(f"{prefix}.norm.{bk}")
+
+        def la(dst, prefix):
+            convnorm(dst.local_embedding, f"{prefix}.local_embedding", False)
+            convnorm(dst.global_embedding, f"{prefix}.global_embedding", False)
+            convnorm(dst.global_act, f"{prefix}.global_act", False)
+
+        if v == "multres":
+            for k in range(self.cfg.enc_convs):
+                w.enc_w[k] = P(f"encoder.conv_list.{k}.weight")
+        else:
+            w.enc_w[0] = P("encoder.weight")
+            w.bottleneck_w, w.bottleneck_b = P("bottleneck.weight"), P("bottleneck.bias")
+        w.ln_gamma, w.ln_beta = P(f"ln.{gk}"), P(f"ln.{bk}")
+        u = "sm.unet"
+        convnorm(w.proj, f"{u}.proj_1x1", True)
+        w.proj_prelu = P(f"{u}.proj_1x1.act.weight")
+        for k in range(d):
+            convnorm(w.spp_dw[k], f"{u}.spp_dw.{k}", True)
+            if v == "best":
+                la(w.loc_glo_fus[k], f"{u}.loc_glo_fus.{k}")
+            if v == "fork":
+                q, cp = f"{u}.conv_pool.{k}", w.conv_pool[k]
+                cp.dw_w, cp.dw_b = P(f"{q}.dw_conv.weight"), P(f"{q}.dw_conv.bias")
+                cp.pw_w, cp.pw_b = P(f"{q}.pw_conv.weight"), P(f"{q}.pw_conv.bias")
+                cp.gamma, cp.beta = P(f"{q}.norm.{gk}"), P(f"{q}.norm.{bk}")
+        for i in range(d - 1):
+            la(w.last_layer[i], f"{u}.last_layer.{i}")
+        w.res_w, w.res_b = P(f"{u}.res_conv.weight"), P(f"{u}.res_conv.bias")
+        a = f"{u}.globalatt.attn"
+        pe = sd[f"{a}.pos_enc.pe"]
+        w.pe, w.pe_rows = P(f"{a}.pos_enc.pe"), int(pe.shape[1])
+        w.ln1_w, w.ln1_b = P(f"{a}.attn_in_norm.weight"), P(f"{a}.attn_in_norm.bias")
+        w.in_proj_w, w.in_proj_b = P(f"{a}.attn.in_proj_weight"), P(f"{a}.attn.in_proj_bias")
+        w.out_proj_w, w.out_proj_b = P(f"{a}.attn.out_proj.weight"), P(f"{a}.attn.out_proj.bias")
+        w.ln2_w, w.ln2_b = P(f"{a}.norm.weight"), P(f"{a}.norm.bias")
+        m = f"{u}.globalatt.mlp"
+        convnorm(w.fc1, f"{m}.fc1", False)
+        w.ffn_dw_w, w.ffn_dw_b = P(f"{m}.dwconv.weight"), P(f"{m}.dwconv.bias")
+        convnorm(w.fc2, f"{m}.fc2", False)
+        w.concat_w, w.concat_b = P("sm.concat_block.0.weight"), P("sm.concat_block.0.bias")
+        w.concat_prelu = P("sm.concat_block.1.weight")
+        w.mask_prelu, w.mask_w, w.mask_b = P("mask_net.0.weight"), P("mask_net.1.weight"), P("mask_net.1.bias")
+        w.dec_w = P("decoder.weight")
+        self._keep = keep
+        return w
+
+    # ------------------------------------------------------------------ workspace
+    def workspace_bytes(self, batch: int, n_samples: int) -> int:
+        n = C.c_size_t()
+        check(_lib.load().tdanet_workspace_bytes(C.byref(self.cfg), batch, n_samples, C.byref(n)))
+        return n.value
+
+    def _workspace(self, device, nbytes: int) -> torch.Tensor:
+        ws = self._ws.get(device)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws[device] = ws
+            self._graphs.clear()
+        return ws
+
+    def workspace_tensor(self, name: str, batch: int, n_samples: int, device) -> torch.Tensor:
+        """View of an intermediate of the last forward (channels-last [B, L, C]); for tests."""
+        off, dims = C.c_size_t(), (C.c_int64 * 3)()
+        check(_lib.load().tdanet_workspace_tensor(C.byref(self.cfg), batch, n_samples, name.encode(), C.byref(off), C.byref(dims)))
+        ws = self._ws[torch.device(device)]
+        n = dims[0] * dims[1] * dims[2]
+        return ws[off.value: off.value + 4 * n].view(torch.float32).view(dims[0], dims[1], dims[2])
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, weights: Weights, wav: torch.Tensor, attn_group: int = 0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """wav [B, T] fp32 CUDA contiguous -> est [B, num_sources, T]; enqueued on the current stream."""
+        if not wav.is_cuda:
+            raise _lib.TdanetError("tdanet_b200 runs on CUDA tensors only (no CPU path); got a CPU tensor")
+        if wav.dtype != torch.float32 or wav.ndim != 2:
+            raise _lib.TdanetError(f"wav must be fp32 [B, T], got {wav.dtype} {tuple(wav.shape)}")
+        wav = wav.contiguous()
+        B, T = wav.shape
+        lib = _lib.load()
+        with torch.cuda.device(wav.device):
+            nbytes = self.workspace_bytes(B, T)
+            ws = self._workspace(wav.device, nbytes)
+            if out is None:
+                out = torch.empty(B, self.cfg.num_sources, T, dtype=torch.float32, device=wav.device)
+            self.cfg.attn_group = attn_group
+            stream = torch.cuda.current_stream(wav.device).cuda_stream
+            check(lib.tdanet_forward(C.byref(self.cfg), C.byref(weights), wav.data_ptr(), B, T, out.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def forward_graphed(self, weights: Weights, wav: torch.Tensor, attn_group: int = 0) -> torch.Tensor:
+        """Same as forward() but replays one captured CUDA graph per (B, T, group, weights) key.
+
+        The returned tensor is the graph's static output buffer: it is overwritten by the next call.
+        """
+        B, T = wav.shape
+        key = (wav.device, B, T, attn_group, self.cfg.gemm_mode, C.addressof(weights))
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = torch.empty_like(wav)
+            static_out = torch.empty(B, self.cfg.num_sources, T, dtype=torch.float32, device=wav.device)
+            static_in.copy_(wav)
+            s = torch.cuda.Stream(wav.device)
+            s.wait_stream(torch.cuda.current_stream(wav.device))
+            with torch.cuda.stream(s):   # warm-up outside capture (function attributes, workspace)
+                self.forward(weights, static_in, attn_group, out=static_out)
+            torch.cuda.current_stream(wav.device).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.forward(weights, static_in, attn_group, out=static_out)
+            entry = (g, static_in, static_out, self._ws[wav.device])
+            self._graphs[key] = entry
+        g, static_in, static_out, _ = entry
+        static_in.copy_(wav)
+        g.replay()
+        return static_out
+
+
+# ---------------------------------------------------------------------- standalone ops
+def gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, mode: str = "tf32",
+         with_stats: bool = False):
+    """D[b, r, :] = A[b, r, :] @ W.T (+ bias) through tdanet_gemm; A [B, L, K], W [N, K]."""
+    lib = _lib.load()
+    B, L, K = A.shape
+    N = W.shape[0]
+    D = torch.empty(B, L, N, dtype=torch.float32, device=A.device)
+    stats = torch.zeros(B, 2, dtype=torch.float64, device=A.device) if with_stats else None
+    nws = lib.tdanet_gemm_workspace_bytes(N, K)
+    ws = torch.empty(nws, dtype=torch.uint8, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib.tdanet_gemm(_lib.GEMM_MODES[mode], A.contiguous().data_ptr(), W.contiguous().data_ptr(),
+                              None if bias is None else bias.data_ptr(), D.data_ptr(), B, L, N, K,
+                              None if stats is None else stats.data_ptr(), ws.data_ptr(), nws,
+                              torch.cuda.current_stream(A.device).cuda_stream))
+    return (D, stats) if with_stats else D
+
+
+def pit_loss(est: torch.Tensor, tgt: torch.Tensor, sdr_type: str = "snr", threshold_byloss: bool = True,
+             want_grad: bool = True):
+    """Fused PIT loss forward (+ d loss / d est).  Returns (loss[1], pw[B,n,n], perm[B,n] int32, grad | None)."""
+    if not (est.is_cuda and tgt.is_cuda):
+        raise _lib.TdanetError("pit_loss runs on CUDA tensors only (no CPU path)")
+    if est.shape != tgt.shape or est.ndim != 3:
+        raise TypeError(f"Inputs must be of shape [batch, n_src, time], got {tuple(tgt.shape)} and {tuple(est.shape)} instead")
+    lib = _lib.load()
+    est = est.contiguous().float()
+    tgt = tgt.contiguous().float()
+    B, n_src, T = est.shape
+    dev = est.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    pw = torch.empty(B, n_src, n_src, dtype=torch.float32, device=dev)
+    perm = torch.empty(B, n_src, dtype=torch.int32, device=dev)
+    grad = torch.empty_like(est) if want_grad else None
+    ns = lib.tdanet_pit_loss_scratch_bytes(B, n_src)
+    scratch = torch.empty(ns, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tdanet_pit_loss(est.data_ptr(), tgt.data_ptr(), B, n_src, T, _lib.SDR_TYPES[sdr_type],
+                                  int(bool(threshold_byloss)), loss.data_ptr(), pw.data_ptr(), perm.data_ptr(),
+                                  None if grad is None else grad.data_ptr(), scratch.data_ptr(), ns,
+                                  torch.cuda.current_stream(dev).cuda_stream))
+    return loss, pw, perm, grad

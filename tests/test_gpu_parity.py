@@ -1,0 +1,244 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed goldens.
+Run on the B200 box: python -m pytest tests -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import tdanet_b200.look2hear as look2hear
+from conftest import CLASSES, golden_state_dict, load_golden, max_rel, oracle_cfg
+from oracle import tdanet_oracle as O
+from tdanet_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+M = look2hear.models
+DEV = "cuda:0"
+
+
+def build_from_golden(variant, g, **over):
+    kw = dict(g["kwargs"])
+    kw.update(over)
+    m = M.get(CLASSES[variant])(sample_rate=g["sample_rate"], **kw).eval()
+    sd = golden_state_dict(g)
+    pe_key = "sm.unet.globalatt.attn.pos_enc.pe"
+    pe = sd.pop(pe_key)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert missing == [pe_key] and not unexpected
+    # the product regenerates the sinusoid table; it must equal the reference buffer
+    assert torch.equal(m.state_dict()[pe_key][:, : pe.shape[1]], pe)
+    return m.to(DEV)
+
+
+def cl(t):
+    """oracle [B, C, L] -> channels-last [B, L, C]"""
+    return t.transpose(1, 2).contiguous()
+
+
+# ----------------------------------------------------------------------------- whole model
+@pytest.mark.parametrize("variant", list(CLASSES))
+@pytest.mark.parametrize("mode,tol", [("fp32", 3e-5), ("tf32", 1e-3), ("tf32x3", 1e-3)])
+def test_small_model_matches_reference_golden(variant, mode, tol):
+    g = load_golden(f"{variant}_small")
+    m = build_from_golden(variant, g)
+    m.gemm_mode = mode
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with torch.no_grad():
+        y = m(x)
+    torch.cuda.synchronize()
+    assert y.shape == g["y"].shape and y.is_contiguous()
+    assert max_rel(y.cpu(), torch.from_numpy(g["y"])) < tol
+
+
+@pytest.mark.parametrize("variant", list(CLASSES))
+def test_stage_taps_last_block(variant):
+    """Every GlobLN-delimited intermediate of the last block against the oracle's."""
+    g = load_golden(f"{variant}_small")
+    m = build_from_golden(variant, g)
+    m.gemm_mode = "fp32"
+    x = torch.from_numpy(g["x"])
+    nb = g["kwargs"]["num_blocks"]
+    cfg = oracle_cfg(variant, g["kwargs"], g["sample_rate"], taps={}, tap_block=nb - 1)
+    with torch.no_grad():
+        O.forward(golden_state_dict(g), x, cfg)
+        m(x.to(DEV))
+    torch.cuda.synchronize()
+    B, T = x.shape[0], x.shape[-1]
+    ws = lambda name: m.engine.workspace_tensor(name, B, T, DEV).cpu()
+    t = cfg.taps
+    u = "sm.unet"
+    checks = {
+        "enc": cl(t["enc"]), "x0": cl(t["bottleneck"]),
+        "proj": cl(t["proj.raw"]),
+        "ga_in": cl(t["ga.in"]), "attn_in": t["ga.attn_in"], "attn_out": t["ga.attn_out"],
+        "ga_mid": cl(t["ga.after_attn"]), "ga_out": cl(t["ga.out"]),
+        "fc1": cl(t[f"raw:{u}.globalatt.mlp.fc1"]), "fc2": cl(t[f"raw:{u}.globalatt.mlp.fc2"]),
+        "block_out": cl(t[f"block.{nb - 1}"]), "masked": cl(t["masked"].flatten(1, 2)),
+    }
+    depth = g["kwargs"]["upsampling_depth"]
+    for k in range(depth):
+        checks[f"spp{k}"] = cl(t[f"raw:{u}.spp_dw.{k}"])
+    for i in range(depth - 1):
+        checks[f"expanded{i}"] = cl(t[f"expanded.{i}"])
+    worst = {}
+    for name, ref in checks.items():
+        got = ws(name)
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        worst[name] = max_rel(got, ref)
+    bad = {k: v for k, v in worst.items() if not v < 5e-5}
+    assert not bad, f"stage mismatches: {bad}\nall: {worst}"
+
+
+@pytest.mark.parametrize("variant", list(CLASSES))
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("tf32", 1e-3)])
+def test_full_model_matches_reference_golden(variant, mode, tol):
+    """BASELINE.json configurations (#1 for multres, #2's architecture at B=2 for best/fork):
+    seeded random-init weights, seeded input, against the stored output of the unmodified reference."""
+    g = load_golden(f"{variant}_full")
+    torch.manual_seed(int(g["init_seed"]))
+    m = M.get(CLASSES[variant])(sample_rate=g["sample_rate"], **g["kwargs"]).eval().to(DEV)
+    m.gemm_mode = mode
+    B = int(g["batch"])
+    x = torch.randn(B, 1, 32000, generator=torch.Generator().manual_seed(int(g["input_seed"]))) * 0.1
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    torch.cuda.synchronize()
+    err = (y.cpu()[:, :, ::16] - torch.from_numpy(g["y_sub"])).abs().max().item() / float(g["y_absmax"])
+    assert err < tol, err
+
+
+def test_input_ranks_and_graph_replay():
+    g = load_golden("best_small")
+    m = build_from_golden("best", g)
+    x = torch.from_numpy(g["x"])[:1].to(DEV)
+    with torch.no_grad():
+        y3, y2, y1 = m(x), m(x[:, 0]), m(x[0, 0])
+        m.use_cuda_graph = True
+        yg1 = m(x)
+        yg2 = m(x)
+    assert y3.shape == (1, 2, x.shape[-1]) and y1.shape == (2, x.shape[-1])
+    assert torch.equal(y3, y2) and torch.equal(y3[0], y1)
+    assert torch.equal(yg1, y3) and torch.equal(yg2, y3)
+
+
+def test_attention_group_equals_separate_batches():
+    """BEST attends over the batch axis: a batch of 4 with attn_group=2 must equal two calls of 2
+    (this is how shards / long-form chunks are batched without changing the reference result)."""
+    g = load_golden("best_small")
+    m = build_from_golden("best", g)
+    x = torch.randn(4, 1, 2000, generator=torch.Generator().manual_seed(3)).to(DEV) * 0.1
+    with torch.no_grad():
+        ya, yb = m(x[:2]).clone(), m(x[2:]).clone()
+        m.attn_group = 2
+        y = m(x)
+        m.attn_group = 0
+        y_all = m(x)
+    assert max_rel(y, torch.cat([ya, yb])) < 1e-6
+    assert max_rel(y_all, torch.cat([ya, yb])) > 1e-4   # the reference really is batch dependent
+
+
+def test_full_size_properties():
+    """Size-independent checks at the headline shape (B=64, 2 s, 4 ms encoder): batch-permutation
+    equivariance (batch-axis attention has no positional term along the batch), exact zeros for
+    silent input, and a shard computed alone equals the same shard inside a grouped batch."""
+    torch.manual_seed(0)
+    m = M.TDANetBest(out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=5, enc_kernel_size=4,
+                     num_sources=2, sample_rate=16000).eval().to(DEV)
+    x = torch.randn(64, 1, 32000, generator=torch.Generator().manual_seed(1234)).to(DEV) * 0.1
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(7)).to(DEV)
+    with torch.no_grad():
+        y = m(x).clone()
+        yp = m(x[perm])
+        assert torch.isfinite(y).all()
+        assert max_rel(yp, y[perm]) < 2e-3          # tf32: accumulation order differs across tiles
+        m.attn_group = 8
+        yg = m(x).clone()
+        m.attn_group = 0
+        y8 = m(x[8:16])
+        assert max_rel(yg[8:16], y8) < 2e-3
+        z = m(torch.zeros(2, 1, 32000, device=DEV))
+        assert torch.count_nonzero(z) == 0
+
+
+def test_full_model_against_oracle_live():
+    """2 ms encoder (BASELINE config #3 architecture) at B=3 against the oracle run on the host."""
+    kw = dict(out_channels=128, in_channels=512, num_blocks=4, upsampling_depth=5, enc_kernel_size=2, num_sources=2)
+    torch.manual_seed(1)
+    m = M.TDANetBest(sample_rate=16000, **kw).eval()
+    x = torch.randn(3, 1, 16000, generator=torch.Generator().manual_seed(5)) * 0.1
+    with torch.no_grad():
+        ref = O.forward({k: v for k, v in m.state_dict().items()}, x, O.OracleConfig(variant="best", sample_rate=16000, **kw))
+        m = m.to(DEV)
+        m.gemm_mode = "fp32"
+        y32 = m(x.to(DEV)).cpu()
+        m.gemm_mode = "tf32"
+        ytf = m(x.to(DEV)).cpu()
+    assert max_rel(y32, ref) < 5e-5
+    assert max_rel(ytf, ref) < 1e-3
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("B,L,N,K", [(2, 2010, 512, 128), (3, 126, 1536, 512), (2, 251, 512, 1024),
+                                     (1, 300, 128, 512), (4, 70, 96, 64), (2, 129, 16, 32), (1, 1, 256, 128)])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
+def test_gemm_against_fp64(B, L, N, K, mode):
+    gen = torch.Generator().manual_seed(B * 1000 + L)
+    A = torch.randn(B, L, K, generator=gen)
+    W = torch.randn(N, K, generator=gen) / K ** 0.5
+    bias = torch.randn(N, generator=gen)
+    ref = A.double() @ W.double().t() + bias.double()
+    D, stats = E.gemm(A.to(DEV), W.to(DEV), bias.to(DEV), mode=mode, with_stats=True)
+    torch.cuda.synchronize()
+    tol = {"fp32": 2e-6, "tf32": 2e-3, "tf32x3": 1e-3}[mode]
+    assert max_rel(D.cpu(), ref) < tol
+    # epilogue statistics: per-item sum and sum of squares of what was stored
+    s = torch.stack([D.double().sum(dim=(1, 2)), (D.double() ** 2).sum(dim=(1, 2))], dim=1).cpu()
+    assert torch.allclose(stats.cpu(), s, rtol=1e-5, atol=1e-3)
+
+
+def test_gemm_tf32_exact_on_representable_inputs():
+    """With inputs exactly representable in TF32 the tensor-core product must equal fp32 to rounding:
+    pins the descriptor / swizzle / tiling logic independently of precision."""
+    gen = torch.Generator().manual_seed(0)
+    A = torch.randint(-8, 9, (2, 515, 256), generator=gen).float() / 8
+    W = torch.randint(-8, 9, (384, 256), generator=gen).float() / 8
+    ref = A.double() @ W.double().t()
+    for mode in ("tf32", "tf32x3"):
+        D = E.gemm(A.to(DEV), W.to(DEV), None, mode=mode)
+        assert (D.cpu().double() - ref).abs().max().item() < 1e-4
+
+
+# ----------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("name", ["snr", "sisdr", "sdsdr"])
+def test_pit_loss_known_answers(name):
+    g = load_golden("loss")
+    est, tgt = torch.from_numpy(g["est"]).to(DEV), torch.from_numpy(g["tgt"]).to(DEV)
+    pw = getattr(look2hear.losses, f"pairwise_neg_{name}")(est, tgt)
+    np.testing.assert_allclose(pw.cpu().numpy(), g[f"pw_{name}"], rtol=2e-5, atol=2e-4)
+    for thr in (True, False):
+        w = look2hear.losses.PITLossWrapper(getattr(look2hear.losses, f"pairwise_neg_{name}"), threshold_byloss=thr)
+        loss, reo = w(est, tgt, return_ests=True)
+        np.testing.assert_allclose(loss.item(), g[f"pit_{name}_{int(thr)}"], rtol=2e-5, atol=2e-4)
+        swapped = (reo[:, 0] == est[:, 1]).all(dim=-1).long().cpu().numpy()
+        np.testing.assert_array_equal(swapped, g[f"perm0_{name}_{int(thr)}"])
+    if name == "snr":
+        w = look2hear.losses.PITLossWrapper(look2hear.losses.pairwise_neg_snr, threshold_byloss=True)
+        loss = w(torch.from_numpy(g["est_all_below"]).to(DEV), tgt)
+        np.testing.assert_allclose(loss.item(), g["pit_snr_all_below"], rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["snr", "sisdr", "sdsdr"])
+@pytest.mark.parametrize("n_src", [2, 3])
+def test_pit_loss_gradient_matches_autograd_of_oracle(name, n_src):
+    gen = torch.Generator().manual_seed(17 + n_src)
+    tgt = torch.randn(5, n_src, 3001, generator=gen) * 0.1
+    est = (tgt[:, torch.randperm(n_src, generator=gen)] + 0.03 * torch.randn(5, n_src, 3001, generator=gen) + 0.02)
+    est[0] = tgt[0] + 1e-5 * torch.randn(n_src, 3001, generator=gen)   # dropped by the threshold
+    e_ref = est.double().requires_grad_(True)
+    loss_ref = O.pit_loss(e_ref, tgt.double(), name, True)
+    loss_ref.backward()
+    e = est.to(DEV).requires_grad_(True)
+    w = look2hear.losses.PITLossWrapper(getattr(look2hear.losses, f"pairwise_neg_{name}"), threshold_byloss=True)
+    loss = w(e, tgt.to(DEV))
+    (loss * 2.0).backward()
+    assert abs(loss.item() - loss_ref.item()) < 2e-4
+    assert max_rel(e.grad.cpu() / 2.0, e_ref.grad) < 1e-4
+    assert torch.count_nonzero(e.grad[0]) == 0
