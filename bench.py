@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Headline benchmark: separated audio-seconds per second of TDANet inference on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+A "step" is one forward of the hot path over one batch of synthetic 2 s / 16 kHz mixtures
+(BASELINE.json configs[1]: TDANet 4 ms encoder, 16 blocks, batch 64 per GPU).  Rank 0 prints ONE
+JSON line.  `value` is device-timed with the inputs resident in HBM; `e2e` goes through the public
+`model(mix)` call with pinned host buffers (H2D of the mixtures and D2H of the separated sources inside
+the timed region).  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SR = 16000
+N_SAMPLES = 32000
+METRIC = "separated_audio_seconds_per_second"
+UNIT = "audio-s/s"
+CLASSES = {"best": "TDANetBest", "fork": "TDANet"}
+
+
+def model_kwargs(enc_ms):
+    return dict(out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=5, enc_kernel_size=enc_ms,
+                num_sources=2)
+
+
+def workload_name(variant, enc_ms, batch):
+    return (f"{CLASSES[variant]} {enc_ms} ms encoder, 16 blocks, inference, batch {batch} x 2 s @16 kHz per GPU "
+            f"(BASELINE.json configs[{1 if enc_ms == 4 else 2}]), random-init weights (seed 0)")
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- algorithmic bytes
+def algorithmic_bytes(variant, lengths, B, C=512, c=128):
+    """Unique input + output bytes per forward for each kernel role (fp32, each tensor counted once per
+    launch); the per-launch figures of DESIGN.md times the launches of one forward (16 blocks)."""
+    L, depth, Lb, f = lengths, len(lengths), lengths[-1], 4
+    blk = {}
+    blk["gemm_proj"] = (L[0] * c + L[0] * C) * f
+    blk["spp_dw0"] = 2 * L[0] * C * f
+    blk["spp_dw_s2"] = sum((L[k - 1] + L[k]) * C for k in range(1, depth)) * f
+    blk["pool_sum"] = (sum(L) + Lb) * C * f
+    stats = comb = 0
+    for i in range(depth - 2, -1, -1):
+        Lg = L[i - 1] if i == depth - 2 else L[i + 1]
+        stats += (L[i] + Lg) * C * f
+        comb += (L[i] + Lg + L[i]) * C * f
+    blk["la_stats"], blk["la_combine"] = stats, comb
+    blk["gemm_res_conv"] = (L[0] * C + 3 * L[0] * c) * f
+    blk["gemm_in_proj"] = Lb * 4 * C * f
+    blk["gemm_out_proj"] = Lb * 2 * C * f
+    blk["gemm_fc1"] = Lb * 3 * C * f
+    blk["gemm_fc2"] = Lb * 3 * C * f
+    blk["ffn_dw"] = Lb * 4 * C * f
+    blk["attention"] = Lb * 4 * C * f
+    return {k: v * B * 16 for k, v in blk.items()}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference algorithm (oracle port of the PyTorch modules, fp32 eager) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import tdanet_oracle as O
+    import tdanet_b200.look2hear.models as M
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = model_kwargs(args.enc_ms)
+    torch.manual_seed(0)
+    model = M.get(CLASSES[args.variant])(sample_rate=SR, **kw)    # parameter container only (CPU)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    cfg = O.OracleConfig(variant=args.variant, sample_rate=SR, **kw)
+    x1 = torch.randn(1, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234)) * 0.1
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.forward(sd, x1, cfg)
+        t1 = time.perf_counter() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    bs = int(max(1, min(args.ref_batch, budget // max(t1, 1e-3))))
+    x = torch.randn(bs, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234)) * 0.1
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.forward(sd, x, cfg)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(sd, x, cfg)
+        dt = time.perf_counter() - t0
+    value = bs * (N_SAMPLES / SR) * args.steps / dt
+    sample = f"{bs} x 2 s mixtures per step (of the {args.batch}-mixture workload), {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.variant, args.enc_ms, args.batch), "batch_per_step": bs,
+                   "note": "the reference is pure PyTorch and cannot travel to the GPU box (sources may not be "
+                           "copied); this arm times oracle/tdanet_oracle.py, the CPU restatement pinned to the "
+                           "reference by tests/golden, on all host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- this framework
+def run_ours(args):
+    import torch.distributed as dist
+    import tdanet_b200.look2hear.models as M
+    from tdanet_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().tdanet_device_supported(local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    B, W, K = args.batch, max(3, args.warmup), args.steps
+    kw = model_kwargs(args.enc_ms)
+    torch.manual_seed(0)
+    model = M.get(CLASSES[args.variant])(sample_rate=SR, **kw).eval().to(dev)
+    model.gemm_mode = args.gemm_mode
+    eng, weights = model.engine, model._weights()
+    # each rank separates its own shard of the global batch (weak scaling: B mixtures per GPU)
+    x_host = (torch.randn(B, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234 + rank)) * 0.1).pin_memory()
+    x_dev = x_host.to(dev).squeeze(1).contiguous()
+    lengths, _, _ = eng.latent_lengths(N_SAMPLES)
+
+    def step():
+        if args.no_graph:
+            return eng.forward(weights, x_dev)
+        return eng.forward_graphed(weights, x_dev)
+
+    with torch.no_grad():
+        n0 = _lib.launch_count()
+        eng.forward(weights, x_dev)
+        launches_per_step = _lib.launch_count() - n0
+        for _ in range(W):
+            step()
+        # ---- timed region: K steps, inputs resident in HBM
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            barrier()
+            ev0.record()
+            for _ in range(K):
+                step()
+            ev1.record()
+            barrier()
+        ms = ev0.elapsed_time(ev1)
+        # ---- end to end through the public API with host buffers
+        out_host = torch.empty(B, 2, N_SAMPLES, dtype=torch.float32).pin_memory()
+        model.use_cuda_graph = not args.no_graph
+        xin = torch.empty(B, 1, N_SAMPLES, device=dev)
+        for _ in range(2):
+            xin.copy_(x_host, non_blocking=True)
+            out_host.copy_(model(xin), non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            xin.copy_(x_host, non_blocking=True)        # H2D of this step's mixtures (pinned)
+            est = model(xin)                            # the call a user makes
+            out_host.copy_(est, non_blocking=True)      # D2H of the separated sources
+            torch.cuda.current_stream().synchronize()   # the result is consumed on the host every step
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        model.use_cuda_graph = False
+        # ---- per-kernel durations (CUDA events around every launch, 2 un-graphed steps)
+        prof = None
+        if rank == 0:
+            _lib.profile_enable(True)
+            for _ in range(2):
+                eng.forward(weights, x_dev)
+            prof = _lib.profile_dump()
+            _lib.profile_enable(False)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # max over ranks
+    ms, ms_e2e = t.tolist()
+    audio_s = world * B * (N_SAMPLES / SR) * K
+    value = audio_s / (ms / 1e3)
+    e2e = audio_s / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg = algorithmic_bytes(args.variant, lengths, B)
+        kernels = []
+        for p in sorted(prof, key=lambda r: -r["ms"]):
+            per_step_ms = p["ms"] / 2
+            row = {"kernel": p["kernel"], "launches_per_step": p["launches"] // 2, "ms_per_step": round(per_step_ms, 4)}
+            if p["kernel"] in alg:
+                row["alg_GB_per_step"] = round(alg[p["kernel"]] / 1e9, 4)
+                row["achieved_GBps"] = round(alg[p["kernel"]] / 1e9 / (per_step_ms / 1e3), 1)
+            kernels.append(row)
+        top = next(r for r in kernels if "achieved_GBps" in r)
+        prof_total = sum(r["ms_per_step"] for r in kernels)
+        roofline = {
+            "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_GBps"], "peak": peak, "unit": "GB/s",
+            "frac": round(top["achieved_GBps"] / peak, 4), "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": int(alg[top["kernel"]] / max(1, top["launches_per_step"])),
+            "avg_launch_ms": round(top["ms_per_step"] / max(1, top["launches_per_step"]), 5),
+            "share_of_step": round(top["ms_per_step"] / prof_total, 4),
+            "how": "CUDA events around every launch on the launch stream, 2 un-graphed steps after the timed region",
+        }
+        # whole-step roofline against SURVEY.md §8(d)'s byte model (1.936 GB / mixture at 4 ms, fp32)
+        model_gb = {("best", 4): 1.936, ("best", 2): 3.859, ("fork", 4): 1.952, ("fork", 2): 3.892}[(args.variant, args.enc_ms)]
+        step_roofline = {"survey_bytes_per_mixture_GB": model_gb, "hbm_roofline_audio_s_per_s": round(peak / model_gb * 2.0, 1),
+                         "frac_of_survey_roofline": round(value / world / (peak / model_gb * 2.0), 4)}
+        cpu = cpu_baseline(args) if world == 1 and not args.skip_cpu else None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tf32 tensor-core GEMMs, fp32 storage/accumulate)" if args.gemm_mode != "fp32" else "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.variant, args.enc_ms, B), "batch_per_gpu": B, "n_samples": N_SAMPLES,
+                       "gemm_mode": args.gemm_mode, "cuda_graph": not args.no_graph,
+                       "l2": "no flush needed: one step streams a 1.7 GB workspace, 13x the 126 MB L2"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": B * 2 * N_SAMPLES * 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches_per_step * K,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clk.summary(),
+            "roofline": roofline,
+            "step_roofline": step_roofline,
+            "kernels": kernels[:14],
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    """Oracle port of the reference on this box's host cores, bounded sample (about 10-30 s of CPU work)."""
+    from oracle import tdanet_oracle as O
+    import tdanet_b200.look2hear.models as M
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = model_kwargs(args.enc_ms)
+    torch.manual_seed(0)
+    model = M.get(CLASSES[args.variant])(sample_rate=SR, **kw)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    cfg = O.OracleConfig(variant=args.variant, sample_rate=SR, **kw)
+    x = torch.randn(8, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234)) * 0.1
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.forward(sd, x[:1], cfg)                         # warm-up, and sizes the sample
+        t1 = time.perf_counter() - t0
+        bs = int(max(1, min(8, 12.0 // max(t1, 1e-3))))
+        t0 = time.perf_counter()
+        O.forward(sd, x[:bs], cfg)
+        dt = time.perf_counter() - t0
+    return {"value": bs * 2.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"one forward of {bs} x 2 s mixtures (of the {args.batch}-mixture step) after one 1-mixture warm-up, fp32 eager, {cores} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="best", choices=list(CLASSES))
+    ap.add_argument("--enc-ms", type=int, default=4, choices=[2, 4])
+    ap.add_argument("--batch", type=int, default=64, help="mixtures per GPU per step")
+    ap.add_argument("--gemm-mode", default="tf32", choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-batch", type=int, default=8, help="upper bound of mixtures per step for --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

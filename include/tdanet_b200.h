@@ -133,6 +133,12 @@ TDANET_API int tdanet_abi_sizes(size_t* config_bytes, size_t* weights_bytes);
 TDANET_API const char* tdanet_last_error(void);
 /* number of kernels this library has enqueued so far in this process */
 TDANET_API uint64_t tdanet_launch_count(void);
+/* Per-launch CUDA-event timing (measurement aid, off by default).  While enabled, every kernel the
+ * library enqueues outside stream capture is bracketed by events on its own stream;
+ * tdanet_profile_dump synchronises and writes a JSON array [{"kernel","launches","ms"}] aggregated by
+ * kernel since the previous dump, returning the length it needs. */
+TDANET_API int tdanet_profile_enable(int on);
+TDANET_API int tdanet_profile_dump(char* out, size_t cap);
 /* 0 if device `dev` can run the library (compute capability 10.x) */
 TDANET_API int tdanet_device_supported(int dev);
 

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "tdanet_last_error": (C.c_char_p, []),
     "tdanet_launch_count": (C.c_uint64, []),
     "tdanet_device_supported": (C.c_int, [C.c_int]),
+    "tdanet_profile_enable": (C.c_int, [C.c_int]),
+    "tdanet_profile_dump": (C.c_int, [C.c_char_p, C.c_size_t]),
     "tdanet_workspace_bytes": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "tdanet_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), fptr, C.c_int, C.c_int, fptr, fptr,
                                  C.c_size_t, fptr]),
@@ -124,3 +126,17 @@ def check(code: int) -> None:
 
 def launch_count() -> int:
     return int(load().tdanet_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(load().tdanet_profile_enable(int(on)))
+
+
+def profile_dump():
+    """[{kernel, launches, ms}] for every launch recorded since the last dump (synchronises)."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    n = load().tdanet_profile_dump(buf, len(buf))
+    if n < 0:
+        check(n)
+    return json.loads(buf.value.decode())

@@ -28,10 +28,23 @@ int fail(int code, const char* fmt, ...);
     if (!(cond)) return td::fail(TDANET_EINVAL, __VA_ARGS__);                            \
   } while (0)
 
+// Optional per-launch CUDA-event timing (tdanet_profile_enable): events are recorded on the stream
+// the kernel is launched on, immediately before and after it.
+extern bool g_profile;
+extern thread_local const char* g_tag;  // role of the next launches ("proj", "la_combine", ...), or null
+void profile_mark(const char* name, cudaStream_t st, bool begin);
+struct Tag {
+  const char* prev;
+  explicit Tag(const char* t) : prev(g_tag) { g_tag = t; }
+  ~Tag() { g_tag = prev; }
+};
+
 // Every kernel launch goes through this so that tdanet_launch_count() is honest.
 #define TD_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
   do {                                                                                   \
+    if (td::g_profile) td::profile_mark(#kernel, (stream), true);                        \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+    if (td::g_profile) td::profile_mark(#kernel, (stream), false);                       \
     td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
     cudaError_t _e = cudaPeekAtLastError();                                              \
     if (_e != cudaSuccess)                                                               \

@@ -24,6 +24,34 @@ int fail(int code, const char* fmt, ...) {
 
 size_t pit_scratch_floats(int B);
 
+// ----------------------------------------------------------------------------- event profiler
+bool g_profile = false;
+thread_local const char* g_tag = nullptr;
+struct ProfRec {
+  const char* name;
+  cudaEvent_t ev[2];
+};
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+
+void profile_mark(const char* name, cudaStream_t st, bool begin) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  cudaEvent_t e;
+  if (!g_ev_pool.empty()) {
+    e = g_ev_pool.back();
+    g_ev_pool.pop_back();
+  } else if (cudaEventCreate(&e) != cudaSuccess) {
+    return;
+  }
+  cudaEventRecord(e, st);
+  if (begin) {
+    g_prof.push_back(ProfRec{g_tag ? g_tag : name, {e, nullptr}});
+  } else if (!g_prof.empty()) {
+    g_prof.back().ev[1] = e;
+  }
+}
+
 // ----------------------------------------------------------------------------- plan
 struct Named {
   std::string name;
@@ -226,16 +254,18 @@ static int global_attention(const Ctx& x) {
   TD_REQUIRE(w->pe_rows >= Lb, "positional encoding has %d rows, need %d", w->pe_rows, Lb);
 
   // attn_in_norm + positional encoding
+  Tag tag("bottom_misc");
   if (int e = launch_ln_pe(x.at(p.ga_in), w->ln1_w, w->ln1_b, w->pe, x.at(p.attn_in), B, Lb, C, x.rnd(), x.st)) return e;
   GemmArgs g{};
   g.A = x.at(p.attn_in); g.W = w->in_proj_w; g.bias = w->in_proj_b; g.D = x.at(p.qkv);
   g.B = B; g.L = Lb; g.N = 3 * C; g.K = C; g.epi = EPI_BIAS;
-  if (int e = gemm(x, g, p.aux_in)) return e;
-  if (int e = launch_attention(x.at(p.qkv), x.at(p.attn_ctx), B, Lb, C, c->n_head, group, time_axis, x.rnd(), x.st)) return e;
+  { Tag t("gemm_in_proj"); if (int e = gemm(x, g, p.aux_in)) return e; }
+  { Tag t("attention");
+  if (int e = launch_attention(x.at(p.qkv), x.at(p.attn_ctx), B, Lb, C, c->n_head, group, time_axis, x.rnd(), x.st)) return e; }
   g = GemmArgs{};
   g.A = x.at(p.attn_ctx); g.W = w->out_proj_w; g.bias = w->out_proj_b; g.D = x.at(p.attn_out);
   g.B = B; g.L = Lb; g.N = C; g.K = C; g.epi = EPI_BIAS;
-  if (int e = gemm(x, g, p.aux_out)) return e;
+  { Tag t("gemm_out_proj"); if (int e = gemm(x, g, p.aux_out)) return e; }
   // x + LayerNorm(out + dropout(out))  [BEST/FORK]   |   x + LayerNorm(pe_in + out)  [MULTRES]
   if (int e = launch_ln_residual(x.at(p.attn_out), x.at(p.attn_in), x.at(p.ga_in), w->ln2_w, w->ln2_b,
                                  x.at(p.ga_mid), !time_axis, B, Lb, C, x.st)) return e;
@@ -243,18 +273,18 @@ static int global_attention(const Ctx& x) {
   g = GemmArgs{};
   g.A = x.at(p.ga_mid); g.W = w->fc1.w; g.bias = nullptr; g.D = x.at(p.fc1);
   g.B = B; g.L = Lb; g.N = 2 * C; g.K = C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_fc1);
-  if (int e = gemm(x, g, p.aux_fc1)) return e;
+  { Tag t("gemm_fc1"); if (int e = gemm(x, g, p.aux_fc1)) return e; }
   if (int e = launch_coef_item(x.at<double>(p.st_fc1), (double)Lb * 2 * C, w->fc1.gamma, w->fc1.beta,
                                x.at(p.fc1_coef), B, 2 * C, x.st)) return e;
   DwArgs d{};
   d.src = affine_src(x.at(p.fc1), Lb, x.at(p.fc1_coef));
   d.kind = SRC_AFFINE; d.B = B; d.C = 2 * C; d.Lout = Lb; d.stride = 1; d.nw = 1;
   d.w[0] = w->ffn_dw_w; d.bias[0] = w->ffn_dw_b; d.out = x.at(p.ffn_dw); d.relu = 1; d.round_out = x.rnd();
-  if (int e = launch_dw5(d, x.st)) return e;
+  { Tag t("ffn_dw"); if (int e = launch_dw5(d, x.st)) return e; }
   g = GemmArgs{};
   g.A = x.at(p.ffn_dw); g.W = w->fc2.w; g.bias = nullptr; g.D = x.at(p.fc2);
   g.B = B; g.L = Lb; g.N = C; g.K = 2 * C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_fc2);
-  if (int e = gemm(x, g, p.aux_fc2)) return e;
+  { Tag t("gemm_fc2"); if (int e = gemm(x, g, p.aux_fc2)) return e; }
   if (int e = launch_coef_item(x.at<double>(p.st_fc2), (double)Lb * C, w->fc2.gamma, w->fc2.beta,
                                x.at(p.fc2_coef), B, C, x.st)) return e;
   // global_f = x + gLN(fc2); BEST also needs its per-channel sums for the closed-form loc_glo_fus
@@ -274,7 +304,8 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   GemmArgs g{};
   g.A = in; g.W = w->proj.w; g.bias = w->proj.b; g.D = x.at(p.proj);
   g.B = B; g.L = p.L[0]; g.N = C; g.K = cc; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_proj);
-  if (int e = gemm(x, g, p.aux_proj)) return e;
+  { Tag t("gemm_proj"); if (int e = gemm(x, g, p.aux_proj)) return e; }
+  Tag tag("coef");
   if (int e = launch_coef_item(x.at<double>(p.st_proj), (double)p.L[0] * C, w->proj.gamma, w->proj.beta,
                                x.at(p.proj_coef), B, C, x.st)) return e;
   // spp_dw[0..depth-1]: depthwise k5 (stride 1, then 2), raw output + per-channel sums
@@ -289,7 +320,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     }
     d.B = B; d.C = C; d.Lout = p.L[k]; d.stride = k == 0 ? 1 : 2; d.nw = 1;
     d.w[0] = w->spp_dw[k].w; d.bias[0] = w->spp_dw[k].b; d.out = x.at(p.spp[k]); d.stats = x.at(p.st_spp[k]);
-    if (int e = launch_dw5(d, x.st)) return e;
+    { Tag t(k == 0 ? "spp_dw0" : "spp_dw_s2"); if (int e = launch_dw5(d, x.st)) return e; }
     if (int e = launch_coef_chan(x.at(p.st_spp[k]), (size_t)2 * C, p.L[k], w->spp_dw[k].gamma, w->spp_dw[k].beta,
                                  x.at(p.spp_coef[k]), B, C, x.st)) return e;
   }
@@ -301,6 +332,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     for (int k = 0; k < depth; ++k) {
       const int j = depth - 1 - k, s = 1 << j, ks = j == 0 ? 5 : 2 * s + 1;
       const tdanet_sepconvnorm_t& q = w->conv_pool[j];
+      Tag tp("conv_pool");
       if (int e = launch_dw_generic(affine_src(x.at(p.spp[k]), p.L[k], x.at(p.spp_coef[k])), SRC_AFFINE, B, C, Lb,
                                     ks, s, q.dw_w, q.dw_b, x.at(p.pool_dw[k]), x.rnd(), x.st)) return e;
       g = GemmArgs{};
@@ -314,6 +346,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     if (int e = launch_affine_sum(pa, x.st)) return e;
   } else {
     for (int k = 0; k < depth; ++k) { pa.x[k] = x.at(p.spp[k]); pa.coef[k] = x.at(p.spp_coef[k]); pa.L[k] = p.L[k]; }
+    Tag tp("pool_sum");
     if (int e = launch_pool_sum(pa, x.st)) return e;
   }
   if (int e = global_attention(x)) return e;
@@ -347,24 +380,25 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     DwArgs d{};
     d.src = loc; d.kind = inj_kind; d.B = B; d.C = C; d.Lout = loc.L; d.stride = 1; d.nw = 1;
     d.w[0] = la.local_embedding.w; d.stats = x.at(p.st_la_l[i]);
-    if (int e = launch_dw5(d, x.st)) return e;
+    { Tag t("la_stats"); if (int e = launch_dw5(d, x.st)) return e; }
     d = DwArgs{};
     d.src = glo; d.kind = gkind; d.B = B; d.C = C; d.Lout = glo.L; d.stride = 1; d.nw = 2;
     d.w[0] = la.global_act.w; d.w[1] = la.global_embedding.w; d.stats = x.at(p.st_la_g[i]);
-    if (int e = launch_dw5(d, x.st)) return e;
+    { Tag t("la_stats"); if (int e = launch_dw5(d, x.st)) return e; }
     if (int e = launch_coef_la(x.at(p.st_la_l[i]), loc.L, x.at(p.st_la_g[i]), glo.L, &la, x.at(p.la_coef[i]), B, C, x.st)) return e;
     LaArgs l{};
     l.loc = loc; l.glo = glo; l.lkind = inj_kind; l.gkind = gkind; l.B = B; l.C = C;
     l.wl = la.local_embedding.w; l.wa = la.global_act.w; l.we = la.global_embedding.w;
     l.coef = x.at(p.la_coef[i]); l.out = x.at(p.expanded[i]); l.scale = nearest_scale(glo.L, loc.L);
     l.round_out = i == 0 && x.rnd();  // expanded[0] only feeds res_conv
-    if (int e = launch_la_combine(l, x.st)) return e;
+    { Tag t("la_combine"); if (int e = launch_la_combine(l, x.st)) return e; }
   }
   // res_conv + residual (+ concat_block for the next iteration)
   g = GemmArgs{};
   g.A = x.at(p.expanded[0]); g.W = w->res_w; g.bias = w->res_b; g.D = out;
   g.B = B; g.L = p.L[0]; g.N = cc; g.K = C; g.epi = EPI_RESIDUAL;
   g.resid = in; g.mix = x.at(p.x0); g.cw = w->concat_w; g.cb = w->concat_b; g.cslope = w->concat_prelu; g.last = last;
+  Tag tr("gemm_res_conv");
   return gemm(x, g, p.aux_res);
 }
 
@@ -379,6 +413,7 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
   const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
 
   TD_CUDA(cudaMemsetAsync(x.ws + p.st_enc, 0, p.st_proj - p.st_enc, st));
+  Tag tag("frontend");
   if (int e = prepare_weights(x)) return e;
   // encoder (+ pad_input folded into the indexing) and its GlobLN statistics
   EncArgs ea{};
@@ -403,6 +438,7 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
   g.A = x.at(p.u[(c->num_blocks - 1) & 1]); g.W = w->mask_w; g.bias = w->mask_b; g.D = x.at(p.masked);
   g.B = B; g.L = L0; g.N = c->num_sources * Nb; g.K = cc; g.epi = EPI_MASK; g.a_slope = w->mask_prelu;
   g.enc = x.at(p.enc); g.Nb = Nb;
+  Tag tb("backend");
   if (int e = launch_gemm_simt(g, st)) return e;
   return launch_decoder(x.at(p.masked), w->dec_w, est, B, L0, Nb, c->num_sources, K, S, T, st);
 }
@@ -431,6 +467,44 @@ int tdanet_device_supported(int dev) {
   TD_CUDA(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) return fail(TDANET_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
   return 0;
+}
+
+int tdanet_profile_enable(int on) {
+  g_profile = on != 0;
+  return 0;
+}
+
+// JSON: [{"kernel": name, "launches": n, "ms": total}, ...] for everything recorded since the last
+// dump; synchronises the device.  Returns the number of bytes needed (excluding the terminator).
+int tdanet_profile_dump(char* out, size_t cap) {
+  TD_CUDA(cudaDeviceSynchronize());
+  struct Agg { std::string name; int n; double ms; };
+  std::vector<Agg> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (r.ev[1] && cudaEventElapsedTime(&ms, r.ev[0], r.ev[1]) == cudaSuccess) {
+      bool found = false;
+      for (auto& a : agg)
+        if (a.name == r.name) { a.n++; a.ms += ms; found = true; break; }
+      if (!found) agg.push_back({r.name, 1, ms});
+    }
+    g_ev_pool.push_back(r.ev[0]);
+    if (r.ev[1]) g_ev_pool.push_back(r.ev[1]);
+  }
+  g_prof.clear();
+  std::string s = "[";
+  char buf[512];
+  for (size_t i = 0; i < agg.size(); ++i) {
+    std::string nm;
+    for (char ch : agg[i].name) if (ch != '"' && ch != '\\') nm += ch;
+    snprintf(buf, sizeof buf, "%s{\"kernel\": \"%s\", \"launches\": %d, \"ms\": %.6f}", i ? ", " : "", nm.c_str(), agg[i].n, agg[i].ms);
+    s += buf;
+  }
+  s += "]";
+  if (out && cap) {
+    snprintf(out, cap, "%s", s.c_str());
+  }
+  return (int)s.size();
 }
 
 int tdanet_workspace_bytes(const tdanet_config_t* cfg, int batch, int n_samples, size_t* bytes) {
