@@ -126,7 +126,7 @@ __device__ __forceinline__ void vround_tf32(vf<V>& r) {
   for (int i = 0; i < V; ++i) r.v[i] = tf32_rna(r.v[i]);
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float preluf_(float x, float a) { return x >= 0.f ? x : a * x; }
 
 __device__ __forceinline__ float warp_sum(float v) {

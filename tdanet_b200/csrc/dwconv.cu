@@ -7,23 +7,28 @@
 //
 // Memory-bound kernels: one thread owns V consecutive channels and walks over time with a
 // register window; all global loads of a chunk of rows are issued before any is consumed.
+// CTAs whose rows (halo included) lie inside the tensor run a path without bounds checks; the
+// nearest-neighbour row indices of a CTA are tabulated once in shared memory.
 #include "kernels.h"
 
 namespace td {
 
 // ----------------------------------------------------------------------------- sources
-template <int KIND, int V>
+// EDGE = true: rows outside [0, L) read as exact zeros (conv zero padding).
+template <int KIND, int V, bool EDGE>
 struct Src {
-  const float* x;
+  const float* x;  // item base + first channel of this thread
   int L, C;
   vf<V> c0_, c1_, c2_, c3_, c4_, c5_;  // coefficient planes
   float slope;
   const float* g;
-  int Lg, cur;
-  float gscale;
-  vf<V> sg, eg, nxt;
+  const int* jtab;  // nearest global row of local row t at jtab[t - tab0]   (inject kinds)
+  int tab0, cur;
+  vf<V> sg, eg;
 
-  __device__ __forceinline__ void init(const SrcDesc& d, int b, int ch, int C_) {
+  static constexpr bool kInject = KIND == SRC_INJECT_GATE || KIND == SRC_INJECT_ADD;
+
+  __device__ __forceinline__ void init(const SrcDesc& d, int b, int ch, int C_, const int* jt, int tab0_) {
     C = C_;
     L = d.L;
     x = d.x + (size_t)b * d.L * C_ + ch;
@@ -40,23 +45,22 @@ struct Src {
       }
     }
     if constexpr (KIND == SRC_AFFINE_PRELU) slope = __ldg(d.slope);
-    if constexpr (KIND == SRC_INJECT_GATE || KIND == SRC_INJECT_ADD) {
+    if constexpr (kInject) {
       g = d.g + (size_t)b * d.Lg * C_ + ch;
-      Lg = d.Lg;
-      gscale = d.gscale;
-      cur = -2;
+      jtab = jt;
+      tab0 = tab0_;
+      cur = -1;
     }
   }
 
   __device__ __forceinline__ vf<V> load_raw(int t) const {
-    if (t < 0 || t >= L) return vzero<V>();
-    return vload<V>(x + (size_t)t * C);
+    if (EDGE && (t < 0 || t >= L)) return vzero<V>();
+    return vload<V>(x + t * C);
   }
 
   __device__ __forceinline__ void seek(int j) {
-    vf<V> gr = (j == cur + 1) ? nxt : vload<V>(g + (size_t)j * C);
+    const vf<V> gr = vload<V>(g + j * C);  // L2-resident: the global feature is small
     cur = j;
-    if (j + 1 < Lg) nxt = vload<V>(g + (size_t)(j + 1) * C);  // prefetch the next global row
     if constexpr (KIND == SRC_INJECT_GATE) {
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -68,9 +72,8 @@ struct Src {
     }
   }
 
-  // value of row t given its raw load; exact zero outside [0, L) (conv zero padding)
   __device__ __forceinline__ vf<V> finalize(vf<V> r, int t) {
-    if (t < 0 || t >= L) return vzero<V>();
+    if (EDGE && (t < 0 || t >= L)) return vzero<V>();
     if constexpr (KIND == SRC_PLAIN) {
       return r;
     } else if constexpr (KIND == SRC_AFFINE) {
@@ -82,7 +85,7 @@ struct Src {
       for (int e = 0; e < V; ++e) r[e] = preluf_(fmaf(r[e], c0_[e], c1_[e]), slope);
       return r;
     } else {
-      const int j = nearest_src(t, gscale, Lg);
+      const int j = jtab[t - tab0];
       if (j != cur) seek(j);
       if constexpr (KIND == SRC_INJECT_GATE) {
 #pragma unroll
@@ -95,6 +98,16 @@ struct Src {
     }
   }
 };
+
+// tab[i] = nearest source row (in a tensor of `in_len` rows) of row clamp(t_first + i) of a tensor
+// that is `scale` = fl32(in_len / out_len) times shorter/longer; cooperative, caller synchronises.
+__device__ __forceinline__ void fill_nearest(int* tab, int n, int t_first, int out_len, float scale, int in_len) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int t = t_first + i;
+    t = t < 0 ? 0 : (t >= out_len ? out_len - 1 : t);
+    tab[i] = nearest_src(t, scale, in_len);
+  }
+}
 
 template <int V>
 __device__ __forceinline__ void load_taps(const float* __restrict__ w, int ch, vf<V> (&tap)[5]) {
@@ -123,16 +136,10 @@ __device__ __forceinline__ vf<V> conv5(const vf<V> (&tap)[5], const vf<V>& x0, c
 }
 
 // ----------------------------------------------------------------------------- dw k=5
-template <int KIND, int V, int NW, int S, int R, bool WRITE, bool STATS>
-__global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
-  const int b = blockIdx.z;
-  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
-  if (ch >= a.C) return;
-  const int t0 = blockIdx.x * rows_per_cta;
-  const int t1 = min(t0 + rows_per_cta, a.Lout);
-
-  Src<KIND, V> src;
-  src.init(a.src, b, ch, a.C);
+template <int KIND, int V, int NW, int S, int R, bool WRITE, bool STATS, bool EDGE>
+__device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0, int t1, const int* jtab, int tab0) {
+  Src<KIND, V, EDGE> src;
+  src.init(a.src, b, ch, a.C, jtab, tab0);
   vf<V> tap[NW][5], bias[NW], s1[NW], s2[NW];
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
@@ -141,7 +148,6 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
     s1[i] = vzero<V>();
     s2[i] = vzero<V>();
   }
-
   constexpr int NR = (R - 1) * S + 5;  // input rows feeding R outputs
   constexpr int CARRY = 5 - S;         // rows shared with the next chunk
   vf<V> xr[NR];
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
     for (int i = 0; i < R * S; ++i) xr[CARRY + i] = src.finalize(xr[CARRY + i], base + i);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (t + r < t1) {
+      if (!EDGE || t + r < t1) {
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
           vf<V> y = conv5<V>(tap[i], xr[r * S], xr[r * S + 1], xr[r * S + 2], xr[r * S + 3], xr[r * S + 4]);
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
               for (int e = 0; e < V; ++e) y[e] = fmaxf(y[e], 0.f);
             }
             if (a.round_out) vround_tf32<V>(y);
-            vstore<V>(outp + (size_t)(t + r) * a.C, y);
+            vstore<V>(outp + (t + r) * a.C, y);
           }
         }
       }
@@ -195,6 +201,26 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
       vred_add<V>(sp + a.C, s2[i]);
     }
   }
+}
+
+template <int KIND, int V, int NW, int S, int R, bool WRITE, bool STATS>
+__global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
+  extern __shared__ int jtab[];  // inject kinds: nearest rows of the input rows this CTA touches
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const int t0 = blockIdx.x * rows_per_cta;
+  const int t1 = min(t0 + rows_per_cta, a.Lout);
+  const int in_first = t0 * S - 2, in_last = (t1 - 1) * S + 2;
+  constexpr bool inj = KIND == SRC_INJECT_GATE || KIND == SRC_INJECT_ADD;
+  if constexpr (inj) {
+    fill_nearest(jtab, rows_per_cta * S + 4, in_first, a.src.L, a.src.gscale, a.src.Lg);
+    __syncthreads();
+  }
+  if (ch >= a.C) return;
+  // interior: whole chunks only, every input row inside the tensor
+  const bool interior = in_first >= 0 && in_last < a.src.L && (t1 - t0) % R == 0;
+  if (interior) dw5_body<KIND, V, NW, S, R, WRITE, STATS, false>(a, b, ch, t0, t1, jtab, in_first);
+  else dw5_body<KIND, V, NW, S, R, WRITE, STATS, true>(a, b, ch, t0, t1, jtab, in_first);
 }
 
 static void pick_tiling(int B, int L, int ctiles, int R, int* rows_per_cta, int* tiles) {
@@ -218,7 +244,8 @@ static int launch_dw5_t(const DwArgs& a, cudaStream_t st) {
   int rows, tiles;
   pick_tiling(a.B, a.Lout, ctiles, R, &rows, &tiles);
   dim3 grid(tiles, ctiles, a.B);
-  TD_LAUNCH((dw5_kernel<KIND, V, NW, S, R, WRITE, STATS>), grid, threads, 0, st, a, rows);
+  const size_t smem = (KIND == SRC_INJECT_GATE || KIND == SRC_INJECT_ADD) ? (size_t)(rows * S + 4) * sizeof(int) : 0;
+  TD_LAUNCH((dw5_kernel<KIND, V, NW, S, R, WRITE, STATS>), grid, threads, smem, st, a, rows);
   return 0;
 }
 
@@ -242,12 +269,13 @@ int launch_dw5(const DwArgs& a, cudaStream_t st) {
   TD_REQUIRE(a.nw == 1 || a.nw == 2, "dw5: nw=%d", a.nw);
   TD_REQUIRE(!(a.nw == 2 && a.out), "dw5: writing needs nw == 1");
   TD_REQUIRE(a.out || a.stats, "dw5: nothing to do");
+  TD_REQUIRE((long)a.src.L * a.C < (1L << 31) && (long)a.Lout * a.C < (1L << 31), "dw5: item too large for 32-bit offsets");
   if (a.nw == 1) {
     switch (a.kind) {
       case SRC_PLAIN: return launch_dw5_k<SRC_PLAIN, 4, 1>(a, st);
       case SRC_AFFINE: return launch_dw5_k<SRC_AFFINE, 4, 1>(a, st);
       case SRC_AFFINE_PRELU: return launch_dw5_k<SRC_AFFINE_PRELU, 4, 1>(a, st);
-      case SRC_INJECT_GATE: return launch_dw5_k<SRC_INJECT_GATE, 2, 1>(a, st);
+      case SRC_INJECT_GATE: return launch_dw5_k<SRC_INJECT_GATE, 4, 1>(a, st);
       case SRC_INJECT_ADD: return launch_dw5_k<SRC_INJECT_ADD, 4, 1>(a, st);
     }
   } else {
@@ -270,8 +298,8 @@ __global__ void dw_generic_kernel(SrcDesc sd, int C, int Lout, int ks, int strid
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const int t = blockIdx.x;
   if (ch >= C || t >= Lout) return;
-  Src<KIND, V> src;
-  src.init(sd, b, ch, C);
+  Src<KIND, V, true> src;
+  src.init(sd, b, ch, C, nullptr, 0);
   const int pad = (ks - 1) / 2;
   vf<V> acc = bias ? vload<V>(bias + ch) : vzero<V>();
   for (int j = 0; j < ks; ++j) {
@@ -300,27 +328,28 @@ int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int 
 }
 
 // ----------------------------------------------------------------------------- LA combine
-// UP   (Lg <= Ll): the global-branch conv is evaluated once per distinct source row of a chunk
-//                  and parked in a thread-private shared-memory column, then gathered per row.
-// DOWN (Lg >  Ll): only the first top-down step (reference quirk, TDANet_best.py:375-376);
-//                  evaluated per output row.
-template <int LKIND, int GKIND, int V, bool DOWN>
-__global__ void __launch_bounds__(256, 2) la_combine_kernel(LaArgs a, int rows_per_cta) {
-  constexpr int R = 8;
-  extern __shared__ float scratch[];  // [R][2][blockDim.x * V], column = this thread's channels
-  const int b = blockIdx.z;
-  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
-  if (ch >= a.C) return;
-  const int Ll = a.loc.L, Lg = a.glo.L;
-  const int t0 = blockIdx.x * rows_per_cta;
-  const int t1 = min(t0 + rows_per_cta, Ll);
-  const int colw = blockDim.x * V;
-  float* mine = scratch + threadIdx.x * V;
+// GC > 0 (Lg <= Ll): the global-branch convs are evaluated once per distinct source row of a chunk
+//          (at most GC of them) and parked in a thread-private shared-memory column, then gathered.
+// GC = 0 (Lg >  Ll): only the first top-down step (reference quirk, TDANet_best.py:375-376);
+//          evaluated per output row.
+struct LaSmem {
+  int* jc;   // [rows]      nearest global row of each output row
+  int* jl;   // [rows + 4]  local inject: nearest g row of each local input row
+  int* jg;   // [glo span]  global inject: nearest g row of each global input row
+  float* scratch;
+};
 
-  Src<LKIND, V> sl;
-  sl.init(a.loc, b, ch, a.C);
-  Src<GKIND, V> sg;
-  sg.init(a.glo, b, ch, a.C);
+template <int LKIND, int GKIND, int V, int GC, bool EDGE>
+__device__ __forceinline__ void la_body(const LaArgs& a, int b, int ch, int t0, int t1, const LaSmem& sm, int g_first) {
+  constexpr int R = 8;
+  const int Ll = a.loc.L;
+  const int colw = blockDim.x * V;
+  float* mine = sm.scratch + threadIdx.x * V;
+
+  Src<LKIND, V, EDGE> sl;
+  sl.init(a.loc, b, ch, a.C, sm.jl, t0 - 2);
+  Src<GKIND, V, EDGE> sg;
+  sg.init(a.glo, b, ch, a.C, sm.jg, g_first);
   vf<V> wl[5], wa[5], we[5];
   load_taps<V>(a.wl, ch, wl);
   load_taps<V>(a.wa, ch, wa);
@@ -338,23 +367,22 @@ __global__ void __launch_bounds__(256, 2) la_combine_kernel(LaArgs a, int rows_p
   float* outp = a.out + (size_t)b * Ll * a.C + ch;
 
   for (int t = t0; t < t1; t += R) {
-    // ---- issue every load of the chunk
 #pragma unroll
     for (int i = 0; i < 4; ++i) xr[i] = xr[R + i];
 #pragma unroll
     for (int i = 0; i < R; ++i) xr[4 + i] = sl.load_raw(t + 2 + i);
-    const int jlo = nearest_src(t, a.scale, Lg);
-    if constexpr (!DOWN) {
-      const int tl = min(t + R, t1) - 1;
-      const int nc = nearest_src(tl, a.scale, Lg) - jlo + 1;  // <= R because Lg <= Ll
-      vf<V> gr[R + 4];
+    const int jlo = sm.jc[t - t0];
+    if constexpr (GC > 0) {
+      // distinct centres of this chunk: jlo .. jc[last row]  (<= GC by construction)
+      const int tl = (EDGE ? min(t + R, t1) : t + R) - 1;
+      const int nc = sm.jc[tl - t0] - jlo + 1;
+      vf<V> gr[GC + 4];
 #pragma unroll
-      for (int i = 0; i < R + 4; ++i) gr[i] = (i < nc + 4) ? sg.load_raw(jlo - 2 + i) : vzero<V>();
+      for (int i = 0; i < GC + 4; ++i) gr[i] = sg.load_raw(jlo - 2 + i);
 #pragma unroll
-      for (int i = 0; i < R + 4; ++i)
-        if (i < nc + 4) gr[i] = sg.finalize(gr[i], jlo - 2 + i);
+      for (int i = 0; i < GC + 4; ++i) gr[i] = sg.finalize(gr[i], jlo - 2 + i);
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
+      for (int i = 0; i < GC; ++i) {
         if (i < nc) {
           vf<V> ca = conv5<V>(wa, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]);
           vf<V> ce = conv5<V>(we, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]);
@@ -363,21 +391,20 @@ __global__ void __launch_bounds__(256, 2) la_combine_kernel(LaArgs a, int rows_p
             ca[e] = sigmoidf_(fmaf(sA[e], ca[e], hA[e]));
             ce[e] = fmaf(sE[e], ce[e], hE[e]);
           }
-          vstore<V>(mine + (size_t)(2 * i) * colw, ca);
-          vstore<V>(mine + (size_t)(2 * i + 1) * colw, ce);
+          vstore<V>(mine + (2 * i) * colw, ca);
+          vstore<V>(mine + (2 * i + 1) * colw, ce);
         }
       }
     }
 #pragma unroll
     for (int i = 0; i < R; ++i) xr[4 + i] = sl.finalize(xr[4 + i], t + 2 + i);
-    // ---- combine
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (t + r < t1) {
+      if (!EDGE || t + r < t1) {
         vf<V> cl = conv5<V>(wl, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
         vf<V> ga, ge;
-        const int j = nearest_src(t + r, a.scale, Lg);
-        if constexpr (DOWN) {
+        const int j = sm.jc[t + r - t0];
+        if constexpr (GC == 0) {
           vf<V> g5[5];
 #pragma unroll
           for (int i = 0; i < 5; ++i) g5[i] = sg.load_raw(j - 2 + i);
@@ -391,12 +418,12 @@ __global__ void __launch_bounds__(256, 2) la_combine_kernel(LaArgs a, int rows_p
             ge[e] = fmaf(sE[e], ge[e], hE[e]);
           }
         } else {
-          const float* col = mine + (size_t)(2 * (j - jlo)) * colw;
+          const float* col = mine + (2 * (j - jlo)) * colw;
           if constexpr (V == 2) {
-            float2 u = *reinterpret_cast<const float2*>(col), w2 = *reinterpret_cast<const float2*>(col + colw);
+            const float2 u = *reinterpret_cast<const float2*>(col), w2 = *reinterpret_cast<const float2*>(col + colw);
             ga[0] = u.x; ga[1] = u.y; ge[0] = w2.x; ge[1] = w2.y;
           } else {
-            float4 u = *reinterpret_cast<const float4*>(col), w4 = *reinterpret_cast<const float4*>(col + colw);
+            const float4 u = *reinterpret_cast<const float4*>(col), w4 = *reinterpret_cast<const float4*>(col + colw);
             ga[0] = u.x; ga[1] = u.y; ga[2] = u.z; ga[3] = u.w;
             ge[0] = w4.x; ge[1] = w4.y; ge[2] = w4.z; ge[3] = w4.w;
           }
@@ -405,10 +432,39 @@ __global__ void __launch_bounds__(256, 2) la_combine_kernel(LaArgs a, int rows_p
 #pragma unroll
         for (int e = 0; e < V; ++e) y[e] = fmaf(fmaf(sL[e], cl[e], hL[e]), ga[e], ge[e]);
         if (a.round_out) vround_tf32<V>(y);
-        vstore<V>(outp + (size_t)(t + r) * a.C, y);
+        vstore<V>(outp + (t + r) * a.C, y);
       }
     }
   }
+}
+
+template <int LKIND, int GKIND, int V, int GC>
+__global__ void __launch_bounds__(256, 2) la_combine_kernel(LaArgs a, int rows_per_cta, int gspan) {
+  extern __shared__ __align__(16) float la_smem[];
+  constexpr int R = 8;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const int Ll = a.loc.L, Lg = a.glo.L;
+  const int t0 = blockIdx.x * rows_per_cta;
+  const int t1 = min(t0 + rows_per_cta, Ll);
+  LaSmem sm;
+  sm.scratch = la_smem;
+  sm.jc = reinterpret_cast<int*>(la_smem + (GC > 0 ? GC : 0) * 2 * blockDim.x * V);
+  sm.jl = sm.jc + rows_per_cta;
+  sm.jg = sm.jl + rows_per_cta + 4;
+  // first global row any output row of this CTA can touch (halo included)
+  const int g_first = nearest_src(t0, a.scale, Lg) - 2;
+  fill_nearest(sm.jc, rows_per_cta, t0, Ll, a.scale, Lg);
+  if constexpr (LKIND == SRC_INJECT_GATE || LKIND == SRC_INJECT_ADD)
+    fill_nearest(sm.jl, rows_per_cta + 4, t0 - 2, Ll, a.loc.gscale, a.loc.Lg);
+  if constexpr (GKIND == SRC_INJECT_GATE || GKIND == SRC_INJECT_ADD)
+    fill_nearest(sm.jg, gspan, g_first, Lg, a.glo.gscale, a.glo.Lg);
+  __syncthreads();
+  if (ch >= a.C) return;
+  const int g_last = nearest_src(t1 - 1, a.scale, Lg) + 2 + (GC > 0 ? GC : 0);
+  const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % R == 0 && g_first >= 0 && g_last < Lg;
+  if (interior) la_body<LKIND, GKIND, V, GC, false>(a, b, ch, t0, t1, sm, g_first);
+  else la_body<LKIND, GKIND, V, GC, true>(a, b, ch, t0, t1, sm, g_first);
 }
 
 template <int LKIND, int GKIND>
@@ -421,17 +477,23 @@ static int launch_la_t(const LaArgs& a, cudaStream_t st) {
   int rows, tiles;
   pick_tiling(a.B, a.loc.L, ctiles, 8, &rows, &tiles);
   dim3 grid(tiles, ctiles, a.B);
-  const size_t smem = (size_t)8 * 2 * threads * V * sizeof(float);
+  // rows of the global tensor one CTA can touch: its rows map to <= rows*scale + 1 centres, + halo
+  const int gspan = (int)((double)rows * a.glo.L / a.loc.L) + 16;
+  const size_t tabs = (size_t)(2 * rows + 4 + gspan) * sizeof(int);
   if (a.glo.L > a.loc.L) {
-    TD_LAUNCH((la_combine_kernel<LKIND, GKIND, V, true>), grid, threads, 0, st, a, rows);
+    TD_LAUNCH((la_combine_kernel<LKIND, GKIND, V, 0>), grid, threads, tabs, st, a, rows, gspan);
+  } else if (7.0 * a.glo.L / a.loc.L <= 3.99) {
+    // ratio >= ~2 (every up-sampling step of the U-Net): 8 output rows see at most 5 centres
+    TD_LAUNCH((la_combine_kernel<LKIND, GKIND, V, 5>), grid, threads, tabs + (size_t)5 * 2 * threads * V * sizeof(float), st, a, rows, gspan);
   } else {
-    TD_LAUNCH((la_combine_kernel<LKIND, GKIND, V, false>), grid, threads, smem, st, a, rows);
+    TD_LAUNCH((la_combine_kernel<LKIND, GKIND, V, 8>), grid, threads, tabs + (size_t)8 * 2 * threads * V * sizeof(float), st, a, rows, gspan);
   }
   return 0;
 }
 
 int launch_la_combine(const LaArgs& a, cudaStream_t st) {
   TD_REQUIRE(a.C % 4 == 0, "la: C=%d must be a multiple of 4", a.C);
+  TD_REQUIRE((long)a.loc.L * a.C < (1L << 31) && (long)a.glo.L * a.C < (1L << 31), "la: item too large for 32-bit offsets");
   if (a.lkind == SRC_INJECT_GATE && a.gkind == SRC_INJECT_GATE) return launch_la_t<SRC_INJECT_GATE, SRC_INJECT_GATE>(a, st);
   if (a.lkind == SRC_INJECT_GATE && a.gkind == SRC_PLAIN) return launch_la_t<SRC_INJECT_GATE, SRC_PLAIN>(a, st);
   if (a.lkind == SRC_INJECT_ADD && a.gkind == SRC_INJECT_ADD) return launch_la_t<SRC_INJECT_ADD, SRC_INJECT_ADD>(a, st);

@@ -88,15 +88,16 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a, int tiles_pe
   Epilogue ep(a, b);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
-    if (r >= a.L) continue;
+  for (int jh = 0; jh < 2; ++jh) {
+    const int n = n0 + jh * 64 + tx * 4;
+    if (n >= a.N) continue;
+    ep.cols(n);
 #pragma unroll
-    for (int jh = 0; jh < 2; ++jh) {
-      const int n = n0 + jh * 64 + tx * 4;
-      if (n >= a.N) continue;
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+      if (r >= a.L) continue;
       float v[4] = {acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]};
-      ep.apply4(r, n, v, s1, s2);
+      ep.row(r, v, s1, s2);
     }
   }
   if (a.stats) {

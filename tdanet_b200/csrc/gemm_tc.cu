@@ -6,9 +6,11 @@
 // core reads fp32 bits as TF32.  Persistent, warp-specialised CTA (one per SM):
 //   warp 0      TMA producer        (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> bias / residual / statistics
-//               -> st.global.  The accumulator is double-buffered in TMEM so the epilogue of tile i
-//               overlaps the loads and MMAs of tile i+1.
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time (thread = row), transposed
+//               through a per-warp shared-memory patch so that 8 lanes hold the 32 columns of one
+//               row, then bias / residual / statistics and coalesced 128-bit st.global.  The
+//               accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the loads
+//               and MMAs of tile i+1.
 // A-tiles are 128 rows of ONE batch item (3-D tensor map, rows past the item are zero-filled by TMA)
 // so that the GlobLN statistics of the epilogue never straddle items.
 //
@@ -16,14 +18,15 @@
 //                 TDANET_GEMM_TF32X3: W used as is (tensor core truncates = W_hi) plus a second pass
 //                                     over W_lo = W - trunc(W); A is taken as stored in both.
 #include "kernels.h"
-#include "gemm_epilogue.cuh"
 #include <cuda.h>
 
 namespace td {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // fp32 elements = one 128-byte swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
+constexpr int TC_PATCH = 32 * 36;  // floats per epilogue warp: 32 rows x (32 + 4 pad) columns
 
 // ----------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -157,11 +160,16 @@ struct TcParams {
   uint32_t idesc;
 };
 
+// EPI: 0 = D = acc + bias                                   (proj_1x1, in/out_proj, fc1, fc2, pw_conv)
+//      1 = y = acc + bias + resid; D = prelu(cw*(mix + y) + cb)  (res_conv + concat_block of the next block)
+//      2 = D = acc + bias + resid                              (res_conv of the last block)
+// STATS: per-item sum / sum of squares of D (GlobLN statistics of the consumer), double atomics.
+template <int EPI, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ CUtensorMap mapW2, GemmArgs a, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages] x { A 16 KB | W BN*128 B | (W_lo) } then barriers
+  // carve: [stages] x { A 16 KB | W BN*128 B | (W_lo) } then barriers, then the epilogue patches
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = TC_BM * TC_BK * 4;
   const uint32_t w_bytes = (uint32_t)p.BN * TC_BK * 4;
@@ -172,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* acc_full = bars + 2 * p.stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* patches = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = a.K / TC_BK;
@@ -185,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full + s, 1);
-      mbar_init(acc_empty + s, 4);  // one arrive per epilogue warp
+      mbar_init(acc_empty + s, TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -249,38 +258,88 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================================================================== epilogue (4 warps)
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32) are visible to this warp
+    // ===================================================================== epilogue (8 warps)
+    // Two warps per TMEM lane quarter (a warp can only read lanes 32*(warp%4)..+31); the pair splits
+    // the 32-column chunks of the tile even/odd.  Two warps per scheduler also hide each other's
+    // instruction-fetch and shared-memory latencies.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float* patch = patches + (warp - 2) * TC_PATCH;
+    const int prow = lane >> 3, pcol = (lane & 7) * 4;  // transposed role: row within a group of 4, column group
+    const int N = a.N;
+    float cslope = 0.f;
+    if constexpr (EPI == 1) cslope = __ldg(a.cslope);
     for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
       const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
       const int b = mt / p.tiles_m, r0 = (mt % p.tiles_m) * TC_BM, n0 = nt * p.BN;
-      const int r = r0 + quarter * 32 + lane;
-      const bool row_ok = r < a.L;
-      Epilogue ep(a, b);
+      const int rbase = r0 + quarter * 32;
+      const size_t item = (size_t)b * a.L;
       float s1 = 0.f, s2 = 0.f;
       mbar_wait(acc_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
         float v[32];
         const int ncol = min(32, p.BN - c0);  // BN is a multiple of 16
         if (ncol == 32) tc_ld32(taddr + c0, v); else tc_ld16(taddr + c0, v);
-        if (row_ok) {
+        // thread = row  ->  patch[row][col]; the 36-float row pitch keeps both sides conflict-free
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncol) {
-              float q[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-              ep.apply4(r, n0 + c0 + j, q, s1, s2);
+        for (int j = 0; j < 32; j += 4)
+          if (j < ncol) *reinterpret_cast<float4*>(patch + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        if (pcol < ncol) {
+          const int n = n0 + c0 + pcol;
+          const float4 bias = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 cw = bias, cb = bias;
+          if constexpr (EPI == 1) {
+            cw = __ldg(reinterpret_cast<const float4*>(a.cw + n));
+            cb = __ldg(reinterpret_cast<const float4*>(a.cb + n));
+          }
+          // row of this lane in iteration i: rbase + 4*i + prow; 8 lanes cover the 128 bytes of a row
+          const int rfirst = rbase + prow;
+          const size_t off0 = (item + rfirst) * N + n;
+          float4 res[8], mix[8];
+          if constexpr (EPI != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool ok = rfirst + 4 * i < a.L;
+              res[i] = ok ? *reinterpret_cast<const float4*>(a.resid + off0 + (size_t)(4 * i) * N) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if constexpr (EPI == 1)
+                mix[i] = ok ? *reinterpret_cast<const float4*>(a.mix + off0 + (size_t)(4 * i) * N) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (rfirst + 4 * i < a.L) {
+              float4 t = *reinterpret_cast<const float4*>(patch + (4 * i + prow) * 36 + pcol);
+              t.x += bias.x; t.y += bias.y; t.z += bias.z; t.w += bias.w;
+              if constexpr (EPI != 0) {
+                // res_conv(expanded) + residual (TDANet_best.py:380)
+                t.x += res[i].x; t.y += res[i].y; t.z += res[i].z; t.w += res[i].w;
+              }
+              if constexpr (EPI == 1) {
+                // concat_block(mixture + x) = PReLU(w_c*(mixture + x) + b_c) (TDANet_best.py:388-398)
+                t.x = preluf_(fmaf(cw.x, mix[i].x + t.x, cb.x), cslope);
+                t.y = preluf_(fmaf(cw.y, mix[i].y + t.y, cb.y), cslope);
+                t.z = preluf_(fmaf(cw.z, mix[i].z + t.z, cb.z), cslope);
+                t.w = preluf_(fmaf(cw.w, mix[i].w + t.w, cb.w), cslope);
+              }
+              if constexpr (STATS) {
+                s1 += (t.x + t.y) + (t.z + t.w);
+                s2 = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, s2))));
+              }
+              *reinterpret_cast<float4*>(a.D + off0 + (size_t)(4 * i) * N) = t;
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + acc);
-      if (a.stats) {
+      if constexpr (STATS) {
         const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
         if (lane == 0) {
           atomicAdd(a.stats + 2 * b, d1);
@@ -337,10 +396,11 @@ static int encode_map(CUtensorMap* m, const float* ptr, int rank, const uint64_t
 }
 
 bool gemm_tc_supported(const GemmArgs& a) {
-  if (a.K % TC_BK != 0 || a.N % 16 != 0 || a.a_slope != nullptr) return false;
+  if (a.K % TC_BK != 0 || a.N % 16 != 0 || a.a_slope != nullptr || a.epi == EPI_MASK) return false;
   if (a.N > 128 && a.N % 128 != 0) return false;
-  if (((uintptr_t)a.A & 15) || ((uintptr_t)a.W & 15)) return false;
-  return true;
+  const uintptr_t all = (uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.D | (uintptr_t)a.bias | (uintptr_t)a.resid |
+                        (uintptr_t)a.mix | (uintptr_t)a.cw | (uintptr_t)a.cb;
+  return (all & 15) == 0;
 }
 
 int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
@@ -349,7 +409,6 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   if (!gemm_tc_supported(a)) return launch_gemm_simt(a, st);
   TD_REQUIRE(a.W_aux != nullptr, "gemm_tc: prepared weights missing");
   static int num_sms = 0;
-  static bool attr_set = false;
   if (!num_sms) {
     int dev = 0;
     TD_CUDA(cudaGetDevice(&dev));
@@ -366,12 +425,12 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   p.tmem_cols = cols;
   p.idesc = make_idesc(TC_BM, p.BN);
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 4 + (size_t)p.BN * TC_BK * 4 * p.nsplit;
-  const size_t budget = 200 * 1024;
+  const size_t budget = 184 * 1024;
   int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(TDANET_EUNSUPPORTED, "gemm_tc: tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + stages * stage_bytes + 256 + TC_EPI_WARPS * TC_PATCH * sizeof(float);
 
   CUtensorMap mapA, mapW, mapW2;
   const uint64_t dA[3] = {(uint64_t)a.K, (uint64_t)a.L, (uint64_t)a.B};
@@ -383,12 +442,22 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   if (int e = encode_map(&mapW, p.nsplit == 2 ? a.W : a.W_aux, 2, dW, bW)) return e;
   if (int e = encode_map(&mapW2, a.W_aux, 2, dW, bW)) return e;
 
-  if (!attr_set) {
-    TD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
   const int grid = p.total < num_sms ? p.total : num_sms;
-  TD_LAUNCH(gemm_tc_kernel, grid, TC_THREADS, smem, st, mapA, mapW, mapW2, a, p);
+  const int epi = a.epi == EPI_RESIDUAL ? (a.last ? 2 : 1) : 0;
+#define TD_TC_LAUNCH(E, S)                                                                                     \
+  do {                                                                                                         \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set) {                                                                                           \
+      TD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<E, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    TD_LAUNCH((gemm_tc_kernel<E, S>), grid, TC_THREADS, smem, st, mapA, mapW, mapW2, a, p);                     \
+  } while (0)
+  if (epi == 0 && a.stats) TD_TC_LAUNCH(0, true);
+  else if (epi == 0) TD_TC_LAUNCH(0, false);
+  else if (epi == 1) TD_TC_LAUNCH(1, false);
+  else TD_TC_LAUNCH(2, false);
+#undef TD_TC_LAUNCH
   return 0;
 }
 
