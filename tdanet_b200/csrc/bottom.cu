@@ -29,8 +29,8 @@ __global__ void pool_sum_kernel(PoolArgs a) {
       for (int e = 0; e < V; ++e) s[e] += v[e];
     }
     const float inv = 1.f / (float)(hi - lo);
-    const float* cf = a.coef[k] + (size_t)b * 2 * a.C + ch;
-    vf<V> sc = vload<V>(cf), sh = vload<V>(cf + a.C);
+    vf<V> sc, sh;
+    norm_coef<V>(a.norm[k], b, ch, sc, sh);
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e] += fmaf(s[e] * inv, sc[e], sh[e]);
   }
@@ -53,8 +53,8 @@ __global__ void affine_sum_kernel(PoolArgs a) {
   vf<V> acc = vzero<V>();
   for (int k = 0; k < a.n; ++k) {
     vf<V> v = vload<V>(a.x[k] + ((size_t)b * a.Lb + j) * a.C + ch);
-    const float* cf = a.coef[k] + (size_t)b * 2 * a.C + ch;
-    vf<V> sc = vload<V>(cf), sh = vload<V>(cf + a.C);
+    vf<V> sc, sh;
+    norm_coef<V>(a.norm[k], b, ch, sc, sh);
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e] += fmaf(v[e], sc[e], sh[e]);
   }
@@ -180,7 +180,7 @@ int launch_ln_residual(const float* a, const float* xin, const float* resid, con
 
 // ----------------------------------------------------------------------------- affine glue
 template <bool RES, bool STATS>
-__global__ void affine_kernel(const float* __restrict__ x, const float* __restrict__ coef,
+__global__ void affine_kernel(const float* __restrict__ x, NormRef norm,
                               const float* __restrict__ resid, float* __restrict__ y,
                               float* __restrict__ chstats, int L, int C, int rows_per_cta) {
   constexpr int V = 4;
@@ -188,8 +188,8 @@ __global__ void affine_kernel(const float* __restrict__ x, const float* __restri
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   if (ch >= C) return;
   const int t0 = blockIdx.x * rows_per_cta, t1 = min(t0 + rows_per_cta, L);
-  const float* cf = coef + (size_t)b * 2 * C + ch;
-  const vf<V> sc = vload<V>(cf), sh = vload<V>(cf + C);
+  vf<V> sc, sh;
+  norm_coef<V>(norm, b, ch, sc, sh);
   vf<V> s1 = vzero<V>(), s2 = vzero<V>();
   for (int t = t0; t < t1; ++t) {
     const size_t off = ((size_t)b * L + t) * C + ch;
@@ -217,26 +217,26 @@ __global__ void affine_kernel(const float* __restrict__ x, const float* __restri
   }
 }
 
-int launch_affine_residual(const float* x, const float* coef, const float* resid, float* y,
+int launch_affine_residual(const float* x, const NormRef& norm, const float* resid, float* y,
                            float* chstats, int B, int L, int C, cudaStream_t st) {
   TD_REQUIRE(C % 4 == 0, "affine_residual: C=%d", C);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
   const int rows = 8;
   dim3 grid(cdiv(L, rows), cdiv(C / 4, threads), B);
   if (chstats) {
-    TD_LAUNCH((affine_kernel<true, true>), grid, threads, 0, st, x, coef, resid, y, chstats, L, C, rows);
+    TD_LAUNCH((affine_kernel<true, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows);
   } else {
-    TD_LAUNCH((affine_kernel<true, false>), grid, threads, 0, st, x, coef, resid, y, chstats, L, C, rows);
+    TD_LAUNCH((affine_kernel<true, false>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows);
   }
   return 0;
 }
 
-int launch_affine(const float* x, const float* coef, float* y, int B, int L, int C, cudaStream_t st) {
+int launch_affine(const float* x, const NormRef& norm, float* y, int B, int L, int C, cudaStream_t st) {
   TD_REQUIRE(C % 4 == 0, "affine: C=%d", C);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
   const int rows = 16;
   dim3 grid(cdiv(L, rows), cdiv(C / 4, threads), B);
-  TD_LAUNCH((affine_kernel<false, false>), grid, threads, 0, st, x, coef, nullptr, y, nullptr, L, C, rows);
+  TD_LAUNCH((affine_kernel<false, false>), grid, threads, 0, st, x, norm, nullptr, y, nullptr, L, C, rows);
   return 0;
 }
 

@@ -152,6 +152,40 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* sh) {
   for (int i = 0; i < nw; ++i) { a += sh[i]; b += sh[32 + i]; }
 }
 
+// A GlobLN (TDANet_best.py:47-64) whose per-item statistics a producer kernel has accumulated:
+// stats[b*item_stride + {0,1}] = sum, sum of squares (double) over `count` elements of item b.
+// Consumers fold the normalisation into one FMA per element: y = x*scale_c + shift_c with
+//   scale_c = gamma_c * r_b,  shift_c = beta_c - gamma_c * mu_b * r_b,  r_b = 1/sqrt(var_b + 1e-8).
+struct NormRef {
+  const double* stats;
+  int item_stride;  // doubles between items
+  double count;
+  const float* gamma;
+  const float* beta;
+};
+
+__device__ __forceinline__ void norm_moments(const NormRef& n, int b, float& r, float& mur) {
+  const double s = n.stats[(size_t)b * n.item_stride], ss = n.stats[(size_t)b * n.item_stride + 1];
+  const double mu = s / n.count;
+  double var = ss / n.count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const double rd = 1.0 / sqrt(var + (double)kEpsGLN);
+  r = (float)rd;
+  mur = (float)(mu * rd);
+}
+
+template <int V>
+__device__ __forceinline__ void norm_coef(const NormRef& n, int b, int ch, vf<V>& scale, vf<V>& shift) {
+  float r, mur;
+  norm_moments(n, b, r, mur);
+  const vf<V> g = vload<V>(n.gamma + ch), be = vload<V>(n.beta + ch);
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    scale[e] = g[e] * r;
+    shift[e] = fmaf(-g[e], mur, be[e]);
+  }
+}
+
 // index of the source row for F.interpolate(mode="nearest"): min(floor(dst * fl32(in/out)), in-1)
 __device__ __forceinline__ int nearest_src(int dst, float scale, int in_len) {
   int s = (int)floorf((float)dst * scale);

@@ -32,17 +32,16 @@ struct Src {
     C = C_;
     L = d.L;
     x = d.x + (size_t)b * d.L * C_ + ch;
-    if constexpr (KIND != SRC_PLAIN) {
-      constexpr int planes = (KIND == SRC_INJECT_GATE) ? 6 : 2;
-      const float* cf = d.coef + (size_t)b * planes * C_ + ch;
+    if constexpr (KIND == SRC_INJECT_GATE) {
+      const float* cf = d.coef + (size_t)b * 6 * C_ + ch;
       c0_ = vload<V>(cf);
       c1_ = vload<V>(cf + C_);
-      if constexpr (KIND == SRC_INJECT_GATE) {
-        c2_ = vload<V>(cf + 2 * C_);
-        c3_ = vload<V>(cf + 3 * C_);
-        c4_ = vload<V>(cf + 4 * C_);
-        c5_ = vload<V>(cf + 5 * C_);
-      }
+      c2_ = vload<V>(cf + 2 * C_);
+      c3_ = vload<V>(cf + 3 * C_);
+      c4_ = vload<V>(cf + 4 * C_);
+      c5_ = vload<V>(cf + 5 * C_);
+    } else if constexpr (KIND != SRC_PLAIN) {
+      norm_coef<V>(d.norm, b, ch, c0_, c1_);
     }
     if constexpr (KIND == SRC_AFFINE_PRELU) slope = __ldg(d.slope);
     if constexpr (kInject) {
@@ -137,7 +136,8 @@ __device__ __forceinline__ vf<V> conv5(const vf<V> (&tap)[5], const vf<V>& x0, c
 
 // ----------------------------------------------------------------------------- dw k=5
 template <int KIND, int V, int NW, int S, int R, bool WRITE, bool STATS, bool EDGE>
-__device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0, int t1, const int* jtab, int tab0) {
+__device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0, int t1, const int* jtab, int tab0,
+                                         float (&tot1)[NW], float (&tot2)[NW]) {
   Src<KIND, V, EDGE> src;
   src.init(a.src, b, ch, a.C, jtab, tab0);
   vf<V> tap[NW][5], bias[NW], s1[NW], s2[NW];
@@ -196,9 +196,31 @@ __device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0,
   if constexpr (STATS) {
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-      float* sp = a.stats + ((size_t)(b * NW + i) * 2) * a.C + ch;
-      vred_add<V>(sp, s1[i]);
-      vred_add<V>(sp + a.C, s2[i]);
+      if (a.chstats) {
+        float* sp = a.chstats + ((size_t)(b * NW + i) * 2) * a.C + ch;
+        vred_add<V>(sp, s1[i]);
+        vred_add<V>(sp + a.C, s2[i]);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        tot1[i] += s1[i][e];
+        tot2[i] += s2[i][e];
+      }
+    }
+  }
+}
+
+// per-item totals: block reduction, then one pair of double atomics per CTA
+template <int NW>
+__device__ __forceinline__ void flush_item_stats(double* stats, int b, const float (&tot1)[NW], const float (&tot2)[NW],
+                                                 double* red) {
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    double d1 = tot1[i], d2 = tot2[i];
+    block_sum2(d1, d2, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(stats + ((size_t)b * NW + i) * 2, d1);
+      atomicAdd(stats + ((size_t)b * NW + i) * 2 + 1, d2);
     }
   }
 }
@@ -206,6 +228,7 @@ __device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0,
 template <int KIND, int V, int NW, int S, int R, bool WRITE, bool STATS>
 __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
   extern __shared__ int jtab[];  // inject kinds: nearest rows of the input rows this CTA touches
+  __shared__ double red[64];
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const int t0 = blockIdx.x * rows_per_cta;
@@ -216,11 +239,16 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
     fill_nearest(jtab, rows_per_cta * S + 4, in_first, a.src.L, a.src.gscale, a.src.Lg);
     __syncthreads();
   }
-  if (ch >= a.C) return;
-  // interior: whole chunks only, every input row inside the tensor
-  const bool interior = in_first >= 0 && in_last < a.src.L && (t1 - t0) % R == 0;
-  if (interior) dw5_body<KIND, V, NW, S, R, WRITE, STATS, false>(a, b, ch, t0, t1, jtab, in_first);
-  else dw5_body<KIND, V, NW, S, R, WRITE, STATS, true>(a, b, ch, t0, t1, jtab, in_first);
+  float tot1[NW], tot2[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) tot1[i] = tot2[i] = 0.f;
+  if (ch < a.C) {
+    // interior: whole chunks only, every input row inside the tensor
+    const bool interior = in_first >= 0 && in_last < a.src.L && (t1 - t0) % R == 0;
+    if (interior) dw5_body<KIND, V, NW, S, R, WRITE, STATS, false>(a, b, ch, t0, t1, jtab, in_first, tot1, tot2);
+    else dw5_body<KIND, V, NW, S, R, WRITE, STATS, true>(a, b, ch, t0, t1, jtab, in_first, tot1, tot2);
+  }
+  if constexpr (STATS) flush_item_stats<NW>(a.stats, b, tot1, tot2, red);
 }
 
 static void pick_tiling(int B, int L, int ctiles, int R, int* rows_per_cta, int* tiles) {
@@ -354,9 +382,10 @@ __device__ __forceinline__ void la_body(const LaArgs& a, int b, int ch, int t0, 
   load_taps<V>(a.wl, ch, wl);
   load_taps<V>(a.wa, ch, wa);
   load_taps<V>(a.we, ch, we);
-  const float* cf = a.coef + (size_t)b * 6 * a.C + ch;
-  const vf<V> sL = vload<V>(cf), hL = vload<V>(cf + a.C), sA = vload<V>(cf + 2 * a.C),
-              hA = vload<V>(cf + 3 * a.C), sE = vload<V>(cf + 4 * a.C), hE = vload<V>(cf + 5 * a.C);
+  vf<V> sL, hL, sA, hA, sE, hE;
+  norm_coef<V>(a.nL, b, ch, sL, hL);
+  norm_coef<V>(a.nA, b, ch, sA, hA);
+  norm_coef<V>(a.nE, b, ch, sE, hE);
 
   vf<V> xr[R + 4];
 #pragma unroll
@@ -467,6 +496,410 @@ __global__ void __launch_bounds__(256, 2) la_combine_kernel(LaArgs a, int rows_p
   else la_body<LKIND, GKIND, V, GC, true>(a, b, ch, t0, t1, sm, g_first);
 }
 
+// ----------------------------------------------------------------------------- injection on staged rows
+// x_fused[k][t] recomputed from a raw spp_dw[k] row and the row of the global feature it sees:
+//   BEST : (al*x + bl) * sigmoid(aa*g + ba) + (ae*g + be)   (loc_glo_fus, closed-form GlobLNs)
+//   FORK : GlobLN(x) + g
+// The gate / offset are cached while consecutive rows map to the same global row.
+template <int KIND, int V>
+struct Injector {
+  vf<V> al, bl, aa, ba, ae, be, sg, eg;
+  int cur;
+  __device__ __forceinline__ void init(const SrcDesc& d, int b, int ch, int C) {
+    cur = -1;
+    if constexpr (KIND == SRC_INJECT_GATE) {
+      const float* cf = d.coef + (size_t)b * 6 * C + ch;
+      al = vload<V>(cf); bl = vload<V>(cf + C); aa = vload<V>(cf + 2 * C); ba = vload<V>(cf + 3 * C);
+      ae = vload<V>(cf + 4 * C); be = vload<V>(cf + 5 * C);
+    } else {
+      norm_coef<V>(d.norm, b, ch, al, bl);
+    }
+  }
+  __device__ __forceinline__ vf<V> apply(vf<V> raw, const vf<V>& grow, int j) {
+    if (j != cur) {
+      cur = j;
+      if constexpr (KIND == SRC_INJECT_GATE) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          sg[e] = sigmoidf_(fmaf(aa[e], grow[e], ba[e]));
+          eg[e] = fmaf(ae[e], grow[e], be[e]);
+        }
+      } else {
+        eg = grow;
+      }
+    }
+    if constexpr (KIND == SRC_INJECT_GATE) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) raw[e] = fmaf(fmaf(raw[e], al[e], bl[e]), sg[e], eg[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) raw[e] = fmaf(raw[e], al[e], bl[e]) + eg[e];
+    }
+    return raw;
+  }
+};
+
+// ----------------------------------------------------------------------------- LA combine, streaming
+// The same arithmetic as la_combine_kernel for the up-sampling steps (Lg <= Ll/2-ish, plain global
+// operand), restructured for memory-level parallelism that does not depend on occupancy: a thread
+// owns 4 channels and prefetches the rows of the NEXT chunk (8 local rows, 9 global rows, 3 rows of
+// the injected global feature) with cp.async into a two-stage ring of thread-private shared-memory
+// columns while it computes the current chunk out of the other stage.  No block-level
+// synchronisation after the index tables are built.
+constexpr int SR = 8;             // output rows per chunk
+constexpr int SGC = 5;            // distinct global centres per chunk (ratio >= 2)
+constexpr int SGR = SGC + 4;      // global rows per chunk (centres + halo)
+constexpr int SGG = 3;            // rows of the injected feature per chunk (ratio to it >= 4)
+constexpr int SROWS = SR + SGR + SGG;
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ vf<4> lds4(const float* p) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  vf<4> r;
+  r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+  return r;
+}
+
+template <int LKIND, bool EDGE>
+__device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, int t0, int t1, float* ring,
+                                               float* scratch, const int* jc, const int* jl) {
+  constexpr int V = 4;
+  const int Ll = a.loc.L, Lg = a.glo.L, Lgg = a.loc.Lg, C = a.C;
+  const int colw = blockDim.x * V;
+  const float* xl = a.loc.x + (size_t)b * Ll * C + ch;
+  const float* xg = a.glo.x + (size_t)b * Lg * C + ch;
+  const float* gg = a.loc.g + (size_t)b * Lgg * C + ch;
+  float* outp = a.out + (size_t)b * Ll * C + ch;
+  float* mine = scratch + threadIdx.x * V;
+  float* col = ring + threadIdx.x * V;
+
+  // per-channel constants
+  Injector<LKIND, V> inj;
+  inj.init(a.loc, b, ch, C);
+  auto inject = [&](vf<V> raw, const vf<V>& grow, int j) { return inj.apply(raw, grow, j); };
+  vf<V> wl[5], wa[5], we[5];
+  load_taps<V>(a.wl, ch, wl);
+  load_taps<V>(a.wa, ch, wa);
+  load_taps<V>(a.we, ch, we);
+  vf<V> sL, hL, sA, hA, sE, hE;
+  norm_coef<V>(a.nL, b, ch, sL, hL);
+  norm_coef<V>(a.nA, b, ch, sA, hA);
+  norm_coef<V>(a.nE, b, ch, sE, hE);
+
+  auto issue = [&](int k) {
+    float* st = col + (size_t)(k & 1) * SROWS * colw;
+    const int t = t0 + k * SR;
+#pragma unroll
+    for (int i = 0; i < SR; ++i) {
+      const int row = t + 2 + i;
+      const bool ok = !EDGE || row < Ll;
+      cp_async16(st + i * colw, xl + (ok ? row : 0) * C, ok);
+    }
+    const int jlo = jc[t - t0];
+#pragma unroll
+    for (int i = 0; i < SGR; ++i) {
+      const int row = jlo - 2 + i;
+      const bool ok = !EDGE || (row >= 0 && row < Lg);
+      cp_async16(st + (SR + i) * colw, xg + (ok ? row : 0) * C, ok);
+    }
+    const int j0 = jl[t - t0 + 4];
+#pragma unroll
+    for (int i = 0; i < SGG; ++i) {
+      const int row = j0 + i;
+      const bool ok = row < Lgg;
+      cp_async16(st + (SR + SGR + i) * colw, gg + (ok ? row : 0) * C, ok);
+    }
+  };
+
+  // rows t0-2 .. t0+1 of the local operand: plain loads (once per CTA)
+  vf<V> xr[SR + 4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 - 2 + i;
+    if (EDGE && (t < 0 || t >= Ll)) {
+      xr[SR + i] = vzero<V>();
+    } else {
+      const int j = jl[i];
+      xr[SR + i] = inject(vload<V>(xl + t * C), vload<V>(gg + j * C), j);
+    }
+  }
+
+  const int nchunks = (t1 - t0 + SR - 1) / SR;
+  issue(0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int k = 0; k < nchunks; ++k) {
+    if (k + 1 < nchunks) issue(k + 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const float* st = col + (size_t)(k & 1) * SROWS * colw;
+    const int t = t0 + k * SR;
+    const int jlo = jc[t - t0];
+    {
+      // global branch: one evaluation per distinct centre of the chunk, parked in the scratch column
+      const int tl = (EDGE ? min(t + SR, t1) : t + SR) - 1;
+      const int nc = jc[tl - t0] - jlo + 1;
+      vf<V> gr[SGR];
+#pragma unroll
+      for (int i = 0; i < SGR; ++i) gr[i] = lds4(st + (SR + i) * colw);
+#pragma unroll
+      for (int i = 0; i < SGC; ++i) {
+        if (i < nc) {
+          vf<V> ca = conv5<V>(wa, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]);
+          vf<V> ce = conv5<V>(we, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]);
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            ca[e] = sigmoidf_(fmaf(sA[e], ca[e], hA[e]));
+            ce[e] = fmaf(sE[e], ce[e], hE[e]);
+          }
+          vstore<V>(mine + (2 * i) * colw, ca);
+          vstore<V>(mine + (2 * i + 1) * colw, ce);
+        }
+      }
+    }
+    // local operand: injection recomputed from the staged raw rows
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xr[i] = xr[SR + i];
+    const int j0 = jl[t - t0 + 4];
+#pragma unroll
+    for (int i = 0; i < SR; ++i) {
+      if (EDGE && t + 2 + i >= Ll) {
+        xr[4 + i] = vzero<V>();
+      } else {
+        const int j = jl[t - t0 + 4 + i];
+        xr[4 + i] = inject(lds4(st + i * colw), lds4(st + (SR + SGR + (j - j0)) * colw), j);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SR; ++r) {
+      if (!EDGE || t + r < t1) {
+        const vf<V> cl = conv5<V>(wl, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
+        const int j = jc[t + r - t0];
+        const vf<V> ga = lds4(mine + (2 * (j - jlo)) * colw), ge = lds4(mine + (2 * (j - jlo) + 1) * colw);
+        vf<V> y;
+#pragma unroll
+        for (int e = 0; e < V; ++e) y[e] = fmaf(fmaf(sL[e], cl[e], hL[e]), ga[e], ge[e]);
+        if (a.round_out) vround_tf32<V>(y);
+        vstore<V>(outp + (t + r) * C, y);
+      }
+    }
+  }
+}
+
+template <int LKIND>
+__global__ void __launch_bounds__(128, 2) la_stream_kernel(LaArgs a, int rows_per_cta) {
+  extern __shared__ __align__(16) float la_smem[];
+  constexpr int V = 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const int Ll = a.loc.L, Lg = a.glo.L;
+  const int t0 = blockIdx.x * rows_per_cta;
+  const int t1 = min(t0 + rows_per_cta, Ll);
+  const int colw = blockDim.x * V;
+  float* ring = la_smem;
+  float* scratch = ring + 2 * SROWS * colw;
+  int* jc = reinterpret_cast<int*>(scratch + 2 * SGC * colw);
+  int* jl = jc + rows_per_cta;
+  fill_nearest(jc, rows_per_cta, t0, Ll, a.scale, Lg);
+  fill_nearest(jl, rows_per_cta + 4, t0 - 2, Ll, a.loc.gscale, a.loc.Lg);
+  __syncthreads();
+  if (ch >= a.C) return;
+  const int g_first = nearest_src(t0, a.scale, Lg) - 2;
+  const int g_last = nearest_src(t1 - 1, a.scale, Lg) + SGR;
+  const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0 && g_first >= 0 && g_last < Lg;
+  if (interior) la_stream_body<LKIND, false>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+  else la_stream_body<LKIND, true>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+}
+
+// the streaming kernel applies when 8 output rows see <= 5 global centres and <= 3 rows of the
+// injected feature, and the global operand needs no transform
+static bool la_stream_applies(const LaArgs& a) {
+  return a.gkind == SRC_PLAIN && (a.lkind == SRC_INJECT_GATE || a.lkind == SRC_INJECT_ADD) && a.glo.L <= a.loc.L &&
+         7.0 * a.glo.L / a.loc.L <= 3.99 && 7.0 * a.loc.Lg / a.loc.L <= 1.99 && a.C % 4 == 0;
+}
+
+template <int LKIND>
+static int launch_la_stream(const LaArgs& a, cudaStream_t st) {
+  int threads = a.C / 4;
+  if (threads > 128) threads = 128;
+  if (threads < 32) threads = 32;
+  const int ctiles = cdiv(a.C / 4, threads);
+  int rows, tiles;
+  pick_tiling(a.B, a.loc.L, ctiles, SR, &rows, &tiles);
+  dim3 grid(tiles, ctiles, a.B);
+  const size_t smem = (size_t)(2 * SROWS + 2 * SGC) * threads * 4 * sizeof(float) + (size_t)(2 * rows + 4) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    attr_set = true;
+  }
+  TD_LAUNCH((la_stream_kernel<LKIND>), grid, threads, smem, st, a, rows);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- LA statistics, one launch
+// GlobLN statistics of the three LA convolutions before the combine: CTAs [0, tiles_l) stream the
+// local operand (injection recomputed, conv local_embedding), the rest walk the global operand
+// (convs global_act and global_embedding from one read).  Nothing is written but the sums.
+constexpr int SSROWS = SR + SGG;  // rows per ring stage of the local part
+
+template <int LKIND, bool EDGE>
+__device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch, int t0, int t1, float* ring,
+                                                  const int* jl, float& tot1, float& tot2) {
+  constexpr int V = 4;
+  const int Ll = a.src.L, Lgg = a.src.Lg, C = a.C;
+  const int colw = blockDim.x * V;
+  const float* xl = a.src.x + (size_t)b * Ll * C + ch;
+  const float* gg = a.src.g + (size_t)b * Lgg * C + ch;
+  float* col = ring + threadIdx.x * V;
+  Injector<LKIND, V> inj;
+  inj.init(a.src, b, ch, C);
+  vf<V> wl[5];
+  load_taps<V>(a.w[0], ch, wl);
+  vf<V> s1 = vzero<V>(), s2 = vzero<V>();
+
+  auto issue = [&](int k) {
+    float* st = col + (size_t)(k & 1) * SSROWS * colw;
+    const int t = t0 + k * SR;
+#pragma unroll
+    for (int i = 0; i < SR; ++i) {
+      const int row = t + 2 + i;
+      const bool ok = !EDGE || row < Ll;
+      cp_async16(st + i * colw, xl + (ok ? row : 0) * C, ok);
+    }
+    const int j0 = jl[t - t0 + 4];
+#pragma unroll
+    for (int i = 0; i < SGG; ++i) {
+      const int row = j0 + i;
+      const bool ok = row < Lgg;
+      cp_async16(st + (SR + i) * colw, gg + (ok ? row : 0) * C, ok);
+    }
+  };
+
+  vf<V> xr[SR + 4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 - 2 + i;
+    if (EDGE && (t < 0 || t >= Ll)) {
+      xr[SR + i] = vzero<V>();
+    } else {
+      const int j = jl[i];
+      xr[SR + i] = inj.apply(vload<V>(xl + t * C), vload<V>(gg + j * C), j);
+    }
+  }
+  const int nchunks = (t1 - t0 + SR - 1) / SR;
+  issue(0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int k = 0; k < nchunks; ++k) {
+    if (k + 1 < nchunks) issue(k + 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const float* st = col + (size_t)(k & 1) * SSROWS * colw;
+    const int t = t0 + k * SR;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xr[i] = xr[SR + i];
+    const int j0 = jl[t - t0 + 4];
+#pragma unroll
+    for (int i = 0; i < SR; ++i) {
+      if (EDGE && t + 2 + i >= Ll) {
+        xr[4 + i] = vzero<V>();
+      } else {
+        const int j = jl[t - t0 + 4 + i];
+        xr[4 + i] = inj.apply(lds4(st + i * colw), lds4(st + (SR + (j - j0)) * colw), j);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SR; ++r) {
+      if (!EDGE || t + r < t1) {
+        const vf<V> y = conv5<V>(wl, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          s1[e] += y[e];
+          s2[e] = fmaf(y[e], y[e], s2[e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    tot1 += s1[e];
+    tot2 += s2[e];
+  }
+}
+
+template <int LKIND>
+__global__ void __launch_bounds__(128, 3) la_stats_kernel(DwArgs loc, DwArgs glo, int rows_l, int tiles_l, int rows_g) {
+  extern __shared__ __align__(16) float la_smem[];
+  __shared__ double red[64];
+  constexpr int V = 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if ((int)blockIdx.x < tiles_l) {
+    // ---- local operand, streamed
+    const int Ll = loc.src.L;
+    const int t0 = blockIdx.x * rows_l, t1 = min(t0 + rows_l, Ll);
+    float* ring = la_smem;
+    int* jl = reinterpret_cast<int*>(ring + 2 * SSROWS * blockDim.x * V);
+    fill_nearest(jl, rows_l + 4, t0 - 2, Ll, loc.src.gscale, loc.src.Lg);
+    __syncthreads();
+    float tot1[1] = {0.f}, tot2[1] = {0.f};
+    if (ch < loc.C) {
+      const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0;
+      if (interior) stats_stream_body<LKIND, false>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
+      else stats_stream_body<LKIND, true>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
+    }
+    flush_item_stats<1>(loc.stats, b, tot1, tot2, red);
+  } else {
+    // ---- global operand (plain), two convolutions from one read
+    constexpr int R = 8;
+    const int tile = blockIdx.x - tiles_l;
+    const int t0 = tile * rows_g, t1 = min(t0 + rows_g, glo.Lout);
+    float tot1[2] = {0.f, 0.f}, tot2[2] = {0.f, 0.f};
+    if (ch < glo.C) {
+      const bool interior = t0 - 2 >= 0 && t1 + 2 <= glo.src.L && (t1 - t0) % R == 0;
+      if (interior) dw5_body<SRC_PLAIN, V, 2, 1, R, false, true, false>(glo, b, ch, t0, t1, nullptr, 0, tot1, tot2);
+      else dw5_body<SRC_PLAIN, V, 2, 1, R, false, true, true>(glo, b, ch, t0, t1, nullptr, 0, tot1, tot2);
+    }
+    flush_item_stats<2>(glo.stats, b, tot1, tot2, red);
+  }
+}
+
+template <int LKIND>
+static int launch_la_stats_t(const DwArgs& loc, const DwArgs& glo, cudaStream_t st) {
+  int threads = loc.C / 4;
+  if (threads > 128) threads = 128;
+  if (threads < 32) threads = 32;
+  const int ctiles = cdiv(loc.C / 4, threads);
+  int rows_l, tiles_l, rows_g, tiles_g;
+  pick_tiling(loc.B, loc.Lout, ctiles, SR, &rows_l, &tiles_l);
+  pick_tiling(glo.B, glo.Lout, ctiles, 8, &rows_g, &tiles_g);
+  dim3 grid(tiles_l + tiles_g, ctiles, loc.B);
+  const size_t smem = (size_t)2 * SSROWS * threads * 4 * sizeof(float) + (size_t)(rows_l + 4) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TD_CUDA(cudaFuncSetAttribute(la_stats_kernel<LKIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  TD_LAUNCH((la_stats_kernel<LKIND>), grid, threads, smem, st, loc, glo, rows_l, tiles_l, rows_g);
+  return 0;
+}
+
+int launch_la_stats(const DwArgs& loc, const DwArgs& glo, cudaStream_t st) {
+  TD_REQUIRE(loc.nw == 1 && glo.nw == 2 && loc.stats && glo.stats && !loc.out && !glo.out, "la_stats: bad arguments");
+  const bool stream_ok = glo.kind == SRC_PLAIN && (loc.kind == SRC_INJECT_GATE || loc.kind == SRC_INJECT_ADD) &&
+                         7.0 * loc.src.Lg / loc.src.L <= 1.99 && loc.C % 4 == 0 && loc.C == glo.C && loc.B == glo.B &&
+                         (long)loc.src.L * loc.C < (1L << 31) && (long)glo.src.L * glo.C < (1L << 31);
+  if (stream_ok) {
+    if (loc.kind == SRC_INJECT_GATE) return launch_la_stats_t<SRC_INJECT_GATE>(loc, glo, st);
+    return launch_la_stats_t<SRC_INJECT_ADD>(loc, glo, st);
+  }
+  if (int e = launch_dw5(loc, st)) return e;
+  return launch_dw5(glo, st);
+}
+
 template <int LKIND, int GKIND>
 static int launch_la_t(const LaArgs& a, cudaStream_t st) {
   constexpr int V = 2;
@@ -494,6 +927,10 @@ static int launch_la_t(const LaArgs& a, cudaStream_t st) {
 int launch_la_combine(const LaArgs& a, cudaStream_t st) {
   TD_REQUIRE(a.C % 4 == 0, "la: C=%d must be a multiple of 4", a.C);
   TD_REQUIRE((long)a.loc.L * a.C < (1L << 31) && (long)a.glo.L * a.C < (1L << 31), "la: item too large for 32-bit offsets");
+  if (la_stream_applies(a)) {
+    if (a.lkind == SRC_INJECT_GATE) return launch_la_stream<SRC_INJECT_GATE>(a, st);
+    return launch_la_stream<SRC_INJECT_ADD>(a, st);
+  }
   if (a.lkind == SRC_INJECT_GATE && a.gkind == SRC_INJECT_GATE) return launch_la_t<SRC_INJECT_GATE, SRC_INJECT_GATE>(a, st);
   if (a.lkind == SRC_INJECT_GATE && a.gkind == SRC_PLAIN) return launch_la_t<SRC_INJECT_GATE, SRC_PLAIN>(a, st);
   if (a.lkind == SRC_INJECT_ADD && a.gkind == SRC_INJECT_ADD) return launch_la_t<SRC_INJECT_ADD, SRC_INJECT_ADD>(a, st);

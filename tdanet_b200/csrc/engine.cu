@@ -69,13 +69,15 @@ struct Plan {
   size_t ga_in, attn_in, qkv, attn_ctx, attn_out, ga_mid, fc1, ffn_dw, fc2, ga_out;
   size_t pool_dw[TDANET_MAX_DEPTH], pool_pw[TDANET_MAX_DEPTH];
   size_t masked;
-  // coefficient tables
-  size_t enc_coef, proj_coef, spp_coef[TDANET_MAX_DEPTH], fc1_coef, fc2_coef, inj_coef[TDANET_MAX_DEPTH],
-      la_coef[TDANET_MAX_DEPTH], pool_coef[TDANET_MAX_DEPTH];
+  // closed-form loc_glo_fus coefficient tables (BEST), [B,6,C] per scale
+  size_t inj_coef[TDANET_MAX_DEPTH];
   // statistics arena (zeroed once per block)
   size_t stats_begin, stats_end;
-  size_t st_enc, st_proj, st_fc1, st_fc2, st_pool[TDANET_MAX_DEPTH];       // double [B,2]
-  size_t st_spp[TDANET_MAX_DEPTH], st_g, st_la_l[TDANET_MAX_DEPTH], st_la_g[TDANET_MAX_DEPTH];  // float
+  // per-item sum / sum of squares in double: [B,2] ([B,2,2] for st_la_g: global_act, global_embedding)
+  size_t st_enc, st_proj, st_fc1, st_fc2, st_pool[TDANET_MAX_DEPTH], st_spp[TDANET_MAX_DEPTH],
+      st_la_l[TDANET_MAX_DEPTH], st_la_g[TDANET_MAX_DEPTH];
+  // per-channel sums in float [B,2,C] (BEST: inputs of the closed-form loc_glo_fus statistics)
+  size_t st_spp_ch[TDANET_MAX_DEPTH], st_g;
   // TF32 auxiliary weight copies
   size_t aux_proj, aux_res, aux_in, aux_out, aux_fc1, aux_fc2, aux_pool[TDANET_MAX_DEPTH];
 
@@ -162,27 +164,19 @@ static int make_plan(const tdanet_config_t* c, int B, int T, Plan& p) {
   p.masked = p.act("masked", L0, c->num_sources * Nb);
 
   auto tab = [&](int planes, int ch) { return p.take((size_t)B * planes * ch * sizeof(float)); };
-  p.enc_coef = tab(2, Nb);
-  p.proj_coef = tab(2, C);
-  p.fc1_coef = tab(2, 2 * C);
-  p.fc2_coef = tab(2, C);
-  for (int k = 0; k < c->depth; ++k) {
-    p.spp_coef[k] = tab(2, C);
-    p.inj_coef[k] = tab(6, C);
-    p.la_coef[k] = tab(6, C);
-    p.pool_coef[k] = tab(2, C);
-  }
+  for (int k = 0; k < c->depth; ++k) p.inj_coef[k] = tab(6, C);
   p.stats_begin = p.bytes;
-  auto dstat = [&]() { return p.take((size_t)B * 2 * sizeof(double)); };
-  p.st_enc = dstat();
-  p.st_proj = dstat();
-  p.st_fc1 = dstat();
-  p.st_fc2 = dstat();
+  auto dstat = [&](int n) { return p.take((size_t)B * n * 2 * sizeof(double)); };
+  p.st_enc = dstat(1);
+  p.st_proj = dstat(1);
+  p.st_fc1 = dstat(1);
+  p.st_fc2 = dstat(1);
   for (int k = 0; k < c->depth; ++k) {
-    p.st_pool[k] = dstat();
-    p.st_spp[k] = tab(2, C);
-    p.st_la_l[k] = tab(2, C);
-    p.st_la_g[k] = tab(4, C);
+    p.st_pool[k] = dstat(1);
+    p.st_spp[k] = dstat(1);
+    p.st_la_l[k] = dstat(1);
+    p.st_la_g[k] = dstat(2);
+    p.st_spp_ch[k] = tab(2, C);
   }
   p.st_g = tab(2, C);
   p.stats_end = p.bytes;
@@ -237,9 +231,19 @@ static int prepare_weights(const Ctx& x) {
   return 0;
 }
 
-static SrcDesc plain_src(const float* x, int L) { return SrcDesc{x, L, nullptr, nullptr, nullptr, 0, 0.f}; }
-static SrcDesc affine_src(const float* x, int L, const float* coef, const float* slope = nullptr) {
-  return SrcDesc{x, L, coef, slope, nullptr, 0, 0.f};
+static NormRef norm_ref(const Ctx& x, size_t stats_off, int item_stride, double count, const float* gamma,
+                        const float* beta) {
+  return NormRef{x.at<double>(stats_off), item_stride, count, gamma, beta};
+}
+static SrcDesc plain_src(const float* x, int L) {
+  SrcDesc s{};
+  s.x = x; s.L = L;
+  return s;
+}
+static SrcDesc affine_src(const float* x, int L, const NormRef& norm, const float* slope = nullptr) {
+  SrcDesc s{};
+  s.x = x; s.L = L; s.norm = norm; s.slope = slope;
+  return s;
 }
 
 // The bottom-scale block: GA / GlobalAttention (TDANet_best.py:254-264)
@@ -274,10 +278,8 @@ static int global_attention(const Ctx& x) {
   g.A = x.at(p.ga_mid); g.W = w->fc1.w; g.bias = nullptr; g.D = x.at(p.fc1);
   g.B = B; g.L = Lb; g.N = 2 * C; g.K = C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_fc1);
   { Tag t("gemm_fc1"); if (int e = gemm(x, g, p.aux_fc1)) return e; }
-  if (int e = launch_coef_item(x.at<double>(p.st_fc1), (double)Lb * 2 * C, w->fc1.gamma, w->fc1.beta,
-                               x.at(p.fc1_coef), B, 2 * C, x.st)) return e;
   DwArgs d{};
-  d.src = affine_src(x.at(p.fc1), Lb, x.at(p.fc1_coef));
+  d.src = affine_src(x.at(p.fc1), Lb, norm_ref(x, p.st_fc1, 2, (double)Lb * 2 * C, w->fc1.gamma, w->fc1.beta));
   d.kind = SRC_AFFINE; d.B = B; d.C = 2 * C; d.Lout = Lb; d.stride = 1; d.nw = 1;
   d.w[0] = w->ffn_dw_w; d.bias[0] = w->ffn_dw_b; d.out = x.at(p.ffn_dw); d.relu = 1; d.round_out = x.rnd();
   { Tag t("ffn_dw"); if (int e = launch_dw5(d, x.st)) return e; }
@@ -285,10 +287,9 @@ static int global_attention(const Ctx& x) {
   g.A = x.at(p.ffn_dw); g.W = w->fc2.w; g.bias = nullptr; g.D = x.at(p.fc2);
   g.B = B; g.L = Lb; g.N = C; g.K = 2 * C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_fc2);
   { Tag t("gemm_fc2"); if (int e = gemm(x, g, p.aux_fc2)) return e; }
-  if (int e = launch_coef_item(x.at<double>(p.st_fc2), (double)Lb * C, w->fc2.gamma, w->fc2.beta,
-                               x.at(p.fc2_coef), B, C, x.st)) return e;
   // global_f = x + gLN(fc2); BEST also needs its per-channel sums for the closed-form loc_glo_fus
-  return launch_affine_residual(x.at(p.fc2), x.at(p.fc2_coef), x.at(p.ga_mid), x.at(p.ga_out),
+  return launch_affine_residual(x.at(p.fc2), norm_ref(x, p.st_fc2, 2, (double)Lb * C, w->fc2.gamma, w->fc2.beta),
+                                x.at(p.ga_mid), x.at(p.ga_out),
                                 c->variant == TDANET_BEST ? x.at(p.st_g) : nullptr, B, Lb, C, x.st);
 }
 
@@ -306,23 +307,25 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   g.B = B; g.L = p.L[0]; g.N = C; g.K = cc; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_proj);
   { Tag t("gemm_proj"); if (int e = gemm(x, g, p.aux_proj)) return e; }
   Tag tag("coef");
-  if (int e = launch_coef_item(x.at<double>(p.st_proj), (double)p.L[0] * C, w->proj.gamma, w->proj.beta,
-                               x.at(p.proj_coef), B, C, x.st)) return e;
+  auto spp_norm = [&](int k) {
+    return norm_ref(x, p.st_spp[k], 2, (double)p.L[k] * C, w->spp_dw[k].gamma, w->spp_dw[k].beta);
+  };
   // spp_dw[0..depth-1]: depthwise k5 (stride 1, then 2), raw output + per-channel sums
   for (int k = 0; k < depth; ++k) {
     DwArgs d{};
     if (k == 0) {
-      d.src = affine_src(x.at(p.proj), p.L[0], x.at(p.proj_coef), w->proj_prelu);
+      d.src = affine_src(x.at(p.proj), p.L[0], norm_ref(x, p.st_proj, 2, (double)p.L[0] * C, w->proj.gamma, w->proj.beta),
+                         w->proj_prelu);
       d.kind = SRC_AFFINE_PRELU;
     } else {
-      d.src = affine_src(x.at(p.spp[k - 1]), p.L[k - 1], x.at(p.spp_coef[k - 1]));
+      d.src = affine_src(x.at(p.spp[k - 1]), p.L[k - 1], spp_norm(k - 1));
       d.kind = SRC_AFFINE;
     }
     d.B = B; d.C = C; d.Lout = p.L[k]; d.stride = k == 0 ? 1 : 2; d.nw = 1;
-    d.w[0] = w->spp_dw[k].w; d.bias[0] = w->spp_dw[k].b; d.out = x.at(p.spp[k]); d.stats = x.at(p.st_spp[k]);
+    d.w[0] = w->spp_dw[k].w; d.bias[0] = w->spp_dw[k].b; d.out = x.at(p.spp[k]);
+    d.stats = x.at<double>(p.st_spp[k]);
+    d.chstats = c->variant == TDANET_BEST ? x.at(p.st_spp_ch[k]) : nullptr;
     { Tag t(k == 0 ? "spp_dw0" : "spp_dw_s2"); if (int e = launch_dw5(d, x.st)) return e; }
-    if (int e = launch_coef_chan(x.at(p.st_spp[k]), (size_t)2 * C, p.L[k], w->spp_dw[k].gamma, w->spp_dw[k].beta,
-                                 x.at(p.spp_coef[k]), B, C, x.st)) return e;
   }
   // global feature at the bottom scale
   PoolArgs pa{};
@@ -333,19 +336,17 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       const int j = depth - 1 - k, s = 1 << j, ks = j == 0 ? 5 : 2 * s + 1;
       const tdanet_sepconvnorm_t& q = w->conv_pool[j];
       Tag tp("conv_pool");
-      if (int e = launch_dw_generic(affine_src(x.at(p.spp[k]), p.L[k], x.at(p.spp_coef[k])), SRC_AFFINE, B, C, Lb,
+      if (int e = launch_dw_generic(affine_src(x.at(p.spp[k]), p.L[k], spp_norm(k)), SRC_AFFINE, B, C, Lb,
                                     ks, s, q.dw_w, q.dw_b, x.at(p.pool_dw[k]), x.rnd(), x.st)) return e;
       g = GemmArgs{};
       g.A = x.at(p.pool_dw[k]); g.W = q.pw_w; g.bias = q.pw_b; g.D = x.at(p.pool_pw[k]);
       g.B = B; g.L = Lb; g.N = C; g.K = C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_pool[k]);
       if (int e = gemm(x, g, p.aux_pool[j])) return e;
-      if (int e = launch_coef_item(x.at<double>(p.st_pool[k]), (double)Lb * C, q.gamma, q.beta, x.at(p.pool_coef[k]),
-                                   B, C, x.st)) return e;
-      pa.x[k] = x.at(p.pool_pw[k]); pa.coef[k] = x.at(p.pool_coef[k]); pa.L[k] = Lb;
+      pa.x[k] = x.at(p.pool_pw[k]); pa.norm[k] = norm_ref(x, p.st_pool[k], 2, (double)Lb * C, q.gamma, q.beta); pa.L[k] = Lb;
     }
     if (int e = launch_affine_sum(pa, x.st)) return e;
   } else {
-    for (int k = 0; k < depth; ++k) { pa.x[k] = x.at(p.spp[k]); pa.coef[k] = x.at(p.spp_coef[k]); pa.L[k] = p.L[k]; }
+    for (int k = 0; k < depth; ++k) { pa.x[k] = x.at(p.spp[k]); pa.norm[k] = spp_norm(k); pa.L[k] = p.L[k]; }
     Tag tp("pool_sum");
     if (int e = launch_pool_sum(pa, x.st)) return e;
   }
@@ -357,14 +358,20 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   auto inj_src = [&](int k) {
     SrcDesc s{};
     s.x = x.at(p.spp[k]); s.L = p.L[k];
-    s.coef = c->variant == TDANET_BEST ? x.at(p.inj_coef[k]) : x.at(p.spp_coef[k]);
+    if (c->variant == TDANET_BEST) s.coef = x.at(p.inj_coef[k]);
+    else s.norm = spp_norm(k);
     s.g = gf; s.Lg = Lb; s.gscale = nearest_scale(Lb, p.L[k]);
     return s;
   };
-  if (c->variant == TDANET_BEST)
-    for (int k = 0; k < depth; ++k)
-      if (int e = launch_coef_inject_gate(x.at(p.st_spp[k]), (size_t)2 * C, p.L[k], &w->spp_dw[k], x.at(p.st_g), Lb,
-                                          &w->loc_glo_fus[k], x.at(p.inj_coef[k]), B, C, x.st)) return e;
+  if (c->variant == TDANET_BEST) {
+    InjectCoefArgs ia{};
+    ia.n = depth; ia.g_stats = x.at(p.st_g); ia.Lg = Lb;
+    for (int k = 0; k < depth; ++k) {
+      ia.spp_stats[k] = x.at(p.st_spp_ch[k]); ia.L[k] = p.L[k]; ia.spp[k] = w->spp_dw[k];
+      ia.la[k] = w->loc_glo_fus[k]; ia.coef[k] = x.at(p.inj_coef[k]);
+    }
+    if (int e = launch_coef_inject_gate(ia, B, C, x.st)) return e;
+  }
   // top-down fusion: last_layer[i](x_fused[i], i == depth-2 ? x_fused[i-1] : expanded)
   for (int i = depth - 2; i >= 0; --i) {
     const tdanet_la_t& la = w->last_layer[i];
@@ -377,19 +384,19 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       glo = plain_src(x.at(p.expanded[i + 1]), p.L[i + 1]);
       gkind = SRC_PLAIN;
     }
-    DwArgs d{};
-    d.src = loc; d.kind = inj_kind; d.B = B; d.C = C; d.Lout = loc.L; d.stride = 1; d.nw = 1;
-    d.w[0] = la.local_embedding.w; d.stats = x.at(p.st_la_l[i]);
-    { Tag t("la_stats"); if (int e = launch_dw5(d, x.st)) return e; }
-    d = DwArgs{};
-    d.src = glo; d.kind = gkind; d.B = B; d.C = C; d.Lout = glo.L; d.stride = 1; d.nw = 2;
-    d.w[0] = la.global_act.w; d.w[1] = la.global_embedding.w; d.stats = x.at(p.st_la_g[i]);
-    { Tag t("la_stats"); if (int e = launch_dw5(d, x.st)) return e; }
-    if (int e = launch_coef_la(x.at(p.st_la_l[i]), loc.L, x.at(p.st_la_g[i]), glo.L, &la, x.at(p.la_coef[i]), B, C, x.st)) return e;
+    DwArgs dl{}, dg{};
+    dl.src = loc; dl.kind = inj_kind; dl.B = B; dl.C = C; dl.Lout = loc.L; dl.stride = 1; dl.nw = 1;
+    dl.w[0] = la.local_embedding.w; dl.stats = x.at<double>(p.st_la_l[i]);
+    dg.src = glo; dg.kind = gkind; dg.B = B; dg.C = C; dg.Lout = glo.L; dg.stride = 1; dg.nw = 2;
+    dg.w[0] = la.global_act.w; dg.w[1] = la.global_embedding.w; dg.stats = x.at<double>(p.st_la_g[i]);
+    { Tag t("la_stats"); if (int e = launch_la_stats(dl, dg, x.st)) return e; }
     LaArgs l{};
     l.loc = loc; l.glo = glo; l.lkind = inj_kind; l.gkind = gkind; l.B = B; l.C = C;
     l.wl = la.local_embedding.w; l.wa = la.global_act.w; l.we = la.global_embedding.w;
-    l.coef = x.at(p.la_coef[i]); l.out = x.at(p.expanded[i]); l.scale = nearest_scale(glo.L, loc.L);
+    l.nL = norm_ref(x, p.st_la_l[i], 2, (double)loc.L * C, la.local_embedding.gamma, la.local_embedding.beta);
+    l.nA = norm_ref(x, p.st_la_g[i], 4, (double)glo.L * C, la.global_act.gamma, la.global_act.beta);
+    l.nE = norm_ref(x, p.st_la_g[i] + 2 * sizeof(double), 4, (double)glo.L * C, la.global_embedding.gamma, la.global_embedding.beta);
+    l.out = x.at(p.expanded[i]); l.scale = nearest_scale(glo.L, loc.L);
     l.round_out = i == 0 && x.rnd();  // expanded[0] only feeds res_conv
     { Tag t("la_combine"); if (int e = launch_la_combine(l, x.st)) return e; }
   }
@@ -422,11 +429,11 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
   for (int k = 0; k < c->enc_convs; ++k) { ea.w[k] = w->enc_w[k]; ea.ks[k] = (k + 1) * K; }
   ea.out = x.at(p.enc); ea.stats = x.at<double>(p.st_enc);
   if (int e = launch_encoder(ea, st)) return e;
-  if (int e = launch_coef_item(x.at<double>(p.st_enc), (double)L0 * Nb, w->ln_gamma, w->ln_beta, x.at(p.enc_coef), B, Nb, st)) return e;
+  const NormRef enc_norm = norm_ref(x, p.st_enc, 2, (double)L0 * Nb, w->ln_gamma, w->ln_beta);
   if (c->variant == TDANET_MULTRES) {
-    if (int e = launch_affine(x.at(p.enc), x.at(p.enc_coef), x.at(p.x0), B, L0, Nb, st)) return e;
+    if (int e = launch_affine(x.at(p.enc), enc_norm, x.at(p.x0), B, L0, Nb, st)) return e;
   } else {
-    if (int e = launch_bottleneck(x.at(p.enc), x.at(p.enc_coef), w->bottleneck_w, w->bottleneck_b, x.at(p.x0), B, L0, Nb, cc, st)) return e;
+    if (int e = launch_bottleneck(x.at(p.enc), enc_norm, w->bottleneck_w, w->bottleneck_b, x.at(p.x0), B, L0, Nb, cc, st)) return e;
   }
   // Recurrent: num_blocks iterations of one shared UConvBlock
   for (int blk = 0; blk < c->num_blocks; ++blk) {

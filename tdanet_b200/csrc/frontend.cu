@@ -79,8 +79,7 @@ int launch_encoder(const EncArgs& a, cudaStream_t st) {
 
 // ----------------------------------------------------------------------------- bottleneck
 // x0 = Conv1d(Nb -> c, k=1)(GlobLN(enc)); the normalisation is folded into the weights per item.
-__global__ void __launch_bounds__(256) bottleneck_kernel(const float* __restrict__ enc,
-                                                         const float* __restrict__ coef,
+__global__ void __launch_bounds__(256) bottleneck_kernel(const float* __restrict__ enc, NormRef norm,
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          float* __restrict__ out, int L0, int Nb, int c,
@@ -92,15 +91,18 @@ __global__ void __launch_bounds__(256) bottleneck_kernel(const float* __restrict
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * rows_per_cta;
   const int rows = min(rows_per_cta, L0 - t0);
-  const float* sc = coef + (size_t)b * 2 * Nb;
-  const float* sh = sc + Nb;
+  float r, mur;
+  norm_moments(norm, b, r, mur);
   for (int i = threadIdx.x; i < c * Nb; i += blockDim.x) {
     const int o = i / Nb, n = i % Nb;
-    wf[o * (Nb + 1) + n] = __ldg(w + i) * __ldg(sc + n);
+    wf[o * (Nb + 1) + n] = __ldg(w + i) * (__ldg(norm.gamma + n) * r);
   }
   for (int o = threadIdx.x; o < c; o += blockDim.x) {
     float acc = __ldg(bias + o);
-    for (int n = 0; n < Nb; ++n) acc = fmaf(__ldg(w + o * Nb + n), __ldg(sh + n), acc);
+    for (int n = 0; n < Nb; ++n) {
+      const float g = __ldg(norm.gamma + n);
+      acc = fmaf(__ldg(w + o * Nb + n), fmaf(-g, mur, __ldg(norm.beta + n)), acc);
+    }
     bf[o] = acc;
   }
   const float* e = enc + ((size_t)b * L0 + t0) * Nb;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) bottleneck_kernel(const float* __restrict
   }
 }
 
-int launch_bottleneck(const float* enc, const float* coef, const float* w, const float* bias,
+int launch_bottleneck(const float* enc, const NormRef& norm, const float* w, const float* bias,
                       float* out, int B, int L0, int Nb, int c, cudaStream_t st) {
   const int rows = 32;
   const size_t smem = ((size_t)c * (Nb + 1) + c + (size_t)rows * Nb) * sizeof(float);
@@ -125,7 +127,7 @@ int launch_bottleneck(const float* enc, const float* coef, const float* w, const
   if (smem > 48 * 1024)
     TD_CUDA(cudaFuncSetAttribute(bottleneck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(L0, rows), 1, B);
-  TD_LAUNCH(bottleneck_kernel, grid, 256, smem, st, enc, coef, w, bias, out, L0, Nb, c, rows);
+  TD_LAUNCH(bottleneck_kernel, grid, 256, smem, st, enc, norm, w, bias, out, L0, Nb, c, rows);
   return 0;
 }
 

@@ -9,16 +9,17 @@ namespace td {
 // How a consumer kernel reads one row of a [B, L, C] activation.
 enum SrcKind {
   SRC_PLAIN = 0,         // x
-  SRC_AFFINE = 1,        // x*scale + shift                    coef planes [B,2,C]
-  SRC_AFFINE_PRELU = 2,  // prelu(x*scale + shift, *slope)
+  SRC_AFFINE = 1,        // GlobLN(x) = x*scale + shift        (norm)
+  SRC_AFFINE_PRELU = 2,  // prelu(GlobLN(x), *slope)           (norm)
   SRC_INJECT_GATE = 3,   // (al*x+bl) * sigmoid(aa*g[j]+ba) + (ae*g[j]+be), j = nearest(t)  coef [B,6,C]
-  SRC_INJECT_ADD = 4     // (a*x+b) + g[j]                                                  coef [B,2,C]
+  SRC_INJECT_ADD = 4     // GlobLN(x) + g[j]                                                (norm)
 };
 
 struct SrcDesc {
   const float* x;      // [B, L, C]
   int L;
-  const float* coef;   // [B, planes, C] or nullptr
+  NormRef norm;        // AFFINE / AFFINE_PRELU / INJECT_ADD
+  const float* coef;   // INJECT_GATE: [B, 6, C] from launch_coef_inject_gate
   const float* slope;  // PReLU slope (1 element) or nullptr
   const float* g;      // injected global feature [B, Lg, C] or nullptr
   int Lg;
@@ -29,7 +30,8 @@ struct SrcDesc {
 // Depthwise k=5 pad=2 conv over time (stride 1 or 2), NW weight sets sharing one input.
 //   w[i]: [C,1,5]  bias[i]: [C] or null
 //   out : [B, Lout, C] (only NW==1) or null;  relu applied to the stored value if `relu`
-//   stats: [B, NW, 2, C] per-channel sum / sum of squares of the (pre-relu) conv output, or null
+//   stats: [B, NW, 2] per-item sum / sum of squares (double) of the pre-relu conv output, or null
+//   chstats: [B, NW, 2, C] the same per channel (float), or null
 struct DwArgs {
   SrcDesc src;
   int kind;  // SrcKind
@@ -37,7 +39,8 @@ struct DwArgs {
   const float* w[2];
   const float* bias[2];
   float* out;
-  float* stats;
+  double* stats;
+  float* chstats;
   int relu;
   int round_out;  // store TF32-rounded values (output only feeds a tensor-core GEMM)
 };
@@ -55,37 +58,38 @@ struct LaArgs {
   int lkind, gkind;
   int B, C;
   const float *wl, *wa, *we;  // [C,1,5]
-  const float* coef;          // [B, 6, C] : sL hL sA hA sE hE
+  NormRef nL, nA, nE;         // GlobLN of local_embedding / global_act / global_embedding outputs
   float* out;                 // [B, Ll, C]
   float scale;                // fl32(Lg / Ll)
   int round_out;
 };
 int launch_la_combine(const LaArgs& a, cudaStream_t st);
+// statistics of the three LA convolutions in one launch: loc (nw = 1) and glo (nw = 2, global_act then
+// global_embedding), both stats-only
+int launch_la_stats(const DwArgs& loc, const DwArgs& glo, cudaStream_t st);
 
 // ------------------------------------------------------------------ coef.cu
-// GlobLN coefficients from per-item (sum, sumsq) in double: scale=gamma*r, shift=beta-gamma*mu*r
-int launch_coef_item(const double* stats, double count, const float* gamma, const float* beta,
-                     float* coef, int B, int C, cudaStream_t st);
-// ... from per-channel stats [B, 2, C] (float), `rows` rows per channel
-int launch_coef_chan(const float* chstats, size_t item_stride, int rows, const float* gamma,
-                     const float* beta, float* coef, int B, int C, cudaStream_t st);
-// LA (k=5) coefficients: three per-channel stat sets -> [B,6,C]
-//   stats_l: [B,1,2,C] over Ll rows; stats_g: [B,2,2,C] (global_act, global_embedding) over Lg rows
-int launch_coef_la(const float* stats_l, int Ll, const float* stats_g, int Lg, const tdanet_la_t* la,
-                   float* coef, int B, int C, cudaStream_t st);
-// BEST loc_glo_fus (k=1 LA) closed form -> SRC_INJECT_GATE table [B,6,C] for one scale
-//   spp_stats: per-channel stats [B,2,C] of the raw spp_dw[k] output (rows Lk), spp: its GlobLN
-//   g_stats:   per-channel stats [B,2,C] of global_f (rows Lg)
-int launch_coef_inject_gate(const float* spp_stats, size_t spp_item_stride, int Lk,
-                            const tdanet_convnorm_t* spp, const float* g_stats, int Lg,
-                            const tdanet_la_t* la, float* coef, int B, int C, cudaStream_t st);
+// BEST loc_glo_fus (k=1 LA) closed form -> SRC_INJECT_GATE tables [B,6,C], every scale in one launch
+//   spp_stats[k]: per-channel stats [B,2,C] of the raw spp_dw[k] output (L[k] rows), spp[k]: its GlobLN
+//   g_stats:      per-channel stats [B,2,C] of global_f (Lg rows)
+struct InjectCoefArgs {
+  int n;
+  const float* spp_stats[TDANET_MAX_DEPTH];
+  int L[TDANET_MAX_DEPTH];
+  tdanet_convnorm_t spp[TDANET_MAX_DEPTH];
+  tdanet_la_t la[TDANET_MAX_DEPTH];
+  float* coef[TDANET_MAX_DEPTH];
+  const float* g_stats;
+  int Lg;
+};
+int launch_coef_inject_gate(const InjectCoefArgs& a, int B, int C, cudaStream_t st);
 
 // ------------------------------------------------------------------ bottom.cu
 // sum_k adaptive_avg_pool(affine_k(x_k)) -> out [B, Lb, C]
 struct PoolArgs {
   int n;
   const float* x[TDANET_MAX_DEPTH];
-  const float* coef[TDANET_MAX_DEPTH];  // [B,2,C]
+  NormRef norm[TDANET_MAX_DEPTH];
   int L[TDANET_MAX_DEPTH];
   int B, C, Lb;
   float* out;
@@ -103,11 +107,11 @@ int launch_attention(const float* qkv, float* ctx, int B, int L, int C, int n_he
 // y = resid + LayerNorm_C(post)*w + b ; post = 2*a (doubled=1) or xin + a (doubled=0)
 int launch_ln_residual(const float* a, const float* xin, const float* resid, const float* w,
                        const float* b, float* y, int doubled, int B, int L, int C, cudaStream_t st);
-// y = resid + (x*scale + shift) with coef [B,2,C]; optional per-channel stats of y -> [B,2,C]
-int launch_affine_residual(const float* x, const float* coef, const float* resid, float* y,
+// y = resid + GlobLN(x); optional per-channel stats of y -> [B,2,C]
+int launch_affine_residual(const float* x, const NormRef& norm, const float* resid, float* y,
                            float* chstats, int B, int L, int C, cudaStream_t st);
-// y = x*scale + shift
-int launch_affine(const float* x, const float* coef, float* y, int B, int L, int C, cudaStream_t st);
+// y = GlobLN(x)
+int launch_affine(const float* x, const NormRef& norm, float* y, int B, int L, int C, cudaStream_t st);
 
 // ------------------------------------------------------------------ frontend.cu
 struct EncArgs {
@@ -122,8 +126,8 @@ struct EncArgs {
   double* stats;  // [B,2]
 };
 int launch_encoder(const EncArgs& a, cudaStream_t st);
-// x0[b,t,:] = Wb . (enc*scale+shift) + bb     enc [B,L0,Nb], coef [B,2,Nb], out [B,L0,c]
-int launch_bottleneck(const float* enc, const float* coef, const float* w, const float* bias,
+// x0[b,t,:] = Wb . GlobLN(enc) + bb     enc [B,L0,Nb], out [B,L0,c]
+int launch_bottleneck(const float* enc, const NormRef& norm, const float* w, const float* bias,
                       float* out, int B, int L0, int Nb, int c, cudaStream_t st);
 // decoder ConvTranspose1d + crop: masked [B, L0, n_src*Nb] -> est [B, n_src, T]
 int launch_decoder(const float* masked, const float* w, float* est, int B, int L0, int Nb,
