@@ -165,13 +165,12 @@ struct NormRef {
 };
 
 __device__ __forceinline__ void norm_moments(const NormRef& n, int b, float& r, float& mur) {
-  const double s = n.stats[(size_t)b * n.item_stride], ss = n.stats[(size_t)b * n.item_stride + 1];
-  const double mu = s / n.count;
-  double var = ss / n.count - mu * mu;
-  if (var < 0.0) var = 0.0;
-  const double rd = 1.0 / sqrt(var + (double)kEpsGLN);
-  r = (float)rd;
-  mur = (float)(mu * rd);
+  // the cancellation-prone part (E[x^2] - mu^2) in double, the rest in float: FP64 is scarce on this part
+  const double inv = 1.0 / n.count;  // folded by the compiler into the launch constants where possible
+  const double mu = n.stats[(size_t)b * n.item_stride] * inv;
+  const double var = fma(-mu, mu, n.stats[(size_t)b * n.item_stride + 1] * inv);
+  r = rsqrtf(fmaxf((float)var, 0.f) + kEpsGLN);
+  mur = (float)mu * r;
 }
 
 template <int V>

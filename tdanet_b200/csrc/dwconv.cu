@@ -251,13 +251,13 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
   if constexpr (STATS) flush_item_stats<NW>(a.stats, b, tot1, tot2, red);
 }
 
-static void pick_tiling(int B, int L, int ctiles, int R, int* rows_per_cta, int* tiles) {
-  // aim at >= ~16 CTAs per SM in total, at most 64 rows per CTA, whole chunks of R rows
-  const long target = 148L * 16;
+static void pick_tiling(int B, int L, int ctiles, int R, int* rows_per_cta, int* tiles, long target = 148L * 16,
+                        int cap = 64) {
+  // aim at `target` CTAs in total, at most `cap` rows per CTA, whole chunks of R rows
   long per = ((long)B * L * ctiles + target - 1) / target;
   per = (per + R - 1) / R * R;
   if (per < R) per = R;
-  if (per > 64) per = 64;
+  if (per > cap) per = cap;
   *rows_per_cta = (int)per;
   *tiles = cdiv(L, (int)per);
 }
@@ -615,22 +615,32 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
     }
   };
 
-  // rows t0-2 .. t0+1 of the local operand: plain loads (once per CTA)
+  // rows t0-2 .. t0+1 of the local operand (+ their rows of the injected feature) ride in chunk 0's
+  // copy group, parked in the free stage, so that a CTA exposes one memory latency, not two
   vf<V> xr[SR + 4];
+  const int nchunks = (t1 - t0 + SR - 1) / SR;
+  {
+    float* pre = col + (size_t)SROWS * colw;  // stage 1 is unused until chunk 1 is issued
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int t = t0 - 2 + i;
-    if (EDGE && (t < 0 || t >= Ll)) {
-      xr[SR + i] = vzero<V>();
-    } else {
-      const int j = jl[i];
-      xr[SR + i] = inject(vload<V>(xl + t * C), vload<V>(gg + j * C), j);
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 - 2 + i;
+      const bool ok = !EDGE || (t >= 0 && t < Ll);
+      cp_async16(pre + i * colw, xl + (ok ? t : 0) * C, ok);
+      cp_async16(pre + (4 + i) * colw, gg + jl[i] * C, true);
     }
   }
-
-  const int nchunks = (t1 - t0 + SR - 1) / SR;
   issue(0);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  {
+    const float* pre = col + (size_t)SROWS * colw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 - 2 + i;
+      if (EDGE && (t < 0 || t >= Ll)) xr[SR + i] = vzero<V>();
+      else xr[SR + i] = inject(lds4(pre + i * colw), lds4(pre + (4 + i) * colw), jl[i]);
+    }
+  }
   for (int k = 0; k < nchunks; ++k) {
     if (k + 1 < nchunks) issue(k + 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -728,7 +738,7 @@ static int launch_la_stream(const LaArgs& a, cudaStream_t st) {
   if (threads < 32) threads = 32;
   const int ctiles = cdiv(a.C / 4, threads);
   int rows, tiles;
-  pick_tiling(a.B, a.loc.L, ctiles, SR, &rows, &tiles);
+  pick_tiling(a.B, a.loc.L, ctiles, SR, &rows, &tiles, 148L * 2 * 4, 128);
   dim3 grid(tiles, ctiles, a.B);
   const size_t smem = (size_t)(2 * SROWS + 2 * SGC) * threads * 4 * sizeof(float) + (size_t)(2 * rows + 4) * sizeof(int);
   static bool attr_set = false;
@@ -780,19 +790,29 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
   };
 
   vf<V> xr[SR + 4];
+  const int nchunks = (t1 - t0 + SR - 1) / SR;
+  {
+    float* pre = col + (size_t)SSROWS * colw;  // stage 1 is unused until chunk 1 is issued
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int t = t0 - 2 + i;
-    if (EDGE && (t < 0 || t >= Ll)) {
-      xr[SR + i] = vzero<V>();
-    } else {
-      const int j = jl[i];
-      xr[SR + i] = inj.apply(vload<V>(xl + t * C), vload<V>(gg + j * C), j);
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 - 2 + i;
+      const bool ok = !EDGE || (t >= 0 && t < Ll);
+      cp_async16(pre + i * colw, xl + (ok ? t : 0) * C, ok);
+      cp_async16(pre + (4 + i) * colw, gg + jl[i] * C, true);
     }
   }
-  const int nchunks = (t1 - t0 + SR - 1) / SR;
   issue(0);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  {
+    const float* pre = col + (size_t)SSROWS * colw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 - 2 + i;
+      if (EDGE && (t < 0 || t >= Ll)) xr[SR + i] = vzero<V>();
+      else xr[SR + i] = inj.apply(lds4(pre + i * colw), lds4(pre + (4 + i) * colw), jl[i]);
+    }
+  }
   for (int k = 0; k < nchunks; ++k) {
     if (k + 1 < nchunks) issue(k + 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
