@@ -186,6 +186,14 @@ TDANET_API int tdanet_pit_loss(const float* est, const float* tgt, int batch, in
                     int sdr_type, int threshold_byloss, float* loss, float* pw, int32_t* perm,
                     float* grad_est, void* scratch, size_t scratch_bytes, tdanet_stream_t stream);
 
+/* Long-form stitching (audio_test_css.py:108-134).  est [n_streams, n_chunks, 2, seg_len]: every chunk
+ * separated on its own (attn_group = 1).  Chunk k > 0 is appended from sample `overlap` on, with its two
+ * sources exchanged when that maximises the cosine similarity of its head with the tail of chunk 0.
+ *   swap [n_streams, n_chunks] int32 (out), out [n_streams, 2, out_len] with
+ *   out_len <= seg_len + (n_chunks-1)*(seg_len-overlap)  (the caller drops the zero padding of the last chunk). */
+TDANET_API int tdanet_css_stitch(const float* est, int n_streams, int n_chunks, int seg_len, int overlap,
+                                 int out_len, int32_t* swap, float* out, tdanet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -325,3 +325,49 @@ def si_snr_db(est, tgt, eps=1e-8):
     tgt = tgt - tgt.mean(dim=-1, keepdim=True)
     proj = (est * tgt).sum(-1, keepdim=True) * tgt / ((tgt ** 2).sum(-1, keepdim=True) + eps)
     return 10.0 * torch.log10((proj ** 2).sum(-1) / (((est - proj) ** 2).sum(-1) + eps) + eps)
+
+
+# --------------------------------------------------------------------------- long-form (CSS)
+def css_segments(wav, seg_len, overlap):
+    """Chunking of LibriCSSDataset (datas/libricssdatamodule.py:73-106): hop = int(seg_len*(1-overlap)),
+    the last chunk is zero padded and ends the loop.  Returns ([n, seg_len] tensor, pad_len)."""
+    hop = int(seg_len * (1 - overlap))
+    n, start, pad_len, segs = wav.shape[-1], 0, 0, []
+    while start < n:
+        seg = wav[start:start + seg_len]
+        if start + seg_len > n:
+            pad_len = start + seg_len - n
+            seg = torch.cat([seg, torch.zeros(pad_len, dtype=seg.dtype)])
+            start += pad_len
+        segs.append(seg)
+        start += hop
+    return torch.stack(segs), pad_len
+
+
+def css_stitch(ests, overlap_len, pad_len, trim_like_reference=False):
+    """Stitching of audio_test_css.py:108-134.  ests: [n_chunks, 2, seg_len] (each chunk separated alone).
+    The permutation of every later chunk is aligned by cosine similarity of its head with the tail of the
+    FIRST chunk (the reference never updates s*_t_minus_1).  `trim_like_reference` reproduces the
+    `[:, :-pad_len]` slice literally (empty output when pad_len == 0)."""
+    out1, out2 = ests[0, 0], ests[0, 1]
+    p1, p2 = ests[0, 0, -overlap_len:], ests[0, 1, -overlap_len:]
+    for k in range(1, ests.shape[0]):
+        e1, e2 = ests[k, 0], ests[k, 1]
+        c1 = F.cosine_similarity(p1, e1[:overlap_len], dim=0) + F.cosine_similarity(p2, e2[:overlap_len], dim=0)
+        c2 = F.cosine_similarity(p1, e2[:overlap_len], dim=0) + F.cosine_similarity(p2, e1[:overlap_len], dim=0)
+        if c1 > c2:
+            out1, out2 = torch.cat([out1, e1[overlap_len:]]), torch.cat([out2, e2[overlap_len:]])
+        else:
+            out1, out2 = torch.cat([out1, e2[overlap_len:]]), torch.cat([out2, e1[overlap_len:]])
+    out = torch.stack([out1, out2])
+    if trim_like_reference or pad_len > 0:
+        out = out[:, :-pad_len] if pad_len > 0 else out[:, :0]
+    return out
+
+
+def css_separate(sd, wav, cfg, segment, overlap):
+    """audio_test_css.main for one recording: chunk, separate every chunk alone (B=1), stitch."""
+    seg_len = int(segment * cfg.sample_rate)
+    segs, pad_len = css_segments(wav, seg_len, overlap)
+    ests = torch.stack([forward(sd, s, cfg) for s in segs])
+    return css_stitch(ests, int(cfg.sample_rate * segment * overlap), pad_len)

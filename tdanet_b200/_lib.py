@@ -87,6 +87,7 @@ _SIGNATURES = {
     "tdanet_gemm": (C.c_int, [C.c_int, fptr, fptr, fptr, fptr, C.c_int, C.c_int, C.c_int, C.c_int, fptr, fptr,
                               C.c_size_t, fptr]),
     "tdanet_gemm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "tdanet_css_stitch": (C.c_int, [fptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fptr, fptr, fptr]),
     "tdanet_pit_loss_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "tdanet_pit_loss": (C.c_int, [fptr, fptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fptr, fptr, fptr, fptr,
                                   fptr, C.c_size_t, fptr]),

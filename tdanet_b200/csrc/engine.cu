@@ -569,6 +569,12 @@ int tdanet_gemm(int gemm_mode, const float* A, const float* W, const float* bias
   return launch_gemm_tc(g, gemm_mode, st);
 }
 
+int tdanet_css_stitch(const float* est, int n_streams, int n_chunks, int seg_len, int overlap, int out_len,
+                      int32_t* swap, float* out, tdanet_stream_t stream) {
+  TD_REQUIRE(est && swap && (out || out_len == 0), "NULL argument");
+  return launch_css_stitch(est, n_streams, n_chunks, seg_len, overlap, out_len, swap, out, (cudaStream_t)stream);
+}
+
 size_t tdanet_pit_loss_scratch_bytes(int batch, int n_src) {
   (void)n_src;
   return pit_scratch_floats(batch) * sizeof(float);

@@ -163,6 +163,10 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st);
 // aux[i] = mode==TF32 ? rna_tf32(w[i]) : w[i] - trunc_tf32(w[i])
 int launch_tf32_prepare(const float* w, float* aux, size_t n, int mode, cudaStream_t st);
 
+// ------------------------------------------------------------------ css.cu
+int launch_css_stitch(const float* est, int n_streams, int n_chunks, int seg_len, int overlap, int out_len,
+                      int32_t* swap, float* out, cudaStream_t st);
+
 // ------------------------------------------------------------------ loss.cu
 int launch_pit_loss(const float* est, const float* tgt, int B, int n_src, int T, int sdr_type,
                     int threshold, float* loss, float* pw, int32_t* perm, float* grad,

@@ -245,3 +245,26 @@ def test_pit_loss_gradient_matches_autograd_of_oracle(name, n_src):
     assert abs(loss.item() - loss_ref.item()) < 2e-4
     assert max_rel(e.grad.cpu() / 2.0, e_ref.grad) < 1e-4
     assert torch.count_nonzero(e.grad[0]) == 0
+
+
+# ----------------------------------------------------------------------------- long-form (CSS)
+@pytest.mark.parametrize("n_samples", [9000, 8000, 11501])
+def test_long_form_matches_oracle_pipeline(n_samples):
+    """Chunk -> separate every chunk alone -> cosine-similarity stitch (audio_test_css.py) on device,
+    against the oracle restatement run chunk by chunk on the host."""
+    from tdanet_b200.look2hear.system import separate_long
+    g = load_golden("best_small")
+    m = build_from_golden("best", g)
+    m.gemm_mode = "fp32"
+    sr = g["sample_rate"]
+    wav = torch.randn(2, n_samples, generator=torch.Generator().manual_seed(n_samples)) * 0.1
+    segment, overlap = 2000 / sr, 0.25
+    out, swap = separate_long(m, wav.to(DEV), segment=segment, overlap=overlap)
+    cfg = oracle_cfg("best", g["kwargs"], sr)
+    sd = golden_state_dict(g)
+    with torch.no_grad():
+        for s in range(2):
+            ref = O.css_separate(sd, wav[s], cfg, segment, overlap)
+            assert out[s].shape == ref.shape
+            assert max_rel(out[s].cpu(), ref) < 5e-5
+    assert swap.shape[0] == 2 and int(swap[:, 0].abs().sum()) == 0

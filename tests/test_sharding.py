@@ -52,3 +52,16 @@ def test_two_rank_sharded_gather(tmp_path):
     res = torch.load(out)
     assert torch.equal(res["full"], torch.arange(21, dtype=torch.float32).view(7, 3) * 2)
     assert res["tmax"].item() == 2.0
+
+
+def test_css_chunking_matches_oracle():
+    """Chunk starts / padding of the long-form runner against the oracle restatement of LibriCSSDataset."""
+    from oracle import tdanet_oracle as O
+    from tdanet_b200.look2hear.system import css_segments
+    for n, seg, ov in [(960000, 32000, 0.25), (64000, 32000, 0.25), (70001, 32000, 0.25), (5000, 2000, 0.5), (1999, 2000, 0.25)]:
+        starts, pad = css_segments(n, seg, ov)
+        segs, pad_o = O.css_segments(torch.arange(n, dtype=torch.float32), seg, ov)
+        assert pad == pad_o and len(starts) == segs.shape[0]
+        for s, row in zip(starts, segs):
+            assert row[0].item() == float(s)
+    assert len(css_segments(960000, 32000, 0.25)[0]) == 40      # BASELINE config #5: 40 chunks per 60 s stream
