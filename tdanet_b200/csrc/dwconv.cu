@@ -251,6 +251,115 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
   if constexpr (STATS) flush_item_stats<NW>(a.stats, b, tot1, tot2, red);
 }
 
+// ----------------------------------------------------------------------------- dw k=5 with fused pooling
+// spp_dw[k] for BEST / MULTRES: besides the raw output and its statistics, the kernel emits the
+// adaptive-average-pooled raw output P_k [B, Lb, C] (bin j = rows [floor(j*L/Lb), ceil((j+1)*L/Lb)),
+// F.adaptive_avg_pool1d).  Pooling commutes with the per-channel affine GlobLN, so
+//   sum_k avgpool(gLN_k(out_k)) = sum_k (scale_k * P_k + shift_k)         (TDANet_best.py:358-364)
+// and the separate pass that re-read every out_k disappears.  Tiles are whole bins: a tile computes
+// rows [lo(ja), hi(jb-1)) and writes / counts rows [lo(ja), lo(jb)), so every bin is owned by one
+// thread and stored plainly (no atomics, no zero-fill); at most one row per tile is computed twice.
+template <int KIND, int S, bool EDGE>
+__device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, int t0, int tw, int tc, const int2* bins,
+                                              int ja, int nb, float& tot1, float& tot2) {
+  constexpr int V = 4, R = (S == 1) ? 8 : 4;
+  Src<KIND, V, EDGE> src;
+  src.init(a.src, b, ch, a.C, nullptr, 0);
+  vf<V> tap[5];
+  load_taps<V>(a.w[0], ch, tap);
+  const vf<V> bias = a.bias[0] ? vload<V>(a.bias[0] + ch) : vzero<V>();
+  vf<V> s1 = vzero<V>(), s2 = vzero<V>(), acc = vzero<V>();
+  int jrel = 0, hi_cur = bins[0].y;
+  float inv_n = 1.f / (float)(bins[0].y - bins[0].x);
+  float* pool = a.pool_out + ((size_t)b * a.Lb + ja) * a.C + ch;
+  constexpr int NR = (R - 1) * S + 5, CARRY = 5 - S;
+  vf<V> xr[NR];
+#pragma unroll
+  for (int i = 0; i < CARRY; ++i) {
+    const int t = t0 * S - 2 + i;
+    xr[R * S + i] = src.finalize(src.load_raw(t), t);
+  }
+  float* outp = a.out + (size_t)b * a.Lout * a.C + ch;
+  for (int t = t0; t < tc; t += R) {
+#pragma unroll
+    for (int i = 0; i < CARRY; ++i) xr[i] = xr[R * S + i];
+    const int base = t * S - 2 + CARRY;
+#pragma unroll
+    for (int i = 0; i < R * S; ++i) xr[CARRY + i] = src.load_raw(base + i);
+#pragma unroll
+    for (int i = 0; i < R * S; ++i) xr[CARRY + i] = src.finalize(xr[CARRY + i], base + i);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = t + r;
+      if (row < tc) {
+        vf<V> y = conv5<V>(tap, xr[r * S], xr[r * S + 1], xr[r * S + 2], xr[r * S + 3], xr[r * S + 4]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) y[e] += bias[e];
+        if (row < tw) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            s1[e] += y[e];
+            s2[e] = fmaf(y[e], y[e], s2[e]);
+          }
+          vstore<V>(outp + row * a.C, y);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += y[e];
+        if (row == hi_cur - 1) {
+          vf<V> m;
+#pragma unroll
+          for (int e = 0; e < V; ++e) m[e] = acc[e] * inv_n;
+          vstore<V>(pool + jrel * a.C, m);
+          ++jrel;
+          const int2 nx = bins[jrel];  // the table has one entry past the tile's last bin
+          const bool both = jrel < nb && nx.x <= row;  // this row is also the first row of the next bin
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = both ? y[e] : 0.f;
+          hi_cur = nx.y;
+          inv_n = 1.f / (float)(nx.y - nx.x);
+        }
+      }
+    }
+  }
+  if (a.chstats) {
+    float* sp = a.chstats + ((size_t)b * 2) * a.C + ch;
+    vred_add<V>(sp, s1);
+    vred_add<V>(sp + a.C, s2);
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    tot1 += s1[e];
+    tot2 += s2[e];
+  }
+}
+
+template <int KIND, int S>
+__global__ void __launch_bounds__(256) dw5_pool_kernel(DwArgs a, int bins_per_cta) {
+  extern __shared__ int2 bins[];  // (lo, hi) of the tile's bins, plus one
+  __shared__ double red[64];
+  constexpr int V = 4, R = (S == 1) ? 8 : 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const int L = a.Lout, Lb = a.Lb;
+  const int ja = blockIdx.x * bins_per_cta, jb = min(ja + bins_per_cta, Lb), nb = jb - ja;
+  for (int i = threadIdx.x; i <= nb; i += blockDim.x) {
+    const long j = ja + i;
+    bins[i] = make_int2((int)((j * L) / Lb), (int)(((j + 1) * L + Lb - 1) / Lb));
+  }
+  __syncthreads();
+  const int t0 = bins[0].x;
+  const int tw = jb < Lb ? bins[nb].x : L;  // rows written / counted by this tile
+  const int tc = bins[nb - 1].y;            // rows computed (the last bin may reach one row further)
+  float tot1[1] = {0.f}, tot2[1] = {0.f};
+  if (ch < a.C) {
+    const int chunks = (tc - t0 + R - 1) / R;
+    const bool interior = t0 * S - 2 >= 0 && (t0 + chunks * R - 1) * S + 2 < a.src.L;
+    if (interior) dw5_pool_body<KIND, S, false>(a, b, ch, t0, tw, tc, bins, ja, nb, tot1[0], tot2[0]);
+    else dw5_pool_body<KIND, S, true>(a, b, ch, t0, tw, tc, bins, ja, nb, tot1[0], tot2[0]);
+  }
+  flush_item_stats<1>(a.stats, b, tot1, tot2, red);
+}
+
 static void pick_tiling(int B, int L, int ctiles, int R, int* rows_per_cta, int* tiles, long target = 148L * 16,
                         int cap = 64) {
   // aim at `target` CTAs in total, at most `cap` rows per CTA, whole chunks of R rows
@@ -292,8 +401,32 @@ static int launch_dw5_k(const DwArgs& a, cudaStream_t st) {
   return fail(TDANET_EINVAL, "dw5: unsupported stride/kind combination");
 }
 
+template <int KIND, int S>
+static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
+  int threads = a.C / 4;
+  if (threads > 256) threads = 256;
+  if (threads < 32) threads = 32;
+  const int ctiles = cdiv(a.C / 4, threads);
+  int rows, tiles;
+  pick_tiling(a.B, a.Lout, ctiles, S == 1 ? 8 : 4, &rows, &tiles);
+  int bpt = (int)(((long)rows * a.Lb + a.Lout / 2) / a.Lout);  // bins per tile ~ rows / (L / Lb)
+  if (bpt < 1) bpt = 1;
+  dim3 grid(cdiv(a.Lb, bpt), ctiles, a.B);
+  TD_LAUNCH((dw5_pool_kernel<KIND, S>), grid, threads, (size_t)(bpt + 1) * sizeof(int2), st, a, bpt);
+  return 0;
+}
+
 int launch_dw5(const DwArgs& a, cudaStream_t st) {
   TD_REQUIRE(a.C % 4 == 0, "dw5: C=%d must be a multiple of 4", a.C);
+  if (a.pool_out) {
+    TD_REQUIRE(a.nw == 1 && a.out && a.stats && !a.relu && !a.round_out && a.Lb > 0 && a.Lb <= a.Lout,
+               "dw5: pooled output needs nw == 1, out, stats and Lb <= Lout");
+    TD_REQUIRE((long)a.src.L * a.C < (1L << 31) && (long)a.Lout * a.C < (1L << 31), "dw5: item too large for 32-bit offsets");
+    if (a.kind == SRC_AFFINE_PRELU && a.stride == 1) return launch_dw5_pool_t<SRC_AFFINE_PRELU, 1>(a, st);
+    if (a.kind == SRC_AFFINE && a.stride == 2) return launch_dw5_pool_t<SRC_AFFINE, 2>(a, st);
+    if (a.kind == SRC_AFFINE && a.stride == 1) return launch_dw5_pool_t<SRC_AFFINE, 1>(a, st);
+    return fail(TDANET_EINVAL, "dw5: pooled output unsupported for kind %d stride %d", a.kind, a.stride);
+  }
   TD_REQUIRE(a.nw == 1 || a.nw == 2, "dw5: nw=%d", a.nw);
   TD_REQUIRE(!(a.nw == 2 && a.out), "dw5: writing needs nw == 1");
   TD_REQUIRE(a.out || a.stats, "dw5: nothing to do");
@@ -750,11 +883,21 @@ static int launch_la_stream(const LaArgs& a, cudaStream_t st) {
   return 0;
 }
 
-// ----------------------------------------------------------------------------- LA statistics, one launch
-// GlobLN statistics of the three LA convolutions before the combine: CTAs [0, tiles_l) stream the
-// local operand (injection recomputed, conv local_embedding), the rest walk the global operand
-// (convs global_act and global_embedding from one read).  Nothing is written but the sums.
-constexpr int SSROWS = SR + SGG;  // rows per ring stage of the local part
+// ----------------------------------------------------------------------------- LA local statistics, one launch
+// GlobLN statistics of local_embedding(x_fused[i]) for EVERY top-down step at once: they depend only on
+// spp_dw[i] and the global feature, not on the top-down chain, so the four scales share one launch
+// (the small scales ride along with the large one instead of paying their own launch and tail).
+// The local operand is streamed (cp.async ring of thread-private columns), the injection recomputed;
+// nothing is written but the sums.
+constexpr int SSG = 5;            // rows of the injected feature per chunk (ratio to it >= 2)
+constexpr int SSROWS = SR + SSG;  // rows per ring stage
+
+struct LocalStatsArgs {
+  int n;
+  DwArgs step[TDANET_MAX_DEPTH];
+  int tile_end[TDANET_MAX_DEPTH];  // exclusive prefix sum of tiles per step
+  int rows;                        // rows per CTA (same for every step)
+};
 
 template <int LKIND, bool EDGE>
 __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch, int t0, int t1, float* ring,
@@ -782,7 +925,7 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
     }
     const int j0 = jl[t - t0 + 4];
 #pragma unroll
-    for (int i = 0; i < SGG; ++i) {
+    for (int i = 0; i < SSG; ++i) {
       const int row = j0 + i;
       const bool ok = row < Lgg;
       cp_async16(st + (SR + i) * colw, gg + (ok ? row : 0) * C, ok);
@@ -851,73 +994,79 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
 }
 
 template <int LKIND>
-__global__ void __launch_bounds__(128, 3) la_stats_kernel(DwArgs loc, DwArgs glo, int rows_l, int tiles_l, int rows_g) {
+__global__ void __launch_bounds__(128, 3) la_local_stats_kernel(LocalStatsArgs p) {
   extern __shared__ __align__(16) float la_smem[];
   __shared__ double red[64];
   constexpr int V = 4;
+  int step = 0;
+  while (step + 1 < p.n && (int)blockIdx.x >= p.tile_end[step]) ++step;
+  const DwArgs& loc = p.step[step];
+  const int tile = blockIdx.x - (step ? p.tile_end[step - 1] : 0);
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
-  if ((int)blockIdx.x < tiles_l) {
-    // ---- local operand, streamed
-    const int Ll = loc.src.L;
-    const int t0 = blockIdx.x * rows_l, t1 = min(t0 + rows_l, Ll);
-    float* ring = la_smem;
-    int* jl = reinterpret_cast<int*>(ring + 2 * SSROWS * blockDim.x * V);
-    fill_nearest(jl, rows_l + 4, t0 - 2, Ll, loc.src.gscale, loc.src.Lg);
-    __syncthreads();
-    float tot1[1] = {0.f}, tot2[1] = {0.f};
-    if (ch < loc.C) {
-      const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0;
-      if (interior) stats_stream_body<LKIND, false>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
-      else stats_stream_body<LKIND, true>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
-    }
-    flush_item_stats<1>(loc.stats, b, tot1, tot2, red);
-  } else {
-    // ---- global operand (plain), two convolutions from one read
-    constexpr int R = 8;
-    const int tile = blockIdx.x - tiles_l;
-    const int t0 = tile * rows_g, t1 = min(t0 + rows_g, glo.Lout);
-    float tot1[2] = {0.f, 0.f}, tot2[2] = {0.f, 0.f};
-    if (ch < glo.C) {
-      const bool interior = t0 - 2 >= 0 && t1 + 2 <= glo.src.L && (t1 - t0) % R == 0;
-      if (interior) dw5_body<SRC_PLAIN, V, 2, 1, R, false, true, false>(glo, b, ch, t0, t1, nullptr, 0, tot1, tot2);
-      else dw5_body<SRC_PLAIN, V, 2, 1, R, false, true, true>(glo, b, ch, t0, t1, nullptr, 0, tot1, tot2);
-    }
-    flush_item_stats<2>(glo.stats, b, tot1, tot2, red);
+  const int Ll = loc.src.L;
+  const int t0 = tile * p.rows, t1 = min(t0 + p.rows, Ll);
+  float* ring = la_smem;
+  int* jl = reinterpret_cast<int*>(ring + 2 * SSROWS * blockDim.x * V);
+  fill_nearest(jl, p.rows + 4, t0 - 2, Ll, loc.src.gscale, loc.src.Lg);
+  __syncthreads();
+  float tot1[1] = {0.f}, tot2[1] = {0.f};
+  if (ch < loc.C) {
+    const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0;
+    if (interior) stats_stream_body<LKIND, false>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
+    else stats_stream_body<LKIND, true>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
   }
+  flush_item_stats<1>(loc.stats, b, tot1, tot2, red);
 }
 
 template <int LKIND>
-static int launch_la_stats_t(const DwArgs& loc, const DwArgs& glo, cudaStream_t st) {
-  int threads = loc.C / 4;
+static int launch_la_local_stats_t(LocalStatsArgs& p, cudaStream_t st) {
+  const DwArgs& a0 = p.step[0];
+  int threads = a0.C / 4;
   if (threads > 128) threads = 128;
   if (threads < 32) threads = 32;
-  const int ctiles = cdiv(loc.C / 4, threads);
-  int rows_l, tiles_l, rows_g, tiles_g;
-  pick_tiling(loc.B, loc.Lout, ctiles, SR, &rows_l, &tiles_l);
-  pick_tiling(glo.B, glo.Lout, ctiles, 8, &rows_g, &tiles_g);
-  dim3 grid(tiles_l + tiles_g, ctiles, loc.B);
-  const size_t smem = (size_t)2 * SSROWS * threads * 4 * sizeof(float) + (size_t)(rows_l + 4) * sizeof(int);
+  const int ctiles = cdiv(a0.C / 4, threads);
+  long total_rows = 0;
+  for (int i = 0; i < p.n; ++i) total_rows += p.step[i].Lout;
+  int rows, tiles;
+  pick_tiling(a0.B, (int)total_rows, ctiles, SR, &rows, &tiles);
+  p.rows = rows;
+  int acc = 0;
+  for (int i = 0; i < p.n; ++i) {
+    acc += cdiv(p.step[i].Lout, rows);
+    p.tile_end[i] = acc;
+  }
+  dim3 grid(acc, ctiles, a0.B);
+  const size_t smem = (size_t)2 * SSROWS * threads * 4 * sizeof(float) + (size_t)(rows + 4) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
-    TD_CUDA(cudaFuncSetAttribute(la_stats_kernel<LKIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     attr_set = true;
   }
-  TD_LAUNCH((la_stats_kernel<LKIND>), grid, threads, smem, st, loc, glo, rows_l, tiles_l, rows_g);
+  TD_LAUNCH((la_local_stats_kernel<LKIND>), grid, threads, smem, st, p);
   return 0;
 }
 
-int launch_la_stats(const DwArgs& loc, const DwArgs& glo, cudaStream_t st) {
-  TD_REQUIRE(loc.nw == 1 && glo.nw == 2 && loc.stats && glo.stats && !loc.out && !glo.out, "la_stats: bad arguments");
-  const bool stream_ok = glo.kind == SRC_PLAIN && (loc.kind == SRC_INJECT_GATE || loc.kind == SRC_INJECT_ADD) &&
-                         7.0 * loc.src.Lg / loc.src.L <= 1.99 && loc.C % 4 == 0 && loc.C == glo.C && loc.B == glo.B &&
-                         (long)loc.src.L * loc.C < (1L << 31) && (long)glo.src.L * glo.C < (1L << 31);
-  if (stream_ok) {
-    if (loc.kind == SRC_INJECT_GATE) return launch_la_stats_t<SRC_INJECT_GATE>(loc, glo, st);
-    return launch_la_stats_t<SRC_INJECT_ADD>(loc, glo, st);
+int launch_la_local_stats(const DwArgs* steps, int n, cudaStream_t st) {
+  TD_REQUIRE(n >= 1 && n <= TDANET_MAX_DEPTH, "la_local_stats: %d steps", n);
+  bool stream_ok = true;
+  for (int i = 0; i < n; ++i) {
+    const DwArgs& a = steps[i];
+    TD_REQUIRE(a.nw == 1 && a.stats && !a.out && a.stride == 1, "la_local_stats: bad arguments");
+    stream_ok = stream_ok && a.kind == steps[0].kind && (a.kind == SRC_INJECT_GATE || a.kind == SRC_INJECT_ADD) &&
+                7.0 * a.src.Lg / a.src.L <= 3.99 && a.C % 4 == 0 && a.C == steps[0].C && a.B == steps[0].B &&
+                (long)a.src.L * a.C < (1L << 31);
   }
-  if (int e = launch_dw5(loc, st)) return e;
-  return launch_dw5(glo, st);
+  if (stream_ok) {
+    LocalStatsArgs p{};
+    p.n = n;
+    for (int i = 0; i < n; ++i) p.step[i] = steps[i];
+    if (steps[0].kind == SRC_INJECT_GATE) return launch_la_local_stats_t<SRC_INJECT_GATE>(p, st);
+    return launch_la_local_stats_t<SRC_INJECT_ADD>(p, st);
+  }
+  for (int i = 0; i < n; ++i)
+    if (int e = launch_dw5(steps[i], st)) return e;
+  return 0;
 }
 
 template <int LKIND, int GKIND>

@@ -154,13 +154,15 @@ static int make_plan(const tdanet_config_t* c, int B, int T, Plan& p) {
   p.ffn_dw = p.act("ffn_dw", Lb, 2 * C);
   p.fc2 = p.act("fc2", Lb, C);
   p.ga_out = p.act("ga_out", Lb, C);
-  if (c->variant == TDANET_FORK)
-    for (int k = 0; k < c->depth; ++k) {
+  for (int k = 0; k < c->depth; ++k) {
+    // FORK: conv_pool dw / pw outputs.  BEST / MULTRES: pool_pw[k] holds the pooled raw spp_dw[k] output.
+    if (c->variant == TDANET_FORK) {
       snprintf(nm, sizeof nm, "pool_dw%d", k);
       p.pool_dw[k] = p.act(nm, Lb, C);
-      snprintf(nm, sizeof nm, "pool_pw%d", k);
-      p.pool_pw[k] = p.act(nm, Lb, C);
     }
+    snprintf(nm, sizeof nm, "pool_pw%d", k);
+    p.pool_pw[k] = p.act(nm, Lb, C);
+  }
   p.masked = p.act("masked", L0, c->num_sources * Nb);
 
   auto tab = [&](int planes, int ch) { return p.take((size_t)B * planes * ch * sizeof(float)); };
@@ -325,6 +327,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     d.w[0] = w->spp_dw[k].w; d.bias[0] = w->spp_dw[k].b; d.out = x.at(p.spp[k]);
     d.stats = x.at<double>(p.st_spp[k]);
     d.chstats = c->variant == TDANET_BEST ? x.at(p.st_spp_ch[k]) : nullptr;
+    if (c->variant != TDANET_FORK) { d.pool_out = x.at(p.pool_pw[k]); d.Lb = Lb; }  // pooled raw output P_k
     { Tag t(k == 0 ? "spp_dw0" : "spp_dw_s2"); if (int e = launch_dw5(d, x.st)) return e; }
   }
   // global feature at the bottom scale
@@ -346,9 +349,10 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     }
     if (int e = launch_affine_sum(pa, x.st)) return e;
   } else {
-    for (int k = 0; k < depth; ++k) { pa.x[k] = x.at(p.spp[k]); pa.norm[k] = spp_norm(k); pa.L[k] = p.L[k]; }
+    // sum_k avgpool(gLN_k(out_k)) = sum_k gLN-affine_k(P_k): the pooling itself rode in the spp_dw kernels
+    for (int k = 0; k < depth; ++k) { pa.x[k] = x.at(p.pool_pw[k]); pa.norm[k] = spp_norm(k); pa.L[k] = Lb; }
     Tag tp("pool_sum");
-    if (int e = launch_pool_sum(pa, x.st)) return e;
+    if (int e = launch_affine_sum(pa, x.st)) return e;
   }
   if (int e = global_attention(x)) return e;
 
@@ -372,6 +376,17 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     }
     if (int e = launch_coef_inject_gate(ia, B, C, x.st)) return e;
   }
+  // statistics of the local branch of every top-down step (independent of the chain): one launch
+  {
+    DwArgs dl[TDANET_MAX_DEPTH];
+    for (int i = 0; i < depth - 1; ++i) {
+      dl[i] = DwArgs{};
+      dl[i].src = inj_src(i); dl[i].kind = inj_kind; dl[i].B = B; dl[i].C = C; dl[i].Lout = p.L[i]; dl[i].stride = 1;
+      dl[i].nw = 1; dl[i].w[0] = w->last_layer[i].local_embedding.w; dl[i].stats = x.at<double>(p.st_la_l[i]);
+    }
+    Tag t("la_stats");
+    if (int e = launch_la_local_stats(dl, depth - 1, x.st)) return e;
+  }
   // top-down fusion: last_layer[i](x_fused[i], i == depth-2 ? x_fused[i-1] : expanded)
   for (int i = depth - 2; i >= 0; --i) {
     const tdanet_la_t& la = w->last_layer[i];
@@ -384,12 +399,10 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       glo = plain_src(x.at(p.expanded[i + 1]), p.L[i + 1]);
       gkind = SRC_PLAIN;
     }
-    DwArgs dl{}, dg{};
-    dl.src = loc; dl.kind = inj_kind; dl.B = B; dl.C = C; dl.Lout = loc.L; dl.stride = 1; dl.nw = 1;
-    dl.w[0] = la.local_embedding.w; dl.stats = x.at<double>(p.st_la_l[i]);
+    DwArgs dg{};
     dg.src = glo; dg.kind = gkind; dg.B = B; dg.C = C; dg.Lout = glo.L; dg.stride = 1; dg.nw = 2;
     dg.w[0] = la.global_act.w; dg.w[1] = la.global_embedding.w; dg.stats = x.at<double>(p.st_la_g[i]);
-    { Tag t("la_stats"); if (int e = launch_la_stats(dl, dg, x.st)) return e; }
+    { Tag t("la_stats"); if (int e = launch_dw5(dg, x.st)) return e; }
     LaArgs l{};
     l.loc = loc; l.glo = glo; l.lkind = inj_kind; l.gkind = gkind; l.B = B; l.C = C;
     l.wl = la.local_embedding.w; l.wa = la.global_act.w; l.we = la.global_embedding.w;

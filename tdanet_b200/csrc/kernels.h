@@ -41,6 +41,8 @@ struct DwArgs {
   float* out;
   double* stats;
   float* chstats;
+  float* pool_out;  // optional [B, Lb, C]: adaptive-average-pooled raw output (nw == 1, out != null)
+  int Lb;
   int relu;
   int round_out;  // store TF32-rounded values (output only feeds a tensor-core GEMM)
 };
@@ -64,9 +66,8 @@ struct LaArgs {
   int round_out;
 };
 int launch_la_combine(const LaArgs& a, cudaStream_t st);
-// statistics of the three LA convolutions in one launch: loc (nw = 1) and glo (nw = 2, global_act then
-// global_embedding), both stats-only
-int launch_la_stats(const DwArgs& loc, const DwArgs& glo, cudaStream_t st);
+// statistics of local_embedding(x_fused[i]) for every top-down step in one launch (nw = 1, stats only)
+int launch_la_local_stats(const DwArgs* steps, int n, cudaStream_t st);
 
 // ------------------------------------------------------------------ coef.cu
 // BEST loc_glo_fus (k=1 LA) closed form -> SRC_INJECT_GATE tables [B,6,C], every scale in one launch
