@@ -109,12 +109,16 @@ def algorithmic_bytes(variant, lengths, B, C=512, c=128):
     blk["spp_dw0"] = 2 * L[0] * C * f
     blk["spp_dw_s2"] = sum((L[k - 1] + L[k]) * C for k in range(1, depth)) * f
     blk["pool_sum"] = (sum(L) + Lb) * C * f
-    stats = comb = 0
+    sl = sg = comb = first = 0
     for i in range(depth - 2, -1, -1):
         Lg = L[i - 1] if i == depth - 2 else L[i + 1]
-        stats += (L[i] + Lg) * C * f
-        comb += (L[i] + Lg + L[i]) * C * f
-    blk["la_stats"], blk["la_combine"] = stats, comb
+        sl += L[i] * C * f
+        sg += Lg * C * f
+        if i == depth - 2:
+            first = (L[i] + Lg + L[i]) * C * f
+        else:
+            comb += (L[i] + Lg + L[i]) * C * f
+    blk["la_stats_local"], blk["la_stats_global"], blk["la_combine"], blk["la_combine_first"] = sl, sg, comb, first
     blk["gemm_res_conv"] = (L[0] * C + 3 * L[0] * c) * f
     blk["gemm_in_proj"] = Lb * 4 * C * f
     blk["gemm_out_proj"] = Lb * 2 * C * f

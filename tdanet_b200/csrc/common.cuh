@@ -126,7 +126,50 @@ __device__ __forceinline__ void vround_tf32(vf<V>& r) {
   for (int i = 0; i < V; ++i) r.v[i] = tf32_rna(r.v[i]);
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// element-wise a*b+c / a+b on V channels; even V goes through the packed fp32x2 pipe of sm_100
+// (FFMA2 / FADD2: one issue slot for two channels)
+template <int V>
+__device__ __forceinline__ vf<V> vfma(const vf<V>& a, const vf<V>& b, const vf<V>& c) {
+  vf<V> r;
+  if constexpr (V % 2 == 0) {
+#pragma unroll
+    for (int e = 0; e < V; e += 2) {
+      const float2 t = __ffma2_rn(make_float2(a.v[e], a.v[e + 1]), make_float2(b.v[e], b.v[e + 1]),
+                                  make_float2(c.v[e], c.v[e + 1]));
+      r.v[e] = t.x;
+      r.v[e + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < V; ++e) r.v[e] = fmaf(a.v[e], b.v[e], c.v[e]);
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ vf<V> vadd(const vf<V>& a, const vf<V>& b) {
+  vf<V> r;
+  if constexpr (V % 2 == 0) {
+#pragma unroll
+    for (int e = 0; e < V; e += 2) {
+      const float2 t = __fadd2_rn(make_float2(a.v[e], a.v[e + 1]), make_float2(b.v[e], b.v[e + 1]));
+      r.v[e] = t.x;
+      r.v[e + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < V; ++e) r.v[e] = a.v[e] + b.v[e];
+  }
+  return r;
+}
+
+// sigmoid on the SFU: 1 / (1 + 2^(-x*log2(e))) with ex2.approx / rcp.approx (4 instructions; exact limits
+// 0 and 1 for large |x|, relative error ~1e-6)
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 __device__ __forceinline__ float preluf_(float x, float a) { return x >= 0.f ? x : a * x; }
 
 __device__ __forceinline__ float warp_sum(float v) {

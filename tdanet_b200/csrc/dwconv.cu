@@ -76,9 +76,7 @@ struct Src {
     if constexpr (KIND == SRC_PLAIN) {
       return r;
     } else if constexpr (KIND == SRC_AFFINE) {
-#pragma unroll
-      for (int e = 0; e < V; ++e) r[e] = fmaf(r[e], c0_[e], c1_[e]);
-      return r;
+      return vfma<V>(r, c0_, c1_);
     } else if constexpr (KIND == SRC_AFFINE_PRELU) {
 #pragma unroll
       for (int e = 0; e < V; ++e) r[e] = preluf_(fmaf(r[e], c0_[e], c1_[e]), slope);
@@ -118,18 +116,33 @@ __device__ __forceinline__ void load_taps(const float* __restrict__ w, int ch, v
     for (int j = 0; j < 5; ++j) tap[j][e] = __ldg(p + e * 5 + j);
 }
 
+// 5-tap depthwise convolution of V channels; pairs of channels go through the packed fp32x2 pipe
+// (FFMA2 on sm_100: one issue slot for two channels)
 template <int V>
 __device__ __forceinline__ vf<V> conv5(const vf<V> (&tap)[5], const vf<V>& x0, const vf<V>& x1,
                                        const vf<V>& x2, const vf<V>& x3, const vf<V>& x4) {
   vf<V> r;
+  if constexpr (V % 2 == 0) {
 #pragma unroll
-  for (int e = 0; e < V; ++e) {
-    float acc = tap[0][e] * x0[e];
-    acc = fmaf(tap[1][e], x1[e], acc);
-    acc = fmaf(tap[2][e], x2[e], acc);
-    acc = fmaf(tap[3][e], x3[e], acc);
-    acc = fmaf(tap[4][e], x4[e], acc);
-    r[e] = acc;
+    for (int e = 0; e < V; e += 2) {
+      float2 acc = __fmul2_rn(make_float2(tap[0][e], tap[0][e + 1]), make_float2(x0[e], x0[e + 1]));
+      acc = __ffma2_rn(make_float2(tap[1][e], tap[1][e + 1]), make_float2(x1[e], x1[e + 1]), acc);
+      acc = __ffma2_rn(make_float2(tap[2][e], tap[2][e + 1]), make_float2(x2[e], x2[e + 1]), acc);
+      acc = __ffma2_rn(make_float2(tap[3][e], tap[3][e + 1]), make_float2(x3[e], x3[e + 1]), acc);
+      acc = __ffma2_rn(make_float2(tap[4][e], tap[4][e + 1]), make_float2(x4[e], x4[e + 1]), acc);
+      r[e] = acc.x;
+      r[e + 1] = acc.y;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float acc = tap[0][e] * x0[e];
+      acc = fmaf(tap[1][e], x1[e], acc);
+      acc = fmaf(tap[2][e], x2[e], acc);
+      acc = fmaf(tap[3][e], x3[e], acc);
+      acc = fmaf(tap[4][e], x4[e], acc);
+      r[e] = acc;
+    }
   }
   return r;
 }
@@ -171,15 +184,10 @@ __device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0,
       if (!EDGE || t + r < t1) {
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-          vf<V> y = conv5<V>(tap[i], xr[r * S], xr[r * S + 1], xr[r * S + 2], xr[r * S + 3], xr[r * S + 4]);
-#pragma unroll
-          for (int e = 0; e < V; ++e) y[e] += bias[i][e];
+          vf<V> y = vadd<V>(conv5<V>(tap[i], xr[r * S], xr[r * S + 1], xr[r * S + 2], xr[r * S + 3], xr[r * S + 4]), bias[i]);
           if constexpr (STATS) {
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-              s1[i][e] += y[e];
-              s2[i][e] = fmaf(y[e], y[e], s2[i][e]);
-            }
+            s1[i] = vadd<V>(s1[i], y);
+            s2[i] = vfma<V>(y, y, s2[i]);
           }
           if constexpr (WRITE) {
             if (a.relu) {
@@ -292,19 +300,13 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
     for (int r = 0; r < R; ++r) {
       const int row = t + r;
       if (row < tc) {
-        vf<V> y = conv5<V>(tap, xr[r * S], xr[r * S + 1], xr[r * S + 2], xr[r * S + 3], xr[r * S + 4]);
-#pragma unroll
-        for (int e = 0; e < V; ++e) y[e] += bias[e];
+        const vf<V> y = vadd<V>(conv5<V>(tap, xr[r * S], xr[r * S + 1], xr[r * S + 2], xr[r * S + 3], xr[r * S + 4]), bias);
         if (row < tw) {
-#pragma unroll
-          for (int e = 0; e < V; ++e) {
-            s1[e] += y[e];
-            s2[e] = fmaf(y[e], y[e], s2[e]);
-          }
+          s1 = vadd<V>(s1, y);
+          s2 = vfma<V>(y, y, s2);
           vstore<V>(outp + row * a.C, y);
         }
-#pragma unroll
-        for (int e = 0; e < V; ++e) acc[e] += y[e];
+        acc = vadd<V>(acc, y);
         if (row == hi_cur - 1) {
           vf<V> m;
 #pragma unroll
@@ -546,13 +548,10 @@ __device__ __forceinline__ void la_body(const LaArgs& a, int b, int ch, int t0, 
 #pragma unroll
       for (int i = 0; i < GC; ++i) {
         if (i < nc) {
-          vf<V> ca = conv5<V>(wa, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]);
-          vf<V> ce = conv5<V>(we, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]);
+          vf<V> ca = vfma<V>(sA, conv5<V>(wa, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]), hA);
+          const vf<V> ce = vfma<V>(sE, conv5<V>(we, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]), hE);
 #pragma unroll
-          for (int e = 0; e < V; ++e) {
-            ca[e] = sigmoidf_(fmaf(sA[e], ca[e], hA[e]));
-            ce[e] = fmaf(sE[e], ce[e], hE[e]);
-          }
+          for (int e = 0; e < V; ++e) ca[e] = sigmoidf_(ca[e]);
           vstore<V>(mine + (2 * i) * colw, ca);
           vstore<V>(mine + (2 * i + 1) * colw, ce);
         }
@@ -601,7 +600,7 @@ __device__ __forceinline__ void la_body(const LaArgs& a, int b, int ch, int t0, 
 }
 
 template <int LKIND, int GKIND, int V, int GC>
-__global__ void __launch_bounds__(256, 2) la_combine_kernel(LaArgs a, int rows_per_cta, int gspan) {
+__global__ void __launch_bounds__(256, GC == 0 ? 1 : 2) la_combine_kernel(LaArgs a, int rows_per_cta, int gspan) {
   extern __shared__ __align__(16) float la_smem[];
   constexpr int R = 8;
   const int b = blockIdx.z;
@@ -661,14 +660,8 @@ struct Injector {
         eg = grow;
       }
     }
-    if constexpr (KIND == SRC_INJECT_GATE) {
-#pragma unroll
-      for (int e = 0; e < V; ++e) raw[e] = fmaf(fmaf(raw[e], al[e], bl[e]), sg[e], eg[e]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < V; ++e) raw[e] = fmaf(raw[e], al[e], bl[e]) + eg[e];
-    }
-    return raw;
+    if constexpr (KIND == SRC_INJECT_GATE) return vfma<V>(vfma<V>(raw, al, bl), sg, eg);
+    else return vadd<V>(vfma<V>(raw, al, bl), eg);
   }
 };
 
@@ -791,13 +784,10 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
 #pragma unroll
       for (int i = 0; i < SGC; ++i) {
         if (i < nc) {
-          vf<V> ca = conv5<V>(wa, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]);
-          vf<V> ce = conv5<V>(we, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]);
+          vf<V> ca = vfma<V>(sA, conv5<V>(wa, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]), hA);
+          const vf<V> ce = vfma<V>(sE, conv5<V>(we, gr[i], gr[i + 1], gr[i + 2], gr[i + 3], gr[i + 4]), hE);
 #pragma unroll
-          for (int e = 0; e < V; ++e) {
-            ca[e] = sigmoidf_(fmaf(sA[e], ca[e], hA[e]));
-            ce[e] = fmaf(sE[e], ce[e], hE[e]);
-          }
+          for (int e = 0; e < V; ++e) ca[e] = sigmoidf_(ca[e]);
           vstore<V>(mine + (2 * i) * colw, ca);
           vstore<V>(mine + (2 * i + 1) * colw, ce);
         }
@@ -822,9 +812,7 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
         const vf<V> cl = conv5<V>(wl, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
         const int j = jc[t + r - t0];
         const vf<V> ga = lds4(mine + (2 * (j - jlo)) * colw), ge = lds4(mine + (2 * (j - jlo) + 1) * colw);
-        vf<V> y;
-#pragma unroll
-        for (int e = 0; e < V; ++e) y[e] = fmaf(fmaf(sL[e], cl[e], hL[e]), ga[e], ge[e]);
+        vf<V> y = vfma<V>(vfma<V>(sL, cl, hL), ga, ge);
         if (a.round_out) vround_tf32<V>(y);
         vstore<V>(outp + (t + r) * C, y);
       }
@@ -978,11 +966,8 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
     for (int r = 0; r < SR; ++r) {
       if (!EDGE || t + r < t1) {
         const vf<V> y = conv5<V>(wl, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          s1[e] += y[e];
-          s2[e] = fmaf(y[e], y[e], s2[e]);
-        }
+        s1 = vadd<V>(s1, y);
+        s2 = vfma<V>(y, y, s2);
       }
     }
   }

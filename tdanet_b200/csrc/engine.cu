@@ -384,7 +384,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       dl[i].src = inj_src(i); dl[i].kind = inj_kind; dl[i].B = B; dl[i].C = C; dl[i].Lout = p.L[i]; dl[i].stride = 1;
       dl[i].nw = 1; dl[i].w[0] = w->last_layer[i].local_embedding.w; dl[i].stats = x.at<double>(p.st_la_l[i]);
     }
-    Tag t("la_stats");
+    Tag t("la_stats_local");
     if (int e = launch_la_local_stats(dl, depth - 1, x.st)) return e;
   }
   // top-down fusion: last_layer[i](x_fused[i], i == depth-2 ? x_fused[i-1] : expanded)
@@ -402,7 +402,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     DwArgs dg{};
     dg.src = glo; dg.kind = gkind; dg.B = B; dg.C = C; dg.Lout = glo.L; dg.stride = 1; dg.nw = 2;
     dg.w[0] = la.global_act.w; dg.w[1] = la.global_embedding.w; dg.stats = x.at<double>(p.st_la_g[i]);
-    { Tag t("la_stats"); if (int e = launch_dw5(dg, x.st)) return e; }
+    { Tag t("la_stats_global"); if (int e = launch_dw5(dg, x.st)) return e; }
     LaArgs l{};
     l.loc = loc; l.glo = glo; l.lkind = inj_kind; l.gkind = gkind; l.B = B; l.C = C;
     l.wl = la.local_embedding.w; l.wa = la.global_act.w; l.we = la.global_embedding.w;
@@ -411,7 +411,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     l.nE = norm_ref(x, p.st_la_g[i] + 2 * sizeof(double), 4, (double)glo.L * C, la.global_embedding.gamma, la.global_embedding.beta);
     l.out = x.at(p.expanded[i]); l.scale = nearest_scale(glo.L, loc.L);
     l.round_out = i == 0 && x.rnd();  // expanded[0] only feeds res_conv
-    { Tag t("la_combine"); if (int e = launch_la_combine(l, x.st)) return e; }
+    { Tag t(i == depth - 2 ? "la_combine_first" : "la_combine"); if (int e = launch_la_combine(l, x.st)) return e; }
   }
   // res_conv + residual (+ concat_block for the next iteration)
   g = GemmArgs{};
