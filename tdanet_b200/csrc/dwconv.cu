@@ -451,6 +451,47 @@ int launch_dw5(const DwArgs& a, cudaStream_t st) {
   return fail(TDANET_EINVAL, "dw5: unsupported source kind %d (nw=%d)", a.kind, a.nw);
 }
 
+// ----------------------------------------------------------------------------- materialise an injected operand
+// y[t] = x_fused[k][t] written out (only for the two small tensors of the first top-down step, whose
+// down-sampling access pattern would otherwise recompute every injected row five times)
+template <int KIND>
+__global__ void __launch_bounds__(256) inject_materialize_kernel(SrcDesc sd, int C, float* __restrict__ out, int rows_per_cta) {
+  extern __shared__ int jtab[];
+  constexpr int V = 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const int t0 = blockIdx.x * rows_per_cta, t1 = min(t0 + rows_per_cta, sd.L);
+  fill_nearest(jtab, rows_per_cta, t0, sd.L, sd.gscale, sd.Lg);
+  __syncthreads();
+  if (ch >= C) return;
+  Src<KIND, V, false> src;
+  src.init(sd, b, ch, C, jtab, t0);
+  float* op = out + (size_t)b * sd.L * C + ch;
+  for (int t = t0; t < t1; t += 4) {
+    vf<V> r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = t + i < t1 ? src.load_raw(t + i) : vzero<V>();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (t + i < t1) vstore<V>(op + (t + i) * C, src.finalize(r[i], t + i));
+  }
+}
+
+int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, cudaStream_t st) {
+  TD_REQUIRE(C % 4 == 0 && (long)src.L * C < (1L << 31), "inject_materialize: C=%d L=%d", C, src.L);
+  int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
+  const int rows = 16;
+  dim3 grid(cdiv(src.L, rows), cdiv(C / 4, threads), B);
+  if (kind == SRC_INJECT_GATE) {
+    TD_LAUNCH((inject_materialize_kernel<SRC_INJECT_GATE>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
+  } else if (kind == SRC_INJECT_ADD) {
+    TD_LAUNCH((inject_materialize_kernel<SRC_INJECT_ADD>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
+  } else {
+    return fail(TDANET_EINVAL, "inject_materialize: kind %d", kind);
+  }
+  return 0;
+}
+
 // ----------------------------------------------------------------------------- generic dw (fork conv_pool)
 template <int KIND>
 __global__ void dw_generic_kernel(SrcDesc sd, int C, int Lout, int ks, int stride,

@@ -68,6 +68,7 @@ struct Plan {
   size_t enc, x0, u[2], proj, spp[TDANET_MAX_DEPTH], expanded[TDANET_MAX_DEPTH];
   size_t ga_in, attn_in, qkv, attn_ctx, attn_out, ga_mid, fc1, ffn_dw, fc2, ga_out;
   size_t pool_dw[TDANET_MAX_DEPTH], pool_pw[TDANET_MAX_DEPTH];
+  size_t fused_a, fused_b;  // x_fused[depth-2] and its "global" partner of the first top-down step, materialised
   size_t masked;
   // closed-form loc_glo_fus coefficient tables (BEST), [B,6,C] per scale
   size_t inj_coef[TDANET_MAX_DEPTH];
@@ -163,6 +164,8 @@ static int make_plan(const tdanet_config_t* c, int B, int T, Plan& p) {
     snprintf(nm, sizeof nm, "pool_pw%d", k);
     p.pool_pw[k] = p.act(nm, Lb, C);
   }
+  p.fused_a = p.act("fused_a", p.L[c->depth - 2], C);
+  p.fused_b = p.act("fused_b", p.L[(c->depth - 3 + c->depth) % c->depth], C);
   p.masked = p.act("masked", L0, c->num_sources * Nb);
 
   auto tab = [&](int planes, int ch) { return p.take((size_t)B * planes * ch * sizeof(float)); };
@@ -391,10 +394,17 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   for (int i = depth - 2; i >= 0; --i) {
     const tdanet_la_t& la = w->last_layer[i];
     SrcDesc loc = inj_src(i), glo;
-    int gkind;
+    int lkind = inj_kind, gkind;
     if (i == depth - 2) {
-      glo = inj_src((i - 1 + depth) % depth);  // python x_fused[i-1]: the finer neighbour (or [-1])
-      gkind = inj_kind;
+      // python x_fused[i-1]: the finer neighbour (or [-1]).  Both operands of this step are small and its
+      // nearest *down*-sampling would re-derive every injected row five times: write the two tensors out once.
+      const SrcDesc gsrc = inj_src((i - 1 + depth) % depth);
+      Tag t("la_combine_first");
+      if (int e = launch_inject_materialize(loc, inj_kind, B, C, x.at(p.fused_a), x.st)) return e;
+      if (int e = launch_inject_materialize(gsrc, inj_kind, B, C, x.at(p.fused_b), x.st)) return e;
+      loc = plain_src(x.at(p.fused_a), loc.L);
+      glo = plain_src(x.at(p.fused_b), gsrc.L);
+      lkind = gkind = SRC_PLAIN;
     } else {
       glo = plain_src(x.at(p.expanded[i + 1]), p.L[i + 1]);
       gkind = SRC_PLAIN;
@@ -404,7 +414,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     dg.w[0] = la.global_act.w; dg.w[1] = la.global_embedding.w; dg.stats = x.at<double>(p.st_la_g[i]);
     { Tag t("la_stats_global"); if (int e = launch_dw5(dg, x.st)) return e; }
     LaArgs l{};
-    l.loc = loc; l.glo = glo; l.lkind = inj_kind; l.gkind = gkind; l.B = B; l.C = C;
+    l.loc = loc; l.glo = glo; l.lkind = lkind; l.gkind = gkind; l.B = B; l.C = C;
     l.wl = la.local_embedding.w; l.wa = la.global_act.w; l.we = la.global_embedding.w;
     l.nL = norm_ref(x, p.st_la_l[i], 2, (double)loc.L * C, la.local_embedding.gamma, la.local_embedding.beta);
     l.nA = norm_ref(x, p.st_la_g[i], 4, (double)glo.L * C, la.global_act.gamma, la.global_act.beta);

@@ -52,6 +52,9 @@ int launch_dw5(const DwArgs& a, cudaStream_t st);
 int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int ks, int stride,
                       const float* w, const float* bias, float* out, int round_out, cudaStream_t st);
 
+// out[b, t, :] = injected operand (SRC_INJECT_GATE / SRC_INJECT_ADD) written out, [B, src.L, C]
+int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, cudaStream_t st);
+
 // LA combine (TDANet_best.py:277-292 with the three GlobLN folded into coef tables):
 //   out[t] = (cL.s*dw_l(xl)[t] + cL.h) * sigmoid(cA.s*dw_a(xg)[j] + cA.h) + (cE.s*dw_e(xg)[j] + cE.h)
 //   j = nearest(t; Lg -> Ll)
