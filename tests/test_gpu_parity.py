@@ -268,3 +268,51 @@ def test_long_form_matches_oracle_pipeline(n_samples):
             assert out[s].shape == ref.shape
             assert max_rel(out[s].cpu(), ref) < 5e-5
     assert swap.shape[0] == 2 and int(swap[:, 0].abs().sum()) == 0
+
+
+# ----------------------------------------------------------------------------- ragged / edge shapes
+@pytest.mark.parametrize("variant", list(CLASSES))
+@pytest.mark.parametrize("T", [640, 1001, 2999, 4097, 12345])
+def test_odd_lengths_and_single_item(variant, T):
+    """Lengths that are not multiples of the window / hop / any tile size, batch 1 and batch 5:
+    exercises every partial-tile and boundary path (the reference pads inside the model)."""
+    g = load_golden(f"{variant}_small")
+    m = build_from_golden(variant, g)
+    m.gemm_mode = "fp32"
+    cfg = oracle_cfg(variant, g["kwargs"], g["sample_rate"])
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}     # full positional-encoding table
+    for B in (1, 5):
+        x = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(T + B)) * 0.1
+        with torch.no_grad():
+            ref = O.forward(sd, x, cfg)
+            y = m(x.to(DEV)).cpu()
+        assert y.shape == ref.shape == (B, 2, T)
+        assert max_rel(y, ref) < 5e-5, (variant, T, B)
+
+
+def test_deeper_and_shallower_unets():
+    """upsampling_depth 3 and 6 (the reference default is 4, every config uses 5)."""
+    for depth in (3, 6):
+        kw = dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=depth, enc_kernel_size=2, num_sources=2)
+        torch.manual_seed(depth)
+        m = M.TDANetBest(sample_rate=16000, **kw).eval()
+        x = torch.randn(2, 1, 5000, generator=torch.Generator().manual_seed(9)) * 0.1
+        with torch.no_grad():
+            ref = O.forward({k: v for k, v in m.state_dict().items()}, x, O.OracleConfig(variant="best", sample_rate=16000, **kw))
+            m = m.to(DEV)
+            m.gemm_mode = "fp32"
+            y = m(x.to(DEV)).cpu()
+        assert max_rel(y, ref) < 5e-5, depth
+
+
+def test_three_sources():
+    kw = dict(out_channels=16, in_channels=32, num_blocks=1, upsampling_depth=4, enc_kernel_size=2, num_sources=3)
+    torch.manual_seed(2)
+    m = M.TDANetBest(sample_rate=16000, **kw).eval()
+    x = torch.randn(2, 1, 3000, generator=torch.Generator().manual_seed(4)) * 0.1
+    with torch.no_grad():
+        ref = O.forward({k: v for k, v in m.state_dict().items()}, x, O.OracleConfig(variant="best", sample_rate=16000, **kw))
+        m = m.to(DEV)
+        m.gemm_mode = "fp32"
+        y = m(x.to(DEV)).cpu()
+    assert y.shape == (2, 3, 3000) and max_rel(y, ref) < 5e-5
