@@ -62,6 +62,12 @@ enum tdanet_gemm_mode {
   TDANET_GEMM_TF32X3 = 2  /* tcgen05 kind::tf32, weights split hi+lo (two MMA passes)     */
 };
 
+enum tdanet_act_dtype {
+  TDANET_ACT_F32 = 0,   /* every intermediate in fp32                                              */
+  TDANET_ACT_BF16 = 1   /* proj_1x1 / spp_dw / top-down outputs stored as bf16 (fp32 arithmetic and
+                           statistics); needs a tensor-core gemm_mode; the "bf16 mode" tolerance    */
+};
+
 /* Static description of one model instance (constructor kwargs of the reference class). */
 typedef struct tdanet_config {
   int32_t variant;       /* enum tdanet_variant                                           */
@@ -78,7 +84,8 @@ typedef struct tdanet_config {
   int32_t gemm_mode;     /* enum tdanet_gemm_mode                                          */
   int32_t attn_group;    /* batch items that attend to each other (BEST/FORK: the reference
                             batch being emulated); 0 = the whole batch of the call         */
-  int32_t reserved[3];
+  int32_t act_dtype;     /* enum tdanet_act_dtype: storage of the large activations             */
+  int32_t reserved[2];
 } tdanet_config_t;
 
 /* conv weight (+ optional bias) followed by a GlobLN: ConvNorm / DilatedConvNorm / ConvNormAct */

@@ -15,6 +15,7 @@ MAX_DEPTH = 8
 MAX_ENC = 4
 VARIANTS = {"best": 0, "fork": 1, "multres": 2}
 GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+ACT_DTYPES = {"fp32": 0, "bf16": 1}
 SDR_TYPES = {"snr": 0, "sisdr": 1, "sdsdr": 2}
 
 fptr = C.c_void_p  # device pointers travel as integers
@@ -23,7 +24,7 @@ fptr = C.c_void_p  # device pointers travel as integers
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "variant", "out_channels", "in_channels", "num_blocks", "depth", "enc_kernel", "enc_stride",
-        "n_basis", "num_sources", "enc_convs", "n_head", "gemm_mode", "attn_group")] + [("reserved", C.c_int32 * 3)]
+        "n_basis", "num_sources", "enc_convs", "n_head", "gemm_mode", "attn_group", "act_dtype")] + [("reserved", C.c_int32 * 2)]
 
 
 class ConvNorm(C.Structure):

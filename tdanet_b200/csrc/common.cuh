@@ -1,6 +1,7 @@
 // Shared device/host helpers for the tdanet_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <atomic>
 #include <cstdio>
@@ -96,6 +97,66 @@ __device__ __forceinline__ void vstore(float* __restrict__ p, const vf<V>& r) {
     *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
   } else {
     *p = r.v[0];
+  }
+}
+
+// Typed activation access: the large activations are stored as fp32 or bf16 (arithmetic is always fp32).
+template <int V>
+__device__ __forceinline__ vf<V> aload(const float* __restrict__ p) { return vload<V>(p); }
+template <int V>
+__device__ __forceinline__ void astore(float* __restrict__ p, const vf<V>& r) { vstore<V>(p, r); }
+template <int V>
+__device__ __forceinline__ vf<V> alds(const float* p) {  // shared memory
+  vf<V> r;
+  if constexpr (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    r.v[0] = t.x; r.v[1] = t.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void bf16x2_unpack(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t bf16x2_pack(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);  // round to nearest even
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+template <int V>
+__device__ __forceinline__ vf<V> aload(const __nv_bfloat16* __restrict__ p) {
+  vf<V> r;
+  if constexpr (V == 4) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    bf16x2_unpack(t.x, r.v[0], r.v[1]);
+    bf16x2_unpack(t.y, r.v[2], r.v[3]);
+  } else {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    bf16x2_unpack(t, r.v[0], r.v[1]);
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ vf<V> alds(const __nv_bfloat16* p) {
+  vf<V> r;
+  if constexpr (V == 4) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    bf16x2_unpack(t.x, r.v[0], r.v[1]);
+    bf16x2_unpack(t.y, r.v[2], r.v[3]);
+  } else {
+    const uint32_t t = *reinterpret_cast<const uint32_t*>(p);
+    bf16x2_unpack(t, r.v[0], r.v[1]);
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void astore(__nv_bfloat16* __restrict__ p, const vf<V>& r) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(bf16x2_pack(r.v[0], r.v[1]), bf16x2_pack(r.v[2], r.v[3]));
+  } else {
+    *reinterpret_cast<uint32_t*>(p) = bf16x2_pack(r.v[0], r.v[1]);
   }
 }
 

@@ -105,6 +105,13 @@ static int check_config(const tdanet_config_t* c) {
   TD_REQUIRE(c->enc_kernel > 0 && c->enc_kernel % 4 == 0 && c->enc_stride == c->enc_kernel / 4, "encoder window %d / hop %d", c->enc_kernel, c->enc_stride);
   TD_REQUIRE(c->num_sources == 2 || c->num_sources == 3, "num_sources %d", c->num_sources);
   TD_REQUIRE(c->gemm_mode >= TDANET_GEMM_FP32 && c->gemm_mode <= TDANET_GEMM_TF32X3, "gemm_mode %d", c->gemm_mode);
+  TD_REQUIRE(c->act_dtype == TDANET_ACT_F32 || c->act_dtype == TDANET_ACT_BF16, "act_dtype %d", c->act_dtype);
+  if (c->act_dtype == TDANET_ACT_BF16) {
+    TD_REQUIRE(c->gemm_mode != TDANET_GEMM_FP32, "bf16 activation storage needs a tensor-core gemm_mode");
+    TD_REQUIRE(c->out_channels % 32 == 0 && c->in_channels % 64 == 0,
+               "bf16 activation storage needs out_channels %% 32 == 0 and in_channels %% 64 == 0 (got %d / %d)",
+               c->out_channels, c->in_channels);
+  }
   if (c->variant == TDANET_MULTRES) {
     TD_REQUIRE(c->enc_convs >= 1 && c->enc_convs <= TDANET_MAX_ENC && c->out_channels % c->enc_convs == 0,
                "MULTRES: out_channels %d not divisible by kernels %d", c->out_channels, c->enc_convs);
@@ -209,6 +216,8 @@ struct Ctx {
   cudaStream_t st;
   // producers of GEMM-only operands store TF32-rounded values when the tensor-core path is on
   int rnd() const { return c->gemm_mode != TDANET_GEMM_FP32; }
+  // large activations (proj, spp, expanded, materialised x_fused) stored as bf16
+  int bf() const { return c->act_dtype == TDANET_ACT_BF16; }
   template <class T = float>
   T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
 };
@@ -225,7 +234,11 @@ static int prepare_weights(const Ctx& x) {
   const size_t C = c->in_channels, cc = c->out_channels;
   const int m = c->gemm_mode;
   if (int e = launch_tf32_prepare(x.w->proj.w, x.at(x.p->aux_proj), C * cc, m, x.st)) return e;
-  if (int e = launch_tf32_prepare(x.w->res_w, x.at(x.p->aux_res), C * cc, m, x.st)) return e;
+  if (x.bf()) {  // res_conv reads its bf16 operand against a bf16 copy of the weight
+    if (int e = launch_bf16_prepare(x.w->res_w, x.at(x.p->aux_res), C * cc, x.st)) return e;
+  } else {
+    if (int e = launch_tf32_prepare(x.w->res_w, x.at(x.p->aux_res), C * cc, m, x.st)) return e;
+  }
   if (int e = launch_tf32_prepare(x.w->in_proj_w, x.at(x.p->aux_in), 3 * C * C, m, x.st)) return e;
   if (int e = launch_tf32_prepare(x.w->out_proj_w, x.at(x.p->aux_out), C * C, m, x.st)) return e;
   if (int e = launch_tf32_prepare(x.w->fc1.w, x.at(x.p->aux_fc1), 2 * C * C, m, x.st)) return e;
@@ -310,6 +323,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   GemmArgs g{};
   g.A = in; g.W = w->proj.w; g.bias = w->proj.b; g.D = x.at(p.proj);
   g.B = B; g.L = p.L[0]; g.N = C; g.K = cc; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_proj);
+  g.d_bf16 = x.bf();
   { Tag t("gemm_proj"); if (int e = gemm(x, g, p.aux_proj)) return e; }
   Tag tag("coef");
   auto spp_norm = [&](int k) {
@@ -326,7 +340,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       d.src = affine_src(x.at(p.spp[k - 1]), p.L[k - 1], spp_norm(k - 1));
       d.kind = SRC_AFFINE;
     }
-    d.B = B; d.C = C; d.Lout = p.L[k]; d.stride = k == 0 ? 1 : 2; d.nw = 1;
+    d.B = B; d.C = C; d.Lout = p.L[k]; d.stride = k == 0 ? 1 : 2; d.nw = 1; d.act_bf16 = x.bf();
     d.w[0] = w->spp_dw[k].w; d.bias[0] = w->spp_dw[k].b; d.out = x.at(p.spp[k]);
     d.stats = x.at<double>(p.st_spp[k]);
     d.chstats = c->variant == TDANET_BEST ? x.at(p.st_spp_ch[k]) : nullptr;
@@ -343,7 +357,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       const tdanet_sepconvnorm_t& q = w->conv_pool[j];
       Tag tp("conv_pool");
       if (int e = launch_dw_generic(affine_src(x.at(p.spp[k]), p.L[k], spp_norm(k)), SRC_AFFINE, B, C, Lb,
-                                    ks, s, q.dw_w, q.dw_b, x.at(p.pool_dw[k]), x.rnd(), x.st)) return e;
+                                    ks, s, q.dw_w, q.dw_b, x.at(p.pool_dw[k]), x.rnd(), x.bf(), x.st)) return e;
       g = GemmArgs{};
       g.A = x.at(p.pool_dw[k]); g.W = q.pw_w; g.bias = q.pw_b; g.D = x.at(p.pool_pw[k]);
       g.B = B; g.L = Lb; g.N = C; g.K = C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_pool[k]);
@@ -386,6 +400,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       dl[i] = DwArgs{};
       dl[i].src = inj_src(i); dl[i].kind = inj_kind; dl[i].B = B; dl[i].C = C; dl[i].Lout = p.L[i]; dl[i].stride = 1;
       dl[i].nw = 1; dl[i].w[0] = w->last_layer[i].local_embedding.w; dl[i].stats = x.at<double>(p.st_la_l[i]);
+      dl[i].act_bf16 = x.bf();
     }
     Tag t("la_stats_local");
     if (int e = launch_la_local_stats(dl, depth - 1, x.st)) return e;
@@ -400,8 +415,8 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       // nearest *down*-sampling would re-derive every injected row five times: write the two tensors out once.
       const SrcDesc gsrc = inj_src((i - 1 + depth) % depth);
       Tag t("la_combine_first");
-      if (int e = launch_inject_materialize(loc, inj_kind, B, C, x.at(p.fused_a), x.st)) return e;
-      if (int e = launch_inject_materialize(gsrc, inj_kind, B, C, x.at(p.fused_b), x.st)) return e;
+      if (int e = launch_inject_materialize(loc, inj_kind, B, C, x.at(p.fused_a), x.bf(), x.st)) return e;
+      if (int e = launch_inject_materialize(gsrc, inj_kind, B, C, x.at(p.fused_b), x.bf(), x.st)) return e;
       loc = plain_src(x.at(p.fused_a), loc.L);
       glo = plain_src(x.at(p.fused_b), gsrc.L);
       lkind = gkind = SRC_PLAIN;
@@ -410,7 +425,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       gkind = SRC_PLAIN;
     }
     DwArgs dg{};
-    dg.src = glo; dg.kind = gkind; dg.B = B; dg.C = C; dg.Lout = glo.L; dg.stride = 1; dg.nw = 2;
+    dg.src = glo; dg.kind = gkind; dg.B = B; dg.C = C; dg.Lout = glo.L; dg.stride = 1; dg.nw = 2; dg.act_bf16 = x.bf();
     dg.w[0] = la.global_act.w; dg.w[1] = la.global_embedding.w; dg.stats = x.at<double>(p.st_la_g[i]);
     { Tag t("la_stats_global"); if (int e = launch_dw5(dg, x.st)) return e; }
     LaArgs l{};
@@ -420,7 +435,8 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     l.nA = norm_ref(x, p.st_la_g[i], 4, (double)glo.L * C, la.global_act.gamma, la.global_act.beta);
     l.nE = norm_ref(x, p.st_la_g[i] + 2 * sizeof(double), 4, (double)glo.L * C, la.global_embedding.gamma, la.global_embedding.beta);
     l.out = x.at(p.expanded[i]); l.scale = nearest_scale(glo.L, loc.L);
-    l.round_out = i == 0 && x.rnd();  // expanded[0] only feeds res_conv
+    l.round_out = i == 0 && x.rnd() && !x.bf();  // expanded[0] only feeds res_conv
+    l.act_bf16 = x.bf();
     { Tag t(i == depth - 2 ? "la_combine_first" : "la_combine"); if (int e = launch_la_combine(l, x.st)) return e; }
   }
   // res_conv + residual (+ concat_block for the next iteration)
@@ -428,6 +444,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   g.A = x.at(p.expanded[0]); g.W = w->res_w; g.bias = w->res_b; g.D = out;
   g.B = B; g.L = p.L[0]; g.N = cc; g.K = C; g.epi = EPI_RESIDUAL;
   g.resid = in; g.mix = x.at(p.x0); g.cw = w->concat_w; g.cb = w->concat_b; g.cslope = w->concat_prelu; g.last = last;
+  g.a_bf16 = x.bf();
   Tag tr("gemm_res_conv");
   return gemm(x, g, p.aux_res);
 }

@@ -102,6 +102,17 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with bf16 operands (K = 16 per instruction)
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane i of the quarter)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -144,8 +155,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 // sm_100 UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) /* D = F32 */ | (2u << 7) /* A = TF32 */ | (2u << 10) /* B = TF32 */ |
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool bf16 = false) {
+  const uint32_t fmt = bf16 ? 1u /* BF16 */ : 2u /* TF32 */;
+  return (1u << 4) /* D = F32 */ | (fmt << 7) /* A */ | (fmt << 10) /* B */ |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -164,7 +176,9 @@ struct TcParams {
 //      1 = y = acc + bias + resid; D = prelu(cw*(mix + y) + cb)  (res_conv + concat_block of the next block)
 //      2 = D = acc + bias + resid                              (res_conv of the last block)
 // STATS: per-item sum / sum of squares of D (GlobLN statistics of the consumer), double atomics.
-template <int EPI, bool STATS>
+// AB16: operands are bf16 (K-block = 64 elements = the same 128-byte swizzle row, kind::f16).
+// D16:  D is stored as bf16.
+template <int EPI, bool STATS, bool AB16, bool D16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ CUtensorMap mapW2, GemmArgs a, TcParams p) {
@@ -183,7 +197,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   float* patches = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = a.K / TC_BK;
+  constexpr int BKE = AB16 ? 2 * TC_BK : TC_BK;  // elements per 128-byte K-block
+  const int nkb = a.K / BKE;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -220,9 +235,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(full + stage, stage_bytes);
-          tma_load_3d(sa, &mapA, full + stage, kb * TC_BK, r0, b);
-          tma_load_2d(sa + a_bytes, &mapW, full + stage, kb * TC_BK, n0);
-          if (p.nsplit == 2) tma_load_2d(sa + a_bytes + w_bytes, &mapW2, full + stage, kb * TC_BK, n0);
+          tma_load_3d(sa, &mapA, full + stage, kb * BKE, r0, b);
+          tma_load_2d(sa + a_bytes, &mapW, full + stage, kb * BKE, n0);
+          if (p.nsplit == 2) tma_load_2d(sa + a_bytes + w_bytes, &mapW2, full + stage, kb * BKE, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -243,9 +258,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint64_t da = make_smem_desc(sa), dw = make_smem_desc(sa + a_bytes), dw2 = make_smem_desc(sa + a_bytes + w_bytes);
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
-            // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            tc_mma_tf32(tmem_d, da + 2 * k, dw + 2 * k, p.idesc, (kb | k) != 0);
-            if (p.nsplit == 2) tc_mma_tf32(tmem_d, da + 2 * k, dw2 + 2 * k, p.idesc, 1);
+            // advance 8 tf32 / 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            if constexpr (AB16) {
+              tc_mma_bf16(tmem_d, da + 2 * k, dw + 2 * k, p.idesc, (kb | k) != 0);
+            } else {
+              tc_mma_tf32(tmem_d, da + 2 * k, dw + 2 * k, p.idesc, (kb | k) != 0);
+              if (p.nsplit == 2) tc_mma_tf32(tmem_d, da + 2 * k, dw2 + 2 * k, p.idesc, 1);
+            }
           }
         }
         __syncwarp();
@@ -330,7 +349,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 s1 += (t.x + t.y) + (t.z + t.w);
                 s2 = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, s2))));
               }
-              *reinterpret_cast<float4*>(a.D + off0 + (size_t)(4 * i) * N) = t;
+              if constexpr (D16) {
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.D) + off0 + (size_t)(4 * i) * N) =
+                    make_uint2(bf16x2_pack(t.x, t.y), bf16x2_pack(t.z, t.w));
+              } else {
+                *reinterpret_cast<float4*>(a.D + off0 + (size_t)(4 * i) * N) = t;
+              }
             }
           }
         }
@@ -376,19 +400,19 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* m, const float* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, bool bf16 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(TDANET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[3], gstride[2];
   cuuint32_t bdim[3], estr[3] = {1, 1, 1};
-  uint64_t stride = sizeof(float);
+  uint64_t stride = bf16 ? 2 : sizeof(float);
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
     stride *= dims[i];
     if (i < rank - 1) gstride[i] = stride;
   }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, gdim, gstride, bdim, estr,
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, gdim, gstride, bdim, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TDANET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -396,7 +420,7 @@ static int encode_map(CUtensorMap* m, const float* ptr, int rank, const uint64_t
 }
 
 bool gemm_tc_supported(const GemmArgs& a) {
-  if (a.K % TC_BK != 0 || a.N % 16 != 0 || a.a_slope != nullptr || a.epi == EPI_MASK) return false;
+  if (a.K % (a.a_bf16 ? 2 * TC_BK : TC_BK) != 0 || a.N % 16 != 0 || a.a_slope != nullptr || a.epi == EPI_MASK) return false;
   if (a.N > 128 && a.N % 128 != 0) return false;
   const uintptr_t all = (uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.D | (uintptr_t)a.bias | (uintptr_t)a.resid |
                         (uintptr_t)a.mix | (uintptr_t)a.cw | (uintptr_t)a.cb;
@@ -406,7 +430,11 @@ bool gemm_tc_supported(const GemmArgs& a) {
 int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   // Shapes the tensor-core tiling cannot express (K not a multiple of 32, N not a multiple of 16,
   // an A-operand transform) run on the CUDA-core kernel of this library.
-  if (!gemm_tc_supported(a)) return launch_gemm_simt(a, st);
+  if (!gemm_tc_supported(a)) {
+    if (a.a_bf16 || a.d_bf16)
+      return fail(TDANET_EUNSUPPORTED, "bf16 activation storage needs tensor-core GEMM shapes (K %% 64 == 0, N %% 16 == 0); got N=%d K=%d", a.N, a.K);
+    return launch_gemm_simt(a, st);
+  }
   TD_REQUIRE(a.W_aux != nullptr, "gemm_tc: prepared weights missing");
   static int num_sms = 0;
   if (!num_sms) {
@@ -415,7 +443,7 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
     TD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   TcParams p{};
-  p.nsplit = mode == TDANET_GEMM_TF32X3 ? 2 : 1;
+  p.nsplit = (mode == TDANET_GEMM_TF32X3 && !a.a_bf16) ? 2 : 1;
   p.BN = a.N % 256 == 0 && p.nsplit == 1 ? 256 : (a.N >= 128 ? 128 : a.N);
   p.tiles_m = cdiv(a.L, TC_BM);
   p.tiles_n = a.N / p.BN;
@@ -423,7 +451,7 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.BN)) cols <<= 1;
   p.tmem_cols = cols;
-  p.idesc = make_idesc(TC_BM, p.BN);
+  p.idesc = make_idesc(TC_BM, p.BN, a.a_bf16 != 0);
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 4 + (size_t)p.BN * TC_BK * 4 * p.nsplit;
   const size_t budget = 184 * 1024;
   int stages = (int)(budget / stage_bytes);
@@ -434,29 +462,38 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
 
   CUtensorMap mapA, mapW, mapW2;
   const uint64_t dA[3] = {(uint64_t)a.K, (uint64_t)a.L, (uint64_t)a.B};
-  const uint32_t bA[3] = {TC_BK, TC_BM, 1};
+  const uint32_t bke = a.a_bf16 ? 2 * TC_BK : TC_BK;
+  const uint32_t bA[3] = {bke, TC_BM, 1};
   const uint64_t dW[2] = {(uint64_t)a.K, (uint64_t)a.N};
-  const uint32_t bW[2] = {TC_BK, (uint32_t)p.BN};
-  if (int e = encode_map(&mapA, a.A, 3, dA, bA)) return e;
+  const uint32_t bW[2] = {bke, (uint32_t)p.BN};
+  if (int e = encode_map(&mapA, a.A, 3, dA, bA, a.a_bf16)) return e;
   // TF32: the rounded copy is the operand.  TF32X3: W itself (hi) and the prepared remainder (lo).
-  if (int e = encode_map(&mapW, p.nsplit == 2 ? a.W : a.W_aux, 2, dW, bW)) return e;
-  if (int e = encode_map(&mapW2, a.W_aux, 2, dW, bW)) return e;
+  // bf16 operands: the bf16 copy.
+  if (int e = encode_map(&mapW, p.nsplit == 2 ? a.W : a.W_aux, 2, dW, bW, a.a_bf16)) return e;
+  if (int e = encode_map(&mapW2, a.W_aux, 2, dW, bW, a.a_bf16)) return e;
 
   const int grid = p.total < num_sms ? p.total : num_sms;
   const int epi = a.epi == EPI_RESIDUAL ? (a.last ? 2 : 1) : 0;
-#define TD_TC_LAUNCH(E, S)                                                                                     \
+#define TD_TC_LAUNCH(E, S, AB, DB)                                                                             \
   do {                                                                                                         \
     static bool attr_set = false;                                                                              \
     if (!attr_set) {                                                                                           \
-      TD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<E, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      TD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<E, S, AB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    TD_LAUNCH((gemm_tc_kernel<E, S>), grid, TC_THREADS, smem, st, mapA, mapW, mapW2, a, p);                     \
+    TD_LAUNCH((gemm_tc_kernel<E, S, AB, DB>), grid, TC_THREADS, smem, st, mapA, mapW, mapW2, a, p);             \
   } while (0)
-  if (epi == 0 && a.stats) TD_TC_LAUNCH(0, true);
-  else if (epi == 0) TD_TC_LAUNCH(0, false);
-  else if (epi == 1) TD_TC_LAUNCH(1, false);
-  else TD_TC_LAUNCH(2, false);
+  if (a.d_bf16) {
+    TD_REQUIRE(epi == 0 && a.stats && !a.a_bf16, "gemm_tc: bf16 output is implemented for the statistics epilogue only");
+    TD_TC_LAUNCH(0, true, false, true);
+  } else if (a.a_bf16) {
+    TD_REQUIRE(epi != 0, "gemm_tc: bf16 operands are implemented for the residual epilogues only");
+    if (epi == 1) TD_TC_LAUNCH(1, false, true, false);
+    else TD_TC_LAUNCH(2, false, true, false);
+  } else if (epi == 0 && a.stats) TD_TC_LAUNCH(0, true, false, false);
+  else if (epi == 0) TD_TC_LAUNCH(0, false, false, false);
+  else if (epi == 1) TD_TC_LAUNCH(1, false, false, false);
+  else TD_TC_LAUNCH(2, false, false, false);
 #undef TD_TC_LAUNCH
   return 0;
 }
@@ -472,6 +509,16 @@ __global__ void tf32_prepare_kernel(const float* __restrict__ w, float* __restri
     const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // what the tensor core sees
     aux[i] = x - hi;
   }
+}
+
+__global__ void bf16_prepare_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ aux, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) aux[i] = __float2bfloat16_rn(w[i]);
+}
+
+int launch_bf16_prepare(const float* w, float* aux, size_t n, cudaStream_t st) {
+  TD_LAUNCH(bf16_prepare_kernel, (unsigned)((n + 255) / 256), 256, 0, st, w, reinterpret_cast<__nv_bfloat16*>(aux), n);
+  return 0;
 }
 
 int launch_tf32_prepare(const float* w, float* aux, size_t n, int mode, cudaStream_t st) {

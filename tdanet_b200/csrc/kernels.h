@@ -43,6 +43,7 @@ struct DwArgs {
   float* chstats;
   float* pool_out;  // optional [B, Lb, C]: adaptive-average-pooled raw output (nw == 1, out != null)
   int Lb;
+  int act_bf16;     // src.x and out are stored as bf16 (large-activation storage mode), else fp32
   int relu;
   int round_out;  // store TF32-rounded values (output only feeds a tensor-core GEMM)
 };
@@ -50,10 +51,10 @@ int launch_dw5(const DwArgs& a, cudaStream_t st);
 
 // Generic depthwise conv (any odd k, any stride), plain/affine source, writes out, no stats.
 int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int ks, int stride,
-                      const float* w, const float* bias, float* out, int round_out, cudaStream_t st);
+                      const float* w, const float* bias, float* out, int round_out, int act_bf16, cudaStream_t st);
 
 // out[b, t, :] = injected operand (SRC_INJECT_GATE / SRC_INJECT_ADD) written out, [B, src.L, C]
-int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, cudaStream_t st);
+int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, int act_bf16, cudaStream_t st);
 
 // LA combine (TDANet_best.py:277-292 with the three GlobLN folded into coef tables):
 //   out[t] = (cL.s*dw_l(xl)[t] + cL.h) * sigmoid(cA.s*dw_a(xg)[j] + cA.h) + (cE.s*dw_e(xg)[j] + cE.h)
@@ -67,6 +68,7 @@ struct LaArgs {
   float* out;                 // [B, Ll, C]
   float scale;                // fl32(Lg / Ll)
   int round_out;
+  int act_bf16;               // loc.x, glo.x and out are stored as bf16, else fp32
 };
 int launch_la_combine(const LaArgs& a, cudaStream_t st);
 // statistics of local_embedding(x_fused[i]) for every top-down step in one launch (nw = 1, stats only)
@@ -159,13 +161,18 @@ struct GemmArgs {
   // EPI_MASK
   const float* enc;
   int Nb;
-  // tensor-core path: weight split prepared by prepare_tf32_weights (lo part / rounded copy)
+  // tensor-core path: weight split prepared by prepare_tf32_weights (lo part / rounded copy / bf16 copy)
   const float* W_aux;
+  // bf16 activation storage: D is written as bf16 (proj_1x1) / A is read as bf16 (res_conv, kind::f16 MMA
+  // against a bf16 copy of W in W_aux)
+  int d_bf16, a_bf16;
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st);
 // aux[i] = mode==TF32 ? rna_tf32(w[i]) : w[i] - trunc_tf32(w[i])
 int launch_tf32_prepare(const float* w, float* aux, size_t n, int mode, cudaStream_t st);
+// aux (as bf16[n]) = round-to-nearest-even bf16 copy of w
+int launch_bf16_prepare(const float* w, float* aux, size_t n, cudaStream_t st);
 
 // ------------------------------------------------------------------ css.cu
 int launch_css_stitch(const float* est, int n_streams, int n_chunks, int seg_len, int overlap, int out_len,

@@ -34,13 +34,13 @@ class SeparationEngine:
 
     def __init__(self, variant: str, out_channels: int, in_channels: int, num_blocks: int, depth: int,
                  enc_kernel: int, n_basis: int, num_sources: int, enc_convs: int = 1, n_head: int = 8,
-                 gemm_mode: str = "tf32"):
+                 gemm_mode: str = "tf32", act_dtype: str = "fp32"):
         self.variant = variant
         self.cfg = Config(
             variant=_lib.VARIANTS[variant], out_channels=out_channels, in_channels=in_channels,
             num_blocks=num_blocks, depth=depth, enc_kernel=enc_kernel, enc_stride=enc_kernel // 4,
             n_basis=n_basis, num_sources=num_sources, enc_convs=enc_convs, n_head=n_head,
-            gemm_mode=_lib.GEMM_MODES[gemm_mode], attn_group=0)
+            gemm_mode=_lib.GEMM_MODES[gemm_mode], attn_group=0, act_dtype=_lib.ACT_DTYPES[act_dtype])
         self._ws: Dict[torch.device, torch.Tensor] = {}
         self._graphs: Dict[Tuple, Tuple] = {}
         self._keep = None  # tensors referenced by the packed weight struct
@@ -53,6 +53,15 @@ class SeparationEngine:
     @gemm_mode.setter
     def gemm_mode(self, mode: str) -> None:
         self.cfg.gemm_mode = _lib.GEMM_MODES[mode]
+        self._graphs.clear()
+
+    @property
+    def act_dtype(self) -> str:
+        return {v: k for k, v in _lib.ACT_DTYPES.items()}[self.cfg.act_dtype]
+
+    @act_dtype.setter
+    def act_dtype(self, dtype: str) -> None:
+        self.cfg.act_dtype = _lib.ACT_DTYPES[dtype]
         self._graphs.clear()
 
     def latent_lengths(self, n_samples: int):
@@ -179,7 +188,7 @@ class SeparationEngine:
         The returned tensor is the graph's static output buffer: it is overwritten by the next call.
         """
         B, T = wav.shape
-        key = (wav.device, B, T, attn_group, self.cfg.gemm_mode, C.addressof(weights))
+        key = (wav.device, B, T, attn_group, self.cfg.gemm_mode, self.cfg.act_dtype, C.addressof(weights))
         entry = self._graphs.get(key)
         if entry is None:
             static_in = torch.empty_like(wav)

@@ -69,6 +69,15 @@ class _TDANetCommon(BaseModel):
     def gemm_mode(self, mode: str) -> None:
         self._engine.gemm_mode = mode
 
+    @property
+    def act_dtype(self) -> str:
+        """Storage of the large activations: "fp32", or "bf16" (fp32 arithmetic; the bf16-mode tolerance)."""
+        return self._engine.act_dtype
+
+    @act_dtype.setter
+    def act_dtype(self, dtype: str) -> None:
+        self._engine.act_dtype = dtype
+
     def _weights(self):
         # (re)pack when any storage moved (e.g. after .cuda() / load_state_dict with assign)
         sd = {k: v for k, v in self.state_dict(keep_vars=True).items()}

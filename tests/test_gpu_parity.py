@@ -316,3 +316,57 @@ def test_three_sources():
         m.gemm_mode = "fp32"
         y = m(x.to(DEV)).cpu()
     assert y.shape == (2, 3, 3000) and max_rel(y, ref) < 5e-5
+
+
+# ----------------------------------------------------------------------------- bf16 activation storage
+def _bf16_checks(y, ref, seed):
+    """The bf16-mode acceptance of BASELINE.json: PIT SI-SNR against synthetic targets within 0.05 dB of the
+    reference's; plus sanity bounds on the direct error."""
+    tgt = torch.randn(ref.shape, generator=torch.Generator().manual_seed(seed)) * 0.1
+    d = abs(O.pit_loss(y, tgt, "sisdr", False).item() - O.pit_loss(ref, tgt, "sisdr", False).item())
+    assert d <= 0.05, f"PIT SI-SNR differs by {d:.4f} dB"
+    assert O.si_snr_db(y, ref).min().item() > 35.0
+    assert max_rel(y, ref) < 2e-2
+
+
+@pytest.mark.parametrize("variant", ["best", "fork", "multres"])
+def test_bf16_storage_small(variant):
+    kw = dict(out_channels=32, in_channels=64, num_blocks=3, upsampling_depth=5, enc_kernel_size=4, num_sources=2)
+    sr = 16000
+    if variant == "multres":
+        kw.update(kernels=4)
+        sr = 8000
+    torch.manual_seed(11)
+    m = M.get(CLASSES[variant])(sample_rate=sr, **kw).eval()
+    x = torch.randn(3, 1, 6000, generator=torch.Generator().manual_seed(2)) * 0.1
+    with torch.no_grad():
+        ref = O.forward({k: v for k, v in m.state_dict().items()}, x, oracle_cfg(variant, kw, sr))
+        m = m.to(DEV)
+        m.act_dtype = "bf16"
+        y = m(x.to(DEV)).cpu()
+    _bf16_checks(y, ref, 5)
+
+
+@pytest.mark.parametrize("variant", ["best", "fork"])
+def test_bf16_storage_full_model(variant):
+    g = load_golden(f"{variant}_full")
+    torch.manual_seed(int(g["init_seed"]))
+    m = M.get(CLASSES[variant])(sample_rate=g["sample_rate"], **g["kwargs"]).eval().to(DEV)
+    m.act_dtype = "bf16"
+    B = int(g["batch"])
+    x = torch.randn(B, 1, 32000, generator=torch.Generator().manual_seed(int(g["input_seed"]))) * 0.1
+    with torch.no_grad():
+        y = m(x.to(DEV)).cpu()
+    ref_sub = torch.from_numpy(g["y_sub"])
+    assert (y[:, :, ::16] - ref_sub).abs().max().item() / float(g["y_absmax"]) < 2e-2
+    assert O.si_snr_db(y[:, :, ::16], ref_sub).min().item() > 35.0
+
+
+def test_bf16_storage_needs_tensor_core_gemm():
+    from tdanet_b200 import _lib
+    kw = dict(out_channels=32, in_channels=64, num_blocks=1, upsampling_depth=4, enc_kernel_size=2, num_sources=2)
+    m = M.TDANetBest(sample_rate=16000, **kw).eval().to(DEV)
+    m.act_dtype = "bf16"
+    m.gemm_mode = "fp32"
+    with pytest.raises(_lib.TdanetError, match="tensor-core"):
+        m(torch.zeros(1, 1, 2000, device=DEV))
