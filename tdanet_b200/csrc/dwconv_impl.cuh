@@ -765,12 +765,15 @@ static size_t ring_bytes(int threads) {
   return 2 * ((size_t)AROWS * threads * 4 * sizeof(ACT_T) + (size_t)GROWS * threads * 4 * sizeof(float));
 }
 
-template <int LKIND, bool EDGE>
+// CT: in_channels when it is the compile-time 512 of every reference configuration (row strides and
+// shared-memory offsets then fold into immediates), 0 = run-time
+template <int LKIND, bool EDGE, int CT>
 __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, int t0, int t1, void* ring,
                                                float* scratch, const int* jc, const int* jl) {
   constexpr int V = 4;
-  const int Ll = a.loc.L, Lg = a.glo.L, Lgg = a.loc.Lg, C = a.C;
-  const int colw = blockDim.x * V;
+  const int Ll = a.loc.L, Lg = a.glo.L, Lgg = a.loc.Lg;
+  const int C = CT ? CT : a.C;
+  const int colw = CT ? CT : blockDim.x * V;
   const ACT_T* xl = reinterpret_cast<const ACT_T*>(a.loc.x) + (size_t)b * Ll * C + ch;
   const ACT_T* xg = reinterpret_cast<const ACT_T*>(a.glo.x) + (size_t)b * Lg * C + ch;
   const float* gg = a.loc.g + (size_t)b * Lgg * C + ch;
@@ -895,7 +898,7 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
   }
 }
 
-template <int LKIND>
+template <int LKIND, int CT>
 __global__ void __launch_bounds__(128, 2) la_stream_kernel(LaArgs a, int rows_per_cta) {
   extern __shared__ __align__(16) float la_smem[];
   constexpr int V = 4;
@@ -904,7 +907,7 @@ __global__ void __launch_bounds__(128, 2) la_stream_kernel(LaArgs a, int rows_pe
   const int Ll = a.loc.L, Lg = a.glo.L;
   const int t0 = blockIdx.x * rows_per_cta;
   const int t1 = min(t0 + rows_per_cta, Ll);
-  const int colw = blockDim.x * V;
+  const int colw = CT ? CT : blockDim.x * V;
   // [ring: 2 stages][scratch 2*SGC rows fp32][tables]; plain pointer arithmetic on the __shared__ array so
   // that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
   void* ring = la_smem;
@@ -918,8 +921,8 @@ __global__ void __launch_bounds__(128, 2) la_stream_kernel(LaArgs a, int rows_pe
   const int g_first = nearest_src(t0, a.scale, Lg) - 2;
   const int g_last = nearest_src(t1 - 1, a.scale, Lg) + SGR;
   const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0 && g_first >= 0 && g_last < Lg;
-  if (interior) la_stream_body<LKIND, false>(a, b, ch, t0, t1, ring, scratch, jc, jl);
-  else la_stream_body<LKIND, true>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+  if (interior) la_stream_body<LKIND, false, CT>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+  else la_stream_body<LKIND, true, CT>(a, b, ch, t0, t1, ring, scratch, jc, jl);
 }
 
 // the streaming kernel applies when 8 output rows see <= 5 global centres and <= 3 rows of the
@@ -942,10 +945,15 @@ static int launch_la_stream(const LaArgs& a, cudaStream_t st) {
                       ring_bytes<SAROWS, SGG>(threads);
   static bool attr_set = false;
   if (!attr_set) {
-    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     attr_set = true;
   }
-  TD_LAUNCH((la_stream_kernel<LKIND>), grid, threads, smem, st, a, rows);
+  if (a.C == 512 && threads == 128) {
+    TD_LAUNCH((la_stream_kernel<LKIND, 512>), grid, threads, smem, st, a, rows);
+  } else {
+    TD_LAUNCH((la_stream_kernel<LKIND, 0>), grid, threads, smem, st, a, rows);
+  }
   return 0;
 }
 
@@ -964,12 +972,13 @@ struct LocalStatsArgs {
   int rows;                        // rows per CTA (same for every step)
 };
 
-template <int LKIND, bool EDGE>
+template <int LKIND, bool EDGE, int CT>
 __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch, int t0, int t1, void* ring,
                                                   const int* jl, float& tot1, float& tot2) {
   constexpr int V = 4;
-  const int Ll = a.src.L, Lgg = a.src.Lg, C = a.C;
-  const int colw = blockDim.x * V;
+  const int Ll = a.src.L, Lgg = a.src.Lg;
+  const int C = CT ? CT : a.C;
+  const int colw = CT ? CT : blockDim.x * V;
   const ACT_T* xl = reinterpret_cast<const ACT_T*>(a.src.x) + (size_t)b * Ll * C + ch;
   const float* gg = a.src.g + (size_t)b * Lgg * C + ch;
   Injector<LKIND, V> inj;
@@ -1055,7 +1064,7 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
   }
 }
 
-template <int LKIND>
+template <int LKIND, int CT>
 __global__ void __launch_bounds__(128, 3) la_local_stats_kernel(LocalStatsArgs p) {
   extern __shared__ __align__(16) float la_smem[];
   __shared__ double red[64];
@@ -1075,8 +1084,8 @@ __global__ void __launch_bounds__(128, 3) la_local_stats_kernel(LocalStatsArgs p
   float tot1[1] = {0.f}, tot2[1] = {0.f};
   if (ch < loc.C) {
     const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0;
-    if (interior) stats_stream_body<LKIND, false>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
-    else stats_stream_body<LKIND, true>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
+    if (interior) stats_stream_body<LKIND, false, CT>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
+    else stats_stream_body<LKIND, true, CT>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
   }
   flush_item_stats<1>(loc.stats, b, tot1, tot2, red);
 }
@@ -1102,10 +1111,15 @@ static int launch_la_local_stats_t(LocalStatsArgs& p, cudaStream_t st) {
   const size_t smem = ring_bytes<SR, SSG>(threads) + (size_t)(rows + 4) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
-    TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     attr_set = true;
   }
-  TD_LAUNCH((la_local_stats_kernel<LKIND>), grid, threads, smem, st, p);
+  if (a0.C == 512 && threads == 128) {
+    TD_LAUNCH((la_local_stats_kernel<LKIND, 512>), grid, threads, smem, st, p);
+  } else {
+    TD_LAUNCH((la_local_stats_kernel<LKIND, 0>), grid, threads, smem, st, p);
+  }
   return 0;
 }
 
