@@ -59,6 +59,8 @@ class OracleConfig:
     n_head: int = 8
     taps: Optional[Dict[str, torch.Tensor]] = field(default=None, repr=False)
     tap_block: int = 0             # per-stage activations are recorded for this block only
+    tap_all: bool = False          # record every block instead, keys "<name>@<block>" (backward-pass tests)
+    cur_block: Optional[int] = field(default=None, repr=False)
 
     @property
     def K(self) -> int:            # encoder window in samples
@@ -75,6 +77,8 @@ class OracleConfig:
 
 def _tap(cfg: OracleConfig, name: str, t: torch.Tensor) -> None:
     if cfg.taps is not None:
+        if cfg.tap_all and cfg.cur_block is not None:
+            name = f"{name}@{cfg.cur_block}"
         cfg.taps[name] = t.detach().clone()
 
 
@@ -134,17 +138,21 @@ def la(sd, prefix, x_l, x_g, cfg):
     return loc * gate + emb
 
 
-def mha_seq_first(x, w_in, b_in, w_out, b_out, n_head):
+def mha_seq_first(x, w_in, b_in, w_out, b_out, n_head, cfg=None):
     """nn.MultiheadAttention eval forward for input laid out (seq, batch, embed)."""
     S, N, E = x.shape
     d = E // n_head
     qkv = F.linear(x, w_in, b_in)
+    if cfg is not None:
+        _tap(cfg, "ga.qkv", qkv)
     q, k, v = qkv.split(E, dim=-1)
     q = q.reshape(S, N * n_head, d).transpose(0, 1) * (1.0 / math.sqrt(d))
     k = k.reshape(S, N * n_head, d).transpose(0, 1)
     v = v.reshape(S, N * n_head, d).transpose(0, 1)
     p = torch.softmax(q @ k.transpose(1, 2), dim=-1)
     o = (p @ v).transpose(0, 1).reshape(S, N, E)
+    if cfg is not None:
+        _tap(cfg, "ga.attn_ctx", o)
     return F.linear(o, w_out, b_out)
 
 
@@ -165,7 +173,7 @@ def global_attention(sd, prefix, x, cfg):
     else:
         # batch_first=False fed [B, T', C]: the *batch* axis is the sequence axis,
         # and the "residual" doubles the attention output (bug-compatible)
-        o = mha_seq_first(h, w_in, b_in, w_out, b_out, cfg.n_head)
+        o = mha_seq_first(h, w_in, b_in, w_out, b_out, cfg.n_head, cfg)
         post = o + o
     _tap(cfg, "ga.attn_out", o)
     post = F.layer_norm(post, (C,), sd[f"{a}.norm.weight"], sd[f"{a}.norm.bias"], EPS_LN)
@@ -176,6 +184,7 @@ def global_attention(sd, prefix, x, cfg):
     y = conv_norm(sd, f"{m}.fc1", x, cfg)
     y = F.conv1d(y, sd[f"{m}.dwconv.weight"], sd[f"{m}.dwconv.bias"], padding=2, groups=y.shape[1])
     y = torch.relu(y)
+    _tap(cfg, "ga.ffn_dw", y)
     y = conv_norm(sd, f"{m}.fc2", y, cfg)
     return x + y
 
@@ -235,11 +244,13 @@ def recurrent(sd, prefix, x, cfg):
         if i > 0:
             x = prelu(F.conv1d(mixture + x, wc, bc, groups=x.shape[1]), ac)
         taps = cfg.taps
-        if i != cfg.tap_block:
+        cfg.cur_block = i
+        if i != cfg.tap_block and not cfg.tap_all:
             cfg.taps = None                    # per-stage taps are recorded for one block only
         _tap(cfg, "block_in", x)
         x = uconv_block(sd, f"{prefix}.unet", x, cfg)
         cfg.taps = taps
+        cfg.cur_block = None
         _tap(cfg, f"block.{i}", x)
     return x
 
@@ -273,6 +284,7 @@ def forward(sd: Dict[str, torch.Tensor], wav: torch.Tensor, cfg: OracleConfig) -
     x = recurrent(sd, "sm", x, cfg)
     x = prelu(x, sd["mask_net.0.weight"])
     x = F.conv1d(x, sd["mask_net.1.weight"], sd["mask_net.1.bias"])
+    _tap(cfg, "mlogit", x)
     B = x.shape[0]
     x = torch.relu(x.view(B, cfg.num_sources, cfg.n_basis, -1)) * s.unsqueeze(1)
     _tap(cfg, "masked", x)

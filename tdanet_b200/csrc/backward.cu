@@ -1,0 +1,544 @@
+// Backward pass of TDANetBest (TDANet_best.py:342-399, 482-521) over the activations kept by
+// tdanet_forward_train: host-side launch sequence + launchers of bwd_kernels.cuh.
+//
+// Replaces what autograd does for the reference's training_step (system/audio_litmodule.py:83-124): given
+// d loss / d est it accumulates d loss / d theta into caller-provided buffers laid out like tdanet_weights_t.
+// The 16 UConvBlock iterations share one set of weights, so every iteration adds into the same buffers.
+//
+// Also compiled by g++ with -DTD_EMU (see emu.h) so that the whole sweep can be checked on a CPU.
+#include "plan.h"
+#include "bwd_kernels.cuh"
+
+namespace td {
+
+#ifdef TD_EMU
+}  // namespace td
+namespace emu {
+thread_local uint3 tid, bid;
+thread_local BlockState* bs = nullptr;
+dim3 bdim, gdim;
+bool coop_reductions = getenv("TD_EMU_COOP") != nullptr;
+}  // namespace emu
+namespace td {
+// ----------------------------------------------------------------------------- emulation build: host pieces
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+bool g_profile = false;
+thread_local const char* g_tag = nullptr;
+void profile_mark(const char*, cudaStream_t, bool) {}
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+// reference semantics of the GEMM launchers (EPI_BIAS, EPI_RESIDUAL with last = 1), enough for the backward pass
+static int emu_gemm(const GemmArgs& a) {
+  TD_REQUIRE(a.epi == EPI_BIAS || (a.epi == EPI_RESIDUAL && a.last), "emu_gemm: epilogue %d", a.epi);
+  for (int b = 0; b < a.B; ++b)
+    for (int r = 0; r < a.L; ++r) {
+      const size_t row = (size_t)b * a.L + r;
+      for (int n = 0; n < a.N; ++n) {
+        double acc = a.bias ? a.bias[n] : 0.0;
+        for (int k = 0; k < a.K; ++k) acc += (double)a.A[row * a.K + k] * a.W[(size_t)n * a.K + k];
+        if (a.epi == EPI_RESIDUAL) acc += a.resid[row * a.N + n];
+        a.D[row * a.N + n] = (float)acc;
+      }
+    }
+  return 0;
+}
+int launch_tf32_prepare(const float* w, float* aux, size_t n, int, cudaStream_t) {
+  memcpy(aux, w, n * sizeof(float));
+  return 0;
+}
+#endif
+
+static int bgemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
+#ifdef TD_EMU
+  (void)x; (void)aux_off;
+  return emu_gemm(g);
+#else
+  if (x.c->gemm_mode == TDANET_GEMM_FP32) return launch_gemm_simt(g, x.st);
+  g.W_aux = x.at(aux_off);
+  return launch_gemm_tc(g, x.c->gemm_mode, x.st);
+#endif
+}
+
+// ----------------------------------------------------------------------------- launchers
+static inline void row_grid(int L, int C4, int B, int rows, dim3& grid, int& threads) {
+  threads = C4 > 256 ? 256 : (C4 < 32 ? 32 : C4);
+  grid = dim3(cdiv(L, rows), cdiv(C4, threads), B);
+}
+
+static int launch_gln_bwd_stats(const float* dy, const float* x, const NormRef& norm, float* dgamma, float* dbeta,
+                                double* S, int B, int L, int C, cudaStream_t st) {
+  dim3 grid;
+  int threads;
+  const int rows = 32;
+  if (C % 4 == 0) {
+    row_grid(L, C / 4, B, rows, grid, threads);
+    TD_LAUNCH_RED((gln_bwd_stats_kernel<4>), grid, threads, 0, st, dy, x, norm, dgamma, dbeta, S, L, C, rows);
+  } else {
+    row_grid(L, C, B, rows, grid, threads);
+    TD_LAUNCH_RED((gln_bwd_stats_kernel<1>), grid, threads, 0, st, dy, x, norm, dgamma, dbeta, S, L, C, rows);
+  }
+  return 0;
+}
+
+static int launch_gln_bwd_apply(const GradSrc& g, float* out, int accumulate, int B, int L, int C, cudaStream_t st) {
+  dim3 grid;
+  int threads;
+  const int rows = 16;
+  if (C % 4 == 0) {
+    row_grid(L, C / 4, B, rows, grid, threads);
+    TD_LAUNCH((gln_bwd_apply_kernel<4>), grid, threads, 0, st, g, out, accumulate, L, C, rows);
+  } else {
+    row_grid(L, C, B, rows, grid, threads);
+    TD_LAUNCH((gln_bwd_apply_kernel<1>), grid, threads, 0, st, g, out, accumulate, L, C, rows);
+  }
+  return 0;
+}
+
+static int launch_dw_bwd(DwBwdArgs& a, int ks, int nw, cudaStream_t st) {
+  TD_REQUIRE(a.C % 4 == 0, "dw_bwd: C=%d", a.C);
+  TD_REQUIRE(a.stride == 1 || a.stride == 2, "dw_bwd: stride %d", a.stride);
+  TD_REQUIRE(a.xkind == SRC_PLAIN || a.xkind == SRC_AFFINE || a.xkind == SRC_AFFINE_PRELU, "dw_bwd: source kind %d", a.xkind);
+  TD_REQUIRE(a.xin.L == a.Lin, "dw_bwd: input length %d != %d", a.xin.L, a.Lin);
+  a.rows_per_thread = 32;
+  dim3 grid;
+  int threads;
+  row_grid(a.Lout, a.C / 4, a.B, a.rows_per_thread, grid, threads);
+  if (ks == 5 && nw == 1) TD_LAUNCH_RED((dw_bwd_kernel<5, 1>), grid, threads, 0, st, a);
+  else if (ks == 5 && nw == 2) TD_LAUNCH_RED((dw_bwd_kernel<5, 2>), grid, threads, 0, st, a);
+  else if (ks == 1 && nw == 1) TD_LAUNCH_RED((dw_bwd_kernel<1, 1>), grid, threads, 0, st, a);
+  else if (ks == 1 && nw == 2) TD_LAUNCH_RED((dw_bwd_kernel<1, 2>), grid, threads, 0, st, a);
+  else return fail(TDANET_EINVAL, "dw_bwd: ks=%d nw=%d", ks, nw);
+  return 0;
+}
+
+static int launch_la_bwd_a(LaBwdArgs& a, int ks, cudaStream_t st) {
+  TD_REQUIRE(a.C % 4 == 0, "la_bwd: C=%d", a.C);
+  // about 32 local rows per thread
+  int jc = (int)(32.0 * a.Lg / a.loc.L + 0.5);
+  a.jchunk = jc < 1 ? 1 : jc;
+  dim3 grid;
+  int threads;
+  row_grid(a.Lg, a.C / 4, a.B, a.jchunk, grid, threads);
+  if (ks == 5) TD_LAUNCH_RED((la_bwd_a_kernel<5>), grid, threads, 0, st, a);
+  else if (ks == 1) TD_LAUNCH_RED((la_bwd_a_kernel<1>), grid, threads, 0, st, a);
+  else return fail(TDANET_EINVAL, "la_bwd: ks=%d", ks);
+  return 0;
+}
+
+static int launch_pool_bwd(const float* g, float* dx, int accumulate, int B, int L, int Lb, int C, cudaStream_t st) {
+  dim3 grid;
+  int threads;
+  const int rows = 16;
+  row_grid(L, C / 4, B, rows, grid, threads);
+  TD_LAUNCH(pool_bwd_kernel, grid, threads, 0, st, g, dx, accumulate, L, Lb, C, rows);
+  return 0;
+}
+
+// gradient through  y = resid + LN(k1*x)*w + b :  out = (add ? add : 0) + k1 * dLN(dy)
+static int launch_ln_bwd(const float* xin, float k1, const float* w, const float* dy, float* rowstat, const float* add,
+                         float* out, float* dw, float* db, int rows, int C, cudaStream_t st) {
+  TD_REQUIRE(C % 4 == 0, "ln_bwd: C=%d", C);
+  TD_LAUNCH_COOP(ln_bwd_rows_kernel, cdiv(rows, 8), 256, 0, st, xin, k1, w, dy, rowstat, rows, C);
+  const int rpt = 16;
+  const int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
+  dim3 grid(cdiv(rows, rpt), cdiv(C / 4, threads));
+  TD_LAUNCH(ln_bwd_apply_kernel, grid, threads, 0, st, xin, k1, w, dy, rowstat, add, k1, out, dw, db, rows, C, rpt);
+  return 0;
+}
+
+template <int D>
+static int launch_att_bwd_d(const float* qkv, const float* dctx, float* P, float* dS, float* dqkv, int B, int L, int C,
+                            int n_head, int group, int time_axis, cudaStream_t st) {
+  const int n = time_axis ? L : group;
+  const int nprob = time_axis ? B : (B / group) * L;
+  const int total = nprob * n_head * n;
+  TD_LAUNCH((att_bwd_dq_kernel<D>), cdiv(total, 128), 128, 0, st, qkv, dctx, P, dS, dqkv, L, C, n, n_head, group, time_axis, total);
+  TD_LAUNCH((att_bwd_dkv_kernel<D>), cdiv(total, 128), 128, 0, st, qkv, dctx, P, dS, dqkv, L, C, n, n_head, group, time_axis, total);
+  return 0;
+}
+
+static int launch_att_bwd(const float* qkv, const float* dctx, float* P, float* dS, float* dqkv, int B, int L, int C,
+                          int n_head, int group, int time_axis, cudaStream_t st) {
+  switch (C / n_head) {
+    case 64: return launch_att_bwd_d<64>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
+    case 32: return launch_att_bwd_d<32>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
+    case 16: return launch_att_bwd_d<16>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
+    case 8: return launch_att_bwd_d<8>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
+    case 4: return launch_att_bwd_d<4>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
+  }
+  return fail(TDANET_EUNSUPPORTED, "attention backward: head dim %d not in {4,8,16,32,64}", C / n_head);
+}
+
+// dW[N, K] += G[R, N]^T f(A[R, K]);  db[N] += column sums of G (db may be null)
+static int launch_wgrad(const float* G, const float* A, float* dW, float* db, int R, int N, int K,
+                        const float* a_slope, cudaStream_t st) {
+  const int tiles = cdiv(N, WG_T) * cdiv(K, WG_T);
+  int splits = cdiv(592, tiles);  // about four CTAs per SM
+  int rps = cdiv(R, splits);
+  rps = cdiv(rps, WG_R) * WG_R;
+  splits = cdiv(R, rps);
+  dim3 grid(cdiv(N, WG_T), cdiv(K, WG_T), splits);
+  TD_LAUNCH_COOP(wgrad_kernel, grid, 256, 0, st, G, A, dW, R, N, K, a_slope, rps);
+  if (db) {
+    const int rpt = 64;
+    dim3 g2(cdiv(N, 128), cdiv(R, rpt));
+    TD_LAUNCH(colsum_kernel, g2, 128, 0, st, G, db, R, N, rpt);
+  }
+  return 0;
+}
+
+static int launch_small_dgrad(const float* G, const float* W, float* D, int R, int Kd, int N, const float* u,
+                              const float* slope, float* dslope, cudaStream_t st) {
+  const size_t n = (size_t)R * N;
+  TD_LAUNCH_RED(small_dgrad_kernel, (unsigned)((n + 255) / 256), 256, 0, st, G, W, D, R, Kd, N, u, slope, dslope);
+  return 0;
+}
+
+static int launch_transpose(const float* W, float* Wt, int N, int K, cudaStream_t st) {
+  const size_t n = (size_t)N * K;
+  TD_LAUNCH(transpose_kernel, (unsigned)((n + 255) / 256), 256, 0, st, W, Wt, N, K);
+  return 0;
+}
+
+static int launch_framed_wgrad(const float* M, const float* sig, float* dW, int B, int L0, int CI, int NO, int K,
+                               int S, int T, int shift, cudaStream_t st) {
+  TD_REQUIRE(K <= 1024, "framed_wgrad: window %d", K);
+  const int R = B * L0;
+  int splits = cdiv(1184, CI * NO);
+  const int rps = cdiv(R, splits);
+  splits = cdiv(R, rps);
+  dim3 grid(CI * NO, splits);
+  TD_LAUNCH(framed_wgrad_kernel, grid, K, 0, st, M, sig, dW, B, L0, CI, NO, K, S, T, shift, rps);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- orchestration
+struct BCtx : Ctx {
+  const tdanet_weights_t* g;  // gradient buffers, same layout as the weights
+  float* gp(const float* p) const { return const_cast<float*>(p); }
+};
+
+static GradSrc gln_grad(const float* dy, const float* x, const NormRef& n, const double* S) {
+  GradSrc g{};
+  g.dy = dy; g.x = x; g.norm = n; g.S = S; g.kind = G_GLN;
+  return g;
+}
+static SrcDesc bplain(const float* x, int L) {
+  SrcDesc s{};
+  s.x = x; s.L = L;
+  return s;
+}
+static SrcDesc baffine(const float* x, int L, const NormRef& n, const float* slope = nullptr) {
+  SrcDesc s{};
+  s.x = x; s.L = L; s.norm = n; s.slope = slope;
+  return s;
+}
+
+// transposed (and, for the tensor-core path, TF32-rounded) copies of the weights the data-gradient GEMMs read
+static int prepare_transposed(const BCtx& x) {
+  const tdanet_weights_t* w = x.w;
+  const Plan& p = *x.p;
+  const int C = x.c->in_channels, cc = x.c->out_channels;
+  struct { const float* w; size_t wt, aux; int N, K; } list[] = {
+      {w->proj.w, p.wt_proj, p.auxt_proj, C, cc},     {w->res_w, p.wt_res, p.auxt_res, cc, C},
+      {w->in_proj_w, p.wt_in, p.auxt_in, 3 * C, C},   {w->out_proj_w, p.wt_out, p.auxt_out, C, C},
+      {w->fc1.w, p.wt_fc1, p.auxt_fc1, 2 * C, C},     {w->fc2.w, p.wt_fc2, p.auxt_fc2, C, 2 * C},
+  };
+  for (auto& e : list) {
+    if (int r = launch_transpose(e.w, x.at(e.wt), e.N, e.K, x.st)) return r;
+    if (x.c->gemm_mode != TDANET_GEMM_FP32)
+      if (int r = launch_tf32_prepare(x.at(e.wt), x.at(e.aux), (size_t)e.N * e.K, x.c->gemm_mode, x.st)) return r;
+  }
+  return 0;
+}
+
+// D[B, L, N] = A[B, L, K] . Wt[N, K]^T (+ resid)
+static int dgrad(const BCtx& x, const float* A, size_t wt, size_t aux, float* D, int L, int N, int K, const float* resid) {
+  GemmArgs g{};
+  g.A = A; g.W = x.at(wt); g.bias = nullptr; g.D = D;
+  g.B = x.p->B; g.L = L; g.N = N; g.K = K;
+  if (resid) { g.epi = EPI_RESIDUAL; g.resid = resid; g.last = 1; }
+  else g.epi = EPI_BIAS;
+  return bgemm(x, g, aux);
+}
+
+// One LA (last_layer[i] with k = 5, or loc_glo_fus[k] with k = 1) backwards.
+//   dout: gradient w.r.t. the LA output [B, Ll, C].  d_loc_in / d_glo_in receive the gradients w.r.t. the two
+//   conv inputs (after their on-load transform), written or accumulated.
+static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdanet_la_t& gla, const SrcDesc& loc, int lkind,
+                       const float* glo, int Lg, const NormRef& nL, const NormRef& nA, const NormRef& nE,
+                       const size_t bs[3], const float* dout, float* d_loc_in, int acc_loc, float* d_glo_in, int acc_glo) {
+  const Plan& p = *x.p;
+  const int B = p.B, C = x.c->in_channels, Ll = loc.L;
+  LaBwdArgs a{};
+  a.loc = loc; a.lkind = lkind; a.glo = glo; a.Lg = Lg; a.B = B; a.C = C;
+  a.wl = la.local_embedding.w; a.wa = la.global_act.w; a.we = la.global_embedding.w;
+  a.nL = nL; a.nA = nA; a.nE = nE; a.dout = dout; a.scale = nearest_scale(Lg, Ll);
+  a.d_loc = x.at(p.t_dloc); a.raw_a = x.at(p.t_rawa);
+  a.d_act = x.at(p.t_dact); a.d_emb = x.at(p.t_demb); a.raw_b = x.at(p.t_rawb); a.raw_e = x.at(p.t_rawe);
+  a.dgamma[0] = x.gp(gla.local_embedding.gamma); a.dbeta[0] = x.gp(gla.local_embedding.beta);
+  a.dgamma[1] = x.gp(gla.global_act.gamma); a.dbeta[1] = x.gp(gla.global_act.beta);
+  a.dgamma[2] = x.gp(gla.global_embedding.gamma); a.dbeta[2] = x.gp(gla.global_embedding.beta);
+  for (int i = 0; i < 3; ++i) a.S[i] = x.at<double>(bs[i]);
+  { Tag t(ks == 5 ? "bwd_la_a" : "bwd_lgf_a"); if (int e = launch_la_bwd_a(a, ks, x.st)) return e; }
+  Tag t(ks == 5 ? "bwd_la_dw" : "bwd_lgf_dw");
+  DwBwdArgs d{};
+  d.g[0] = gln_grad(a.d_loc, a.raw_a, nL, a.S[0]);
+  d.w[0] = la.local_embedding.w; d.dw[0] = x.gp(gla.local_embedding.w);
+  d.xin = loc; d.xkind = lkind; d.B = B; d.C = C; d.Lin = Ll; d.Lout = Ll; d.stride = 1;
+  d.dx = d_loc_in; d.accumulate = acc_loc;
+  if (int e = launch_dw_bwd(d, ks, 1, x.st)) return e;
+  d = DwBwdArgs{};
+  d.g[0] = gln_grad(a.d_act, a.raw_b, nA, a.S[1]);
+  d.g[1] = gln_grad(a.d_emb, a.raw_e, nE, a.S[2]);
+  d.w[0] = la.global_act.w; d.dw[0] = x.gp(gla.global_act.w);
+  d.w[1] = la.global_embedding.w; d.dw[1] = x.gp(gla.global_embedding.w);
+  d.xin = bplain(glo, Lg); d.xkind = SRC_PLAIN; d.B = B; d.C = C; d.Lin = Lg; d.Lout = Lg; d.stride = 1;
+  d.dx = d_glo_in; d.accumulate = acc_glo;
+  return launch_dw_bwd(d, ks, 2, x.st);
+}
+
+// GA / GlobalAttention backwards: g_ga_out -> g_ga_in
+static int global_attention_backward(const BCtx& x) {
+  const tdanet_config_t* c = x.c;
+  const tdanet_weights_t* w = x.w;
+  const tdanet_weights_t* gw = x.g;
+  const Plan& p = *x.p;
+  const int B = p.B, C = c->in_channels, Lb = p.Lb, R = B * Lb;
+  const int group = c->attn_group > 0 ? c->attn_group : B;
+  TD_REQUIRE(B % group == 0, "batch %d is not a multiple of attn_group %d", B, group);
+  // ga_out = ga_mid + gLN(fc2)
+  const NormRef n_fc2 = norm_ref(x, p.st_fc2, 2, (double)Lb * C, w->fc2.gamma, w->fc2.beta);
+  const NormRef n_fc1 = norm_ref(x, p.st_fc1, 2, (double)Lb * 2 * C, w->fc1.gamma, w->fc1.beta);
+  {
+    Tag t("bwd_bottom_misc");
+    if (int e = launch_gln_bwd_stats(x.at(p.g_ga_out), x.at(p.fc2), n_fc2, x.gp(gw->fc2.gamma), x.gp(gw->fc2.beta),
+                                     x.at<double>(p.bs_fc2), B, Lb, C, x.st)) return e;
+    if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_ga_out), x.at(p.fc2), n_fc2, x.at<double>(p.bs_fc2)),
+                                     x.at(p.g_fc2), 0, B, Lb, C, x.st)) return e;
+  }
+  { Tag t("wgrad_fc2"); if (int e = launch_wgrad(x.at(p.g_fc2), x.at(p.ffn_dw), x.gp(gw->fc2.w), nullptr, R, C, 2 * C, nullptr, x.st)) return e; }
+  { Tag t("dgrad_fc2"); if (int e = dgrad(x, x.at(p.g_fc2), p.wt_fc2, p.auxt_fc2, x.at(p.g_ffn), Lb, 2 * C, C, nullptr)) return e; }
+  {
+    // relu -> dwconv k5 (+bias) on gLN(fc1)
+    Tag t("bwd_ffn_dw");
+    DwBwdArgs d{};
+    d.g[0].dy = x.at(p.g_ffn); d.g[0].x = x.at(p.ffn_dw); d.g[0].kind = G_RELU;
+    d.w[0] = w->ffn_dw_w; d.dw[0] = x.gp(gw->ffn_dw_w); d.db[0] = x.gp(gw->ffn_dw_b);
+    d.xin = baffine(x.at(p.fc1), Lb, n_fc1); d.xkind = SRC_AFFINE;
+    d.B = B; d.C = 2 * C; d.Lin = Lb; d.Lout = Lb; d.stride = 1; d.dx = x.at(p.g_fc1);
+    if (int e = launch_dw_bwd(d, 5, 1, x.st)) return e;
+  }
+  {
+    Tag t("bwd_bottom_misc");
+    if (int e = launch_gln_bwd_stats(x.at(p.g_fc1), x.at(p.fc1), n_fc1, x.gp(gw->fc1.gamma), x.gp(gw->fc1.beta),
+                                     x.at<double>(p.bs_fc1), B, Lb, 2 * C, x.st)) return e;
+    if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_fc1), x.at(p.fc1), n_fc1, x.at<double>(p.bs_fc1)),
+                                     x.at(p.g_ffn), 0, B, Lb, 2 * C, x.st)) return e;  // g_ffn is free again
+  }
+  { Tag t("wgrad_fc1"); if (int e = launch_wgrad(x.at(p.g_ffn), x.at(p.ga_mid), x.gp(gw->fc1.w), nullptr, R, 2 * C, C, nullptr, x.st)) return e; }
+  // g_ga_mid = g_ga_out (skip) + fc1 data gradient
+  { Tag t("dgrad_fc1"); if (int e = dgrad(x, x.at(p.g_ffn), p.wt_fc1, p.auxt_fc1, x.at(p.g_ga_mid), Lb, C, 2 * C, x.at(p.g_ga_out))) return e; }
+  // ga_mid = ga_in + LN2(2 * attn_out)
+  { Tag t("bwd_bottom_misc");
+    if (int e = launch_ln_bwd(x.at(p.attn_out), 2.f, w->ln2_w, x.at(p.g_ga_mid), x.at(p.ln_rows), nullptr,
+                              x.at(p.g_attn_out), x.gp(gw->ln2_w), x.gp(gw->ln2_b), R, C, x.st)) return e; }
+  { Tag t("wgrad_out_proj"); if (int e = launch_wgrad(x.at(p.g_attn_out), x.at(p.attn_ctx), x.gp(gw->out_proj_w), x.gp(gw->out_proj_b), R, C, C, nullptr, x.st)) return e; }
+  { Tag t("dgrad_out_proj"); if (int e = dgrad(x, x.at(p.g_attn_out), p.wt_out, p.auxt_out, x.at(p.g_ctx), Lb, C, C, nullptr)) return e; }
+  { Tag t("bwd_attention");
+    if (int e = launch_att_bwd(x.at(p.qkv), x.at(p.g_ctx), x.at(p.att_p), x.at(p.att_ds), x.at(p.g_qkv), B, Lb, C,
+                               c->n_head, group, 0, x.st)) return e; }
+  { Tag t("wgrad_in_proj"); if (int e = launch_wgrad(x.at(p.g_qkv), x.at(p.attn_in), x.gp(gw->in_proj_w), x.gp(gw->in_proj_b), R, 3 * C, C, nullptr, x.st)) return e; }
+  { Tag t("dgrad_in_proj"); if (int e = dgrad(x, x.at(p.g_qkv), p.wt_in, p.auxt_in, x.at(p.g_attn_in), Lb, C, 3 * C, nullptr)) return e; }
+  // attn_in = LN1(ga_in) + pe;  g_ga_in = g_ga_mid (skip) + LN1 backward
+  Tag t("bwd_bottom_misc");
+  return launch_ln_bwd(x.at(p.ga_in), 1.f, w->ln1_w, x.at(p.g_attn_in), x.at(p.ln_rows), x.at(p.g_ga_mid),
+                       x.at(p.g_ga_in), x.gp(gw->ln1_w), x.gp(gw->ln1_b), R, C, x.st);
+}
+
+// One UConvBlock iteration backwards.  d_y: gradient w.r.t. the block output y = res_conv(...) + in  [B, L0, c];
+// d_in: receives the gradient w.r.t. the block input.
+static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y, float* d_in) {
+  const tdanet_config_t* c = x.c;
+  const tdanet_weights_t* w = x.w;
+  const tdanet_weights_t* gw = x.g;
+  const Plan& p = *x.p;
+  const int B = p.B, C = c->in_channels, cc = c->out_channels, depth = c->depth, Lb = p.Lb, L0 = p.L[0];
+  const int R0 = B * L0;
+  TD_CUDA(cudaMemsetAsync(x.at<char>(p.bs_begin), 0, p.bs_end - p.bs_begin, x.st));
+  auto spp_norm = [&](int k) {
+    return norm_ref(x, p.st_spp[k], 2, (double)p.L[k] * C, w->spp_dw[k].gamma, w->spp_dw[k].beta);
+  };
+  // ---- res_conv
+  { Tag t("wgrad_res_conv"); if (int e = launch_wgrad(d_y, x.at(p.expanded[0]), x.gp(gw->res_w), x.gp(gw->res_b), R0, cc, C, nullptr, x.st)) return e; }
+  { Tag t("dgrad_res_conv"); if (int e = dgrad(x, d_y, p.wt_res, p.auxt_res, x.at(p.g_exp[0]), L0, C, cc, nullptr)) return e; }
+  // ---- top-down fusion, in the reverse of the forward order
+  bool fused_written[TDANET_MAX_DEPTH] = {};
+  for (int i = 0; i <= depth - 2; ++i) {
+    const tdanet_la_t& la = w->last_layer[i];
+    const bool first = i == depth - 2;  // the first forward step: its "global" input is x_fused[partner]
+    const int gi = first ? first_step_partner(depth) : -1;
+    const int Lg = first ? p.L[gi] : p.L[i + 1];
+    const float* glo = first ? x.at(p.fused[gi]) : x.at(p.expanded[i + 1]);
+    const NormRef nL = norm_ref(x, p.st_la_l[i], 2, (double)p.L[i] * C, la.local_embedding.gamma, la.local_embedding.beta);
+    const NormRef nA = norm_ref(x, p.st_la_g[i], 4, (double)Lg * C, la.global_act.gamma, la.global_act.beta);
+    const NormRef nE = norm_ref(x, p.st_la_g[i] + 2 * sizeof(double), 4, (double)Lg * C, la.global_embedding.gamma, la.global_embedding.beta);
+    float* d_glo = first ? x.at(p.g_fused[gi]) : x.at(p.g_exp[i + 1]);
+    // x_fused[i] may already hold the gradient it received as the partner of the first step (depth == 2 only)
+    const int acc_loc = fused_written[i];
+    if (int e = la_backward(x, 5, la, gw->last_layer[i], bplain(x.at(p.fused[i]), p.L[i]), SRC_PLAIN, glo, Lg, nL, nA, nE,
+                            p.bs_la[i], x.at(p.g_exp[i]), x.at(p.g_fused[i]), acc_loc, d_glo,
+                            first ? (int)fused_written[gi] : 0)) return e;
+    fused_written[i] = true;
+    if (first) fused_written[gi] = true;
+  }
+  // ---- loc_glo_fus[k] (1-tap LA): x_fused[k] = LA(gLN(spp_k), ga_out)
+  bool spp_written[TDANET_MAX_DEPTH] = {};
+  bool ga_out_written = false;
+  for (int k = 0; k < depth; ++k) {
+    if (!fused_written[k]) continue;
+    const tdanet_la_t& la = w->loc_glo_fus[k];
+    const NormRef nL = norm_ref(x, p.st_lgf[k], 6, (double)p.L[k] * C, la.local_embedding.gamma, la.local_embedding.beta);
+    const NormRef nA = norm_ref(x, p.st_lgf[k] + 2 * sizeof(double), 6, (double)Lb * C, la.global_act.gamma, la.global_act.beta);
+    const NormRef nE = norm_ref(x, p.st_lgf[k] + 4 * sizeof(double), 6, (double)Lb * C, la.global_embedding.gamma, la.global_embedding.beta);
+    if (int e = la_backward(x, 1, la, gw->loc_glo_fus[k], baffine(x.at(p.spp[k]), p.L[k], spp_norm(k)), SRC_AFFINE,
+                            x.at(p.ga_out), Lb, nL, nA, nE, p.bs_lgf[k], x.at(p.g_fused[k]), x.at(p.g_spp[k]), 0,
+                            x.at(p.g_ga_out), ga_out_written)) return e;
+    spp_written[k] = true;
+    ga_out_written = true;
+  }
+  TD_REQUIRE(ga_out_written, "no live x_fused tensor");
+  // ---- bottom-scale block
+  if (int e = global_attention_backward(x)) return e;
+  // ---- ga_in = sum_k avgpool(gLN(spp_k))
+  {
+    Tag t("bwd_pool");
+    for (int k = 0; k < depth; ++k)
+      if (int e = launch_pool_bwd(x.at(p.g_ga_in), x.at(p.g_spp[k]), spp_written[k], B, p.L[k], Lb, C, x.st)) return e;
+  }
+  // ---- spp_dw chain
+  for (int k = depth - 1; k >= 0; --k) {
+    const NormRef nk = spp_norm(k);
+    { Tag t("bwd_gln_stats");
+      if (int e = launch_gln_bwd_stats(x.at(p.g_spp[k]), x.at(p.spp[k]), nk, x.gp(gw->spp_dw[k].gamma),
+                                       x.gp(gw->spp_dw[k].beta), x.at<double>(p.bs_spp[k]), B, p.L[k], C, x.st)) return e; }
+    DwBwdArgs d{};
+    d.g[0] = gln_grad(x.at(p.g_spp[k]), x.at(p.spp[k]), nk, x.at<double>(p.bs_spp[k]));
+    d.w[0] = w->spp_dw[k].w; d.dw[0] = x.gp(gw->spp_dw[k].w); d.db[0] = x.gp(gw->spp_dw[k].b);
+    d.B = B; d.C = C; d.Lout = p.L[k];
+    if (k == 0) {
+      d.xin = baffine(x.at(p.proj), L0, norm_ref(x, p.st_proj, 2, (double)L0 * C, w->proj.gamma, w->proj.beta), w->proj_prelu);
+      d.xkind = SRC_AFFINE_PRELU; d.Lin = L0; d.stride = 1; d.dx = x.at(p.g_proj); d.accumulate = 0;
+      d.dslope = x.gp(gw->proj_prelu);
+    } else {
+      d.xin = baffine(x.at(p.spp[k - 1]), p.L[k - 1], spp_norm(k - 1));
+      d.xkind = SRC_AFFINE; d.Lin = p.L[k - 1]; d.stride = 2; d.dx = x.at(p.g_spp[k - 1]); d.accumulate = 1;
+    }
+    Tag t(k == 0 ? "bwd_spp_dw0" : "bwd_spp_dw_s2");
+    if (int e = launch_dw_bwd(d, 5, 1, x.st)) return e;
+  }
+  // ---- proj_1x1
+  const NormRef n_proj = norm_ref(x, p.st_proj, 2, (double)L0 * C, w->proj.gamma, w->proj.beta);
+  { Tag t("bwd_gln_stats");
+    if (int e = launch_gln_bwd_stats(x.at(p.g_proj), x.at(p.proj), n_proj, x.gp(gw->proj.gamma), x.gp(gw->proj.beta),
+                                     x.at<double>(p.bs_proj), B, L0, C, x.st)) return e; }
+  { Tag t("bwd_gln_apply");
+    if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_proj), x.at(p.proj), n_proj, x.at<double>(p.bs_proj)),
+                                     x.at(p.t_dloc), 0, B, L0, C, x.st)) return e; }  // LA temporaries are free by now
+  { Tag t("wgrad_proj"); if (int e = launch_wgrad(x.at(p.t_dloc), in, x.gp(gw->proj.w), x.gp(gw->proj.b), R0, C, cc, nullptr, x.st)) return e; }
+  Tag t("dgrad_proj");
+  return dgrad(x, x.at(p.t_dloc), p.wt_proj, p.auxt_proj, d_in, L0, cc, C, d_y);
+}
+
+static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const tdanet_weights_t* gw, const float* wav,
+                    const float* d_est, int B, int T, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  Plan p;
+  if (int e = make_plan(c, B, T, p, true)) return e;
+  TD_REQUIRE(w && gw && wav && d_est && workspace, "NULL argument");
+  if (ws_bytes < p.bytes) return fail(TDANET_ENOSPACE, "workspace has %zu bytes, need %zu", ws_bytes, p.bytes);
+  BCtx x{};
+  x.c = c; x.w = w; x.p = &p; x.ws = (char*)workspace; x.st = st; x.blk = 0; x.g = gw;
+  const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
+  const int NS = c->num_sources, CI = NS * Nb, R0 = B * L0, nb = c->num_blocks;
+
+  if (int e = prepare_transposed(x)) return e;
+  TD_CUDA(cudaMemsetAsync(x.at<char>(p.bs_enc), 0, (size_t)B * 2 * sizeof(double), st));
+  TD_CUDA(cudaMemsetAsync(x.at<char>(p.g_x0), 0, (size_t)R0 * cc * sizeof(float), st));
+  {
+    Tag t("bwd_backend");
+    // decoder ConvTranspose1d + crop
+    const size_t n = (size_t)R0 * CI;
+    TD_LAUNCH(dec_bwd_data_kernel, (unsigned)((n + 127) / 128), 128, 0, st, d_est, w->dec_w, x.at(p.g_masked), B, L0, CI, NS, K, S, T, K - S);
+    if (int e = launch_framed_wgrad(x.at(p.masked), d_est, x.gp(gw->dec_w), B, L0, CI, NS, K, S, T, K - S, st)) return e;
+    // masked = relu(m) * enc
+    const size_t ne = (size_t)R0 * Nb;
+    TD_LAUNCH(mask_bwd_kernel, (unsigned)((ne + 255) / 256), 256, 0, st, x.at(p.g_masked), x.at(p.mlogit), x.at(p.enc), x.at(p.g_enc), R0, NS, Nb);
+    // m = mask_conv(prelu(y_last)) + bias
+    const float* y_last = x.at_blk(p.y, nb - 1);
+    if (int e = launch_wgrad(x.at(p.g_masked), y_last, x.gp(gw->mask_w), x.gp(gw->mask_b), R0, CI, cc, w->mask_prelu, st)) return e;
+    if (int e = launch_small_dgrad(x.at(p.g_masked), w->mask_w, x.at(p.g_u[0]), R0, CI, cc, y_last, w->mask_prelu, x.gp(gw->mask_prelu), st)) return e;
+  }
+  // Recurrent, backwards: g_u[cur] holds d loss / d y_blk
+  int cur = 0;
+  for (int blk = nb - 1; blk >= 0; --blk) {
+    BCtx xb = x;
+    xb.blk = blk;
+    const float* in = blk == 0 ? x.at(p.x0) : xb.at(p.bin);
+    if (int e = uconv_block_backward(xb, in, x.at(p.g_u[cur]), x.at(p.g_u[cur ^ 1]))) return e;
+    cur ^= 1;  // g_u[cur] = d loss / d in_blk
+    if (blk > 0) {
+      // in_blk = concat_block(x0 + y_{blk-1})
+      Tag t("bwd_concat");
+      const int rpt = 32;
+      const int threads = cc / 4 > 256 ? 256 : (cc / 4 < 32 ? 32 : cc / 4);
+      dim3 grid(cdiv(R0, rpt), cdiv(cc / 4, threads));
+      TD_LAUNCH_RED(concat_bwd_kernel, grid, threads, 0, st, x.at(p.g_u[cur]), x.at_blk(p.y, blk - 1), x.at(p.x0),
+                     w->concat_w, w->concat_b, w->concat_prelu, x.at(p.g_u[cur ^ 1]), x.at(p.g_x0), x.gp(gw->concat_w),
+                     x.gp(gw->concat_b), x.gp(gw->concat_prelu), R0, cc, rpt);
+      cur ^= 1;  // g_u[cur] = d loss / d y_{blk-1}
+    }
+  }
+  Tag t("bwd_frontend");
+  // d x0 = d in_0 + the mixture path of every concat_block
+  {
+    const size_t n = (size_t)R0 * cc;
+    TD_LAUNCH(add_kernel, (unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, x.at(p.g_u[cur]), x.at(p.g_x0), x.at(p.g_x0), n);
+  }
+  // x0 = bottleneck(gLN(enc))
+  const NormRef n_enc = norm_ref(x, p.st_enc, 2, (double)L0 * Nb, w->ln_gamma, w->ln_beta);
+  {
+    dim3 grid(cdiv(L0 * Nb, 256), 1, B);
+    TD_LAUNCH(gln_fwd_apply_kernel, grid, 256, 0, st, x.at(p.enc), n_enc, x.at(p.nenc), L0, Nb);
+  }
+  if (int e = launch_wgrad(x.at(p.g_x0), x.at(p.nenc), x.gp(gw->bottleneck_w), x.gp(gw->bottleneck_b), R0, cc, Nb, nullptr, st)) return e;
+  float* d_nenc = x.at(p.g_masked);  // free by now, large enough
+  if (int e = launch_small_dgrad(x.at(p.g_x0), w->bottleneck_w, d_nenc, R0, cc, Nb, nullptr, nullptr, nullptr, st)) return e;
+  if (int e = launch_gln_bwd_stats(d_nenc, x.at(p.enc), n_enc, x.gp(gw->ln_gamma), x.gp(gw->ln_beta), x.at<double>(p.bs_enc), B, L0, Nb, st)) return e;
+  if (int e = launch_gln_bwd_apply(gln_grad(d_nenc, x.at(p.enc), n_enc, x.at<double>(p.bs_enc)), x.at(p.g_enc), 1, B, L0, Nb, st)) return e;
+  // encoder Conv1d (pad_input folded into the indexing)
+  return launch_framed_wgrad(x.at(p.g_enc), wav, x.gp(gw->enc_w[0]), B, L0, Nb, 1, K, S, T, K - S, st);
+}
+
+}  // namespace td
+
+using namespace td;
+
+extern "C" {
+
+int tdanet_backward(const tdanet_config_t* cfg, const tdanet_weights_t* w, const tdanet_weights_t* grads,
+                    const float* wav, const float* d_est, int batch, int n_samples, void* workspace,
+                    size_t workspace_bytes, tdanet_stream_t stream) {
+  return backward(cfg, w, grads, wav, d_est, batch, n_samples, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+#ifdef TD_EMU
+const char* tdanet_last_error(void) { return g_err; }
+#endif
+
+}  // extern "C"

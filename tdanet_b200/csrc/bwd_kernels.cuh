@@ -1,0 +1,921 @@
+// Backward kernels of the TDANet separation path (TDANetBest), channels-last [B, L, C] like the forward.
+//
+// What they differentiate (reference lines, all under look2hear/models/TDANet_best.py unless noted):
+//   GlobLN                         :47-64     gln_bwd_stats / GradLoad (normalise-on-load, backward form)
+//   depthwise Conv1d k5/k1 (+bias) :128-156   dw_bwd_kernel (data + weight + bias gradients)
+//   LA gate fusion                 :277-292   la_bwd_a_kernel (sigmoid gate, nearest up-sampling, three GlobLN)
+//   adaptive_avg_pool1d sum        :358-364   pool_bwd_kernel
+//   LayerNorm / MultiheadAttention :236-252   ln_bwd_*, att_bwd_*
+//   1x1 Conv1d / Linear weights      wgrad_kernel, colsum_kernel
+//   concat_block, mask, decoder, encoder :388-398, :505-518, :497   concat_bwd, mask_bwd, dec_bwd_data, framed_wgrad
+//
+// Rule mirrored from the forward: a GlobLN is never applied by a kernel of its own.  For the backward
+// pass that means: whoever produces dY (the gradient w.r.t. a GlobLN *output*) also accumulates
+//   S1_b = sum gamma_c*dY,  S2_b = sum gamma_c*dY*xhat   (per item, double)   and   dgamma_c, dbeta_c,
+// and whoever consumes the gradient w.r.t. the GlobLN *input* forms it on load (GradLoad):
+//   dX = r_b * (gamma_c*dY - S1_b/N - xhat*S2_b/N),   xhat = (X - mu_b) * r_b.
+//
+// The file is written in a subset of CUDA that the CPU emulation shim (emu.h, TD_EMU) can execute, so that
+// gradients are checked against autograd of the oracle before they reach a GPU.
+#pragma once
+#include "kernels.h"
+
+namespace td {
+
+// Adds (a, b) to dst[0], dst[1]: one atomic pair per CTA.  Every thread of the CTA must call it.
+__device__ __forceinline__ void block_accum2(double* dst, double a, double b) {
+#ifdef TD_EMU
+  if (!emu::bs) {  // sequential emulation: no block to reduce over
+    atomicAdd(dst, a);
+    atomicAdd(dst + 1, b);
+    return;
+  }
+#endif
+  __shared__ double sh[64];
+  block_sum2(a, b, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(dst, a);
+    atomicAdd(dst + 1, b);
+  }
+}
+
+// ----------------------------------------------------------------------------- gradient sources
+enum GradKind {
+  G_PLAIN = 0,  // dy
+  G_GLN = 1,    // gradient through a GlobLN, formed on load from (dy, raw x, forward statistics, S1/S2)
+  G_RELU = 2    // dy * [x > 0]   (x: the forward tensor after the ReLU)
+};
+
+struct GradSrc {
+  const float* dy;  // [B, L, C]
+  const float* x;   // G_GLN: raw GlobLN input; G_RELU: forward output
+  NormRef norm;     // G_GLN: forward statistics + gamma
+  const double* S;  // G_GLN: [B, 2]
+  int kind;
+};
+
+template <int V>
+struct GradLoad {
+  vf<V> gr;
+  float r, mur, k1, k2;
+  const float* dy;
+  const float* x;
+  int kind;
+  __device__ __forceinline__ void init(const GradSrc& g, int b, int ch, size_t item_elems) {
+    kind = g.kind;
+    dy = g.dy + (size_t)b * item_elems + ch;
+    x = g.x ? g.x + (size_t)b * item_elems + ch : nullptr;
+    r = 1.f; mur = 0.f; k1 = 0.f; k2 = 0.f;
+    gr = vzero<V>();
+    if (kind == G_GLN) {
+      norm_moments(g.norm, b, r, mur);
+      const vf<V> gam = vload<V>(g.norm.gamma + ch);
+#pragma unroll
+      for (int e = 0; e < V; ++e) gr[e] = gam[e] * r;
+      const double inv = 1.0 / g.norm.count;
+      k1 = (float)((double)r * g.S[2 * b] * inv);
+      k2 = (float)((double)r * g.S[2 * b + 1] * inv);
+    }
+  }
+  // off: row * C
+  __device__ __forceinline__ vf<V> load(size_t off) const {
+    vf<V> d = vload<V>(dy + off);
+    if (kind == G_PLAIN) return d;
+    const vf<V> xv = vload<V>(x + off);
+    if (kind == G_RELU) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) d[e] = xv[e] > 0.f ? d[e] : 0.f;
+      return d;
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float xh = fmaf(xv[e], r, -mur);
+      d[e] = fmaf(gr[e], d[e], -k1) - xh * k2;
+    }
+    return d;
+  }
+};
+
+// forward value of a conv input row (normalise-on-load): PLAIN, AFFINE, AFFINE_PRELU
+template <int V>
+struct FwdLoad {
+  vf<V> sc, sh;
+  float slope;
+  const float* x;
+  int kind;
+  __device__ __forceinline__ void init(const SrcDesc& s, int kind_, int b, int ch, int C) {
+    kind = kind_;
+    x = s.x + (size_t)b * s.L * C + ch;
+    slope = 1.f;
+    if (kind != SRC_PLAIN) norm_coef<V>(s.norm, b, ch, sc, sh);
+    if (kind == SRC_AFFINE_PRELU) slope = __ldg(s.slope);
+  }
+  // pre-activation value (GlobLN output; the raw value for PLAIN)
+  __device__ __forceinline__ vf<V> pre(size_t off) const {
+    vf<V> v = vload<V>(x + off);
+    if (kind != SRC_PLAIN) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
+    }
+    return v;
+  }
+  __device__ __forceinline__ vf<V> load(size_t off) const {
+    vf<V> v = pre(off);
+    if (kind == SRC_AFFINE_PRELU) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = preluf_(v[e], slope);
+    }
+    return v;
+  }
+};
+
+// ----------------------------------------------------------------------------- GlobLN backward
+// statistics pass: dgamma_c += sum dy*xhat, dbeta_c += sum dy, S[b] += (sum gamma*dy, sum gamma*dy*xhat)
+template <int V>
+__global__ void gln_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, NormRef norm,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     double* __restrict__ S, int L, int C, int rows_per_thread) {
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const bool active = ch < C;
+  double s1 = 0.0, s2 = 0.0;
+  if (active) {
+    const int t0 = blockIdx.x * rows_per_thread, t1 = min(t0 + rows_per_thread, L);
+    float r, mur;
+    norm_moments(norm, b, r, mur);
+    const vf<V> gam = vload<V>(norm.gamma + ch);
+    vf<V> dg = vzero<V>(), db = vzero<V>();
+    float a1 = 0.f, a2 = 0.f;
+    for (int t = t0; t < t1; ++t) {
+      const size_t off = ((size_t)b * L + t) * C + ch;
+      const vf<V> d = vload<V>(dy + off), xv = vload<V>(x + off);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float xh = fmaf(xv[e], r, -mur);
+        dg[e] = fmaf(d[e], xh, dg[e]);
+        db[e] += d[e];
+        const float gd = gam[e] * d[e];
+        a1 += gd;
+        a2 = fmaf(gd, xh, a2);
+      }
+    }
+    vred_add<V>(dgamma + ch, dg);
+    vred_add<V>(dbeta + ch, db);
+    s1 = a1;
+    s2 = a2;
+  }
+  block_accum2(S + 2 * b, s1, s2);
+}
+
+// out = dX formed on load (out must not alias g.dy: the source is read through the read-only path); accumulate: out += dX
+template <int V>
+__global__ void gln_bwd_apply_kernel(GradSrc g, float* __restrict__ out, int accumulate, int L, int C,
+                                     int rows_per_thread) {
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (ch >= C) return;
+  const int t0 = blockIdx.x * rows_per_thread, t1 = min(t0 + rows_per_thread, L);
+  GradLoad<V> gl;
+  gl.init(g, b, ch, (size_t)L * C);
+  float* op = out + (size_t)b * L * C + ch;
+  for (int t = t0; t < t1; ++t) {
+    vf<V> v = gl.load((size_t)t * C);
+    if (accumulate) {
+      const vf<V> o = vload_rw<V>(op + (size_t)t * C);
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] += o[e];
+    }
+    vstore<V>(op + (size_t)t * C, v);
+  }
+}
+
+// y = GlobLN(x) materialised (operand of a weight-gradient GEMM), any C
+__global__ void gln_fwd_apply_kernel(const float* __restrict__ x, NormRef norm, float* __restrict__ y, int L, int C) {
+  const int b = blockIdx.z;
+  float r, mur;
+  norm_moments(norm, b, r, mur);
+  const size_t n = (size_t)L * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float g = __ldg(norm.gamma + c);
+    y[(size_t)b * n + i] = fmaf(x[(size_t)b * n + i], g * r, fmaf(-g, mur, __ldg(norm.beta + c)));
+  }
+}
+
+// ----------------------------------------------------------------------------- depthwise conv backward
+// Forward: out_g[to] = sum_tap w_g[c, tap] * xin[to*stride + tap - PAD] (+ bias_g), g < NW convs sharing xin.
+//   dx[ti]    = sum_g sum_tap w_g[c, tap] * G_g[(ti + PAD - tap) / stride]
+//   dw_g[tap] += sum_to G_g[to] * xin[to*stride + tap - PAD];   db_g += sum_to G_g[to]
+// xin is read through its forward on-load transform; for SRC_AFFINE(_PRELU) the stored dx is the gradient
+// w.r.t. the GlobLN output (PReLU derivative applied, slope gradient accumulated).
+struct DwBwdArgs {
+  GradSrc g[2];
+  const float* w[2];
+  float* dw[2];
+  float* db[2];
+  SrcDesc xin;
+  int xkind;
+  int B, C, Lin, Lout, stride;
+  float* dx;       // [B, Lin, C]
+  int accumulate;  // dx += instead of =
+  float* dslope;   // SRC_AFFINE_PRELU
+  int rows_per_thread;
+};
+
+template <int KS, int NW>
+__global__ void dw_bwd_kernel(DwBwdArgs a) {
+  constexpr int V = 4, PAD = (KS - 1) / 2;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const bool active = ch < a.C;
+  double dsl = 0.0;
+  if (active) {
+    const int o0 = blockIdx.x * a.rows_per_thread, o1 = min(o0 + a.rows_per_thread, a.Lout);
+    const int i0 = o0 * a.stride, i1 = o1 == a.Lout ? a.Lin : min(o1 * a.stride, a.Lin);
+    GradLoad<V> gl[NW];
+    float w[NW][KS][V];
+#pragma unroll
+    for (int g = 0; g < NW; ++g) {
+      gl[g].init(a.g[g], b, ch, (size_t)a.Lout * a.C);
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+#pragma unroll
+        for (int k = 0; k < KS; ++k) w[g][k][e] = __ldg(a.w[g] + (size_t)(ch + e) * KS + k);
+    }
+    FwdLoad<V> fx;
+    fx.init(a.xin, a.xkind, b, ch, a.C);
+    // ---- data gradient
+    float* dxp = a.dx + (size_t)b * a.Lin * a.C + ch;
+    float sl_acc = 0.f;
+    for (int ti = i0; ti < i1; ++ti) {
+      vf<V> acc = vzero<V>();
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int num = ti + PAD - k;
+        if (num < 0 || (a.stride == 2 && (num & 1))) continue;
+        const int to = a.stride == 2 ? num >> 1 : num;
+        if (to >= a.Lout) continue;
+#pragma unroll
+        for (int g = 0; g < NW; ++g) {
+          const vf<V> gv = gl[g].load((size_t)to * a.C);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = fmaf(w[g][k][e], gv[e], acc[e]);
+        }
+      }
+      if (a.xkind == SRC_AFFINE_PRELU) {
+        const vf<V> n = fx.pre((size_t)ti * a.C);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          if (n[e] < 0.f) {
+            sl_acc = fmaf(acc[e], n[e], sl_acc);
+            acc[e] *= fx.slope;
+          }
+        }
+      }
+      if (a.accumulate) {
+        const vf<V> o = vload_rw<V>(dxp + (size_t)ti * a.C);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += o[e];
+      }
+      vstore<V>(dxp + (size_t)ti * a.C, acc);
+    }
+    dsl = sl_acc;
+    // ---- weight / bias gradients of the output rows this thread owns
+    float dw[NW][KS][V], db[NW][V];
+#pragma unroll
+    for (int g = 0; g < NW; ++g)
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        db[g][e] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) dw[g][k][e] = 0.f;
+      }
+    for (int to = o0; to < o1; ++to) {
+      vf<V> gv[NW];
+#pragma unroll
+      for (int g = 0; g < NW; ++g) {
+        gv[g] = gl[g].load((size_t)to * a.C);
+#pragma unroll
+        for (int e = 0; e < V; ++e) db[g][e] += gv[g][e];
+      }
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int ti = to * a.stride + k - PAD;
+        if (ti < 0 || ti >= a.Lin) continue;
+        const vf<V> xv = fx.load((size_t)ti * a.C);
+#pragma unroll
+        for (int g = 0; g < NW; ++g)
+#pragma unroll
+          for (int e = 0; e < V; ++e) dw[g][k][e] = fmaf(gv[g][e], xv[e], dw[g][k][e]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < NW; ++g) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) atomicAdd(a.dw[g] + (size_t)(ch + e) * KS + k, dw[g][k][e]);
+        if (a.db[g]) atomicAdd(a.db[g] + ch + e, db[g][e]);
+      }
+    }
+  }
+  if (a.dslope) {  // uniform across the grid
+    __shared__ double sh[64];
+    double z = 0.0;
+#ifdef TD_EMU
+    if (!emu::bs) { atomicAdd(a.dslope, (float)dsl); return; }
+#endif
+    block_sum2(dsl, z, sh);
+    if (threadIdx.x == 0) atomicAdd(a.dslope, (float)dsl);
+  }
+}
+
+// ----------------------------------------------------------------------------- LA backward, phase A
+// Forward (TDANet_best.py:277-292):  A = dw_l(xl), Bt = dw_a(xg), E = dw_e(xg);
+//   out[t] = gLN_L(A)[t] * sigmoid(gLN_A(Bt)[j]) + gLN_E(E)[j],   j = nearest(t; Lg -> Ll).
+// This phase recomputes the three raw conv outputs, writes them and the gradients w.r.t. the three GlobLN
+// outputs, and accumulates the GlobLN backward sums; dw_bwd_kernel finishes the convolutions.
+struct LaBwdArgs {
+  SrcDesc loc;
+  int lkind;         // SRC_PLAIN (x_fused) or SRC_AFFINE (GlobLN(spp_dw[k]) for loc_glo_fus)
+  const float* glo;  // [B, Lg, C]
+  int Lg, B, C;
+  const float *wl, *wa, *we;
+  NormRef nL, nA, nE;
+  const float* dout;  // [B, Ll, C]
+  float scale;        // fl32(Lg / Ll)
+  float *d_loc, *raw_a;                  // [B, Ll, C]
+  float *d_act, *d_emb, *raw_b, *raw_e;  // [B, Lg, C]
+  float *dgamma[3], *dbeta[3];           // local, act, embedding GlobLN
+  double* S[3];
+  int jchunk;
+};
+
+// first local row whose nearest source row is >= j
+__device__ __forceinline__ int first_local_row(int j, float scale, int Ll, int Lg) {
+  if (j <= 0) return 0;
+  if (j >= Lg) return Ll;
+  int t = (int)ceilf((float)j / scale);
+  t = t < 0 ? 0 : (t > Ll ? Ll : t);
+  while (t > 0 && nearest_src(t - 1, scale, Lg) >= j) --t;
+  while (t < Ll && nearest_src(t, scale, Lg) < j) ++t;
+  return t;
+}
+
+template <int KS>
+__global__ void la_bwd_a_kernel(LaBwdArgs a) {
+  constexpr int V = 4, PAD = (KS - 1) / 2;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const bool active = ch < a.C;
+  double s[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+  if (active) {
+    const int Ll = a.loc.L, Lg = a.Lg, C = a.C;
+    const int j0 = blockIdx.x * a.jchunk, j1 = min(j0 + a.jchunk, Lg);
+    float wl[KS][V], wa[KS][V], we[KS][V];
+#pragma unroll
+    for (int e = 0; e < V; ++e)
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        wl[k][e] = __ldg(a.wl + (size_t)(ch + e) * KS + k);
+        wa[k][e] = __ldg(a.wa + (size_t)(ch + e) * KS + k);
+        we[k][e] = __ldg(a.we + (size_t)(ch + e) * KS + k);
+      }
+    vf<V> scL, shL, scA, shA, scE, shE;
+    norm_coef<V>(a.nL, b, ch, scL, shL);
+    norm_coef<V>(a.nA, b, ch, scA, shA);
+    norm_coef<V>(a.nE, b, ch, scE, shE);
+    float rL, murL, rA, murA, rE, murE;
+    norm_moments(a.nL, b, rL, murL);
+    norm_moments(a.nA, b, rA, murA);
+    norm_moments(a.nE, b, rE, murE);
+    const vf<V> gL = vload<V>(a.nL.gamma + ch), gA = vload<V>(a.nA.gamma + ch), gE = vload<V>(a.nE.gamma + ch);
+    FwdLoad<V> fl;
+    fl.init(a.loc, a.lkind, b, ch, C);
+    const float* gp = a.glo + (size_t)b * Lg * C + ch;
+    const float* dop = a.dout + (size_t)b * Ll * C + ch;
+    float* dlp = a.d_loc + (size_t)b * Ll * C + ch;
+    float* rap = a.raw_a + (size_t)b * Ll * C + ch;
+    const size_t goff = (size_t)b * Lg * C + ch;
+    vf<V> dg[3], db[3];
+    float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dg[i] = vzero<V>(); db[i] = vzero<V>(); }
+    int t = first_local_row(j0, a.scale, Ll, Lg);
+    for (int j = j0; j < j1; ++j) {
+      // global branch at centre j
+      vf<V> Bt = vzero<V>(), Et = vzero<V>();
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int jj = j + k - PAD;
+        if (jj < 0 || jj >= Lg) continue;
+        const vf<V> xv = vload<V>(gp + (size_t)jj * C);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          Bt[e] = fmaf(wa[k][e], xv[e], Bt[e]);
+          Et[e] = fmaf(we[k][e], xv[e], Et[e]);
+        }
+      }
+      vf<V> gate;
+#pragma unroll
+      for (int e = 0; e < V; ++e) gate[e] = sigmoidf_(fmaf(Bt[e], scA[e], shA[e]));
+      vf<V> sum_e = vzero<V>(), sum_a = vzero<V>();
+      const int tend = first_local_row(j + 1, a.scale, Ll, Lg);
+      for (; t < tend; ++t) {
+        vf<V> A = vzero<V>();
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const int tt = t + k - PAD;
+          if (tt < 0 || tt >= Ll) continue;
+          const vf<V> xv = fl.load((size_t)tt * C);
+#pragma unroll
+          for (int e = 0; e < V; ++e) A[e] = fmaf(wl[k][e], xv[e], A[e]);
+        }
+        const vf<V> d = vload<V>(dop + (size_t)t * C);
+        vf<V> dl;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float loc = fmaf(A[e], scL[e], shL[e]);
+          sum_e[e] += d[e];
+          sum_a[e] = fmaf(d[e], loc, sum_a[e]);
+          dl[e] = d[e] * gate[e];
+          const float xh = fmaf(A[e], rL, -murL);
+          dg[0][e] = fmaf(dl[e], xh, dg[0][e]);
+          db[0][e] += dl[e];
+          const float gd = gL[e] * dl[e];
+          s1[0] += gd;
+          s2[0] = fmaf(gd, xh, s2[0]);
+        }
+        vstore<V>(dlp + (size_t)t * C, dl);
+        vstore<V>(rap + (size_t)t * C, A);
+      }
+      vf<V> da;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        da[e] = sum_a[e] * gate[e] * (1.f - gate[e]);
+        const float bh = fmaf(Bt[e], rA, -murA), eh = fmaf(Et[e], rE, -murE);
+        dg[1][e] = fmaf(da[e], bh, dg[1][e]);
+        db[1][e] += da[e];
+        const float ga = gA[e] * da[e];
+        s1[1] += ga;
+        s2[1] = fmaf(ga, bh, s2[1]);
+        dg[2][e] = fmaf(sum_e[e], eh, dg[2][e]);
+        db[2][e] += sum_e[e];
+        const float ge = gE[e] * sum_e[e];
+        s1[2] += ge;
+        s2[2] = fmaf(ge, eh, s2[2]);
+      }
+      vstore<V>(a.d_act + goff + (size_t)j * C, da);
+      vstore<V>(a.d_emb + goff + (size_t)j * C, sum_e);
+      vstore<V>(a.raw_b + goff + (size_t)j * C, Bt);
+      vstore<V>(a.raw_e + goff + (size_t)j * C, Et);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      vred_add<V>(a.dgamma[i] + ch, dg[i]);
+      vred_add<V>(a.dbeta[i] + ch, db[i]);
+      s[i][0] = s1[i];
+      s[i][1] = s2[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) block_accum2(a.S[i] + 2 * b, s[i][0], s[i][1]);
+}
+
+// ----------------------------------------------------------------------------- pooling backward
+// ga_in[j] = sum_k mean_{t in bin_k(j)} n_k[t]   =>   dn_k[t] = sum_{j : t in bin_k(j)} g[j] / |bin_k(j)|
+__global__ void pool_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, int accumulate, int L, int Lb,
+                                int C, int rows_per_thread) {
+  constexpr int V = 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (ch >= C) return;
+  const int t0 = blockIdx.x * rows_per_thread, t1 = min(t0 + rows_per_thread, L);
+  const float* gp = g + (size_t)b * Lb * C + ch;
+  float* dp = dx + (size_t)b * L * C + ch;
+  for (int t = t0; t < t1; ++t) {
+    const int jc = (int)(((long)t * Lb) / L);
+    vf<V> acc = vzero<V>();
+    for (int j = jc - 1; j <= jc + 1; ++j) {
+      if (j < 0 || j >= Lb) continue;
+      const int lo = (int)(((long)j * L) / Lb);
+      const int hi = (int)((((long)j + 1) * L + Lb - 1) / Lb);
+      if (t < lo || t >= hi) continue;
+      const float inv = 1.f / (float)(hi - lo);
+      const vf<V> gv = vload<V>(gp + (size_t)j * C);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = fmaf(gv[e], inv, acc[e]);
+    }
+    if (accumulate) {
+      const vf<V> o = vload_rw<V>(dp + (size_t)t * C);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += o[e];
+    }
+    vstore<V>(dp + (size_t)t * C, acc);
+  }
+}
+
+// ----------------------------------------------------------------------------- LayerNorm backward
+// y = LN(k1*x)*w + b per row.  Row pass (one warp per row): rowstat[row] = {mu, rstd, mean(w*dy), mean(w*dy*xhat)}
+__global__ void ln_bwd_rows_kernel(const float* __restrict__ x, float k1, const float* __restrict__ w,
+                                   const float* __restrict__ dy, float* __restrict__ rowstat, int rows, int C) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * C;
+  const float* dr = dy + (size_t)row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += k1 * xr[c];
+  const float mu = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = k1 * xr[c] - mu;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + kEpsLN);
+  float m1 = 0.f, m2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float wd = __ldg(w + c) * dr[c];
+    m1 += wd;
+    m2 = fmaf(wd, (k1 * xr[c] - mu) * rstd, m2);
+  }
+  m1 = warp_sum(m1) / (float)C;
+  m2 = warp_sum(m2) / (float)C;
+  if (lane == 0) {
+    float* o = rowstat + (size_t)row * 4;
+    o[0] = mu; o[1] = rstd; o[2] = m1; o[3] = m2;
+  }
+}
+
+// out = (add ? add : 0) + kout * rstd*(w*dy - m1 - xhat*m2);  dw_c += sum dy*xhat;  db_c += sum dy
+__global__ void ln_bwd_apply_kernel(const float* __restrict__ x, float k1, const float* __restrict__ w,
+                                    const float* __restrict__ dy, const float* __restrict__ rowstat,
+                                    const float* __restrict__ add, float kout, float* __restrict__ out,
+                                    float* __restrict__ dw, float* __restrict__ db, int rows, int C,
+                                    int rows_per_thread) {
+  constexpr int V = 4;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (ch >= C) return;
+  const int r0 = blockIdx.x * rows_per_thread, r1 = min(r0 + rows_per_thread, rows);
+  const vf<V> wv = vload<V>(w + ch);
+  vf<V> aw = vzero<V>(), ab = vzero<V>();
+  for (int r = r0; r < r1; ++r) {
+    const float* rs = rowstat + (size_t)r * 4;
+    const float mu = rs[0], rstd = rs[1], m1 = rs[2], m2 = rs[3];
+    const size_t off = (size_t)r * C + ch;
+    const vf<V> xv = vload<V>(x + off), d = vload<V>(dy + off);
+    vf<V> o = add ? vload<V>(add + off) : vzero<V>();
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float xh = (k1 * xv[e] - mu) * rstd;
+      aw[e] = fmaf(d[e], xh, aw[e]);
+      ab[e] += d[e];
+      o[e] = fmaf(kout * rstd, wv[e] * d[e] - m1 - xh * m2, o[e]);
+    }
+    vstore<V>(out + off, o);
+  }
+  vred_add<V>(dw + ch, aw);
+  vred_add<V>(db + ch, ab);
+}
+
+// ----------------------------------------------------------------------------- attention backward
+// Problem geometry as in attention_kernel (bottom.cu): token(s) = base + s*stride, n tokens per problem.
+// Scratch P, dS: [problem, head, query, key].
+__device__ __forceinline__ void att_problem(int prob, int L, int group, int time_axis, long& base, long& stride) {
+  if (time_axis) {
+    base = (long)prob * L;
+    stride = 1;
+  } else {
+    const int grp = prob / L, t = prob % L;
+    base = (long)grp * group * L + t;
+    stride = L;
+  }
+}
+
+// one thread per (problem, head, query i): softmax row, dS row, dq
+template <int D>
+__global__ void att_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
+                                  float* __restrict__ P, float* __restrict__ dS, float* __restrict__ dqkv,
+                                  int L, int C, int n, int n_head, int group, int time_axis, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int i = idx % n, head = (idx / n) % n_head, prob = idx / (n * n_head);
+  long base, stride;
+  att_problem(prob, L, group, time_axis, base, stride);
+  const float scale = rsqrtf((float)D);
+  const size_t C3 = (size_t)3 * C;
+  const float* qp = qkv + (size_t)(base + (long)i * stride) * C3 + head * D;
+  const float* dop = dctx + (size_t)(base + (long)i * stride) * C + head * D;
+  float* prow = P + ((size_t)(prob * n_head + head) * n + i) * n;
+  float* srow = dS + ((size_t)(prob * n_head + head) * n + i) * n;
+  // scores (kept in prow), running maximum
+  float m = -3.4e38f;
+  for (int j = 0; j < n; ++j) {
+    const float* kp = qkv + (size_t)(base + (long)j * stride) * C3 + C + head * D;
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) acc = fmaf(qp[d] * scale, kp[d], acc);
+    prow[j] = acc;
+    m = fmaxf(m, acc);
+  }
+  float l = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float p = expf(prow[j] - m);
+    prow[j] = p;
+    l += p;
+  }
+  const float inv = 1.f / l;
+  float dsum = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float* vp = qkv + (size_t)(base + (long)j * stride) * C3 + 2 * C + head * D;
+    float dp = 0.f;
+    for (int d = 0; d < D; ++d) dp = fmaf(dop[d], vp[d], dp);
+    const float p = prow[j] * inv;
+    prow[j] = p;
+    srow[j] = dp;
+    dsum = fmaf(p, dp, dsum);
+  }
+  float dq[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) dq[d] = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float ds = prow[j] * (srow[j] - dsum);
+    srow[j] = ds;
+    const float* kp = qkv + (size_t)(base + (long)j * stride) * C3 + C + head * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, kp[d], dq[d]);
+  }
+  float* o = dqkv + (size_t)(base + (long)i * stride) * C3 + head * D;
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = dq[d] * scale;
+}
+
+// one thread per (problem, head, key j): dk, dv
+template <int D>
+__global__ void att_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
+                                   const float* __restrict__ P, const float* __restrict__ dS,
+                                   float* __restrict__ dqkv, int L, int C, int n, int n_head, int group,
+                                   int time_axis, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = idx % n, head = (idx / n) % n_head, prob = idx / (n * n_head);
+  long base, stride;
+  att_problem(prob, L, group, time_axis, base, stride);
+  const float scale = rsqrtf((float)D);
+  const size_t C3 = (size_t)3 * C;
+  const float* pm = P + (size_t)(prob * n_head + head) * n * n;
+  const float* sm = dS + (size_t)(prob * n_head + head) * n * n;
+  float dk[D], dv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+  for (int i = 0; i < n; ++i) {
+    const float p = pm[(size_t)i * n + j], ds = sm[(size_t)i * n + j] * scale;
+    const float* qp = qkv + (size_t)(base + (long)i * stride) * C3 + head * D;
+    const float* dop = dctx + (size_t)(base + (long)i * stride) * C + head * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      dk[d] = fmaf(ds, qp[d], dk[d]);
+      dv[d] = fmaf(p, dop[d], dv[d]);
+    }
+  }
+  float* o = dqkv + (size_t)(base + (long)j * stride) * C3 + C + head * D;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    o[d] = dk[d];
+    o[C + d] = dv[d];
+  }
+}
+
+// ----------------------------------------------------------------------------- weight gradients of 1x1 convs
+// dW[n, k] += sum_r G[r, n] * f(A[r, k]),  f = PReLU(*a_slope) or identity.  64x64 tile per CTA, rows split
+// over blockIdx.z, fp32 FMA, atomics into dW.
+constexpr int WG_T = 64, WG_R = 16;
+__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ G, const float* __restrict__ A,
+                                                    float* __restrict__ dW, int R, int N, int K,
+                                                    const float* __restrict__ a_slope, int rows_per_split) {
+  __shared__ float Gs[WG_R][WG_T + 4];
+  __shared__ float As[WG_R][WG_T + 4];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * WG_T, k0 = blockIdx.y * WG_T;
+  const int r_begin = blockIdx.z * rows_per_split, r_end = min(r_begin + rows_per_split, R);
+  const int tx = tid & 15, ty = tid >> 4;  // tx -> k, ty -> n
+  const float slope = a_slope ? __ldg(a_slope) : 1.f;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int r0 = r_begin; r0 < r_end; r0 += WG_R) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int rr = idx / WG_T, col = idx % WG_T;
+      const int r = r0 + rr;
+      const bool rok = r < r_end;
+      Gs[rr][col] = (rok && n0 + col < N) ? G[(size_t)r * N + n0 + col] : 0.f;
+      float av = (rok && k0 + col < K) ? A[(size_t)r * K + k0 + col] : 0.f;
+      if (a_slope) av = preluf_(av, slope);
+      As[rr][col] = av;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < WG_R; ++rr) {
+      float gv[4], av[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        gv[i] = Gs[rr][ty * 4 + i];
+        av[i] = As[rr][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], av[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) atomicAdd(dW + (size_t)n * K + k, acc[i][j]);
+    }
+  }
+}
+
+// db[n] += sum_r G[r, n]
+__global__ void colsum_kernel(const float* __restrict__ G, float* __restrict__ db, int R, int N, int rows_per_thread) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int r0 = blockIdx.y * rows_per_thread, r1 = min(r0 + rows_per_thread, R);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += G[(size_t)r * N + n];
+  atomicAdd(db + n, acc);
+}
+
+// D[r, n] = sum_k G[r, k] * W[k, n]  (W: a forward weight [out = Kd, in = N], so this is its data gradient),
+// optionally followed by the PReLU derivative of the forward input u:  D *= (u >= 0 ? 1 : slope),
+// dslope += sum D_pre * u * [u < 0].  For the narrow layers (mask conv N_out = 66, bottleneck K = 33).
+__global__ void small_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ W, float* __restrict__ D,
+                                   int R, int Kd, int N, const float* __restrict__ u,
+                                   const float* __restrict__ slope, float* __restrict__ dslope) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double dsl = 0.0;
+  if (idx < (size_t)R * N) {
+    const size_t r = idx / N;
+    const int n = (int)(idx % N);
+    const float* gr = G + r * Kd;
+    float acc = 0.f;
+    for (int k = 0; k < Kd; ++k) acc = fmaf(gr[k], __ldg(W + (size_t)k * N + n), acc);
+    if (u) {
+      const float uv = u[idx];
+      if (uv < 0.f) {
+        dsl = (double)acc * uv;
+        acc *= __ldg(slope);
+      }
+    }
+    D[idx] = acc;
+  }
+  if (dslope) {
+    __shared__ double sh[64];
+    double z = 0.0;
+#ifdef TD_EMU
+    if (!emu::bs) { atomicAdd(dslope, (float)dsl); return; }
+#endif
+    block_sum2(dsl, z, sh);
+    if (threadIdx.x == 0) atomicAdd(dslope, (float)dsl);
+  }
+}
+
+// Wt[k, n] = W[n, k]
+__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int N, int K) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * K) return;
+  const int k = (int)(idx / N), n = (int)(idx % N);
+  Wt[idx] = W[(size_t)n * K + k];
+}
+
+// dst = a + b
+__global__ void add_kernel(const float* a, const float* b, float* dst, size_t n) {  // dst may alias a or b
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = a[i] + b[i];
+}
+
+// ----------------------------------------------------------------------------- concat_block backward
+// forward: out = prelu(z), z = cw_c*(mix + y) + cb_c  (TDANet_best.py:388-398)
+__global__ void concat_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                  const float* __restrict__ mix, const float* __restrict__ cw,
+                                  const float* __restrict__ cb, const float* __restrict__ slope,
+                                  float* __restrict__ dy, float* __restrict__ dmix, float* __restrict__ dcw,
+                                  float* __restrict__ dcb, float* __restrict__ dslope, int rows, int c,
+                                  int rows_per_thread) {
+  constexpr int V = 4;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  double dsl = 0.0;
+  if (ch < c) {
+    const int r0 = blockIdx.x * rows_per_thread, r1 = min(r0 + rows_per_thread, rows);
+    const vf<V> w = vload<V>(cw + ch), bb = vload<V>(cb + ch);
+    const float sl = __ldg(slope);
+    vf<V> aw = vzero<V>(), ab = vzero<V>();
+    float asl = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const size_t off = (size_t)r * c + ch;
+      const vf<V> d = vload<V>(dout + off), yv = vload<V>(y + off), mv = vload<V>(mix + off);
+      vf<V> o, dm = vload_rw<V>(dmix + off);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float s = mv[e] + yv[e];
+        const float z = fmaf(w[e], s, bb[e]);
+        float dz = d[e];
+        if (z < 0.f) {
+          asl = fmaf(d[e], z, asl);
+          dz *= sl;
+        }
+        aw[e] = fmaf(dz, s, aw[e]);
+        ab[e] += dz;
+        o[e] = dz * w[e];
+        dm[e] += o[e];
+      }
+      vstore<V>(dy + off, o);
+      vstore<V>(dmix + off, dm);
+    }
+    vred_add<V>(dcw + ch, aw);
+    vred_add<V>(dcb + ch, ab);
+    dsl = asl;
+  }
+  {
+    __shared__ double sh[64];
+    double z = 0.0;
+#ifdef TD_EMU
+    if (!emu::bs) { atomicAdd(dslope, (float)dsl); return; }
+#endif
+    block_sum2(dsl, z, sh);
+    if (threadIdx.x == 0) atomicAdd(dslope, (float)dsl);
+  }
+}
+
+// ----------------------------------------------------------------------------- mask / decoder / encoder
+// masked[r, s*Nb+n] = relu(m) * enc[r, n]:  d_m (in place over d_masked) and d_enc
+__global__ void mask_bwd_kernel(float* __restrict__ dmasked, const float* __restrict__ m,
+                                const float* __restrict__ enc, float* __restrict__ denc, int rows, int n_src, int Nb) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * Nb) return;
+  const size_t r = idx / Nb;
+  const int n = (int)(idx % Nb);
+  const float ev = enc[idx];
+  float de = 0.f;
+  for (int s = 0; s < n_src; ++s) {
+    const size_t off = r * (size_t)(n_src * Nb) + (size_t)s * Nb + n;
+    const float dm = dmasked[off], mv = m[off];
+    de = fmaf(dm, fmaxf(mv, 0.f), de);
+    dmasked[off] = mv > 0.f ? dm * ev : 0.f;
+  }
+  denc[idx] = de;
+}
+
+// full-length signal of the framed (transposed) convolutions: sig_full[o, n] = sig[o, n - shift] inside [0, T)
+__device__ __forceinline__ float framed_sig(const float* __restrict__ sig, int n, int shift, int T) {
+  const int q = n - shift;
+  return (q >= 0 && q < T) ? sig[q] : 0.f;
+}
+
+// decoder ConvTranspose1d backward w.r.t. its input:
+//   dM[b, l, ci] = sum_o sum_j dfull[b, o, l*S + j - K/2] * W[ci, o, j]
+__global__ void dec_bwd_data_kernel(const float* __restrict__ dest, const float* __restrict__ w,
+                                    float* __restrict__ dM, int B, int L0, int CI, int NO, int K, int S, int T,
+                                    int shift) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * L0 * CI) return;
+  const int ci = (int)(idx % CI);
+  const int l = (int)((idx / CI) % L0);
+  const int b = (int)(idx / ((size_t)CI * L0));
+  float acc = 0.f;
+  for (int o = 0; o < NO; ++o) {
+    const float* sp = dest + ((size_t)b * NO + o) * T;
+    const float* wp = w + ((size_t)ci * NO + o) * K;
+    for (int j = 0; j < K; ++j) acc = fmaf(framed_sig(sp, l * S + j - K / 2, shift, T), __ldg(wp + j), acc);
+  }
+  dM[idx] = acc;
+}
+
+// dW[ci, o, j] += sum_{b, l} M[b, l, ci] * sig_full[b, o, l*S + j - K/2]
+//   decoder weight: M = masked, sig = d_est;   encoder weight: M = d_enc, sig = wav (NO = 1)
+__global__ void framed_wgrad_kernel(const float* __restrict__ M, const float* __restrict__ sig,
+                                    float* __restrict__ dW, int B, int L0, int CI, int NO, int K, int S, int T,
+                                    int shift, int rows_per_split) {
+  const int j = threadIdx.x;
+  const int ci = blockIdx.x / NO, o = blockIdx.x % NO;
+  if (j >= K) return;
+  const int R = B * L0;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(r0 + rows_per_split, R);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const int b = r / L0, l = r % L0;
+    const float mv = M[(size_t)r * CI + ci];
+    acc = fmaf(mv, framed_sig(sig + ((size_t)b * NO + o) * T, l * S + j - K / 2, shift, T), acc);
+  }
+  atomicAdd(dW + ((size_t)ci * NO + o) * K + j, acc);
+}
+
+}  // namespace td

@@ -62,6 +62,11 @@ __global__ void __launch_bounds__(256) coef_inject_gate_kernel(InjectCoefArgs a,
   moments(zs, zq, (double)Lk * C, muz, rz);
   moments(as, aq, (double)a.Lg * C, mua, ra);
   moments(es, eq, (double)a.Lg * C, mue, re);
+  if (a.conv_stats[k] && threadIdx.x == 0) {
+    // sums / sums of squares of the three 1-tap conv outputs, in the NormRef layout, for the backward pass
+    double* cs = a.conv_stats[k] + (size_t)b * 6;
+    cs[0] = zs; cs[1] = zq; cs[2] = as; cs[3] = aq; cs[4] = es; cs[5] = eq;
+  }
   float* o = a.coef[k] + (size_t)b * 6 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double gm = spp.gamma[c];

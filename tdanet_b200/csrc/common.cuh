@@ -1,7 +1,11 @@
 // Shared device/host helpers for the tdanet_b200 kernels (sm_100a only).
 #pragma once
+#ifdef TD_EMU
+#include "emu.h"  // CPU emulation build of the backward pass (tests only)
+#else
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#endif
 #include <stdint.h>
 #include <atomic>
 #include <cstdio>
@@ -41,6 +45,28 @@ struct Tag {
 };
 
 // Every kernel launch goes through this so that tdanet_launch_count() is honest.
+// TD_LAUNCH_COOP marks kernels whose threads communicate (__syncthreads / shuffles); the distinction only
+// matters to the CPU emulation build.
+#ifdef TD_EMU
+#define TD_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
+  do {                                                                                   \
+    emu::launch(dim3(grid), dim3(block), false, [&]() { kernel(__VA_ARGS__); });        \
+    td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+  } while (0)
+#define TD_LAUNCH_COOP(kernel, grid, block, smem, stream, ...)                           \
+  do {                                                                                   \
+    emu::launch(dim3(grid), dim3(block), true, [&]() { kernel(__VA_ARGS__); });         \
+    td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+  } while (0)
+// kernels whose only intra-block communication is a final block reduction (sequential unless TD_EMU_COOP is set)
+#define TD_LAUNCH_RED(kernel, grid, block, smem, stream, ...)                            \
+  do {                                                                                   \
+    emu::launch(dim3(grid), dim3(block), emu::coop_reductions, [&]() { kernel(__VA_ARGS__); }); \
+    td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+  } while (0)
+#else
+#define TD_LAUNCH_COOP TD_LAUNCH
+#define TD_LAUNCH_RED TD_LAUNCH
 #define TD_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
   do {                                                                                   \
     if (td::g_profile) td::profile_mark(#kernel, (stream), true);                        \
@@ -51,6 +77,7 @@ struct Tag {
     if (_e != cudaSuccess)                                                               \
       return td::fail(TDANET_ECUDA, "launch of %s failed: %s", #kernel, cudaGetErrorString(_e)); \
   } while (0)
+#endif
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -89,6 +116,22 @@ __device__ __forceinline__ vf<V> vload(const float* __restrict__ p) {
   return r;
 }
 
+// load of a location the same kernel also writes (read-modify-write): no non-coherent path
+template <int V>
+__device__ __forceinline__ vf<V> vload_rw(const float* p) {
+  vf<V> r;
+  if constexpr (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (V == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = *p;
+  }
+  return r;
+}
+
 template <int V>
 __device__ __forceinline__ void vstore(float* __restrict__ p, const vf<V>& r) {
   if constexpr (V == 4) {
@@ -117,6 +160,7 @@ __device__ __forceinline__ vf<V> alds(const float* p) {  // shared memory
   }
   return r;
 }
+#ifndef TD_EMU
 __device__ __forceinline__ void bf16x2_unpack(uint32_t u, float& lo, float& hi) {
   lo = __uint_as_float(u << 16);
   hi = __uint_as_float(u & 0xffff0000u);
@@ -160,9 +204,14 @@ __device__ __forceinline__ void astore(__nv_bfloat16* __restrict__ p, const vf<V
   }
 }
 
+#endif  // !TD_EMU
+
 // fire-and-forget vector reduction into global memory (red.global.add.v{2,4}.f32 on sm_90+)
 template <int V>
 __device__ __forceinline__ void vred_add(float* p, const vf<V>& r) {
+#ifdef TD_EMU
+  for (int e = 0; e < V; ++e) atomicAdd(p + e, r.v[e]);
+#else
   if constexpr (V == 4) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
                  "f"(r.v[2]), "f"(r.v[3])
@@ -172,14 +221,19 @@ __device__ __forceinline__ void vred_add(float* p, const vf<V>& r) {
   } else {
     atomicAdd(p, r.v[0]);
   }
+#endif
 }
 
 // round-to-nearest (ties away) to TF32: what producers of GEMM-only operands store in TF32 mode so
 // that the tensor core's truncation of the low 13 mantissa bits is exact
 __device__ __forceinline__ float tf32_rna(float x) {
+#ifdef TD_EMU
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+#else
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+#endif
 }
 template <int V>
 __device__ __forceinline__ void vround_tf32(vf<V>& r) {
@@ -226,10 +280,14 @@ __device__ __forceinline__ vf<V> vadd(const vf<V>& a, const vf<V>& b) {
 // sigmoid on the SFU: 1 / (1 + 2^(-x*log2(e))) with ex2.approx / rcp.approx (4 instructions; exact limits
 // 0 and 1 for large |x|, relative error ~1e-6)
 __device__ __forceinline__ float sigmoidf_(float x) {
+#ifdef TD_EMU
+  return 1.f / (1.f + expf(-x));
+#else
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
   return r;
+#endif
 }
 __device__ __forceinline__ float preluf_(float x, float a) { return x >= 0.f ? x : a * x; }
 

@@ -4,10 +4,7 @@
 // (TDANet_best.py:342-399, 482-521; TDANet.py:586-636, 769-785, 869-909; TDANet_mult_tes.py:391-434,
 // 540-579).  Everything between two GlobLN-delimited tensors is one launch; see DESIGN.md for the
 // stage list and the bytes each stage moves.
-#include "kernels.h"
-#include <cstring>
-#include <string>
-#include <vector>
+#include "plan.h"
 
 namespace td {
 
@@ -52,176 +49,7 @@ void profile_mark(const char* name, cudaStream_t st, bool begin) {
   }
 }
 
-// ----------------------------------------------------------------------------- plan
-struct Named {
-  std::string name;
-  size_t off;  // bytes
-  int64_t dims[3];
-};
-
-struct Plan {
-  int B, T, Tp, rest;
-  int depth, L[TDANET_MAX_DEPTH], Lb;
-  size_t bytes = 0;
-  std::vector<Named> named;
-  // activations
-  size_t enc, x0, u[2], proj, spp[TDANET_MAX_DEPTH], expanded[TDANET_MAX_DEPTH];
-  size_t ga_in, attn_in, qkv, attn_ctx, attn_out, ga_mid, fc1, ffn_dw, fc2, ga_out;
-  size_t pool_dw[TDANET_MAX_DEPTH], pool_pw[TDANET_MAX_DEPTH];
-  size_t fused_a, fused_b;  // x_fused[depth-2] and its "global" partner of the first top-down step, materialised
-  size_t masked;
-  // closed-form loc_glo_fus coefficient tables (BEST), [B,6,C] per scale
-  size_t inj_coef[TDANET_MAX_DEPTH];
-  // statistics arena (zeroed once per block)
-  size_t stats_begin, stats_end;
-  // per-item sum / sum of squares in double: [B,2] ([B,2,2] for st_la_g: global_act, global_embedding)
-  size_t st_enc, st_proj, st_fc1, st_fc2, st_pool[TDANET_MAX_DEPTH], st_spp[TDANET_MAX_DEPTH],
-      st_la_l[TDANET_MAX_DEPTH], st_la_g[TDANET_MAX_DEPTH];
-  // per-channel sums in float [B,2,C] (BEST: inputs of the closed-form loc_glo_fus statistics)
-  size_t st_spp_ch[TDANET_MAX_DEPTH], st_g;
-  // TF32 auxiliary weight copies
-  size_t aux_proj, aux_res, aux_in, aux_out, aux_fc1, aux_fc2, aux_pool[TDANET_MAX_DEPTH];
-
-  size_t take(size_t nbytes) {
-    size_t o = bytes;
-    bytes += (nbytes + 255) / 256 * 256;
-    return o;
-  }
-  size_t act(const char* name, int64_t L_, int64_t C_) {
-    size_t o = take((size_t)B * L_ * C_ * sizeof(float));
-    if (name) named.push_back({name, o, {B, L_, C_}});
-    return o;
-  }
-};
-
-static int check_config(const tdanet_config_t* c) {
-  TD_REQUIRE(c != nullptr, "config is NULL");
-  TD_REQUIRE(c->variant >= TDANET_BEST && c->variant <= TDANET_MULTRES, "unknown variant %d", c->variant);
-  TD_REQUIRE(c->depth >= 2 && c->depth <= TDANET_MAX_DEPTH, "upsampling_depth %d outside [2, %d]", c->depth, TDANET_MAX_DEPTH);
-  TD_REQUIRE(c->num_blocks >= 1, "num_blocks %d", c->num_blocks);
-  TD_REQUIRE(c->out_channels > 0 && c->out_channels % 16 == 0, "out_channels %d must be a multiple of 16", c->out_channels);
-  TD_REQUIRE(c->in_channels > 0 && c->in_channels % 16 == 0, "in_channels %d must be a multiple of 16", c->in_channels);
-  TD_REQUIRE(c->n_head > 0 && c->in_channels % c->n_head == 0, "in_channels %d not divisible by n_head %d", c->in_channels, c->n_head);
-  TD_REQUIRE(c->enc_kernel > 0 && c->enc_kernel % 4 == 0 && c->enc_stride == c->enc_kernel / 4, "encoder window %d / hop %d", c->enc_kernel, c->enc_stride);
-  TD_REQUIRE(c->num_sources == 2 || c->num_sources == 3, "num_sources %d", c->num_sources);
-  TD_REQUIRE(c->gemm_mode >= TDANET_GEMM_FP32 && c->gemm_mode <= TDANET_GEMM_TF32X3, "gemm_mode %d", c->gemm_mode);
-  TD_REQUIRE(c->act_dtype == TDANET_ACT_F32 || c->act_dtype == TDANET_ACT_BF16, "act_dtype %d", c->act_dtype);
-  if (c->act_dtype == TDANET_ACT_BF16) {
-    TD_REQUIRE(c->gemm_mode != TDANET_GEMM_FP32, "bf16 activation storage needs a tensor-core gemm_mode");
-    TD_REQUIRE(c->out_channels % 32 == 0 && c->in_channels % 64 == 0,
-               "bf16 activation storage needs out_channels %% 32 == 0 and in_channels %% 64 == 0 (got %d / %d)",
-               c->out_channels, c->in_channels);
-  }
-  if (c->variant == TDANET_MULTRES) {
-    TD_REQUIRE(c->enc_convs >= 1 && c->enc_convs <= TDANET_MAX_ENC && c->out_channels % c->enc_convs == 0,
-               "MULTRES: out_channels %d not divisible by kernels %d", c->out_channels, c->enc_convs);
-    TD_REQUIRE(c->n_basis == c->out_channels, "MULTRES: n_basis %d != out_channels %d", c->n_basis, c->out_channels);
-  } else {
-    TD_REQUIRE(c->enc_convs == 1, "enc_convs %d", c->enc_convs);
-    TD_REQUIRE(c->n_basis == c->enc_kernel / 2 + 1, "n_basis %d != K/2+1", c->n_basis);
-  }
-  return 0;
-}
-
-static int make_plan(const tdanet_config_t* c, int B, int T, Plan& p) {
-  if (int e = check_config(c)) return e;
-  TD_REQUIRE(B > 0 && T > 0, "batch %d / n_samples %d", B, T);
-  const int K = c->enc_kernel, S = c->enc_stride, C = c->in_channels, cc = c->out_channels;
-  p.B = B;
-  p.T = T;
-  // pad_input (TDANet_best.py:465-479)
-  p.rest = K - (S + T % K) % K;
-  p.Tp = T + p.rest + 2 * (K - S);
-  p.depth = c->depth;
-  p.L[0] = p.Tp / S + 1;  // Conv1d(k, stride S, padding k/2), k even
-  for (int k = 1; k < c->depth; ++k) p.L[k] = (p.L[k - 1] - 1) / 2 + 1;
-  p.Lb = p.L[c->depth - 1];
-  const int L0 = p.L[0], Lb = p.Lb, Nb = c->n_basis;
-  char nm[32];
-
-  p.enc = p.act("enc", L0, Nb);
-  p.x0 = p.act("x0", L0, cc);
-  p.u[0] = p.act("u0", L0, cc);
-  p.u[1] = p.act("u1", L0, cc);
-  p.proj = p.act("proj", L0, C);
-  for (int k = 0; k < c->depth; ++k) {
-    snprintf(nm, sizeof nm, "spp%d", k);
-    p.spp[k] = p.act(nm, p.L[k], C);
-  }
-  for (int k = 0; k < c->depth - 1; ++k) {
-    snprintf(nm, sizeof nm, "expanded%d", k);
-    p.expanded[k] = p.act(nm, p.L[k], C);
-  }
-  p.ga_in = p.act("ga_in", Lb, C);
-  p.attn_in = p.act("attn_in", Lb, C);
-  p.qkv = p.act("qkv", Lb, 3 * C);
-  p.attn_ctx = p.act("attn_ctx", Lb, C);
-  p.attn_out = p.act("attn_out", Lb, C);
-  p.ga_mid = p.act("ga_mid", Lb, C);
-  p.fc1 = p.act("fc1", Lb, 2 * C);
-  p.ffn_dw = p.act("ffn_dw", Lb, 2 * C);
-  p.fc2 = p.act("fc2", Lb, C);
-  p.ga_out = p.act("ga_out", Lb, C);
-  for (int k = 0; k < c->depth; ++k) {
-    // FORK: conv_pool dw / pw outputs.  BEST / MULTRES: pool_pw[k] holds the pooled raw spp_dw[k] output.
-    if (c->variant == TDANET_FORK) {
-      snprintf(nm, sizeof nm, "pool_dw%d", k);
-      p.pool_dw[k] = p.act(nm, Lb, C);
-    }
-    snprintf(nm, sizeof nm, "pool_pw%d", k);
-    p.pool_pw[k] = p.act(nm, Lb, C);
-  }
-  p.fused_a = p.act("fused_a", p.L[c->depth - 2], C);
-  p.fused_b = p.act("fused_b", p.L[(c->depth - 3 + c->depth) % c->depth], C);
-  p.masked = p.act("masked", L0, c->num_sources * Nb);
-
-  auto tab = [&](int planes, int ch) { return p.take((size_t)B * planes * ch * sizeof(float)); };
-  for (int k = 0; k < c->depth; ++k) p.inj_coef[k] = tab(6, C);
-  p.stats_begin = p.bytes;
-  auto dstat = [&](int n) { return p.take((size_t)B * n * 2 * sizeof(double)); };
-  p.st_enc = dstat(1);
-  p.st_proj = dstat(1);
-  p.st_fc1 = dstat(1);
-  p.st_fc2 = dstat(1);
-  for (int k = 0; k < c->depth; ++k) {
-    p.st_pool[k] = dstat(1);
-    p.st_spp[k] = dstat(1);
-    p.st_la_l[k] = dstat(1);
-    p.st_la_g[k] = dstat(2);
-    p.st_spp_ch[k] = tab(2, C);
-  }
-  p.st_g = tab(2, C);
-  p.stats_end = p.bytes;
-
-  auto wbuf = [&](size_t n) { return p.take(n * sizeof(float)); };
-  p.aux_proj = wbuf((size_t)C * cc);
-  p.aux_res = wbuf((size_t)cc * C);
-  p.aux_in = wbuf((size_t)3 * C * C);
-  p.aux_out = wbuf((size_t)C * C);
-  p.aux_fc1 = wbuf((size_t)2 * C * C);
-  p.aux_fc2 = wbuf((size_t)2 * C * C);
-  for (int k = 0; k < c->depth; ++k) p.aux_pool[k] = c->variant == TDANET_FORK ? wbuf((size_t)C * C) : 0;
-  // "block_out" aliases the u buffer the last block writes
-  p.named.push_back({"block_out", p.u[(c->num_blocks - 1) & 1], {B, L0, cc}});
-  p.named.push_back({"u", p.u[(c->num_blocks & 1)], {B, L0, cc}});
-  return 0;
-}
-
 // ----------------------------------------------------------------------------- forward
-struct Ctx {
-  const tdanet_config_t* c;
-  const tdanet_weights_t* w;
-  const Plan* p;
-  char* ws;
-  cudaStream_t st;
-  // producers of GEMM-only operands store TF32-rounded values when the tensor-core path is on
-  int rnd() const { return c->gemm_mode != TDANET_GEMM_FP32; }
-  // large activations (proj, spp, expanded, materialised x_fused) stored as bf16
-  int bf() const { return c->act_dtype == TDANET_ACT_BF16; }
-  template <class T = float>
-  T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
-};
-
 static int gemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
   if (x.c->gemm_mode == TDANET_GEMM_FP32) return launch_gemm_simt(g, x.st);
   g.W_aux = x.at(aux_off);
@@ -249,10 +77,6 @@ static int prepare_weights(const Ctx& x) {
   return 0;
 }
 
-static NormRef norm_ref(const Ctx& x, size_t stats_off, int item_stride, double count, const float* gamma,
-                        const float* beta) {
-  return NormRef{x.at<double>(stats_off), item_stride, count, gamma, beta};
-}
 static SrcDesc plain_src(const float* x, int L) {
   SrcDesc s{};
   s.x = x; s.L = L;
@@ -317,7 +141,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   const tdanet_weights_t* w = x.w;
   const Plan& p = *x.p;
   const int B = p.B, C = c->in_channels, cc = c->out_channels, depth = c->depth, Lb = p.Lb;
-  TD_CUDA(cudaMemsetAsync(x.ws + p.st_proj, 0, p.stats_end - p.st_proj, x.st));
+  TD_CUDA(cudaMemsetAsync(x.at<char>(p.st_proj), 0, p.stats_end - p.st_proj, x.st));
 
   // proj_1x1: 1x1 conv c -> C (+bias); GlobLN + PReLU are applied by the consumer on load
   GemmArgs g{};
@@ -390,15 +214,27 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     for (int k = 0; k < depth; ++k) {
       ia.spp_stats[k] = x.at(p.st_spp_ch[k]); ia.L[k] = p.L[k]; ia.spp[k] = w->spp_dw[k];
       ia.la[k] = w->loc_glo_fus[k]; ia.coef[k] = x.at(p.inj_coef[k]);
+      ia.conv_stats[k] = p.train ? x.at<double>(p.st_lgf[k]) : nullptr;
     }
     if (int e = launch_coef_inject_gate(ia, B, C, x.st)) return e;
+  }
+  // training: every live x_fused[k] is kept for the backward pass, and the top-down steps read it back
+  bool fused_live[TDANET_MAX_DEPTH] = {};
+  if (p.train) {
+    for (int k = 0; k < depth - 1; ++k) fused_live[k] = true;
+    fused_live[first_step_partner(depth)] = true;
+    Tag t("fused_materialize");
+    for (int k = 0; k < depth; ++k)
+      if (fused_live[k])
+        if (int e = launch_inject_materialize(inj_src(k), inj_kind, B, C, x.at(p.fused[k]), 0, x.st)) return e;
   }
   // statistics of the local branch of every top-down step (independent of the chain): one launch
   {
     DwArgs dl[TDANET_MAX_DEPTH];
     for (int i = 0; i < depth - 1; ++i) {
       dl[i] = DwArgs{};
-      dl[i].src = inj_src(i); dl[i].kind = inj_kind; dl[i].B = B; dl[i].C = C; dl[i].Lout = p.L[i]; dl[i].stride = 1;
+      if (p.train) { dl[i].src = plain_src(x.at(p.fused[i]), p.L[i]); dl[i].kind = SRC_PLAIN; }
+      else { dl[i].src = inj_src(i); dl[i].kind = inj_kind; } dl[i].B = B; dl[i].C = C; dl[i].Lout = p.L[i]; dl[i].stride = 1;
       dl[i].nw = 1; dl[i].w[0] = w->last_layer[i].local_embedding.w; dl[i].stats = x.at<double>(p.st_la_l[i]);
       dl[i].act_bf16 = x.bf();
     }
@@ -410,7 +246,12 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     const tdanet_la_t& la = w->last_layer[i];
     SrcDesc loc = inj_src(i), glo;
     int lkind = inj_kind, gkind;
-    if (i == depth - 2) {
+    if (p.train) {
+      const int gi = i == depth - 2 ? first_step_partner(depth) : -1;
+      loc = plain_src(x.at(p.fused[i]), p.L[i]);
+      glo = gi >= 0 ? plain_src(x.at(p.fused[gi]), p.L[gi]) : plain_src(x.at(p.expanded[i + 1]), p.L[i + 1]);
+      lkind = gkind = SRC_PLAIN;
+    } else if (i == depth - 2) {
       // python x_fused[i-1]: the finer neighbour (or [-1]).  Both operands of this step are small and its
       // nearest *down*-sampling would re-derive every injected row five times: write the two tensors out once.
       const SrcDesc gsrc = inj_src((i - 1 + depth) % depth);
@@ -446,20 +287,25 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   g.resid = in; g.mix = x.at(p.x0); g.cw = w->concat_w; g.cb = w->concat_b; g.cslope = w->concat_prelu; g.last = last;
   g.a_bf16 = x.bf();
   Tag tr("gemm_res_conv");
-  return gemm(x, g, p.aux_res);
+  if (!p.train) return gemm(x, g, p.aux_res);
+  // training: keep y = res_conv(expanded) + residual, and apply concat_block in its own launch
+  g.D = x.at(p.y); g.last = 1;
+  if (int e = gemm(x, g, p.aux_res)) return e;
+  if (last) return 0;
+  return launch_concat(x.at(p.y), x.at(p.x0), w->concat_w, w->concat_b, w->concat_prelu, out, B * p.L[0], cc, x.st);
 }
 
 static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const float* wav, int B, int T,
-                   float* est, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                   float* est, void* workspace, size_t ws_bytes, cudaStream_t st, bool train) {
   Plan p;
-  if (int e = make_plan(c, B, T, p)) return e;
+  if (int e = make_plan(c, B, T, p, train)) return e;
   TD_REQUIRE(w && wav && est && workspace, "NULL argument");
   if (ws_bytes < p.bytes) return fail(TDANET_ENOSPACE, "workspace has %zu bytes, need %zu", ws_bytes, p.bytes);
   TD_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   Ctx x{c, w, &p, (char*)workspace, st};
   const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
 
-  TD_CUDA(cudaMemsetAsync(x.ws + p.st_enc, 0, p.st_proj - p.st_enc, st));
+  TD_CUDA(cudaMemsetAsync(x.ws + p.st_enc, 0, (size_t)B * 2 * sizeof(double), st));
   Tag tag("frontend");
   if (int e = prepare_weights(x)) return e;
   // encoder (+ pad_input folded into the indexing) and its GlobLN statistics
@@ -477,16 +323,31 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
   }
   // Recurrent: num_blocks iterations of one shared UConvBlock
   for (int blk = 0; blk < c->num_blocks; ++blk) {
+    if (train) {
+      // block `blk` reads its own arena's `bin` (block 0: x0) and writes the next block's `bin`
+      Ctx xb = x;
+      xb.blk = blk;
+      const bool last = blk == c->num_blocks - 1;
+      const float* in = blk == 0 ? x.at(p.x0) : xb.at(p.bin);
+      if (int e = uconv_block(xb, in, last ? nullptr : x.at_blk(p.bin, blk + 1), last)) return e;
+      continue;
+    }
     const float* in = blk == 0 ? x.at(p.x0) : x.at(p.u[(blk - 1) & 1]);
     if (int e = uconv_block(x, in, x.at(p.u[blk & 1]), blk == c->num_blocks - 1)) return e;
   }
   // mask_net (PReLU -> 1x1) -> ReLU -> * encoder output, then decoder + crop
   GemmArgs g{};
-  g.A = x.at(p.u[(c->num_blocks - 1) & 1]); g.W = w->mask_w; g.bias = w->mask_b; g.D = x.at(p.masked);
+  g.A = train ? x.at_blk(p.y, c->num_blocks - 1) : x.at(p.u[(c->num_blocks - 1) & 1]);
+  g.W = w->mask_w; g.bias = w->mask_b; g.D = x.at(p.masked);
   g.B = B; g.L = L0; g.N = c->num_sources * Nb; g.K = cc; g.epi = EPI_MASK; g.a_slope = w->mask_prelu;
   g.enc = x.at(p.enc); g.Nb = Nb;
   Tag tb("backend");
-  if (int e = launch_gemm_simt(g, st)) return e;
+  if (train) {
+    // keep the mask logits: masked = relu(m) * enc is applied by its own launch
+    g.D = x.at(p.mlogit); g.epi = EPI_BIAS;
+    if (int e = launch_gemm_simt(g, st)) return e;
+    if (int e = launch_mask_apply(x.at(p.mlogit), x.at(p.enc), x.at(p.masked), B * L0, c->num_sources, Nb, st)) return e;
+  } else if (int e = launch_gemm_simt(g, st)) return e;
   return launch_decoder(x.at(p.masked), w->dec_w, est, B, L0, Nb, c->num_sources, K, S, T, st);
 }
 
@@ -554,40 +415,14 @@ int tdanet_profile_dump(char* out, size_t cap) {
   return (int)s.size();
 }
 
-int tdanet_workspace_bytes(const tdanet_config_t* cfg, int batch, int n_samples, size_t* bytes) {
-  Plan p;
-  if (int e = make_plan(cfg, batch, n_samples, p)) return e;
-  TD_REQUIRE(bytes != nullptr, "bytes is NULL");
-  *bytes = p.bytes;
-  return 0;
-}
-
-int tdanet_latent_lengths(const tdanet_config_t* cfg, int n_samples, int32_t* lengths, int32_t* padded_len, int32_t* rest) {
-  Plan p;
-  if (int e = make_plan(cfg, 1, n_samples, p)) return e;
-  if (lengths) for (int k = 0; k < cfg->depth; ++k) lengths[k] = p.L[k];
-  if (padded_len) *padded_len = p.Tp;
-  if (rest) *rest = p.rest;
-  return 0;
-}
-
-int tdanet_workspace_tensor(const tdanet_config_t* cfg, int batch, int n_samples, const char* name,
-                            size_t* byte_offset, int64_t dims[3]) {
-  Plan p;
-  if (int e = make_plan(cfg, batch, n_samples, p)) return e;
-  TD_REQUIRE(name != nullptr, "name is NULL");
-  for (auto it = p.named.rbegin(); it != p.named.rend(); ++it)
-    if (it->name == name) {
-      if (byte_offset) *byte_offset = it->off;
-      if (dims) { dims[0] = it->dims[0]; dims[1] = it->dims[1]; dims[2] = it->dims[2]; }
-      return 0;
-    }
-  return fail(TDANET_EINVAL, "unknown workspace tensor '%s'", name);
-}
-
 int tdanet_forward(const tdanet_config_t* cfg, const tdanet_weights_t* w, const float* wav, int batch,
                    int n_samples, float* est, void* workspace, size_t workspace_bytes, tdanet_stream_t stream) {
-  return forward(cfg, w, wav, batch, n_samples, est, workspace, workspace_bytes, (cudaStream_t)stream);
+  return forward(cfg, w, wav, batch, n_samples, est, workspace, workspace_bytes, (cudaStream_t)stream, false);
+}
+
+int tdanet_forward_train(const tdanet_config_t* cfg, const tdanet_weights_t* w, const float* wav, int batch,
+                         int n_samples, float* est, void* workspace, size_t workspace_bytes, tdanet_stream_t stream) {
+  return forward(cfg, w, wav, batch, n_samples, est, workspace, workspace_bytes, (cudaStream_t)stream, true);
 }
 
 size_t tdanet_gemm_workspace_bytes(int N, int K) { return ((size_t)N * K * sizeof(float) + 255) / 256 * 256; }

@@ -213,4 +213,38 @@ int launch_decoder(const float* masked, const float* w, float* est, int B, int L
   return 0;
 }
 
+// ----------------------------------------------------------------------------- training-forward glue
+__global__ void concat_kernel(const float* __restrict__ y, const float* __restrict__ mix,
+                              const float* __restrict__ cw, const float* __restrict__ cb,
+                              const float* __restrict__ slope, float* __restrict__ out, size_t n, int c) {
+  const float sl = __ldg(slope);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    out[i] = preluf_(fmaf(__ldg(cw + ch), mix[i] + y[i], __ldg(cb + ch)), sl);
+  }
+}
+
+int launch_concat(const float* y, const float* mix, const float* cw, const float* cb, const float* slope,
+                  float* out, int rows, int c, cudaStream_t st) {
+  const size_t n = (size_t)rows * c;
+  TD_LAUNCH(concat_kernel, (unsigned)((n + 255) / 256), 256, 0, st, y, mix, cw, cb, slope, out, n, c);
+  return 0;
+}
+
+__global__ void mask_apply_kernel(const float* __restrict__ m, const float* __restrict__ enc,
+                                  float* __restrict__ masked, size_t n, int CI, int Nb) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / CI;
+    const int col = (int)(i % CI);
+    masked[i] = fmaxf(m[i], 0.f) * enc[r * Nb + col % Nb];
+  }
+}
+
+int launch_mask_apply(const float* m, const float* enc, float* masked, int rows, int n_src, int Nb, cudaStream_t st) {
+  const int CI = n_src * Nb;
+  const size_t n = (size_t)rows * CI;
+  TD_LAUNCH(mask_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, m, enc, masked, n, CI, Nb);
+  return 0;
+}
+
 }  // namespace td

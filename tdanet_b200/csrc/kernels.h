@@ -85,6 +85,7 @@ struct InjectCoefArgs {
   tdanet_convnorm_t spp[TDANET_MAX_DEPTH];
   tdanet_la_t la[TDANET_MAX_DEPTH];
   float* coef[TDANET_MAX_DEPTH];
+  double* conv_stats[TDANET_MAX_DEPTH];  // optional [B,3,2]: sum / sum of squares of the local, act, embedding conv outputs
   const float* g_stats;
   int Lg;
 };
@@ -138,6 +139,12 @@ int launch_bottleneck(const float* enc, const NormRef& norm, const float* w, con
 // decoder ConvTranspose1d + crop: masked [B, L0, n_src*Nb] -> est [B, n_src, T]
 int launch_decoder(const float* masked, const float* w, float* est, int B, int L0, int Nb,
                    int n_src, int K, int S, int T, cudaStream_t st);
+
+// training forward: out = prelu(cw*(mix + y) + cb, *slope)   (concat_block, TDANet_best.py:388-398), [rows, c]
+int launch_concat(const float* y, const float* mix, const float* cw, const float* cb, const float* slope,
+                  float* out, int rows, int c, cudaStream_t st);
+// training forward: masked[r, s*Nb+n] = relu(m[r, s*Nb+n]) * enc[r, n]   (TDANet_best.py:507-509)
+int launch_mask_apply(const float* m, const float* enc, float* masked, int rows, int n_src, int Nb, cudaStream_t st);
 
 // ------------------------------------------------------------------ gemm_simt.cu / gemm_tc.cu
 enum GemmEpi {

@@ -15,9 +15,11 @@ from . import _lib
 from ._lib import Config, Weights, check
 
 
-def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+def _ptr(t: Optional[torch.Tensor], allow_host: bool = False) -> Optional[int]:
     if t is None:
         return None
+    if allow_host and not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+        return t.data_ptr()   # tests/test_backward_emu.py only: the CPU emulation build of the kernels
     if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
         raise _lib.TdanetError(
             f"parameter must be a contiguous fp32 CUDA tensor (got {t.dtype}, {t.device}); "
@@ -71,21 +73,25 @@ class SeparationEngine:
         return list(lens[: self.cfg.depth]), tp.value, rest.value
 
     # ------------------------------------------------------------------ weights
-    def pack(self, sd: Dict[str, torch.Tensor]) -> Weights:
-        """state_dict (reference key names) -> tdanet_weights_t of device pointers."""
+    def pack(self, sd: Dict[str, torch.Tensor], _allow_host: bool = False, optional: bool = False) -> Weights:
+        """state_dict (reference key names) -> tdanet_weights_t of device pointers.
+
+        `optional`: missing keys become NULL (used to pack gradient buffers, which have no `pe`)."""
         v, d = self.variant, self.cfg.depth
         gk, bk = ("gamma", "beta") if v == "best" else ("weight", "bias")
         w = Weights()
         keep = []
 
+        all_optional = optional
+
         def P(key, optional=False):
             t = sd.get(key)
             if t is None:
-                if optional:
+                if optional or all_optional:
                     return None
                 raise KeyError(f"state_dict has no '{key}'")
             keep.append(t)
-            return _ptr(t)
+            return _ptr(t, _allow_host)
 
         def convnorm(dst, prefix, bias):
             dst.w = P(f"{prefix}.conv.weight")
@@ -121,8 +127,8 @@ class SeparationEngine:
             la(w.last_layer[i], f"{u}.last_layer.{i}")
         w.res_w, w.res_b = P(f"{u}.res_conv.weight"), P(f"{u}.res_conv.bias")
         a = f"{u}.globalatt.attn"
-        pe = sd[f"{a}.pos_enc.pe"]
-        w.pe, w.pe_rows = P(f"{a}.pos_enc.pe"), int(pe.shape[1])
+        pe = sd.get(f"{a}.pos_enc.pe")
+        w.pe, w.pe_rows = P(f"{a}.pos_enc.pe"), (int(pe.shape[1]) if pe is not None else 0)
         w.ln1_w, w.ln1_b = P(f"{a}.attn_in_norm.weight"), P(f"{a}.attn_in_norm.bias")
         w.in_proj_w, w.in_proj_b = P(f"{a}.attn.in_proj_weight"), P(f"{a}.attn.in_proj_bias")
         w.out_proj_w, w.out_proj_b = P(f"{a}.attn.out_proj.weight"), P(f"{a}.attn.out_proj.bias")
@@ -135,7 +141,7 @@ class SeparationEngine:
         w.concat_prelu = P("sm.concat_block.1.weight")
         w.mask_prelu, w.mask_w, w.mask_b = P("mask_net.0.weight"), P("mask_net.1.weight"), P("mask_net.1.bias")
         w.dec_w = P("decoder.weight")
-        self._keep = keep
+        self._keep = (self._keep or []) + keep if optional else keep
         return w
 
     # ------------------------------------------------------------------ workspace
