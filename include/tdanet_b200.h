@@ -36,7 +36,7 @@ extern "C" {
 #define TDANET_API
 #endif
 
-#define TDANET_ABI_VERSION 1
+#define TDANET_ABI_VERSION 2
 #define TDANET_MAX_DEPTH 8
 #define TDANET_MAX_ENC 4
 
@@ -169,6 +169,38 @@ TDANET_API int tdanet_workspace_tensor(const tdanet_config_t* cfg, int batch, in
 /* latent lengths L[0..depth-1] for n_samples input samples, and padded length / rest */
 TDANET_API int tdanet_latent_lengths(const tdanet_config_t* cfg, int n_samples, int32_t* lengths,
                           int32_t* padded_len, int32_t* rest);
+
+/* ------------------------------------------------------------------ training step (TDANetBest)
+ * Replaces the autograd graph of AudioLightningModule.training_step (system/audio_litmodule.py:83-124) and
+ * the Trainer's clip + optimiser (audio_train.py:71,187-197; configs/tdanet_lsr2.yml:42-45) for the model
+ * path: forward keeping every GlobLN-delimited tensor of every UConvBlock iteration, hand-written backward,
+ * global-norm clipping and Adam on flat buffers.  Dropout / DropPath are not applied (p = 0).
+ *
+ * tdanet_forward_train   same result as tdanet_forward; `workspace` (tdanet_train_workspace_bytes) then holds
+ *                        what tdanet_backward needs and must stay untouched until it has run.
+ * tdanet_backward        d_est [B, n_src, T] = d loss / d est.  `grads` has the layout of tdanet_weights_t and
+ *                        points at the gradient buffer of every parameter (pe: NULL); gradients are ADDED to
+ *                        those buffers (zero them first; the 16 iterations of the shared block accumulate).
+ *                        Parameters the forward never reads (loc_glo_fus of the last scale) are left alone. */
+TDANET_API int tdanet_train_workspace_bytes(const tdanet_config_t* cfg, int batch, int n_samples, size_t* bytes);
+TDANET_API int tdanet_forward_train(const tdanet_config_t* cfg, const tdanet_weights_t* w, const float* wav,
+                   int batch, int n_samples, float* est, void* workspace, size_t workspace_bytes,
+                   tdanet_stream_t stream);
+TDANET_API int tdanet_backward(const tdanet_config_t* cfg, const tdanet_weights_t* w, const tdanet_weights_t* grads,
+                   const float* wav, const float* d_est, int batch, int n_samples, void* workspace,
+                   size_t workspace_bytes, tdanet_stream_t stream);
+/* Locate a tensor of UConvBlock iteration `block` in the training workspace (tests).  Names of
+ * tdanet_workspace_tensor plus "bin" "y" "fused0".. "mlogit" and the statistics "st_*" (elem_bytes = 8). */
+TDANET_API int tdanet_train_workspace_tensor(const tdanet_config_t* cfg, int batch, int n_samples, const char* name,
+                   int block, size_t* byte_offset, int64_t dims[3], int32_t* elem_bytes);
+/* sqnorm[0] = sum of squares of grads[0..n) (double, device; sqnorm has 2 elements). */
+TDANET_API int tdanet_grad_sqnorm(const float* grads, size_t n, double* sqnorm, tdanet_stream_t stream);
+/* clip_grad_norm_(max_grad_norm) (skipped if <= 0) then one torch.optim.Adam step (no weight decay, no amsgrad)
+ * on flat buffers; gradients are first multiplied by grad_scale (1/world_size after a sum all-reduce).
+ * `step` is a device counter of the steps taken so far; it is incremented. */
+TDANET_API int tdanet_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                   float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale,
+                   const double* sqnorm, int32_t* step, tdanet_stream_t stream);
 
 /* ------------------------------------------------------------------ standalone ops
  * D[b, r, :N] = A[b, r, :K] . W[:N, :K]^T (+ bias), rows r < rows_per_item of each of `batch`

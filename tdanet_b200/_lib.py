@@ -85,6 +85,16 @@ _SIGNATURES = {
                                           C.POINTER(C.c_size_t), C.POINTER(C.c_int64 * 3)]),
     "tdanet_latent_lengths": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(C.c_int32 * MAX_DEPTH),
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "tdanet_train_workspace_bytes": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "tdanet_forward_train": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), fptr, C.c_int, C.c_int, fptr, fptr,
+                                       C.c_size_t, fptr]),
+    "tdanet_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Weights), fptr, fptr, C.c_int,
+                                  C.c_int, fptr, C.c_size_t, fptr]),
+    "tdanet_train_workspace_tensor": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                                C.POINTER(C.c_size_t), C.POINTER(C.c_int64 * 3), C.POINTER(C.c_int32)]),
+    "tdanet_grad_sqnorm": (C.c_int, [fptr, C.c_size_t, fptr, fptr]),
+    "tdanet_adam_step": (C.c_int, [fptr, fptr, fptr, fptr, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.c_float, C.c_float, fptr, fptr, fptr]),
     "tdanet_gemm": (C.c_int, [C.c_int, fptr, fptr, fptr, fptr, C.c_int, C.c_int, C.c_int, C.c_int, fptr, fptr,
                               C.c_size_t, fptr]),
     "tdanet_gemm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

@@ -22,23 +22,6 @@
 
 namespace td {
 
-// Adds (a, b) to dst[0], dst[1]: one atomic pair per CTA.  Every thread of the CTA must call it.
-__device__ __forceinline__ void block_accum2(double* dst, double a, double b) {
-#ifdef TD_EMU
-  if (!emu::bs) {  // sequential emulation: no block to reduce over
-    atomicAdd(dst, a);
-    atomicAdd(dst + 1, b);
-    return;
-  }
-#endif
-  __shared__ double sh[64];
-  block_sum2(a, b, sh);
-  if (threadIdx.x == 0) {
-    atomicAdd(dst, a);
-    atomicAdd(dst + 1, b);
-  }
-}
-
 // ----------------------------------------------------------------------------- gradient sources
 enum GradKind {
   G_PLAIN = 0,  // dy

@@ -314,6 +314,23 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* sh) {
   for (int i = 0; i < nw; ++i) { a += sh[i]; b += sh[32 + i]; }
 }
 
+// Adds (a, b) to dst[0], dst[1]: one atomic pair per CTA.  Every thread of the CTA must call it.
+__device__ __forceinline__ void block_accum2(double* dst, double a, double b) {
+#ifdef TD_EMU
+  if (!emu::bs) {  // sequential emulation: no block to reduce over
+    atomicAdd(dst, a);
+    atomicAdd(dst + 1, b);
+    return;
+  }
+#endif
+  __shared__ double sh[64];
+  block_sum2(a, b, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(dst, a);
+    atomicAdd(dst + 1, b);
+  }
+}
+
 // A GlobLN (TDANet_best.py:47-64) whose per-item statistics a producer kernel has accumulated:
 // stats[b*item_stride + {0,1}] = sum, sum of squares (double) over `count` elements of item b.
 // Consumers fold the normalisation into one FMA per element: y = x*scale_c + shift_c with

@@ -122,7 +122,6 @@ static inline int check_train_config(const tdanet_config_t* c) {
     return fail(TDANET_EUNSUPPORTED, "training step: only TDANetBest (variant 0) has a backward pass in this build (got %d)", c->variant);
   if (c->act_dtype != TDANET_ACT_F32)
     return fail(TDANET_EUNSUPPORTED, "training step: activations are kept in fp32 (act_dtype fp32)");
-  TD_REQUIRE(c->gemm_mode != TDANET_GEMM_TF32X3, "training step: gemm_mode fp32 or tf32");
   return 0;
 }
 

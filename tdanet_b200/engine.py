@@ -44,6 +44,7 @@ class SeparationEngine:
             n_basis=n_basis, num_sources=num_sources, enc_convs=enc_convs, n_head=n_head,
             gemm_mode=_lib.GEMM_MODES[gemm_mode], attn_group=0, act_dtype=_lib.ACT_DTYPES[act_dtype])
         self._ws: Dict[torch.device, torch.Tensor] = {}
+        self._tws: Dict[torch.device, torch.Tensor] = {}   # training workspace (activations of every block)
         self._graphs: Dict[Tuple, Tuple] = {}
         self._keep = None  # tensors referenced by the packed weight struct
 
@@ -188,6 +189,72 @@ class SeparationEngine:
                                      ws.data_ptr(), ws.numel(), stream))
         return out
 
+    # ------------------------------------------------------------------ training: forward keeping activations, backward
+    def train_workspace_bytes(self, batch: int, n_samples: int) -> int:
+        n = C.c_size_t()
+        check(_lib.load().tdanet_train_workspace_bytes(C.byref(self.cfg), batch, n_samples, C.byref(n)))
+        return n.value
+
+    def _train_workspace(self, device, nbytes: int) -> torch.Tensor:
+        ws = self._tws.get(device)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._tws[device] = ws
+        return ws
+
+    def train_workspace_tensor(self, name: str, block: int, batch: int, n_samples: int, device) -> torch.Tensor:
+        """View of a tensor kept by forward_train for UConvBlock iteration `block` (tests)."""
+        off, dims, es = C.c_size_t(), (C.c_int64 * 3)(), C.c_int32()
+        check(_lib.load().tdanet_train_workspace_tensor(C.byref(self.cfg), batch, n_samples, name.encode(), block,
+                                                        C.byref(off), C.byref(dims), C.byref(es)))
+        ws = self._tws[torch.device(device)]
+        n = dims[0] * dims[1] * dims[2]
+        dt = torch.float32 if es.value == 4 else torch.float64
+        return ws[off.value: off.value + es.value * n].view(dt).view(dims[0], dims[1], dims[2])
+
+    def _check_wav(self, wav):
+        if not wav.is_cuda:
+            raise _lib.TdanetError("tdanet_b200 runs on CUDA tensors only (no CPU path); got a CPU tensor")
+        if wav.dtype != torch.float32 or wav.ndim != 2:
+            raise _lib.TdanetError(f"wav must be fp32 [B, T], got {wav.dtype} {tuple(wav.shape)}")
+
+    def forward_train(self, weights: Weights, wav: torch.Tensor, attn_group: int = 0,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Like forward(), but every block's activations stay in the training workspace for backward()."""
+        self._check_wav(wav)
+        wav = wav.contiguous()
+        B, T = wav.shape
+        lib = _lib.load()
+        with torch.cuda.device(wav.device):
+            ws = self._train_workspace(wav.device, self.train_workspace_bytes(B, T))
+            if out is None:
+                out = torch.empty(B, self.cfg.num_sources, T, dtype=torch.float32, device=wav.device)
+            self.cfg.attn_group = attn_group
+            stream = torch.cuda.current_stream(wav.device).cuda_stream
+            check(lib.tdanet_forward_train(C.byref(self.cfg), C.byref(weights), wav.data_ptr(), B, T, out.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def backward(self, weights: Weights, grad_weights: Weights, wav: torch.Tensor, d_est: torch.Tensor,
+                 attn_group: int = 0) -> None:
+        """Adds d loss / d theta into the buffers `grad_weights` points at, from d_est = d loss / d est and the
+        workspace the matching forward_train() call left behind."""
+        self._check_wav(wav)
+        B, T = wav.shape
+        if d_est.shape != (B, self.cfg.num_sources, T) or d_est.dtype != torch.float32 or not d_est.is_cuda:
+            raise _lib.TdanetError(f"d_est must be fp32 CUDA [B, n_src, T], got {d_est.dtype} {tuple(d_est.shape)}")
+        d_est = d_est.contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(wav.device):
+            ws = self._tws.get(wav.device)
+            need = self.train_workspace_bytes(B, T)
+            if ws is None or ws.numel() < need:
+                raise _lib.TdanetError("backward() without a matching forward_train() on this device")
+            self.cfg.attn_group = attn_group
+            stream = torch.cuda.current_stream(wav.device).cuda_stream
+            check(lib.tdanet_backward(C.byref(self.cfg), C.byref(weights), C.byref(grad_weights), wav.data_ptr(),
+                                      d_est.data_ptr(), B, T, ws.data_ptr(), ws.numel(), stream))
+
     def forward_graphed(self, weights: Weights, wav: torch.Tensor, attn_group: int = 0) -> torch.Tensor:
         """Same as forward() but replays one captured CUDA graph per (B, T, group, weights) key.
 
@@ -259,3 +326,26 @@ def pit_loss(est: torch.Tensor, tgt: torch.Tensor, sdr_type: str = "snr", thresh
                                   None if grad is None else grad.data_ptr(), scratch.data_ptr(), ns,
                                   torch.cuda.current_stream(dev).cuda_stream))
     return loss, pw, perm, grad
+
+
+def grad_sqnorm(flat_grads: torch.Tensor, out: torch.Tensor) -> None:
+    """out[0] = sum of squares of a flat fp32 gradient buffer (out: float64[2], CUDA)."""
+    lib = _lib.load()
+    with torch.cuda.device(flat_grads.device):
+        check(lib.tdanet_grad_sqnorm(flat_grads.data_ptr(), flat_grads.numel(), out.data_ptr(),
+                                     torch.cuda.current_stream(flat_grads.device).cuda_stream))
+
+
+def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+              step: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: float = 0.0,
+              grad_scale: float = 1.0, sqnorm: Optional[torch.Tensor] = None) -> None:
+    """clip_grad_norm_(max_grad_norm) + torch.optim.Adam step on flat fp32 CUDA buffers (csrc/optim.cu)."""
+    lib = _lib.load()
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == params.numel()):
+            raise _lib.TdanetError("adam_step needs flat contiguous fp32 CUDA buffers of equal length")
+    with torch.cuda.device(params.device):
+        check(lib.tdanet_adam_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                   params.numel(), lr, betas[0], betas[1], eps, max_grad_norm, grad_scale,
+                                   None if sqnorm is None else sqnorm.data_ptr(), step.data_ptr(),
+                                   torch.cuda.current_stream(params.device).cuda_stream))

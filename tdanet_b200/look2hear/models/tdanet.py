@@ -16,6 +16,35 @@ from . import _params as P
 from .base_model import BaseModel
 
 
+class _SeparateFn(torch.autograd.Function):
+    """model(mix) with gradients: tdanet_forward_train / tdanet_backward behind torch.autograd, so that the
+    reference's `loss.backward()` keeps working.  (The fused step in look2hear.system.TrainingStep skips
+    autograd altogether.)"""
+
+    @staticmethod
+    def forward(ctx, model, wav, names, *params):
+        ctx.model, ctx.names = model, names
+        ctx.save_for_backward(wav, *params)
+        return model._engine.forward_train(model._weights(), wav, model.attn_group)
+
+    @staticmethod
+    def backward(ctx, d_est):
+        model, names = ctx.model, ctx.names
+        wav, *params = ctx.saved_tensors
+        # gradients land in one zeroed flat buffer; parameters the forward never reads get None, like autograd
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=wav.device)
+        views, off = {}, 0
+        for n, p, s in zip(names, params, sizes):
+            views[n] = flat[off:off + p.numel()].view(p.shape)
+            off += s
+        gw = model._engine.pack(views, optional=True)
+        model._engine.backward(model._weights(), gw, wav, d_est.contiguous().float(), model.attn_group)
+        dead = model._unused_parameter_names()
+        grads = tuple(None if (n in dead or not p.requires_grad) else views[n] for n, p in zip(names, params))
+        return (None, None, None) + grads
+
+
 class _TDANetCommon(BaseModel):
     _variant = None
 
@@ -106,18 +135,35 @@ class _TDANetCommon(BaseModel):
         if not input_wav.is_cuda:
             raise _lib.TdanetError(
                 f"{type(self).__name__} (tdanet_b200) runs on CUDA tensors only; there is no CPU fallback")
-        if torch.is_grad_enabled() and (input_wav.requires_grad or any(p.requires_grad for p in self.parameters())) \
-                and self.training:
-            raise NotImplementedError(
-                "training-mode forward (autograd through the CUDA path) is not part of this build yet; "
-                "call .eval() / torch.no_grad() for separation")
         wav = input_wav.float().contiguous()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # gradients w.r.t. the parameters through the hand-written backward pass (TDANetBest; dropout and
+            # DropPath are not applied).  There is no gradient w.r.t. the waveform.
+            if self._variant == "best":
+                named = [(n, p) for n, p in self.named_parameters()]
+                est = _SeparateFn.apply(self, wav, tuple(n for n, _ in named), *[p for _, p in named])
+                return est.squeeze(0) if was_one_d else est
+            if self.training:
+                raise NotImplementedError(
+                    f"{type(self).__name__}: only TDANetBest has a backward pass in this build; "
+                    "call .eval() under torch.no_grad() for separation")
         w = self._weights()
         if self.use_cuda_graph:
             est = self._engine.forward_graphed(w, wav, self.attn_group).clone()
         else:
             est = self._engine.forward(w, wav, self.attn_group)
         return est.squeeze(0) if was_one_d else est
+
+    def _unused_parameter_names(self):
+        """Parameters no forward reads (their reference gradient is None): loc_glo_fus of the last scale unless
+        it is the first top-down step's partner (depth 2), concat_block when there is a single block."""
+        d = self.upsampling_depth
+        dead = set()
+        if self._variant == "best" and (d - 3 + d) % d != d - 1:
+            dead |= {n for n, _ in self.named_parameters() if f"loc_glo_fus.{d - 1}." in n}
+        if self.num_blocks == 1:
+            dead |= {n for n, _ in self.named_parameters() if "concat_block" in n}
+        return dead
 
     def get_model_args(self):
         return {"n_src": 2}

@@ -1,7 +1,10 @@
 """look2hear.system mirror for the hot path: the sharded separation runner (inference over a batch
-split across ranks) and the long-form chunk / separate / stitch runner (audio_test_css.py).  The training step (`AudioLightningModule.training_step`,
-audio_litmodule.py:83-124) needs the backward kernels and is not part of this build yet."""
+split across ranks), the long-form chunk / separate / stitch runner (audio_test_css.py) and the training
+step (`AudioLightningModule.training_step`, audio_litmodule.py:83-124, plus the Trainer's backward /
+gradient mean / clip / Adam) on the CUDA forward and backward kernels."""
 from .longform import css_segments, separate_long
 from .sharding import shard_bounds, separate_sharded
+from .training import AudioLightningModule, FlatParameters, TrainingStep
 
-__all__ = ["shard_bounds", "separate_sharded", "css_segments", "separate_long"]
+__all__ = ["shard_bounds", "separate_sharded", "css_segments", "separate_long", "AudioLightningModule",
+           "FlatParameters", "TrainingStep"]
