@@ -129,6 +129,124 @@ def algorithmic_bytes(variant, lengths, B, C=512, c=128):
     return {k: v * B * 16 for k, v in blk.items()}
 
 
+# ----------------------------------------------------------------------------- training step
+TRAIN_BATCH = 8   # per GPU (BASELINE.json configs[3])
+
+
+def train_targets(rank, B, seed=4321):
+    tgt = torch.randn(B, 2, N_SAMPLES, generator=torch.Generator().manual_seed(seed + rank)) * 0.1
+    return tgt.sum(1), tgt
+
+
+def run_train_leg(args, dev, rank, world, local, barrier):
+    """BASELINE.json configs[3]: full training step (forward, PIT SI-SDR loss, backward, gradient all-reduce,
+    clip 5.0, Adam) of the 4 ms / 16-block TDANetBest at batch 8 per GPU.  Returns the "train" object of the
+    JSON line (rank 0) or None."""
+    import torch.distributed as dist
+    import tdanet_b200.look2hear as look2hear
+    from tdanet_b200 import _lib
+    B, W, K = TRAIN_BATCH, max(3, args.warmup), args.steps
+    torch.manual_seed(0)
+    model = look2hear.models.TDANetBest(sample_rate=SR, **model_kwargs(args.enc_ms)).to(dev).train()
+    model.gemm_mode = args.gemm_mode
+    L = look2hear.losses
+    ts = look2hear.system.TrainingStep(model, L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True),
+                                       lr=1e-3, clip_grad_norm=5.0)
+    mix_h, tgt_h = train_targets(rank, B)
+    mix_h, tgt_h = mix_h.pin_memory(), tgt_h.pin_memory()
+    mix, tgt = mix_h.to(dev), tgt_h.to(dev)
+    step = ts.step if args.no_graph else ts.step_captured
+    n0 = _lib.launch_count()
+    ts.step(mix, tgt)
+    launches = _lib.launch_count() - n0
+    for _ in range(W):
+        step(mix, tgt)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            loss = step(mix, tgt)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    # end to end: this step's mixtures and targets come from pinned host memory, the loss goes back to the host
+    loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
+    min_d, tgt_d = torch.empty_like(mix), torch.empty_like(tgt)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        min_d.copy_(mix_h, non_blocking=True)
+        tgt_d.copy_(tgt_h, non_blocking=True)
+        loss_h.copy_(step(min_d, tgt_d).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    final_loss = float(loss_h.item())
+    prof = None
+    if rank == 0:
+        _lib.profile_enable(True)
+        ts.params.zero_grad()
+        ts.forward_backward(mix, tgt)
+        prof = _lib.profile_dump()
+        _lib.profile_enable(False)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return None
+    kernels = [{"kernel": p["kernel"], "launches_per_step": p["launches"], "ms_per_step": round(p["ms"], 4)}
+               for p in sorted(prof, key=lambda r: -r["ms"])]
+    out = {
+        "metric": "train_steps_per_second", "value": K / (ms / 1e3), "unit": "steps/s", "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "n_gpus": world,
+        "config": {"workload": f"TDANetBest {args.enc_ms} ms encoder, 16 blocks, full training step (forward, PIT SI-SDR, "
+                               f"backward, gradient all-reduce, clip 5.0, Adam), batch {B} x 2 s per GPU "
+                               "(BASELINE.json configs[3]), dropout/DropPath off",
+                   "batch_per_gpu": B, "global_batch": B * world, "gemm_mode": args.gemm_mode,
+                   "cuda_graph": not args.no_graph},
+        "samples_per_second": world * B * K / (ms / 1e3),
+        "e2e": {"value": K / (ms_e2e / 1e3), "unit": "steps/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": B * 3 * N_SAMPLES * 4, "d2h_bytes_per_step": 4},
+        "gpu_launches_per_step": launches, "loss_after": final_loss, "clocks": clk.summary(),
+        "profiled_ms_per_step": round(sum(k["ms_per_step"] for k in kernels), 3),
+        "kernels": kernels[:16],
+    }
+    if world == 1 and not args.skip_cpu:
+        out["cpu_baseline"] = cpu_train_baseline(args)
+    return out
+
+
+def cpu_train_baseline(args):
+    """Oracle port + autograd + torch clip/Adam on this box's host cores: one step at batch 2, scaled to batch 8."""
+    from oracle import tdanet_oracle as O
+    import tdanet_b200.look2hear.models as M
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = model_kwargs(args.enc_ms)
+    torch.manual_seed(0)
+    model = M.TDANetBest(sample_rate=SR, **kw)
+    sd = {k: (torch.nn.Parameter(v.detach().clone()) if "pos_enc.pe" not in k else v) for k, v in model.state_dict().items()}
+    params = [v for k, v in sd.items() if "pos_enc.pe" not in k]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    cfg = O.OracleConfig(variant="best", sample_rate=SR, **kw)
+    bs = 2
+    mix, tgt = train_targets(0, bs)
+    t0 = time.perf_counter()
+    opt.zero_grad()
+    loss = O.pit_loss(O.forward(sd, mix.unsqueeze(1), cfg), tgt, "sisdr", True)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 5.0)
+    opt.step()
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / (dt * TRAIN_BATCH / bs), "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": f"one full step at batch {bs} (fp32 eager + autograd, {cores} threads) took {dt:.2f} s; "
+                      f"scaled by {TRAIN_BATCH // bs} to the batch-{TRAIN_BATCH} step"}
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference algorithm (oracle port of the PyTorch modules, fp32 eager) on the host cores."""
@@ -197,6 +315,13 @@ def run_ours(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
+    if args.train_only:
+        train = run_train_leg(args, dev, rank, world, local, barrier)
+        if rank == 0:
+            print(json.dumps(train))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     B, W, K = args.batch, max(3, args.warmup), args.steps
     kw = model_kwargs(args.enc_ms)
     torch.manual_seed(0)
@@ -262,6 +387,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)   # max over ranks
     ms, ms_e2e = t.tolist()
+    train = None
+    if not args.skip_train and args.variant == "best":
+        del x_dev, xin
+        model._engine._ws.clear()
+        model._engine._graphs.clear()
+        torch.cuda.empty_cache()
+        train = run_train_leg(args, dev, rank, world, local, barrier)
     audio_s = world * B * (N_SAMPLES / SR) * K
     value = audio_s / (ms / 1e3)
     e2e = audio_s / (ms_e2e / 1e3)
@@ -314,6 +446,8 @@ def run_ours(args):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if train is not None:
+            out["train"] = train
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -356,7 +490,9 @@ def main():
     ap.add_argument("--act-dtype", default="fp32", choices=["fp32", "bf16"],
                     help="storage of the large activations (bf16 = the bf16-mode tolerance of BASELINE.json)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
-    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--train-only", action="store_true", help="print the training-step leg as the JSON line (profiling aid)")
+    ap.add_argument("--skip-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[3])")
     ap.add_argument("--ref-batch", type=int, default=8, help="upper bound of mixtures per step for --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -70,12 +70,19 @@ static inline void row_grid(int L, int C4, int B, int rows, dim3& grid, int& thr
   threads = C4 > 256 ? 256 : (C4 < 32 ? 32 : C4);
   grid = dim3(cdiv(L, rows), cdiv(C4, threads), B);
 }
+// rows per thread (a multiple of the 4-row tile): as many as `max_rows`, but keep at least two CTAs per SM
+static inline int pick_rows(int L, int C4, int B, int max_rows) {
+  const int threads = C4 > 256 ? 256 : (C4 < 32 ? 32 : C4);
+  int rows = max_rows;
+  while (rows > 4 && (long)cdiv(L, rows) * cdiv(C4, threads) * B < 2 * 148) rows >>= 1;
+  return rows;
+}
 
 static int launch_gln_bwd_stats(const float* dy, const float* x, const NormRef& norm, float* dgamma, float* dbeta,
                                 double* S, int B, int L, int C, cudaStream_t st) {
   dim3 grid;
   int threads;
-  const int rows = 32;
+  const int rows = pick_rows(L, C % 4 == 0 ? C / 4 : C, B, 32);
   if (C % 4 == 0) {
     row_grid(L, C / 4, B, rows, grid, threads);
     TD_LAUNCH_RED((gln_bwd_stats_kernel<4>), grid, threads, 0, st, dy, x, norm, dgamma, dbeta, S, L, C, rows);
@@ -89,7 +96,7 @@ static int launch_gln_bwd_stats(const float* dy, const float* x, const NormRef& 
 static int launch_gln_bwd_apply(const GradSrc& g, float* out, int accumulate, int B, int L, int C, cudaStream_t st) {
   dim3 grid;
   int threads;
-  const int rows = 16;
+  const int rows = pick_rows(L, C % 4 == 0 ? C / 4 : C, B, 16);
   if (C % 4 == 0) {
     row_grid(L, C / 4, B, rows, grid, threads);
     TD_LAUNCH((gln_bwd_apply_kernel<4>), grid, threads, 0, st, g, out, accumulate, L, C, rows);
@@ -105,36 +112,44 @@ static int launch_dw_bwd(DwBwdArgs& a, int ks, int nw, cudaStream_t st) {
   TD_REQUIRE(a.stride == 1 || a.stride == 2, "dw_bwd: stride %d", a.stride);
   TD_REQUIRE(a.xkind == SRC_PLAIN || a.xkind == SRC_AFFINE || a.xkind == SRC_AFFINE_PRELU, "dw_bwd: source kind %d", a.xkind);
   TD_REQUIRE(a.xin.L == a.Lin, "dw_bwd: input length %d != %d", a.xin.L, a.Lin);
-  a.rows_per_thread = 32;
+  a.rows_per_thread = pick_rows(a.Lout, a.C / 4, a.B, 32);
   dim3 grid;
   int threads;
   row_grid(a.Lout, a.C / 4, a.B, a.rows_per_thread, grid, threads);
-  if (ks == 5 && nw == 1) TD_LAUNCH_RED((dw_bwd_kernel<5, 1>), grid, threads, 0, st, a);
-  else if (ks == 5 && nw == 2) TD_LAUNCH_RED((dw_bwd_kernel<5, 2>), grid, threads, 0, st, a);
-  else if (ks == 1 && nw == 1) TD_LAUNCH_RED((dw_bwd_kernel<1, 1>), grid, threads, 0, st, a);
-  else if (ks == 1 && nw == 2) TD_LAUNCH_RED((dw_bwd_kernel<1, 2>), grid, threads, 0, st, a);
+  const int key = ks * 100 + nw * 10 + a.stride;
+  if (key == 511) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1>), grid, threads, 0, st, a);
+  else if (key == 512) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 2>), grid, threads, 0, st, a);
+  else if (key == 521) TD_LAUNCH_RED((dw_bwd_kernel<5, 2, 1>), grid, threads, 0, st, a);
+  else if (key == 111) TD_LAUNCH_RED((dw_bwd_kernel<1, 1, 1>), grid, threads, 0, st, a);
+  else if (key == 121) TD_LAUNCH_RED((dw_bwd_kernel<1, 2, 1>), grid, threads, 0, st, a);
   else return fail(TDANET_EINVAL, "dw_bwd: ks=%d nw=%d", ks, nw);
   return 0;
 }
 
 static int launch_la_bwd_a(LaBwdArgs& a, int ks, cudaStream_t st) {
   TD_REQUIRE(a.C % 4 == 0, "la_bwd: C=%d", a.C);
-  // about 32 local rows per thread
-  int jc = (int)(32.0 * a.Lg / a.loc.L + 0.5);
-  a.jchunk = jc < 1 ? 1 : jc;
+  TD_REQUIRE(ks == 5 || ks == 1, "la_bwd: ks=%d", ks);
   dim3 grid;
   int threads;
-  row_grid(a.Lg, a.C / 4, a.B, a.jchunk, grid, threads);
-  if (ks == 5) TD_LAUNCH_RED((la_bwd_a_kernel<5>), grid, threads, 0, st, a);
-  else if (ks == 1) TD_LAUNCH_RED((la_bwd_a_kernel<1>), grid, threads, 0, st, a);
-  else return fail(TDANET_EINVAL, "la_bwd: ks=%d", ks);
+  const int grows = pick_rows(a.Lg, a.C / 4, a.B, 16);  // global rows per thread of the G and F passes
+  row_grid(a.Lg, a.C / 4, a.B, grows, grid, threads);
+  if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5>), grid, threads, 0, st, a, grows);
+  else TD_LAUNCH((la_bwd_g_kernel<1>), grid, threads, 0, st, a, grows);
+  // L pass: chunks of centres covering about 32 local rows per thread
+  int jc = (int)((double)pick_rows(a.loc.L, a.C / 4, a.B, 32) * a.Lg / a.loc.L + 0.5);
+  a.jchunk = jc < 1 ? 1 : jc;
+  dim3 lgrid;
+  row_grid(a.Lg, a.C / 4, a.B, a.jchunk, lgrid, threads);
+  if (ks == 5) TD_LAUNCH_RED((la_bwd_l_kernel<5>), lgrid, threads, 0, st, a);
+  else TD_LAUNCH_RED((la_bwd_l_kernel<1>), lgrid, threads, 0, st, a);
+  TD_LAUNCH_RED(la_bwd_f_kernel, grid, threads, 0, st, a, grows);
   return 0;
 }
 
 static int launch_pool_bwd(const float* g, float* dx, int accumulate, int B, int L, int Lb, int C, cudaStream_t st) {
   dim3 grid;
   int threads;
-  const int rows = 16;
+  const int rows = pick_rows(L, C / 4, B, 16);
   row_grid(L, C / 4, B, rows, grid, threads);
   TD_LAUNCH(pool_bwd_kernel, grid, threads, 0, st, g, dx, accumulate, L, Lb, C, rows);
   return 0;
@@ -145,7 +160,7 @@ static int launch_ln_bwd(const float* xin, float k1, const float* w, const float
                          float* out, float* dw, float* db, int rows, int C, cudaStream_t st) {
   TD_REQUIRE(C % 4 == 0, "ln_bwd: C=%d", C);
   TD_LAUNCH_COOP(ln_bwd_rows_kernel, cdiv(rows, 8), 256, 0, st, xin, k1, w, dy, rowstat, rows, C);
-  const int rpt = 16;
+  const int rpt = pick_rows(rows, C / 4, 1, 16);
   const int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
   dim3 grid(cdiv(rows, rpt), cdiv(C / 4, threads));
   TD_LAUNCH(ln_bwd_apply_kernel, grid, threads, 0, st, xin, k1, w, dy, rowstat, add, k1, out, dw, db, rows, C, rpt);

@@ -47,7 +47,7 @@ struct GradLoad {
   __device__ __forceinline__ void init(const GradSrc& g, int b, int ch, size_t item_elems) {
     kind = g.kind;
     dy = g.dy + (size_t)b * item_elems + ch;
-    x = g.x ? g.x + (size_t)b * item_elems + ch : nullptr;
+    x = (g.x ? g.x : g.dy) + (size_t)b * item_elems + ch;  // always loadable: loads are issued unconditionally
     r = 1.f; mur = 0.f; k1 = 0.f; k2 = 0.f;
     gr = vzero<V>();
     if (kind == G_GLN) {
@@ -60,22 +60,27 @@ struct GradLoad {
       k2 = (float)((double)r * g.S[2 * b + 1] * inv);
     }
   }
-  // off: row * C
+  // off: row * C.  Branch-free (selects on the uniform `kind`) so that callers can issue many loads back to back.
   __device__ __forceinline__ vf<V> load(size_t off) const {
     vf<V> d = vload<V>(dy + off);
-    if (kind == G_PLAIN) return d;
     const vf<V> xv = vload<V>(x + off);
-    if (kind == G_RELU) {
-#pragma unroll
-      for (int e = 0; e < V; ++e) d[e] = xv[e] > 0.f ? d[e] : 0.f;
-      return d;
-    }
 #pragma unroll
     for (int e = 0; e < V; ++e) {
       const float xh = fmaf(xv[e], r, -mur);
-      d[e] = fmaf(gr[e], d[e], -k1) - xh * k2;
+      const float gln = fmaf(gr[e], d[e], -k1) - xh * k2;
+      const float relu = xv[e] > 0.f ? d[e] : 0.f;
+      d[e] = kind == G_GLN ? gln : (kind == G_RELU ? relu : d[e]);
     }
     return d;
+  }
+  // row clamped into [0, L): the load is always issued; rows outside the tensor read as zero
+  __device__ __forceinline__ vf<V> load_row(int row, int L, int C) const {
+    const int rc = row < 0 ? 0 : (row >= L ? L - 1 : row);
+    vf<V> v = load((size_t)rc * C);
+    const bool ok = row == rc;
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = ok ? v[e] : 0.f;
+    return v;
   }
 };
 
@@ -90,24 +95,37 @@ struct FwdLoad {
     kind = kind_;
     x = s.x + (size_t)b * s.L * C + ch;
     slope = 1.f;
+#pragma unroll
+    for (int e = 0; e < V; ++e) { sc[e] = 1.f; sh[e] = 0.f; }
     if (kind != SRC_PLAIN) norm_coef<V>(s.norm, b, ch, sc, sh);
     if (kind == SRC_AFFINE_PRELU) slope = __ldg(s.slope);
   }
-  // pre-activation value (GlobLN output; the raw value for PLAIN)
+  // pre-activation value (GlobLN output; the raw value for PLAIN: sc = 1, sh = 0)
   __device__ __forceinline__ vf<V> pre(size_t off) const {
     vf<V> v = vload<V>(x + off);
-    if (kind != SRC_PLAIN) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
-    }
+    for (int e = 0; e < V; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
+    return v;
+  }
+  // rows outside [0, L) read as zero (the conv pads its input, i.e. the value after the transform)
+  __device__ __forceinline__ vf<V> pre_row(int row, int L, int C) const {
+    const int rc = row < 0 ? 0 : (row >= L ? L - 1 : row);
+    vf<V> v = pre((size_t)rc * C);
+    const bool ok = row == rc;
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = ok ? v[e] : 0.f;
+    return v;
+  }
+  __device__ __forceinline__ vf<V> load_row(int row, int L, int C) const {
+    vf<V> v = pre_row(row, L, C);
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = preluf_(v[e], slope);  // slope = 1 unless AFFINE_PRELU
     return v;
   }
   __device__ __forceinline__ vf<V> load(size_t off) const {
     vf<V> v = pre(off);
-    if (kind == SRC_AFFINE_PRELU) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) v[e] = preluf_(v[e], slope);
-    }
+    for (int e = 0; e < V; ++e) v[e] = preluf_(v[e], slope);
     return v;
   }
 };
@@ -129,17 +147,27 @@ __global__ void gln_bwd_stats_kernel(const float* __restrict__ dy, const float* 
     const vf<V> gam = vload<V>(norm.gamma + ch);
     vf<V> dg = vzero<V>(), db = vzero<V>();
     float a1 = 0.f, a2 = 0.f;
-    for (int t = t0; t < t1; ++t) {
-      const size_t off = ((size_t)b * L + t) * C + ch;
-      const vf<V> d = vload<V>(dy + off), xv = vload<V>(x + off);
+    for (int t = t0; t < t1; t += 4) {
+      vf<V> d[4], xv[4];
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const float xh = fmaf(xv[e], r, -mur);
-        dg[e] = fmaf(d[e], xh, dg[e]);
-        db[e] += d[e];
-        const float gd = gam[e] * d[e];
-        a1 += gd;
-        a2 = fmaf(gd, xh, a2);
+      for (int i = 0; i < 4; ++i) {  // unconditional, clamped; rows past t1 contribute zero
+        const size_t off = ((size_t)b * L + (t + i < L ? t + i : L - 1)) * C + ch;
+        d[i] = vload<V>(dy + off);
+        xv[i] = vload<V>(x + off);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = t + i < t1;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float dv = ok ? d[i][e] : 0.f;
+          const float xh = fmaf(xv[i][e], r, -mur);
+          dg[e] = fmaf(dv, xh, dg[e]);
+          db[e] += dv;
+          const float gd = gam[e] * dv;
+          a1 += gd;
+          a2 = fmaf(gd, xh, a2);
+        }
       }
     }
     vred_add<V>(dgamma + ch, dg);
@@ -161,14 +189,24 @@ __global__ void gln_bwd_apply_kernel(GradSrc g, float* __restrict__ out, int acc
   GradLoad<V> gl;
   gl.init(g, b, ch, (size_t)L * C);
   float* op = out + (size_t)b * L * C + ch;
-  for (int t = t0; t < t1; ++t) {
-    vf<V> v = gl.load((size_t)t * C);
-    if (accumulate) {
-      const vf<V> o = vload_rw<V>(op + (size_t)t * C);
+  for (int t = t0; t < t1; t += 4) {
+    vf<V> v[4], o[4];
 #pragma unroll
-      for (int e = 0; e < V; ++e) v[e] += o[e];
+    for (int i = 0; i < 4; ++i) {
+      const size_t off = (size_t)(t + i < L ? t + i : L - 1) * C;
+      v[i] = gl.load(off);
+      if (accumulate) o[i] = vload_rw<V>(op + off);
     }
-    vstore<V>(op + (size_t)t * C, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (t + i < t1) {
+        if (accumulate) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) v[i][e] += o[i][e];
+        }
+        vstore<V>(op + (size_t)(t + i) * C, v[i]);
+      }
+    }
   }
 }
 
@@ -205,65 +243,41 @@ struct DwBwdArgs {
   int rows_per_thread;
 };
 
-template <int KS, int NW>
+// Streaming form: a thread owns 4 channels and a run of output rows, walks it in tiles of R = 4 output rows and
+// keeps the gradient rows / input rows a tile needs in registers (the rows shared with the previous tile are
+// carried over), so every row is fetched once and all loads of a tile are issued back to back.
+//   stride 1: tile t..t+3 needs G[t-PAD .. t+3+PAD] and xin[t-PAD .. t+3+PAD]          (carry 2*PAD rows)
+//   stride 2: output tile t..t+3 = input rows 2t..2t+7 needs G[t-1 .. t+4], xin[2t-2 .. 2t+8]   (carry 2 / 3 rows)
+template <int KS, int NW, int STRIDE>
 __global__ void dw_bwd_kernel(DwBwdArgs a) {
-  constexpr int V = 4, PAD = (KS - 1) / 2;
+  constexpr int V = 4, PAD = (KS - 1) / 2, R = 4;
+  constexpr int GW = STRIDE == 1 ? R + 2 * PAD : R + 2;       // gradient rows held per tile
+  constexpr int XW = STRIDE == 1 ? R + 2 * PAD : 2 * R + 3;   // input rows held per tile
+  constexpr int GC = GW - R, XC = XW - R * STRIDE;            // rows carried from the previous tile
+  constexpr int G0 = STRIDE == 1 ? -PAD : -1, X0 = -PAD;      // row of slot 0 relative to the tile base (t resp. STRIDE*t)
+  static_assert(STRIDE == 1 || KS == 5, "stride 2 is implemented for k = 5");
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const bool active = ch < a.C;
   double dsl = 0.0;
   if (active) {
-    const int o0 = blockIdx.x * a.rows_per_thread, o1 = min(o0 + a.rows_per_thread, a.Lout);
-    const int i0 = o0 * a.stride, i1 = o1 == a.Lout ? a.Lin : min(o1 * a.stride, a.Lin);
+    const int C = a.C, Lin = a.Lin, Lout = a.Lout;
+    const int o0 = blockIdx.x * a.rows_per_thread, o1 = min(o0 + a.rows_per_thread, Lout);
+    const int i1 = o1 == Lout ? Lin : min(o1 * STRIDE, Lin);
     GradLoad<V> gl[NW];
     float w[NW][KS][V];
 #pragma unroll
     for (int g = 0; g < NW; ++g) {
-      gl[g].init(a.g[g], b, ch, (size_t)a.Lout * a.C);
+      gl[g].init(a.g[g], b, ch, (size_t)Lout * C);
 #pragma unroll
       for (int e = 0; e < V; ++e)
 #pragma unroll
         for (int k = 0; k < KS; ++k) w[g][k][e] = __ldg(a.w[g] + (size_t)(ch + e) * KS + k);
     }
     FwdLoad<V> fx;
-    fx.init(a.xin, a.xkind, b, ch, a.C);
-    // ---- data gradient
-    float* dxp = a.dx + (size_t)b * a.Lin * a.C + ch;
-    float sl_acc = 0.f;
-    for (int ti = i0; ti < i1; ++ti) {
-      vf<V> acc = vzero<V>();
-#pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const int num = ti + PAD - k;
-        if (num < 0 || (a.stride == 2 && (num & 1))) continue;
-        const int to = a.stride == 2 ? num >> 1 : num;
-        if (to >= a.Lout) continue;
-#pragma unroll
-        for (int g = 0; g < NW; ++g) {
-          const vf<V> gv = gl[g].load((size_t)to * a.C);
-#pragma unroll
-          for (int e = 0; e < V; ++e) acc[e] = fmaf(w[g][k][e], gv[e], acc[e]);
-        }
-      }
-      if (a.xkind == SRC_AFFINE_PRELU) {
-        const vf<V> n = fx.pre((size_t)ti * a.C);
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          if (n[e] < 0.f) {
-            sl_acc = fmaf(acc[e], n[e], sl_acc);
-            acc[e] *= fx.slope;
-          }
-        }
-      }
-      if (a.accumulate) {
-        const vf<V> o = vload_rw<V>(dxp + (size_t)ti * a.C);
-#pragma unroll
-        for (int e = 0; e < V; ++e) acc[e] += o[e];
-      }
-      vstore<V>(dxp + (size_t)ti * a.C, acc);
-    }
-    dsl = sl_acc;
-    // ---- weight / bias gradients of the output rows this thread owns
+    fx.init(a.xin, a.xkind, b, ch, C);
+    const bool prelu = a.xkind == SRC_AFFINE_PRELU;
+    float* dxp = a.dx + (size_t)b * Lin * C + ch;
     float dw[NW][KS][V], db[NW][V];
 #pragma unroll
     for (int g = 0; g < NW; ++g)
@@ -273,25 +287,95 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
 #pragma unroll
         for (int k = 0; k < KS; ++k) dw[g][k][e] = 0.f;
       }
-    for (int to = o0; to < o1; ++to) {
-      vf<V> gv[NW];
+    float sl_acc = 0.f;
+    vf<V> G[NW][GW], X[XW];  // X holds the value before the PReLU (the GlobLN output)
+    auto loadG = [&](int g, int row) { return gl[g].load_row(row, Lout, C); };
+    auto loadX = [&](int row) { return fx.pre_row(row, Lin, C); };
+    // rows carried into the first tile
 #pragma unroll
-      for (int g = 0; g < NW; ++g) {
-        gv[g] = gl[g].load((size_t)to * a.C);
+    for (int j = 0; j < GC; ++j)
 #pragma unroll
-        for (int e = 0; e < V; ++e) db[g][e] += gv[g][e];
+      for (int g = 0; g < NW; ++g) G[g][j] = loadG(g, o0 + G0 + j);
+#pragma unroll
+    for (int j = 0; j < XC; ++j) X[j] = loadX(o0 * STRIDE + X0 + j);
+    for (int t = o0; t < o1; t += R) {
+#pragma unroll
+      for (int j = GC; j < GW; ++j)
+#pragma unroll
+        for (int g = 0; g < NW; ++g) G[g][j] = loadG(g, t + G0 + j);
+#pragma unroll
+      for (int j = XC; j < XW; ++j) X[j] = loadX(t * STRIDE + X0 + j);
+      vf<V> O[R * STRIDE];  // previous content of dx (accumulate mode), fetched with the other loads of the tile
+      if (a.accumulate) {
+#pragma unroll
+        for (int q = 0; q < R * STRIDE; ++q) {
+          const int ti = t * STRIDE + q;
+          O[q] = vload_rw<V>(dxp + (size_t)(ti < Lin ? ti : Lin - 1) * C);
+        }
       }
+      // ---- data gradient of the input rows of this tile
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const int ti = to * a.stride + k - PAD;
-        if (ti < 0 || ti >= a.Lin) continue;
-        const vf<V> xv = fx.load((size_t)ti * a.C);
+      for (int q = 0; q < R * STRIDE; ++q) {
+        const int ti = t * STRIDE + q;
+        if (ti < i1) {
+          vf<V> acc = vzero<V>();
 #pragma unroll
-        for (int g = 0; g < NW; ++g)
+          for (int k = 0; k < KS; ++k) {
+            // output row (ti + PAD - k) / STRIDE
+            if (STRIDE == 2 && ((q + PAD - k) & 1)) continue;
+            const int slot = STRIDE == 1 ? q + 2 * PAD - k : (q + PAD - k) / 2 + 1;
 #pragma unroll
-          for (int e = 0; e < V; ++e) dw[g][k][e] = fmaf(gv[g][e], xv[e], dw[g][k][e]);
+            for (int g = 0; g < NW; ++g)
+#pragma unroll
+              for (int e = 0; e < V; ++e) acc[e] = fmaf(w[g][k][e], G[g][slot][e], acc[e]);
+          }
+          if (prelu) {
+            const vf<V>& n = X[q - X0];
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+              if (n[e] < 0.f) {
+                sl_acc = fmaf(acc[e], n[e], sl_acc);
+                acc[e] *= fx.slope;
+              }
+          }
+          if (a.accumulate) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += O[q][e];
+          }
+          vstore<V>(dxp + (size_t)ti * C, acc);
+        }
       }
+      // ---- weight / bias gradients of the output rows of this tile
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (t + r < o1) {
+#pragma unroll
+          for (int g = 0; g < NW; ++g)
+#pragma unroll
+            for (int e = 0; e < V; ++e) db[g][e] += G[g][r - G0][e];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            vf<V> xv = X[r * STRIDE + k];  // input row (t + r)*STRIDE + k - PAD
+            if (prelu) {
+#pragma unroll
+              for (int e = 0; e < V; ++e) xv[e] = preluf_(xv[e], fx.slope);
+            }
+#pragma unroll
+            for (int g = 0; g < NW; ++g)
+#pragma unroll
+              for (int e = 0; e < V; ++e) dw[g][k][e] = fmaf(G[g][r - G0][e], xv[e], dw[g][k][e]);
+          }
+        }
+      }
+      // ---- carry
+#pragma unroll
+      for (int j = 0; j < GC; ++j)
+#pragma unroll
+        for (int g = 0; g < NW; ++g) G[g][j] = G[g][j + R];
+#pragma unroll
+      for (int j = 0; j < XC; ++j) X[j] = X[j + R * STRIDE];
     }
+    dsl = sl_acc;
 #pragma unroll
     for (int g = 0; g < NW; ++g) {
 #pragma unroll
@@ -345,124 +429,233 @@ __device__ __forceinline__ int first_local_row(int j, float scale, int Ll, int L
   return t;
 }
 
+// Three regular streaming passes (each thread: 4 channels, tiles of 4 rows, all loads of a tile issued together):
+//   G  over the global rows : raw_b = dw_a(xg), raw_e = dw_e(xg)
+//   L  over the local rows  : raw_a = dw_l(xl), d_loc = dout * gate[j], GlobLN_L sums, and per centre j the sums
+//                             d_act[j] <- sum dout*loc (before the sigmoid derivative), d_emb[j] <- sum dout
+//   F  over the global rows : d_act *= gate*(1-gate), GlobLN_A / GlobLN_E sums
 template <int KS>
-__global__ void la_bwd_a_kernel(LaBwdArgs a) {
-  constexpr int V = 4, PAD = (KS - 1) / 2;
+__global__ void la_bwd_g_kernel(LaBwdArgs a, int rows_per_thread) {
+  constexpr int V = 4, PAD = (KS - 1) / 2, R = 4, W = R + 2 * PAD;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (ch >= a.C) return;
+  const int Lg = a.Lg, C = a.C;
+  const int j0 = blockIdx.x * rows_per_thread, j1 = min(j0 + rows_per_thread, Lg);
+  float wa[KS][V], we[KS][V];
+#pragma unroll
+  for (int e = 0; e < V; ++e)
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      wa[k][e] = __ldg(a.wa + (size_t)(ch + e) * KS + k);
+      we[k][e] = __ldg(a.we + (size_t)(ch + e) * KS + k);
+    }
+  const float* gp = a.glo + (size_t)b * Lg * C + ch;
+  const size_t goff = (size_t)b * Lg * C + ch;
+  auto loadg = [&](int row) {
+    const int rc = row < 0 ? 0 : (row >= Lg ? Lg - 1 : row);
+    vf<V> v = vload<V>(gp + (size_t)rc * C);
+    const bool ok = row == rc;
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = ok ? v[e] : 0.f;
+    return v;
+  };
+  vf<V> X[W];
+#pragma unroll
+  for (int j = 0; j < 2 * PAD; ++j) X[j] = loadg(j0 - PAD + j);
+  for (int t = j0; t < j1; t += R) {
+#pragma unroll
+    for (int j = 2 * PAD; j < W; ++j) X[j] = loadg(t - PAD + j);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (t + r < j1) {
+        vf<V> Bt = vzero<V>(), Et = vzero<V>();
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            Bt[e] = fmaf(wa[k][e], X[r + k][e], Bt[e]);
+            Et[e] = fmaf(we[k][e], X[r + k][e], Et[e]);
+          }
+        vstore<V>(a.raw_b + goff + (size_t)(t + r) * C, Bt);
+        vstore<V>(a.raw_e + goff + (size_t)(t + r) * C, Et);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * PAD; ++j) X[j] = X[j + R];
+  }
+}
+
+template <int KS>
+__global__ void la_bwd_l_kernel(LaBwdArgs a) {
+  constexpr int V = 4, PAD = (KS - 1) / 2, R = 4, W = R + 2 * PAD;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const bool active = ch < a.C;
-  double s[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+  double S1 = 0.0, S2 = 0.0;
   if (active) {
     const int Ll = a.loc.L, Lg = a.Lg, C = a.C;
     const int j0 = blockIdx.x * a.jchunk, j1 = min(j0 + a.jchunk, Lg);
-    float wl[KS][V], wa[KS][V], we[KS][V];
+    const int t_begin = first_local_row(j0, a.scale, Ll, Lg), t_end = first_local_row(j1, a.scale, Ll, Lg);
+    float wl[KS][V];
 #pragma unroll
     for (int e = 0; e < V; ++e)
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        wl[k][e] = __ldg(a.wl + (size_t)(ch + e) * KS + k);
-        wa[k][e] = __ldg(a.wa + (size_t)(ch + e) * KS + k);
-        we[k][e] = __ldg(a.we + (size_t)(ch + e) * KS + k);
-      }
-    vf<V> scL, shL, scA, shA, scE, shE;
+      for (int k = 0; k < KS; ++k) wl[k][e] = __ldg(a.wl + (size_t)(ch + e) * KS + k);
+    vf<V> scL, shL, scA, shA;
     norm_coef<V>(a.nL, b, ch, scL, shL);
     norm_coef<V>(a.nA, b, ch, scA, shA);
-    norm_coef<V>(a.nE, b, ch, scE, shE);
-    float rL, murL, rA, murA, rE, murE;
+    float rL, murL;
     norm_moments(a.nL, b, rL, murL);
-    norm_moments(a.nA, b, rA, murA);
-    norm_moments(a.nE, b, rE, murE);
-    const vf<V> gL = vload<V>(a.nL.gamma + ch), gA = vload<V>(a.nA.gamma + ch), gE = vload<V>(a.nE.gamma + ch);
+    const vf<V> gL = vload<V>(a.nL.gamma + ch);
     FwdLoad<V> fl;
     fl.init(a.loc, a.lkind, b, ch, C);
-    const float* gp = a.glo + (size_t)b * Lg * C + ch;
     const float* dop = a.dout + (size_t)b * Ll * C + ch;
     float* dlp = a.d_loc + (size_t)b * Ll * C + ch;
     float* rap = a.raw_a + (size_t)b * Ll * C + ch;
     const size_t goff = (size_t)b * Lg * C + ch;
-    vf<V> dg[3], db[3];
-    float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
+    const float* rbp = a.raw_b + goff;
+    // zero padding applies to the conv input, i.e. after the on-load transform
+    auto loadx = [&](int row) { return fl.load_row(row, Ll, C); };
+    vf<V> dg = vzero<V>(), db = vzero<V>(), sum_e = vzero<V>(), sum_a = vzero<V>();
+    float s1 = 0.f, s2 = 0.f;
+    // centres of this chunk that no local row maps to (down-sampling step) get zero sums
+    auto zero_centres = [&](int ja, int jb) {
+      for (int j = ja; j < jb; ++j) {
+        vstore<V>(a.d_act + goff + (size_t)j * C, vzero<V>());
+        vstore<V>(a.d_emb + goff + (size_t)j * C, vzero<V>());
+      }
+    };
+    if (t_begin >= t_end) {
+      zero_centres(j0, j1);
+    } else {
+      zero_centres(j0, nearest_src(t_begin, a.scale, Lg));
+      vf<V> X[W];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { dg[i] = vzero<V>(); db[i] = vzero<V>(); }
-    int t = first_local_row(j0, a.scale, Ll, Lg);
-    for (int j = j0; j < j1; ++j) {
-      // global branch at centre j
-      vf<V> Bt = vzero<V>(), Et = vzero<V>();
+      for (int j = 0; j < 2 * PAD; ++j) X[j] = loadx(t_begin - PAD + j);
+      for (int t = t_begin; t < t_end; t += R) {
+        vf<V> D[R], Bt[R];
+        int jr[R + 1];
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const int jj = j + k - PAD;
-        if (jj < 0 || jj >= Lg) continue;
-        const vf<V> xv = vload<V>(gp + (size_t)jj * C);
+        for (int j = 2 * PAD; j < W; ++j) X[j] = loadx(t - PAD + j);
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          Bt[e] = fmaf(wa[k][e], xv[e], Bt[e]);
-          Et[e] = fmaf(we[k][e], xv[e], Et[e]);
+        for (int r = 0; r <= R; ++r) jr[r] = t + r < t_end ? nearest_src(t + r, a.scale, Lg) : j1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {  // unconditional, clamped (rows past t_end are not used)
+          const int tr = t + r < Ll ? t + r : Ll - 1;
+          const int jc = jr[r] < Lg ? jr[r] : Lg - 1;
+          D[r] = vload<V>(dop + (size_t)tr * C);
+          Bt[r] = vload_rw<V>(rbp + (size_t)jc * C);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (t + r < t_end) {
+            vf<V> A = vzero<V>(), dl;
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+#pragma unroll
+              for (int e = 0; e < V; ++e) A[e] = fmaf(wl[k][e], X[r + k][e], A[e]);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              const float gate = sigmoidf_(fmaf(Bt[r][e], scA[e], shA[e]));
+              const float loc = fmaf(A[e], scL[e], shL[e]);
+              sum_e[e] += D[r][e];
+              sum_a[e] = fmaf(D[r][e], loc, sum_a[e]);
+              dl[e] = D[r][e] * gate;
+              const float xh = fmaf(A[e], rL, -murL);
+              dg[e] = fmaf(dl[e], xh, dg[e]);
+              db[e] += dl[e];
+              const float gd = gL[e] * dl[e];
+              s1 += gd;
+              s2 = fmaf(gd, xh, s2);
+            }
+            vstore<V>(dlp + (size_t)(t + r) * C, dl);
+            vstore<V>(rap + (size_t)(t + r) * C, A);
+            if (jr[r + 1] != jr[r]) {  // last local row of centre jr[r]
+              vstore<V>(a.d_act + goff + (size_t)jr[r] * C, sum_a);
+              vstore<V>(a.d_emb + goff + (size_t)jr[r] * C, sum_e);
+              sum_a = vzero<V>();
+              sum_e = vzero<V>();
+              zero_centres(jr[r] + 1, jr[r + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2 * PAD; ++j) X[j] = X[j + R];
+      }
+    }
+    vred_add<V>(a.dgamma[0] + ch, dg);
+    vred_add<V>(a.dbeta[0] + ch, db);
+    S1 = s1;
+    S2 = s2;
+  }
+  block_accum2(a.S[0] + 2 * b, S1, S2);
+}
+
+__global__ void la_bwd_f_kernel(LaBwdArgs a, int rows_per_thread) {
+  constexpr int V = 4, R = 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const bool active = ch < a.C;
+  double s[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  if (active) {
+    const int Lg = a.Lg, C = a.C;
+    const int j0 = blockIdx.x * rows_per_thread, j1 = min(j0 + rows_per_thread, Lg);
+    vf<V> scA, shA;
+    norm_coef<V>(a.nA, b, ch, scA, shA);
+    float rA, murA, rE, murE;
+    norm_moments(a.nA, b, rA, murA);
+    norm_moments(a.nE, b, rE, murE);
+    const vf<V> gA = vload<V>(a.nA.gamma + ch), gE = vload<V>(a.nE.gamma + ch);
+    const size_t goff = (size_t)b * Lg * C + ch;
+    vf<V> dg[2], db[2];
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { dg[i] = vzero<V>(); db[i] = vzero<V>(); }
+    for (int t = j0; t < j1; t += R) {
+      vf<V> SA[R], SE[R], Bt[R], Et[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {  // unconditional, clamped (rows past j1 are not used)
+        const size_t off = goff + (size_t)(t + r < Lg ? t + r : Lg - 1) * C;
+        SA[r] = vload_rw<V>(a.d_act + off);
+        SE[r] = vload_rw<V>(a.d_emb + off);
+        Bt[r] = vload_rw<V>(a.raw_b + off);
+        Et[r] = vload_rw<V>(a.raw_e + off);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (t + r < j1) {
+          vf<V> da;
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const float gate = sigmoidf_(fmaf(Bt[r][e], scA[e], shA[e]));
+            da[e] = SA[r][e] * gate * (1.f - gate);
+            const float bh = fmaf(Bt[r][e], rA, -murA), eh = fmaf(Et[r][e], rE, -murE);
+            dg[0][e] = fmaf(da[e], bh, dg[0][e]);
+            db[0][e] += da[e];
+            const float ga = gA[e] * da[e];
+            s1[0] += ga;
+            s2[0] = fmaf(ga, bh, s2[0]);
+            dg[1][e] = fmaf(SE[r][e], eh, dg[1][e]);
+            db[1][e] += SE[r][e];
+            const float ge = gE[e] * SE[r][e];
+            s1[1] += ge;
+            s2[1] = fmaf(ge, eh, s2[1]);
+          }
+          vstore<V>(a.d_act + goff + (size_t)(t + r) * C, da);
         }
       }
-      vf<V> gate;
-#pragma unroll
-      for (int e = 0; e < V; ++e) gate[e] = sigmoidf_(fmaf(Bt[e], scA[e], shA[e]));
-      vf<V> sum_e = vzero<V>(), sum_a = vzero<V>();
-      const int tend = first_local_row(j + 1, a.scale, Ll, Lg);
-      for (; t < tend; ++t) {
-        vf<V> A = vzero<V>();
-#pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          const int tt = t + k - PAD;
-          if (tt < 0 || tt >= Ll) continue;
-          const vf<V> xv = fl.load((size_t)tt * C);
-#pragma unroll
-          for (int e = 0; e < V; ++e) A[e] = fmaf(wl[k][e], xv[e], A[e]);
-        }
-        const vf<V> d = vload<V>(dop + (size_t)t * C);
-        vf<V> dl;
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const float loc = fmaf(A[e], scL[e], shL[e]);
-          sum_e[e] += d[e];
-          sum_a[e] = fmaf(d[e], loc, sum_a[e]);
-          dl[e] = d[e] * gate[e];
-          const float xh = fmaf(A[e], rL, -murL);
-          dg[0][e] = fmaf(dl[e], xh, dg[0][e]);
-          db[0][e] += dl[e];
-          const float gd = gL[e] * dl[e];
-          s1[0] += gd;
-          s2[0] = fmaf(gd, xh, s2[0]);
-        }
-        vstore<V>(dlp + (size_t)t * C, dl);
-        vstore<V>(rap + (size_t)t * C, A);
-      }
-      vf<V> da;
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        da[e] = sum_a[e] * gate[e] * (1.f - gate[e]);
-        const float bh = fmaf(Bt[e], rA, -murA), eh = fmaf(Et[e], rE, -murE);
-        dg[1][e] = fmaf(da[e], bh, dg[1][e]);
-        db[1][e] += da[e];
-        const float ga = gA[e] * da[e];
-        s1[1] += ga;
-        s2[1] = fmaf(ga, bh, s2[1]);
-        dg[2][e] = fmaf(sum_e[e], eh, dg[2][e]);
-        db[2][e] += sum_e[e];
-        const float ge = gE[e] * sum_e[e];
-        s1[2] += ge;
-        s2[2] = fmaf(ge, eh, s2[2]);
-      }
-      vstore<V>(a.d_act + goff + (size_t)j * C, da);
-      vstore<V>(a.d_emb + goff + (size_t)j * C, sum_e);
-      vstore<V>(a.raw_b + goff + (size_t)j * C, Bt);
-      vstore<V>(a.raw_e + goff + (size_t)j * C, Et);
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      vred_add<V>(a.dgamma[i] + ch, dg[i]);
-      vred_add<V>(a.dbeta[i] + ch, db[i]);
+    for (int i = 0; i < 2; ++i) {
+      vred_add<V>(a.dgamma[1 + i] + ch, dg[i]);
+      vred_add<V>(a.dbeta[1 + i] + ch, db[i]);
       s[i][0] = s1[i];
       s[i][1] = s2[i];
     }
   }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) block_accum2(a.S[i] + 2 * b, s[i][0], s[i][1]);
+  for (int i = 0; i < 2; ++i) block_accum2(a.S[1 + i] + 2 * b, s[i][0], s[i][1]);
 }
 
 // ----------------------------------------------------------------------------- pooling backward
@@ -476,25 +669,38 @@ __global__ void pool_bwd_kernel(const float* __restrict__ g, float* __restrict__
   const int t0 = blockIdx.x * rows_per_thread, t1 = min(t0 + rows_per_thread, L);
   const float* gp = g + (size_t)b * Lb * C + ch;
   float* dp = dx + (size_t)b * L * C + ch;
-  for (int t = t0; t < t1; ++t) {
-    const int jc = (int)(((long)t * Lb) / L);
-    vf<V> acc = vzero<V>();
-    for (int j = jc - 1; j <= jc + 1; ++j) {
-      if (j < 0 || j >= Lb) continue;
-      const int lo = (int)(((long)j * L) / Lb);
-      const int hi = (int)((((long)j + 1) * L + Lb - 1) / Lb);
-      if (t < lo || t >= hi) continue;
-      const float inv = 1.f / (float)(hi - lo);
-      const vf<V> gv = vload<V>(gp + (size_t)j * C);
+  // only bins jc = floor(t*Lb/L) and jc + 1 can contain t (bins overlap by at most one row)
+  auto bin_weight = [&](int j, int t) {
+    if (j >= Lb) return 0.f;
+    const int lo = (int)(((long)j * L) / Lb);
+    const int hi = (int)((((long)j + 1) * L + Lb - 1) / Lb);
+    return (t >= lo && t < hi) ? 1.f / (float)(hi - lo) : 0.f;
+  };
+  for (int t = t0; t < t1; t += 4) {
+    vf<V> g0[4], g1[4], o[4];
+    float w0[4], w1[4];
 #pragma unroll
-      for (int e = 0; e < V; ++e) acc[e] = fmaf(gv[e], inv, acc[e]);
+    for (int i = 0; i < 4; ++i) {  // unconditional, clamped loads
+      const int tt = t + i < L ? t + i : L - 1;
+      const int jc = (int)(((long)tt * Lb) / L);
+      w0[i] = bin_weight(jc, tt);
+      w1[i] = bin_weight(jc + 1, tt);
+      g0[i] = vload<V>(gp + (size_t)jc * C);
+      g1[i] = vload<V>(gp + (size_t)(jc + 1 < Lb ? jc + 1 : Lb - 1) * C);
+      if (accumulate) o[i] = vload_rw<V>(dp + (size_t)tt * C);
     }
-    if (accumulate) {
-      const vf<V> o = vload_rw<V>(dp + (size_t)t * C);
 #pragma unroll
-      for (int e = 0; e < V; ++e) acc[e] += o[e];
+    for (int i = 0; i < 4; ++i) {
+      if (t + i < t1) {
+        vf<V> acc;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          acc[e] = fmaf(g0[i][e], w0[i], g1[i][e] * w1[i]);
+          if (accumulate) acc[e] += o[i][e];
+        }
+        vstore<V>(dp + (size_t)(t + i) * C, acc);
+      }
     }
-    vstore<V>(dp + (size_t)t * C, acc);
   }
 }
 
@@ -542,20 +748,32 @@ __global__ void ln_bwd_apply_kernel(const float* __restrict__ x, float k1, const
   const int r0 = blockIdx.x * rows_per_thread, r1 = min(r0 + rows_per_thread, rows);
   const vf<V> wv = vload<V>(w + ch);
   vf<V> aw = vzero<V>(), ab = vzero<V>();
-  for (int r = r0; r < r1; ++r) {
-    const float* rs = rowstat + (size_t)r * 4;
-    const float mu = rs[0], rstd = rs[1], m1 = rs[2], m2 = rs[3];
-    const size_t off = (size_t)r * C + ch;
-    const vf<V> xv = vload<V>(x + off), d = vload<V>(dy + off);
-    vf<V> o = add ? vload<V>(add + off) : vzero<V>();
+  for (int r = r0; r < r1; r += 4) {
+    vf<V> xv[4], d[4], o[4];
+    float4 rs[4];
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float xh = (k1 * xv[e] - mu) * rstd;
-      aw[e] = fmaf(d[e], xh, aw[e]);
-      ab[e] += d[e];
-      o[e] = fmaf(kout * rstd, wv[e] * d[e] - m1 - xh * m2, o[e]);
+    for (int i = 0; i < 4; ++i) {  // unconditional, clamped loads
+      const int rr = r + i < rows ? r + i : rows - 1;
+      const size_t off = (size_t)rr * C + ch;
+      rs[i] = __ldg(reinterpret_cast<const float4*>(rowstat) + rr);
+      xv[i] = vload<V>(x + off);
+      d[i] = vload<V>(dy + off);
+      o[i] = add ? vload<V>(add + off) : vzero<V>();
     }
-    vstore<V>(out + off, o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (r + i < r1) {
+        const float mu = rs[i].x, rstd = rs[i].y, m1 = rs[i].z, m2 = rs[i].w;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float xh = (k1 * xv[i][e] - mu) * rstd;
+          aw[e] = fmaf(d[i][e], xh, aw[e]);
+          ab[e] += d[i][e];
+          o[i][e] = fmaf(kout * rstd, wv[e] * d[i][e] - m1 - xh * m2, o[i][e]);
+        }
+        vstore<V>(out + (size_t)(r + i) * C + ch, o[i]);
+      }
+    }
   }
   vred_add<V>(dw + ch, aw);
   vred_add<V>(db + ch, ab);
