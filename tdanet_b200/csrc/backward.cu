@@ -65,6 +65,23 @@ static int bgemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
 #endif
 }
 
+struct RepEntry { float* dst; size_t off; int n; };
+struct BCtx : Ctx {
+  const tdanet_weights_t* g;  // gradient buffers, same layout as the weights
+  std::vector<RepEntry>* reps;  // replicated accumulators handed out so far (shared by the per-block copies)
+  float* gp(const float* p) const { return const_cast<float*>(p); }
+  // replica 0 of the accumulator that stands in for the depthwise gradient buffer `dst` (n floats) during the sweep
+  float* rep_of(const float* dst, int n) const {
+    if (!dst) return nullptr;
+    for (auto& e : *reps)
+      if (e.dst == dst) return at(p->rep_arena) + e.off;
+    size_t off = reps->empty() ? 0 : reps->back().off + (size_t)(reps->back().n + 3) / 4 * 4;
+    if (off + n > p->rep_floats || reps->size() >= 64) return nullptr;
+    reps->push_back({const_cast<float*>(dst), off, n});
+    return at(p->rep_arena) + off;
+  }
+};
+
 // ----------------------------------------------------------------------------- launchers
 static inline void row_grid(int L, int C4, int B, int rows, dim3& grid, int& threads) {
   threads = C4 > 256 ? 256 : (C4 < 32 ? 32 : C4);
@@ -107,8 +124,19 @@ static int launch_gln_bwd_apply(const GradSrc& g, float* out, int accumulate, in
   return 0;
 }
 
-static int launch_dw_bwd(DwBwdArgs& a, int ks, int nw, cudaStream_t st) {
+static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
+  cudaStream_t st = x.st;
   TD_REQUIRE(a.C % 4 == 0, "dw_bwd: C=%d", a.C);
+  a.rep_stride = x.p->rep_floats;
+  a.n_rep = TDANET_DW_REPLICAS;
+  for (int g = 0; g < nw; ++g) {
+    a.dw[g] = x.rep_of(a.dw[g], a.C * ks);
+    TD_REQUIRE(a.dw[g] != nullptr, "dw_bwd: replica arena exhausted");
+    if (a.db[g]) {
+      a.db[g] = x.rep_of(a.db[g], a.C);
+      TD_REQUIRE(a.db[g] != nullptr, "dw_bwd: replica arena exhausted");
+    }
+  }
   TD_REQUIRE(a.stride == 1 || a.stride == 2, "dw_bwd: stride %d", a.stride);
   TD_REQUIRE(a.xkind == SRC_PLAIN || a.xkind == SRC_AFFINE || a.xkind == SRC_AFFINE_PRELU, "dw_bwd: source kind %d", a.xkind);
   TD_REQUIRE(a.xin.L == a.Lin, "dw_bwd: input length %d != %d", a.xin.L, a.Lin);
@@ -234,11 +262,6 @@ static int launch_framed_wgrad(const float* M, const float* sig, float* dW, int 
 }
 
 // ----------------------------------------------------------------------------- orchestration
-struct BCtx : Ctx {
-  const tdanet_weights_t* g;  // gradient buffers, same layout as the weights
-  float* gp(const float* p) const { return const_cast<float*>(p); }
-};
-
 static GradSrc gln_grad(const float* dy, const float* x, const NormRef& n, const double* S) {
   GradSrc g{};
   g.dy = dy; g.x = x; g.norm = n; g.S = S; g.kind = G_GLN;
@@ -308,7 +331,7 @@ static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdane
   d.w[0] = la.local_embedding.w; d.dw[0] = x.gp(gla.local_embedding.w);
   d.xin = loc; d.xkind = lkind; d.B = B; d.C = C; d.Lin = Ll; d.Lout = Ll; d.stride = 1;
   d.dx = d_loc_in; d.accumulate = acc_loc;
-  if (int e = launch_dw_bwd(d, ks, 1, x.st)) return e;
+  if (int e = launch_dw_bwd(x, d, ks, 1)) return e;
   d = DwBwdArgs{};
   d.g[0] = gln_grad(a.d_act, a.raw_b, nA, a.S[1]);
   d.g[1] = gln_grad(a.d_emb, a.raw_e, nE, a.S[2]);
@@ -316,7 +339,7 @@ static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdane
   d.w[1] = la.global_embedding.w; d.dw[1] = x.gp(gla.global_embedding.w);
   d.xin = bplain(glo, Lg); d.xkind = SRC_PLAIN; d.B = B; d.C = C; d.Lin = Lg; d.Lout = Lg; d.stride = 1;
   d.dx = d_glo_in; d.accumulate = acc_glo;
-  return launch_dw_bwd(d, ks, 2, x.st);
+  return launch_dw_bwd(x, d, ks, 2);
 }
 
 // GA / GlobalAttention backwards: g_ga_out -> g_ga_in
@@ -348,7 +371,7 @@ static int global_attention_backward(const BCtx& x) {
     d.w[0] = w->ffn_dw_w; d.dw[0] = x.gp(gw->ffn_dw_w); d.db[0] = x.gp(gw->ffn_dw_b);
     d.xin = baffine(x.at(p.fc1), Lb, n_fc1); d.xkind = SRC_AFFINE;
     d.B = B; d.C = 2 * C; d.Lin = Lb; d.Lout = Lb; d.stride = 1; d.dx = x.at(p.g_fc1);
-    if (int e = launch_dw_bwd(d, 5, 1, x.st)) return e;
+    if (int e = launch_dw_bwd(x, d, 5, 1)) return e;
   }
   {
     Tag t("bwd_bottom_misc");
@@ -456,7 +479,7 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
       d.xkind = SRC_AFFINE; d.Lin = p.L[k - 1]; d.stride = 2; d.dx = x.at(p.g_spp[k - 1]); d.accumulate = 1;
     }
     Tag t(k == 0 ? "bwd_spp_dw0" : "bwd_spp_dw_s2");
-    if (int e = launch_dw_bwd(d, 5, 1, x.st)) return e;
+    if (int e = launch_dw_bwd(x, d, 5, 1)) return e;
   }
   // ---- proj_1x1
   const NormRef n_proj = norm_ref(x, p.st_proj, 2, (double)L0 * C, w->proj.gamma, w->proj.beta);
@@ -478,7 +501,9 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
   TD_REQUIRE(w && gw && wav && d_est && workspace, "NULL argument");
   if (ws_bytes < p.bytes) return fail(TDANET_ENOSPACE, "workspace has %zu bytes, need %zu", ws_bytes, p.bytes);
   BCtx x{};
-  x.c = c; x.w = w; x.p = &p; x.ws = (char*)workspace; x.st = st; x.blk = 0; x.g = gw;
+  std::vector<RepEntry> reps;
+  x.c = c; x.w = w; x.p = &p; x.ws = (char*)workspace; x.st = st; x.blk = 0; x.g = gw; x.reps = &reps;
+  TD_CUDA(cudaMemsetAsync(x.at<char>(p.rep_arena), 0, p.rep_floats * TDANET_DW_REPLICAS * sizeof(float), st));
   const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
   const int NS = c->num_sources, CI = NS * Nb, R0 = B * L0, nb = c->num_blocks;
 
@@ -537,7 +562,20 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
   if (int e = launch_gln_bwd_stats(d_nenc, x.at(p.enc), n_enc, x.gp(gw->ln_gamma), x.gp(gw->ln_beta), x.at<double>(p.bs_enc), B, L0, Nb, st)) return e;
   if (int e = launch_gln_bwd_apply(gln_grad(d_nenc, x.at(p.enc), n_enc, x.at<double>(p.bs_enc)), x.at(p.g_enc), 1, B, L0, Nb, st)) return e;
   // encoder Conv1d (pad_input folded into the indexing)
-  return launch_framed_wgrad(x.at(p.g_enc), wav, x.gp(gw->enc_w[0]), B, L0, Nb, 1, K, S, T, K - S, st);
+  if (int e = launch_framed_wgrad(x.at(p.g_enc), wav, x.gp(gw->enc_w[0]), B, L0, Nb, 1, K, S, T, K - S, st)) return e;
+  // depthwise weight / bias gradients: replicas -> the caller's buffers
+  if (!reps.empty()) {
+    FoldArgs f{};
+    f.count = (int)reps.size(); f.n_rep = TDANET_DW_REPLICAS; f.rep_stride = p.rep_floats;
+    int nmax = 0;
+    for (int i = 0; i < f.count; ++i) {
+      f.e[i].dst = reps[i].dst; f.e[i].rep = x.at(p.rep_arena) + reps[i].off; f.e[i].n = reps[i].n;
+      nmax = reps[i].n > nmax ? reps[i].n : nmax;
+    }
+    dim3 grid(cdiv(nmax, 256), f.count);
+    TD_LAUNCH(fold_replicas_kernel, grid, 256, 0, st, f);
+  }
+  return 0;
 }
 
 }  // namespace td

@@ -237,6 +237,11 @@ struct DwBwdArgs {
   SrcDesc xin;
   int xkind;
   int B, C, Lin, Lout, stride;
+  // dw / db point at replica 0 of an accumulator that exists `n_rep` times (`rep_stride` floats apart): CTAs spread
+  // their atomics over the replicas (every depthwise weight lives in ~80 cache lines, and a launch adds ~10^6
+  // values to them), fold_replicas_kernel sums them into the real gradient at the end of the backward pass
+  size_t rep_stride;
+  int n_rep;       // power of two
   float* dx;       // [B, Lin, C]
   int accumulate;  // dx += instead of =
   float* dslope;   // SRC_AFFINE_PRELU
@@ -376,13 +381,22 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
       for (int j = 0; j < XC; ++j) X[j] = X[j + R * STRIDE];
     }
     dsl = sl_acc;
+    // the thread's V*KS weight gradients are contiguous in [C][KS]: KS vector reductions per conv
+    const size_t roff = (size_t)((blockIdx.x + blockIdx.z) & (a.n_rep - 1)) * a.rep_stride;
 #pragma unroll
     for (int g = 0; g < NW; ++g) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
+      for (int q = 0; q < KS; ++q) {
+        vf<V> v;
 #pragma unroll
-        for (int k = 0; k < KS; ++k) atomicAdd(a.dw[g] + (size_t)(ch + e) * KS + k, dw[g][k][e]);
-        if (a.db[g]) atomicAdd(a.db[g] + ch + e, db[g][e]);
+        for (int i = 0; i < V; ++i) v[i] = dw[g][(q * V + i) % KS][(q * V + i) / KS];
+        vred_add<V>(a.dw[g] + roff + (size_t)ch * KS + q * V, v);
+      }
+      if (a.db[g]) {
+        vf<V> v;
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = db[g][e];
+        vred_add<V>(a.db[g] + roff + ch, v);
       }
     }
   }
@@ -394,6 +408,21 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
 #endif
     block_sum2(dsl, z, sh);
     if (threadIdx.x == 0) atomicAdd(a.dslope, (float)dsl);
+  }
+}
+
+// grad[i] += sum_r rep[r][i] for every registered accumulator
+struct FoldArgs {
+  struct Entry { float* dst; const float* rep; int n; } e[64];
+  int count, n_rep;
+  size_t rep_stride;
+};
+__global__ void fold_replicas_kernel(FoldArgs a) {
+  const FoldArgs::Entry& en = a.e[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < en.n; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < a.n_rep; ++r) acc += en.rep[(size_t)r * a.rep_stride + i];
+    en.dst[i] += acc;
   }
 }
 

@@ -12,6 +12,8 @@
 
 namespace td {
 
+constexpr int TDANET_DW_REPLICAS = 8;
+
 struct Named {
   std::string name;
   size_t off;  // bytes
@@ -61,6 +63,8 @@ struct Plan {
   size_t t_dloc, t_rawa, t_dact, t_demb, t_rawb, t_rawe;  // LA backward temporaries
   size_t g_ga_out, g_fc2, g_ffn, g_fc1, g_ga_mid, g_attn_out, g_ctx, g_qkv, g_attn_in, g_ga_in;
   size_t att_p, att_ds, ln_rows;
+  // replicated accumulators of the depthwise weight / bias gradients: [REP_COUNT][rep_floats]
+  size_t rep_arena, rep_floats;
   // backward GlobLN sums S1 = sum(gamma*dy), S2 = sum(gamma*dy*xhat): [B,2] double each
   size_t bs_begin, bs_end, bs_enc, bs_proj, bs_fc1, bs_fc2, bs_spp[TDANET_MAX_DEPTH], bs_la[TDANET_MAX_DEPTH][3],
       bs_lgf[TDANET_MAX_DEPTH][3];
@@ -297,6 +301,12 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     p.att_p = p.take(n * sizeof(float));
     p.att_ds = p.take(n * sizeof(float));
     p.ln_rows = p.take((size_t)B * Lb * 4 * sizeof(float));
+  }
+  {
+    // every depthwise conv weight (+ bias) of the block: spp_dw, ffn dwconv, last_layer (k5), loc_glo_fus (k1)
+    size_t n = (size_t)depth * (C * 5 + C) + (size_t)(2 * C * 5 + 2 * C) + (size_t)(depth - 1) * 3 * C * 5 + (size_t)depth * 3 * C;
+    p.rep_floats = (n + 63) / 64 * 64;
+    p.rep_arena = p.take(p.rep_floats * TDANET_DW_REPLICAS * sizeof(float));
   }
   p.bs_enc = p.dstat("bs_enc", 1);
   p.bs_begin = p.bytes;

@@ -201,13 +201,17 @@ def test_training_step_matches_reference_loop():
     ref = {k: (torch.nn.Parameter(v.double()) if k != PE else v.double()) for k, v in sd.items()}
     params = [v for k, v in ref.items() if k != PE]
     opt = torch.optim.Adam(params, lr=lr)
-    ref_losses = []
+    ref_losses, solid = [], {}
     for s in range(steps):
         opt.zero_grad()
         est = O.forward(ref, mix[s].double(), O.OracleConfig(variant="best", sample_rate=SR, **kw))
         loss = O.pit_loss(est, tgt[s].double(), "sisdr", True)
         loss.backward()
         torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 5.0)
+        if s == 0:
+            # elements whose gradient is not at the rounding level (the key bias of the attention has an exactly
+            # zero gradient - softmax is shift invariant - and Adam turns its rounding noise into +-lr moves)
+            solid = {k: (v.grad.abs() > 1e-7 * v.grad.abs().max()) for k, v in ref.items() if k != PE and v.grad is not None}
         opt.step()
         ref_losses.append(loss.item())
     # CUDA path
@@ -226,6 +230,10 @@ def test_training_step_matches_reference_loop():
         if k == PE:
             continue
         d = (new[k].cpu().double() - v.detach()).abs()
+        if k in solid:
+            d = d[solid[k]]
+        if d.numel() == 0:
+            continue
         assert d.max().item() < 0.6 * lr * steps, k
         frac_off.append((d > 0.05 * lr).double().mean().item())
     # Adam's first steps move every element by ~lr * sign(g): an element whose gradient is at the rounding level
