@@ -133,6 +133,28 @@ def algorithmic_bytes(variant, lengths, B, C=512, c=128):
 TRAIN_BATCH = 8   # per GPU (BASELINE.json configs[3])
 
 
+def train_algorithmic_bytes(lengths, B, C=512):
+    """Unique input + output bytes per training step of the main backward roles (fp32, each tensor counted once
+    per launch, 16 blocks); DESIGN.md section 8 lists what every launch reads and writes."""
+    L, depth, Lb, f = lengths, len(lengths), lengths[-1], 4
+    partner = (depth - 3 + depth) % depth
+    la_a = la_dw = 0
+    for i in range(depth - 1):
+        Ll, Lg = L[i], (L[partner] if i == depth - 2 else L[i + 1])
+        la_a += 4 * Ll + 11 * Lg       # G: 1R+2W (Lg); L: 2R+2W (Ll) + 1R+2W (Lg); F: 4R+1W (Lg)
+        la_dw += 4 * Ll + 6 * Lg       # local: d_loc, raw_a, x_fused -> g_fused; global: 4 grads/raws + x_g -> g
+    lgf_a = sum(4 * L[k] + 11 * Lb for k in range(depth - 1))
+    lgf_dw = sum(4 * L[k] + 7 * Lb for k in range(depth - 1))
+    blk = {
+        "bwd_la_a": la_a, "bwd_la_dw": la_dw, "bwd_lgf_a": lgf_a, "bwd_lgf_dw": lgf_dw,
+        "bwd_spp_dw_s2": sum(2 * L[k] + 3 * L[k - 1] for k in range(1, depth)),
+        "bwd_spp_dw0": 4 * L[0],
+        "bwd_pool": sum(2 * L[k] for k in range(depth)) + depth * Lb,
+        "bwd_gln_stats": 2 * (sum(L) + L[0]),
+    }
+    return {k: v * C * f * B * 16 for k, v in blk.items()}
+
+
 def train_targets(rank, B, seed=4321):
     tgt = torch.randn(B, 2, N_SAMPLES, generator=torch.Generator().manual_seed(seed + rank)) * 0.1
     return tgt.sum(1), tgt
@@ -198,8 +220,24 @@ def run_train_leg(args, dev, rank, world, local, barrier):
     ms, ms_e2e = t.tolist()
     if rank != 0:
         return None
-    kernels = [{"kernel": p["kernel"], "launches_per_step": p["launches"], "ms_per_step": round(p["ms"], 4)}
-               for p in sorted(prof, key=lambda r: -r["ms"])]
+    alg = train_algorithmic_bytes(model.engine.latent_lengths(N_SAMPLES)[0], B)
+    peak, peak_src = measured_peaks()
+    kernels = []
+    for p in sorted(prof, key=lambda r: -r["ms"]):
+        row = {"kernel": p["kernel"], "launches_per_step": p["launches"], "ms_per_step": round(p["ms"], 4)}
+        if p["kernel"] in alg:
+            row["alg_GB_per_step"] = round(alg[p["kernel"]] / 1e9, 3)
+            row["achieved_GBps"] = round(alg[p["kernel"]] / 1e9 / (p["ms"] / 1e3), 1)
+        kernels.append(row)
+    top = next((r for r in kernels if "achieved_GBps" in r), None)
+    roofline = None if top is None else {
+        "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_GBps"], "peak": peak, "unit": "GB/s",
+        "frac": round(top["achieved_GBps"] / peak, 4), "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": int(alg[top["kernel"]] / max(1, top["launches_per_step"])),
+        "avg_launch_ms": round(top["ms_per_step"] / max(1, top["launches_per_step"]), 5),
+        "share_of_step": round(top["ms_per_step"] / max(1e-9, sum(k["ms_per_step"] for k in kernels)), 4),
+        "how": "CUDA events around every launch of one un-graphed forward+backward after the timed region "
+               "(launch gaps inflate the short kernels; the graph-replayed step is what `value` times)"}
     out = {
         "metric": "train_steps_per_second", "value": K / (ms / 1e3), "unit": "steps/s", "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "n_gpus": world,
@@ -211,7 +249,7 @@ def run_train_leg(args, dev, rank, world, local, barrier):
         "samples_per_second": world * B * K / (ms / 1e3),
         "e2e": {"value": K / (ms_e2e / 1e3), "unit": "steps/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": B * 3 * N_SAMPLES * 4, "d2h_bytes_per_step": 4},
-        "gpu_launches_per_step": launches, "loss_after": final_loss, "clocks": clk.summary(),
+        "gpu_launches_per_step": launches, "loss_after": final_loss, "clocks": clk.summary(), "roofline": roofline,
         "profiled_ms_per_step": round(sum(k["ms_per_step"] for k in kernels), 3),
         "kernels": kernels[:16],
     }

@@ -193,6 +193,11 @@ TDANET_API int tdanet_backward(const tdanet_config_t* cfg, const tdanet_weights_
  * tdanet_workspace_tensor plus "bin" "y" "fused0".. "mlogit" and the statistics "st_*" (elem_bytes = 8). */
 TDANET_API int tdanet_train_workspace_tensor(const tdanet_config_t* cfg, int batch, int n_samples, const char* name,
                    int block, size_t* byte_offset, int64_t dims[3], int32_t* elem_bytes);
+/* Weight / bias gradient of a 1x1 Conv1d / Linear in channels-last form: dW[N, K] += G[rows, N]^T A[rows, K],
+ * db[N] += column sums of G (db may be NULL).  gemm_mode fp32: CUDA-core fp32; tf32 / tf32x3: TF32 tensor cores
+ * (mma.sync) when N and K are multiples of 4. */
+TDANET_API int tdanet_wgrad(int gemm_mode, const float* G, const float* A, float* dW, float* db, int rows, int N,
+                   int K, tdanet_stream_t stream);
 /* sqnorm[0] = sum of squares of grads[0..n) (double, device; sqnorm has 2 elements). */
 TDANET_API int tdanet_grad_sqnorm(const float* grads, size_t n, double* sqnorm, tdanet_stream_t stream);
 /* clip_grad_norm_(max_grad_norm) (skipped if <= 0) then one torch.optim.Adam step (no weight decay, no amsgrad)

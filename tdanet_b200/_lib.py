@@ -92,6 +92,7 @@ _SIGNATURES = {
                                   C.c_int, fptr, C.c_size_t, fptr]),
     "tdanet_train_workspace_tensor": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_char_p, C.c_int,
                                                 C.POINTER(C.c_size_t), C.POINTER(C.c_int64 * 3), C.POINTER(C.c_int32)]),
+    "tdanet_wgrad": (C.c_int, [C.c_int, fptr, fptr, fptr, fptr, C.c_int, C.c_int, C.c_int, fptr]),
     "tdanet_grad_sqnorm": (C.c_int, [fptr, C.c_size_t, fptr, fptr]),
     "tdanet_adam_step": (C.c_int, [fptr, fptr, fptr, fptr, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_float, C.c_float, fptr, fptr, fptr]),

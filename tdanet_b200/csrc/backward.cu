@@ -220,7 +220,14 @@ static int launch_att_bwd(const float* qkv, const float* dctx, float* P, float* 
 
 // dW[N, K] += G[R, N]^T f(A[R, K]);  db[N] += column sums of G (db may be null)
 static int launch_wgrad(const float* G, const float* A, float* dW, float* db, int R, int N, int K,
-                        const float* a_slope, cudaStream_t st) {
+                        const float* a_slope, cudaStream_t st, int gemm_mode = TDANET_GEMM_FP32) {
+#ifndef TD_EMU
+  // tensor-core GEMM modes: TF32 mma.sync kernel (shapes it covers); gemm_mode fp32 keeps the exact fp32 kernel
+  if (gemm_mode != TDANET_GEMM_FP32 && !a_slope && N % 4 == 0 && K % 4 == 0)
+    return launch_wgrad_mma(G, A, dW, db, R, N, K, st);
+#else
+  (void)gemm_mode;
+#endif
   const int tiles = cdiv(N, WG_T) * cdiv(K, WG_T);
   int splits = cdiv(592, tiles);  // about four CTAs per SM
   int rps = cdiv(R, splits);
@@ -361,7 +368,7 @@ static int global_attention_backward(const BCtx& x) {
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_ga_out), x.at(p.fc2), n_fc2, x.at<double>(p.bs_fc2)),
                                      x.at(p.g_fc2), 0, B, Lb, C, x.st)) return e;
   }
-  { Tag t("wgrad_fc2"); if (int e = launch_wgrad(x.at(p.g_fc2), x.at(p.ffn_dw), x.gp(gw->fc2.w), nullptr, R, C, 2 * C, nullptr, x.st)) return e; }
+  { Tag t("wgrad_fc2"); if (int e = launch_wgrad(x.at(p.g_fc2), x.at(p.ffn_dw), x.gp(gw->fc2.w), nullptr, R, C, 2 * C, nullptr, x.st, x.c->gemm_mode)) return e; }
   { Tag t("dgrad_fc2"); if (int e = dgrad(x, x.at(p.g_fc2), p.wt_fc2, p.auxt_fc2, x.at(p.g_ffn), Lb, 2 * C, C, nullptr)) return e; }
   {
     // relu -> dwconv k5 (+bias) on gLN(fc1)
@@ -380,19 +387,19 @@ static int global_attention_backward(const BCtx& x) {
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_fc1), x.at(p.fc1), n_fc1, x.at<double>(p.bs_fc1)),
                                      x.at(p.g_ffn), 0, B, Lb, 2 * C, x.st)) return e;  // g_ffn is free again
   }
-  { Tag t("wgrad_fc1"); if (int e = launch_wgrad(x.at(p.g_ffn), x.at(p.ga_mid), x.gp(gw->fc1.w), nullptr, R, 2 * C, C, nullptr, x.st)) return e; }
+  { Tag t("wgrad_fc1"); if (int e = launch_wgrad(x.at(p.g_ffn), x.at(p.ga_mid), x.gp(gw->fc1.w), nullptr, R, 2 * C, C, nullptr, x.st, x.c->gemm_mode)) return e; }
   // g_ga_mid = g_ga_out (skip) + fc1 data gradient
   { Tag t("dgrad_fc1"); if (int e = dgrad(x, x.at(p.g_ffn), p.wt_fc1, p.auxt_fc1, x.at(p.g_ga_mid), Lb, C, 2 * C, x.at(p.g_ga_out))) return e; }
   // ga_mid = ga_in + LN2(2 * attn_out)
   { Tag t("bwd_bottom_misc");
     if (int e = launch_ln_bwd(x.at(p.attn_out), 2.f, w->ln2_w, x.at(p.g_ga_mid), x.at(p.ln_rows), nullptr,
                               x.at(p.g_attn_out), x.gp(gw->ln2_w), x.gp(gw->ln2_b), R, C, x.st)) return e; }
-  { Tag t("wgrad_out_proj"); if (int e = launch_wgrad(x.at(p.g_attn_out), x.at(p.attn_ctx), x.gp(gw->out_proj_w), x.gp(gw->out_proj_b), R, C, C, nullptr, x.st)) return e; }
+  { Tag t("wgrad_out_proj"); if (int e = launch_wgrad(x.at(p.g_attn_out), x.at(p.attn_ctx), x.gp(gw->out_proj_w), x.gp(gw->out_proj_b), R, C, C, nullptr, x.st, x.c->gemm_mode)) return e; }
   { Tag t("dgrad_out_proj"); if (int e = dgrad(x, x.at(p.g_attn_out), p.wt_out, p.auxt_out, x.at(p.g_ctx), Lb, C, C, nullptr)) return e; }
   { Tag t("bwd_attention");
     if (int e = launch_att_bwd(x.at(p.qkv), x.at(p.g_ctx), x.at(p.att_p), x.at(p.att_ds), x.at(p.g_qkv), B, Lb, C,
                                c->n_head, group, 0, x.st)) return e; }
-  { Tag t("wgrad_in_proj"); if (int e = launch_wgrad(x.at(p.g_qkv), x.at(p.attn_in), x.gp(gw->in_proj_w), x.gp(gw->in_proj_b), R, 3 * C, C, nullptr, x.st)) return e; }
+  { Tag t("wgrad_in_proj"); if (int e = launch_wgrad(x.at(p.g_qkv), x.at(p.attn_in), x.gp(gw->in_proj_w), x.gp(gw->in_proj_b), R, 3 * C, C, nullptr, x.st, x.c->gemm_mode)) return e; }
   { Tag t("dgrad_in_proj"); if (int e = dgrad(x, x.at(p.g_qkv), p.wt_in, p.auxt_in, x.at(p.g_attn_in), Lb, C, 3 * C, nullptr)) return e; }
   // attn_in = LN1(ga_in) + pe;  g_ga_in = g_ga_mid (skip) + LN1 backward
   Tag t("bwd_bottom_misc");
@@ -414,7 +421,7 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
     return norm_ref(x, p.st_spp[k], 2, (double)p.L[k] * C, w->spp_dw[k].gamma, w->spp_dw[k].beta);
   };
   // ---- res_conv
-  { Tag t("wgrad_res_conv"); if (int e = launch_wgrad(d_y, x.at(p.expanded[0]), x.gp(gw->res_w), x.gp(gw->res_b), R0, cc, C, nullptr, x.st)) return e; }
+  { Tag t("wgrad_res_conv"); if (int e = launch_wgrad(d_y, x.at(p.expanded[0]), x.gp(gw->res_w), x.gp(gw->res_b), R0, cc, C, nullptr, x.st, x.c->gemm_mode)) return e; }
   { Tag t("dgrad_res_conv"); if (int e = dgrad(x, d_y, p.wt_res, p.auxt_res, x.at(p.g_exp[0]), L0, C, cc, nullptr)) return e; }
   // ---- top-down fusion, in the reverse of the forward order
   bool fused_written[TDANET_MAX_DEPTH] = {};
@@ -489,7 +496,7 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
   { Tag t("bwd_gln_apply");
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_proj), x.at(p.proj), n_proj, x.at<double>(p.bs_proj)),
                                      x.at(p.t_dloc), 0, B, L0, C, x.st)) return e; }  // LA temporaries are free by now
-  { Tag t("wgrad_proj"); if (int e = launch_wgrad(x.at(p.t_dloc), in, x.gp(gw->proj.w), x.gp(gw->proj.b), R0, C, cc, nullptr, x.st)) return e; }
+  { Tag t("wgrad_proj"); if (int e = launch_wgrad(x.at(p.t_dloc), in, x.gp(gw->proj.w), x.gp(gw->proj.b), R0, C, cc, nullptr, x.st, x.c->gemm_mode)) return e; }
   Tag t("dgrad_proj");
   return dgrad(x, x.at(p.t_dloc), p.wt_proj, p.auxt_proj, d_in, L0, cc, C, d_y);
 }
@@ -588,6 +595,13 @@ int tdanet_backward(const tdanet_config_t* cfg, const tdanet_weights_t* w, const
                     const float* wav, const float* d_est, int batch, int n_samples, void* workspace,
                     size_t workspace_bytes, tdanet_stream_t stream) {
   return backward(cfg, w, grads, wav, d_est, batch, n_samples, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int tdanet_wgrad(int gemm_mode, const float* G, const float* A, float* dW, float* db, int rows, int N, int K,
+                 tdanet_stream_t stream) {
+  TD_REQUIRE(G && A && dW && rows > 0 && N > 0 && K > 0, "bad argument");
+  TD_REQUIRE(gemm_mode >= TDANET_GEMM_FP32 && gemm_mode <= TDANET_GEMM_TF32X3, "gemm_mode %d", gemm_mode);
+  return launch_wgrad(G, A, dW, db, rows, N, K, nullptr, (cudaStream_t)stream, gemm_mode);
 }
 
 #ifdef TD_EMU

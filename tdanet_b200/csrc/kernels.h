@@ -181,6 +181,10 @@ int launch_tf32_prepare(const float* w, float* aux, size_t n, int mode, cudaStre
 // aux (as bf16[n]) = round-to-nearest-even bf16 copy of w
 int launch_bf16_prepare(const float* w, float* aux, size_t n, cudaStream_t st);
 
+// ------------------------------------------------------------------ wgrad_mma.cu
+// dW[N, K] += G[R, N]^T A[R, K] (TF32 mma.sync, fp32 accumulate), db[N] += column sums of G (db may be null)
+int launch_wgrad_mma(const float* G, const float* A, float* dW, float* db, int R, int N, int K, cudaStream_t st);
+
 // ------------------------------------------------------------------ css.cu
 int launch_css_stitch(const float* est, int n_streams, int n_chunks, int seg_len, int overlap, int out_len,
                       int32_t* swap, float* out, cudaStream_t st);

@@ -349,3 +349,17 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
                                    params.numel(), lr, betas[0], betas[1], eps, max_grad_norm, grad_scale,
                                    None if sqnorm is None else sqnorm.data_ptr(), step.data_ptr(),
                                    torch.cuda.current_stream(params.device).cuda_stream))
+
+
+def wgrad(G: torch.Tensor, A: torch.Tensor, mode: str = "tf32", with_bias: bool = True):
+    """dW = G^T A ([N, K]) and db = column sums of G through tdanet_wgrad; G [R, N], A [R, K] fp32 CUDA."""
+    lib = _lib.load()
+    R, N = G.shape
+    K = A.shape[1]
+    dW = torch.zeros(N, K, dtype=torch.float32, device=G.device)
+    db = torch.zeros(N, dtype=torch.float32, device=G.device) if with_bias else None
+    with torch.cuda.device(G.device):
+        check(lib.tdanet_wgrad(_lib.GEMM_MODES[mode], G.contiguous().data_ptr(), A.contiguous().data_ptr(), dW.data_ptr(),
+                               None if db is None else db.data_ptr(), R, N, K,
+                               torch.cuda.current_stream(G.device).cuda_stream))
+    return dW, db

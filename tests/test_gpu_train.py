@@ -263,3 +263,21 @@ def test_training_reduces_loss_and_model_api_backward():
     m.zero_grad(set_to_none=True)
     losses = [system.fit_step((mix, tgt, None), lr=1e-3)["loss"].item() for _ in range(30)]
     assert losses[-1] < losses[0] - 0.5, losses
+
+
+@pytest.mark.parametrize("R,N,K", [(16080, 512, 128), (16080, 128, 512), (1008, 1536, 512), (1008, 512, 1024),
+                                   (1000, 64, 32), (77, 36, 20), (5, 4, 4)])
+def test_wgrad_tensor_core_matches_fp32(R, N, K):
+    """The TF32 mma.sync weight-gradient kernel against the exact fp32 kernel and torch (shapes of SURVEY.md
+    Appendix C plus ragged ones)."""
+    g = torch.Generator().manual_seed(R + N + K)
+    G = torch.randn(R, N, generator=g).to(DEV)
+    A = torch.randn(R, K, generator=g).to(DEV)
+    ref = G.double().t() @ A.double()
+    ref_b = G.double().sum(0)
+    scale = ref.abs().max().item()
+    for mode, tol in (("fp32", 2e-6), ("tf32", 2e-3)):
+        dW, db = E.wgrad(G, A, mode)
+        torch.cuda.synchronize()
+        assert (dW.double() - ref).abs().max().item() / scale < tol, mode
+        assert (db.double() - ref_b).abs().max().item() / ref_b.abs().max().item() < 1e-5, mode
