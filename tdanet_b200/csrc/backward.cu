@@ -65,10 +65,41 @@ static int bgemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
 #endif
 }
 
+// Side streams of the backward sweep (lazily created per device, never destroyed): `w` runs the weight-gradient
+// GEMMs, which nothing in the sweep waits for before the end of a block; `l` runs the local-branch depthwise
+// backward of every top-down step followed by that scale's loc_glo_fus chain, while the main stream continues
+// down the global-branch chain.  Dependencies are cudaEventRecord / cudaStreamWaitEvent pairs, which stream capture
+// turns into graph edges, so a captured training step keeps the concurrency.
+struct SideStreams {
+  cudaStream_t w = nullptr, l = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t next = 0;
+  int init() {
+    if (w) return 0;
+    TD_CUDA(cudaStreamCreateWithFlags(&w, cudaStreamNonBlocking));
+    TD_CUDA(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking));
+    events.resize(512);
+    for (auto& e : events) TD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+  }
+  // everything enqueued on `from` so far happens before whatever is enqueued on `to` from now on
+  int order(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = events[next++ % events.size()];
+    TD_CUDA(cudaEventRecord(e, from));
+    TD_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+  }
+};
+static SideStreams g_side[16];
+
 struct RepEntry { float* dst; size_t off; int n; };
 struct BCtx : Ctx {
   const tdanet_weights_t* g;  // gradient buffers, same layout as the weights
   std::vector<RepEntry>* reps;  // replicated accumulators handed out so far (shared by the per-block copies)
+  SideStreams* side;
+  cudaStream_t main_st;         // the caller's stream (x.st is the stream launches currently go to)
+  int tset = 0;                 // LA temporary set in use
+  BCtx on(cudaStream_t s, int set) const { BCtx y = *this; y.st = s; y.tset = set; return y; }
   float* gp(const float* p) const { return const_cast<float*>(p); }
   // replica 0 of the accumulator that stands in for the depthwise gradient buffer `dst` (n floats) during the sweep
   float* rep_of(const float* dst, int n) const {
@@ -170,7 +201,6 @@ static int launch_la_bwd_a(LaBwdArgs& a, int ks, cudaStream_t st) {
   row_grid(a.Lg, a.C / 4, a.B, a.jchunk, lgrid, threads);
   if (ks == 5) TD_LAUNCH_RED((la_bwd_l_kernel<5>), lgrid, threads, 0, st, a);
   else TD_LAUNCH_RED((la_bwd_l_kernel<1>), lgrid, threads, 0, st, a);
-  TD_LAUNCH_RED(la_bwd_f_kernel, grid, threads, 0, st, a, grows);
   return 0;
 }
 
@@ -200,6 +230,12 @@ static int launch_att_bwd_d(const float* qkv, const float* dctx, float* P, float
                             int n_head, int group, int time_axis, cudaStream_t st) {
   const int n = time_axis ? L : group;
   const int nprob = time_axis ? B : (B / group) * L;
+  if (n <= 16) {
+    const int warps = nprob * n_head;
+    if (n <= 8) TD_LAUNCH_COOP((att_bwd_warp_kernel<D, 8>), cdiv(warps, 4), 128, 0, st, qkv, dctx, dqkv, L, C, n, n_head, group, time_axis, warps);
+    else TD_LAUNCH_COOP((att_bwd_warp_kernel<D, 16>), cdiv(warps, 4), 128, 0, st, qkv, dctx, dqkv, L, C, n, n_head, group, time_axis, warps);
+    return 0;
+  }
   const int total = nprob * n_head * n;
   TD_LAUNCH((att_bwd_dq_kernel<D>), cdiv(total, 128), 128, 0, st, qkv, dctx, P, dS, dqkv, L, C, n, n_head, group, time_axis, total);
   TD_LAUNCH((att_bwd_dkv_kernel<D>), cdiv(total, 128), 128, 0, st, qkv, dctx, P, dS, dqkv, L, C, n, n_head, group, time_axis, total);
@@ -303,6 +339,13 @@ static int prepare_transposed(const BCtx& x) {
   return 0;
 }
 
+// weight gradient on the side stream `w`: it waits for everything the main stream has enqueued so far (its operands)
+// and is joined back at the end of the block (uconv_block_backward) before any operand buffer is reused
+static int wgrad_side(const BCtx& x, const float* G, const float* A, float* dW, float* db, int R, int N, int K) {
+  if (int e = x.side->order(x.st, x.side->w)) return e;
+  return launch_wgrad(G, A, dW, db, R, N, K, nullptr, x.side->w, x.c->gemm_mode);
+}
+
 // D[B, L, N] = A[B, L, K] . Wt[N, K]^T (+ resid)
 static int dgrad(const BCtx& x, const float* A, size_t wt, size_t aux, float* D, int L, int N, int K, const float* resid) {
   GemmArgs g{};
@@ -318,15 +361,17 @@ static int dgrad(const BCtx& x, const float* A, size_t wt, size_t aux, float* D,
 //   conv inputs (after their on-load transform), written or accumulated.
 static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdanet_la_t& gla, const SrcDesc& loc, int lkind,
                        const float* glo, int Lg, const NormRef& nL, const NormRef& nA, const NormRef& nE,
-                       const size_t bs[3], const float* dout, float* d_loc_in, int acc_loc, float* d_glo_in, int acc_glo) {
+                       const size_t bs[3], const float* dout, float* d_loc_in, int acc_loc, float* d_glo_in, int acc_glo,
+                       cudaStream_t local_st = nullptr) {
   const Plan& p = *x.p;
   const int B = p.B, C = x.c->in_channels, Ll = loc.L;
   LaBwdArgs a{};
   a.loc = loc; a.lkind = lkind; a.glo = glo; a.Lg = Lg; a.B = B; a.C = C;
   a.wl = la.local_embedding.w; a.wa = la.global_act.w; a.we = la.global_embedding.w;
   a.nL = nL; a.nA = nA; a.nE = nE; a.dout = dout; a.scale = nearest_scale(Lg, Ll);
-  a.d_loc = x.at(p.t_dloc); a.raw_a = x.at(p.t_rawa);
-  a.d_act = x.at(p.t_dact); a.d_emb = x.at(p.t_demb); a.raw_b = x.at(p.t_rawb); a.raw_e = x.at(p.t_rawe);
+  const int ts = x.tset;
+  a.d_loc = x.at(p.t_dloc[ts]); a.raw_a = x.at(p.t_rawa[ts]);
+  a.d_act = x.at(p.t_dact[ts]); a.d_emb = x.at(p.t_demb[ts]); a.raw_b = x.at(p.t_rawb[ts]); a.raw_e = x.at(p.t_rawe[ts]);
   a.dgamma[0] = x.gp(gla.local_embedding.gamma); a.dbeta[0] = x.gp(gla.local_embedding.beta);
   a.dgamma[1] = x.gp(gla.global_act.gamma); a.dbeta[1] = x.gp(gla.global_act.beta);
   a.dgamma[2] = x.gp(gla.global_embedding.gamma); a.dbeta[2] = x.gp(gla.global_embedding.beta);
@@ -338,7 +383,11 @@ static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdane
   d.w[0] = la.local_embedding.w; d.dw[0] = x.gp(gla.local_embedding.w);
   d.xin = loc; d.xkind = lkind; d.B = B; d.C = C; d.Lin = Ll; d.Lout = Ll; d.stride = 1;
   d.dx = d_loc_in; d.accumulate = acc_loc;
-  if (int e = launch_dw_bwd(x, d, ks, 1)) return e;
+  if (local_st && local_st != x.st) {
+    // the local branch only feeds loc_glo_fus: it runs on the side stream while x.st continues with the global branch
+    if (int e = x.side->order(x.st, local_st)) return e;
+    if (int e = launch_dw_bwd(x.on(local_st, x.tset), d, ks, 1)) return e;
+  } else if (int e = launch_dw_bwd(x, d, ks, 1)) return e;
   d = DwBwdArgs{};
   d.g[0] = gln_grad(a.d_act, a.raw_b, nA, a.S[1]);
   d.g[1] = gln_grad(a.d_emb, a.raw_e, nE, a.S[2]);
@@ -368,7 +417,7 @@ static int global_attention_backward(const BCtx& x) {
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_ga_out), x.at(p.fc2), n_fc2, x.at<double>(p.bs_fc2)),
                                      x.at(p.g_fc2), 0, B, Lb, C, x.st)) return e;
   }
-  { Tag t("wgrad_fc2"); if (int e = launch_wgrad(x.at(p.g_fc2), x.at(p.ffn_dw), x.gp(gw->fc2.w), nullptr, R, C, 2 * C, nullptr, x.st, x.c->gemm_mode)) return e; }
+  { Tag t("wgrad_fc2"); if (int e = wgrad_side(x, x.at(p.g_fc2), x.at(p.ffn_dw), x.gp(gw->fc2.w), nullptr, R, C, 2 * C)) return e; }
   { Tag t("dgrad_fc2"); if (int e = dgrad(x, x.at(p.g_fc2), p.wt_fc2, p.auxt_fc2, x.at(p.g_ffn), Lb, 2 * C, C, nullptr)) return e; }
   {
     // relu -> dwconv k5 (+bias) on gLN(fc1)
@@ -387,19 +436,19 @@ static int global_attention_backward(const BCtx& x) {
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_fc1), x.at(p.fc1), n_fc1, x.at<double>(p.bs_fc1)),
                                      x.at(p.g_ffn), 0, B, Lb, 2 * C, x.st)) return e;  // g_ffn is free again
   }
-  { Tag t("wgrad_fc1"); if (int e = launch_wgrad(x.at(p.g_ffn), x.at(p.ga_mid), x.gp(gw->fc1.w), nullptr, R, 2 * C, C, nullptr, x.st, x.c->gemm_mode)) return e; }
+  { Tag t("wgrad_fc1"); if (int e = wgrad_side(x, x.at(p.g_ffn), x.at(p.ga_mid), x.gp(gw->fc1.w), nullptr, R, 2 * C, C)) return e; }
   // g_ga_mid = g_ga_out (skip) + fc1 data gradient
   { Tag t("dgrad_fc1"); if (int e = dgrad(x, x.at(p.g_ffn), p.wt_fc1, p.auxt_fc1, x.at(p.g_ga_mid), Lb, C, 2 * C, x.at(p.g_ga_out))) return e; }
   // ga_mid = ga_in + LN2(2 * attn_out)
   { Tag t("bwd_bottom_misc");
     if (int e = launch_ln_bwd(x.at(p.attn_out), 2.f, w->ln2_w, x.at(p.g_ga_mid), x.at(p.ln_rows), nullptr,
                               x.at(p.g_attn_out), x.gp(gw->ln2_w), x.gp(gw->ln2_b), R, C, x.st)) return e; }
-  { Tag t("wgrad_out_proj"); if (int e = launch_wgrad(x.at(p.g_attn_out), x.at(p.attn_ctx), x.gp(gw->out_proj_w), x.gp(gw->out_proj_b), R, C, C, nullptr, x.st, x.c->gemm_mode)) return e; }
+  { Tag t("wgrad_out_proj"); if (int e = wgrad_side(x, x.at(p.g_attn_out), x.at(p.attn_ctx), x.gp(gw->out_proj_w), x.gp(gw->out_proj_b), R, C, C)) return e; }
   { Tag t("dgrad_out_proj"); if (int e = dgrad(x, x.at(p.g_attn_out), p.wt_out, p.auxt_out, x.at(p.g_ctx), Lb, C, C, nullptr)) return e; }
   { Tag t("bwd_attention");
     if (int e = launch_att_bwd(x.at(p.qkv), x.at(p.g_ctx), x.at(p.att_p), x.at(p.att_ds), x.at(p.g_qkv), B, Lb, C,
                                c->n_head, group, 0, x.st)) return e; }
-  { Tag t("wgrad_in_proj"); if (int e = launch_wgrad(x.at(p.g_qkv), x.at(p.attn_in), x.gp(gw->in_proj_w), x.gp(gw->in_proj_b), R, 3 * C, C, nullptr, x.st, x.c->gemm_mode)) return e; }
+  { Tag t("wgrad_in_proj"); if (int e = wgrad_side(x, x.at(p.g_qkv), x.at(p.attn_in), x.gp(gw->in_proj_w), x.gp(gw->in_proj_b), R, 3 * C, C)) return e; }
   { Tag t("dgrad_in_proj"); if (int e = dgrad(x, x.at(p.g_qkv), p.wt_in, p.auxt_in, x.at(p.g_attn_in), Lb, C, 3 * C, nullptr)) return e; }
   // attn_in = LN1(ga_in) + pe;  g_ga_in = g_ga_mid (skip) + LN1 backward
   Tag t("bwd_bottom_misc");
@@ -421,44 +470,62 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
     return norm_ref(x, p.st_spp[k], 2, (double)p.L[k] * C, w->spp_dw[k].gamma, w->spp_dw[k].beta);
   };
   // ---- res_conv
-  { Tag t("wgrad_res_conv"); if (int e = launch_wgrad(d_y, x.at(p.expanded[0]), x.gp(gw->res_w), x.gp(gw->res_b), R0, cc, C, nullptr, x.st, x.c->gemm_mode)) return e; }
+  { Tag t("wgrad_res_conv"); if (int e = wgrad_side(x, d_y, x.at(p.expanded[0]), x.gp(gw->res_w), x.gp(gw->res_b), R0, cc, C)) return e; }
   { Tag t("dgrad_res_conv"); if (int e = dgrad(x, d_y, p.wt_res, p.auxt_res, x.at(p.g_exp[0]), L0, C, cc, nullptr)) return e; }
-  // ---- top-down fusion, in the reverse of the forward order
+  // ---- top-down fusion, in the reverse of the forward order.  Main stream: passes G/L/F and the global-branch
+  // depthwise backward of every step (the chain g_exp[i] -> g_exp[i+1]).  Side stream `l`: the local-branch depthwise
+  // backward of step i (-> g_fused[i]) followed by loc_glo_fus[i] backwards (-> g_spp[i], g_ga_out).
+  cudaStream_t sl = x.side->l;
+  const int gi = first_step_partner(depth);  // x_fused[gi] also receives the first step's global-branch gradient
   bool fused_written[TDANET_MAX_DEPTH] = {};
+  bool spp_written[TDANET_MAX_DEPTH] = {};
+  bool ga_out_written = false;
+  cudaEvent_t local_done[TDANET_MAX_DEPTH] = {};
+  // loc_glo_fus[k] (1-tap LA): x_fused[k] = LA(gLN(spp_k), ga_out); runs on `sl` with temporary set 2
+  auto lgf_backward = [&](int k) -> int {
+    const tdanet_la_t& la = w->loc_glo_fus[k];
+    const NormRef nL = norm_ref(x, p.st_lgf[k], 6, (double)p.L[k] * C, la.local_embedding.gamma, la.local_embedding.beta);
+    const NormRef nA = norm_ref(x, p.st_lgf[k] + 2 * sizeof(double), 6, (double)Lb * C, la.global_act.gamma, la.global_act.beta);
+    const NormRef nE = norm_ref(x, p.st_lgf[k] + 4 * sizeof(double), 6, (double)Lb * C, la.global_embedding.gamma, la.global_embedding.beta);
+    if (int e = la_backward(x.on(sl, 2), 1, la, gw->loc_glo_fus[k], baffine(x.at(p.spp[k]), p.L[k], spp_norm(k)), SRC_AFFINE,
+                            x.at(p.ga_out), Lb, nL, nA, nE, p.bs_lgf[k], x.at(p.g_fused[k]), x.at(p.g_spp[k]), 0,
+                            x.at(p.g_ga_out), ga_out_written)) return e;
+    spp_written[k] = true;
+    ga_out_written = true;
+    return 0;
+  };
   for (int i = 0; i <= depth - 2; ++i) {
     const tdanet_la_t& la = w->last_layer[i];
-    const bool first = i == depth - 2;  // the first forward step: its "global" input is x_fused[partner]
-    const int gi = first ? first_step_partner(depth) : -1;
+    const bool first = i == depth - 2;  // the first forward step: its "global" input is x_fused[gi]
     const int Lg = first ? p.L[gi] : p.L[i + 1];
     const float* glo = first ? x.at(p.fused[gi]) : x.at(p.expanded[i + 1]);
     const NormRef nL = norm_ref(x, p.st_la_l[i], 2, (double)p.L[i] * C, la.local_embedding.gamma, la.local_embedding.beta);
     const NormRef nA = norm_ref(x, p.st_la_g[i], 4, (double)Lg * C, la.global_act.gamma, la.global_act.beta);
     const NormRef nE = norm_ref(x, p.st_la_g[i] + 2 * sizeof(double), 4, (double)Lg * C, la.global_embedding.gamma, la.global_embedding.beta);
     float* d_glo = first ? x.at(p.g_fused[gi]) : x.at(p.g_exp[i + 1]);
-    // x_fused[i] may already hold the gradient it received as the partner of the first step (depth == 2 only)
-    const int acc_loc = fused_written[i];
-    if (int e = la_backward(x, 5, la, gw->last_layer[i], bplain(x.at(p.fused[i]), p.L[i]), SRC_PLAIN, glo, Lg, nL, nA, nE,
-                            p.bs_la[i], x.at(p.g_exp[i]), x.at(p.g_fused[i]), acc_loc, d_glo,
-                            first ? (int)fused_written[gi] : 0)) return e;
+    // this step's passes overwrite temporary set i % 2: the local branch of step i - 2 must have read it
+    if (i >= 2) TD_CUDA(cudaStreamWaitEvent(x.st, local_done[i - 2], 0));
+    // the first step adds into g_fused[gi], which the side stream wrote in step gi
+    if (first && fused_written[gi]) TD_CUDA(cudaStreamWaitEvent(x.st, local_done[gi], 0));
+    if (int e = la_backward(x.on(x.st, i & 1), 5, la, gw->last_layer[i], bplain(x.at(p.fused[i]), p.L[i]), SRC_PLAIN, glo, Lg,
+                            nL, nA, nE, p.bs_la[i], x.at(p.g_exp[i]), x.at(p.g_fused[i]), fused_written[i], d_glo,
+                            first ? (int)fused_written[gi] : 0, sl)) return e;
     fused_written[i] = true;
     if (first) fused_written[gi] = true;
+    local_done[i] = x.side->events[x.side->next++ % x.side->events.size()];
+    TD_CUDA(cudaEventRecord(local_done[i], sl));
+    // x_fused[i] is complete unless it still waits for the first step's global-branch gradient
+    if (i != gi || first) {
+      if (int e = lgf_backward(i)) return e;
+    }
   }
-  // ---- loc_glo_fus[k] (1-tap LA): x_fused[k] = LA(gLN(spp_k), ga_out)
-  bool spp_written[TDANET_MAX_DEPTH] = {};
-  bool ga_out_written = false;
-  for (int k = 0; k < depth; ++k) {
-    if (!fused_written[k]) continue;
-    const tdanet_la_t& la = w->loc_glo_fus[k];
-    const NormRef nL = norm_ref(x, p.st_lgf[k], 6, (double)p.L[k] * C, la.local_embedding.gamma, la.local_embedding.beta);
-    const NormRef nA = norm_ref(x, p.st_lgf[k] + 2 * sizeof(double), 6, (double)Lb * C, la.global_act.gamma, la.global_act.beta);
-    const NormRef nE = norm_ref(x, p.st_lgf[k] + 4 * sizeof(double), 6, (double)Lb * C, la.global_embedding.gamma, la.global_embedding.beta);
-    if (int e = la_backward(x, 1, la, gw->loc_glo_fus[k], baffine(x.at(p.spp[k]), p.L[k], spp_norm(k)), SRC_AFFINE,
-                            x.at(p.ga_out), Lb, nL, nA, nE, p.bs_lgf[k], x.at(p.g_fused[k]), x.at(p.g_spp[k]), 0,
-                            x.at(p.g_ga_out), ga_out_written)) return e;
-    spp_written[k] = true;
-    ga_out_written = true;
+  if (gi != depth - 2 && fused_written[gi]) {
+    // deferred: x_fused[gi] got its second contribution from the main stream in the last iteration
+    if (int e = x.side->order(x.st, sl)) return e;
+    if (int e = lgf_backward(gi)) return e;
   }
   TD_REQUIRE(ga_out_written, "no live x_fused tensor");
+  if (int e = x.side->order(sl, x.st)) return e;  // g_spp[*], g_ga_out
   // ---- bottom-scale block
   if (int e = global_attention_backward(x)) return e;
   // ---- ga_in = sum_k avgpool(gLN(spp_k))
@@ -495,10 +562,12 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
                                      x.at<double>(p.bs_proj), B, L0, C, x.st)) return e; }
   { Tag t("bwd_gln_apply");
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_proj), x.at(p.proj), n_proj, x.at<double>(p.bs_proj)),
-                                     x.at(p.t_dloc), 0, B, L0, C, x.st)) return e; }  // LA temporaries are free by now
-  { Tag t("wgrad_proj"); if (int e = launch_wgrad(x.at(p.t_dloc), in, x.gp(gw->proj.w), x.gp(gw->proj.b), R0, C, cc, nullptr, x.st, x.c->gemm_mode)) return e; }
+                                     x.at(p.t_dloc[0]), 0, B, L0, C, x.st)) return e; }  // LA temporaries are free by now
+  { Tag t("wgrad_proj"); if (int e = wgrad_side(x, x.at(p.t_dloc[0]), in, x.gp(gw->proj.w), x.gp(gw->proj.b), R0, C, cc)) return e; }
   Tag t("dgrad_proj");
-  return dgrad(x, x.at(p.t_dloc), p.wt_proj, p.auxt_proj, d_in, L0, cc, C, d_y);
+  if (int e = dgrad(x, x.at(p.t_dloc[0]), p.wt_proj, p.auxt_proj, d_in, L0, cc, C, d_y)) return e;
+  // the weight-gradient GEMMs of this block must be done before the next block (or the caller) reuses their operands
+  return x.side->order(x.side->w, x.st);
 }
 
 static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const tdanet_weights_t* gw, const float* wav,
@@ -510,6 +579,12 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
   BCtx x{};
   std::vector<RepEntry> reps;
   x.c = c; x.w = w; x.p = &p; x.ws = (char*)workspace; x.st = st; x.blk = 0; x.g = gw; x.reps = &reps;
+  int dev = 0;
+  TD_CUDA(cudaGetDevice(&dev));
+  TD_REQUIRE(dev >= 0 && dev < 16, "device %d", dev);
+  x.side = &g_side[dev];
+  x.main_st = st;
+  if (int e = x.side->init()) return e;
   TD_CUDA(cudaMemsetAsync(x.at<char>(p.rep_arena), 0, p.rep_floats * TDANET_DW_REPLICAS * sizeof(float), st));
   const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
   const int NS = c->num_sources, CI = NS * Nb, R0 = B * L0, nb = c->num_blocks;
@@ -520,8 +595,14 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
   {
     Tag t("bwd_backend");
     // decoder ConvTranspose1d + crop
-    const size_t n = (size_t)R0 * CI;
-    TD_LAUNCH(dec_bwd_data_kernel, (unsigned)((n + 127) / 128), 128, 0, st, d_est, w->dec_w, x.at(p.g_masked), B, L0, CI, NS, K, S, T, K - S);
+    const int wpad = NS * K + 1;  // odd row stride: conflict-free weight reads
+    if ((size_t)NS * ((DEC_FR - 1) * S + K) + (size_t)CI * wpad <= 11264) {
+      dim3 dgrid(cdiv(L0, DEC_FR), B);
+      TD_LAUNCH_COOP(dec_bwd_data_kernel, dgrid, 256, 0, st, d_est, w->dec_w, x.at(p.g_masked), B, L0, CI, NS, K, S, T, K - S, wpad);
+    } else {
+      const size_t n = (size_t)R0 * CI;
+      TD_LAUNCH(dec_bwd_data_naive_kernel, (unsigned)((n + 127) / 128), 128, 0, st, d_est, w->dec_w, x.at(p.g_masked), B, L0, CI, NS, K, S, T, K - S);
+    }
     if (int e = launch_framed_wgrad(x.at(p.masked), d_est, x.gp(gw->dec_w), B, L0, CI, NS, K, S, T, K - S, st)) return e;
     // masked = relu(m) * enc
     const size_t ne = (size_t)R0 * Nb;

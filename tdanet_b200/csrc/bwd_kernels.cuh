@@ -458,11 +458,11 @@ __device__ __forceinline__ int first_local_row(int j, float scale, int Ll, int L
   return t;
 }
 
-// Three regular streaming passes (each thread: 4 channels, tiles of 4 rows, all loads of a tile issued together):
+// Two regular streaming passes (each thread: 4 channels, tiles of 4 rows, all loads of a tile issued together):
 //   G  over the global rows : raw_b = dw_a(xg), raw_e = dw_e(xg)
-//   L  over the local rows  : raw_a = dw_l(xl), d_loc = dout * gate[j], GlobLN_L sums, and per centre j the sums
-//                             d_act[j] <- sum dout*loc (before the sigmoid derivative), d_emb[j] <- sum dout
-//   F  over the global rows : d_act *= gate*(1-gate), GlobLN_A / GlobLN_E sums
+//   L  over the local rows  : raw_a = dw_l(xl), d_loc = dout * gate[j], GlobLN_L sums; a thread owns whole centres,
+//                             so when it leaves centre j it writes d_act[j] = (sum dout*loc) * gate*(1-gate),
+//                             d_emb[j] = sum dout and adds them to the GlobLN_A / GlobLN_E sums
 template <int KS>
 __global__ void la_bwd_g_kernel(LaBwdArgs a, int rows_per_thread) {
   constexpr int V = 4, PAD = (KS - 1) / 2, R = 4, W = R + 2 * PAD;
@@ -521,7 +521,7 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const bool active = ch < a.C;
-  double S1 = 0.0, S2 = 0.0;
+  double S[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
   if (active) {
     const int Ll = a.loc.L, Lg = a.Lg, C = a.C;
     const int j0 = blockIdx.x * a.jchunk, j1 = min(j0 + a.jchunk, Lg);
@@ -534,9 +534,11 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
     vf<V> scL, shL, scA, shA;
     norm_coef<V>(a.nL, b, ch, scL, shL);
     norm_coef<V>(a.nA, b, ch, scA, shA);
-    float rL, murL;
+    float rL, murL, rA, murA, rE, murE;
     norm_moments(a.nL, b, rL, murL);
-    const vf<V> gL = vload<V>(a.nL.gamma + ch);
+    norm_moments(a.nA, b, rA, murA);
+    norm_moments(a.nE, b, rE, murE);
+    const vf<V> gL = vload<V>(a.nL.gamma + ch), gA = vload<V>(a.nA.gamma + ch), gE = vload<V>(a.nE.gamma + ch);
     FwdLoad<V> fl;
     fl.init(a.loc, a.lkind, b, ch, C);
     const float* dop = a.dout + (size_t)b * Ll * C + ch;
@@ -544,10 +546,12 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
     float* rap = a.raw_a + (size_t)b * Ll * C + ch;
     const size_t goff = (size_t)b * Lg * C + ch;
     const float* rbp = a.raw_b + goff;
+    const float* rep_ = a.raw_e + goff;
     // zero padding applies to the conv input, i.e. after the on-load transform
     auto loadx = [&](int row) { return fl.load_row(row, Ll, C); };
     vf<V> dg = vzero<V>(), db = vzero<V>(), sum_e = vzero<V>(), sum_a = vzero<V>();
-    float s1 = 0.f, s2 = 0.f;
+    vf<V> dgA = vzero<V>(), dbA = vzero<V>(), dgE = vzero<V>(), dbE = vzero<V>();
+    float s1 = 0.f, s2 = 0.f, s1A = 0.f, s2A = 0.f, s1E = 0.f, s2E = 0.f;
     // centres of this chunk that no local row maps to (down-sampling step) get zero sums
     auto zero_centres = [&](int ja, int jb) {
       for (int j = ja; j < jb; ++j) {
@@ -563,7 +567,7 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
 #pragma unroll
       for (int j = 0; j < 2 * PAD; ++j) X[j] = loadx(t_begin - PAD + j);
       for (int t = t_begin; t < t_end; t += R) {
-        vf<V> D[R], Bt[R];
+        vf<V> D[R], Bt[R], Et[R];
         int jr[R + 1];
 #pragma unroll
         for (int j = 2 * PAD; j < W; ++j) X[j] = loadx(t - PAD + j);
@@ -575,11 +579,12 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
           const int jc = jr[r] < Lg ? jr[r] : Lg - 1;
           D[r] = vload<V>(dop + (size_t)tr * C);
           Bt[r] = vload_rw<V>(rbp + (size_t)jc * C);
+          Et[r] = vload_rw<V>(rep_ + (size_t)jc * C);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (t + r < t_end) {
-            vf<V> A = vzero<V>(), dl;
+            vf<V> A = vzero<V>(), dl, gate4;
 #pragma unroll
             for (int k = 0; k < KS; ++k)
 #pragma unroll
@@ -587,6 +592,7 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
 #pragma unroll
             for (int e = 0; e < V; ++e) {
               const float gate = sigmoidf_(fmaf(Bt[r][e], scA[e], shA[e]));
+              gate4[e] = gate;
               const float loc = fmaf(A[e], scL[e], shL[e]);
               sum_e[e] += D[r][e];
               sum_a[e] = fmaf(D[r][e], loc, sum_a[e]);
@@ -600,8 +606,24 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
             }
             vstore<V>(dlp + (size_t)(t + r) * C, dl);
             vstore<V>(rap + (size_t)(t + r) * C, A);
-            if (jr[r + 1] != jr[r]) {  // last local row of centre jr[r]
-              vstore<V>(a.d_act + goff + (size_t)jr[r] * C, sum_a);
+            if (jr[r + 1] != jr[r]) {  // last local row of centre jr[r]: its sums are complete
+              vf<V> da;
+#pragma unroll
+              for (int e = 0; e < V; ++e) {
+                da[e] = sum_a[e] * gate4[e] * (1.f - gate4[e]);  // through the sigmoid
+                const float bh = fmaf(Bt[r][e], rA, -murA), eh = fmaf(Et[r][e], rE, -murE);
+                dgA[e] = fmaf(da[e], bh, dgA[e]);
+                dbA[e] += da[e];
+                const float ga = gA[e] * da[e];
+                s1A += ga;
+                s2A = fmaf(ga, bh, s2A);
+                dgE[e] = fmaf(sum_e[e], eh, dgE[e]);
+                dbE[e] += sum_e[e];
+                const float ge = gE[e] * sum_e[e];
+                s1E += ge;
+                s2E = fmaf(ge, eh, s2E);
+              }
+              vstore<V>(a.d_act + goff + (size_t)jr[r] * C, da);
               vstore<V>(a.d_emb + goff + (size_t)jr[r] * C, sum_e);
               sum_a = vzero<V>();
               sum_e = vzero<V>();
@@ -615,76 +637,14 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
     }
     vred_add<V>(a.dgamma[0] + ch, dg);
     vred_add<V>(a.dbeta[0] + ch, db);
-    S1 = s1;
-    S2 = s2;
-  }
-  block_accum2(a.S[0] + 2 * b, S1, S2);
-}
-
-__global__ void la_bwd_f_kernel(LaBwdArgs a, int rows_per_thread) {
-  constexpr int V = 4, R = 4;
-  const int b = blockIdx.z;
-  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
-  const bool active = ch < a.C;
-  double s[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  if (active) {
-    const int Lg = a.Lg, C = a.C;
-    const int j0 = blockIdx.x * rows_per_thread, j1 = min(j0 + rows_per_thread, Lg);
-    vf<V> scA, shA;
-    norm_coef<V>(a.nA, b, ch, scA, shA);
-    float rA, murA, rE, murE;
-    norm_moments(a.nA, b, rA, murA);
-    norm_moments(a.nE, b, rE, murE);
-    const vf<V> gA = vload<V>(a.nA.gamma + ch), gE = vload<V>(a.nE.gamma + ch);
-    const size_t goff = (size_t)b * Lg * C + ch;
-    vf<V> dg[2], db[2];
-    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { dg[i] = vzero<V>(); db[i] = vzero<V>(); }
-    for (int t = j0; t < j1; t += R) {
-      vf<V> SA[R], SE[R], Bt[R], Et[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {  // unconditional, clamped (rows past j1 are not used)
-        const size_t off = goff + (size_t)(t + r < Lg ? t + r : Lg - 1) * C;
-        SA[r] = vload_rw<V>(a.d_act + off);
-        SE[r] = vload_rw<V>(a.d_emb + off);
-        Bt[r] = vload_rw<V>(a.raw_b + off);
-        Et[r] = vload_rw<V>(a.raw_e + off);
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (t + r < j1) {
-          vf<V> da;
-#pragma unroll
-          for (int e = 0; e < V; ++e) {
-            const float gate = sigmoidf_(fmaf(Bt[r][e], scA[e], shA[e]));
-            da[e] = SA[r][e] * gate * (1.f - gate);
-            const float bh = fmaf(Bt[r][e], rA, -murA), eh = fmaf(Et[r][e], rE, -murE);
-            dg[0][e] = fmaf(da[e], bh, dg[0][e]);
-            db[0][e] += da[e];
-            const float ga = gA[e] * da[e];
-            s1[0] += ga;
-            s2[0] = fmaf(ga, bh, s2[0]);
-            dg[1][e] = fmaf(SE[r][e], eh, dg[1][e]);
-            db[1][e] += SE[r][e];
-            const float ge = gE[e] * SE[r][e];
-            s1[1] += ge;
-            s2[1] = fmaf(ge, eh, s2[1]);
-          }
-          vstore<V>(a.d_act + goff + (size_t)(t + r) * C, da);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      vred_add<V>(a.dgamma[1 + i] + ch, dg[i]);
-      vred_add<V>(a.dbeta[1 + i] + ch, db[i]);
-      s[i][0] = s1[i];
-      s[i][1] = s2[i];
-    }
+    vred_add<V>(a.dgamma[1] + ch, dgA);
+    vred_add<V>(a.dbeta[1] + ch, dbA);
+    vred_add<V>(a.dgamma[2] + ch, dgE);
+    vred_add<V>(a.dbeta[2] + ch, dbE);
+    S[0][0] = s1; S[0][1] = s2; S[1][0] = s1A; S[1][1] = s2A; S[2][0] = s1E; S[2][1] = s2E;
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) block_accum2(a.S[1 + i] + 2 * b, s[i][0], s[i][1]);
+  for (int i = 0; i < 3; ++i) block_accum2(a.S[i] + 2 * b, S[i][0], S[i][1]);
 }
 
 // ----------------------------------------------------------------------------- pooling backward
@@ -915,6 +875,101 @@ __global__ void att_bwd_dkv_kernel(const float* __restrict__ qkv, const float* _
   }
 }
 
+// One warp per (problem, head) for short sequences (n <= NMAX; training attends over the batch axis, n = 8):
+// lanes split the head dimension, q / k / v / dO of the problem live in registers, scores and dP are warp
+// reductions, so nothing goes through a scratch buffer and every global load is issued up front.
+template <int D, int NMAX>
+__global__ void att_bwd_warp_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
+                                    float* __restrict__ dqkv, int L, int C, int n, int n_head, int group,
+                                    int time_axis, int total_warps) {
+  constexpr int EPL = D >= 32 ? D / 32 : 1;  // head-dim elements per lane
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= total_warps) return;
+  const int head = wid % n_head, prob = wid / n_head;
+  long base, stride;
+  att_problem(prob, L, group, time_axis, base, stride);
+  const bool lane_ok = lane * EPL < D;
+  const float scale = rsqrtf((float)D);
+  const size_t C3 = (size_t)3 * C;
+  float q[NMAX][EPL], k[NMAX][EPL], v[NMAX][EPL], dO[NMAX][EPL];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    const bool ok = i < n && lane_ok;
+    const size_t tok = (size_t)(base + (long)(i < n ? i : 0) * stride);
+    const float* p = qkv + tok * C3 + head * D + (lane_ok ? lane * EPL : 0);
+    const float* dp = dctx + tok * C + head * D + (lane_ok ? lane * EPL : 0);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const float qv = p[e], kv = p[C + e], vv = p[2 * C + e], dv = dp[e];
+      q[i][e] = ok ? qv * scale : 0.f;
+      k[i][e] = ok ? kv : 0.f;
+      v[i][e] = ok ? vv : 0.f;
+      dO[i][e] = ok ? dv : 0.f;
+    }
+  }
+  float dq[NMAX][EPL], dk[NMAX][EPL], dvv[NMAX][EPL];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i)
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) { dq[i][e] = 0.f; dk[i][e] = 0.f; dvv[i][e] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {  // uniform across the warp
+      float s[NMAX], dp[NMAX];
+      float m = -3.4e38f;
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j) {
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          a1 = fmaf(q[i][e], k[j][e], a1);
+          a2 = fmaf(dO[i][e], v[j][e], a2);
+        }
+        s[j] = warp_sum(a1);
+        dp[j] = warp_sum(a2);
+        if (j < n) m = fmaxf(m, s[j]);
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j) {
+        s[j] = j < n ? expf(s[j] - m) : 0.f;
+        l += s[j];
+      }
+      const float inv = 1.f / l;
+      float dsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j) {
+        s[j] *= inv;  // P[i][j]
+        dsum = fmaf(s[j], dp[j], dsum);
+      }
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j) {
+        const float ds = s[j] * (dp[j] - dsum);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          dq[i][e] = fmaf(ds, k[j][e], dq[i][e]);    // d s_ij / d q_i (scaled q): k_j
+          dk[j][e] = fmaf(ds, q[i][e], dk[j][e]);    // q already carries the 1/sqrt(D)
+          dvv[j][e] = fmaf(s[j], dO[i][e], dvv[j][e]);
+        }
+      }
+    }
+  }
+  if (!lane_ok) return;
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      float* o = dqkv + (size_t)(base + (long)i * stride) * C3 + head * D + lane * EPL;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        o[e] = dq[i][e] * scale;
+        o[C + e] = dk[i][e];
+        o[2 * C + e] = dvv[i][e];
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- weight gradients of 1x1 convs
 // dW[n, k] += sum_r G[r, n] * f(A[r, k]),  f = PReLU(*a_slope) or identity.  64x64 tile per CTA, rows split
 // over blockIdx.z, fp32 FMA, atomics into dW.
@@ -1112,9 +1167,10 @@ __device__ __forceinline__ float framed_sig(const float* __restrict__ sig, int n
 
 // decoder ConvTranspose1d backward w.r.t. its input:
 //   dM[b, l, ci] = sum_o sum_j dfull[b, o, l*S + j - K/2] * W[ci, o, j]
-__global__ void dec_bwd_data_kernel(const float* __restrict__ dest, const float* __restrict__ w,
-                                    float* __restrict__ dM, int B, int L0, int CI, int NO, int K, int S, int T,
-                                    int shift) {
+// fallback for configurations whose weights do not fit the shared-memory kernel below: one thread per output
+__global__ void dec_bwd_data_naive_kernel(const float* __restrict__ dest, const float* __restrict__ w,
+                                          float* __restrict__ dM, int B, int L0, int CI, int NO, int K, int S, int T,
+                                          int shift) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * L0 * CI) return;
   const int ci = (int)(idx % CI);
@@ -1127,6 +1183,36 @@ __global__ void dec_bwd_data_kernel(const float* __restrict__ dest, const float*
     for (int j = 0; j < K; ++j) acc = fmaf(framed_sig(sp, l * S + j - K / 2, shift, T), __ldg(wp + j), acc);
   }
   dM[idx] = acc;
+}
+
+constexpr int DEC_FR = 32;  // frames per CTA
+__global__ void __launch_bounds__(256) dec_bwd_data_kernel(const float* __restrict__ dest, const float* __restrict__ w,
+                                                           float* __restrict__ dM, int B, int L0, int CI, int NO, int K,
+                                                           int S, int T, int shift, int wpad) {
+  // shared: the signal window of DEC_FR frames for every output channel, and the weights [CI][NO*K (+pad)]
+  __shared__ float sh[11264];
+  const int span = (DEC_FR - 1) * S + K;
+  float* sig = sh;              // [NO][span]
+  float* ws = sh + NO * span;   // [CI][wpad]
+  const int b = blockIdx.y, l0 = blockIdx.x * DEC_FR;
+  const int NK = NO * K;
+  for (int i = threadIdx.x; i < NO * span; i += blockDim.x) {
+    const int o = i / span, n = l0 * S - K / 2 + i % span;
+    sig[i] = framed_sig(dest + ((size_t)b * NO + o) * T, n, shift, T);
+  }
+  for (int i = threadIdx.x; i < CI * NK; i += blockDim.x) ws[(i / NK) * wpad + i % NK] = __ldg(w + i);
+  __syncthreads();
+  const int frames = min(DEC_FR, L0 - l0);
+  for (int idx = threadIdx.x; idx < frames * CI; idx += blockDim.x) {
+    const int f = idx / CI, ci = idx % CI;
+    const float* wr = ws + ci * wpad;
+    float acc = 0.f;
+    for (int o = 0; o < NO; ++o) {
+      const float* sp = sig + o * span + f * S;
+      for (int j = 0; j < K; ++j) acc = fmaf(sp[j], wr[o * K + j], acc);
+    }
+    dM[((size_t)b * L0 + l0 + f) * CI + ci] = acc;
+  }
 }
 
 // dW[ci, o, j] += sum_{b, l} M[b, l, ci] * sig_full[b, o, l*S + j - K/2]

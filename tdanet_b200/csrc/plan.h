@@ -60,7 +60,9 @@ struct Plan {
   // gradient arena
   size_t g_masked, g_enc, g_x0, g_u[2], g_proj, g_spp[TDANET_MAX_DEPTH], g_fused[TDANET_MAX_DEPTH],
       g_exp[TDANET_MAX_DEPTH];
-  size_t t_dloc, t_rawa, t_dact, t_demb, t_rawb, t_rawe;  // LA backward temporaries
+  // LA backward temporaries, TDANET_LA_TEMP_SETS sets: the top-down steps alternate between sets 0 / 1 so that the
+  // local-branch kernels of step i (side stream) overlap step i+1; the loc_glo_fus chain (side stream) owns set 2
+  size_t t_dloc[3], t_rawa[3], t_dact[3], t_demb[3], t_rawb[3], t_rawe[3];
   size_t g_ga_out, g_fc2, g_ffn, g_fc1, g_ga_mid, g_attn_out, g_ctx, g_qkv, g_attn_in, g_ga_in;
   size_t att_p, att_ds, ln_rows;
   // replicated accumulators of the depthwise weight / bias gradients: [REP_COUNT][rep_floats]
@@ -279,12 +281,14 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     const int Lg = i == depth - 2 ? p.L[first_step_partner(depth)] : p.L[i + 1];
     Lg_max = Lg > Lg_max ? Lg : Lg_max;
   }
-  p.t_dloc = p.act("t_dloc", L0, C);
-  p.t_rawa = p.act("t_rawa", L0, C);
-  p.t_dact = p.act("t_dact", Lg_max, C);
-  p.t_demb = p.act("t_demb", Lg_max, C);
-  p.t_rawb = p.act("t_rawb", Lg_max, C);
-  p.t_rawe = p.act("t_rawe", Lg_max, C);
+  for (int s = 0; s < 3; ++s) {
+    p.t_dloc[s] = p.act(nullptr, L0, C);
+    p.t_rawa[s] = p.act(nullptr, L0, C);
+    p.t_dact[s] = p.act(nullptr, Lg_max, C);
+    p.t_demb[s] = p.act(nullptr, Lg_max, C);
+    p.t_rawb[s] = p.act(nullptr, Lg_max, C);
+    p.t_rawe[s] = p.act(nullptr, Lg_max, C);
+  }
   p.g_ga_out = p.act("g_ga_out", Lb, C);
   p.g_fc2 = p.act("g_fc2", Lb, C);
   p.g_ffn = p.act("g_ffn", Lb, 2 * C);

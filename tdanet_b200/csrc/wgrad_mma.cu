@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const float* __restrict_
 int launch_wgrad_mma(const float* G, const float* A, float* dW, float* db, int R, int N, int K, cudaStream_t st) {
   TD_REQUIRE(N % 4 == 0 && K % 4 == 0, "wgrad_mma: N=%d K=%d must be multiples of 4", N, K);
   const int tiles = cdiv(N, WM_T) * cdiv(K, WM_T);
-  int splits = cdiv(2 * 148, tiles);
+  int splits = cdiv(4 * 148, tiles);  // ~4 CTAs per SM: the row loop of a CTA is a serial chain of global-load latencies
   int rps = cdiv(cdiv(R, splits), WM_R) * WM_R;
   splits = cdiv(R, rps);
   dim3 grid(cdiv(N, WM_T), cdiv(K, WM_T), splits);
