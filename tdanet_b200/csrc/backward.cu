@@ -175,12 +175,14 @@ static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
   dim3 grid;
   int threads;
   row_grid(a.Lout, a.C / 4, a.B, a.rows_per_thread, grid, threads);
+  const bool extra = a.xkind == SRC_AFFINE_PRELU || a.up_S || a.pool_g || a.dslope;
   const int key = ks * 100 + nw * 10 + a.stride;
-  if (key == 511) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1>), grid, threads, 0, st, a);
-  else if (key == 512) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 2>), grid, threads, 0, st, a);
-  else if (key == 521) TD_LAUNCH_RED((dw_bwd_kernel<5, 2, 1>), grid, threads, 0, st, a);
-  else if (key == 111) TD_LAUNCH_RED((dw_bwd_kernel<1, 1, 1>), grid, threads, 0, st, a);
-  else if (key == 121) TD_LAUNCH_RED((dw_bwd_kernel<1, 2, 1>), grid, threads, 0, st, a);
+  if (key == 511 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, false>), grid, threads, 0, st, a);
+  else if (key == 511) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, true>), grid, threads, 0, st, a);
+  else if (key == 512) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 2, true>), grid, threads, 0, st, a);
+  else if (key == 521 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 2, 1, false>), grid, threads, 0, st, a);
+  else if (key == 111 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<1, 1, 1, false>), grid, threads, 0, st, a);
+  else if (key == 121 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<1, 2, 1, false>), grid, threads, 0, st, a);
   else return fail(TDANET_EINVAL, "dw_bwd: ks=%d nw=%d", ks, nw);
   return 0;
 }
@@ -427,12 +429,12 @@ static int global_attention_backward(const BCtx& x) {
     d.w[0] = w->ffn_dw_w; d.dw[0] = x.gp(gw->ffn_dw_w); d.db[0] = x.gp(gw->ffn_dw_b);
     d.xin = baffine(x.at(p.fc1), Lb, n_fc1); d.xkind = SRC_AFFINE;
     d.B = B; d.C = 2 * C; d.Lin = Lb; d.Lout = Lb; d.stride = 1; d.dx = x.at(p.g_fc1);
+    // sole producer of g_fc1: accumulates the backward sums of the fc1 GlobLN as well
+    d.up_dgamma = x.gp(gw->fc1.gamma); d.up_dbeta = x.gp(gw->fc1.beta); d.up_S = x.at<double>(p.bs_fc1);
     if (int e = launch_dw_bwd(x, d, 5, 1)) return e;
   }
   {
     Tag t("bwd_bottom_misc");
-    if (int e = launch_gln_bwd_stats(x.at(p.g_fc1), x.at(p.fc1), n_fc1, x.gp(gw->fc1.gamma), x.gp(gw->fc1.beta),
-                                     x.at<double>(p.bs_fc1), B, Lb, 2 * C, x.st)) return e;
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_fc1), x.at(p.fc1), n_fc1, x.at<double>(p.bs_fc1)),
                                      x.at(p.g_ffn), 0, B, Lb, 2 * C, x.st)) return e;  // g_ffn is free again
   }
@@ -528,38 +530,45 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
   if (int e = x.side->order(sl, x.st)) return e;  // g_spp[*], g_ga_out
   // ---- bottom-scale block
   if (int e = global_attention_backward(x)) return e;
-  // ---- ga_in = sum_k avgpool(gLN(spp_k))
+  // ---- ga_in = sum_k avgpool(gLN(spp_k)): the coarsest scale (identity bins) here, the others inside the spp_dw
+  // backward that completes g_spp[k]
   {
     Tag t("bwd_pool");
-    for (int k = 0; k < depth; ++k)
-      if (int e = launch_pool_bwd(x.at(p.g_ga_in), x.at(p.g_spp[k]), spp_written[k], B, p.L[k], Lb, C, x.st)) return e;
+    const int k = depth - 1;
+    if (int e = launch_pool_bwd(x.at(p.g_ga_in), x.at(p.g_spp[k]), spp_written[k], B, p.L[k], Lb, C, x.st)) return e;
   }
-  // ---- spp_dw chain
+  // ---- spp_dw chain.  The depthwise backward of spp_dw[k] is the last launch that adds to g_spp[k-1] (k = 0: the only
+  // one that writes g_proj), so it also accumulates the backward sums of that GlobLN; only the coarsest scale, whose
+  // gradient is completed by the pooling backward, needs a statistics launch of its own.
+  const NormRef n_proj = norm_ref(x, p.st_proj, 2, (double)L0 * C, w->proj.gamma, w->proj.beta);
   for (int k = depth - 1; k >= 0; --k) {
     const NormRef nk = spp_norm(k);
-    { Tag t("bwd_gln_stats");
+    if (k == depth - 1) {
+      Tag t("bwd_gln_stats");
       if (int e = launch_gln_bwd_stats(x.at(p.g_spp[k]), x.at(p.spp[k]), nk, x.gp(gw->spp_dw[k].gamma),
-                                       x.gp(gw->spp_dw[k].beta), x.at<double>(p.bs_spp[k]), B, p.L[k], C, x.st)) return e; }
+                                       x.gp(gw->spp_dw[k].beta), x.at<double>(p.bs_spp[k]), B, p.L[k], C, x.st)) return e;
+    }
     DwBwdArgs d{};
     d.g[0] = gln_grad(x.at(p.g_spp[k]), x.at(p.spp[k]), nk, x.at<double>(p.bs_spp[k]));
     d.w[0] = w->spp_dw[k].w; d.dw[0] = x.gp(gw->spp_dw[k].w); d.db[0] = x.gp(gw->spp_dw[k].b);
     d.B = B; d.C = C; d.Lout = p.L[k];
     if (k == 0) {
-      d.xin = baffine(x.at(p.proj), L0, norm_ref(x, p.st_proj, 2, (double)L0 * C, w->proj.gamma, w->proj.beta), w->proj_prelu);
+      d.xin = baffine(x.at(p.proj), L0, n_proj, w->proj_prelu);
       d.xkind = SRC_AFFINE_PRELU; d.Lin = L0; d.stride = 1; d.dx = x.at(p.g_proj); d.accumulate = 0;
       d.dslope = x.gp(gw->proj_prelu);
+      d.up_dgamma = x.gp(gw->proj.gamma); d.up_dbeta = x.gp(gw->proj.beta); d.up_S = x.at<double>(p.bs_proj);
     } else {
       d.xin = baffine(x.at(p.spp[k - 1]), p.L[k - 1], spp_norm(k - 1));
-      d.xkind = SRC_AFFINE; d.Lin = p.L[k - 1]; d.stride = 2; d.dx = x.at(p.g_spp[k - 1]); d.accumulate = 1;
+      d.xkind = SRC_AFFINE; d.Lin = p.L[k - 1]; d.stride = 2; d.dx = x.at(p.g_spp[k - 1]);
+      d.accumulate = spp_written[k - 1];  // the loc_glo_fus local branch wrote it (every scale but a dead last one)
+      d.pool_g = x.at(p.g_ga_in); d.pool_Lb = Lb;
+      d.up_dgamma = x.gp(gw->spp_dw[k - 1].gamma); d.up_dbeta = x.gp(gw->spp_dw[k - 1].beta);
+      d.up_S = x.at<double>(p.bs_spp[k - 1]);
     }
     Tag t(k == 0 ? "bwd_spp_dw0" : "bwd_spp_dw_s2");
     if (int e = launch_dw_bwd(x, d, 5, 1)) return e;
   }
-  // ---- proj_1x1
-  const NormRef n_proj = norm_ref(x, p.st_proj, 2, (double)L0 * C, w->proj.gamma, w->proj.beta);
-  { Tag t("bwd_gln_stats");
-    if (int e = launch_gln_bwd_stats(x.at(p.g_proj), x.at(p.proj), n_proj, x.gp(gw->proj.gamma), x.gp(gw->proj.beta),
-                                     x.at<double>(p.bs_proj), B, L0, C, x.st)) return e; }
+  // ---- proj_1x1 (its GlobLN sums were accumulated by the spp_dw[0] backward)
   { Tag t("bwd_gln_apply");
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_proj), x.at(p.proj), n_proj, x.at<double>(p.bs_proj)),
                                      x.at(p.t_dloc[0]), 0, B, L0, C, x.st)) return e; }  // LA temporaries are free by now

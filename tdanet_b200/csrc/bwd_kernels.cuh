@@ -87,17 +87,21 @@ struct GradLoad {
 // forward value of a conv input row (normalise-on-load): PLAIN, AFFINE, AFFINE_PRELU
 template <int V>
 struct FwdLoad {
-  vf<V> sc, sh;
-  float slope;
+  vf<V> sc, sh, gam;
+  float slope, r, mur;
   const float* x;
   int kind;
   __device__ __forceinline__ void init(const SrcDesc& s, int kind_, int b, int ch, int C) {
     kind = kind_;
     x = s.x + (size_t)b * s.L * C + ch;
-    slope = 1.f;
+    slope = 1.f; r = 1.f; mur = 0.f;
 #pragma unroll
-    for (int e = 0; e < V; ++e) { sc[e] = 1.f; sh[e] = 0.f; }
-    if (kind != SRC_PLAIN) norm_coef<V>(s.norm, b, ch, sc, sh);
+    for (int e = 0; e < V; ++e) { sc[e] = 1.f; sh[e] = 0.f; gam[e] = 0.f; }
+    if (kind != SRC_PLAIN) {
+      norm_coef<V>(s.norm, b, ch, sc, sh);
+      norm_moments(s.norm, b, r, mur);
+      gam = vload<V>(s.norm.gamma + ch);
+    }
     if (kind == SRC_AFFINE_PRELU) slope = __ldg(s.slope);
   }
   // pre-activation value (GlobLN output; the raw value for PLAIN: sc = 1, sh = 0)
@@ -105,6 +109,19 @@ struct FwdLoad {
     vf<V> v = vload<V>(x + off);
 #pragma unroll
     for (int e = 0; e < V; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
+    return v;
+  }
+  // raw stored value of a row clamped into [0, L)
+  __device__ __forceinline__ vf<V> raw_row(int row, int L, int C) const {
+    const int rc = row < 0 ? 0 : (row >= L ? L - 1 : row);
+    return vload<V>(x + (size_t)rc * C);
+  }
+  // GlobLN output from a raw value; rows outside [0, L) are the conv's zero padding
+  __device__ __forceinline__ vf<V> pre_of(const vf<V>& raw, int row, int L) const {
+    vf<V> v;
+    const bool ok = row >= 0 && row < L;
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = ok ? fmaf(raw[e], sc[e], sh[e]) : 0.f;
     return v;
   }
   // rows outside [0, L) read as zero (the conv pads its input, i.e. the value after the transform)
@@ -223,6 +240,14 @@ __global__ void gln_fwd_apply_kernel(const float* __restrict__ x, NormRef norm, 
   }
 }
 
+// weight of F.adaptive_avg_pool1d bin j = [floor(j*L/Lb), ceil((j+1)*L/Lb)) for input row t: 1/|bin| if t is in it
+__device__ __forceinline__ float pool_bin_weight(int j, int t, int L, int Lb) {
+  if (j >= Lb) return 0.f;
+  const int lo = (int)(((long)j * L) / Lb);
+  const int hi = (int)((((long)j + 1) * L + Lb - 1) / Lb);
+  return (t >= lo && t < hi) ? 1.f / (float)(hi - lo) : 0.f;
+}
+
 // ----------------------------------------------------------------------------- depthwise conv backward
 // Forward: out_g[to] = sum_tap w_g[c, tap] * xin[to*stride + tap - PAD] (+ bias_g), g < NW convs sharing xin.
 //   dx[ti]    = sum_g sum_tap w_g[c, tap] * G_g[(ti + PAD - tap) / stride]
@@ -245,17 +270,28 @@ struct DwBwdArgs {
   float* dx;       // [B, Lin, C]
   int accumulate;  // dx += instead of =
   float* dslope;   // SRC_AFFINE_PRELU
+  // optional: this launch completes dx (the gradient w.r.t. the GlobLN output xin is read through), so it also
+  // accumulates that GlobLN's backward sums instead of a separate statistics pass
+  float *up_dgamma, *up_dbeta;
+  double* up_S;
+  // optional: xin is also an input of the adaptive average pooling into the bottom scale; the pooling's gradient
+  // (gathered from pool_g [B, pool_Lb, C]) is added to dx here instead of by a pass of its own
+  const float* pool_g;
+  int pool_Lb;
   int rows_per_thread;
 };
 
 // Streaming form: a thread owns 4 channels and a run of output rows, walks it in tiles of R = 4 output rows and
 // keeps the gradient rows / input rows a tile needs in registers (the rows shared with the previous tile are
 // carried over), so every row is fetched once and all loads of a tile are issued back to back.
-//   stride 1: tile t..t+3 needs G[t-PAD .. t+3+PAD] and xin[t-PAD .. t+3+PAD]          (carry 2*PAD rows)
-//   stride 2: output tile t..t+3 = input rows 2t..2t+7 needs G[t-1 .. t+4], xin[2t-2 .. 2t+8]   (carry 2 / 3 rows)
-template <int KS, int NW, int STRIDE>
+//   stride 1: tile t..t+R-1 needs G[t-PAD .. t+R-1+PAD] and xin[t-PAD .. t+R-1+PAD]               (carry 2*PAD rows)
+//   stride 2: output tile t..t+R-1 = input rows 2t..2t+2R-1 needs G[t-1 .. t+R], xin[2t-2 .. 2t+2R]  (carry 2 / 3 rows)
+// EXTRA compiles in the optional epilogues (PReLU derivative + slope gradient, upstream GlobLN sums, pooling gradient);
+// the plain variants (LA branches) stay lean in registers.
+template <int KS, int NW, int STRIDE, bool EXTRA>
 __global__ void dw_bwd_kernel(DwBwdArgs a) {
-  constexpr int V = 4, PAD = (KS - 1) / 2, R = 4;
+  // output rows per tile: 4, or 2 where the windows are wide (two convs, or stride 2 with its 2x input rows)
+  constexpr int V = 4, PAD = (KS - 1) / 2, R = (NW == 2 && KS == 5) || STRIDE == 2 ? 2 : 4;
   constexpr int GW = STRIDE == 1 ? R + 2 * PAD : R + 2;       // gradient rows held per tile
   constexpr int XW = STRIDE == 1 ? R + 2 * PAD : 2 * R + 3;   // input rows held per tile
   constexpr int GC = GW - R, XC = XW - R * STRIDE;            // rows carried from the previous tile
@@ -264,7 +300,7 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const bool active = ch < a.C;
-  double dsl = 0.0;
+  double dsl = 0.0, us[2] = {0.0, 0.0};
   if (active) {
     const int C = a.C, Lin = a.Lin, Lout = a.Lout;
     const int o0 = blockIdx.x * a.rows_per_thread, o1 = min(o0 + a.rows_per_thread, Lout);
@@ -281,7 +317,7 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
     }
     FwdLoad<V> fx;
     fx.init(a.xin, a.xkind, b, ch, C);
-    const bool prelu = a.xkind == SRC_AFFINE_PRELU;
+    const bool prelu = EXTRA && a.xkind == SRC_AFFINE_PRELU;
     float* dxp = a.dx + (size_t)b * Lin * C + ch;
     float dw[NW][KS][V], db[NW][V];
 #pragma unroll
@@ -293,9 +329,13 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
         for (int k = 0; k < KS; ++k) dw[g][k][e] = 0.f;
       }
     float sl_acc = 0.f;
-    vf<V> G[NW][GW], X[XW];  // X holds the value before the PReLU (the GlobLN output)
+    vf<V> G[NW][GW], X[XW];  // X holds the stored (raw) rows; the GlobLN / PReLU are applied at the point of use
     auto loadG = [&](int g, int row) { return gl[g].load_row(row, Lout, C); };
-    auto loadX = [&](int row) { return fx.pre_row(row, Lin, C); };
+    auto loadX = [&](int row) { return fx.raw_row(row, Lin, C); };
+    const bool up = EXTRA && a.up_S != nullptr;
+    const bool pool = EXTRA && a.pool_g != nullptr;
+    vf<V> udg = vzero<V>(), udb = vzero<V>();
+    float us1 = 0.f, us2 = 0.f;
     // rows carried into the first tile
 #pragma unroll
     for (int j = 0; j < GC; ++j)
@@ -318,6 +358,22 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
           O[q] = vload_rw<V>(dxp + (size_t)(ti < Lin ? ti : Lin - 1) * C);
         }
       }
+      if (pool) {
+        // d/dx of sum_j mean_{t in bin(j)} x[t]: only bins jc = floor(t*Lb/L) and jc + 1 can contain t
+        const int Lb = a.pool_Lb;
+        const float* gp = a.pool_g + (size_t)b * Lb * C + ch;
+#pragma unroll
+        for (int q = 0; q < R * STRIDE; ++q) {
+          const int ti = min(t * STRIDE + q, Lin - 1);
+          const int jc = (int)(((long)ti * Lb) / Lin);
+          const vf<V> g0 = vload<V>(gp + (size_t)jc * C), g1 = vload<V>(gp + (size_t)min(jc + 1, Lb - 1) * C);
+          const float w0 = pool_bin_weight(jc, ti, Lin, Lb), w1 = pool_bin_weight(jc + 1, ti, Lin, Lb);
+          if (!a.accumulate) O[q] = vzero<V>();
+#pragma unroll
+          for (int e = 0; e < V; ++e) O[q][e] += fmaf(g0[e], w0, g1[e] * w1);
+        }
+      }
+      const bool add_o = a.accumulate || pool;
       // ---- data gradient of the input rows of this tile
 #pragma unroll
       for (int q = 0; q < R * STRIDE; ++q) {
@@ -335,7 +391,7 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
               for (int e = 0; e < V; ++e) acc[e] = fmaf(w[g][k][e], G[g][slot][e], acc[e]);
           }
           if (prelu) {
-            const vf<V>& n = X[q - X0];
+            const vf<V> n = fx.pre_of(X[q - X0], ti, Lin);
 #pragma unroll
             for (int e = 0; e < V; ++e)
               if (n[e] < 0.f) {
@@ -343,11 +399,22 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
                 acc[e] *= fx.slope;
               }
           }
-          if (a.accumulate) {
+          if (add_o) {
 #pragma unroll
             for (int e = 0; e < V; ++e) acc[e] += O[q][e];
           }
           vstore<V>(dxp + (size_t)ti * C, acc);
+          if (up) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              const float xh = fmaf(X[q - X0][e], fx.r, -fx.mur);
+              udg[e] = fmaf(acc[e], xh, udg[e]);
+              udb[e] += acc[e];
+              const float gd = fx.gam[e] * acc[e];
+              us1 += gd;
+              us2 = fmaf(gd, xh, us2);
+            }
+          }
         }
       }
       // ---- weight / bias gradients of the output rows of this tile
@@ -360,11 +427,9 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
             for (int e = 0; e < V; ++e) db[g][e] += G[g][r - G0][e];
 #pragma unroll
           for (int k = 0; k < KS; ++k) {
-            vf<V> xv = X[r * STRIDE + k];  // input row (t + r)*STRIDE + k - PAD
-            if (prelu) {
+            vf<V> xv = fx.pre_of(X[r * STRIDE + k], (t + r) * STRIDE + k - PAD, Lin);
 #pragma unroll
-              for (int e = 0; e < V; ++e) xv[e] = preluf_(xv[e], fx.slope);
-            }
+            for (int e = 0; e < V; ++e) xv[e] = preluf_(xv[e], fx.slope);  // slope = 1 unless AFFINE_PRELU
 #pragma unroll
             for (int g = 0; g < NW; ++g)
 #pragma unroll
@@ -381,6 +446,12 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
       for (int j = 0; j < XC; ++j) X[j] = X[j + R * STRIDE];
     }
     dsl = sl_acc;
+    if (up) {
+      vred_add<V>(a.up_dgamma + ch, udg);
+      vred_add<V>(a.up_dbeta + ch, udb);
+      us[0] = us1;
+      us[1] = us2;
+    }
     // the thread's V*KS weight gradients are contiguous in [C][KS]: KS vector reductions per conv
     const size_t roff = (size_t)((blockIdx.x + blockIdx.z) & (a.n_rep - 1)) * a.rep_stride;
 #pragma unroll
@@ -400,7 +471,8 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
       }
     }
   }
-  if (a.dslope) {  // uniform across the grid
+  if (EXTRA && a.up_S) block_accum2(a.up_S + 2 * b, us[0], us[1]);  // uniform across the grid
+  if (EXTRA && a.dslope) {  // uniform across the grid
     __shared__ double sh[64];
     double z = 0.0;
 #ifdef TD_EMU

@@ -218,7 +218,8 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     }
     if (int e = launch_coef_inject_gate(ia, B, C, x.st)) return e;
   }
-  // training: every live x_fused[k] is kept for the backward pass, and the top-down steps read it back
+  // training: every live x_fused[k] is kept for the backward pass (the top-down steps below still recompute it on
+  // load, like inference: the streaming kernels are the fast path; both evaluate the same expression)
   bool fused_live[TDANET_MAX_DEPTH] = {};
   if (p.train) {
     for (int k = 0; k < depth - 1; ++k) fused_live[k] = true;
@@ -233,8 +234,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     DwArgs dl[TDANET_MAX_DEPTH];
     for (int i = 0; i < depth - 1; ++i) {
       dl[i] = DwArgs{};
-      if (p.train) { dl[i].src = plain_src(x.at(p.fused[i]), p.L[i]); dl[i].kind = SRC_PLAIN; }
-      else { dl[i].src = inj_src(i); dl[i].kind = inj_kind; } dl[i].B = B; dl[i].C = C; dl[i].Lout = p.L[i]; dl[i].stride = 1;
+      dl[i].src = inj_src(i); dl[i].kind = inj_kind; dl[i].B = B; dl[i].C = C; dl[i].Lout = p.L[i]; dl[i].stride = 1;
       dl[i].nw = 1; dl[i].w[0] = w->last_layer[i].local_embedding.w; dl[i].stats = x.at<double>(p.st_la_l[i]);
       dl[i].act_bf16 = x.bf();
     }
@@ -246,10 +246,11 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     const tdanet_la_t& la = w->last_layer[i];
     SrcDesc loc = inj_src(i), glo;
     int lkind = inj_kind, gkind;
-    if (p.train) {
-      const int gi = i == depth - 2 ? first_step_partner(depth) : -1;
+    if (i == depth - 2 && p.train) {
+      // fused_a / fused_b alias x_fused[depth-2] / x_fused[partner], materialised above
+      const int gi = first_step_partner(depth);
       loc = plain_src(x.at(p.fused[i]), p.L[i]);
-      glo = gi >= 0 ? plain_src(x.at(p.fused[gi]), p.L[gi]) : plain_src(x.at(p.expanded[i + 1]), p.L[i + 1]);
+      glo = plain_src(x.at(p.fused[gi]), p.L[gi]);
       lkind = gkind = SRC_PLAIN;
     } else if (i == depth - 2) {
       // python x_fused[i-1]: the finer neighbour (or [-1]).  Both operands of this step are small and its
