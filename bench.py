@@ -169,7 +169,7 @@ def run_train_leg(args, dev, rank, world, local, barrier):
     from tdanet_b200 import _lib
     B, W, K = TRAIN_BATCH, max(3, args.warmup), args.steps
     torch.manual_seed(0)
-    model = look2hear.models.TDANetBest(sample_rate=SR, **model_kwargs(args.enc_ms)).to(dev).train()
+    model = getattr(look2hear.models, CLASSES[args.variant])(sample_rate=SR, **model_kwargs(args.enc_ms)).to(dev).train()
     model.gemm_mode = args.gemm_mode
     L = look2hear.losses
     ts = look2hear.system.TrainingStep(model, L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True),
@@ -220,7 +220,7 @@ def run_train_leg(args, dev, rank, world, local, barrier):
     ms, ms_e2e = t.tolist()
     if rank != 0:
         return None
-    alg = train_algorithmic_bytes(model.engine.latent_lengths(N_SAMPLES)[0], B)
+    alg = train_algorithmic_bytes(model.engine.latent_lengths(N_SAMPLES)[0], B) if args.variant == "best" else {}
     peak, peak_src = measured_peaks()
     kernels = []
     for p in sorted(prof, key=lambda r: -r["ms"]):
@@ -241,7 +241,7 @@ def run_train_leg(args, dev, rank, world, local, barrier):
     out = {
         "metric": "train_steps_per_second", "value": K / (ms / 1e3), "unit": "steps/s", "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "n_gpus": world,
-        "config": {"workload": f"TDANetBest {args.enc_ms} ms encoder, 16 blocks, full training step (forward, PIT SI-SDR, "
+        "config": {"workload": f"{CLASSES[args.variant]} {args.enc_ms} ms encoder, 16 blocks, full training step (forward, PIT SI-SDR, "
                                f"backward, gradient all-reduce, clip 5.0, Adam), batch {B} x 2 s per GPU "
                                "(BASELINE.json configs[3]), dropout/DropPath off",
                    "batch_per_gpu": B, "global_batch": B * world, "gemm_mode": args.gemm_mode,
@@ -266,11 +266,11 @@ def cpu_train_baseline(args):
     torch.set_num_threads(cores)
     kw = model_kwargs(args.enc_ms)
     torch.manual_seed(0)
-    model = M.TDANetBest(sample_rate=SR, **kw)
+    model = M.get(CLASSES[args.variant])(sample_rate=SR, **kw)
     sd = {k: (torch.nn.Parameter(v.detach().clone()) if "pos_enc.pe" not in k else v) for k, v in model.state_dict().items()}
     params = [v for k, v in sd.items() if "pos_enc.pe" not in k]
     opt = torch.optim.Adam(params, lr=1e-3)
-    cfg = O.OracleConfig(variant="best", sample_rate=SR, **kw)
+    cfg = O.OracleConfig(variant=args.variant, sample_rate=SR, **kw)
     bs = 2
     mix, tgt = train_targets(0, bs)
     t0 = time.perf_counter()
@@ -426,7 +426,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)   # max over ranks
     ms, ms_e2e = t.tolist()
     train = None
-    if not args.skip_train and args.variant == "best":
+    if not args.skip_train:
         del x_dev, xin
         model._engine._ws.clear()
         model._engine._graphs.clear()

@@ -211,7 +211,9 @@ def uconv_block(sd, prefix, x, cfg):
             wd = sd[f"{q}.dw_conv.weight"]
             s = 2 ** (depth - 1 - k)                      # conv_pool[j] strides by 2^j
             z = F.conv1d(o, wd, sd[f"{q}.dw_conv.bias"], stride=s, padding=(wd.shape[-1] - 1) // 2, groups=C)
+            _tap(cfg, f"pool.dw.{k}", z)
             z = F.conv1d(z, sd[f"{q}.pw_conv.weight"], sd[f"{q}.pw_conv.bias"])
+            _tap(cfg, f"pool.pw.{k}", z)
             g = g + _norm(sd, f"{q}.norm", z, cfg)
     else:
         g = 0

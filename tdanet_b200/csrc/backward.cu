@@ -338,6 +338,12 @@ static int prepare_transposed(const BCtx& x) {
     if (x.c->gemm_mode != TDANET_GEMM_FP32)
       if (int r = launch_tf32_prepare(x.at(e.wt), x.at(e.aux), (size_t)e.N * e.K, x.c->gemm_mode, x.st)) return r;
   }
+  if (x.c->variant == TDANET_FORK)
+    for (int j = 0; j < x.c->depth; ++j) {
+      if (int r = launch_transpose(w->conv_pool[j].pw_w, x.at(p.wt_pool[j]), C, C, x.st)) return r;
+      if (x.c->gemm_mode != TDANET_GEMM_FP32)
+        if (int r = launch_tf32_prepare(x.at(p.wt_pool[j]), x.at(p.auxt_pool[j]), (size_t)C * C, x.c->gemm_mode, x.st)) return r;
+    }
   return 0;
 }
 
@@ -485,6 +491,20 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
   cudaEvent_t local_done[TDANET_MAX_DEPTH] = {};
   // loc_glo_fus[k] (1-tap LA): x_fused[k] = LA(gLN(spp_k), ga_out); runs on `sl` with temporary set 2
   auto lgf_backward = [&](int k) -> int {
+    if (c->variant != TDANET_BEST) {
+      // x_fused[k] = n_k + near(ga_out): g_fused[k] aliases g_spp[k]; the global feature gets the per-centre sums
+      Tag t("bwd_inject_add");
+      int jc = (int)((double)pick_rows(p.L[k], C / 4, B, 32) * Lb / p.L[k] + 0.5);
+      jc = jc < 1 ? 1 : jc;
+      dim3 grid;
+      int threads;
+      row_grid(Lb, C / 4, B, jc, grid, threads);
+      TD_LAUNCH(inject_add_bwd_kernel, grid, threads, 0, sl, x.at(p.g_fused[k]), x.at(p.g_ga_out), (int)ga_out_written,
+                p.L[k], Lb, C, nearest_scale(Lb, p.L[k]), jc);
+      spp_written[k] = true;
+      ga_out_written = true;
+      return 0;
+    }
     const tdanet_la_t& la = w->loc_glo_fus[k];
     const NormRef nL = norm_ref(x, p.st_lgf[k], 6, (double)p.L[k] * C, la.local_embedding.gamma, la.local_embedding.beta);
     const NormRef nA = norm_ref(x, p.st_lgf[k] + 2 * sizeof(double), 6, (double)Lb * C, la.global_act.gamma, la.global_act.beta);
@@ -530,9 +550,36 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
   if (int e = x.side->order(sl, x.st)) return e;  // g_spp[*], g_ga_out
   // ---- bottom-scale block
   if (int e = global_attention_backward(x)) return e;
-  // ---- ga_in = sum_k avgpool(gLN(spp_k)): the coarsest scale (identity bins) here, the others inside the spp_dw
-  // backward that completes g_spp[k]
-  {
+  if (c->variant == TDANET_FORK) {
+    // ---- ga_in = sum_k gLN(pw_conv(dw_conv(gLN(spp_k))))  with conv_pool[depth-1-k] (TDANet.py:605-620)
+    const int R = B * Lb;
+    for (int k = 0; k < depth; ++k) {
+      const int j = depth - 1 - k, s = 1 << j, ks = j == 0 ? 5 : 2 * s + 1;
+      const tdanet_sepconvnorm_t& q = w->conv_pool[j];
+      const tdanet_sepconvnorm_t& gq = gw->conv_pool[j];
+      const NormRef nq = norm_ref(x, p.st_pool[k], 2, (double)Lb * C, q.gamma, q.beta);
+      Tag t("bwd_conv_pool");
+      if (int e = launch_gln_bwd_stats(x.at(p.g_ga_in), x.at(p.pool_pw[k]), nq, x.gp(gq.gamma), x.gp(gq.beta),
+                                       x.at<double>(p.bs_pool[k]), B, Lb, C, x.st)) return e;
+      if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_ga_in), x.at(p.pool_pw[k]), nq, x.at<double>(p.bs_pool[k])),
+                                       x.at(p.g_pool_x[k]), 0, B, Lb, C, x.st)) return e;
+      if (int e = wgrad_side(x, x.at(p.g_pool_x[k]), x.at(p.pool_dw[k]), x.gp(gq.pw_w), x.gp(gq.pw_b), R, C, C)) return e;
+      if (int e = dgrad(x, x.at(p.g_pool_x[k]), p.wt_pool[j], p.auxt_pool[j], x.at(p.g_pool_dw), Lb, C, C, nullptr)) return e;
+      // depthwise conv of conv_pool[j] on gLN(spp_k): data gradient into g_spp[k], weights / bias
+      const int rows = pick_rows(p.L[k], C / 4, B, 16);
+      dim3 grid;
+      int threads;
+      row_grid(p.L[k], C / 4, B, rows, grid, threads);
+      TD_LAUNCH(dwg_bwd_data_kernel, grid, threads, 0, x.st, x.at(p.g_pool_dw), q.dw_w, x.at(p.g_spp[k]), (int)spp_written[k],
+                p.L[k], Lb, C, ks, s, rows);
+      spp_written[k] = true;
+      dim3 wgrid(cdiv(C / 4, threads), ks + 1);
+      TD_LAUNCH(dwg_bwd_weight_kernel, wgrid, threads, 0, x.st, x.at(p.g_pool_dw), baffine(x.at(p.spp[k]), p.L[k], spp_norm(k)),
+                (int)SRC_AFFINE, x.gp(gq.dw_w), x.gp(gq.dw_b), B, Lb, C, ks, s);
+    }
+  } else {
+    // ---- ga_in = sum_k avgpool(gLN(spp_k)): the coarsest scale (identity bins) here, the others inside the spp_dw
+    // backward that completes g_spp[k]
     Tag t("bwd_pool");
     const int k = depth - 1;
     if (int e = launch_pool_bwd(x.at(p.g_ga_in), x.at(p.g_spp[k]), spp_written[k], B, p.L[k], Lb, C, x.st)) return e;
@@ -561,7 +608,7 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
       d.xin = baffine(x.at(p.spp[k - 1]), p.L[k - 1], spp_norm(k - 1));
       d.xkind = SRC_AFFINE; d.Lin = p.L[k - 1]; d.stride = 2; d.dx = x.at(p.g_spp[k - 1]);
       d.accumulate = spp_written[k - 1];  // the loc_glo_fus local branch wrote it (every scale but a dead last one)
-      d.pool_g = x.at(p.g_ga_in); d.pool_Lb = Lb;
+      if (c->variant != TDANET_FORK) { d.pool_g = x.at(p.g_ga_in); d.pool_Lb = Lb; }
       d.up_dgamma = x.gp(gw->spp_dw[k - 1].gamma); d.up_dbeta = x.gp(gw->spp_dw[k - 1].beta);
       d.up_S = x.at<double>(p.bs_spp[k - 1]);
     }

@@ -719,6 +719,102 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
   for (int i = 0; i < 3; ++i) block_accum2(a.S[i] + 2 * b, S[i][0], S[i][1]);
 }
 
+// ----------------------------------------------------------------------------- FORK: additive injection backward
+// x_fused[k][t] = n_k[t] + g[nearest(t)]  (TDANet.py:622-626):  d n_k = d x_fused[k] (same buffer),
+// dg[j] (+)= sum_{t : nearest(t) = j} d x_fused[k][t].  A thread owns whole centres j.
+__global__ void inject_add_bwd_kernel(const float* __restrict__ dfused, float* __restrict__ dg, int accumulate, int Ll,
+                                      int Lg, int C, float scale, int jchunk) {
+  constexpr int V = 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (ch >= C) return;
+  const int j0 = blockIdx.x * jchunk, j1 = min(j0 + jchunk, Lg);
+  const float* dp = dfused + (size_t)b * Ll * C + ch;
+  float* gp = dg + (size_t)b * Lg * C + ch;
+  int t = first_local_row(j0, scale, Ll, Lg);
+  for (int j = j0; j < j1; ++j) {
+    const int tend = first_local_row(j + 1, scale, Ll, Lg);
+    vf<V> acc = accumulate ? vload_rw<V>(gp + (size_t)j * C) : vzero<V>();
+    for (; t + 4 <= tend; t += 4) {
+      vf<V> d[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] = vload<V>(dp + (size_t)(t + i) * C);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += d[i][e];
+    }
+    for (; t < tend; ++t) {
+      const vf<V> d = vload<V>(dp + (size_t)t * C);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += d[e];
+    }
+    vstore<V>(gp + (size_t)j * C, acc);
+  }
+}
+
+// ----------------------------------------------------------------------------- FORK: conv_pool depthwise backward
+// Forward (TDANet.py:190-228, 560-569): out[to] = sum_tap w[c, tap] * xin[to*s + tap - pad] + bias, any odd ks, stride s.
+//   dx[ti] (+)= sum_{to} w[c, ti + pad - to*s] * G[to]      (taps inside [0, ks))
+__global__ void dwg_bwd_data_kernel(const float* __restrict__ G, const float* __restrict__ w, float* __restrict__ dx,
+                                    int accumulate, int Lin, int Lout, int C, int ks, int stride, int rows_per_thread) {
+  constexpr int V = 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (ch >= C) return;
+  const int pad = (ks - 1) / 2;
+  const int t0 = blockIdx.x * rows_per_thread, t1 = min(t0 + rows_per_thread, Lin);
+  const float* gp = G + (size_t)b * Lout * C + ch;
+  float* dp = dx + (size_t)b * Lin * C + ch;
+  for (int ti = t0; ti < t1; ++ti) {
+    vf<V> acc = accumulate ? vload_rw<V>(dp + (size_t)ti * C) : vzero<V>();
+    // to*s <= ti + pad  and  ti + pad - to*s < ks
+    int to_hi = (ti + pad) / stride;
+    if (to_hi > Lout - 1) to_hi = Lout - 1;
+    int to_lo = ti + pad - ks + 1;
+    to_lo = to_lo <= 0 ? 0 : (to_lo + stride - 1) / stride;
+    for (int to = to_lo; to <= to_hi; ++to) {
+      const int tap = ti + pad - to * stride;
+      const vf<V> g = vload<V>(gp + (size_t)to * C);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = fmaf(__ldg(w + (size_t)(ch + e) * ks + tap), g[e], acc[e]);
+    }
+    vstore<V>(dp + (size_t)ti * C, acc);
+  }
+}
+
+//   dw[c, tap] += sum_{b, to} G[b, to, c] * xin[b, to*s + tap - pad, c];   db[c] += sum G      (one thread per (tap, 4 channels))
+__global__ void dwg_bwd_weight_kernel(const float* __restrict__ G, SrcDesc xin, int xkind, float* __restrict__ dw,
+                                      float* __restrict__ db, int B, int Lout, int C, int ks, int stride) {
+  constexpr int V = 4;
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  const int tap = blockIdx.y;  // ks taps, + one extra row of blocks for the bias
+  if (ch >= C) return;
+  const int pad = (ks - 1) / 2, Lin = xin.L;
+  vf<V> acc = vzero<V>();
+  for (int b = 0; b < B; ++b) {
+    FwdLoad<V> fx;
+    fx.init(xin, xkind, b, ch, C);
+    const float* gp = G + (size_t)b * Lout * C + ch;
+    for (int to = 0; to < Lout; ++to) {
+      const vf<V> g = vload<V>(gp + (size_t)to * C);
+      if (tap == ks) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += g[e];
+      } else {
+        const vf<V> xv = fx.load_row(to * stride + tap - pad, Lin, C);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = fmaf(g[e], xv[e], acc[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    if (tap == ks) atomicAdd(db + ch + e, acc[e]);
+    else atomicAdd(dw + (size_t)(ch + e) * ks + tap, acc[e]);
+  }
+}
+
 // ----------------------------------------------------------------------------- pooling backward
 // ga_in[j] = sum_k mean_{t in bin_k(j)} n_k[t]   =>   dn_k[t] = sum_{j : t in bin_k(j)} g[j] / |bin_k(j)|
 __global__ void pool_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, int accumulate, int L, int Lb,

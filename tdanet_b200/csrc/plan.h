@@ -55,8 +55,10 @@ struct Plan {
   size_t mlogit;                    // mask_net output before ReLU [B, L0, n_src*Nb]
   size_t nenc;                      // GlobLN(enc) [B, L0, Nb] (operand of the bottleneck weight gradient)
   // transposed weights for the data-gradient GEMMs (+ their TF32 copies)
-  size_t wt_proj, wt_res, wt_in, wt_out, wt_fc1, wt_fc2;
-  size_t auxt_proj, auxt_res, auxt_in, auxt_out, auxt_fc1, auxt_fc2;
+  size_t wt_proj, wt_res, wt_in, wt_out, wt_fc1, wt_fc2, wt_pool[TDANET_MAX_DEPTH];
+  size_t auxt_proj, auxt_res, auxt_in, auxt_out, auxt_fc1, auxt_fc2, auxt_pool[TDANET_MAX_DEPTH];
+  // FORK conv_pool backward: gradient w.r.t. the pw_conv output (through its GlobLN) per scale, and w.r.t. the dw output
+  size_t g_pool_x[TDANET_MAX_DEPTH], g_pool_dw;
   // gradient arena
   size_t g_masked, g_enc, g_x0, g_u[2], g_proj, g_spp[TDANET_MAX_DEPTH], g_fused[TDANET_MAX_DEPTH],
       g_exp[TDANET_MAX_DEPTH];
@@ -69,7 +71,7 @@ struct Plan {
   size_t rep_arena, rep_floats;
   // backward GlobLN sums S1 = sum(gamma*dy), S2 = sum(gamma*dy*xhat): [B,2] double each
   size_t bs_begin, bs_end, bs_enc, bs_proj, bs_fc1, bs_fc2, bs_spp[TDANET_MAX_DEPTH], bs_la[TDANET_MAX_DEPTH][3],
-      bs_lgf[TDANET_MAX_DEPTH][3];
+      bs_lgf[TDANET_MAX_DEPTH][3], bs_pool[TDANET_MAX_DEPTH];
 
   size_t take(size_t nbytes) {
     size_t o = bytes;
@@ -124,8 +126,8 @@ static inline int check_config(const tdanet_config_t* c) {
 // What the training path supports in this build (everything else raises instead of falling back).
 static inline int check_train_config(const tdanet_config_t* c) {
   if (int e = check_config(c)) return e;
-  if (c->variant != TDANET_BEST)
-    return fail(TDANET_EUNSUPPORTED, "training step: only TDANetBest (variant 0) has a backward pass in this build (got %d)", c->variant);
+  if (c->variant == TDANET_MULTRES)
+    return fail(TDANET_EUNSUPPORTED, "training step: TDANetMultRes (variant 2) has no backward pass in this build");
   if (c->act_dtype != TDANET_ACT_F32)
     return fail(TDANET_EUNSUPPORTED, "training step: activations are kept in fp32 (act_dtype fp32)");
   return 0;
@@ -175,6 +177,10 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     p.wt_out = wbuf((size_t)C * C); p.auxt_out = wbuf((size_t)C * C);
     p.wt_fc1 = wbuf((size_t)2 * C * C); p.auxt_fc1 = wbuf((size_t)2 * C * C);
     p.wt_fc2 = wbuf((size_t)2 * C * C); p.auxt_fc2 = wbuf((size_t)2 * C * C);
+    for (int k = 0; k < depth; ++k) {
+      p.wt_pool[k] = c->variant == TDANET_FORK ? wbuf((size_t)C * C) : 0;
+      p.auxt_pool[k] = c->variant == TDANET_FORK ? wbuf((size_t)C * C) : 0;
+    }
   }
 
   // ---- block arena
@@ -270,8 +276,10 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
   for (int k = 0; k < depth; ++k) {
     snprintf(nm, sizeof nm, "g_spp%d", k);
     p.g_spp[k] = p.act(nm, p.L[k], C);
+    // BEST: x_fused[k] = loc_glo_fus(n_k, g) has its own gradient; FORK: x_fused[k] = near(g) + n_k, so the gradient
+    // w.r.t. x_fused[k] IS a gradient w.r.t. n_k and lands directly in g_spp[k]
     snprintf(nm, sizeof nm, "g_fused%d", k);
-    p.g_fused[k] = p.act(nm, p.L[k], C);
+    p.g_fused[k] = c->variant == TDANET_BEST ? p.act(nm, p.L[k], C) : p.g_spp[k];
     if (k < depth - 1) {
       snprintf(nm, sizeof nm, "g_exp%d", k);
       p.g_exp[k] = p.act(nm, p.L[k], C);
@@ -299,6 +307,10 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
   p.g_qkv = p.act("g_qkv", Lb, 3 * C);
   p.g_attn_in = p.act("g_attn_in", Lb, C);
   p.g_ga_in = p.act("g_ga_in", Lb, C);
+  if (c->variant == TDANET_FORK) {
+    for (int k = 0; k < depth; ++k) p.g_pool_x[k] = p.act(nullptr, Lb, C);
+    p.g_pool_dw = p.act(nullptr, Lb, C);
+  }
   {
     const int group = c->attn_group > 0 ? c->attn_group : B;
     const size_t n = (size_t)B * Lb * c->n_head * group;  // [problem, head, query, key]
@@ -309,6 +321,7 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
   {
     // every depthwise conv weight (+ bias) of the block: spp_dw, ffn dwconv, last_layer (k5), loc_glo_fus (k1)
     size_t n = (size_t)depth * (C * 5 + C) + (size_t)(2 * C * 5 + 2 * C) + (size_t)(depth - 1) * 3 * C * 5 + (size_t)depth * 3 * C;
+    // (the FORK conv_pool depthwise weights accumulate straight into the caller's buffers)
     p.rep_floats = (n + 63) / 64 * 64;
     p.rep_arena = p.take(p.rep_floats * TDANET_DW_REPLICAS * sizeof(float));
   }
@@ -319,6 +332,7 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
   p.bs_fc2 = p.dstat("bs_fc2", 1);
   for (int k = 0; k < depth; ++k) {
     p.bs_spp[k] = p.dstat(nullptr, 1);
+    p.bs_pool[k] = p.dstat(nullptr, 1);
     for (int j = 0; j < 3; ++j) {
       p.bs_la[k][j] = p.dstat(nullptr, 1);
       p.bs_lgf[k][j] = p.dstat(nullptr, 1);

@@ -137,15 +137,15 @@ class _TDANetCommon(BaseModel):
                 f"{type(self).__name__} (tdanet_b200) runs on CUDA tensors only; there is no CPU fallback")
         wav = input_wav.float().contiguous()
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # gradients w.r.t. the parameters through the hand-written backward pass (TDANetBest; dropout and
+            # gradients w.r.t. the parameters through the hand-written backward pass (TDANetBest / TDANet; dropout and
             # DropPath are not applied).  There is no gradient w.r.t. the waveform.
-            if self._variant == "best":
+            if self._variant in ("best", "fork"):
                 named = [(n, p) for n, p in self.named_parameters()]
                 est = _SeparateFn.apply(self, wav, tuple(n for n, _ in named), *[p for _, p in named])
                 return est.squeeze(0) if was_one_d else est
             if self.training:
                 raise NotImplementedError(
-                    f"{type(self).__name__}: only TDANetBest has a backward pass in this build; "
+                    f"{type(self).__name__}: only TDANetBest and TDANet have a backward pass in this build; "
                     "call .eval() under torch.no_grad() for separation")
         w = self._weights()
         if self.use_cuda_graph:

@@ -70,9 +70,9 @@ def _check(lib, code):
         raise RuntimeError(f"emu error {code}: {lib.tdanet_last_error().decode()}")
 
 
-def make_engine(kw, sample_rate, gemm_mode="fp32"):
+def make_engine(kw, sample_rate, gemm_mode="fp32", variant="best"):
     K = kw["enc_kernel_size"] * sample_rate // 1000
-    return SeparationEngine("best", kw["out_channels"], kw["in_channels"], kw["num_blocks"], kw["upsampling_depth"],
+    return SeparationEngine(variant, kw["out_channels"], kw["in_channels"], kw["num_blocks"], kw["upsampling_depth"],
                             K, K // 2 + 1, kw["num_sources"], gemm_mode=gemm_mode)
 
 
@@ -121,7 +121,7 @@ def _stats(*raws):
     return torch.stack(out, dim=1)
 
 
-def fill_workspace(ws: Workspace, taps, kw):
+def fill_workspace(ws: Workspace, taps, kw, variant="best"):
     """What tdanet_forward_train leaves in the workspace, written from the taps of an oracle forward."""
     depth, nb = kw["upsampling_depth"], kw["num_blocks"]
     u = "sm.unet"
@@ -146,8 +146,13 @@ def fill_workspace(ws: Workspace, taps, kw):
             ws.put(f"st_spp{k}", _stats(raw), b)
             if k in live:
                 ws.put(f"fused{k}", _cl(t(f"fused.{k}")), b)
-                q = f"raw:{u}.loc_glo_fus.{k}"
-                ws.put(f"st_lgf{k}", _stats(t(f"{q}.local_embedding"), t(f"{q}.global_act"), t(f"{q}.global_embedding")), b)
+                if variant == "best":
+                    q = f"raw:{u}.loc_glo_fus.{k}"
+                    ws.put(f"st_lgf{k}", _stats(t(f"{q}.local_embedding"), t(f"{q}.global_act"), t(f"{q}.global_embedding")), b)
+            if variant == "fork":
+                ws.put(f"pool_dw{k}", _cl(t(f"pool.dw.{k}")), b)
+                ws.put(f"pool_pw{k}", _cl(t(f"pool.pw.{k}")), b)
+                ws.put(f"st_pool{k}", _stats(t(f"pool.pw.{k}")), b)
         for i in range(depth - 1):
             ws.put(f"expanded{i}", _cl(t(f"expanded.{i}")), b)
             q = f"raw:{u}.last_layer.{i}"
@@ -168,17 +173,17 @@ def fill_workspace(ws: Workspace, taps, kw):
         ws.put("ga_out", _cl(t("ga.out")), b)
 
 
-def emu_backward(sd, wav, d_est, kw, sample_rate):
+def emu_backward(sd, wav, d_est, kw, sample_rate, variant="best"):
     """Gradients of sum(est * d_est) w.r.t. every parameter, computed by the emulated CUDA backward pass.
     Returns (grads dict keyed like the state_dict, oracle output)."""
     lib = load_emu()
-    eng = make_engine(kw, sample_rate)
-    cfg = O.OracleConfig(variant="best", sample_rate=sample_rate, taps={}, tap_all=True, **kw)
+    eng = make_engine(kw, sample_rate, variant=variant)
+    cfg = O.OracleConfig(variant=variant, sample_rate=sample_rate, taps={}, tap_all=True, **kw)
     with torch.no_grad():
         est = O.forward(sd, wav, cfg)
     B, T = wav.shape[0], wav.shape[-1]
     ws = Workspace(lib, eng.cfg, B, T)
-    fill_workspace(ws, cfg.taps, kw)
+    fill_workspace(ws, cfg.taps, kw, variant)
     sd_c = {k: v.detach().contiguous().float() for k, v in sd.items()}
     grads = {k: torch.zeros_like(v) for k, v in sd_c.items() if not k.endswith("pos_enc.pe")}
     w = eng.pack(sd_c, _allow_host=True)

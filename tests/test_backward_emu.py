@@ -11,9 +11,12 @@ import emu_harness as H
 SR = 8000
 
 
-def _model_sd(kw, seed=0):
+CLASS = {"best": "TDANetBest", "fork": "TDANet"}
+
+
+def _model_sd(kw, seed=0, variant="best"):
     torch.manual_seed(seed)
-    model = look2hear.models.TDANetBest(sample_rate=SR, **kw)
+    model = getattr(look2hear.models, CLASS[variant])(sample_rate=SR, **kw)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(seed + 1)
     # move the parameters that initialise to constants (GlobLN gamma = 1, beta = 0, biases) off their defaults
@@ -25,9 +28,9 @@ def _model_sd(kw, seed=0):
     return sd
 
 
-def _autograd(sd, wav, d_est, kw):
+def _autograd(sd, wav, d_est, kw, variant="best"):
     sd64 = {k: v.double().requires_grad_(not k.endswith("pos_enc.pe")) for k, v in sd.items()}
-    est = O.forward(sd64, wav.double(), O.OracleConfig(variant="best", sample_rate=SR, **kw))
+    est = O.forward(sd64, wav.double(), O.OracleConfig(variant=variant, sample_rate=SR, **kw))
     (est * d_est.double()).sum().backward()
     return {k: v.grad for k, v in sd64.items() if not k.endswith("pos_enc.pe")}
 
@@ -40,15 +43,17 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("name,B,T", [("depth4", 2, 1203), ("depth5_odd", 3, 1111), ("depth2_3src", 2, 800), ("depth3", 1, 997)])
-def test_emulated_backward_matches_autograd(name, B, T):
+@pytest.mark.parametrize("variant,name,B,T", [
+    ("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111), ("best", "depth2_3src", 2, 800), ("best", "depth3", 1, 997),
+    ("fork", "depth4", 2, 1203), ("fork", "depth5_odd", 2, 1111), ("fork", "depth2_3src", 2, 800)])
+def test_emulated_backward_matches_autograd(variant, name, B, T):
     kw = CASES[name]
-    sd = _model_sd(kw)
+    sd = _model_sd(kw, variant=variant)
     g = torch.Generator().manual_seed(7)
     wav = torch.randn(B, 1, T, generator=g) * 0.1
     d_est = torch.randn(B, kw["num_sources"], T, generator=g)
-    grads, _, _ = H.emu_backward(sd, wav, d_est, kw, SR)
-    ref = _autograd(sd, wav, d_est, kw)
+    grads, _, _ = H.emu_backward(sd, wav, d_est, kw, SR, variant)
+    ref = _autograd(sd, wav, d_est, kw, variant)
     dead = f"loc_glo_fus.{kw['upsampling_depth'] - 1}."
     worst = 0.0
     for k, r in ref.items():
@@ -63,4 +68,4 @@ def test_emulated_backward_matches_autograd(name, B, T):
         rel = err / max(scale, 1e-12)
         worst = max(worst, rel)
         assert rel < 2e-4, f"{k}: max-rel {rel:.3e} (|ref|max {scale:.3e})"
-    print(f"{name}: worst max-rel gradient error {worst:.2e}")
+    print(f"{variant}/{name}: worst max-rel gradient error {worst:.2e}")

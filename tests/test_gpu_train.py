@@ -10,15 +10,15 @@ import emu_harness as H
 import tdanet_b200.look2hear as look2hear
 from oracle import tdanet_oracle as O
 from tdanet_b200 import engine as E
-from test_backward_emu import CASES, SR, _autograd, _model_sd
+from test_backward_emu import CASES, CLASS, SR, _autograd, _model_sd
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 PE = "sm.unet.globalatt.attn.pos_enc.pe"
 
 
-def _model(kw, sd, sr=SR):
-    m = look2hear.models.TDANetBest(sample_rate=sr, **kw)
+def _model(kw, sd, sr=SR, variant="best"):
+    m = getattr(look2hear.models, CLASS[variant])(sample_rate=sr, **kw)
     m.load_state_dict({k: v for k, v in sd.items() if k != PE}, strict=False)
     return m.to(DEV)
 
@@ -45,11 +45,13 @@ class _CompareWorkspace:
         self.worst[f"{name}@{block}"] = err
 
 
-@pytest.mark.parametrize("name,B,T", [("depth4", 2, 1203), ("depth5_odd", 3, 1111), ("depth2_3src", 2, 800)])
-def test_forward_train_keeps_what_backward_needs(name, B, T):
+@pytest.mark.parametrize("variant,name,B,T", [("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111),
+                                              ("best", "depth2_3src", 2, 800), ("fork", "depth4", 2, 1203),
+                                              ("fork", "depth5_odd", 3, 1111)])
+def test_forward_train_keeps_what_backward_needs(variant, name, B, T):
     kw = CASES[name]
-    sd = _model_sd(kw)
-    m = _model(kw, sd).eval()
+    sd = _model_sd(kw, variant=variant)
+    m = _model(kw, sd, variant=variant).eval()
     m.gemm_mode = "fp32"
     wav, _ = _inputs(kw, B, T)
     x = wav.squeeze(1).to(DEV)
@@ -57,14 +59,14 @@ def test_forward_train_keeps_what_backward_needs(name, B, T):
         y_inf = m(x)
         y_tr = m.engine.forward_train(m._weights(), x)
     torch.cuda.synchronize()
-    cfg = O.OracleConfig(variant="best", sample_rate=SR, taps={}, tap_all=True, **kw)
+    cfg = O.OracleConfig(variant=variant, sample_rate=SR, taps={}, tap_all=True, **kw)
     with torch.no_grad():
         ref = O.forward(sd, wav, cfg)
     scale = ref.abs().max().item()
     assert (y_tr.cpu() - ref).abs().max().item() / scale < 3e-5
     assert (y_tr - y_inf).abs().max().item() / scale < 1e-5
     cmp = _CompareWorkspace(m.engine, B, T)
-    H.fill_workspace(cmp, cfg.taps, kw)
+    H.fill_workspace(cmp, cfg.taps, kw, variant)
     bad = {k: v for k, v in cmp.worst.items() if v > 5e-5}
     assert not bad, bad
 
@@ -87,26 +89,29 @@ def _grad_errors(named_grads, ref):
 
 # fp32 GEMMs: every tensor to 2e-4 of its largest element (measured 2e-6 .. 8e-6).  TF32 tensor-core GEMMs
 # (forward and data gradients with 10-bit mantissa operands, compounded over ~10 GEMMs per block): the whole
-# gradient to 1e-2 in relative L2 (measured 2e-4 .. 4e-3 on these 16..64-channel models); single tensors whose
-# gradient is a heavily cancelling sum (the encoder GlobLN beta) amplify the operand rounding (measured <= 9e-2).
+# gradient to 2e-2 in relative L2 (measured 2e-4 .. 1e-2 on these 16..64-channel models); single tensors whose
+# gradient is a heavily cancelling sum (the encoder GlobLN beta) amplify the operand rounding (measured <= 0.15).
 # scripts/diag_tf32_grad.py splits the error: a TF32 backward over an exact forward stays at 1e-4 .. 2e-4; the
 # rest is the gradient being evaluated at the TF32 forward's activations (ReLU / PReLU kinks), which split
 # weights (tf32x3) do not change because the activation operand is still a 10-bit mantissa.
-@pytest.mark.parametrize("mode,tol_max,tol_all", [("fp32", 2e-4, 1e-4), ("tf32x3", 0.15, 1e-2), ("tf32", 0.15, 1e-2)])
-@pytest.mark.parametrize("name,B,T", [("depth4", 2, 1203), ("depth5_odd", 3, 1111), ("depth2_3src", 2, 800), ("depth3", 1, 997)])
-def test_gradients_match_autograd(name, B, T, mode, tol_max, tol_all):
+@pytest.mark.parametrize("mode,tol_max,tol_all", [("fp32", 2e-4, 1e-4), ("tf32x3", 0.2, 2e-2), ("tf32", 0.2, 2e-2)])
+@pytest.mark.parametrize("variant,name,B,T", [("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111),
+                                              ("best", "depth2_3src", 2, 800), ("best", "depth3", 1, 997),
+                                              ("fork", "depth4", 2, 1203), ("fork", "depth5_odd", 3, 1111),
+                                              ("fork", "depth2_3src", 2, 800)])
+def test_gradients_match_autograd(variant, name, B, T, mode, tol_max, tol_all):
     kw = CASES[name]
-    sd = _model_sd(kw)
-    m = _model(kw, sd).train()
+    sd = _model_sd(kw, variant=variant)
+    m = _model(kw, sd, variant=variant).train()
     m.gemm_mode = mode
     wav, d_est = _inputs(kw, B, T)
     est = m(wav.to(DEV))
     assert est.requires_grad
     (est * d_est.to(DEV)).sum().backward()
     torch.cuda.synchronize()
-    ref = _autograd(sd, wav, d_est, kw)
+    ref = _autograd(sd, wav, d_est, kw, variant)
     wmax, wl2, all_l2 = _grad_errors([(k, p.grad) for k, p in m.named_parameters()], ref)
-    print(f"{name}/{mode}: worst per-tensor max-rel {wmax:.2e}, worst per-tensor rel-L2 {wl2:.2e}, whole-gradient rel-L2 {all_l2:.2e}")
+    print(f"{variant}/{name}/{mode}: worst per-tensor max-rel {wmax:.2e}, worst per-tensor rel-L2 {wl2:.2e}, whole-gradient rel-L2 {all_l2:.2e}")
     assert wmax < tol_max and all_l2 < tol_all
 
 
@@ -281,3 +286,16 @@ def test_wgrad_tensor_core_matches_fp32(R, N, K):
         torch.cuda.synchronize()
         assert (dW.double() - ref).abs().max().item() / scale < tol, mode
         assert (db.double() - ref_b).abs().max().item() / ref_b.abs().max().item() < 1e-5, mode
+
+
+def test_fork_training_step_reduces_loss():
+    """The fork TDANet (learned conv_pool gather, additive injection) through the fused training step."""
+    kw = CASES["depth4"]
+    m = _model(kw, _model_sd(kw, variant="fork"), variant="fork").train()
+    L = look2hear.losses
+    ts = look2hear.system.TrainingStep(m, L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True), lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    tgt = (torch.randn(4, 2, 2000, generator=g) * 0.1).to(DEV)
+    mix = tgt.sum(1)
+    losses = [ts.step_captured(mix, tgt).item() for _ in range(30)]
+    assert losses[-1] < losses[0] - 0.5, losses
