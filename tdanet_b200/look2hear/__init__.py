@@ -4,4 +4,4 @@
 kwargs, forward signatures and state_dict keys, so `import tdanet_b200.look2hear as
 look2hear` is the whole migration for code that only touches this path.
 """
-from . import losses, models, system  # noqa: F401
+from . import losses, metrics, models, system  # noqa: F401

@@ -5,6 +5,8 @@ gradient mean / clip / Adam) on the CUDA forward and backward kernels."""
 from .longform import css_segments, separate_long
 from .sharding import shard_bounds, separate_sharded
 from .training import AudioLightningModule, FlatParameters, TrainingStep
+from .checkpoint import ReduceLROnPlateau
+from . import checkpoint
 
 __all__ = ["shard_bounds", "separate_sharded", "css_segments", "separate_long", "AudioLightningModule",
-           "FlatParameters", "TrainingStep"]
+           "FlatParameters", "TrainingStep", "ReduceLROnPlateau", "checkpoint"]

@@ -165,6 +165,39 @@ class TrainingStep:
         self.optimizer_step()
         return self._static_loss
 
+    # ------------------------------------------------------------------ checkpoints (reference Lightning layout)
+    def _named_shapes(self):
+        return [(n, self.params.views[n].shape) for n in self.params.names]
+
+    def optimizer_state_dict(self):
+        """`torch.optim.Adam(model.parameters()).state_dict()` of this run (audio_train.py:208-213 stores it under
+        `optimizer_states`)."""
+        from .checkpoint import adam_state_to_torch
+        return adam_state_to_torch(self._named_shapes(), self.exp_avg, self.exp_avg_sq, int(self.step_count.item()),
+                                   self.lr, self.betas, self.eps)
+
+    def load_optimizer_state_dict(self, state) -> None:
+        from .checkpoint import torch_to_adam_state
+        step, self.lr, self.betas, self.eps = torch_to_adam_state(self._named_shapes(), state, self.exp_avg,
+                                                                  self.exp_avg_sq)
+        self.step_count.fill_(step)
+
+    def checkpoint(self, epoch: int = 0, schedulers=()):
+        """A dict laid out like the reference's Lightning checkpoint (loadable by `BaseModel.from_pretrain`)."""
+        from .checkpoint import lightning_state_dict
+        return {"epoch": epoch, "global_step": int(self.step_count.item()),
+                "state_dict": lightning_state_dict({k: v.detach().clone() for k, v in self.model.state_dict().items()}),
+                "optimizer_states": [self.optimizer_state_dict()],
+                "lr_schedulers": [s.state_dict() for s in schedulers]}
+
+    def load_checkpoint(self, ckpt, schedulers=()) -> None:
+        from .checkpoint import strip_lightning_prefix
+        self.model.load_state_dict(strip_lightning_prefix(ckpt["state_dict"]))   # copies into the flat views
+        if ckpt.get("optimizer_states"):
+            self.load_optimizer_state_dict(ckpt["optimizer_states"][0])
+        for s, st in zip(schedulers, ckpt.get("lr_schedulers", [])):
+            s.load_state_dict(st)
+
     def grad_norm(self) -> float:
         """Global L2 norm of the gradient of the last step (after the all-reduce, before scaling); syncs."""
         return float(self.sqnorm[0].sqrt().item())
@@ -200,6 +233,16 @@ class AudioLightningModule(torch.nn.Module):
         est_sources = self(mixtures)
         loss = self.loss_func["train"](est_sources, targets)
         return {"loss": loss}
+
+    def validation_step(self, batch, batch_nb=0, dataloader_idx=0):
+        """audio_litmodule.py:127-165: PIT loss of the separated sources under no_grad (eval forward)."""
+        mixtures, targets = batch[0], batch[1]
+        was_training = self.audio_model.training
+        self.audio_model.eval()
+        with torch.no_grad():
+            loss = self.loss_func["val"](self(mixtures), targets)
+        self.audio_model.train(was_training)
+        return {"val_loss" if dataloader_idx == 0 else "test_loss": loss}
 
     def fit_step(self, batch, lr: Optional[float] = None, clip_grad_norm: float = 5.0):
         mixtures, targets = batch[0], batch[1]

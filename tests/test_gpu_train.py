@@ -299,3 +299,47 @@ def test_fork_training_step_reduces_loss():
     mix = tgt.sum(1)
     losses = [ts.step_captured(mix, tgt).item() for _ in range(30)]
     assert losses[-1] < losses[0] - 0.5, losses
+
+
+def test_checkpoint_resume_and_metrics(tmp_path):
+    """Lightning-layout checkpoint written by the fused step resumes bit-identically (parameters, Adam moments,
+    step counter); validation_step / SI-SNRi run on the device."""
+    kw = CASES["depth4"]
+    L = look2hear.losses
+    loss_fn = L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True)
+    g = torch.Generator().manual_seed(1)
+    tgt = (torch.randn(4, 2, 2000, generator=g) * 0.1).to(DEV)
+    mix = tgt.sum(1)
+
+    def fresh():
+        m = _model(kw, _model_sd(kw)).train()
+        m.gemm_mode = "fp32"
+        return look2hear.system.TrainingStep(m, loss_fn, lr=1e-3)
+
+    a = fresh()
+    for _ in range(3):
+        a.step(mix, tgt)
+    path = tmp_path / "epoch=0.ckpt"
+    torch.save(a.checkpoint(epoch=0), path)
+    b = fresh()
+    b.load_checkpoint(torch.load(path, map_location=DEV, weights_only=False))
+    assert torch.equal(a.params.flat, b.params.flat) and torch.equal(a.exp_avg, b.exp_avg)
+    assert torch.equal(a.exp_avg_sq, b.exp_avg_sq) and int(b.step_count.item()) == 3
+    # the optimizer state loads into the reference's optimizer class
+    opt = torch.optim.Adam(b.model.parameters(), lr=1e-3)
+    opt.load_state_dict(a.optimizer_state_dict())
+    la, lb = a.step(mix, tgt).item(), b.step(mix, tgt).item()
+    assert abs(la - lb) < 1e-4 * max(1.0, abs(la))
+    # the reference's inference entry point reads the same file
+    m2 = look2hear.models.TDANetBest.from_pretrain("TDANetBest", str(path), sample_rate=SR, **kw).to(DEV).eval()
+    system = look2hear.system.AudioLightningModule(audio_model=m2, loss_func={"train": loss_fn, "val": loss_fn})
+    val = system.validation_step((mix, tgt, None), 0, 0)["val_loss"]
+    with torch.no_grad():
+        est = m2(mix)
+    s, si = look2hear.metrics.si_snr_improvement(mix, tgt, est)
+    ref = O.si_snr_db(est.cpu(), tgt.cpu())      # identity permutation
+    ref_sw = O.si_snr_db(est.cpu(), tgt.cpu().flip(1))
+    best = torch.maximum(ref.mean(1), ref_sw.mean(1))
+    assert torch.allclose(s.cpu(), best, atol=2e-3)
+    assert abs(val.item() + s.mean().item()) < 5e-3
+    assert si.shape == (4,)
