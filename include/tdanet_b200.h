@@ -53,7 +53,9 @@ enum tdanet_error {
 enum tdanet_variant {
   TDANET_BEST = 0,    /* look2hear.models.TDANetBest   (TDANet_best.py)     */
   TDANET_FORK = 1,    /* look2hear.models.TDANet       (TDANet.py)          */
-  TDANET_MULTRES = 2  /* look2hear.models.TDANetMultRes(TDANet_mult_tes.py) */
+  TDANET_MULTRES = 2, /* look2hear.models.TDANetMultRes(TDANet_mult_tes.py) */
+  TDANET_ORIGIN = 3   /* look2hear.models.TDANetOrigin / TDANetYang (TDANet_origin.py, TDANet_yang.py):
+                         GroupNorm GlobLN, average-pool gather, additive injection, batch-axis attention */
 };
 
 enum tdanet_gemm_mode {

@@ -32,7 +32,8 @@ import look2hear.losses as RL          # noqa: E402
 from oracle import tdanet_oracle as O  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
-CLASSES = {"best": "TDANetBest", "fork": "TDANet", "multres": "TDANetMultRes"}
+CLASSES = {"best": "TDANetBest", "fork": "TDANet", "multres": "TDANetMultRes", "origin": "TDANetOrigin",
+           "yang": "TDANetYang"}
 
 SMALL = dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=5,
              enc_kernel_size=4, num_sources=2)
@@ -84,7 +85,8 @@ def hook_taps(model, names):
 def main():
     os.makedirs(OUT, exist_ok=True)
     report = []
-    for variant in CLASSES:
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv[1:] if a.startswith("--only=")]
+    for variant in (only[0] if only else CLASSES):
         sr = 8000 if variant == "multres" else 16000
         kw = dict(SMALL)
         if variant == "multres":
@@ -138,6 +140,11 @@ def main():
                             kwargs=np.array(repr(kwf)), sample_rate=np.array(sr),
                             batch=np.array(B), input_seed=np.array(1234), init_seed=np.array(0))
 
+    if only:   # model fixtures of the named variants only; the loss fixtures and the report stay as they are
+        with open(os.path.join(OUT, "REPORT.txt"), "a") as f:
+            f.write("\n".join(report) + "\n")
+        print("\n".join(report))
+        return
     # ---------------- loss known answers
     g = torch.Generator().manual_seed(99)
     tgt = torch.randn(6, 2, 2000, generator=g) * 0.1

@@ -47,7 +47,8 @@ EPS_LN = 1e-5
 
 @dataclass
 class OracleConfig:
-    variant: str = "best"          # "best" | "fork" | "multres"
+    variant: str = "best"          # "best" | "fork" | "multres" | "origin" / "yang" (TDANetOrigin / TDANetYang:
+                                   # GroupNorm norms, average-pool gather, additive injection, batch-axis attention)
     out_channels: int = 128
     in_channels: int = 512
     num_blocks: int = 16

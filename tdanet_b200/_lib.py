@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtdanet_b200.so")
 
 MAX_DEPTH = 8
 MAX_ENC = 4
-VARIANTS = {"best": 0, "fork": 1, "multres": 2}
+VARIANTS = {"best": 0, "fork": 1, "multres": 2, "origin": 3, "yang": 3}
 GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 ACT_DTYPES = {"fp32": 0, "bf16": 1}
 SDR_TYPES = {"snr": 0, "sisdr": 1, "sdsdr": 2}

@@ -96,7 +96,7 @@ struct Plan {
 
 static inline int check_config(const tdanet_config_t* c) {
   TD_REQUIRE(c != nullptr, "config is NULL");
-  TD_REQUIRE(c->variant >= TDANET_BEST && c->variant <= TDANET_MULTRES, "unknown variant %d", c->variant);
+  TD_REQUIRE(c->variant >= TDANET_BEST && c->variant <= TDANET_ORIGIN, "unknown variant %d", c->variant);
   TD_REQUIRE(c->depth >= 2 && c->depth <= TDANET_MAX_DEPTH, "upsampling_depth %d outside [2, %d]", c->depth, TDANET_MAX_DEPTH);
   TD_REQUIRE(c->num_blocks >= 1, "num_blocks %d", c->num_blocks);
   TD_REQUIRE(c->out_channels > 0 && c->out_channels % 16 == 0, "out_channels %d must be a multiple of 16", c->out_channels);

@@ -1,9 +1,10 @@
-"""look2hear.models mirror: the three TDANet classes BASELINE.json names, `get`, `register_model`
+"""look2hear.models mirror: the TDANet classes on the hot path (TDANetBest, the fork TDANet, TDANetMultRes, and the
+TDANetOrigin / TDANetYang heads of configs/tdanet_origin.yml / tdanet.yml), `get`, `register_model`
 (reference: look2hear/models/__init__.py:82-114)."""
 from .base_model import BaseModel
-from .tdanet import TDANet, TDANetBest, TDANetMultRes
+from .tdanet import TDANet, TDANetBest, TDANetMultRes, TDANetOrigin, TDANetYang
 
-__all__ = ["BaseModel", "TDANet", "TDANetBest", "TDANetMultRes"]
+__all__ = ["BaseModel", "TDANet", "TDANetBest", "TDANetMultRes", "TDANetOrigin", "TDANetYang"]
 
 
 def register_model(custom_model):

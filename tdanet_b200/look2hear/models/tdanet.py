@@ -139,13 +139,13 @@ class _TDANetCommon(BaseModel):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # gradients w.r.t. the parameters through the hand-written backward pass (TDANetBest / TDANet; dropout and
             # DropPath are not applied).  There is no gradient w.r.t. the waveform.
-            if self._variant in ("best", "fork"):
+            if self._variant in ("best", "fork", "origin", "yang"):
                 named = [(n, p) for n, p in self.named_parameters()]
                 est = _SeparateFn.apply(self, wav, tuple(n for n, _ in named), *[p for _, p in named])
                 return est.squeeze(0) if was_one_d else est
             if self.training:
                 raise NotImplementedError(
-                    f"{type(self).__name__}: only TDANetBest and TDANet have a backward pass in this build; "
+                    f"{type(self).__name__}: TDANetMultRes has no backward pass in this build; "
                     "call .eval() under torch.no_grad() for separation")
         w = self._weights()
         if self.use_cuda_graph:
@@ -190,6 +190,24 @@ class TDANet(_TDANetCommon):
         super().__init__(sample_rate=sample_rate)
         self._build(out_channels, in_channels, num_blocks, upsampling_depth, enc_kernel_size, num_sources,
                     sample_rate)
+
+
+class TDANetOrigin(_TDANetCommon):
+    """The original TDANet (TDANet_origin.py:393): like TDANetBest without loc_glo_fus - average-pool gather,
+    additive injection of the global feature, GroupNorm(1, C) norms."""
+    _variant = "origin"
+
+    def __init__(self, out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
+                 enc_kernel_size=21, num_sources=2, sample_rate=16000, feat_len=3010):
+        super().__init__(sample_rate=sample_rate)
+        self._build(out_channels, in_channels, num_blocks, upsampling_depth, enc_kernel_size, num_sources,
+                    sample_rate)
+
+
+class TDANetYang(TDANetOrigin):
+    """TDANet_yang.py:441: the same computation as TDANetOrigin (its time-axis attention module is defined but not
+    used by its GlobalAttention), kept as its own class name for `models.get` / configs/tdanet.yml."""
+    _variant = "yang"
 
 
 class TDANetMultRes(_TDANetCommon):

@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CLASSES = {"best": "TDANetBest", "fork": "TDANet", "multres": "TDANetMultRes"}
+CLASSES = {"best": "TDANetBest", "fork": "TDANet", "multres": "TDANetMultRes", "origin": "TDANetOrigin",
+           "yang": "TDANetYang"}
 
 
 def pytest_configure(config):

@@ -11,7 +11,7 @@ import emu_harness as H
 SR = 8000
 
 
-CLASS = {"best": "TDANetBest", "fork": "TDANet"}
+CLASS = {"best": "TDANetBest", "fork": "TDANet", "origin": "TDANetOrigin"}
 
 
 def _model_sd(kw, seed=0, variant="best"):
@@ -45,7 +45,8 @@ CASES = {
 
 @pytest.mark.parametrize("variant,name,B,T", [
     ("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111), ("best", "depth2_3src", 2, 800), ("best", "depth3", 1, 997),
-    ("fork", "depth4", 2, 1203), ("fork", "depth5_odd", 2, 1111), ("fork", "depth2_3src", 2, 800)])
+    ("fork", "depth4", 2, 1203), ("fork", "depth5_odd", 2, 1111), ("fork", "depth2_3src", 2, 800),
+    ("origin", "depth4", 2, 1203), ("origin", "depth3", 1, 997)])
 def test_emulated_backward_matches_autograd(variant, name, B, T):
     kw = CASES[name]
     sd = _model_sd(kw, variant=variant)

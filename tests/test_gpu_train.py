@@ -98,7 +98,7 @@ def _grad_errors(named_grads, ref):
 @pytest.mark.parametrize("variant,name,B,T", [("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111),
                                               ("best", "depth2_3src", 2, 800), ("best", "depth3", 1, 997),
                                               ("fork", "depth4", 2, 1203), ("fork", "depth5_odd", 3, 1111),
-                                              ("fork", "depth2_3src", 2, 800)])
+                                              ("fork", "depth2_3src", 2, 800), ("origin", "depth5_odd", 3, 1111)])
 def test_gradients_match_autograd(variant, name, B, T, mode, tol_max, tol_all):
     kw = CASES[name]
     sd = _model_sd(kw, variant=variant)
