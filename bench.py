@@ -243,8 +243,8 @@ def run_train_leg(args, dev, rank, world, local, barrier):
         "higher_is_better": True, "scaling": "weak", "n_gpus": world,
         "config": {"workload": f"{CLASSES[args.variant]} {args.enc_ms} ms encoder, 16 blocks, full training step (forward, PIT SI-SDR, "
                                f"backward, gradient all-reduce, clip 5.0, Adam), batch {B} x 2 s per GPU "
-                               "(BASELINE.json configs[3]), dropout/DropPath off",
-                   "batch_per_gpu": B, "global_batch": B * world, "gemm_mode": args.gemm_mode,
+                               "(BASELINE.json configs[3]), train mode: dropout 0.1 / DropPath 0.1 like the reference (Philox keep-masks drawn on the device every step)",
+                   "dropout": model.dropout, "drop_path": model.drop_path, "batch_per_gpu": B, "global_batch": B * world, "gemm_mode": args.gemm_mode,
                    "cuda_graph": not args.no_graph},
         "samples_per_second": world * B * K / (ms / 1e3),
         "e2e": {"value": K / (ms_e2e / 1e3), "unit": "steps/s", "ms_per_step": ms_e2e / K,

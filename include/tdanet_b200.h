@@ -36,7 +36,7 @@ extern "C" {
 #define TDANET_API
 #endif
 
-#define TDANET_ABI_VERSION 2
+#define TDANET_ABI_VERSION 3
 #define TDANET_MAX_DEPTH 8
 #define TDANET_MAX_ENC 4
 
@@ -87,7 +87,10 @@ typedef struct tdanet_config {
   int32_t attn_group;    /* batch items that attend to each other (BEST/FORK: the reference
                             batch being emulated); 0 = the whole batch of the call         */
   int32_t act_dtype;     /* enum tdanet_act_dtype: storage of the large activations             */
-  int32_t reserved[2];
+  /* Training-mode regularisation (tdanet_forward_train_rng / tdanet_backward only; tdanet_forward is eval).
+   * The reference hard-codes both to 0.1 (TDANet_best.py:256-259,335-337; TDANet.py:397-401,573-575).   */
+  float dropout;         /* nn.MultiheadAttention(dropout), MultiHeadAttention.dropout, FFN.drop */
+  float drop_path;       /* GA.drop_path (per-item stochastic depth on both GA branches)         */
 } tdanet_config_t;
 
 /* conv weight (+ optional bias) followed by a GlobLN: ConvNorm / DilatedConvNorm / ConvNormAct */
@@ -176,7 +179,15 @@ TDANET_API int tdanet_latent_lengths(const tdanet_config_t* cfg, int n_samples, 
  * Replaces the autograd graph of AudioLightningModule.training_step (system/audio_litmodule.py:83-124) and
  * the Trainer's clip + optimiser (audio_train.py:71,187-197; configs/tdanet_lsr2.yml:42-45) for the model
  * path: forward keeping every GlobLN-delimited tensor of every UConvBlock iteration, hand-written backward,
- * global-norm clipping and Adam on flat buffers.  Dropout / DropPath are not applied (p = 0).
+ * global-norm clipping and Adam on flat buffers.
+ *
+ * Dropout / DropPath (cfg->dropout, cfg->drop_path > 0; drop_path / DropPath TDANet_best.py:7-30, nn.Dropout
+ * sites :210,:212,:251, nn.MultiheadAttention(dropout) :241): tdanet_forward_train_rng draws every keep-mask of
+ * every UConvBlock iteration up front with Philox4x32-10 (key = rng_state[0], counter = {element group, site |
+ * iteration << 8, rng_state[1]}), stores them as bytes in the training workspace ("m_att" "m_ao" "m_f1" "m_f2"
+ * "m_dp", elem_bytes 1) and then advances rng_state[1] on the device, so a captured CUDA graph draws fresh masks
+ * at every replay; tdanet_backward reads the stored masks.  element kept  <=>  u32 >= floor(p * 2^32); kept
+ * elements are scaled by 1/(1-p) like torch.  tdanet_forward_train is the p = 0 form (it fails if p > 0).
  *
  * tdanet_forward_train   same result as tdanet_forward; `workspace` (tdanet_train_workspace_bytes) then holds
  *                        what tdanet_backward needs and must stay untouched until it has run.
@@ -188,11 +199,17 @@ TDANET_API int tdanet_train_workspace_bytes(const tdanet_config_t* cfg, int batc
 TDANET_API int tdanet_forward_train(const tdanet_config_t* cfg, const tdanet_weights_t* w, const float* wav,
                    int batch, int n_samples, float* est, void* workspace, size_t workspace_bytes,
                    tdanet_stream_t stream);
+/* rng_state: device uint64[2] = {seed, offset}; offset is incremented by the call (on the stream). */
+TDANET_API int tdanet_forward_train_rng(const tdanet_config_t* cfg, const tdanet_weights_t* w, const float* wav,
+                   int batch, int n_samples, float* est, void* workspace, size_t workspace_bytes,
+                   uint64_t* rng_state, tdanet_stream_t stream);
 TDANET_API int tdanet_backward(const tdanet_config_t* cfg, const tdanet_weights_t* w, const tdanet_weights_t* grads,
                    const float* wav, const float* d_est, int batch, int n_samples, void* workspace,
                    size_t workspace_bytes, tdanet_stream_t stream);
 /* Locate a tensor of UConvBlock iteration `block` in the training workspace (tests).  Names of
- * tdanet_workspace_tensor plus "bin" "y" "fused0".. "mlogit" and the statistics "st_*" (elem_bytes = 8). */
+ * tdanet_workspace_tensor plus "bin" "y" "fused0".. "mlogit", the statistics "st_*" (elem_bytes = 8) and, with
+ * dropout, the keep-masks (elem_bytes = 1): "m_att" [problems*heads, n, n] (problem = group*L + t), "m_ao" /
+ * "m_f2" [B, L, C], "m_f1" [B, L, 2C], "m_dp" [2, B, 1] (attention branch, FFN branch). */
 TDANET_API int tdanet_train_workspace_tensor(const tdanet_config_t* cfg, int batch, int n_samples, const char* name,
                    int block, size_t* byte_offset, int64_t dims[3], int32_t* elem_bytes);
 /* Weight / bias gradient of a 1x1 Conv1d / Linear in channels-last form: dW[N, K] += G[rows, N]^T A[rows, K],

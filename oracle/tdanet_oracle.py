@@ -62,6 +62,24 @@ class OracleConfig:
     tap_block: int = 0             # per-stage activations are recorded for this block only
     tap_all: bool = False          # record every block instead, keys "<name>@<block>" (backward-pass tests)
     cur_block: Optional[int] = field(default=None, repr=False)
+    # train-mode stochastic layers with EXPLICIT keep-masks (so a run can be compared element for element):
+    # drop_masks[block] = {"att" [T'*heads, B, B], "ao" [B, T', C], "f1" [B, T', 2C], "f2" [B, T', C], "dp" [2, B]}
+    # (bool / 0-1 tensors, channels-last like the CUDA workspace; missing keys = layer not applied).  Kept entries are
+    # scaled by 1/(1-p): nn.Dropout(dropout) (TDANet_best.py:210,212,251), the dropout on the attention weights of
+    # nn.MultiheadAttention(dropout) (:241), DropPath(drop_path) (:7-30,:262-263).
+    drop_masks: Optional[list] = field(default=None, repr=False)
+    dropout: float = 0.1
+    drop_path: float = 0.1
+
+    def mask(self, name):
+        """Multiplier tensor (mask / keep_prob) of stochastic layer `name` in the current block, or None."""
+        if self.drop_masks is None or self.cur_block is None:
+            return None
+        m = self.drop_masks[self.cur_block].get(name)
+        if m is None:
+            return None
+        p = self.drop_path if name == "dp" else self.dropout
+        return m.to(torch.get_default_dtype()) / (1.0 - p)
 
     @property
     def K(self) -> int:            # encoder window in samples
@@ -151,6 +169,8 @@ def mha_seq_first(x, w_in, b_in, w_out, b_out, n_head, cfg=None):
     k = k.reshape(S, N * n_head, d).transpose(0, 1)
     v = v.reshape(S, N * n_head, d).transpose(0, 1)
     p = torch.softmax(q @ k.transpose(1, 2), dim=-1)
+    if cfg is not None and cfg.mask("att") is not None:
+        p = p * cfg.mask("att").to(p.dtype)          # dropout on the attention weights, [N*heads, S, S]
     o = (p @ v).transpose(0, 1).reshape(S, N, E)
     if cfg is not None:
         _tap(cfg, "ga.attn_ctx", o)
@@ -175,9 +195,15 @@ def global_attention(sd, prefix, x, cfg):
         # batch_first=False fed [B, T', C]: the *batch* axis is the sequence axis,
         # and the "residual" doubles the attention output (bug-compatible)
         o = mha_seq_first(h, w_in, b_in, w_out, b_out, cfg.n_head, cfg)
-        post = o + o
+        m_ao = cfg.mask("ao")
+        post = o + (o if m_ao is None else o * m_ao.to(o.dtype))          # output + self.dropout(output)
+        if m_ao is not None:
+            o = post           # what the CUDA workspace keeps in train mode: out * (1 + mask / keep)
     _tap(cfg, "ga.attn_out", o)
     post = F.layer_norm(post, (C,), sd[f"{a}.norm.weight"], sd[f"{a}.norm.bias"], EPS_LN)
+    dp = cfg.mask("dp")
+    if dp is not None:
+        post = post * dp[0].to(post.dtype).view(-1, 1, 1)                  # self.drop_path(self.attn(x))
     x = x + post.transpose(1, 2)
     _tap(cfg, "ga.after_attn", x)
     # FFN
@@ -185,8 +211,14 @@ def global_attention(sd, prefix, x, cfg):
     y = conv_norm(sd, f"{m}.fc1", x, cfg)
     y = F.conv1d(y, sd[f"{m}.dwconv.weight"], sd[f"{m}.dwconv.bias"], padding=2, groups=y.shape[1])
     y = torch.relu(y)
+    if cfg.mask("f1") is not None:
+        y = y * cfg.mask("f1").to(y.dtype).transpose(1, 2)                 # FFN.drop after the activation
     _tap(cfg, "ga.ffn_dw", y)
     y = conv_norm(sd, f"{m}.fc2", y, cfg)
+    if cfg.mask("f2") is not None:
+        y = y * cfg.mask("f2").to(y.dtype).transpose(1, 2)                 # FFN.drop after fc2
+    if dp is not None:
+        y = y * dp[1].to(y.dtype).view(-1, 1, 1)                           # self.drop_path(self.mlp(x))
     return x + y
 
 

@@ -24,7 +24,8 @@ fptr = C.c_void_p  # device pointers travel as integers
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "variant", "out_channels", "in_channels", "num_blocks", "depth", "enc_kernel", "enc_stride",
-        "n_basis", "num_sources", "enc_convs", "n_head", "gemm_mode", "attn_group", "act_dtype")] + [("reserved", C.c_int32 * 2)]
+        "n_basis", "num_sources", "enc_convs", "n_head", "gemm_mode", "attn_group", "act_dtype")] + [
+        ("dropout", C.c_float), ("drop_path", C.c_float)]   # training-mode only (tdanet_forward_train_rng / tdanet_backward)
 
 
 class ConvNorm(C.Structure):
@@ -88,6 +89,8 @@ _SIGNATURES = {
     "tdanet_train_workspace_bytes": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "tdanet_forward_train": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), fptr, C.c_int, C.c_int, fptr, fptr,
                                        C.c_size_t, fptr]),
+    "tdanet_forward_train_rng": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), fptr, C.c_int, C.c_int, fptr, fptr,
+                                           C.c_size_t, fptr, fptr]),
     "tdanet_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Weights), fptr, fptr, C.c_int,
                                   C.c_int, fptr, C.c_size_t, fptr]),
     "tdanet_train_workspace_tensor": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_char_p, C.c_int,

@@ -229,34 +229,43 @@ static int launch_ln_bwd(const float* xin, float k1, const float* w, const float
 
 template <int D>
 static int launch_att_bwd_d(const float* qkv, const float* dctx, float* P, float* dS, float* dqkv, int B, int L, int C,
-                            int n_head, int group, int time_axis, cudaStream_t st) {
+                            int n_head, int group, int time_axis, const uint8_t* amask, float inv_keep, cudaStream_t st) {
   const int n = time_axis ? L : group;
   const int nprob = time_axis ? B : (B / group) * L;
   if (n <= 16) {
     const int warps = nprob * n_head;
-    if (n <= 8) TD_LAUNCH_COOP((att_bwd_warp_kernel<D, 8>), cdiv(warps, 4), 128, 0, st, qkv, dctx, dqkv, L, C, n, n_head, group, time_axis, warps);
-    else TD_LAUNCH_COOP((att_bwd_warp_kernel<D, 16>), cdiv(warps, 4), 128, 0, st, qkv, dctx, dqkv, L, C, n, n_head, group, time_axis, warps);
+    if (n <= 8) TD_LAUNCH_COOP((att_bwd_warp_kernel<D, 8>), cdiv(warps, 4), 128, 0, st, qkv, dctx, dqkv, L, C, n, n_head, group, time_axis, warps, amask, inv_keep);
+    else TD_LAUNCH_COOP((att_bwd_warp_kernel<D, 16>), cdiv(warps, 4), 128, 0, st, qkv, dctx, dqkv, L, C, n, n_head, group, time_axis, warps, amask, inv_keep);
     return 0;
   }
   const int total = nprob * n_head * n;
-  TD_LAUNCH((att_bwd_dq_kernel<D>), cdiv(total, 128), 128, 0, st, qkv, dctx, P, dS, dqkv, L, C, n, n_head, group, time_axis, total);
+  TD_LAUNCH((att_bwd_dq_kernel<D>), cdiv(total, 128), 128, 0, st, qkv, dctx, P, dS, dqkv, L, C, n, n_head, group, time_axis, total, amask, inv_keep);
   TD_LAUNCH((att_bwd_dkv_kernel<D>), cdiv(total, 128), 128, 0, st, qkv, dctx, P, dS, dqkv, L, C, n, n_head, group, time_axis, total);
   return 0;
 }
 
 static int launch_att_bwd(const float* qkv, const float* dctx, float* P, float* dS, float* dqkv, int B, int L, int C,
-                          int n_head, int group, int time_axis, cudaStream_t st) {
+                          int n_head, int group, int time_axis, const uint8_t* amask, float inv_keep, cudaStream_t st) {
   switch (C / n_head) {
-    case 64: return launch_att_bwd_d<64>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
-    case 32: return launch_att_bwd_d<32>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
-    case 16: return launch_att_bwd_d<16>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
-    case 8: return launch_att_bwd_d<8>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
-    case 4: return launch_att_bwd_d<4>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, st);
+    case 64: return launch_att_bwd_d<64>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, amask, inv_keep, st);
+    case 32: return launch_att_bwd_d<32>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, amask, inv_keep, st);
+    case 16: return launch_att_bwd_d<16>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, amask, inv_keep, st);
+    case 8: return launch_att_bwd_d<8>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, amask, inv_keep, st);
+    case 4: return launch_att_bwd_d<4>(qkv, dctx, P, dS, dqkv, B, L, C, n_head, group, time_axis, amask, inv_keep, st);
   }
   return fail(TDANET_EUNSUPPORTED, "attention backward: head dim %d not in {4,8,16,32,64}", C / n_head);
 }
 
 // dW[N, K] += G[R, N]^T f(A[R, K]);  db[N] += column sums of G (db may be null)
+int launch_mask_scale(const float* in, float* out, size_t n, const uint8_t* mask, float k0, float k1,
+                      const uint8_t* item_mask, float item_scale, size_t per_item, int round_out, cudaStream_t st) {
+  TD_REQUIRE(n % 4 == 0 && per_item > 0 && (item_mask == nullptr || per_item % 4 == 0), "mask_scale: n=%zu per_item=%zu", n, per_item);
+  const size_t n4 = n / 4;
+  TD_LAUNCH(mask_scale_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, in, out, n4, mask, k0, k1, item_mask, item_scale,
+            per_item, round_out);
+  return 0;
+}
+
 static int launch_wgrad(const float* G, const float* A, float* dW, float* db, int R, int N, int K,
                         const float* a_slope, cudaStream_t st, int gemm_mode = TDANET_GEMM_FP32) {
 #ifndef TD_EMU
@@ -418,18 +427,35 @@ static int global_attention_backward(const BCtx& x) {
   // ga_out = ga_mid + gLN(fc2)
   const NormRef n_fc2 = norm_ref(x, p.st_fc2, 2, (double)Lb * C, w->fc2.gamma, w->fc2.beta);
   const NormRef n_fc1 = norm_ref(x, p.st_fc1, 2, (double)Lb * 2 * C, w->fc1.gamma, w->fc1.beta);
+  // training-mode keep-masks of this iteration (drawn by the forward pass, dropout.cu); null when p = 0
+  const float ik = p.drop_elem ? 1.f / (1.f - c->dropout) : 1.f, ikp = p.drop_item ? 1.f / (1.f - c->drop_path) : 1.f;
+  const uint8_t* m_att = p.drop_elem ? x.at<uint8_t>(p.m_att) : nullptr;
+  const uint8_t* m_ao = p.drop_elem ? x.at<uint8_t>(p.m_ao) : nullptr;
+  const uint8_t* m_f1 = p.drop_elem ? x.at<uint8_t>(p.m_f1) : nullptr;
+  const uint8_t* m_f2 = p.drop_elem ? x.at<uint8_t>(p.m_f2) : nullptr;
+  const uint8_t* m_dp = p.drop_item ? x.at<uint8_t>(p.m_dp) : nullptr;
+  const size_t nRC = (size_t)R * C, per_item = (size_t)Lb * C;
   {
     Tag t("bwd_bottom_misc");
-    if (int e = launch_gln_bwd_stats(x.at(p.g_ga_out), x.at(p.fc2), n_fc2, x.gp(gw->fc2.gamma), x.gp(gw->fc2.beta),
+    // ga_out = ga_mid + DropPath(drop(gLN(fc2))): gradient w.r.t. the GlobLN output (g_attn_out is free here)
+    const float* dy = x.at(p.g_ga_out);
+    if (m_f2 || m_dp) {
+      if (int e = launch_mask_scale(dy, x.at(p.g_attn_out), nRC, m_f2, 0.f, ik, m_dp ? m_dp + B : nullptr, ikp, per_item, 0, x.st)) return e;
+      dy = x.at(p.g_attn_out);
+    }
+    if (int e = launch_gln_bwd_stats(dy, x.at(p.fc2), n_fc2, x.gp(gw->fc2.gamma), x.gp(gw->fc2.beta),
                                      x.at<double>(p.bs_fc2), B, Lb, C, x.st)) return e;
-    if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_ga_out), x.at(p.fc2), n_fc2, x.at<double>(p.bs_fc2)),
+    if (int e = launch_gln_bwd_apply(gln_grad(dy, x.at(p.fc2), n_fc2, x.at<double>(p.bs_fc2)),
                                      x.at(p.g_fc2), 0, B, Lb, C, x.st)) return e;
   }
   { Tag t("wgrad_fc2"); if (int e = wgrad_side(x, x.at(p.g_fc2), x.at(p.ffn_dw), x.gp(gw->fc2.w), nullptr, R, C, 2 * C)) return e; }
   { Tag t("dgrad_fc2"); if (int e = dgrad(x, x.at(p.g_fc2), p.wt_fc2, p.auxt_fc2, x.at(p.g_ffn), Lb, 2 * C, C, nullptr)) return e; }
   {
-    // relu -> dwconv k5 (+bias) on gLN(fc1)
+    // relu -> dwconv k5 (+bias) on gLN(fc1); FFN.drop sits after the ReLU: ffn_dw holds the dropped tensor, whose
+    // sign still marks the live elements, the gradient takes the mask / keep factor here
     Tag t("bwd_ffn_dw");
+    if (m_f1)
+      if (int e = launch_mask_scale(x.at(p.g_ffn), x.at(p.g_ffn), (size_t)R * 2 * C, m_f1, 0.f, ik, nullptr, 1.f, 1, 0, x.st)) return e;
     DwBwdArgs d{};
     d.g[0].dy = x.at(p.g_ffn); d.g[0].x = x.at(p.ffn_dw); d.g[0].kind = G_RELU;
     d.w[0] = w->ffn_dw_w; d.dw[0] = x.gp(gw->ffn_dw_w); d.db[0] = x.gp(gw->ffn_dw_b);
@@ -447,15 +473,23 @@ static int global_attention_backward(const BCtx& x) {
   { Tag t("wgrad_fc1"); if (int e = wgrad_side(x, x.at(p.g_ffn), x.at(p.ga_mid), x.gp(gw->fc1.w), nullptr, R, 2 * C, C)) return e; }
   // g_ga_mid = g_ga_out (skip) + fc1 data gradient
   { Tag t("dgrad_fc1"); if (int e = dgrad(x, x.at(p.g_ffn), p.wt_fc1, p.auxt_fc1, x.at(p.g_ga_mid), Lb, C, 2 * C, x.at(p.g_ga_out))) return e; }
-  // ga_mid = ga_in + LN2(2 * attn_out)
+  // ga_mid = ga_in + DropPath(LN2(2 * attn_out));  with dropout: LN2(attn_out') where the forward left
+  // attn_out' = attn_out * (1 + mask/keep) in the workspace
   { Tag t("bwd_bottom_misc");
-    if (int e = launch_ln_bwd(x.at(p.attn_out), 2.f, w->ln2_w, x.at(p.g_ga_mid), x.at(p.ln_rows), nullptr,
-                              x.at(p.g_attn_out), x.gp(gw->ln2_w), x.gp(gw->ln2_b), R, C, x.st)) return e; }
+    const float* dy = x.at(p.g_ga_mid);
+    if (m_dp) {  // g_ctx is free here
+      if (int e = launch_mask_scale(dy, x.at(p.g_ctx), nRC, nullptr, 1.f, 0.f, m_dp, ikp, per_item, 0, x.st)) return e;
+      dy = x.at(p.g_ctx);
+    }
+    if (int e = launch_ln_bwd(x.at(p.attn_out), m_ao ? 1.f : 2.f, w->ln2_w, dy, x.at(p.ln_rows), nullptr,
+                              x.at(p.g_attn_out), x.gp(gw->ln2_w), x.gp(gw->ln2_b), R, C, x.st)) return e;
+    if (m_ao)
+      if (int e = launch_mask_scale(x.at(p.g_attn_out), x.at(p.g_attn_out), nRC, m_ao, 1.f, ik, nullptr, 1.f, 1, 0, x.st)) return e; }
   { Tag t("wgrad_out_proj"); if (int e = wgrad_side(x, x.at(p.g_attn_out), x.at(p.attn_ctx), x.gp(gw->out_proj_w), x.gp(gw->out_proj_b), R, C, C)) return e; }
   { Tag t("dgrad_out_proj"); if (int e = dgrad(x, x.at(p.g_attn_out), p.wt_out, p.auxt_out, x.at(p.g_ctx), Lb, C, C, nullptr)) return e; }
   { Tag t("bwd_attention");
     if (int e = launch_att_bwd(x.at(p.qkv), x.at(p.g_ctx), x.at(p.att_p), x.at(p.att_ds), x.at(p.g_qkv), B, Lb, C,
-                               c->n_head, group, 0, x.st)) return e; }
+                               c->n_head, group, 0, m_att, ik, x.st)) return e; }
   { Tag t("wgrad_in_proj"); if (int e = wgrad_side(x, x.at(p.g_qkv), x.at(p.attn_in), x.gp(gw->in_proj_w), x.gp(gw->in_proj_b), R, 3 * C, C)) return e; }
   { Tag t("dgrad_in_proj"); if (int e = dgrad(x, x.at(p.g_qkv), p.wt_in, p.auxt_in, x.at(p.g_attn_in), Lb, C, 3 * C, nullptr)) return e; }
   // attn_in = LN1(ga_in) + pe;  g_ga_in = g_ga_mid (skip) + LN1 backward

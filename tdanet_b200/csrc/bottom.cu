@@ -135,14 +135,16 @@ int launch_ln_pe(const float* x, const float* w, const float* b, const float* pe
   return 0;
 }
 
-// y = resid + LN(k1*a + k2*xin)*w + b
+// y = resid + f*(LN(k1*a + k2*xin)*w + b);  f = DropPath multiplier of the row's item (training), else 1
 __global__ void ln_residual_kernel(const float* __restrict__ a, const float* __restrict__ xin,
                                    const float* __restrict__ resid, const float* __restrict__ w,
                                    const float* __restrict__ bias, float* __restrict__ y, float k1,
-                                   float k2, int rows, int C) {
+                                   float k2, int rows, int C, const uint8_t* __restrict__ item_mask,
+                                   float item_inv_keep, int L) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  const float f = item_mask ? (item_mask[row / L] ? item_inv_keep : 0.f) : 1.f;
   const float* ar = a + (size_t)row * C;
   const float* xr = xin ? xin + (size_t)row * C : nullptr;
   float mu, rstd;
@@ -159,30 +161,39 @@ __global__ void ln_residual_kernel(const float* __restrict__ a, const float* __r
     float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
     float4 r = *reinterpret_cast<const float4*>(resid + (size_t)row * C + c);
     float4 o;
-    o.x = r.x + ((v.x - mu) * rstd * g.x + bb.x);
-    o.y = r.y + ((v.y - mu) * rstd * g.y + bb.y);
-    o.z = r.z + ((v.z - mu) * rstd * g.z + bb.z);
-    o.w = r.w + ((v.w - mu) * rstd * g.w + bb.w);
+    if (item_mask) {
+      o.x = fmaf(f, (v.x - mu) * rstd * g.x + bb.x, r.x);
+      o.y = fmaf(f, (v.y - mu) * rstd * g.y + bb.y, r.y);
+      o.z = fmaf(f, (v.z - mu) * rstd * g.z + bb.z, r.z);
+      o.w = fmaf(f, (v.w - mu) * rstd * g.w + bb.w, r.w);
+    } else {
+      o.x = r.x + ((v.x - mu) * rstd * g.x + bb.x);
+      o.y = r.y + ((v.y - mu) * rstd * g.y + bb.y);
+      o.z = r.z + ((v.z - mu) * rstd * g.z + bb.z);
+      o.w = r.w + ((v.w - mu) * rstd * g.w + bb.w);
+    }
     *reinterpret_cast<float4*>(y + (size_t)row * C + c) = o;
   }
 }
 
 int launch_ln_residual(const float* a, const float* xin, const float* resid, const float* w,
-                       const float* b, float* y, int doubled, int B, int L, int C, cudaStream_t st) {
+                       const float* b, float* y, int mode, const DropRef& drop, int B, int L, int C, cudaStream_t st) {
   TD_REQUIRE(C % 4 == 0, "ln_residual: C=%d", C);
+  TD_REQUIRE(mode >= 0 && mode <= 2, "ln_residual: mode %d", mode);
   const int rows = B * L;
-  // doubled: LayerNorm(out + dropout(out)) == LN(2*out) in eval (TDANet_best.py:251)
-  const float k1 = doubled ? 2.f : 1.f, k2 = doubled ? 0.f : 1.f;
-  TD_LAUNCH(ln_residual_kernel, cdiv(rows, 8), 256, 0, st, a, doubled ? nullptr : xin, resid, w, b, y,
-            k1, k2, rows, C);
+  // mode 1: LayerNorm(out + dropout(out)) == LN(2*out) in eval (TDANet_best.py:251); mode 2: the caller folded the
+  // training-mode (1 + mask/keep) into `a`
+  const float k1 = mode == 1 ? 2.f : 1.f, k2 = mode == 0 ? 1.f : 0.f;
+  TD_LAUNCH(ln_residual_kernel, cdiv(rows, 8), 256, 0, st, a, mode == 0 ? xin : nullptr, resid, w, b, y,
+            k1, k2, rows, C, drop.item_mask, drop.item_inv_keep, L);
   return 0;
 }
 
 // ----------------------------------------------------------------------------- affine glue
-template <bool RES, bool STATS>
+template <bool RES, bool STATS, bool DROP = false>
 __global__ void affine_kernel(const float* __restrict__ x, NormRef norm,
                               const float* __restrict__ resid, float* __restrict__ y,
-                              float* __restrict__ chstats, int L, int C, int rows_per_cta) {
+                              float* __restrict__ chstats, int L, int C, int rows_per_cta, DropRef drop) {
   constexpr int V = 4;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -190,12 +201,21 @@ __global__ void affine_kernel(const float* __restrict__ x, NormRef norm,
   const int t0 = blockIdx.x * rows_per_cta, t1 = min(t0 + rows_per_cta, L);
   vf<V> sc, sh;
   norm_coef<V>(norm, b, ch, sc, sh);
+  float fi = 1.f;
+  if constexpr (DROP) fi = drop.item_mask ? (drop.item_mask[b] ? drop.item_inv_keep : 0.f) : 1.f;
   vf<V> s1 = vzero<V>(), s2 = vzero<V>();
   for (int t = t0; t < t1; ++t) {
     const size_t off = ((size_t)b * L + t) * C + ch;
     vf<V> v = vload<V>(x + off);
 #pragma unroll
     for (int e = 0; e < V; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
+    if constexpr (DROP) {
+      // FFN.drop after fc2's GlobLN (TDANet_best.py:212), then GA.drop_path on the branch (:263)
+      uchar4 mk = drop.mask ? *reinterpret_cast<const uchar4*>(drop.mask + off) : make_uchar4(1, 1, 1, 1);
+      const float fe = drop.mask ? drop.inv_keep * fi : fi;
+      v[0] = mk.x ? v[0] * fe : 0.f; v[1] = mk.y ? v[1] * fe : 0.f;
+      v[2] = mk.z ? v[2] * fe : 0.f; v[3] = mk.w ? v[3] * fe : 0.f;
+    }
     if constexpr (RES) {
       vf<V> r = vload<V>(resid + off);
 #pragma unroll
@@ -218,15 +238,23 @@ __global__ void affine_kernel(const float* __restrict__ x, NormRef norm,
 }
 
 int launch_affine_residual(const float* x, const NormRef& norm, const float* resid, float* y,
-                           float* chstats, int B, int L, int C, cudaStream_t st) {
+                           float* chstats, const DropRef& drop, int B, int L, int C, cudaStream_t st) {
   TD_REQUIRE(C % 4 == 0, "affine_residual: C=%d", C);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
   const int rows = 8;
   dim3 grid(cdiv(L, rows), cdiv(C / 4, threads), B);
+  if (drop.mask || drop.item_mask) {
+    if (chstats) {
+      TD_LAUNCH((affine_kernel<true, true, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, drop);
+    } else {
+      TD_LAUNCH((affine_kernel<true, false, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, drop);
+    }
+    return 0;
+  }
   if (chstats) {
-    TD_LAUNCH((affine_kernel<true, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows);
+    TD_LAUNCH((affine_kernel<true, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, DropRef{});
   } else {
-    TD_LAUNCH((affine_kernel<true, false>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows);
+    TD_LAUNCH((affine_kernel<true, false>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, DropRef{});
   }
   return 0;
 }
@@ -236,7 +264,7 @@ int launch_affine(const float* x, const NormRef& norm, float* y, int B, int L, i
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
   const int rows = 16;
   dim3 grid(cdiv(L, rows), cdiv(C / 4, threads), B);
-  TD_LAUNCH((affine_kernel<false, false>), grid, threads, 0, st, x, norm, nullptr, y, nullptr, L, C, rows);
+  TD_LAUNCH((affine_kernel<false, false>), grid, threads, 0, st, x, norm, nullptr, y, nullptr, L, C, rows, DropRef{});
   return 0;
 }
 
@@ -245,12 +273,17 @@ int launch_affine(const float* x, const NormRef& norm, float* y, int B, int L, i
 // per (problem, head).  A problem is a set of `n` tokens token(s) = base + s*stride:
 //   batch-axis (BEST / FORK, batch_first=False fed [B,T',C]): tokens of the `group` batch items
 //       that share a time index;  time-axis (MULTRES): the L tokens of one batch item.
-// One thread per query: q and the output accumulator live in registers, K/V chunks are staged in
-// shared memory and read as warp-wide broadcasts; online softmax over key chunks of 8.
-template <int D>
-__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv,
-                                                        float* __restrict__ ctx, int L, int C, int n,
-                                                        int group, int time_axis, int kchunk, int round_out) {
+// QL lanes share one query: lane j owns the float4 segments {j, j+QL, ...} of the head dimension for q, the score
+// partial sums (completed by xor-shuffles inside the lane group) and the output accumulator, so a CTA of 64
+// queries runs 64*QL threads; K/V chunks are staged in shared memory and read as 16-byte segments that are
+// contiguous across a lane group and broadcast across queries; online softmax over key chunks of 8.
+template <int D, int QL>
+__global__ void __launch_bounds__(64 * QL) attention_kernel(const float* __restrict__ qkv,
+                                                           float* __restrict__ ctx, int L, int C, int n,
+                                                           int group, int time_axis, int kchunk, int round_out,
+                                                           const uint8_t* __restrict__ amask, float inv_keep) {
+  constexpr int NS = D / QL / 4;  // float4 segments per lane
+  constexpr int DL = NS * 4;
   extern __shared__ float smem[];  // K [kchunk][D], V [kchunk][D]
   float* Ks = smem;
   float* Vs = smem + (size_t)kchunk * D;
@@ -265,23 +298,26 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     base = (long)grp * group * L + t;
     stride = L;
   }
-  const int q0 = blockIdx.z * blockDim.x;
-  const int qi = q0 + threadIdx.x;
+  const int qpc = blockDim.x / QL;
+  const int lq = threadIdx.x % QL;
+  const int qi = blockIdx.z * qpc + threadIdx.x / QL;
   const bool active = qi < n;
   const float scale = rsqrtf((float)D);
   const size_t C3 = (size_t)3 * C;
-  float q[D], o[D];
+  float q[DL], o[DL];
+#pragma unroll
+  for (int i = 0; i < DL; ++i) { q[i] = 0.f; o[i] = 0.f; }
   if (active) {
     const float* qp = qkv + (size_t)(base + (long)qi * stride) * C3 + head * D;
 #pragma unroll
-    for (int i = 0; i < D; i += 4) {
-      float4 v = *reinterpret_cast<const float4*>(qp + i);
-      q[i] = v.x * scale; q[i + 1] = v.y * scale; q[i + 2] = v.z * scale; q[i + 3] = v.w * scale;
+    for (int i = 0; i < NS; ++i) {
+      float4 v = *reinterpret_cast<const float4*>(qp + (lq + QL * i) * 4);
+      q[4 * i] = v.x * scale; q[4 * i + 1] = v.y * scale; q[4 * i + 2] = v.z * scale; q[4 * i + 3] = v.w * scale;
     }
   }
-#pragma unroll
-  for (int i = 0; i < D; ++i) o[i] = 0.f;
   float m = -FLT_MAX, l = 0.f;
+  // training: dropout on the normalised weights (nn.MultiheadAttention(dropout)); row of this query's keep-mask
+  const uint8_t* mrow = amask && active ? amask + (((size_t)prob * gridDim.y + head) * n + qi) * n : nullptr;
 
   for (int k0 = 0; k0 < n; k0 += kchunk) {
     const int kn = min(kchunk, n - k0);
@@ -293,46 +329,53 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
       *reinterpret_cast<float4*>(Vs + s * D + i) = *reinterpret_cast<const float4*>(kp + C);
     }
     __syncthreads();
-    if (active) {
-      for (int s0 = 0; s0 < kn; s0 += 8) {
-        float sc[8];
-        float cm = -FLT_MAX;
+    // inactive queries (q = 0) run along: the shuffles below need whole warps
+    for (int s0 = 0; s0 < kn; s0 += 8) {
+      float sc[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (s0 + u < kn) {
-            const float* kr = Ks + (s0 + u) * D;
-            float acc = 0.f;
+      for (int u = 0; u < 8; ++u) {
+        float acc = 0.f;
+        if (s0 + u < kn) {
+          const float* kr = Ks + (s0 + u) * D + lq * 4;
 #pragma unroll
-            for (int i = 0; i < D; i += 4) {
-              float4 kv = *reinterpret_cast<const float4*>(kr + i);
-              acc = fmaf(q[i], kv.x, acc); acc = fmaf(q[i + 1], kv.y, acc);
-              acc = fmaf(q[i + 2], kv.z, acc); acc = fmaf(q[i + 3], kv.w, acc);
-            }
-            sc[u] = acc;
-            cm = fmaxf(cm, acc);
-          } else {
-            sc[u] = -FLT_MAX;
+          for (int i = 0; i < NS; ++i) {
+            float4 kv = *reinterpret_cast<const float4*>(kr + QL * 4 * i);
+            acc = fmaf(q[4 * i], kv.x, acc); acc = fmaf(q[4 * i + 1], kv.y, acc);
+            acc = fmaf(q[4 * i + 2], kv.z, acc); acc = fmaf(q[4 * i + 3], kv.w, acc);
           }
         }
-        if (cm > m) {
-          const float f = expf(m - cm);
-          l *= f;
+        sc[u] = acc;
+      }
 #pragma unroll
-          for (int i = 0; i < D; ++i) o[i] *= f;
-          m = cm;
-        }
+      for (int off = 1; off < QL; off <<= 1) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (s0 + u < kn) {
-            const float p = expf(sc[u] - m);
-            l += p;
-            const float* vr = Vs + (s0 + u) * D;
+        for (int u = 0; u < 8; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], off);
+      }
+      float cm = -FLT_MAX;
 #pragma unroll
-            for (int i = 0; i < D; i += 4) {
-              float4 vv = *reinterpret_cast<const float4*>(vr + i);
-              o[i] = fmaf(p, vv.x, o[i]); o[i + 1] = fmaf(p, vv.y, o[i + 1]);
-              o[i + 2] = fmaf(p, vv.z, o[i + 2]); o[i + 3] = fmaf(p, vv.w, o[i + 3]);
-            }
+      for (int u = 0; u < 8; ++u) {
+        if (s0 + u >= kn) sc[u] = -FLT_MAX;
+        cm = fmaxf(cm, sc[u]);
+      }
+      if (cm > m) {
+        const float f = expf(m - cm);
+        l *= f;
+#pragma unroll
+        for (int i = 0; i < DL; ++i) o[i] *= f;
+        m = cm;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (s0 + u < kn) {
+          float p = expf(sc[u] - m);
+          l += p;
+          if (mrow) p = mrow[k0 + s0 + u] ? p * inv_keep : 0.f;
+          const float* vr = Vs + (s0 + u) * D + lq * 4;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            float4 vv = *reinterpret_cast<const float4*>(vr + QL * 4 * i);
+            o[4 * i] = fmaf(p, vv.x, o[4 * i]); o[4 * i + 1] = fmaf(p, vv.y, o[4 * i + 1]);
+            o[4 * i + 2] = fmaf(p, vv.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(p, vv.w, o[4 * i + 3]);
           }
         }
       }
@@ -341,38 +384,41 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   if (active) {
     const float inv = 1.f / l;
 #pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = round_out ? tf32_rna(o[i] * inv) : o[i] * inv;
+    for (int i = 0; i < DL; ++i) o[i] = round_out ? tf32_rna(o[i] * inv) : o[i] * inv;
     float* op = ctx + (size_t)(base + (long)qi * stride) * C + head * D;
 #pragma unroll
-    for (int i = 0; i < D; i += 4)
-      *reinterpret_cast<float4*>(op + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+    for (int i = 0; i < NS; ++i)
+      *reinterpret_cast<float4*>(op + (lq + QL * i) * 4) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
   }
 }
 
 template <int D>
 static int launch_attention_d(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
-                              int time_axis, int round_out, cudaStream_t st) {
+                              int time_axis, int round_out, const uint8_t* amask, float inv_keep, cudaStream_t st) {
+  constexpr int QL = D >= 16 ? 4 : D / 4;  // lanes per query, each owning >= one float4 of the head dimension
   const int n = time_axis ? L : group;
   const int nprob = time_axis ? B : (B / group) * L;
-  int threads = n >= 128 ? 128 : (n + 31) / 32 * 32;
+  const int qstep = 32 / QL;  // queries per warp
+  const int qpc = n >= 64 ? 64 : (n + qstep - 1) / qstep * qstep;
   int kchunk = n < 64 ? n : 64;  // 2*64*D floats <= 32 KB of static-limit shared memory
   kchunk = (kchunk + 7) / 8 * 8;
-  dim3 grid(nprob, n_head, cdiv(n, threads));
+  dim3 grid(nprob, n_head, cdiv(n, qpc));
   const size_t smem = (size_t)2 * kchunk * D * sizeof(float);
-  TD_LAUNCH((attention_kernel<D>), grid, threads, smem, st, qkv, ctx, L, C, n, group, time_axis, kchunk, round_out);
+  TD_LAUNCH((attention_kernel<D, QL>), grid, qpc * QL, smem, st, qkv, ctx, L, C, n, group, time_axis, kchunk, round_out,
+            amask, inv_keep);
   return 0;
 }
 
 int launch_attention(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
-                     int time_axis, int round_out, cudaStream_t st) {
+                     int time_axis, int round_out, const uint8_t* amask, float inv_keep, cudaStream_t st) {
   TD_REQUIRE(C % n_head == 0, "attention: C=%d n_head=%d", C, n_head);
   TD_REQUIRE(time_axis || (group > 0 && B % group == 0), "attention: batch %d not a multiple of group %d", B, group);
   switch (C / n_head) {
-    case 64: return launch_attention_d<64>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, st);
-    case 32: return launch_attention_d<32>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, st);
-    case 16: return launch_attention_d<16>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, st);
-    case 8: return launch_attention_d<8>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, st);
-    case 4: return launch_attention_d<4>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, st);
+    case 64: return launch_attention_d<64>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
+    case 32: return launch_attention_d<32>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
+    case 16: return launch_attention_d<16>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
+    case 8: return launch_attention_d<8>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
+    case 4: return launch_attention_d<4>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
   }
   return fail(TDANET_EUNSUPPORTED, "attention: head dim %d not in {4,8,16,32,64}", C / n_head);
 }

@@ -936,6 +936,32 @@ __global__ void ln_bwd_apply_kernel(const float* __restrict__ x, float k1, const
   vred_add<V>(db + ch, ab);
 }
 
+// ----------------------------------------------------------------------------- dropout multipliers
+// out[i] = in[i] * (k0 + k1*mask[i]) * (item_mask ? item_mask[i / per_item]*item_scale : 1); 4 elements per thread.
+// Applies nn.Dropout / DropPath keep-masks to an activation (forward) or to its gradient (backward).
+__global__ void mask_scale_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n4,
+                                  const uint8_t* __restrict__ mask, float k0, float k1,
+                                  const uint8_t* __restrict__ item_mask, float item_scale, size_t per_item,
+                                  int round_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = *reinterpret_cast<const float4*>(in + i * 4);
+  float f[4] = {k0 + k1, k0 + k1, k0 + k1, k0 + k1};
+  if (mask) {
+    const uint32_t mk = *reinterpret_cast<const uint32_t*>(mask + i * 4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) f[e] = ((mk >> (8 * e)) & 0xffu) ? k0 + k1 : k0;
+  }
+  if (item_mask) {
+    const float fi = item_mask[(i * 4) / per_item] ? item_scale : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) f[e] *= fi;
+  }
+  v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+  if (round_out) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
+  *reinterpret_cast<float4*>(out + i * 4) = v;
+}
+
 // ----------------------------------------------------------------------------- attention backward
 // Problem geometry as in attention_kernel (bottom.cu): token(s) = base + s*stride, n tokens per problem.
 // Scratch P, dS: [problem, head, query, key].
@@ -954,10 +980,13 @@ __device__ __forceinline__ void att_problem(int prob, int L, int group, int time
 template <int D>
 __global__ void att_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
                                   float* __restrict__ P, float* __restrict__ dS, float* __restrict__ dqkv,
-                                  int L, int C, int n, int n_head, int group, int time_axis, int total) {
+                                  int L, int C, int n, int n_head, int group, int time_axis, int total,
+                                  const uint8_t* __restrict__ amask, float inv_keep) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int i = idx % n, head = (idx / n) % n_head, prob = idx / (n * n_head);
+  // training dropout on the weights: ctx = (P o M/keep) V, so dP = (dO V^T) o M/keep and dV uses P o M/keep
+  const uint8_t* mrow = amask ? amask + ((size_t)(prob * n_head + head) * n + i) * n : nullptr;
   long base, stride;
   att_problem(prob, L, group, time_axis, base, stride);
   const float scale = rsqrtf((float)D);
@@ -988,6 +1017,7 @@ __global__ void att_bwd_dq_kernel(const float* __restrict__ qkv, const float* __
     float dp = 0.f;
     for (int d = 0; d < D; ++d) dp = fmaf(dop[d], vp[d], dp);
     const float p = prow[j] * inv;
+    if (mrow) dp = mrow[j] ? dp * inv_keep : 0.f;
     prow[j] = p;
     srow[j] = dp;
     dsum = fmaf(p, dp, dsum);
@@ -998,6 +1028,7 @@ __global__ void att_bwd_dq_kernel(const float* __restrict__ qkv, const float* __
   for (int j = 0; j < n; ++j) {
     const float ds = prow[j] * (srow[j] - dsum);
     srow[j] = ds;
+    if (mrow) prow[j] = mrow[j] ? prow[j] * inv_keep : 0.f;  // what att_bwd_dkv_kernel needs for dV
     const float* kp = qkv + (size_t)(base + (long)j * stride) * C3 + C + head * D;
 #pragma unroll
     for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, kp[d], dq[d]);
@@ -1049,7 +1080,8 @@ __global__ void att_bwd_dkv_kernel(const float* __restrict__ qkv, const float* _
 template <int D, int NMAX>
 __global__ void att_bwd_warp_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
                                     float* __restrict__ dqkv, int L, int C, int n, int n_head, int group,
-                                    int time_axis, int total_warps) {
+                                    int time_axis, int total_warps, const uint8_t* __restrict__ amask,
+                                    float inv_keep) {
   constexpr int EPL = D >= 32 ? D / 32 : 1;  // head-dim elements per lane
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -1105,20 +1137,27 @@ __global__ void att_bwd_warp_kernel(const float* __restrict__ qkv, const float* 
         l += s[j];
       }
       const float inv = 1.f / l;
+      // training dropout on the weights: mk[j] = keep-mask / keep_prob of (query i, key j), else 1
+      float mk[NMAX];
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j)
+        mk[j] = amask && j < n ? (amask[((size_t)wid * n + i) * n + j] ? inv_keep : 0.f) : 1.f;
       float dsum = 0.f;
 #pragma unroll
       for (int j = 0; j < NMAX; ++j) {
         s[j] *= inv;  // P[i][j]
+        dp[j] *= mk[j];
         dsum = fmaf(s[j], dp[j], dsum);
       }
 #pragma unroll
       for (int j = 0; j < NMAX; ++j) {
         const float ds = s[j] * (dp[j] - dsum);
+        const float pm = s[j] * mk[j];
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
           dq[i][e] = fmaf(ds, k[j][e], dq[i][e]);    // d s_ij / d q_i (scaled q): k_j
           dk[j][e] = fmaf(ds, q[i][e], dk[j][e]);    // q already carries the 1/sqrt(D)
-          dvv[j][e] = fmaf(s[j], dO[i][e], dvv[j][e]);
+          dvv[j][e] = fmaf(pm, dO[i][e], dvv[j][e]);
         }
       }
     }

@@ -106,15 +106,25 @@ static int global_attention(const Ctx& x) {
   g.A = x.at(p.attn_in); g.W = w->in_proj_w; g.bias = w->in_proj_b; g.D = x.at(p.qkv);
   g.B = B; g.L = Lb; g.N = 3 * C; g.K = C; g.epi = EPI_BIAS;
   { Tag t("gemm_in_proj"); if (int e = gemm(x, g, p.aux_in)) return e; }
+  // training-mode multipliers (nn.Dropout / DropPath keep-masks drawn by launch_dropout_masks): null in eval
+  const float ik = p.drop_elem ? 1.f / (1.f - c->dropout) : 1.f, ikp = p.drop_item ? 1.f / (1.f - c->drop_path) : 1.f;
+  const uint8_t* m_att = p.drop_elem ? x.at<uint8_t>(p.m_att) : nullptr;
+  const uint8_t* m_ao = p.drop_elem ? x.at<uint8_t>(p.m_ao) : nullptr;
+  const uint8_t* m_f1 = p.drop_elem ? x.at<uint8_t>(p.m_f1) : nullptr;
+  const uint8_t* m_f2 = p.drop_elem ? x.at<uint8_t>(p.m_f2) : nullptr;
+  const uint8_t* m_dp = p.drop_item ? x.at<uint8_t>(p.m_dp) : nullptr;
   { Tag t("attention");
-  if (int e = launch_attention(x.at(p.qkv), x.at(p.attn_ctx), B, Lb, C, c->n_head, group, time_axis, x.rnd(), x.st)) return e; }
+  if (int e = launch_attention(x.at(p.qkv), x.at(p.attn_ctx), B, Lb, C, c->n_head, group, time_axis, x.rnd(), m_att, ik, x.st)) return e; }
   g = GemmArgs{};
   g.A = x.at(p.attn_ctx); g.W = w->out_proj_w; g.bias = w->out_proj_b; g.D = x.at(p.attn_out);
   g.B = B; g.L = Lb; g.N = C; g.K = C; g.epi = EPI_BIAS;
   { Tag t("gemm_out_proj"); if (int e = gemm(x, g, p.aux_out)) return e; }
-  // x + LayerNorm(out + dropout(out))  [BEST/FORK]   |   x + LayerNorm(pe_in + out)  [MULTRES]
+  // x + DropPath(LayerNorm(out + dropout(out)))  [BEST/FORK]   |   x + LayerNorm(pe_in + out)  [MULTRES]
+  // training: attn_out <- out * (1 + mask/keep) in place (the backward pass expects it in this form)
+  if (m_ao)
+    if (int e = launch_mask_scale(x.at(p.attn_out), x.at(p.attn_out), (size_t)B * Lb * C, m_ao, 1.f, ik, nullptr, 1.f, 1, 0, x.st)) return e;
   if (int e = launch_ln_residual(x.at(p.attn_out), x.at(p.attn_in), x.at(p.ga_in), w->ln2_w, w->ln2_b,
-                                 x.at(p.ga_mid), !time_axis, B, Lb, C, x.st)) return e;
+                                 x.at(p.ga_mid), time_axis ? 0 : (m_ao ? 2 : 1), DropRef{nullptr, 1.f, m_dp, ikp}, B, Lb, C, x.st)) return e;
   // FFN: fc1 (1x1, no bias) -> gLN -> dw k5 + bias -> ReLU -> fc2 (1x1, no bias) -> gLN
   g = GemmArgs{};
   g.A = x.at(p.ga_mid); g.W = w->fc1.w; g.bias = nullptr; g.D = x.at(p.fc1);
@@ -125,6 +135,8 @@ static int global_attention(const Ctx& x) {
   d.kind = SRC_AFFINE; d.B = B; d.C = 2 * C; d.Lout = Lb; d.stride = 1; d.nw = 1;
   d.w[0] = w->ffn_dw_w; d.bias[0] = w->ffn_dw_b; d.out = x.at(p.ffn_dw); d.relu = 1; d.round_out = x.rnd();
   { Tag t("ffn_dw"); if (int e = launch_dw5(d, x.st)) return e; }
+  if (m_f1)  // FFN.drop after the ReLU, in place (x > 0 still marks the live elements for the backward pass)
+    if (int e = launch_mask_scale(x.at(p.ffn_dw), x.at(p.ffn_dw), (size_t)B * Lb * 2 * C, m_f1, 0.f, ik, nullptr, 1.f, 1, x.rnd(), x.st)) return e;
   g = GemmArgs{};
   g.A = x.at(p.ffn_dw); g.W = w->fc2.w; g.bias = nullptr; g.D = x.at(p.fc2);
   g.B = B; g.L = Lb; g.N = C; g.K = 2 * C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_fc2);
@@ -132,7 +144,8 @@ static int global_attention(const Ctx& x) {
   // global_f = x + gLN(fc2); BEST also needs its per-channel sums for the closed-form loc_glo_fus
   return launch_affine_residual(x.at(p.fc2), norm_ref(x, p.st_fc2, 2, (double)Lb * C, w->fc2.gamma, w->fc2.beta),
                                 x.at(p.ga_mid), x.at(p.ga_out),
-                                c->variant == TDANET_BEST ? x.at(p.st_g) : nullptr, B, Lb, C, x.st);
+                                c->variant == TDANET_BEST ? x.at(p.st_g) : nullptr,
+                                DropRef{m_f2, ik, m_dp ? m_dp + B : nullptr, ikp}, B, Lb, C, x.st);
 }
 
 // One UConvBlock (TDANet_best.py:342-380) including the concat_block that feeds the next one.
@@ -297,9 +310,12 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
 }
 
 static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const float* wav, int B, int T,
-                   float* est, void* workspace, size_t ws_bytes, cudaStream_t st, bool train) {
+                   float* est, void* workspace, size_t ws_bytes, cudaStream_t st, bool train,
+                   uint64_t* rng_state = nullptr) {
   Plan p;
   if (int e = make_plan(c, B, T, p, train)) return e;
+  TD_REQUIRE(!(p.drop_elem || p.drop_item) || rng_state,
+             "dropout %g / drop_path %g > 0 needs tdanet_forward_train_rng", (double)c->dropout, (double)c->drop_path);
   TD_REQUIRE(w && wav && est && workspace, "NULL argument");
   if (ws_bytes < p.bytes) return fail(TDANET_ENOSPACE, "workspace has %zu bytes, need %zu", ws_bytes, p.bytes);
   TD_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
@@ -321,6 +337,21 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
     if (int e = launch_affine(x.at(p.enc), enc_norm, x.at(p.x0), B, L0, Nb, st)) return e;
   } else {
     if (int e = launch_bottleneck(x.at(p.enc), enc_norm, w->bottleneck_w, w->bottleneck_b, x.at(p.x0), B, L0, Nb, cc, st)) return e;
+  }
+  if (p.drop_elem || p.drop_item) {
+    // every keep-mask of every iteration, one launch (dropout.cu)
+    MaskRegion reg[5];
+    int n = 0;
+    const uint32_t te = (uint32_t)((double)c->dropout * 4294967296.0), tp = (uint32_t)((double)c->drop_path * 4294967296.0);
+    if (p.drop_elem) {
+      reg[n++] = MaskRegion{p.m_att, p.n_att, te, 0};
+      reg[n++] = MaskRegion{p.m_ao, (size_t)B * p.Lb * c->in_channels, te, 1};
+      reg[n++] = MaskRegion{p.m_f1, (size_t)B * p.Lb * 2 * c->in_channels, te, 2};
+      reg[n++] = MaskRegion{p.m_f2, (size_t)B * p.Lb * c->in_channels, te, 3};
+    }
+    if (p.drop_item) reg[n++] = MaskRegion{p.m_dp, (size_t)2 * B, tp, 4};
+    Tag tdm("dropout_masks");
+    if (int e = launch_dropout_masks(x.ws, p.blk_stride, c->num_blocks, reg, n, rng_state, st)) return e;
   }
   // Recurrent: num_blocks iterations of one shared UConvBlock
   for (int blk = 0; blk < c->num_blocks; ++blk) {
@@ -424,6 +455,12 @@ int tdanet_forward(const tdanet_config_t* cfg, const tdanet_weights_t* w, const 
 int tdanet_forward_train(const tdanet_config_t* cfg, const tdanet_weights_t* w, const float* wav, int batch,
                          int n_samples, float* est, void* workspace, size_t workspace_bytes, tdanet_stream_t stream) {
   return forward(cfg, w, wav, batch, n_samples, est, workspace, workspace_bytes, (cudaStream_t)stream, true);
+}
+
+int tdanet_forward_train_rng(const tdanet_config_t* cfg, const tdanet_weights_t* w, const float* wav, int batch,
+                             int n_samples, float* est, void* workspace, size_t workspace_bytes, uint64_t* rng_state,
+                             tdanet_stream_t stream) {
+  return forward(cfg, w, wav, batch, n_samples, est, workspace, workspace_bytes, (cudaStream_t)stream, true, rng_state);
 }
 
 size_t tdanet_gemm_workspace_bytes(int N, int K) { return ((size_t)N * K * sizeof(float) + 255) / 256 * 256; }

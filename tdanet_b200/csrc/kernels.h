@@ -109,14 +109,40 @@ int launch_ln_pe(const float* x, const float* w, const float* b, const float* pe
                  int L, int C, int round_out, cudaStream_t st);
 // multi-head attention core on packed qkv [B*L, 3C]; ctx [B*L, C]
 //   time_axis=0: sequence = the `group` batch items sharing a time index; 1: sequence = time
+//   amask (training, may be null): keep-mask bytes [problem*head, query, key] of the dropout on the attention
+//   weights; kept weights are scaled by inv_keep
 int launch_attention(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
-                     int time_axis, int round_out, cudaStream_t st);
-// y = resid + LayerNorm_C(post)*w + b ; post = 2*a (doubled=1) or xin + a (doubled=0)
+                     int time_axis, int round_out, const uint8_t* amask, float inv_keep, cudaStream_t st);
+// Training-mode multipliers of a residual branch: element keep-mask (nn.Dropout) and per-item keep-mask (DropPath),
+// both optional byte tensors; kept entries are scaled by the matching inv_keep.
+struct DropRef {
+  const uint8_t* mask;       // [B, L, C] or null
+  float inv_keep;
+  const uint8_t* item_mask;  // [B] or null
+  float item_inv_keep;
+};
+// y = resid + f_b * (LayerNorm_C(post)*w + b) ; post = 2*a (mode 1), xin + a (mode 0) or a (mode 2: the dropout of
+// `a + dropout(a)` was already folded into a); f_b: DropPath multiplier of drop.item_mask (1 if null)
 int launch_ln_residual(const float* a, const float* xin, const float* resid, const float* w,
-                       const float* b, float* y, int doubled, int B, int L, int C, cudaStream_t st);
-// y = resid + GlobLN(x); optional per-channel stats of y -> [B,2,C]
+                       const float* b, float* y, int mode, const DropRef& drop, int B, int L, int C, cudaStream_t st);
+// y = resid + f_b * m * GlobLN(x) (m, f_b: multipliers of `drop`); optional per-channel stats of y -> [B,2,C]
 int launch_affine_residual(const float* x, const NormRef& norm, const float* resid, float* y,
-                           float* chstats, int B, int L, int C, cudaStream_t st);
+                           float* chstats, const DropRef& drop, int B, int L, int C, cudaStream_t st);
+// ------------------------------------------------------------------ dropout.cu (training only)
+struct MaskRegion {
+  size_t off;      // byte offset inside one iteration's block arena
+  size_t n;        // mask bytes (padded to a multiple of 16 by the generator's index space)
+  uint32_t thresh; // keep  <=>  u32 >= thresh
+  uint32_t site;   // 0 m_att, 1 m_ao, 2 m_f1, 3 m_f2, 4 m_dp: part of the Philox counter
+};
+// draws the keep-masks of every region for iterations [0, n_blk): base + blk*blk_stride + region.off; then
+// rng_state[1] += 1 (device uint64[2] = {seed, offset})
+int launch_dropout_masks(char* base, size_t blk_stride, int n_blk, const MaskRegion* regions, int n_regions,
+                         uint64_t* rng_state, cudaStream_t st);
+// out[i] = in[i] * (k0 + k1*mask[i]) * (item_mask ? item_mask[i / per_item]*item_scale : 1), optionally rounded to
+// TF32; mask / item_mask may be null (mask null: factor k0 + k1); in == out allowed.  (backward.cu)
+int launch_mask_scale(const float* in, float* out, size_t n, const uint8_t* mask, float k0, float k1,
+                      const uint8_t* item_mask, float item_scale, size_t per_item, int round_out, cudaStream_t st);
 // y = GlobLN(x)
 int launch_affine(const float* x, const NormRef& norm, float* y, int B, int L, int C, cudaStream_t st);
 

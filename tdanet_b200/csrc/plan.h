@@ -52,6 +52,10 @@ struct Plan {
   size_t bin, y;                    // block arena: input of the block (blocks > 0) / res_conv output before concat_block
   size_t fused[TDANET_MAX_DEPTH];   // block arena: x_fused[k] materialised
   size_t st_lgf[TDANET_MAX_DEPTH];  // block arena: [B,3,2] double sums of loc_glo_fus[k] local / act / embedding conv outputs
+  // block arena: dropout keep-masks (bytes) of this iteration; valid when drop_elem / drop_item
+  bool drop_elem = false, drop_item = false;  // cfg->dropout > 0 / cfg->drop_path > 0
+  size_t m_begin = 0, m_att = 0, m_ao = 0, m_f1 = 0, m_f2 = 0, m_dp = 0, m_end = 0;
+  size_t n_att = 0;                 // bytes of m_att
   size_t mlogit;                    // mask_net output before ReLU [B, L0, n_src*Nb]
   size_t nenc;                      // GlobLN(enc) [B, L0, Nb] (operand of the bottleneck weight gradient)
   // transposed weights for the data-gradient GEMMs (+ their TF32 copies)
@@ -130,6 +134,8 @@ static inline int check_train_config(const tdanet_config_t* c) {
     return fail(TDANET_EUNSUPPORTED, "training step: TDANetMultRes (variant 2) has no backward pass in this build");
   if (c->act_dtype != TDANET_ACT_F32)
     return fail(TDANET_EUNSUPPORTED, "training step: activations are kept in fp32 (act_dtype fp32)");
+  TD_REQUIRE(c->dropout >= 0.f && c->dropout < 1.f && c->drop_path >= 0.f && c->drop_path < 1.f,
+             "dropout %g / drop_path %g outside [0, 1)", (double)c->dropout, (double)c->drop_path);
   return 0;
 }
 
@@ -222,6 +228,24 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     }
     p.fused_a = p.fused[depth - 2];
     p.fused_b = p.fused[first_step_partner(depth)];
+    p.drop_elem = c->dropout > 0.f;
+    p.drop_item = c->drop_path > 0.f;
+    if (p.drop_elem || p.drop_item) {
+      auto bytes_of = [&](const char* name, int64_t d0, int64_t d1, int64_t d2) {
+        size_t o = p.take((size_t)(d0 * d1 * d2));
+        p.named.push_back({name, o, {d0, d1, d2}, 1});
+        return o;
+      };
+      const int group = c->attn_group > 0 ? c->attn_group : B;
+      p.m_begin = p.bytes;
+      p.n_att = (size_t)B * Lb * c->n_head * group;
+      p.m_att = bytes_of("m_att", (int64_t)(B / group) * Lb * c->n_head, group, group);
+      p.m_ao = bytes_of("m_ao", B, Lb, C);
+      p.m_f1 = bytes_of("m_f1", B, Lb, 2 * C);
+      p.m_f2 = bytes_of("m_f2", B, Lb, C);
+      p.m_dp = bytes_of("m_dp", 2, B, 1);
+      p.m_end = p.bytes;
+    }
   } else {
     p.fused_a = p.act("fused_a", p.L[depth - 2], C);
     p.fused_b = p.act("fused_b", p.L[first_step_partner(depth)], C);

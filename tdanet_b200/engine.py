@@ -47,6 +47,7 @@ class SeparationEngine:
         self._tws: Dict[torch.device, torch.Tensor] = {}   # training workspace (activations of every block)
         self._graphs: Dict[Tuple, Tuple] = {}
         self._keep = None  # tensors referenced by the packed weight struct
+        self._rng: Dict[torch.device, torch.Tensor] = {}   # device int64[2] = {seed, offset} of the dropout masks
 
     # ------------------------------------------------------------------ configuration
     @property
@@ -66,6 +67,21 @@ class SeparationEngine:
     def act_dtype(self, dtype: str) -> None:
         self.cfg.act_dtype = _lib.ACT_DTYPES[dtype]
         self._graphs.clear()
+
+    def set_dropout(self, dropout: float, drop_path: float) -> None:
+        """Training-mode probabilities of forward_train / backward (the reference hard-codes 0.1 / 0.1,
+        TDANet_best.py:256-259,335-337); 0 / 0 is the deterministic form every parity test uses."""
+        self.cfg.dropout, self.cfg.drop_path = float(dropout), float(drop_path)
+
+    def rng_state(self, device, seed: Optional[int] = None) -> torch.Tensor:
+        """Device int64[2] = {seed, offset} that tdanet_forward_train_rng reads and advances.  Seeded from
+        torch's default generator on first use (so torch.manual_seed makes the masks reproducible)."""
+        device = torch.device(device)
+        if seed is not None or device not in self._rng:
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self._rng[device] = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        return self._rng[device]
 
     def latent_lengths(self, n_samples: int):
         lens = (C.c_int32 * _lib.MAX_DEPTH)()
@@ -209,7 +225,7 @@ class SeparationEngine:
                                                         C.byref(off), C.byref(dims), C.byref(es)))
         ws = self._tws[torch.device(device)]
         n = dims[0] * dims[1] * dims[2]
-        dt = torch.float32 if es.value == 4 else torch.float64
+        dt = {1: torch.uint8, 4: torch.float32, 8: torch.float64}[es.value]
         return ws[off.value: off.value + es.value * n].view(dt).view(dims[0], dims[1], dims[2])
 
     def _check_wav(self, wav):
@@ -231,8 +247,13 @@ class SeparationEngine:
                 out = torch.empty(B, self.cfg.num_sources, T, dtype=torch.float32, device=wav.device)
             self.cfg.attn_group = attn_group
             stream = torch.cuda.current_stream(wav.device).cuda_stream
-            check(lib.tdanet_forward_train(C.byref(self.cfg), C.byref(weights), wav.data_ptr(), B, T, out.data_ptr(),
-                                           ws.data_ptr(), ws.numel(), stream))
+            if self.cfg.dropout > 0 or self.cfg.drop_path > 0:
+                rng = self.rng_state(wav.device)
+                check(lib.tdanet_forward_train_rng(C.byref(self.cfg), C.byref(weights), wav.data_ptr(), B, T,
+                                                   out.data_ptr(), ws.data_ptr(), ws.numel(), rng.data_ptr(), stream))
+            else:
+                check(lib.tdanet_forward_train(C.byref(self.cfg), C.byref(weights), wav.data_ptr(), B, T, out.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), stream))
         return out
 
     def backward(self, weights: Weights, grad_weights: Weights, wav: torch.Tensor, d_est: torch.Tensor,

@@ -25,6 +25,7 @@ class _SeparateFn(torch.autograd.Function):
     def forward(ctx, model, wav, names, *params):
         ctx.model, ctx.names = model, names
         ctx.save_for_backward(wav, *params)
+        model._sync_dropout()
         return model._engine.forward_train(model._weights(), wav, model.attn_group)
 
     @staticmethod
@@ -84,6 +85,10 @@ class _TDANetCommon(BaseModel):
         # knobs of this implementation (not in the reference signature)
         self.attn_group = 0       # 0: the call's whole batch attends together, like the reference
         self.use_cuda_graph = False
+        # train-mode regularisation, hard-coded in the reference (GA(..., 0.1): DropPath; MultiHeadAttention(.., 0.1),
+        # FFN(drop=0.1): nn.Dropout; TDANet_best.py:256-259,335-337).  Applied only while `self.training`.
+        self.dropout = 0.1
+        self.drop_path = 0.1
 
     # ------------------------------------------------------------------ engine access
     @property
@@ -106,6 +111,16 @@ class _TDANetCommon(BaseModel):
     @act_dtype.setter
     def act_dtype(self, dtype: str) -> None:
         self._engine.act_dtype = dtype
+
+    def _sync_dropout(self) -> None:
+        """Hands the train-mode dropout / DropPath probabilities to the engine (0 / 0 in eval mode, like nn.Dropout)."""
+        on = self.training
+        self._engine.set_dropout(self.dropout if on else 0.0, self.drop_path if on else 0.0)
+
+    def manual_seed(self, seed: int, device=None) -> None:
+        """Seeds the Philox stream of the dropout masks on `device` (default: the parameters' device)."""
+        device = device if device is not None else next(self.parameters()).device
+        self._engine.rng_state(device, seed)
 
     def _weights(self):
         # (re)pack when any storage moved (e.g. after .cuda() / load_state_dict with assign)
@@ -137,8 +152,8 @@ class _TDANetCommon(BaseModel):
                 f"{type(self).__name__} (tdanet_b200) runs on CUDA tensors only; there is no CPU fallback")
         wav = input_wav.float().contiguous()
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # gradients w.r.t. the parameters through the hand-written backward pass (TDANetBest / TDANet; dropout and
-            # DropPath are not applied).  There is no gradient w.r.t. the waveform.
+            # gradients w.r.t. the parameters through the hand-written backward pass; in train mode with the
+            # reference's dropout / DropPath.  There is no gradient w.r.t. the waveform.
             if self._variant in ("best", "fork", "origin", "yang"):
                 named = [(n, p) for n, p in self.named_parameters()]
                 est = _SeparateFn.apply(self, wav, tuple(n for n, _ in named), *[p for _, p in named])

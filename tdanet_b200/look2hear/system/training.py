@@ -12,8 +12,10 @@ tdanet_adam_step.  Parameters, gradients and the Adam moments live in flat buffe
 `nn.Parameter` of the model (and its `.grad`) is a view into them, so `state_dict()`, checkpoints and
 `torch.optim` interoperate unchanged.
 
-Dropout / DropPath (p = 0.1 in the reference's train mode) are not applied: the step is deterministic
-(the stochastic masks cannot be matched bit for bit and parity is defined at p = 0).
+Dropout / DropPath (p = 0.1 in the reference's train mode) are applied while
+`model.training`: the keep-masks are drawn on the device (Philox, csrc/dropout.cu) inside the same enqueue, so
+a CUDA-graph replay of the step draws fresh masks.  `model.dropout = model.drop_path = 0.0` (or `.eval()`)
+gives the deterministic step the parity tests compare with autograd of the oracle.
 """
 from __future__ import annotations
 
@@ -106,6 +108,7 @@ class TrainingStep:
         wav = mixtures.float().contiguous()
         eng = self.model.engine
         w, gw = self._pack()
+        self.model._sync_dropout()
         est = eng.forward_train(w, wav, self.model.attn_group)
         loss, _, _, d_est = pit_loss(est, targets, self.loss.loss_func.sdr_type, self.loss.threshold_byloss,
                                      want_grad=True)

@@ -96,7 +96,7 @@ class Workspace:
         _check(self.lib, self.lib.tdanet_train_workspace_tensor(C.byref(self.cfg), self.B, self.T, name.encode(), block,
                                                                 C.byref(off), C.byref(dims), C.byref(es)))
         n = dims[0] * dims[1] * dims[2]
-        dt = np.float32 if es.value == 4 else np.float64
+        dt = {1: np.uint8, 4: np.float32, 8: np.float64}[es.value]
         raw = self.buf[self.base + off.value: self.base + off.value + n * es.value]
         return raw.view(dt).reshape(dims[0], dims[1], dims[2])
 
@@ -121,9 +121,32 @@ def _stats(*raws):
     return torch.stack(out, dim=1)
 
 
-def fill_workspace(ws: Workspace, taps, kw, variant="best"):
+def random_drop_masks(B, Lb, C, n_head, num_blocks, dropout, drop_path, seed=11):
+    """Keep-masks of every stochastic layer of every block in the layout of the CUDA workspace / OracleConfig.drop_masks."""
+    g = torch.Generator().manual_seed(seed)
+    keep = lambda shape, p: (torch.rand(shape, generator=g) >= p).to(torch.uint8)
+    out = []
+    for _ in range(num_blocks):
+        m = {}
+        if dropout > 0:
+            m.update(att=keep((Lb * n_head, B, B), dropout), ao=keep((B, Lb, C), dropout),
+                     f1=keep((B, Lb, 2 * C), dropout), f2=keep((B, Lb, C), dropout))
+        if drop_path > 0:
+            m["dp"] = keep((2, B), drop_path)
+        out.append(m)
+    return out
+
+
+def fill_workspace(ws: Workspace, taps, kw, variant="best", drop_masks=None):
     """What tdanet_forward_train leaves in the workspace, written from the taps of an oracle forward."""
     depth, nb = kw["upsampling_depth"], kw["num_blocks"]
+    if drop_masks is not None:
+        for b, m in enumerate(drop_masks):
+            for key, name in (("att", "m_att"), ("ao", "m_ao"), ("f1", "m_f1"), ("f2", "m_f2")):
+                if key in m:
+                    ws.put(name, m[key], b)
+            if "dp" in m:
+                ws.put("m_dp", m["dp"].unsqueeze(-1), b)
     u = "sm.unet"
     ws.put("enc", _cl(taps["enc"]))
     ws.put("st_enc", _stats(taps["enc"]))
@@ -173,17 +196,20 @@ def fill_workspace(ws: Workspace, taps, kw, variant="best"):
         ws.put("ga_out", _cl(t("ga.out")), b)
 
 
-def emu_backward(sd, wav, d_est, kw, sample_rate, variant="best"):
+def emu_backward(sd, wav, d_est, kw, sample_rate, variant="best", dropout=0.0, drop_path=0.0, drop_masks=None):
     """Gradients of sum(est * d_est) w.r.t. every parameter, computed by the emulated CUDA backward pass.
-    Returns (grads dict keyed like the state_dict, oracle output)."""
+    Returns (grads dict keyed like the state_dict, oracle output).  drop_masks: explicit keep-masks of a train-mode
+    step (OracleConfig.drop_masks), written into the workspace where the forward pass would have drawn them."""
     lib = load_emu()
     eng = make_engine(kw, sample_rate, variant=variant)
-    cfg = O.OracleConfig(variant=variant, sample_rate=sample_rate, taps={}, tap_all=True, **kw)
+    eng.set_dropout(dropout, drop_path)
+    cfg = O.OracleConfig(variant=variant, sample_rate=sample_rate, taps={}, tap_all=True, drop_masks=drop_masks,
+                         dropout=dropout, drop_path=drop_path, **kw)
     with torch.no_grad():
         est = O.forward(sd, wav, cfg)
     B, T = wav.shape[0], wav.shape[-1]
     ws = Workspace(lib, eng.cfg, B, T)
-    fill_workspace(ws, cfg.taps, kw, variant)
+    fill_workspace(ws, cfg.taps, kw, variant, drop_masks)
     sd_c = {k: v.detach().contiguous().float() for k, v in sd.items()}
     grads = {k: torch.zeros_like(v) for k, v in sd_c.items() if not k.endswith("pos_enc.pe")}
     w = eng.pack(sd_c, _allow_host=True)

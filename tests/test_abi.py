@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert lib.tdanet_abi_version() == 2
+    assert lib.tdanet_abi_version() == 3
 
 
 def test_struct_sizes_match():

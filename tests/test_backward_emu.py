@@ -28,9 +28,9 @@ def _model_sd(kw, seed=0, variant="best"):
     return sd
 
 
-def _autograd(sd, wav, d_est, kw, variant="best"):
+def _autograd(sd, wav, d_est, kw, variant="best", **drop):
     sd64 = {k: v.double().requires_grad_(not k.endswith("pos_enc.pe")) for k, v in sd.items()}
-    est = O.forward(sd64, wav.double(), O.OracleConfig(variant=variant, sample_rate=SR, **kw))
+    est = O.forward(sd64, wav.double(), O.OracleConfig(variant=variant, sample_rate=SR, **kw, **drop))
     (est * d_est.double()).sum().backward()
     return {k: v.grad for k, v in sd64.items() if not k.endswith("pos_enc.pe")}
 
@@ -70,3 +70,39 @@ def test_emulated_backward_matches_autograd(variant, name, B, T):
         worst = max(worst, rel)
         assert rel < 2e-4, f"{k}: max-rel {rel:.3e} (|ref|max {scale:.3e})"
     print(f"{variant}/{name}: worst max-rel gradient error {worst:.2e}")
+
+
+@pytest.mark.parametrize("variant,name,B,T,dropout,drop_path", [
+    ("best", "depth4", 3, 1203, 0.1, 0.1), ("best", "depth3", 2, 997, 0.3, 0.0), ("best", "depth4", 4, 1203, 0.0, 0.4),
+    ("fork", "depth4", 3, 1203, 0.2, 0.3), ("origin", "depth4", 2, 1203, 0.1, 0.1)])
+def test_emulated_backward_with_dropout_masks(variant, name, B, T, dropout, drop_path):
+    """Train-mode stochastic layers: with the SAME keep-masks in the workspace and in the oracle,
+    the emulated backward pass matches autograd of the oracle through nn.Dropout / attention-weight dropout / DropPath."""
+    kw = CASES[name]
+    sd = _model_sd(kw, variant=variant)
+    g = torch.Generator().manual_seed(9)
+    wav = torch.randn(B, 1, T, generator=g) * 0.1
+    d_est = torch.randn(B, kw["num_sources"], T, generator=g)
+    eng = H.make_engine(kw, SR, variant=variant)
+    Lb = eng.latent_lengths(T)[0][-1]
+    masks = H.random_drop_masks(B, Lb, kw["in_channels"], 8, kw["num_blocks"], dropout, drop_path)
+    if drop_path > 0:
+        masks[0]["dp"][0, 0] = 0          # at least one dropped and one kept path
+        masks[0]["dp"][1, -1] = 0
+        masks[-1]["dp"][0, -1] = 1
+    grads, est, _ = H.emu_backward(sd, wav, d_est, kw, SR, variant, dropout, drop_path, masks)
+    drop = dict(drop_masks=masks, dropout=dropout, drop_path=drop_path)
+    ref = _autograd(sd, wav, d_est, kw, variant, **drop)
+    # the masks matter: the deterministic forward gives another output
+    est0 = O.forward(sd, wav, O.OracleConfig(variant=variant, sample_rate=SR, **kw))
+    assert (est - est0).abs().max().item() > 1e-4 * est0.abs().max().item()
+    worst = 0.0
+    for k, r in ref.items():
+        if r is None:
+            assert grads[k].abs().max().item() == 0.0, k
+            continue
+        scale = r.abs().max().item()
+        rel = (grads[k].double() - r).abs().max().item() / max(scale, 1e-12)
+        worst = max(worst, rel)
+        assert rel < 2e-4, f"{k}: max-rel {rel:.3e} (|ref|max {scale:.3e})"
+    print(f"{variant}/{name} dropout {dropout} drop_path {drop_path}: worst max-rel gradient error {worst:.2e}")

@@ -20,6 +20,7 @@ PE = "sm.unet.globalatt.attn.pos_enc.pe"
 def _model(kw, sd, sr=SR, variant="best"):
     m = getattr(look2hear.models, CLASS[variant])(sample_rate=sr, **kw)
     m.load_state_dict({k: v for k, v in sd.items() if k != PE}, strict=False)
+    m.dropout = m.drop_path = 0.0   # the deterministic step; the train-mode masks have their own tests below
     return m.to(DEV)
 
 
@@ -122,6 +123,7 @@ def test_gradient_is_linear_in_d_est_at_headline_shape():
     m = look2hear.models.TDANetBest(out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=5,
                                     enc_kernel_size=4, num_sources=2, sample_rate=16000).to(DEV).train()
     m.gemm_mode = "fp32"
+    m.dropout = m.drop_path = 0.0
     B, T = 8, 32000
     g = torch.Generator().manual_seed(3)
     wav = (torch.randn(B, 1, T, generator=g) * 0.1).to(DEV)
@@ -150,6 +152,7 @@ def test_full_size_gradients_match_autograd():
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     m = m.to(DEV).train()
     m.gemm_mode = "fp32"
+    m.dropout = m.drop_path = 0.0
     wav, d_est = _inputs(kw, 1, 8000, seed=11)
     (m(wav.to(DEV)) * d_est.to(DEV)).sum().backward()
     sdr = {k: v.clone().requires_grad_(k != PE) for k, v in sd.items()}
@@ -343,3 +346,156 @@ def test_checkpoint_resume_and_metrics(tmp_path):
     assert torch.allclose(s.cpu(), best, atol=2e-3)
     assert abs(val.item() + s.mean().item()) < 5e-3
     assert si.shape == (4,)
+
+
+# ----------------------------------------------------------------------------- train-mode stochastic layers (§8 a21)
+def _philox4x32_10(ctr, key):
+    """numpy restatement of Philox4x32-10 (Salmon et al., SC'11): ctr [n, 4] uint32, key (k0, k1) -> [n, 4] uint32"""
+    import numpy as np
+    c = ctr.astype(np.uint64)
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & MASK, (k1 + np.uint64(0xBB67AE85)) & MASK
+    return c.astype(np.uint32)
+
+
+def test_philox_known_answer():
+    import numpy as np
+    out = _philox4x32_10(np.zeros((1, 4), np.uint32), (0, 0))[0]
+    assert [hex(int(v)) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    out = _philox4x32_10(np.full((1, 4), 0xFFFFFFFF, np.uint32), (0xFFFFFFFF, 0xFFFFFFFF))[0]
+    assert [hex(int(v)) for v in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+SITES = {"m_att": 0, "m_ao": 1, "m_f1": 2, "m_f2": 3, "m_dp": 4}
+
+
+def _read_masks(m, B, T, nb):
+    out = []
+    for b in range(nb):
+        d = {}
+        for name in SITES:
+            try:
+                d[name] = m.engine.train_workspace_tensor(name, b, B, T, DEV).cpu().clone()
+            except Exception:
+                pass
+        out.append(d)
+    return out
+
+
+def _oracle_masks(masks):
+    return [{k[2:]: (v.squeeze(-1) if k == "m_dp" else v) for k, v in d.items()} for d in masks]
+
+
+def test_dropout_masks_are_philox_and_advance():
+    """The keep-masks tdanet_forward_train_rng stores are exactly Philox4x32-10(key = seed, counter = {element
+    group, site | iteration << 8, offset}) >= floor(p * 2^32); the device offset advances once per forward."""
+    import numpy as np
+    kw = CASES["depth4"]
+    m = _model(kw, _model_sd(kw)).train()
+    m.dropout, m.drop_path = 0.1, 0.25
+    m.manual_seed(0x1234_5678_9ABC)
+    B, T = 6, 1203
+    wav, _ = _inputs(kw, B, T)
+    x = wav.squeeze(1).to(DEV)
+    m._sync_dropout()
+    rng = m.engine.rng_state(DEV)
+    seen = []
+    for call in range(2):
+        assert rng.tolist() == [0x1234_5678_9ABC, call]
+        m.engine.forward_train(m._weights(), x)
+        torch.cuda.synchronize()
+        masks = _read_masks(m, B, T, kw["num_blocks"])
+        seen.append(masks)
+        for b, d in enumerate(masks):
+            assert set(d) == set(SITES)
+            for name, t in d.items():
+                flat = t.numpy().reshape(-1)
+                n = flat.size
+                groups = np.arange((n + 3) // 4, dtype=np.uint64)
+                ctr = np.stack([groups & 0xFFFFFFFF, groups >> 32, np.full_like(groups, SITES[name] | (b << 8)),
+                                np.full_like(groups, call)], axis=1).astype(np.uint32)
+                r = _philox4x32_10(ctr, (0x1234_5678_9ABC & 0xFFFFFFFF, 0x1234_5678_9ABC >> 32)).reshape(-1)[:n]
+                p = 0.25 if name == "m_dp" else 0.1
+                want = (r >= np.uint32(int(p * 4294967296.0))).astype(np.uint8)
+                assert np.array_equal(flat, want), (name, b, call)
+        big = torch.cat([d["m_f1"].flatten() for d in masks]).float()
+        assert abs(big.mean().item() - 0.9) < 0.01
+    assert not torch.equal(seen[0][0]["m_ao"], seen[1][0]["m_ao"])      # fresh masks per forward
+    assert not torch.equal(seen[0][0]["m_ao"], seen[0][1]["m_ao"])      # and per UConvBlock iteration
+    assert rng.tolist() == [0x1234_5678_9ABC, 2]
+
+
+@pytest.mark.parametrize("variant,name,B,T,dropout,drop_path,mode", [
+    ("best", "depth4", 4, 1203, 0.1, 0.1, "fp32"), ("best", "depth5_odd", 3, 1111, 0.3, 0.5, "fp32"),
+    ("fork", "depth4", 4, 1203, 0.2, 0.3, "fp32"), ("origin", "depth5_odd", 3, 1111, 0.1, 0.1, "fp32"),
+    ("best", "depth4", 12, 1203, 0.1, 0.0, "fp32"), ("best", "depth4", 20, 800, 0.1, 0.1, "fp32"),
+    ("best", "depth4", 4, 1203, 0.1, 0.1, "tf32")])
+def test_train_mode_matches_oracle_with_the_same_masks(variant, name, B, T, dropout, drop_path, mode):
+    """model.train(): output and every parameter gradient equal the oracle evaluated with the keep-masks the
+    device drew (nn.Dropout x3, attention-weight dropout, DropPath x2), scaled by 1/(1-p) like torch."""
+    kw = CASES[name]
+    sd = _model_sd(kw, variant=variant)
+    m = _model(kw, sd, variant=variant).train()
+    m.dropout, m.drop_path = dropout, drop_path
+    m.gemm_mode = mode
+    m.manual_seed(42)
+    wav, d_est = _inputs(kw, B, T)
+    est = m(wav.to(DEV))
+    (est * d_est.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    masks = _oracle_masks(_read_masks(m, B, T, kw["num_blocks"]))
+    drop = dict(drop_masks=masks, dropout=dropout, drop_path=drop_path)
+    with torch.no_grad():
+        ref_est = O.forward(sd, wav, O.OracleConfig(variant=variant, sample_rate=SR, **kw, **drop))
+        det_est = O.forward(sd, wav, O.OracleConfig(variant=variant, sample_rate=SR, **kw))
+    scale = ref_est.abs().max().item()
+    err = (est.detach().cpu() - ref_est).abs().max().item() / scale
+    assert (ref_est - det_est).abs().max().item() / scale > 1e-3       # the masks do change the output
+    ref = _autograd(sd, wav, d_est, kw, variant, **drop)
+    wmax, wl2, all_l2 = _grad_errors([(k, p.grad) for k, p in m.named_parameters()], ref)
+    print(f"{variant}/{name}/{mode} p={dropout}/{drop_path}: est max-rel {err:.2e}, grad worst max-rel {wmax:.2e}, whole rel-L2 {all_l2:.2e}")
+    if mode == "fp32":
+        assert err < 3e-5 and wmax < 2e-4 and all_l2 < 1e-4
+    else:
+        assert err < 1e-3 and wmax < 0.2 and all_l2 < 2e-2
+
+
+def test_eval_mode_ignores_dropout_and_graph_replays_draw_fresh_masks():
+    kw = CASES["depth4"]
+    sd = _model_sd(kw)
+    m = _model(kw, sd).train()
+    m.dropout = m.drop_path = 0.1
+    m.gemm_mode = "fp32"
+    wav, _ = _inputs(kw, 4, 1203)
+    x = wav.to(DEV)
+    with torch.no_grad():
+        y_eval = m.eval()(x).clone()
+        ref = O.forward(sd, wav, O.OracleConfig(sample_rate=SR, **kw))
+    assert (y_eval.cpu() - ref).abs().max().item() / ref.abs().max().item() < 3e-5
+    # eval under grad: still deterministic (nn.Dropout semantics), train: differs from eval and between calls
+    y_eval_grad = m(x)
+    assert torch.equal(y_eval_grad.detach(), y_eval)
+    m.train()
+    y1, y2 = m(x).detach().clone(), m(x).detach().clone()
+    assert not torch.equal(y1, y_eval) and not torch.equal(y1, y2)
+    # the fused step as a CUDA graph: every replay advances the device offset and draws new masks
+    L = look2hear.losses
+    ts = look2hear.system.TrainingStep(m, L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True), lr=0.0)
+    g = torch.Generator().manual_seed(1)
+    tgt = (torch.randn(4, 2, 1203, generator=g) * 0.1).to(DEV)
+    mix = tgt.sum(1)
+    ts.capture(mix, tgt)
+    rng = m.engine.rng_state(DEV)
+    off0 = int(rng[1].item())
+    losses, masks = [], []
+    for _ in range(3):
+        losses.append(ts.step_captured(mix, tgt).item())
+        masks.append(m.engine.train_workspace_tensor("m_f1", 0, 4, 1203, DEV).clone())
+    assert int(rng[1].item()) == off0 + 3
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    assert len({round(v, 6) for v in losses}) == 3, losses     # lr = 0: only the masks differ between the replays
