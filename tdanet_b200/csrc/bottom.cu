@@ -273,15 +273,16 @@ int launch_affine(const float* x, const NormRef& norm, float* y, int B, int L, i
 // per (problem, head).  A problem is a set of `n` tokens token(s) = base + s*stride:
 //   batch-axis (BEST / FORK, batch_first=False fed [B,T',C]): tokens of the `group` batch items
 //       that share a time index;  time-axis (MULTRES): the L tokens of one batch item.
-// QL lanes share one query: lane j owns the float4 segments {j, j+QL, ...} of the head dimension for q, the score
-// partial sums (completed by xor-shuffles inside the lane group) and the output accumulator, so a CTA of 64
-// queries runs 64*QL threads; K/V chunks are staged in shared memory and read as 16-byte segments that are
-// contiguous across a lane group and broadcast across queries; online softmax over key chunks of 8.
-template <int D, int QL>
-__global__ void __launch_bounds__(64 * QL) attention_kernel(const float* __restrict__ qkv,
-                                                           float* __restrict__ ctx, int L, int C, int n,
-                                                           int group, int time_axis, int kchunk, int round_out,
-                                                           const uint8_t* __restrict__ amask, float inv_keep) {
+// Register tiling against the shared-memory pipe (a broadcast LDS.128 still costs four LSU cycles per warp, which
+// bounded the one-query-per-thread form at ~57 us per launch): QL lanes share a group of QPT queries; lane j owns
+// the float4 segments {j, j+QL, ...} of the head dimension of q, of the score partial sums (completed by
+// xor-shuffles inside the lane group) and of the output accumulators, so every K / V segment read from shared
+// memory feeds QPT queries.  K/V chunks of <= 64 keys are staged in shared memory; online softmax per chunk of 8.
+template <int D, int QL, int QPT>
+__global__ void __launch_bounds__(64 * QL / QPT) attention_kernel(const float* __restrict__ qkv,
+                                                                 float* __restrict__ ctx, int L, int C, int n,
+                                                                 int group, int time_axis, int kchunk, int round_out,
+                                                                 const uint8_t* __restrict__ amask, float inv_keep) {
   constexpr int NS = D / QL / 4;  // float4 segments per lane
   constexpr int DL = NS * 4;
   extern __shared__ float smem[];  // K [kchunk][D], V [kchunk][D]
@@ -298,26 +299,29 @@ __global__ void __launch_bounds__(64 * QL) attention_kernel(const float* __restr
     base = (long)grp * group * L + t;
     stride = L;
   }
-  const int qpc = blockDim.x / QL;
+  const int gpc = blockDim.x / QL;  // query groups per CTA
   const int lq = threadIdx.x % QL;
-  const int qi = blockIdx.z * qpc + threadIdx.x / QL;
-  const bool active = qi < n;
+  const int q0 = (blockIdx.z * gpc + threadIdx.x / QL) * QPT;  // first query of this thread's group
   const float scale = rsqrtf((float)D);
   const size_t C3 = (size_t)3 * C;
-  float q[DL], o[DL];
+  float q[QPT][DL], o[QPT][DL], m[QPT], l[QPT];
+  const uint8_t* mrow[QPT];
 #pragma unroll
-  for (int i = 0; i < DL; ++i) { q[i] = 0.f; o[i] = 0.f; }
-  if (active) {
-    const float* qp = qkv + (size_t)(base + (long)qi * stride) * C3 + head * D;
+  for (int a = 0; a < QPT; ++a) {
+    const bool active = q0 + a < n;
+    m[a] = -FLT_MAX;
+    l[a] = 0.f;
+    // training: dropout on the normalised weights (nn.MultiheadAttention(dropout)); row of this query's keep-mask
+    mrow[a] = amask && active ? amask + (((size_t)prob * gridDim.y + head) * n + (q0 + a)) * n : nullptr;
+    const float* qp = qkv + (size_t)(base + (long)(active ? q0 + a : 0) * stride) * C3 + head * D;
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       float4 v = *reinterpret_cast<const float4*>(qp + (lq + QL * i) * 4);
-      q[4 * i] = v.x * scale; q[4 * i + 1] = v.y * scale; q[4 * i + 2] = v.z * scale; q[4 * i + 3] = v.w * scale;
+      if (!active) v = make_float4(0.f, 0.f, 0.f, 0.f);  // inactive queries run along: the shuffles need whole warps
+      q[a][4 * i] = v.x * scale; q[a][4 * i + 1] = v.y * scale; q[a][4 * i + 2] = v.z * scale; q[a][4 * i + 3] = v.w * scale;
+      o[a][4 * i] = 0.f; o[a][4 * i + 1] = 0.f; o[a][4 * i + 2] = 0.f; o[a][4 * i + 3] = 0.f;
     }
   }
-  float m = -FLT_MAX, l = 0.f;
-  // training: dropout on the normalised weights (nn.MultiheadAttention(dropout)); row of this query's keep-mask
-  const uint8_t* mrow = amask && active ? amask + (((size_t)prob * gridDim.y + head) * n + qi) * n : nullptr;
 
   for (int k0 = 0; k0 < n; k0 += kchunk) {
     const int kn = min(kchunk, n - k0);
@@ -329,84 +333,113 @@ __global__ void __launch_bounds__(64 * QL) attention_kernel(const float* __restr
       *reinterpret_cast<float4*>(Vs + s * D + i) = *reinterpret_cast<const float4*>(kp + C);
     }
     __syncthreads();
-    // inactive queries (q = 0) run along: the shuffles below need whole warps
     for (int s0 = 0; s0 < kn; s0 += 8) {
-      float sc[8];
+      float sc[QPT][8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) sc[a][u] = 0.f;
         if (s0 + u < kn) {
           const float* kr = Ks + (s0 + u) * D + lq * 4;
 #pragma unroll
           for (int i = 0; i < NS; ++i) {
-            float4 kv = *reinterpret_cast<const float4*>(kr + QL * 4 * i);
-            acc = fmaf(q[4 * i], kv.x, acc); acc = fmaf(q[4 * i + 1], kv.y, acc);
-            acc = fmaf(q[4 * i + 2], kv.z, acc); acc = fmaf(q[4 * i + 3], kv.w, acc);
+            const float4 kv = *reinterpret_cast<const float4*>(kr + QL * 4 * i);
+#pragma unroll
+            for (int a = 0; a < QPT; ++a) {
+              sc[a][u] = fmaf(q[a][4 * i], kv.x, sc[a][u]); sc[a][u] = fmaf(q[a][4 * i + 1], kv.y, sc[a][u]);
+              sc[a][u] = fmaf(q[a][4 * i + 2], kv.z, sc[a][u]); sc[a][u] = fmaf(q[a][4 * i + 3], kv.w, sc[a][u]);
+            }
           }
         }
-        sc[u] = acc;
       }
 #pragma unroll
       for (int off = 1; off < QL; off <<= 1) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], off);
-      }
-      float cm = -FLT_MAX;
+        for (int a = 0; a < QPT; ++a)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (s0 + u >= kn) sc[u] = -FLT_MAX;
-        cm = fmaxf(cm, sc[u]);
+          for (int u = 0; u < 8; ++u) sc[a][u] += __shfl_xor_sync(0xffffffffu, sc[a][u], off);
       }
-      if (cm > m) {
-        const float f = expf(m - cm);
-        l *= f;
 #pragma unroll
-        for (int i = 0; i < DL; ++i) o[i] *= f;
-        m = cm;
+      for (int a = 0; a < QPT; ++a) {
+        float cm = -FLT_MAX;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (s0 + u >= kn) sc[a][u] = -FLT_MAX;
+          cm = fmaxf(cm, sc[a][u]);
+        }
+        if (cm > m[a]) {
+          const float f = expf(m[a] - cm);
+          l[a] *= f;
+#pragma unroll
+          for (int i = 0; i < DL; ++i) o[a][i] *= f;
+          m[a] = cm;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float p = s0 + u < kn ? expf(sc[a][u] - m[a]) : 0.f;
+          l[a] += p;
+          if (mrow[a] && s0 + u < kn) p = mrow[a][k0 + s0 + u] ? p * inv_keep : 0.f;
+          sc[a][u] = p;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         if (s0 + u < kn) {
-          float p = expf(sc[u] - m);
-          l += p;
-          if (mrow) p = mrow[k0 + s0 + u] ? p * inv_keep : 0.f;
           const float* vr = Vs + (s0 + u) * D + lq * 4;
 #pragma unroll
           for (int i = 0; i < NS; ++i) {
-            float4 vv = *reinterpret_cast<const float4*>(vr + QL * 4 * i);
-            o[4 * i] = fmaf(p, vv.x, o[4 * i]); o[4 * i + 1] = fmaf(p, vv.y, o[4 * i + 1]);
-            o[4 * i + 2] = fmaf(p, vv.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(p, vv.w, o[4 * i + 3]);
+            const float4 vv = *reinterpret_cast<const float4*>(vr + QL * 4 * i);
+#pragma unroll
+            for (int a = 0; a < QPT; ++a) {
+              const float p = sc[a][u];
+              o[a][4 * i] = fmaf(p, vv.x, o[a][4 * i]); o[a][4 * i + 1] = fmaf(p, vv.y, o[a][4 * i + 1]);
+              o[a][4 * i + 2] = fmaf(p, vv.z, o[a][4 * i + 2]); o[a][4 * i + 3] = fmaf(p, vv.w, o[a][4 * i + 3]);
+            }
           }
         }
       }
     }
   }
-  if (active) {
-    const float inv = 1.f / l;
 #pragma unroll
-    for (int i = 0; i < DL; ++i) o[i] = round_out ? tf32_rna(o[i] * inv) : o[i] * inv;
-    float* op = ctx + (size_t)(base + (long)qi * stride) * C + head * D;
+  for (int a = 0; a < QPT; ++a) {
+    if (q0 + a < n) {
+      const float inv = 1.f / l[a];
+      float* op = ctx + (size_t)(base + (long)(q0 + a) * stride) * C + head * D;
 #pragma unroll
-    for (int i = 0; i < NS; ++i)
-      *reinterpret_cast<float4*>(op + (lq + QL * i) * 4) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      for (int i = 0; i < NS; ++i) {
+        float4 r = make_float4(o[a][4 * i] * inv, o[a][4 * i + 1] * inv, o[a][4 * i + 2] * inv, o[a][4 * i + 3] * inv);
+        if (round_out) { r.x = tf32_rna(r.x); r.y = tf32_rna(r.y); r.z = tf32_rna(r.z); r.w = tf32_rna(r.w); }
+        *reinterpret_cast<float4*>(op + (lq + QL * i) * 4) = r;
+      }
+    }
   }
+}
+
+template <int D, int QPT>
+static int launch_attention_q(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
+                              int time_axis, int round_out, const uint8_t* amask, float inv_keep, cudaStream_t st) {
+  constexpr int QL = D >= 16 ? 4 : D / 4;  // lanes per query group, each owning >= one float4 of the head dimension
+  const int n = time_axis ? L : group;
+  const int nprob = time_axis ? B : (B / group) * L;
+  const int gstep = 32 / QL;  // query groups per warp
+  const int groups = cdiv(n, QPT);
+  const int gpc = n >= 64 ? 64 / QPT : cdiv(groups, gstep) * gstep;  // query groups per CTA (whole warps)
+  int kchunk = n < 64 ? n : 64;  // 2*64*D floats <= 32 KB of static-limit shared memory
+  kchunk = (kchunk + 7) / 8 * 8;
+  dim3 grid(nprob, n_head, cdiv(groups, gpc));
+  const size_t smem = (size_t)2 * kchunk * D * sizeof(float);
+  TD_LAUNCH((attention_kernel<D, QL, QPT>), grid, gpc * QL, smem, st, qkv, ctx, L, C, n, group, time_axis, kchunk, round_out,
+            amask, inv_keep);
+  return 0;
 }
 
 template <int D>
 static int launch_attention_d(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
                               int time_axis, int round_out, const uint8_t* amask, float inv_keep, cudaStream_t st) {
-  constexpr int QL = D >= 16 ? 4 : D / 4;  // lanes per query, each owning >= one float4 of the head dimension
   const int n = time_axis ? L : group;
-  const int nprob = time_axis ? B : (B / group) * L;
-  const int qstep = 32 / QL;  // queries per warp
-  const int qpc = n >= 64 ? 64 : (n + qstep - 1) / qstep * qstep;
-  int kchunk = n < 64 ? n : 64;  // 2*64*D floats <= 32 KB of static-limit shared memory
-  kchunk = (kchunk + 7) / 8 * 8;
-  dim3 grid(nprob, n_head, cdiv(n, qpc));
-  const size_t smem = (size_t)2 * kchunk * D * sizeof(float);
-  TD_LAUNCH((attention_kernel<D, QL>), grid, qpc * QL, smem, st, qkv, ctx, L, C, n, group, time_axis, kchunk, round_out,
-            amask, inv_keep);
-  return 0;
+  // four queries per thread once there are enough of them to fill warps (inference batches, time-axis attention)
+  if (n >= 32) return launch_attention_q<D, 4>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
+  return launch_attention_q<D, 1>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
 }
 
 int launch_attention(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
