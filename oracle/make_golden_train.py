@@ -67,11 +67,13 @@ def main():
             for k, p in m.named_parameters():
                 if p.ndim == 1:
                     p.add_(0.2 * torch.randn(p.shape, generator=g))
-        m.train()
+        # float64 end to end: in fp32 the autograd chains of the reference and of the oracle differ by their own
+        # rounding (up to 1.6e-2 on single tensors of the GroupNorm variant), which would hide a semantic difference
+        m.double().train()
         B, T = 5, 1203
         g = torch.Generator().manual_seed(1234)
-        x = torch.randn(B, 1, T, generator=g) * 0.1
-        d = torch.randn(B, 2, T, generator=g)
+        x = (torch.randn(B, 1, T, generator=g) * 0.1).double()
+        d = torch.randn(B, 2, T, generator=g).double()
         torch.manual_seed(3)
         with Recorder() as rec:
             y = m(x)
@@ -101,7 +103,7 @@ def main():
                 continue
             grads[k] = p.grad.detach().clone()
             e_g = max(e_g, (p.grad - sdg[k].grad).abs().max().item() / max(p.grad.abs().max().item(), 1e-12))
-        report.append(f"{variant}_train: oracle(masks) vs reference train mode: output max-rel {e_y:.3e}, "
+        report.append(f"{variant}_train (float64): oracle(masks) vs reference train mode: output max-rel {e_y:.3e}, "
                       f"worst parameter-gradient max-rel {e_g:.3e} (B={B}, T={T}, dropped paths "
                       f"{sum(int((mm['dp'] == 0).sum()) for mm in masks)})")
         arrs = {"x": x.numpy(), "d": d.numpy(), "y": y.detach().numpy(), "kwargs": np.array(repr(SMALL)),

@@ -71,7 +71,7 @@ class OracleConfig:
     dropout: float = 0.1
     drop_path: float = 0.1
 
-    def mask(self, name):
+    def mask(self, name, dtype=torch.float32):
         """Multiplier tensor (mask / keep_prob) of stochastic layer `name` in the current block, or None."""
         if self.drop_masks is None or self.cur_block is None:
             return None
@@ -79,7 +79,7 @@ class OracleConfig:
         if m is None:
             return None
         p = self.drop_path if name == "dp" else self.dropout
-        return m.to(torch.get_default_dtype()) / (1.0 - p)
+        return m.to(dtype) / (1.0 - p)
 
     @property
     def K(self) -> int:            # encoder window in samples
@@ -170,7 +170,7 @@ def mha_seq_first(x, w_in, b_in, w_out, b_out, n_head, cfg=None):
     v = v.reshape(S, N * n_head, d).transpose(0, 1)
     p = torch.softmax(q @ k.transpose(1, 2), dim=-1)
     if cfg is not None and cfg.mask("att") is not None:
-        p = p * cfg.mask("att").to(p.dtype)          # dropout on the attention weights, [N*heads, S, S]
+        p = p * cfg.mask("att", p.dtype)             # dropout on the attention weights, [N*heads, S, S]
     o = (p @ v).transpose(0, 1).reshape(S, N, E)
     if cfg is not None:
         _tap(cfg, "ga.attn_ctx", o)
@@ -195,15 +195,15 @@ def global_attention(sd, prefix, x, cfg):
         # batch_first=False fed [B, T', C]: the *batch* axis is the sequence axis,
         # and the "residual" doubles the attention output (bug-compatible)
         o = mha_seq_first(h, w_in, b_in, w_out, b_out, cfg.n_head, cfg)
-        m_ao = cfg.mask("ao")
-        post = o + (o if m_ao is None else o * m_ao.to(o.dtype))          # output + self.dropout(output)
+        m_ao = cfg.mask("ao", o.dtype)
+        post = o + (o if m_ao is None else o * m_ao)                       # output + self.dropout(output)
         if m_ao is not None:
             o = post           # what the CUDA workspace keeps in train mode: out * (1 + mask / keep)
     _tap(cfg, "ga.attn_out", o)
     post = F.layer_norm(post, (C,), sd[f"{a}.norm.weight"], sd[f"{a}.norm.bias"], EPS_LN)
-    dp = cfg.mask("dp")
+    dp = cfg.mask("dp", post.dtype)
     if dp is not None:
-        post = post * dp[0].to(post.dtype).view(-1, 1, 1)                  # self.drop_path(self.attn(x))
+        post = post * dp[0].view(-1, 1, 1)                                 # self.drop_path(self.attn(x))
     x = x + post.transpose(1, 2)
     _tap(cfg, "ga.after_attn", x)
     # FFN
@@ -212,13 +212,13 @@ def global_attention(sd, prefix, x, cfg):
     y = F.conv1d(y, sd[f"{m}.dwconv.weight"], sd[f"{m}.dwconv.bias"], padding=2, groups=y.shape[1])
     y = torch.relu(y)
     if cfg.mask("f1") is not None:
-        y = y * cfg.mask("f1").to(y.dtype).transpose(1, 2)                 # FFN.drop after the activation
+        y = y * cfg.mask("f1", y.dtype).transpose(1, 2)                    # FFN.drop after the activation
     _tap(cfg, "ga.ffn_dw", y)
     y = conv_norm(sd, f"{m}.fc2", y, cfg)
     if cfg.mask("f2") is not None:
-        y = y * cfg.mask("f2").to(y.dtype).transpose(1, 2)                 # FFN.drop after fc2
+        y = y * cfg.mask("f2", y.dtype).transpose(1, 2)                    # FFN.drop after fc2
     if dp is not None:
-        y = y * dp[1].to(y.dtype).view(-1, 1, 1)                           # self.drop_path(self.mlp(x))
+        y = y * dp[1].view(-1, 1, 1)                                       # self.drop_path(self.mlp(x))
     return x + y
 
 

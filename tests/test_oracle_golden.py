@@ -101,3 +101,42 @@ def test_oracle_against_live_reference():
         "print('ok')\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def golden_drop_masks(g):
+    """keep-masks of a *_train fixture -> OracleConfig.drop_masks"""
+    masks = []
+    for b in range(g["kwargs"]["num_blocks"]):
+        m = {}
+        for k in ("att", "ao", "f1", "f2", "dp"):
+            shape = tuple(int(v) for v in g[f"mshape/{b}/{k}"])
+            m[k] = torch.from_numpy(np.unpackbits(g[f"mask/{b}/{k}"])[: int(np.prod(shape))].reshape(shape).copy())
+        masks.append(m)
+    return masks
+
+
+@pytest.mark.parametrize("variant", ["best", "fork", "origin"])
+def test_train_mode_with_reference_masks(variant):
+    """the reference in TRAIN mode (float64; oracle/make_golden_train.py recorded what its nn.Dropout,
+    attention-weight dropout and DropPath drew).  With the same keep-masks the oracle reproduces the output and every
+    parameter gradient; without them it does not."""
+    g = load_golden(f"{variant}_train")
+    sd = {k[3:]: torch.from_numpy(g[k]).double().requires_grad_(not k.endswith("pos_enc.pe"))
+          for k in g if k.startswith("sd/")}
+    x, d, y_ref = (torch.from_numpy(g[k]) for k in ("x", "d", "y"))
+    masks = golden_drop_masks(g)
+    assert any((m["dp"] == 0).any() for m in masks) and all(0.8 < m["ao"].float().mean() < 0.97 for m in masks)
+    cfg = oracle_cfg(variant, g["kwargs"], g["sample_rate"])
+    cfg.drop_masks, cfg.dropout, cfg.drop_path = masks, 0.1, 0.1
+    y = O.forward(sd, x, cfg)
+    assert max_rel(y.detach(), y_ref) < 1e-12
+    (y * d).sum().backward()
+    n = 0
+    for k in g:
+        if k.startswith("grad/"):
+            assert max_rel(sd[k[5:]].grad, torch.from_numpy(g[k])) < 1e-10, k
+            n += 1
+    assert n > 60
+    with torch.no_grad():
+        y_eval = O.forward(sd, x, oracle_cfg(variant, g["kwargs"], g["sample_rate"]))
+    assert max_rel(y_eval, y_ref) > 1e-3
