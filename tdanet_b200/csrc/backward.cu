@@ -171,12 +171,26 @@ static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
   TD_REQUIRE(a.stride == 1 || a.stride == 2, "dw_bwd: stride %d", a.stride);
   TD_REQUIRE(a.xkind == SRC_PLAIN || a.xkind == SRC_AFFINE || a.xkind == SRC_AFFINE_PRELU, "dw_bwd: source kind %d", a.xkind);
   TD_REQUIRE(a.xin.L == a.Lin, "dw_bwd: input length %d != %d", a.xin.L, a.Lin);
-  a.rows_per_thread = pick_rows(a.Lout, a.C / 4, a.B, 32);
-  dim3 grid;
-  int threads;
-  row_grid(a.Lout, a.C / 4, a.B, a.rows_per_thread, grid, threads);
   const bool extra = a.xkind == SRC_AFFINE_PRELU || a.up_S || a.pool_g || a.dslope;
   const int key = ks * 100 + nw * 10 + a.stride;
+  dim3 grid;
+  int threads;
+  a.rows_per_thread = pick_rows(a.Lout, a.C / 4, a.B, 32);
+  row_grid(a.Lout, a.C / 4, a.B, a.rows_per_thread, grid, threads);
+  // fewer than ~16 warps per SM with 4 channels per thread (training batches): 2 channels per thread
+  const long warps4 = (long)grid.x * grid.y * grid.z * (threads / 32);
+  if (warps4 < 148L * 16 && a.C % 2 == 0) {
+    a.rows_per_thread = pick_rows(a.Lout, a.C / 2, a.B, 32);
+    row_grid(a.Lout, a.C / 2, a.B, a.rows_per_thread, grid, threads);
+    if (key == 511 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, false, 2>), grid, threads, 0, st, a);
+    else if (key == 511) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, true, 2>), grid, threads, 0, st, a);
+    else if (key == 512) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 2, true, 2>), grid, threads, 0, st, a);
+    else if (key == 521 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 2, 1, false, 2>), grid, threads, 0, st, a);
+    else if (key == 111 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<1, 1, 1, false, 2>), grid, threads, 0, st, a);
+    else if (key == 121 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<1, 2, 1, false, 2>), grid, threads, 0, st, a);
+    else return fail(TDANET_EINVAL, "dw_bwd: ks=%d nw=%d", ks, nw);
+    return 0;
+  }
   if (key == 511 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, false>), grid, threads, 0, st, a);
   else if (key == 511) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, true>), grid, threads, 0, st, a);
   else if (key == 512) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 2, true>), grid, threads, 0, st, a);

@@ -433,11 +433,194 @@ static int launch_attention_q(const float* qkv, float* ctx, int B, int L, int C,
   return 0;
 }
 
+// ----------------------------------------------------------------------------- attention core on the tensor cores
+// 16 < n <= 64 tokens per problem (the inference batches: attention over the batch axis).  The CUDA-core kernel
+// above is bound by instruction issue there (39.6 M warp instructions per launch at B = 64, 94 us, ncu
+// profiles/r01_ncu_attention.txt); here S = Q K^T and O = P V are warp-level mma.sync.m16n8k8 TF32 with every
+// operand split into hi + lo TF32 parts and three MMAs per tile (hi*hi + lo*hi + hi*lo), which keeps fp32-level
+// accuracy (the dropped lo*lo term is ~2^-22), so the same kernel serves gemm_mode fp32.
+// One CTA per (problem, head): four warps x 16 query rows; K and V are staged once, already split, in shared
+// memory rows padded to D + 4 floats (conflict-free fragment gathers).  Whole softmax rows live in the
+// accumulator fragments (n <= 64), so there is no online rescaling.  The P fragment feeds the second product
+// without a shuffle: the accumulator columns {2t, 2t+1} of a key tile are taken as the A columns {t, t+4}, and
+// the V fragment is gathered with the same relabelling of the keys.
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  const float h = tf32_rna(x);
+  hi = __float_as_uint(h);
+  lo = __float_as_uint(tf32_rna(x - h));
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
+                                                            int L, int C, int n, int group, int time_axis,
+                                                            int round_out, const uint8_t* __restrict__ amask,
+                                                            float inv_keep) {
+  constexpr int NK = 64, LD = D + 4, KT = D / 8, NT = NK / 8;
+  extern __shared__ float smem[];
+  float* Khi = smem;
+  float* Klo = Khi + NK * LD;
+  float* Vhi = Klo + NK * LD;
+  float* Vlo = Vhi + NK * LD;
+  const int head = blockIdx.y, prob = blockIdx.x;
+  long base, stride;
+  if (time_axis) {
+    base = (long)prob * L;
+    stride = 1;
+  } else {
+    const int grp = prob / L, t = prob % L;
+    base = (long)grp * group * L + t;
+    stride = L;
+  }
+  const size_t C3 = (size_t)3 * C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- stage K, V (rows >= n are zero), split into TF32 hi / lo
+  for (int idx = tid; idx < NK * (D / 4); idx += 128) {
+    const int sidx = idx / (D / 4), i = (idx % (D / 4)) * 4;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (sidx < n) {
+      const float* kp = qkv + (size_t)(base + (long)sidx * stride) * C3 + C + head * D + i;
+      kv = *reinterpret_cast<const float4*>(kp);
+      vv = *reinterpret_cast<const float4*>(kp + C);
+    }
+    uint32_t h[4], l[4];
+    split_tf32(kv.x, h[0], l[0]); split_tf32(kv.y, h[1], l[1]); split_tf32(kv.z, h[2], l[2]); split_tf32(kv.w, h[3], l[3]);
+    *reinterpret_cast<uint4*>(Khi + sidx * LD + i) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(Klo + sidx * LD + i) = make_uint4(l[0], l[1], l[2], l[3]);
+    split_tf32(vv.x, h[0], l[0]); split_tf32(vv.y, h[1], l[1]); split_tf32(vv.z, h[2], l[2]); split_tf32(vv.w, h[3], l[3]);
+    *reinterpret_cast<uint4*>(Vhi + sidx * LD + i) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(Vlo + sidx * LD + i) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+  // ---- Q fragments of this warp's 16 rows (rows g and g + 8), scaled, split
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const float scale = rsqrtf((float)D);
+  uint32_t qh[KT][4], ql[KT][4];
+  {
+    const float* q0 = qkv + (size_t)(base + (long)(r0 < n ? r0 : 0) * stride) * C3 + head * D;
+    const float* q1 = qkv + (size_t)(base + (long)(r1 < n ? r1 : 0) * stride) * C3 + head * D;
+    const float m0 = r0 < n ? scale : 0.f, m1 = r1 < n ? scale : 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      split_tf32(q0[8 * kt + t] * m0, qh[kt][0], ql[kt][0]);
+      split_tf32(q1[8 * kt + t] * m1, qh[kt][1], ql[kt][1]);
+      split_tf32(q0[8 * kt + t + 4] * m0, qh[kt][2], ql[kt][2]);
+      split_tf32(q1[8 * kt + t + 4] * m1, qh[kt][3], ql[kt][3]);
+    }
+  }
+  __syncthreads();
+  if (warp * 16 >= n) return;  // no barrier below
+  // ---- S = Q K^T : NT key tiles of 8, accumulator (row g: c0 c1 | row g+8: c2 c3), columns 2t, 2t+1
+  float S[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+    if (nt * 8 < n) {  // uniform
+      const uint32_t* kh = reinterpret_cast<const uint32_t*>(Khi) + (nt * 8 + g) * LD + t;
+      const uint32_t* kl = reinterpret_cast<const uint32_t*>(Klo) + (nt * 8 + g) * LD + t;
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        const uint32_t bh0 = kh[8 * kt], bh1 = kh[8 * kt + 4], bl0 = kl[8 * kt], bl1 = kl[8 * kt + 4];
+        mma_tf32_16x8x8(S[nt], ql[kt], bh0, bh1);
+        mma_tf32_16x8x8(S[nt], qh[kt], bl0, bl1);
+        mma_tf32_16x8x8(S[nt], qh[kt], bh0, bh1);
+      }
+    }
+  }
+  // ---- softmax over the keys of rows r0, r1 (a row is spread over the 4 lanes of a quad)
+  float mx0 = -FLT_MAX, mx1 = -FLT_MAX;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    if (c >= n) { S[nt][0] = -FLT_MAX; S[nt][2] = -FLT_MAX; }
+    if (c + 1 >= n) { S[nt][1] = -FLT_MAX; S[nt][3] = -FLT_MAX; }
+    mx0 = fmaxf(mx0, fmaxf(S[nt][0], S[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(S[nt][2], S[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  // training: dropout on the normalised weights (nn.MultiheadAttention(dropout)): the sums use the undropped weights
+  const uint8_t* mr0 = amask && r0 < n ? amask + (((size_t)prob * gridDim.y + head) * n + r0) * n : nullptr;
+  const uint8_t* mr1 = amask && r1 < n ? amask + (((size_t)prob * gridDim.y + head) * n + r1) * n : nullptr;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int c = nt * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = c + (e & 1);
+      float p = col < n ? expf(S[nt][e] - (e < 2 ? mx0 : mx1)) : 0.f;
+      if (e < 2) l0 += p; else l1 += p;
+      const uint8_t* mr = e < 2 ? mr0 : mr1;
+      if (mr && col < n) p = mr[col] ? p * inv_keep : 0.f;
+      S[nt][e] = p;
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // ---- O = P V : key tile j is the k dimension; A columns {t, t+4} <- keys {2t, 2t+1} of the tile
+  float O[KT][4];
+#pragma unroll
+  for (int dt = 0; dt < KT; ++dt) O[dt][0] = O[dt][1] = O[dt][2] = O[dt][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (j * 8 < n) {  // uniform
+      uint32_t ph[4], pl[4];
+      split_tf32(S[j][0], ph[0], pl[0]);  // (row g,   key 2t)
+      split_tf32(S[j][2], ph[1], pl[1]);  // (row g+8, key 2t)
+      split_tf32(S[j][1], ph[2], pl[2]);  // (row g,   key 2t+1)
+      split_tf32(S[j][3], ph[3], pl[3]);  // (row g+8, key 2t+1)
+      const uint32_t* vh = reinterpret_cast<const uint32_t*>(Vhi) + (j * 8 + 2 * t) * LD + g;
+      const uint32_t* vl = reinterpret_cast<const uint32_t*>(Vlo) + (j * 8 + 2 * t) * LD + g;
+#pragma unroll
+      for (int dt = 0; dt < KT; ++dt) {
+        const uint32_t bh0 = vh[8 * dt], bh1 = vh[LD + 8 * dt], bl0 = vl[8 * dt], bl1 = vl[LD + 8 * dt];
+        mma_tf32_16x8x8(O[dt], pl, bh0, bh1);
+        mma_tf32_16x8x8(O[dt], ph, bl0, bl1);
+        mma_tf32_16x8x8(O[dt], ph, bh0, bh1);
+      }
+    }
+  }
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+  for (int dt = 0; dt < KT; ++dt) {
+    float2 a = make_float2(O[dt][0] * i0, O[dt][1] * i0), b = make_float2(O[dt][2] * i1, O[dt][3] * i1);
+    if (round_out) { a.x = tf32_rna(a.x); a.y = tf32_rna(a.y); b.x = tf32_rna(b.x); b.y = tf32_rna(b.y); }
+    if (r0 < n) *reinterpret_cast<float2*>(ctx + (size_t)(base + (long)r0 * stride) * C + head * D + 8 * dt + 2 * t) = a;
+    if (r1 < n) *reinterpret_cast<float2*>(ctx + (size_t)(base + (long)r1 * stride) * C + head * D + 8 * dt + 2 * t) = b;
+  }
+}
+
+template <int D>
+static int launch_attention_mma(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
+                                int time_axis, int round_out, const uint8_t* amask, float inv_keep, cudaStream_t st) {
+  const int n = time_axis ? L : group;
+  const int nprob = time_axis ? B : (B / group) * L;
+  const size_t smem = (size_t)4 * 64 * (D + 4) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TD_CUDA(cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(nprob, n_head);
+  TD_LAUNCH((attention_mma_kernel<D>), grid, 128, smem, st, qkv, ctx, L, C, n, group, time_axis, round_out, amask, inv_keep);
+  return 0;
+}
+
 template <int D>
 static int launch_attention_d(const float* qkv, float* ctx, int B, int L, int C, int n_head, int group,
                               int time_axis, int round_out, const uint8_t* amask, float inv_keep, cudaStream_t st) {
   const int n = time_axis ? L : group;
-  // four queries per thread once there are enough of them to fill warps (inference batches, time-axis attention)
+  // whole softmax rows in tensor-core fragments for the inference batches (attention over <= 64 batch items)
+  if constexpr (D % 8 == 0 && D >= 16)
+    if (n > 16 && n <= 64)
+      return launch_attention_mma<D>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
+  // four queries per thread once there are enough of them to fill warps (time-axis attention)
   if (n >= 32) return launch_attention_q<D, 4>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
   return launch_attention_q<D, 1>(qkv, ctx, B, L, C, n_head, group, time_axis, round_out, amask, inv_keep, st);
 }

@@ -288,10 +288,12 @@ struct DwBwdArgs {
 //   stride 2: output tile t..t+R-1 = input rows 2t..2t+2R-1 needs G[t-1 .. t+R], xin[2t-2 .. 2t+2R]  (carry 2 / 3 rows)
 // EXTRA compiles in the optional epilogues (PReLU derivative + slope gradient, upstream GlobLN sums, pooling gradient);
 // the plain variants (LA branches) stay lean in registers.
-template <int KS, int NW, int STRIDE, bool EXTRA>
+// V = 4 channels per thread, or 2 for small launches (training batches): twice the warps at about half the registers,
+// where the kernel is bound by latency at low occupancy rather than by bytes (rows are still read as whole sectors).
+template <int KS, int NW, int STRIDE, bool EXTRA, int V = 4>
 __global__ void dw_bwd_kernel(DwBwdArgs a) {
   // output rows per tile: 4, or 2 where the windows are wide (two convs, or stride 2 with its 2x input rows)
-  constexpr int V = 4, PAD = (KS - 1) / 2, R = (NW == 2 && KS == 5) || STRIDE == 2 ? 2 : 4;
+  constexpr int PAD = (KS - 1) / 2, R = (NW == 2 && KS == 5) || STRIDE == 2 ? 2 : 4;
   constexpr int GW = STRIDE == 1 ? R + 2 * PAD : R + 2;       // gradient rows held per tile
   constexpr int XW = STRIDE == 1 ? R + 2 * PAD : 2 * R + 3;   // input rows held per tile
   constexpr int GC = GW - R, XC = XW - R * STRIDE;            // rows carried from the previous tile

@@ -239,11 +239,13 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
       const int group = c->attn_group > 0 ? c->attn_group : B;
       p.m_begin = p.bytes;
       p.n_att = (size_t)B * Lb * c->n_head * group;
-      p.m_att = bytes_of("m_att", (int64_t)(B / group) * Lb * c->n_head, group, group);
-      p.m_ao = bytes_of("m_ao", B, Lb, C);
-      p.m_f1 = bytes_of("m_f1", B, Lb, 2 * C);
-      p.m_f2 = bytes_of("m_f2", B, Lb, C);
-      p.m_dp = bytes_of("m_dp", 2, B, 1);
+      if (p.drop_elem) {
+        p.m_att = bytes_of("m_att", (int64_t)(B / group) * Lb * c->n_head, group, group);
+        p.m_ao = bytes_of("m_ao", B, Lb, C);
+        p.m_f1 = bytes_of("m_f1", B, Lb, 2 * C);
+        p.m_f2 = bytes_of("m_f2", B, Lb, C);
+      }
+      if (p.drop_item) p.m_dp = bytes_of("m_dp", 2, B, 1);
       p.m_end = p.bytes;
     }
   } else {

@@ -305,6 +305,36 @@ def test_deeper_and_shallower_unets():
         assert max_rel(y, ref) < 5e-5, depth
 
 
+@pytest.mark.parametrize("variant,C,B,group,mode,tol", [
+    ("best", 128, 20, 0, "fp32", 5e-5), ("best", 512, 33, 0, "fp32", 5e-5), ("fork", 256, 64, 0, "fp32", 5e-5),
+    ("best", 128, 40, 20, "fp32", 5e-5), ("best", 128, 17, 0, "tf32", 1e-3), ("best", 128, 70, 0, "fp32", 5e-5),
+    ("multres", 128, 2, 0, "fp32", 5e-5)])
+def test_attention_over_larger_batches(variant, C, B, group, mode, tol):
+    """The bottom-scale attention runs over the BATCH axis: batches of 17..64 items take the
+    tensor-core attention kernel (head dims 16 / 32 / 64), 70 items and the time-axis attention of MultRes the
+    CUDA-core kernel with four queries per thread; all against the oracle on the same batch."""
+    kw = dict(out_channels=16, in_channels=C, num_blocks=1, upsampling_depth=4, enc_kernel_size=4, num_sources=2)
+    sr = 16000
+    if variant == "multres":
+        kw.update(kernels=4)
+        sr = 8000
+    torch.manual_seed(C + B)
+    m = M.get(CLASSES[variant])(sample_rate=sr, **kw).eval()
+    T = 2500 if variant == "multres" else 1500
+    x = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(3)) * 0.1
+    sd = {k: v for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        if group:
+            ref = torch.cat([O.forward(sd, x[i:i + group], oracle_cfg(variant, kw, sr)) for i in range(0, B, group)])
+        else:
+            ref = O.forward(sd, x, oracle_cfg(variant, kw, sr))
+        m = m.to(DEV)
+        m.gemm_mode = mode
+        m.attn_group = group
+        y = m(x.to(DEV)).cpu()
+    assert max_rel(y, ref) < tol, max_rel(y, ref)
+
+
 def test_three_sources():
     kw = dict(out_channels=16, in_channels=32, num_blocks=1, upsampling_depth=4, enc_kernel_size=2, num_sources=3)
     torch.manual_seed(2)

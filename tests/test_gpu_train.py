@@ -465,6 +465,30 @@ def test_train_mode_matches_oracle_with_the_same_masks(variant, name, B, T, drop
         assert err < 1e-3 and wmax < 0.2 and all_l2 < 2e-2
 
 
+def test_train_mode_masks_on_the_tensor_core_attention():
+    """Batch of 24 with 16-wide heads: the forward takes attention_mma_kernel (keep-mask applied to the P fragment),
+    the backward the scratch-buffer kernels (n > 16); same masks in the oracle."""
+    kw = dict(out_channels=16, in_channels=128, num_blocks=2, upsampling_depth=3, enc_kernel_size=4, num_sources=2)
+    sd = _model_sd(kw)
+    m = _model(kw, sd).train()
+    m.dropout, m.drop_path = 0.2, 0.1
+    m.gemm_mode = "fp32"
+    B, T = 24, 700
+    wav, d_est = _inputs(kw, B, T)
+    est = m(wav.to(DEV))
+    (est * d_est.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    masks = _oracle_masks(_read_masks(m, B, T, kw["num_blocks"]))
+    drop = dict(drop_masks=masks, dropout=0.2, drop_path=0.1)
+    with torch.no_grad():
+        ref_est = O.forward(sd, wav, O.OracleConfig(sample_rate=SR, **kw, **drop))
+    err = (est.detach().cpu() - ref_est).abs().max().item() / ref_est.abs().max().item()
+    ref = _autograd(sd, wav, d_est, kw, "best", **drop)
+    wmax, wl2, all_l2 = _grad_errors([(k, p.grad) for k, p in m.named_parameters()], ref)
+    print(f"mma attention with masks: est max-rel {err:.2e}, grad worst max-rel {wmax:.2e}, whole rel-L2 {all_l2:.2e}")
+    assert err < 3e-5 and wmax < 2e-4 and all_l2 < 1e-4
+
+
 def test_eval_mode_ignores_dropout_and_graph_replays_draw_fresh_masks():
     kw = CASES["depth4"]
     sd = _model_sd(kw)
