@@ -160,6 +160,17 @@ def train_targets(rank, B, seed=4321):
     return tgt.sum(1), tgt
 
 
+def ncu_traffic(role):
+    """DRAM bytes per launch of `role`'s kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json),
+    or None when this round has no capture of it."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f).get(role)
+        return (None, None) if e is None else (e["bytes_per_launch"], e["source"])
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 def run_train_leg(args, dev, rank, world, local, barrier):
     """BASELINE.json configs[3]: full training step (forward, PIT SI-SDR loss, backward, gradient all-reduce,
     clip 5.0, Adam) of the 4 ms / 16-block TDANetBest at batch 8 per GPU.  Returns the "train" object of the
@@ -232,7 +243,7 @@ def run_train_leg(args, dev, rank, world, local, barrier):
     top = next((r for r in kernels if "achieved_GBps" in r), None)
     roofline = None if top is None else {
         "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_GBps"], "peak": peak, "unit": "GB/s",
-        "frac": round(top["achieved_GBps"] / peak, 4), "traffic": None, "peak_source": peak_src,
+        "frac": round(top["achieved_GBps"] / peak, 4), "traffic": ncu_traffic(top["kernel"])[0], "traffic_source": ncu_traffic(top["kernel"])[1], "peak_source": peak_src,
         "algorithmic_bytes_per_launch": int(alg[top["kernel"]] / max(1, top["launches_per_step"])),
         "avg_launch_ms": round(top["ms_per_step"] / max(1, top["launches_per_step"]), 5),
         "share_of_step": round(top["ms_per_step"] / max(1e-9, sum(k["ms_per_step"] for k in kernels)), 4),
@@ -453,7 +464,7 @@ def run_ours(args):
         prof_total = sum(r["ms_per_step"] for r in kernels)
         roofline = None if top is None else {
             "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_GBps"], "peak": peak, "unit": "GB/s",
-            "frac": round(top["achieved_GBps"] / peak, 4), "traffic": None, "peak_source": peak_src,
+            "frac": round(top["achieved_GBps"] / peak, 4), "traffic": ncu_traffic(top["kernel"])[0], "traffic_source": ncu_traffic(top["kernel"])[1], "peak_source": peak_src,
             "algorithmic_bytes_per_launch": int(alg[top["kernel"]] / max(1, top["launches_per_step"])),
             "avg_launch_ms": round(top["ms_per_step"] / max(1, top["launches_per_step"]), 5),
             "share_of_step": round(top["ms_per_step"] / prof_total, 4),

@@ -177,9 +177,11 @@ static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
   int threads;
   a.rows_per_thread = pick_rows(a.Lout, a.C / 4, a.B, 32);
   row_grid(a.Lout, a.C / 4, a.B, a.rows_per_thread, grid, threads);
-  // fewer than ~16 warps per SM with 4 channels per thread (training batches): 2 channels per thread
+  // 2 channels per thread: only where 4 channels per thread leave most SMs without a single CTA (very small
+  // launches).  Measured on B200 at the training shape (B = 8, 2016 warps per launch): V = 2 is SLOWER (bwd_spp_dw0
+  // 0.81 -> 1.30 ms per step, bwd_la_dw 5.20 -> 5.35): the kernels are not occupancy-bound there.
   const long warps4 = (long)grid.x * grid.y * grid.z * (threads / 32);
-  if (warps4 < 148L * 16 && a.C % 2 == 0) {
+  if (warps4 < 148L && a.C % 2 == 0) {
     a.rows_per_thread = pick_rows(a.Lout, a.C / 2, a.B, 32);
     row_grid(a.Lout, a.C / 2, a.B, a.rows_per_thread, grid, threads);
     if (key == 511 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, false, 2>), grid, threads, 0, st, a);

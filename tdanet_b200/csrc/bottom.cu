@@ -279,7 +279,7 @@ int launch_affine(const float* x, const NormRef& norm, float* y, int B, int L, i
 // xor-shuffles inside the lane group) and of the output accumulators, so every K / V segment read from shared
 // memory feeds QPT queries.  K/V chunks of <= 64 keys are staged in shared memory; online softmax per chunk of 8.
 template <int D, int QL, int QPT>
-__global__ void __launch_bounds__(64 * QL / QPT) attention_kernel(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(64 * QL / QPT < 32 ? 32 : 64 * QL / QPT) attention_kernel(const float* __restrict__ qkv,
                                                                  float* __restrict__ ctx, int L, int C, int n,
                                                                  int group, int time_axis, int kchunk, int round_out,
                                                                  const uint8_t* __restrict__ amask, float inv_keep) {
@@ -423,7 +423,8 @@ static int launch_attention_q(const float* qkv, float* ctx, int B, int L, int C,
   const int nprob = time_axis ? B : (B / group) * L;
   const int gstep = 32 / QL;  // query groups per warp
   const int groups = cdiv(n, QPT);
-  const int gpc = n >= 64 ? 64 / QPT : cdiv(groups, gstep) * gstep;  // query groups per CTA (whole warps)
+  const int cap = 64 / QPT > gstep ? 64 / QPT : gstep;               // <= 64 queries per CTA, at least one warp
+  const int gpc = cdiv(groups < cap ? groups : cap, gstep) * gstep;  // query groups per CTA (whole warps)
   int kchunk = n < 64 ? n : 64;  // 2*64*D floats <= 32 KB of static-limit shared memory
   kchunk = (kchunk + 7) / 8 * 8;
   dim3 grid(nprob, n_head, cdiv(groups, gpc));
