@@ -171,6 +171,71 @@ def ncu_traffic(role):
         return None, None
 
 
+def run_longform_leg(args, dev, rank, world, barrier):
+    """BASELINE.json configs[4]: 16 synthetic 60 s recordings, chunked like audio_test_css.py (segment 2 s, overlap
+    0.25 -> 40 chunks each, the last one zero-padded), every chunk separated alone (attn_group 1), stitched on the
+    device by cosine similarity.  The 16 recordings are split over the ranks (strong scaling, no collective).
+    Returns the "longform" object of the JSON line (rank 0) or None."""
+    import torch.distributed as dist
+    import tdanet_b200.look2hear as look2hear
+    n_streams, seconds = 16, 60.0
+    if n_streams % world:
+        return None
+    mine = n_streams // world
+    torch.manual_seed(0)
+    model = getattr(look2hear.models, CLASSES[args.variant])(sample_rate=SR, **model_kwargs(args.enc_ms)).eval().to(dev)
+    model.gemm_mode = args.gemm_mode
+    model.act_dtype = args.act_dtype
+    n = int(seconds * SR)
+    wav_h = (torch.randn(mine, n, generator=torch.Generator().manual_seed(77 + rank)) * 0.1).pin_memory()
+    wav = wav_h.to(dev)
+    chunks = 160
+
+    def once(src):
+        return look2hear.system.separate_long(model, src, segment=2.0, overlap=0.25, max_chunks_per_call=chunks)
+
+    for _ in range(3):
+        out, swap = once(wav)
+    K = max(3, min(args.steps, 10))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        out, swap = once(wav)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    out_h = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        o, _ = once(wav_h.to(dev, non_blocking=True))
+        out_h.copy_(o, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    del model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    audio = n_streams * seconds * K
+    return {"metric": "separated_audio_seconds_per_second", "value": audio / (ms / 1e3), "unit": UNIT,
+            "ms_per_pass": ms / K, "scaling": "strong", "n_gpus": world,
+            "config": {"workload": f"{CLASSES[args.variant]} {args.enc_ms} ms, long-form separation of 16 x 60 s recordings "
+                                   "(BASELINE.json configs[4]): 40 chunks of 2 s per recording (overlap 0.25, last chunk padded), "
+                                   "attention group 1, cosine-similarity stitch on the device",
+                       "recordings_per_gpu": mine, "chunks_per_forward": chunks, "gemm_mode": args.gemm_mode,
+                       "act_dtype": args.act_dtype},
+            "e2e": {"value": audio / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_pass": mine * n * 4,
+                    "d2h_bytes_per_pass": int(out.numel()) * 4},
+            "stitched_samples": int(out.shape[-1]), "swapped_chunks": int(swap.sum().item())}
+
+
 def run_train_leg(args, dev, rank, world, local, barrier):
     """BASELINE.json configs[3]: full training step (forward, PIT SI-SDR loss, backward, gradient all-reduce,
     clip 5.0, Adam) of the 4 ms / 16-block TDANetBest at batch 8 per GPU.  Returns the "train" object of the
@@ -443,6 +508,12 @@ def run_ours(args):
         model._engine._graphs.clear()
         torch.cuda.empty_cache()
         train = run_train_leg(args, dev, rank, world, local, barrier)
+    longform = None
+    if not args.skip_longform:
+        model._engine._ws.clear()
+        model._engine._graphs.clear()
+        torch.cuda.empty_cache()
+        longform = run_longform_leg(args, dev, rank, world, barrier)
     audio_s = world * B * (N_SAMPLES / SR) * K
     value = audio_s / (ms / 1e3)
     e2e = audio_s / (ms_e2e / 1e3)
@@ -497,6 +568,8 @@ def run_ours(args):
             out["cpu_baseline"] = cpu
         if train is not None:
             out["train"] = train
+        if longform is not None:
+            out["longform"] = longform
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -542,6 +615,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--train-only", action="store_true", help="print the training-step leg as the JSON line (profiling aid)")
     ap.add_argument("--skip-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[3])")
+    ap.add_argument("--skip-longform", action="store_true", help="skip the long-form leg (BASELINE.json configs[4])")
     ap.add_argument("--ref-batch", type=int, default=8, help="upper bound of mixtures per step for --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":

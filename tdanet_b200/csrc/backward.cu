@@ -623,9 +623,12 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
       TD_LAUNCH(dwg_bwd_data_kernel, grid, threads, 0, x.st, x.at(p.g_pool_dw), q.dw_w, x.at(p.g_spp[k]), (int)spp_written[k],
                 p.L[k], Lb, C, ks, s, rows);
       spp_written[k] = true;
-      dim3 wgrid(cdiv(C / 4, threads), ks + 1);
+      // rows per CTA: as long as possible (fewer atomics) while the launch still has ~4 CTAs per SM
+      int wrows = 4;
+      while (wrows < Lb && (long)cdiv(C / 4, threads) * (ks + 1) * B * cdiv(Lb, wrows * 2) >= 4 * 148) wrows *= 2;
+      dim3 wgrid(cdiv(C / 4, threads), ks + 1, B * cdiv(Lb, wrows));
       TD_LAUNCH(dwg_bwd_weight_kernel, wgrid, threads, 0, x.st, x.at(p.g_pool_dw), baffine(x.at(p.spp[k]), p.L[k], spp_norm(k)),
-                (int)SRC_AFFINE, x.gp(gq.dw_w), x.gp(gq.dw_b), B, Lb, C, ks, s);
+                (int)SRC_AFFINE, x.gp(gq.dw_w), x.gp(gq.dw_b), B, Lb, C, ks, s, wrows);
     }
   } else {
     // ---- ga_in = sum_k avgpool(gLN(spp_k)): the coarsest scale (identity bins) here, the others inside the spp_dw

@@ -785,28 +785,39 @@ __global__ void dwg_bwd_data_kernel(const float* __restrict__ G, const float* __
   }
 }
 
-//   dw[c, tap] += sum_{b, to} G[b, to, c] * xin[b, to*s + tap - pad, c];   db[c] += sum G      (one thread per (tap, 4 channels))
+//   dw[c, tap] += sum_{b, to} G[b, to, c] * xin[b, to*s + tap - pad, c];   db[c] += sum G
+// One thread per (4 channels, tap, batch item, chunk of output rows): blockIdx.y = tap (ks taps + one extra row of
+// blocks for the bias), blockIdx.z = item * chunks + chunk.  Rows in tiles of 4 with every load issued before use.
+// (The first version walked all B * Lout rows in one thread per (tap, 4 channels): 34 CTAs, ~0.5 ms per launch,
+// 50.8 of the 68.7 ms of a fork training step.)
 __global__ void dwg_bwd_weight_kernel(const float* __restrict__ G, SrcDesc xin, int xkind, float* __restrict__ dw,
-                                      float* __restrict__ db, int B, int Lout, int C, int ks, int stride) {
+                                      float* __restrict__ db, int B, int Lout, int C, int ks, int stride,
+                                      int rows_per_cta) {
   constexpr int V = 4;
   const int ch = (blockIdx.x * blockDim.x + threadIdx.x) * V;
-  const int tap = blockIdx.y;  // ks taps, + one extra row of blocks for the bias
+  const int tap = blockIdx.y;
   if (ch >= C) return;
+  const int chunks = (Lout + rows_per_cta - 1) / rows_per_cta;
+  const int b = blockIdx.z / chunks, to0 = (blockIdx.z % chunks) * rows_per_cta;
+  const int to1 = min(to0 + rows_per_cta, Lout);
   const int pad = (ks - 1) / 2, Lin = xin.L;
   vf<V> acc = vzero<V>();
-  for (int b = 0; b < B; ++b) {
-    FwdLoad<V> fx;
-    fx.init(xin, xkind, b, ch, C);
-    const float* gp = G + (size_t)b * Lout * C + ch;
-    for (int to = 0; to < Lout; ++to) {
-      const vf<V> g = vload<V>(gp + (size_t)to * C);
-      if (tap == ks) {
+  FwdLoad<V> fx;
+  fx.init(xin, xkind, b, ch, C);
+  const float* gp = G + (size_t)b * Lout * C + ch;
+  for (int to = to0; to < to1; to += 4) {
+    vf<V> g[4], xv[4];
 #pragma unroll
-        for (int e = 0; e < V; ++e) acc[e] += g[e];
-      } else {
-        const vf<V> xv = fx.load_row(to * stride + tap - pad, Lin, C);
+    for (int i = 0; i < 4; ++i) {  // unconditional, clamped loads
+      const int tc = to + i < Lout ? to + i : Lout - 1;
+      g[i] = vload<V>(gp + (size_t)tc * C);
+      xv[i] = tap == ks ? g[i] : fx.load_row(tc * stride + tap - pad, Lin, C);
+    }
 #pragma unroll
-        for (int e = 0; e < V; ++e) acc[e] = fmaf(g[e], xv[e], acc[e]);
+    for (int i = 0; i < 4; ++i) {
+      if (to + i < to1) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = tap == ks ? acc[e] + g[i][e] : fmaf(g[i][e], xv[i][e], acc[e]);
       }
     }
   }

@@ -510,11 +510,26 @@ __global__ void dw_generic_kernel(SrcDesc sd, int C, int Lout, int ks, int strid
   src.init(sd, b, ch, C, nullptr, 0);
   const int pad = (ks - 1) / 2;
   vf<V> acc = bias ? vload<V>(bias + ch) : vzero<V>();
-  for (int j = 0; j < ks; ++j) {
-    const int ti = t * stride - pad + j;
-    vf<V> xv = src.finalize(src.load_raw(ti), ti);
+  // taps in groups of 8: the row loads (and the weight loads) of a group are issued before any is consumed
+  for (int j0 = 0; j0 < ks; j0 += 8) {
+    vf<V> xr[8];
+    float wv[8][V];
 #pragma unroll
-    for (int e = 0; e < V; ++e) acc[e] = fmaf(__ldg(w + (size_t)(ch + e) * ks + j), xv[e], acc[e]);
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u < ks ? j0 + u : ks - 1;
+      xr[u] = src.load_raw(t * stride - pad + j);
+#pragma unroll
+      for (int e = 0; e < V; ++e) wv[u][e] = __ldg(w + (size_t)(ch + e) * ks + j);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (j0 + u < ks) {
+        const int ti = t * stride - pad + j0 + u;
+        const vf<V> xv = src.finalize(xr[u], ti);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = fmaf(wv[u][e], xv[e], acc[e]);
+      }
+    }
   }
   if (round_out) vround_tf32<V>(acc);
   vstore<V>(out + ((size_t)b * Lout + t) * C + ch, acc);

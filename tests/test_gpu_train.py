@@ -502,11 +502,12 @@ def test_eval_mode_ignores_dropout_and_graph_replays_draw_fresh_masks():
         ref = O.forward(sd, wav, O.OracleConfig(sample_rate=SR, **kw))
     assert (y_eval.cpu() - ref).abs().max().item() / ref.abs().max().item() < 3e-5
     # eval under grad: still deterministic (nn.Dropout semantics), train: differs from eval and between calls
-    y_eval_grad = m(x)
-    assert torch.equal(y_eval_grad.detach(), y_eval)
+    y_eval_grad = m(x)          # (the training forward materialises x_fused: same values up to fp32 rounding)
+    assert (y_eval_grad.detach() - y_eval).abs().max().item() / y_eval.abs().max().item() < 1e-5
     m.train()
     y1, y2 = m(x).detach().clone(), m(x).detach().clone()
-    assert not torch.equal(y1, y_eval) and not torch.equal(y1, y2)
+    scale = y_eval.abs().max().item()
+    assert (y1 - y_eval).abs().max().item() / scale > 1e-3 and (y1 - y2).abs().max().item() / scale > 1e-3
     # the fused step as a CUDA graph: every replay advances the device offset and draws new masks
     L = look2hear.losses
     ts = look2hear.system.TrainingStep(m, L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True), lr=0.0)
