@@ -84,6 +84,19 @@ __global__ void __launch_bounds__(256) coef_inject_gate_kernel(InjectCoefArgs a,
   }
 }
 
+// wT[k, c] = w[c, k]: depthwise weights [C][ks] -> [ks][C], so that a thread's 4 channels of one tap are one vector load
+__global__ void weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wT, int C, int ks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * ks) return;
+  const int k = i / C, c = i % C;
+  wT[i] = w[(size_t)c * ks + k];
+}
+
+int launch_weight_transpose(const float* w, float* wT, int C, int ks, cudaStream_t st) {
+  TD_LAUNCH(weight_transpose_kernel, cdiv(C * ks, 256), 256, 0, st, w, wT, C, ks);
+  return 0;
+}
+
 int launch_coef_inject_gate(const InjectCoefArgs& a, int B, int C, cudaStream_t st) {
   dim3 grid(B, a.n);
   TD_LAUNCH(coef_inject_gate_kernel, grid, 256, 0, st, a, C);

@@ -7,7 +7,7 @@ namespace td {
   namespace NS {                                                                                              \
   int launch_dw5(const DwArgs& a, cudaStream_t st);                                                           \
   int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int ks, int stride, const float* w, \
-                        const float* bias, float* out, int round_out, cudaStream_t st);                       \
+                        const float* wT, const float* bias, float* out, int round_out, cudaStream_t st);      \
   int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, cudaStream_t st);     \
   int launch_la_combine(const LaArgs& a, cudaStream_t st);                                                    \
   int launch_la_local_stats(const DwArgs* steps, int n, cudaStream_t st);                                     \
@@ -20,9 +20,9 @@ int launch_dw5(const DwArgs& a, cudaStream_t st) {
   return a.act_bf16 ? act_bf16::launch_dw5(a, st) : act_f32::launch_dw5(a, st);
 }
 int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int ks, int stride, const float* w,
-                      const float* bias, float* out, int round_out, int act_bf16, cudaStream_t st) {
-  return act_bf16 ? act_bf16::launch_dw_generic(src, kind, B, C, Lout, ks, stride, w, bias, out, round_out, st)
-                  : act_f32::launch_dw_generic(src, kind, B, C, Lout, ks, stride, w, bias, out, round_out, st);
+                      const float* wT, const float* bias, float* out, int round_out, int act_bf16, cudaStream_t st) {
+  return act_bf16 ? act_bf16::launch_dw_generic(src, kind, B, C, Lout, ks, stride, w, wT, bias, out, round_out, st)
+                  : act_f32::launch_dw_generic(src, kind, B, C, Lout, ks, stride, w, wT, bias, out, round_out, st);
 }
 int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, int act_bf16, cudaStream_t st) {
   return act_bf16 ? act_bf16::launch_inject_materialize(src, kind, B, C, out, st)

@@ -510,35 +510,78 @@ __global__ void dw_generic_kernel(SrcDesc sd, int C, int Lout, int ks, int strid
   src.init(sd, b, ch, C, nullptr, 0);
   const int pad = (ks - 1) / 2;
   vf<V> acc = bias ? vload<V>(bias + ch) : vzero<V>();
-  // taps in groups of 8: the row loads (and the weight loads) of a group are issued before any is consumed
-  for (int j0 = 0; j0 < ks; j0 += 8) {
-    vf<V> xr[8];
-    float wv[8][V];
+  for (int j = 0; j < ks; ++j) {
+    const int ti = t * stride - pad + j;
+    vf<V> xv = src.finalize(src.load_raw(ti), ti);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u < ks ? j0 + u : ks - 1;
-      xr[u] = src.load_raw(t * stride - pad + j);
-#pragma unroll
-      for (int e = 0; e < V; ++e) wv[u][e] = __ldg(w + (size_t)(ch + e) * ks + j);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (j0 + u < ks) {
-        const int ti = t * stride - pad + j0 + u;
-        const vf<V> xv = src.finalize(xr[u], ti);
-#pragma unroll
-        for (int e = 0; e < V; ++e) acc[e] = fmaf(wv[u][e], xv[e], acc[e]);
-      }
-    }
+    for (int e = 0; e < V; ++e) acc[e] = fmaf(__ldg(w + (size_t)(ch + e) * ks + j), xv[e], acc[e]);
   }
   if (round_out) vround_tf32<V>(acc);
   vstore<V>(out + ((size_t)b * Lout + t) * C + ch, acc);
 }
 
+// Input-stationary form of the same convolution for the fork's conv_pool (k = 2s+1, stride s up to 16): a thread owns
+// 4 channels and RO = 8 consecutive output rows, walks the (RO-1)*s + k input rows they cover ONCE (each row is
+// loaded and normalised once, in batches of 8 loads issued back to back) and adds it to the <= 3 outputs whose
+// window contains it.  Weights are read from a transposed copy wT [k][C] (one vector load per (row, output) pair,
+// L1-resident) instead of four scalar loads per tap.  The output-stationary kernel above re-read every input row
+// through ~2 windows and ran 6x off the HBM roofline (conv_pool 7.4 of the fork's 25 ms per step at B = 64).
+template <int KIND>
+__global__ void __launch_bounds__(256) dw_strided_kernel(SrcDesc sd, int C, int Lout, int ks, int stride,
+                                                         const float* __restrict__ wT, const float* __restrict__ bias,
+                                                         float* __restrict__ out, int round_out) {
+  constexpr int V = 4, RO = 8;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (ch >= C) return;
+  Src<KIND, V, true> src;
+  src.init(sd, b, ch, C, nullptr, 0);
+  const int pad = (ks - 1) / 2;
+  const int to0 = blockIdx.x * RO, to1 = min(to0 + RO, Lout);  // uniform across the CTA, like every branch below
+  vf<V> acc[RO];
+  const vf<V> bv = bias ? vload<V>(bias + ch) : vzero<V>();
+#pragma unroll
+  for (int r = 0; r < RO; ++r) acc[r] = bv;
+  const int ti0 = to0 * stride - pad, ti1 = (to1 - 1) * stride + pad;  // inclusive
+  for (int tb = ti0; tb <= ti1; tb += 8) {
+    vf<V> xr[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xr[u] = src.load_raw(tb + u <= ti1 ? tb + u : ti1);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int ti = tb + u;
+      if (ti <= ti1) {
+        const vf<V> xv = src.finalize(xr[u], ti);
+#pragma unroll
+        for (int r = 0; r < RO; ++r) {
+          const int tap = ti + pad - (to0 + r) * stride;
+          if (tap >= 0 && tap < ks && to0 + r < to1) {
+            const vf<V> wv = vload<V>(wT + (size_t)tap * C + ch);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[r][e] = fmaf(wv[e], xv[e], acc[r][e]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RO; ++r) {
+    if (to0 + r < to1) {
+      if (round_out) vround_tf32<V>(acc[r]);
+      vstore<V>(out + ((size_t)b * Lout + to0 + r) * C + ch, acc[r]);
+    }
+  }
+}
+
 int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int ks, int stride,
-                      const float* w, const float* bias, float* out, int round_out, cudaStream_t st) {
+                      const float* w, const float* wT, const float* bias, float* out, int round_out, cudaStream_t st) {
   TD_REQUIRE(C % 4 == 0 && (ks & 1), "dw_generic: C=%d ks=%d", C, ks);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
+  if (wT && kind == SRC_AFFINE) {
+    dim3 grid(cdiv(Lout, 8), cdiv(C / 4, threads), B);
+    TD_LAUNCH((dw_strided_kernel<SRC_AFFINE>), grid, threads, 0, st, src, C, Lout, ks, stride, wT, bias, out, round_out);
+    return 0;
+  }
   dim3 grid(Lout, cdiv(C / 4, threads), B);
   if (kind == SRC_AFFINE) {
     TD_LAUNCH((dw_generic_kernel<SRC_AFFINE>), grid, threads, 0, st, src, C, Lout, ks, stride, w, bias, out, round_out);

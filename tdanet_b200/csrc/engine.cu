@@ -58,6 +58,10 @@ static int gemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
 
 static int prepare_weights(const Ctx& x) {
   const tdanet_config_t* c = x.c;
+  if (c->variant == TDANET_FORK)  // conv_pool[j] depthwise weights [C][k] -> [k][C] for the input-stationary kernel
+    for (int j = 0; j < c->depth; ++j)
+      if (int e = launch_weight_transpose(x.w->conv_pool[j].dw_w, x.at(x.p->aux_pool_dwT[j]), c->in_channels,
+                                          j == 0 ? 5 : 2 * (1 << j) + 1, x.st)) return e;
   if (c->gemm_mode == TDANET_GEMM_FP32) return 0;
   const size_t C = c->in_channels, cc = c->out_channels;
   const int m = c->gemm_mode;
@@ -194,7 +198,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       const tdanet_sepconvnorm_t& q = w->conv_pool[j];
       Tag tp("conv_pool");
       if (int e = launch_dw_generic(affine_src(x.at(p.spp[k]), p.L[k], spp_norm(k)), SRC_AFFINE, B, C, Lb,
-                                    ks, s, q.dw_w, q.dw_b, x.at(p.pool_dw[k]), x.rnd(), x.bf(), x.st)) return e;
+                                    ks, s, q.dw_w, x.at(p.aux_pool_dwT[j]), q.dw_b, x.at(p.pool_dw[k]), x.rnd(), x.bf(), x.st)) return e;
       g = GemmArgs{};
       g.A = x.at(p.pool_dw[k]); g.W = q.pw_w; g.bias = q.pw_b; g.D = x.at(p.pool_pw[k]);
       g.B = B; g.L = Lb; g.N = C; g.K = C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_pool[k]);

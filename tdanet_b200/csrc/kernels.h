@@ -50,8 +50,12 @@ struct DwArgs {
 int launch_dw5(const DwArgs& a, cudaStream_t st);
 
 // Generic depthwise conv (any odd k, any stride), plain/affine source, writes out, no stats.
+// wT (optional): transposed copy [ks][C] of w [C][ks] (launch_weight_transpose) - selects the input-stationary kernel.
 int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int ks, int stride,
-                      const float* w, const float* bias, float* out, int round_out, int act_bf16, cudaStream_t st);
+                      const float* w, const float* wT, const float* bias, float* out, int round_out, int act_bf16,
+                      cudaStream_t st);
+// wT[k, c] = w[c, k]   (coef.cu)
+int launch_weight_transpose(const float* w, float* wT, int C, int ks, cudaStream_t st);
 
 // out[b, t, :] = injected operand (SRC_INJECT_GATE / SRC_INJECT_ADD) written out, [B, src.L, C]
 int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, int act_bf16, cudaStream_t st);

@@ -31,6 +31,7 @@ struct Plan {
   size_t st_enc;  // [B,2] double
   // TF32 auxiliary weight copies
   size_t aux_proj, aux_res, aux_in, aux_out, aux_fc1, aux_fc2, aux_pool[TDANET_MAX_DEPTH];
+  size_t aux_pool_dwT[TDANET_MAX_DEPTH];  // FORK: conv_pool[j].dw_conv.weight transposed to [k][C]
   // ---- block arena [blk_begin, blk_begin + blk_stride)
   size_t blk_begin = 0, blk_stride = 0;
   int n_blk = 1;
@@ -173,7 +174,10 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
   p.aux_out = wbuf((size_t)C * C);
   p.aux_fc1 = wbuf((size_t)2 * C * C);
   p.aux_fc2 = wbuf((size_t)2 * C * C);
-  for (int k = 0; k < depth; ++k) p.aux_pool[k] = c->variant == TDANET_FORK ? wbuf((size_t)C * C) : 0;
+  for (int k = 0; k < depth; ++k) {
+    p.aux_pool[k] = c->variant == TDANET_FORK ? wbuf((size_t)C * C) : 0;
+    p.aux_pool_dwT[k] = c->variant == TDANET_FORK ? wbuf((size_t)C * (k == 0 ? 5 : 2 * (1 << k) + 1)) : 0;
+  }
   if (train) {
     p.mlogit = p.act("mlogit", L0, NS * Nb);
     p.nenc = p.act("nenc", L0, Nb);
