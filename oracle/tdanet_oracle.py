@@ -157,12 +157,12 @@ def la(sd, prefix, x_l, x_g, cfg):
     return loc * gate + emb
 
 
-def mha_seq_first(x, w_in, b_in, w_out, b_out, n_head, cfg=None):
+def mha_seq_first(x, w_in, b_in, w_out, b_out, n_head, cfg=None, tap=True):
     """nn.MultiheadAttention eval forward for input laid out (seq, batch, embed)."""
     S, N, E = x.shape
     d = E // n_head
     qkv = F.linear(x, w_in, b_in)
-    if cfg is not None:
+    if cfg is not None and tap:
         _tap(cfg, "ga.qkv", qkv)
     q, k, v = qkv.split(E, dim=-1)
     q = q.reshape(S, N * n_head, d).transpose(0, 1) * (1.0 / math.sqrt(d))
@@ -173,7 +173,7 @@ def mha_seq_first(x, w_in, b_in, w_out, b_out, n_head, cfg=None):
         p = p * cfg.mask("att", p.dtype)             # dropout on the attention weights, [N*heads, S, S]
     o = (p @ v).transpose(0, 1).reshape(S, N, E)
     if cfg is not None:
-        _tap(cfg, "ga.attn_ctx", o)
+        _tap(cfg, "ga.attn_ctx", o if tap else o.transpose(0, 1))       # [B, T', C] either way
     return F.linear(o, w_out, b_out)
 
 
@@ -189,7 +189,11 @@ def global_attention(sd, prefix, x, cfg):
     w_out, b_out = sd[f"{a}.attn.out_proj.weight"], sd[f"{a}.attn.out_proj.bias"]
     if cfg.variant == "multres":
         # batch_first=True: sequence axis is time; correct residual
-        o = mha_seq_first(h.transpose(0, 1), w_in, b_in, w_out, b_out, cfg.n_head).transpose(0, 1)
+        o = mha_seq_first(h.transpose(0, 1), w_in, b_in, w_out, b_out, cfg.n_head, cfg, tap=False).transpose(0, 1)
+        _tap(cfg, "ga.qkv", F.linear(h, w_in, b_in))
+        m_ao = cfg.mask("ao", o.dtype)
+        if m_ao is not None:
+            o = o * m_ao                                   # output + self.dropout(attn_output)
         post = h + o
     else:
         # batch_first=False fed [B, T', C]: the *batch* axis is the sequence axis,

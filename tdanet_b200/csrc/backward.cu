@@ -320,14 +320,14 @@ static int launch_transpose(const float* W, float* Wt, int N, int K, cudaStream_
 }
 
 static int launch_framed_wgrad(const float* M, const float* sig, float* dW, int B, int L0, int CI, int NO, int K,
-                               int S, int T, int shift, cudaStream_t st) {
+                               int S, int T, int shift, int m_stride, cudaStream_t st) {
   TD_REQUIRE(K <= 1024, "framed_wgrad: window %d", K);
   const int R = B * L0;
   int splits = cdiv(1184, CI * NO);
   const int rps = cdiv(R, splits);
   splits = cdiv(R, rps);
   dim3 grid(CI * NO, splits);
-  TD_LAUNCH(framed_wgrad_kernel, grid, K, 0, st, M, sig, dW, B, L0, CI, NO, K, S, T, shift, rps);
+  TD_LAUNCH(framed_wgrad_kernel, grid, K, 0, st, M, sig, dW, B, L0, CI, NO, K, S, T, shift, rps, m_stride);
   return 0;
 }
 
@@ -438,8 +438,9 @@ static int global_attention_backward(const BCtx& x) {
   const tdanet_weights_t* gw = x.g;
   const Plan& p = *x.p;
   const int B = p.B, C = c->in_channels, Lb = p.Lb, R = B * Lb;
+  const bool time_axis = c->variant == TDANET_MULTRES;  // MultiHeadAttentionFixed: sequence = time, LN(x_pe + drop(a))
   const int group = c->attn_group > 0 ? c->attn_group : B;
-  TD_REQUIRE(B % group == 0, "batch %d is not a multiple of attn_group %d", B, group);
+  TD_REQUIRE(time_axis || B % group == 0, "batch %d is not a multiple of attn_group %d", B, group);
   // ga_out = ga_mid + gLN(fc2)
   const NormRef n_fc2 = norm_ref(x, p.st_fc2, 2, (double)Lb * C, w->fc2.gamma, w->fc2.beta);
   const NormRef n_fc1 = norm_ref(x, p.st_fc1, 2, (double)Lb * 2 * C, w->fc1.gamma, w->fc1.beta);
@@ -490,24 +491,39 @@ static int global_attention_backward(const BCtx& x) {
   // g_ga_mid = g_ga_out (skip) + fc1 data gradient
   { Tag t("dgrad_fc1"); if (int e = dgrad(x, x.at(p.g_ffn), p.wt_fc1, p.auxt_fc1, x.at(p.g_ga_mid), Lb, C, 2 * C, x.at(p.g_ga_out))) return e; }
   // ga_mid = ga_in + DropPath(LN2(2 * attn_out));  with dropout: LN2(attn_out') where the forward left
-  // attn_out' = attn_out * (1 + mask/keep) in the workspace
+  // attn_out' = attn_out * (1 + mask/keep) in the workspace.
+  // MULTRES: ga_mid = ga_in + DropPath(LN2(attn_in + attn_out')), attn_out' = attn_out * mask/keep: the gradient w.r.t.
+  // the LayerNorm input goes to attn_out (through the mask) AND, as `g_ln_in`, to attn_in (added by dgrad_in_proj).
+  const float* g_ln_in = nullptr;
   { Tag t("bwd_bottom_misc");
     const float* dy = x.at(p.g_ga_mid);
     if (m_dp) {  // g_ctx is free here
       if (int e = launch_mask_scale(dy, x.at(p.g_ctx), nRC, nullptr, 1.f, 0.f, m_dp, ikp, per_item, 0, x.st)) return e;
       dy = x.at(p.g_ctx);
     }
-    if (int e = launch_ln_bwd(x.at(p.attn_out), m_ao ? 1.f : 2.f, w->ln2_w, dy, x.at(p.ln_rows), nullptr,
-                              x.at(p.g_attn_out), x.gp(gw->ln2_w), x.gp(gw->ln2_b), R, C, x.st)) return e;
-    if (m_ao)
-      if (int e = launch_mask_scale(x.at(p.g_attn_out), x.at(p.g_attn_out), nRC, m_ao, 1.f, ik, nullptr, 1.f, 1, 0, x.st)) return e; }
+    if (time_axis) {
+      float* z = x.at(p.g_qkv);  // free until the attention backward writes it
+      TD_LAUNCH(add_kernel, (unsigned)((nRC + 255) / 256 > 4096 ? 4096 : (nRC + 255) / 256), 256, 0, x.st, x.at(p.attn_in),
+                x.at(p.attn_out), z, nRC);
+      float* gz = m_ao ? x.at(p.g_fc1) : x.at(p.g_attn_out);  // g_fc1 is free by now and read by no side-stream launch
+      if (int e = launch_ln_bwd(z, 1.f, w->ln2_w, dy, x.at(p.ln_rows), nullptr, gz, x.gp(gw->ln2_w), x.gp(gw->ln2_b), R, C, x.st)) return e;
+      if (m_ao)
+        if (int e = launch_mask_scale(gz, x.at(p.g_attn_out), nRC, m_ao, 0.f, ik, nullptr, 1.f, 1, 0, x.st)) return e;
+      g_ln_in = gz;
+    } else {
+      if (int e = launch_ln_bwd(x.at(p.attn_out), m_ao ? 1.f : 2.f, w->ln2_w, dy, x.at(p.ln_rows), nullptr,
+                                x.at(p.g_attn_out), x.gp(gw->ln2_w), x.gp(gw->ln2_b), R, C, x.st)) return e;
+      if (m_ao)
+        if (int e = launch_mask_scale(x.at(p.g_attn_out), x.at(p.g_attn_out), nRC, m_ao, 1.f, ik, nullptr, 1.f, 1, 0, x.st)) return e;
+    }
+  }
   { Tag t("wgrad_out_proj"); if (int e = wgrad_side(x, x.at(p.g_attn_out), x.at(p.attn_ctx), x.gp(gw->out_proj_w), x.gp(gw->out_proj_b), R, C, C)) return e; }
   { Tag t("dgrad_out_proj"); if (int e = dgrad(x, x.at(p.g_attn_out), p.wt_out, p.auxt_out, x.at(p.g_ctx), Lb, C, C, nullptr)) return e; }
   { Tag t("bwd_attention");
     if (int e = launch_att_bwd(x.at(p.qkv), x.at(p.g_ctx), x.at(p.att_p), x.at(p.att_ds), x.at(p.g_qkv), B, Lb, C,
-                               c->n_head, group, 0, m_att, ik, x.st)) return e; }
+                               c->n_head, group, time_axis, m_att, ik, x.st)) return e; }
   { Tag t("wgrad_in_proj"); if (int e = wgrad_side(x, x.at(p.g_qkv), x.at(p.attn_in), x.gp(gw->in_proj_w), x.gp(gw->in_proj_b), R, 3 * C, C)) return e; }
-  { Tag t("dgrad_in_proj"); if (int e = dgrad(x, x.at(p.g_qkv), p.wt_in, p.auxt_in, x.at(p.g_attn_in), Lb, C, 3 * C, nullptr)) return e; }
+  { Tag t("dgrad_in_proj"); if (int e = dgrad(x, x.at(p.g_qkv), p.wt_in, p.auxt_in, x.at(p.g_attn_in), Lb, C, 3 * C, g_ln_in)) return e; }
   // attn_in = LN1(ga_in) + pe;  g_ga_in = g_ga_mid (skip) + LN1 backward
   Tag t("bwd_bottom_misc");
   return launch_ln_bwd(x.at(p.ga_in), 1.f, w->ln1_w, x.at(p.g_attn_in), x.at(p.ln_rows), x.at(p.g_ga_mid),
@@ -712,7 +728,7 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
       const size_t n = (size_t)R0 * CI;
       TD_LAUNCH(dec_bwd_data_naive_kernel, (unsigned)((n + 127) / 128), 128, 0, st, d_est, w->dec_w, x.at(p.g_masked), B, L0, CI, NS, K, S, T, K - S);
     }
-    if (int e = launch_framed_wgrad(x.at(p.masked), d_est, x.gp(gw->dec_w), B, L0, CI, NS, K, S, T, K - S, st)) return e;
+    if (int e = launch_framed_wgrad(x.at(p.masked), d_est, x.gp(gw->dec_w), B, L0, CI, NS, K, S, T, K - S, CI, st)) return e;
     // masked = relu(m) * enc
     const size_t ne = (size_t)R0 * Nb;
     TD_LAUNCH(mask_bwd_kernel, (unsigned)((ne + 255) / 256), 256, 0, st, x.at(p.g_masked), x.at(p.mlogit), x.at(p.enc), x.at(p.g_enc), R0, NS, Nb);
@@ -747,19 +763,25 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
     const size_t n = (size_t)R0 * cc;
     TD_LAUNCH(add_kernel, (unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, x.at(p.g_u[cur]), x.at(p.g_x0), x.at(p.g_x0), n);
   }
-  // x0 = bottleneck(gLN(enc))
+  // x0 = bottleneck(gLN(enc))   |   MULTRES: x0 = gLN(enc)
   const NormRef n_enc = norm_ref(x, p.st_enc, 2, (double)L0 * Nb, w->ln_gamma, w->ln_beta);
-  {
+  float* d_nenc = x.at(p.g_masked);  // free by now, large enough
+  if (c->variant == TDANET_MULTRES) {
+    d_nenc = x.at(p.g_x0);
+  } else {
     dim3 grid(cdiv(L0 * Nb, 256), 1, B);
     TD_LAUNCH(gln_fwd_apply_kernel, grid, 256, 0, st, x.at(p.enc), n_enc, x.at(p.nenc), L0, Nb);
+    if (int e = launch_wgrad(x.at(p.g_x0), x.at(p.nenc), x.gp(gw->bottleneck_w), x.gp(gw->bottleneck_b), R0, cc, Nb, nullptr, st)) return e;
+    if (int e = launch_small_dgrad(x.at(p.g_x0), w->bottleneck_w, d_nenc, R0, cc, Nb, nullptr, nullptr, nullptr, st)) return e;
   }
-  if (int e = launch_wgrad(x.at(p.g_x0), x.at(p.nenc), x.gp(gw->bottleneck_w), x.gp(gw->bottleneck_b), R0, cc, Nb, nullptr, st)) return e;
-  float* d_nenc = x.at(p.g_masked);  // free by now, large enough
-  if (int e = launch_small_dgrad(x.at(p.g_x0), w->bottleneck_w, d_nenc, R0, cc, Nb, nullptr, nullptr, nullptr, st)) return e;
   if (int e = launch_gln_bwd_stats(d_nenc, x.at(p.enc), n_enc, x.gp(gw->ln_gamma), x.gp(gw->ln_beta), x.at<double>(p.bs_enc), B, L0, Nb, st)) return e;
   if (int e = launch_gln_bwd_apply(gln_grad(d_nenc, x.at(p.enc), n_enc, x.at<double>(p.bs_enc)), x.at(p.g_enc), 1, B, L0, Nb, st)) return e;
-  // encoder Conv1d (pad_input folded into the indexing)
-  if (int e = launch_framed_wgrad(x.at(p.g_enc), wav, x.gp(gw->enc_w[0]), B, L0, Nb, 1, K, S, T, K - S, st)) return e;
+  // encoder Conv1d (pad_input folded into the indexing); MULTRES: conv k has window (k+1)*K and its slice of the channels
+  {
+    const int cpc = Nb / c->enc_convs;
+    for (int k = 0; k < c->enc_convs; ++k)
+      if (int e = launch_framed_wgrad(x.at(p.g_enc) + k * cpc, wav, x.gp(gw->enc_w[k]), B, L0, cpc, 1, (k + 1) * K, S, T, K - S, Nb, st)) return e;
+  }
   // depthwise weight / bias gradients: replicas -> the caller's buffers
   if (!reps.empty()) {
     FoldArgs f{};

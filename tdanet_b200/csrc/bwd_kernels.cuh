@@ -1439,7 +1439,7 @@ __global__ void __launch_bounds__(256) dec_bwd_data_kernel(const float* __restri
 //   decoder weight: M = masked, sig = d_est;   encoder weight: M = d_enc, sig = wav (NO = 1)
 __global__ void framed_wgrad_kernel(const float* __restrict__ M, const float* __restrict__ sig,
                                     float* __restrict__ dW, int B, int L0, int CI, int NO, int K, int S, int T,
-                                    int shift, int rows_per_split) {
+                                    int shift, int rows_per_split, int m_stride) {  // m_stride: row stride of M (>= CI)
   const int j = threadIdx.x;
   const int ci = blockIdx.x / NO, o = blockIdx.x % NO;
   if (j >= K) return;
@@ -1448,7 +1448,7 @@ __global__ void framed_wgrad_kernel(const float* __restrict__ M, const float* __
   float acc = 0.f;
   for (int r = r0; r < r1; ++r) {
     const int b = r / L0, l = r % L0;
-    const float mv = M[(size_t)r * CI + ci];
+    const float mv = M[(size_t)r * m_stride + ci];
     acc = fmaf(mv, framed_sig(sig + ((size_t)b * NO + o) * T, l * S + j - K / 2, shift, T), acc);
   }
   atomicAdd(dW + ((size_t)ci * NO + o) * K + j, acc);

@@ -520,14 +520,18 @@ __global__ void dw_generic_kernel(SrcDesc sd, int C, int Lout, int ks, int strid
   vstore<V>(out + ((size_t)b * Lout + t) * C + ch, acc);
 }
 
-// Input-stationary form of the same convolution for the fork's conv_pool (k = 2s+1, stride s up to 16): a thread owns
-// 4 channels and RO = 8 consecutive output rows, walks the (RO-1)*s + k input rows they cover ONCE (each row is
-// loaded and normalised once, in batches of 8 loads issued back to back) and adds it to the <= 3 outputs whose
-// window contains it.  Weights are read from a transposed copy wT [k][C] (one vector load per (row, output) pair,
-// L1-resident) instead of four scalar loads per tap.  The output-stationary kernel above re-read every input row
-// through ~2 windows and ran 6x off the HBM roofline (conv_pool 7.4 of the fork's 25 ms per step at B = 64).
+// Input-stationary form of the same convolution for the fork's conv_pool (k = 2s+1, stride s = 2..16, pad s): a thread
+// owns 4 channels and RO = 8 consecutive output rows and walks the (RO+1)*s + 1 input rows they cover once.  Input
+// row base + q*s + ph (q = 0..RO, ph = 0..s-1) feeds output q through tap ph and output q-1 through tap s+ph, so the
+// loop runs over the phase ph with q unrolled: two weight vectors (from the transposed copy wT [k][C]) and RO+1
+// independent row loads per iteration, 8 FMAs per row and accumulators with static indices.  The rows q*s also
+// close output q-2 through the last tap 2s (a short pass of its own).
+// History: the output-stationary kernel re-read every row through ~2 windows with 4 scalar weight loads per tap
+// (conv_pool 7.4 of the fork's 25 ms per step at B = 64); a first input-stationary version that tested all RO
+// outputs per row moved the right bytes (292 MB for 263 MB) but issued 103 M warp instructions (ncu
+// profiles/r01_ncu_dw_strided.txt: 201 us, issue-bound).
 template <int KIND>
-__global__ void __launch_bounds__(256) dw_strided_kernel(SrcDesc sd, int C, int Lout, int ks, int stride,
+__global__ void __launch_bounds__(256) dw_strided_kernel(SrcDesc sd, int C, int Lout, int S,
                                                          const float* __restrict__ wT, const float* __restrict__ bias,
                                                          float* __restrict__ out, int round_out) {
   constexpr int V = 4, RO = 8;
@@ -536,37 +540,45 @@ __global__ void __launch_bounds__(256) dw_strided_kernel(SrcDesc sd, int C, int 
   if (ch >= C) return;
   Src<KIND, V, true> src;
   src.init(sd, b, ch, C, nullptr, 0);
-  const int pad = (ks - 1) / 2;
-  const int to0 = blockIdx.x * RO, to1 = min(to0 + RO, Lout);  // uniform across the CTA, like every branch below
+  const int to0 = blockIdx.x * RO;
+  const int base = to0 * S - S;  // input row of (q = 0, ph = 0); rows outside [0, L) are the conv's zero padding
   vf<V> acc[RO];
   const vf<V> bv = bias ? vload<V>(bias + ch) : vzero<V>();
 #pragma unroll
   for (int r = 0; r < RO; ++r) acc[r] = bv;
-  const int ti0 = to0 * stride - pad, ti1 = (to1 - 1) * stride + pad;  // inclusive
-  for (int tb = ti0; tb <= ti1; tb += 8) {
-    vf<V> xr[8];
+  {  // last tap: output r takes row base + (r + 2) * S
+    const vf<V> w2 = vload<V>(wT + (size_t)(2 * S) * C + ch);
+    vf<V> xr[RO];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) xr[u] = src.load_raw(tb + u <= ti1 ? tb + u : ti1);
+    for (int r = 0; r < RO; ++r) xr[r] = src.load_raw(base + (r + 2) * S);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int ti = tb + u;
-      if (ti <= ti1) {
-        const vf<V> xv = src.finalize(xr[u], ti);
+    for (int r = 0; r < RO; ++r) {
+      const vf<V> xv = src.finalize(xr[r], base + (r + 2) * S);
 #pragma unroll
-        for (int r = 0; r < RO; ++r) {
-          const int tap = ti + pad - (to0 + r) * stride;
-          if (tap >= 0 && tap < ks && to0 + r < to1) {
-            const vf<V> wv = vload<V>(wT + (size_t)tap * C + ch);
+      for (int e = 0; e < V; ++e) acc[r][e] = fmaf(w2[e], xv[e], acc[r][e]);
+    }
+  }
+  for (int ph = 0; ph < S; ++ph) {
+    const vf<V> wlo = vload<V>(wT + (size_t)ph * C + ch), whi = vload<V>(wT + (size_t)(S + ph) * C + ch);
+    vf<V> xr[RO + 1];
 #pragma unroll
-            for (int e = 0; e < V; ++e) acc[r][e] = fmaf(wv[e], xv[e], acc[r][e]);
-          }
-        }
+    for (int q = 0; q <= RO; ++q) xr[q] = src.load_raw(base + q * S + ph);
+#pragma unroll
+    for (int q = 0; q <= RO; ++q) {
+      const vf<V> xv = src.finalize(xr[q], base + q * S + ph);
+      if (q < RO) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[q][e] = fmaf(wlo[e], xv[e], acc[q][e]);
+      }
+      if (q >= 1) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[q - 1][e] = fmaf(whi[e], xv[e], acc[q - 1][e]);
       }
     }
   }
 #pragma unroll
   for (int r = 0; r < RO; ++r) {
-    if (to0 + r < to1) {
+    if (to0 + r < Lout) {
       if (round_out) vround_tf32<V>(acc[r]);
       vstore<V>(out + ((size_t)b * Lout + to0 + r) * C + ch, acc[r]);
     }
@@ -577,9 +589,9 @@ int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int 
                       const float* w, const float* wT, const float* bias, float* out, int round_out, cudaStream_t st) {
   TD_REQUIRE(C % 4 == 0 && (ks & 1), "dw_generic: C=%d ks=%d", C, ks);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
-  if (wT && kind == SRC_AFFINE) {
+  if (wT && kind == SRC_AFFINE && stride >= 2 && ks == 2 * stride + 1) {
     dim3 grid(cdiv(Lout, 8), cdiv(C / 4, threads), B);
-    TD_LAUNCH((dw_strided_kernel<SRC_AFFINE>), grid, threads, 0, st, src, C, Lout, ks, stride, wT, bias, out, round_out);
+    TD_LAUNCH((dw_strided_kernel<SRC_AFFINE>), grid, threads, 0, st, src, C, Lout, stride, wT, bias, out, round_out);
     return 0;
   }
   dim3 grid(Lout, cdiv(C / 4, threads), B);

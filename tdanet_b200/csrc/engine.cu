@@ -125,8 +125,9 @@ static int global_attention(const Ctx& x) {
   { Tag t("gemm_out_proj"); if (int e = gemm(x, g, p.aux_out)) return e; }
   // x + DropPath(LayerNorm(out + dropout(out)))  [BEST/FORK]   |   x + LayerNorm(pe_in + out)  [MULTRES]
   // training: attn_out <- out * (1 + mask/keep) in place (the backward pass expects it in this form)
+  //           MULTRES: attn_out <- out * mask/keep
   if (m_ao)
-    if (int e = launch_mask_scale(x.at(p.attn_out), x.at(p.attn_out), (size_t)B * Lb * C, m_ao, 1.f, ik, nullptr, 1.f, 1, 0, x.st)) return e;
+    if (int e = launch_mask_scale(x.at(p.attn_out), x.at(p.attn_out), (size_t)B * Lb * C, m_ao, time_axis ? 0.f : 1.f, ik, nullptr, 1.f, 1, 0, x.st)) return e;
   if (int e = launch_ln_residual(x.at(p.attn_out), x.at(p.attn_in), x.at(p.ga_in), w->ln2_w, w->ln2_b,
                                  x.at(p.ga_mid), time_axis ? 0 : (m_ao ? 2 : 1), DropRef{nullptr, 1.f, m_dp, ikp}, B, Lb, C, x.st)) return e;
   // FFN: fc1 (1x1, no bias) -> gLN -> dw k5 + bias -> ReLU -> fc2 (1x1, no bias) -> gLN

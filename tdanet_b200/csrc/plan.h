@@ -131,8 +131,6 @@ static inline int check_config(const tdanet_config_t* c) {
 // What the training path supports in this build (everything else raises instead of falling back).
 static inline int check_train_config(const tdanet_config_t* c) {
   if (int e = check_config(c)) return e;
-  if (c->variant == TDANET_MULTRES)
-    return fail(TDANET_EUNSUPPORTED, "training step: TDANetMultRes (variant 2) has no backward pass in this build");
   if (c->act_dtype != TDANET_ACT_F32)
     return fail(TDANET_EUNSUPPORTED, "training step: activations are kept in fp32 (act_dtype fp32)");
   TD_REQUIRE(c->dropout >= 0.f && c->dropout < 1.f && c->drop_path >= 0.f && c->drop_path < 1.f,
@@ -240,11 +238,14 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
         p.named.push_back({name, o, {d0, d1, d2}, 1});
         return o;
       };
-      const int group = c->attn_group > 0 ? c->attn_group : B;
+      // attention problems: (batch group, time index) with `group` tokens each; MULTRES: one per item with Lb tokens
+      const bool time_axis = c->variant == TDANET_MULTRES;
+      const int group = time_axis ? Lb : (c->attn_group > 0 ? c->attn_group : B);
+      const int64_t nprob = time_axis ? B : (int64_t)(B / group) * Lb;
       p.m_begin = p.bytes;
-      p.n_att = (size_t)B * Lb * c->n_head * group;
+      p.n_att = (size_t)nprob * c->n_head * group * group;
       if (p.drop_elem) {
-        p.m_att = bytes_of("m_att", (int64_t)(B / group) * Lb * c->n_head, group, group);
+        p.m_att = bytes_of("m_att", nprob * c->n_head, group, group);
         p.m_ao = bytes_of("m_ao", B, Lb, C);
         p.m_f1 = bytes_of("m_f1", B, Lb, 2 * C);
         p.m_f2 = bytes_of("m_f2", B, Lb, C);
@@ -342,7 +343,8 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     p.g_pool_dw = p.act(nullptr, Lb, C);
   }
   {
-    const int group = c->attn_group > 0 ? c->attn_group : B;
+    const bool time_axis = c->variant == TDANET_MULTRES;
+    const int group = time_axis ? Lb : (c->attn_group > 0 ? c->attn_group : B);
     const size_t n = (size_t)B * Lb * c->n_head * group;  // [problem, head, query, key]
     p.att_p = p.take(n * sizeof(float));
     p.att_ds = p.take(n * sizeof(float));

@@ -154,14 +154,9 @@ class _TDANetCommon(BaseModel):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # gradients w.r.t. the parameters through the hand-written backward pass; in train mode with the
             # reference's dropout / DropPath.  There is no gradient w.r.t. the waveform.
-            if self._variant in ("best", "fork", "origin", "yang"):
-                named = [(n, p) for n, p in self.named_parameters()]
-                est = _SeparateFn.apply(self, wav, tuple(n for n, _ in named), *[p for _, p in named])
-                return est.squeeze(0) if was_one_d else est
-            if self.training:
-                raise NotImplementedError(
-                    f"{type(self).__name__}: TDANetMultRes has no backward pass in this build; "
-                    "call .eval() under torch.no_grad() for separation")
+            named = [(n, p) for n, p in self.named_parameters()]
+            est = _SeparateFn.apply(self, wav, tuple(n for n, _ in named), *[p for _, p in named])
+            return est.squeeze(0) if was_one_d else est
         w = self._weights()
         if self.use_cuda_graph:
             est = self._engine.forward_graphed(w, wav, self.attn_group).clone()

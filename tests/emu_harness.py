@@ -72,8 +72,10 @@ def _check(lib, code):
 
 def make_engine(kw, sample_rate, gemm_mode="fp32", variant="best"):
     K = kw["enc_kernel_size"] * sample_rate // 1000
+    multres = variant == "multres"
     return SeparationEngine(variant, kw["out_channels"], kw["in_channels"], kw["num_blocks"], kw["upsampling_depth"],
-                            K, K // 2 + 1, kw["num_sources"], gemm_mode=gemm_mode)
+                            K, kw["out_channels"] if multres else K // 2 + 1, kw["num_sources"],
+                            enc_convs=kw.get("kernels", 4) if multres else 1, gemm_mode=gemm_mode)
 
 
 class Workspace:
@@ -121,7 +123,7 @@ def _stats(*raws):
     return torch.stack(out, dim=1)
 
 
-def random_drop_masks(B, Lb, C, n_head, num_blocks, dropout, drop_path, seed=11):
+def random_drop_masks(B, Lb, C, n_head, num_blocks, dropout, drop_path, seed=11, time_axis=False):
     """Keep-masks of every stochastic layer of every block in the layout of the CUDA workspace / OracleConfig.drop_masks."""
     g = torch.Generator().manual_seed(seed)
     keep = lambda shape, p: (torch.rand(shape, generator=g) >= p).to(torch.uint8)
@@ -129,7 +131,7 @@ def random_drop_masks(B, Lb, C, n_head, num_blocks, dropout, drop_path, seed=11)
     for _ in range(num_blocks):
         m = {}
         if dropout > 0:
-            m.update(att=keep((Lb * n_head, B, B), dropout), ao=keep((B, Lb, C), dropout),
+            m.update(att=keep((B * n_head, Lb, Lb) if time_axis else (Lb * n_head, B, B), dropout), ao=keep((B, Lb, C), dropout),
                      f1=keep((B, Lb, 2 * C), dropout), f2=keep((B, Lb, C), dropout))
         if drop_path > 0:
             m["dp"] = keep((2, B), drop_path)
@@ -203,8 +205,9 @@ def emu_backward(sd, wav, d_est, kw, sample_rate, variant="best", dropout=0.0, d
     lib = load_emu()
     eng = make_engine(kw, sample_rate, variant=variant)
     eng.set_dropout(dropout, drop_path)
+    okw = {k: v for k, v in kw.items() if k != "feat_len"}
     cfg = O.OracleConfig(variant=variant, sample_rate=sample_rate, taps={}, tap_all=True, drop_masks=drop_masks,
-                         dropout=dropout, drop_path=drop_path, **kw)
+                         dropout=dropout, drop_path=drop_path, **okw)
     with torch.no_grad():
         est = O.forward(sd, wav, cfg)
     B, T = wav.shape[0], wav.shape[-1]

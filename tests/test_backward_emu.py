@@ -11,7 +11,7 @@ import emu_harness as H
 SR = 8000
 
 
-CLASS = {"best": "TDANetBest", "fork": "TDANet", "origin": "TDANetOrigin"}
+CLASS = {"best": "TDANetBest", "fork": "TDANet", "origin": "TDANetOrigin", "multres": "TDANetMultRes"}
 
 
 def _model_sd(kw, seed=0, variant="best"):
@@ -40,13 +40,17 @@ CASES = {
     "depth5_odd": dict(out_channels=16, in_channels=64, num_blocks=2, upsampling_depth=5, enc_kernel_size=2, num_sources=2),
     "depth2_3src": dict(out_channels=16, in_channels=32, num_blocks=3, upsampling_depth=2, enc_kernel_size=4, num_sources=3),
     "depth3": dict(out_channels=32, in_channels=32, num_blocks=1, upsampling_depth=3, enc_kernel_size=4, num_sources=2),
+    # TDANetMultRes: `kernels` encoder convs of window (k+1)*K, no bottleneck, attention over the time axis
+    "multres4": dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=4, enc_kernel_size=4, num_sources=2, kernels=4),
+    "multres2": dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=3, enc_kernel_size=2, num_sources=2, kernels=2),
 }
 
 
 @pytest.mark.parametrize("variant,name,B,T", [
     ("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111), ("best", "depth2_3src", 2, 800), ("best", "depth3", 1, 997),
     ("fork", "depth4", 2, 1203), ("fork", "depth5_odd", 2, 1111), ("fork", "depth2_3src", 2, 800),
-    ("origin", "depth4", 2, 1203), ("origin", "depth3", 1, 997)])
+    ("origin", "depth4", 2, 1203), ("origin", "depth3", 1, 997),
+    ("multres", "multres4", 2, 1203), ("multres", "multres2", 3, 1111)])
 def test_emulated_backward_matches_autograd(variant, name, B, T):
     kw = CASES[name]
     sd = _model_sd(kw, variant=variant)
@@ -74,7 +78,8 @@ def test_emulated_backward_matches_autograd(variant, name, B, T):
 
 @pytest.mark.parametrize("variant,name,B,T,dropout,drop_path", [
     ("best", "depth4", 3, 1203, 0.1, 0.1), ("best", "depth3", 2, 997, 0.3, 0.0), ("best", "depth4", 4, 1203, 0.0, 0.4),
-    ("fork", "depth4", 3, 1203, 0.2, 0.3), ("origin", "depth4", 2, 1203, 0.1, 0.1)])
+    ("fork", "depth4", 3, 1203, 0.2, 0.3), ("origin", "depth4", 2, 1203, 0.1, 0.1),
+    ("multres", "multres4", 2, 1203, 0.2, 0.3), ("multres", "multres2", 3, 1111, 0.1, 0.0)])
 def test_emulated_backward_with_dropout_masks(variant, name, B, T, dropout, drop_path):
     """Train-mode stochastic layers: with the SAME keep-masks in the workspace and in the oracle,
     the emulated backward pass matches autograd of the oracle through nn.Dropout / attention-weight dropout / DropPath."""
@@ -85,7 +90,8 @@ def test_emulated_backward_with_dropout_masks(variant, name, B, T, dropout, drop
     d_est = torch.randn(B, kw["num_sources"], T, generator=g)
     eng = H.make_engine(kw, SR, variant=variant)
     Lb = eng.latent_lengths(T)[0][-1]
-    masks = H.random_drop_masks(B, Lb, kw["in_channels"], 8, kw["num_blocks"], dropout, drop_path)
+    masks = H.random_drop_masks(B, Lb, kw["in_channels"], 8, kw["num_blocks"], dropout, drop_path,
+                                time_axis=variant == "multres")
     if drop_path > 0:
         masks[0]["dp"][0, 0] = 0          # at least one dropped and one kept path
         masks[0]["dp"][1, -1] = 0

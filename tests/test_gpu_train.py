@@ -48,7 +48,7 @@ class _CompareWorkspace:
 
 @pytest.mark.parametrize("variant,name,B,T", [("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111),
                                               ("best", "depth2_3src", 2, 800), ("fork", "depth4", 2, 1203),
-                                              ("fork", "depth5_odd", 3, 1111)])
+                                              ("fork", "depth5_odd", 3, 1111), ("multres", "multres4", 2, 1203)])
 def test_forward_train_keeps_what_backward_needs(variant, name, B, T):
     kw = CASES[name]
     sd = _model_sd(kw, variant=variant)
@@ -99,7 +99,8 @@ def _grad_errors(named_grads, ref):
 @pytest.mark.parametrize("variant,name,B,T", [("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111),
                                               ("best", "depth2_3src", 2, 800), ("best", "depth3", 1, 997),
                                               ("fork", "depth4", 2, 1203), ("fork", "depth5_odd", 3, 1111),
-                                              ("fork", "depth2_3src", 2, 800), ("origin", "depth5_odd", 3, 1111)])
+                                              ("fork", "depth2_3src", 2, 800), ("origin", "depth5_odd", 3, 1111),
+                                              ("multres", "multres4", 2, 1203), ("multres", "multres2", 3, 1111)])
 def test_gradients_match_autograd(variant, name, B, T, mode, tol_max, tol_all):
     kw = CASES[name]
     sd = _model_sd(kw, variant=variant)
@@ -434,6 +435,7 @@ def test_dropout_masks_are_philox_and_advance():
     ("best", "depth4", 4, 1203, 0.1, 0.1, "fp32"), ("best", "depth5_odd", 3, 1111, 0.3, 0.5, "fp32"),
     ("fork", "depth4", 4, 1203, 0.2, 0.3, "fp32"), ("origin", "depth5_odd", 3, 1111, 0.1, 0.1, "fp32"),
     ("best", "depth4", 12, 1203, 0.1, 0.0, "fp32"), ("best", "depth4", 20, 800, 0.1, 0.1, "fp32"),
+    ("multres", "multres4", 3, 1203, 0.2, 0.3, "fp32"), ("multres", "multres2", 2, 1111, 0.1, 0.0, "fp32"),
     ("best", "depth4", 4, 1203, 0.1, 0.1, "tf32")])
 def test_train_mode_matches_oracle_with_the_same_masks(variant, name, B, T, dropout, drop_path, mode):
     """model.train(): output and every parameter gradient equal the oracle evaluated with the keep-masks the
