@@ -50,6 +50,32 @@ void profile_mark(const char* name, cudaStream_t st, bool begin) {
 }
 
 // ----------------------------------------------------------------------------- forward
+// Side stream of the forward pass (lazily created per device, never destroyed): runs the statistics of the LOCAL
+// branch of every top-down step, which depend only on spp_dw[*] and the global feature, next to the top-down chain
+// (small, dependent launches that leave most of the HBM bandwidth idle).  Fork / join are cudaEventRecord /
+// cudaStreamWaitEvent pairs, which stream capture turns into graph edges.
+struct FwdSide {
+  cudaStream_t s = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t next = 0;
+  int init() {
+    if (s) return 0;
+    TD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    events.resize(256);
+    for (auto& e : events) TD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+  }
+  // everything enqueued on `from` so far happens before whatever is enqueued on `to` from now on
+  int order(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = events[next++ % events.size()];
+    TD_CUDA(cudaEventRecord(e, from));
+    TD_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+  }
+};
+static FwdSide g_fside[16];
+static thread_local FwdSide* t_fside = nullptr;  // set by forward() for the duration of the call
+
 static int gemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
   if (x.c->gemm_mode == TDANET_GEMM_FP32) return launch_gemm_simt(g, x.st);
   g.W_aux = x.at(aux_off);
@@ -247,7 +273,10 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       if (fused_live[k])
         if (int e = launch_inject_materialize(inj_src(k), inj_kind, B, C, x.at(p.fused[k]), 0, x.st)) return e;
   }
-  // statistics of the local branch of every top-down step (independent of the chain): one launch
+  // statistics of the local branch of every top-down step: independent of the chain below, so they run on the side
+  // stream - the coarse scales first (one launch; the first steps of the chain need them), then the finest scale,
+  // which is most of the bytes and is only needed by the last step.  Each la_combine waits for its own statistics.
+  cudaEvent_t local_ready[TDANET_MAX_DEPTH] = {};
   {
     DwArgs dl[TDANET_MAX_DEPTH];
     for (int i = 0; i < depth - 1; ++i) {
@@ -257,7 +286,20 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       dl[i].act_bf16 = x.bf();
     }
     Tag t("la_stats_local");
-    if (int e = launch_la_local_stats(dl, depth - 1, x.st)) return e;
+    FwdSide* fs = t_fside;
+    if (fs == nullptr || depth < 3) {
+      if (int e = launch_la_local_stats(dl, depth - 1, x.st)) return e;
+    } else {
+      if (int e = fs->order(x.st, fs->s)) return e;
+      if (int e = launch_la_local_stats(dl + 1, depth - 2, fs->s)) return e;  // scales 1 .. depth-2
+      cudaEvent_t ec = fs->events[fs->next++ % fs->events.size()];
+      TD_CUDA(cudaEventRecord(ec, fs->s));
+      for (int i = 1; i < depth - 1; ++i) local_ready[i] = ec;
+      if (int e = launch_la_local_stats(dl, 1, fs->s)) return e;              // scale 0
+      cudaEvent_t e0 = fs->events[fs->next++ % fs->events.size()];
+      TD_CUDA(cudaEventRecord(e0, fs->s));
+      local_ready[0] = e0;
+    }
   }
   // top-down fusion: last_layer[i](x_fused[i], i == depth-2 ? x_fused[i-1] : expanded)
   for (int i = depth - 2; i >= 0; --i) {
@@ -297,6 +339,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     l.out = x.at(p.expanded[i]); l.scale = nearest_scale(glo.L, loc.L);
     l.round_out = i == 0 && x.rnd() && !x.bf();  // expanded[0] only feeds res_conv
     l.act_bf16 = x.bf();
+    if (local_ready[i]) TD_CUDA(cudaStreamWaitEvent(x.st, local_ready[i], 0));  // st_la_l[i] (side stream)
     { Tag t(i == depth - 2 ? "la_combine_first" : "la_combine"); if (int e = launch_la_combine(l, x.st)) return e; }
   }
   // res_conv + residual (+ concat_block for the next iteration)
@@ -326,6 +369,15 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
   TD_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   Ctx x{c, w, &p, (char*)workspace, st};
   const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
+  {
+    int dev = 0;
+    TD_CUDA(cudaGetDevice(&dev));
+    t_fside = nullptr;
+    if (dev >= 0 && dev < 16) {
+      if (int e = g_fside[dev].init()) return e;
+      t_fside = &g_fside[dev];
+    }
+  }
 
   TD_CUDA(cudaMemsetAsync(x.ws + p.st_enc, 0, (size_t)B * 2 * sizeof(double), st));
   Tag tag("frontend");
