@@ -651,6 +651,15 @@ __device__ __forceinline__ void la_body(const LaArgs& a, int b, int ch, int t0, 
 #pragma unroll
     for (int i = 0; i < R; ++i) xr[4 + i] = sl.load_raw(t + 2 + i);
     const int jlo = sm.jc[t - t0];
+    // GC < 0: down-sampling by ~2 (the first top-down step): the 2R+4 global rows a chunk can touch are loaded up
+    // front, like the local rows; output row r then takes its window at offset 2r or 2r-1 (see launch_la_t)
+    vf<V> gr2[GC < 0 ? 2 * R + 4 : 1];
+    if constexpr (GC < 0) {
+#pragma unroll
+      for (int i = 0; i < 2 * R + 4; ++i) gr2[i] = sg.load_raw(jlo - 2 + i);
+#pragma unroll
+      for (int i = 0; i < 2 * R + 4; ++i) gr2[i] = sg.finalize(gr2[i], jlo - 2 + i);
+    }
     if constexpr (GC > 0) {
       // distinct centres of this chunk: jlo .. jc[last row]  (<= GC by construction)
       const int tl = (EDGE ? min(t + R, t1) : t + R) - 1;
@@ -680,12 +689,21 @@ __device__ __forceinline__ void la_body(const LaArgs& a, int b, int ch, int t0, 
         vf<V> cl = conv5<V>(wl, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
         vf<V> ga, ge;
         const int j = sm.jc[t + r - t0];
-        if constexpr (GC == 0) {
+        if constexpr (GC <= 0) {
           vf<V> g5[5];
+          if constexpr (GC < 0) {
+            const bool even = j - jlo == 2 * r;  // else 2r - 1
 #pragma unroll
-          for (int i = 0; i < 5; ++i) g5[i] = sg.load_raw(j - 2 + i);
+            for (int i = 0; i < 5; ++i) {
 #pragma unroll
-          for (int i = 0; i < 5; ++i) g5[i] = sg.finalize(g5[i], j - 2 + i);
+              for (int e = 0; e < V; ++e) g5[i][e] = (r == 0 || even) ? gr2[2 * r + i][e] : gr2[(r == 0 ? 1 : 2 * r) - 1 + i][e];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) g5[i] = sg.load_raw(j - 2 + i);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) g5[i] = sg.finalize(g5[i], j - 2 + i);
+          }
           ga = conv5<V>(wa, g5[0], g5[1], g5[2], g5[3], g5[4]);
           ge = conv5<V>(we, g5[0], g5[1], g5[2], g5[3], g5[4]);
 #pragma unroll
@@ -715,7 +733,7 @@ __device__ __forceinline__ void la_body(const LaArgs& a, int b, int ch, int t0, 
 }
 
 template <int LKIND, int GKIND, int V, int GC>
-__global__ void __launch_bounds__(256, GC == 0 ? 1 : 2) la_combine_kernel(LaArgs a, int rows_per_cta, int gspan) {
+__global__ void __launch_bounds__(256, GC <= 0 ? 1 : 2) la_combine_kernel(LaArgs a, int rows_per_cta, int gspan) {
   extern __shared__ __align__(16) float la_smem[];
   constexpr int R = 8;
   const int b = blockIdx.z;
@@ -737,7 +755,7 @@ __global__ void __launch_bounds__(256, GC == 0 ? 1 : 2) la_combine_kernel(LaArgs
     fill_nearest(sm.jg, gspan, g_first, Lg, a.glo.gscale, a.glo.Lg);
   __syncthreads();
   if (ch >= a.C) return;
-  const int g_last = nearest_src(t1 - 1, a.scale, Lg) + 2 + (GC > 0 ? GC : 0);
+  const int g_last = nearest_src(t1 - 1, a.scale, Lg) + 2 + (GC > 0 ? GC : (GC < 0 ? 2 : 0));
   const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % R == 0 && g_first >= 0 && g_last < Lg;
   if (interior) la_body<LKIND, GKIND, V, GC, false>(a, b, ch, t0, t1, sm, g_first);
   else la_body<LKIND, GKIND, V, GC, true>(a, b, ch, t0, t1, sm, g_first);
@@ -1220,6 +1238,8 @@ static int launch_la_t(const LaArgs& a, cudaStream_t st) {
   constexpr int V = 2;
   int threads = a.C / V;
   if (threads > 256) threads = 256;
+  // the down-sampling forms hold ~150 registers: CTAs of 128 threads fit three to an SM instead of one of 256
+  if (a.glo.L > a.loc.L && threads > 128) threads = 128;
   if (threads < 32) threads = 32;
   const int ctiles = cdiv(a.C / V, threads);
   int rows, tiles;
@@ -1228,7 +1248,11 @@ static int launch_la_t(const LaArgs& a, cudaStream_t st) {
   // rows of the global tensor one CTA can touch: its rows map to <= rows*scale + 1 centres, + halo
   const int gspan = (int)((double)rows * a.glo.L / a.loc.L) + 16;
   const size_t tabs = (size_t)(2 * rows + 4 + gspan) * sizeof(int);
-  if (a.glo.L > a.loc.L) {
+  if (a.glo.L > a.loc.L && a.scale >= 1.86f && a.scale <= 2.0f) {
+    // the first top-down step of every reference configuration (Lg = 2*Ll or 2*Ll - 1): with s = Lg/Ll in
+    // (2 - 1/7, 2], floor((t+r)*s) - floor(t*s) is 2r or 2r-1 for r < 8, so a chunk's windows sit at static offsets
+    TD_LAUNCH((la_combine_kernel<LKIND, GKIND, V, -2>), grid, threads, tabs, st, a, rows, gspan);
+  } else if (a.glo.L > a.loc.L) {
     TD_LAUNCH((la_combine_kernel<LKIND, GKIND, V, 0>), grid, threads, tabs, st, a, rows, gspan);
   } else if (7.0 * a.glo.L / a.loc.L <= 3.99) {
     // ratio >= ~2 (every up-sampling step of the U-Net): 8 output rows see at most 5 centres
