@@ -21,7 +21,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-Xptxas", "-v", "-DTDANET_BUILD",
-]
+] + os.environ.get("TDANET_NVCC_FLAGS", "").split()   # experiments, e.g. -DTD_PDL_EARLY=1
 
 
 def _sources():

@@ -12,6 +12,7 @@ namespace td {
 // out[b, j, c] = sum_k mean_{t in bin_k(j)} (x_k[b,t,c]*scale_k + shift_k)
 // bin_k(j) = [floor(j*L_k/Lb), ceil((j+1)*L_k/Lb))   (F.adaptive_avg_pool1d)
 __global__ void pool_sum_kernel(PoolArgs a) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int b = blockIdx.z, j = blockIdx.x;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -46,6 +47,7 @@ int launch_pool_sum(const PoolArgs& a, cudaStream_t st) {
 }
 
 __global__ void affine_sum_kernel(PoolArgs a) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int b = blockIdx.z, j = blockIdx.x;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -105,6 +107,7 @@ __device__ __forceinline__ void row_moments(const float* __restrict__ x, const f
 __global__ void ln_pe_kernel(const float* __restrict__ x, const float* __restrict__ w,
                              const float* __restrict__ bias, const float* __restrict__ pe,
                              float* __restrict__ y, int rows, int L, int C, int round_out) {
+  grid_dep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -141,6 +144,7 @@ __global__ void ln_residual_kernel(const float* __restrict__ a, const float* __r
                                    const float* __restrict__ bias, float* __restrict__ y, float k1,
                                    float k2, int rows, int C, const uint8_t* __restrict__ item_mask,
                                    float item_inv_keep, int L) {
+  grid_dep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -194,6 +198,7 @@ template <bool RES, bool STATS, bool DROP = false>
 __global__ void affine_kernel(const float* __restrict__ x, NormRef norm,
                               const float* __restrict__ resid, float* __restrict__ y,
                               float* __restrict__ chstats, int L, int C, int rows_per_cta, DropRef drop) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -283,6 +288,7 @@ __global__ void __launch_bounds__(64 * QL / QPT < 32 ? 32 : 64 * QL / QPT) atten
                                                                  float* __restrict__ ctx, int L, int C, int n,
                                                                  int group, int time_axis, int kchunk, int round_out,
                                                                  const uint8_t* __restrict__ amask, float inv_keep) {
+  grid_dep_wait();
   constexpr int NS = D / QL / 4;  // float4 segments per lane
   constexpr int DL = NS * 4;
   extern __shared__ float smem[];  // K [kchunk][D], V [kchunk][D]
@@ -462,6 +468,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restr
                                                             int L, int C, int n, int group, int time_axis,
                                                             int round_out, const uint8_t* __restrict__ amask,
                                                             float inv_keep) {
+  grid_dep_wait();
   constexpr int NK = 64, LD = D + 4, KT = D / 8, NT = NK / 8;
   extern __shared__ float smem[];
   float* Khi = smem;

@@ -153,6 +153,7 @@ template <int V>
 __global__ void gln_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, NormRef norm,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      double* __restrict__ S, int L, int C, int rows_per_thread) {
+  grid_dep_wait();
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const bool active = ch < C;
@@ -199,6 +200,7 @@ __global__ void gln_bwd_stats_kernel(const float* __restrict__ dy, const float* 
 template <int V>
 __global__ void gln_bwd_apply_kernel(GradSrc g, float* __restrict__ out, int accumulate, int L, int C,
                                      int rows_per_thread) {
+  grid_dep_wait();
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   if (ch >= C) return;
@@ -229,6 +231,7 @@ __global__ void gln_bwd_apply_kernel(GradSrc g, float* __restrict__ out, int acc
 
 // y = GlobLN(x) materialised (operand of a weight-gradient GEMM), any C
 __global__ void gln_fwd_apply_kernel(const float* __restrict__ x, NormRef norm, float* __restrict__ y, int L, int C) {
+  grid_dep_wait();
   const int b = blockIdx.z;
   float r, mur;
   norm_moments(norm, b, r, mur);
@@ -292,6 +295,7 @@ struct DwBwdArgs {
 // where the kernel is bound by latency at low occupancy rather than by bytes (rows are still read as whole sectors).
 template <int KS, int NW, int STRIDE, bool EXTRA, int V = 4>
 __global__ void dw_bwd_kernel(DwBwdArgs a) {
+  grid_dep_wait();
   // output rows per tile: 4, or 2 where the windows are wide (two convs, or stride 2 with its 2x input rows)
   constexpr int PAD = (KS - 1) / 2, R = (NW == 2 && KS == 5) || STRIDE == 2 ? 2 : 4;
   constexpr int GW = STRIDE == 1 ? R + 2 * PAD : R + 2;       // gradient rows held per tile
@@ -492,6 +496,7 @@ struct FoldArgs {
   size_t rep_stride;
 };
 __global__ void fold_replicas_kernel(FoldArgs a) {
+  grid_dep_wait();
   const FoldArgs::Entry& en = a.e[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < en.n; i += gridDim.x * blockDim.x) {
     float acc = 0.f;
@@ -539,6 +544,7 @@ __device__ __forceinline__ int first_local_row(int j, float scale, int Ll, int L
 //                             d_emb[j] = sum dout and adds them to the GlobLN_A / GlobLN_E sums
 template <int KS>
 __global__ void la_bwd_g_kernel(LaBwdArgs a, int rows_per_thread) {
+  grid_dep_wait();
   constexpr int V = 4, PAD = (KS - 1) / 2, R = 4, W = R + 2 * PAD;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -591,6 +597,7 @@ __global__ void la_bwd_g_kernel(LaBwdArgs a, int rows_per_thread) {
 
 template <int KS>
 __global__ void la_bwd_l_kernel(LaBwdArgs a) {
+  grid_dep_wait();
   constexpr int V = 4, PAD = (KS - 1) / 2, R = 4, W = R + 2 * PAD;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -726,6 +733,7 @@ __global__ void la_bwd_l_kernel(LaBwdArgs a) {
 // dg[j] (+)= sum_{t : nearest(t) = j} d x_fused[k][t].  A thread owns whole centres j.
 __global__ void inject_add_bwd_kernel(const float* __restrict__ dfused, float* __restrict__ dg, int accumulate, int Ll,
                                       int Lg, int C, float scale, int jchunk) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -760,6 +768,7 @@ __global__ void inject_add_bwd_kernel(const float* __restrict__ dfused, float* _
 //   dx[ti] (+)= sum_{to} w[c, ti + pad - to*s] * G[to]      (taps inside [0, ks))
 __global__ void dwg_bwd_data_kernel(const float* __restrict__ G, const float* __restrict__ w, float* __restrict__ dx,
                                     int accumulate, int Lin, int Lout, int C, int ks, int stride, int rows_per_thread) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -793,6 +802,7 @@ __global__ void dwg_bwd_data_kernel(const float* __restrict__ G, const float* __
 __global__ void dwg_bwd_weight_kernel(const float* __restrict__ G, SrcDesc xin, int xkind, float* __restrict__ dw,
                                       float* __restrict__ db, int B, int Lout, int C, int ks, int stride,
                                       int rows_per_cta) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int ch = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   const int tap = blockIdx.y;
@@ -832,6 +842,7 @@ __global__ void dwg_bwd_weight_kernel(const float* __restrict__ G, SrcDesc xin, 
 // ga_in[j] = sum_k mean_{t in bin_k(j)} n_k[t]   =>   dn_k[t] = sum_{j : t in bin_k(j)} g[j] / |bin_k(j)|
 __global__ void pool_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, int accumulate, int L, int Lb,
                                 int C, int rows_per_thread) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -878,6 +889,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ g, float* __restrict__
 // y = LN(k1*x)*w + b per row.  Row pass (one warp per row): rowstat[row] = {mu, rstd, mean(w*dy), mean(w*dy*xhat)}
 __global__ void ln_bwd_rows_kernel(const float* __restrict__ x, float k1, const float* __restrict__ w,
                                    const float* __restrict__ dy, float* __restrict__ rowstat, int rows, int C) {
+  grid_dep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -912,6 +924,7 @@ __global__ void ln_bwd_apply_kernel(const float* __restrict__ x, float k1, const
                                     const float* __restrict__ add, float kout, float* __restrict__ out,
                                     float* __restrict__ dw, float* __restrict__ db, int rows, int C,
                                     int rows_per_thread) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   if (ch >= C) return;
@@ -956,6 +969,7 @@ __global__ void mask_scale_kernel(const float* __restrict__ in, float* __restric
                                   const uint8_t* __restrict__ mask, float k0, float k1,
                                   const uint8_t* __restrict__ item_mask, float item_scale, size_t per_item,
                                   int round_out) {
+  grid_dep_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 v = *reinterpret_cast<const float4*>(in + i * 4);
@@ -995,6 +1009,7 @@ __global__ void att_bwd_dq_kernel(const float* __restrict__ qkv, const float* __
                                   float* __restrict__ P, float* __restrict__ dS, float* __restrict__ dqkv,
                                   int L, int C, int n, int n_head, int group, int time_axis, int total,
                                   const uint8_t* __restrict__ amask, float inv_keep) {
+  grid_dep_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int i = idx % n, head = (idx / n) % n_head, prob = idx / (n * n_head);
@@ -1057,6 +1072,7 @@ __global__ void att_bwd_dkv_kernel(const float* __restrict__ qkv, const float* _
                                    const float* __restrict__ P, const float* __restrict__ dS,
                                    float* __restrict__ dqkv, int L, int C, int n, int n_head, int group,
                                    int time_axis, int total) {
+  grid_dep_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int j = idx % n, head = (idx / n) % n_head, prob = idx / (n * n_head);
@@ -1095,6 +1111,7 @@ __global__ void att_bwd_warp_kernel(const float* __restrict__ qkv, const float* 
                                     float* __restrict__ dqkv, int L, int C, int n, int n_head, int group,
                                     int time_axis, int total_warps, const uint8_t* __restrict__ amask,
                                     float inv_keep) {
+  grid_dep_wait();
   constexpr int EPL = D >= 32 ? D / 32 : 1;  // head-dim elements per lane
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -1197,6 +1214,7 @@ constexpr int WG_T = 64, WG_R = 16;
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ G, const float* __restrict__ A,
                                                     float* __restrict__ dW, int R, int N, int K,
                                                     const float* __restrict__ a_slope, int rows_per_split) {
+  grid_dep_wait();
   __shared__ float Gs[WG_R][WG_T + 4];
   __shared__ float As[WG_R][WG_T + 4];
   const int tid = threadIdx.x;
@@ -1251,6 +1269,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ G,
 
 // db[n] += sum_r G[r, n]
 __global__ void colsum_kernel(const float* __restrict__ G, float* __restrict__ db, int R, int N, int rows_per_thread) {
+  grid_dep_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int r0 = blockIdx.y * rows_per_thread, r1 = min(r0 + rows_per_thread, R);
@@ -1265,6 +1284,7 @@ __global__ void colsum_kernel(const float* __restrict__ G, float* __restrict__ d
 __global__ void small_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ W, float* __restrict__ D,
                                    int R, int Kd, int N, const float* __restrict__ u,
                                    const float* __restrict__ slope, float* __restrict__ dslope) {
+  grid_dep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   double dsl = 0.0;
   if (idx < (size_t)R * N) {
@@ -1295,6 +1315,7 @@ __global__ void small_dgrad_kernel(const float* __restrict__ G, const float* __r
 
 // Wt[k, n] = W[n, k]
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int N, int K) {
+  grid_dep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)N * K) return;
   const int k = (int)(idx / N), n = (int)(idx % N);
@@ -1302,7 +1323,8 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
 }
 
 // dst = a + b
-__global__ void add_kernel(const float* a, const float* b, float* dst, size_t n) {  // dst may alias a or b
+__global__ void add_kernel(const float* a, const float* b, float* dst, size_t n) {
+  grid_dep_wait();  // dst may alias a or b
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = a[i] + b[i];
 }
@@ -1315,6 +1337,7 @@ __global__ void concat_bwd_kernel(const float* __restrict__ dout, const float* _
                                   float* __restrict__ dy, float* __restrict__ dmix, float* __restrict__ dcw,
                                   float* __restrict__ dcb, float* __restrict__ dslope, int rows, int c,
                                   int rows_per_thread) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   double dsl = 0.0;
@@ -1364,6 +1387,7 @@ __global__ void concat_bwd_kernel(const float* __restrict__ dout, const float* _
 // masked[r, s*Nb+n] = relu(m) * enc[r, n]:  d_m (in place over d_masked) and d_enc
 __global__ void mask_bwd_kernel(float* __restrict__ dmasked, const float* __restrict__ m,
                                 const float* __restrict__ enc, float* __restrict__ denc, int rows, int n_src, int Nb) {
+  grid_dep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)rows * Nb) return;
   const size_t r = idx / Nb;
@@ -1391,6 +1415,7 @@ __device__ __forceinline__ float framed_sig(const float* __restrict__ sig, int n
 __global__ void dec_bwd_data_naive_kernel(const float* __restrict__ dest, const float* __restrict__ w,
                                           float* __restrict__ dM, int B, int L0, int CI, int NO, int K, int S, int T,
                                           int shift) {
+  grid_dep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * L0 * CI) return;
   const int ci = (int)(idx % CI);
@@ -1409,6 +1434,7 @@ constexpr int DEC_FR = 32;  // frames per CTA
 __global__ void __launch_bounds__(256) dec_bwd_data_kernel(const float* __restrict__ dest, const float* __restrict__ w,
                                                            float* __restrict__ dM, int B, int L0, int CI, int NO, int K,
                                                            int S, int T, int shift, int wpad) {
+  grid_dep_wait();
   // shared: the signal window of DEC_FR frames for every output channel, and the weights [CI][NO*K (+pad)]
   __shared__ float sh[11264];
   const int span = (DEC_FR - 1) * S + K;
@@ -1439,7 +1465,8 @@ __global__ void __launch_bounds__(256) dec_bwd_data_kernel(const float* __restri
 //   decoder weight: M = masked, sig = d_est;   encoder weight: M = d_enc, sig = wav (NO = 1)
 __global__ void framed_wgrad_kernel(const float* __restrict__ M, const float* __restrict__ sig,
                                     float* __restrict__ dW, int B, int L0, int CI, int NO, int K, int S, int T,
-                                    int shift, int rows_per_split, int m_stride) {  // m_stride: row stride of M (>= CI)
+                                    int shift, int rows_per_split, int m_stride) {
+  grid_dep_wait();  // m_stride: row stride of M (>= CI)
   const int j = threadIdx.x;
   const int ci = blockIdx.x / NO, o = blockIdx.x % NO;
   if (j >= K) return;

@@ -20,6 +20,7 @@ __device__ __forceinline__ void moments(double s, double ss, double n, double& m
 }
 
 __global__ void __launch_bounds__(256) coef_inject_gate_kernel(InjectCoefArgs a, int C) {
+  grid_dep_wait();
   __shared__ double sh[64];
   const int b = blockIdx.x, k = blockIdx.y;
   const int Lk = a.L[k];
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) coef_inject_gate_kernel(InjectCoefArgs a,
 
 // wT[k, c] = w[c, k]: depthwise weights [C][ks] -> [ks][C], so that a thread's 4 channels of one tap are one vector load
 __global__ void weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wT, int C, int ks) {
+  grid_dep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * ks) return;
   const int k = i / C, c = i % C;

@@ -70,7 +70,7 @@ struct Tag {
 #define TD_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
   do {                                                                                   \
     if (td::g_profile) td::profile_mark(#kernel, (stream), true);                        \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+    td::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__); \
     if (td::g_profile) td::profile_mark(#kernel, (stream), false);                       \
     td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
     cudaError_t _e = cudaPeekAtLastError();                                              \
@@ -80,6 +80,42 @@ struct Tag {
 #endif
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch: every kernel of this library begins with grid_dep_wait() (griddepcontrol.wait: block
+// until the previous kernel of the stream has completed and its writes are visible) and is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled - launch latency, parameter and
+// constant setup - while the previous kernel drains instead of after it.  A forward is ~470 dependent launches and
+// a training step ~1650, most of them 10-50 us long.  TDANET_PDL=0 in the environment restores plain launches.
+#ifdef TD_EMU
+__device__ __forceinline__ void grid_dep_wait() {}
+#else
+#ifndef TD_PDL_EARLY
+#define TD_PDL_EARLY 0
+#endif
+__device__ __forceinline__ void grid_dep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if TD_PDL_EARLY
+  // let the next kernel's CTAs become resident as this kernel's CTAs retire (they park in their own wait)
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+extern bool g_pdl;
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through cudaPeekAtLastError
+}
+#endif
 
 // ----------------------------------------------------------------------------- device side
 constexpr float kEpsGLN = 1e-8f;

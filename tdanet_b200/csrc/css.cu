@@ -11,6 +11,7 @@ namespace td {
 // swap[s, k] = 1 if chunk k of stream s must be appended with its two sources exchanged
 __global__ void __launch_bounds__(256) css_score_kernel(const float* __restrict__ est, int n_chunks, int seg_len,
                                                         int overlap, int32_t* __restrict__ swap) {
+  grid_dep_wait();
   __shared__ double sh[64];
   const int s = blockIdx.y, k = blockIdx.x + 1;
   const float* first = est + ((size_t)s * n_chunks) * 2 * seg_len;
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) css_score_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) css_copy_kernel(const float* __restrict__ est, const int32_t* __restrict__ swap,
                                                        int n_chunks, int seg_len, int overlap, int out_len,
                                                        float* __restrict__ out) {
+  grid_dep_wait();
   const int s = blockIdx.z, c = blockIdx.y;
   const int hop = seg_len - overlap;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < out_len; n += gridDim.x * blockDim.x) {

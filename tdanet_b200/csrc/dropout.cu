@@ -34,6 +34,7 @@ struct MaskJob {
 // one thread per 16 mask bytes (4 Philox calls); blockIdx.y = UConvBlock iteration
 __global__ void __launch_bounds__(256) dropout_masks_kernel(char* __restrict__ base, size_t blk_stride, MaskJob job,
                                                             const uint64_t* __restrict__ rng_state) {
+  grid_dep_wait();
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= job.first_group[job.n]) return;
   int ri = 0;
@@ -60,7 +61,10 @@ __global__ void __launch_bounds__(256) dropout_masks_kernel(char* __restrict__ b
   }
 }
 
-__global__ void rng_advance_kernel(uint64_t* rng_state) { rng_state[1] += 1; }
+__global__ void rng_advance_kernel(uint64_t* rng_state) {
+  grid_dep_wait();
+  rng_state[1] += 1;
+}
 
 int launch_dropout_masks(char* base, size_t blk_stride, int n_blk, const MaskRegion* regions, int n_regions,
                          uint64_t* rng_state, cudaStream_t st) {

@@ -239,6 +239,7 @@ __device__ __forceinline__ void flush_item_stats(double* stats, int b, const flo
 
 template <int KIND, int V, int NW, int S, int R, bool WRITE, bool STATS>
 __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
+  grid_dep_wait();
   extern __shared__ int jtab[];  // inject kinds: nearest rows of the input rows this CTA touches
   __shared__ double red[64];
   const int b = blockIdx.z;
@@ -341,6 +342,7 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
 
 template <int KIND, int S>
 __global__ void __launch_bounds__(256) dw5_pool_kernel(DwArgs a, int bins_per_cta) {
+  grid_dep_wait();
   extern __shared__ int2 bins[];  // (lo, hi) of the tile's bins, plus one
   __shared__ double red[64];
   constexpr int V = 4, R = (S == 1) ? 8 : 4;
@@ -460,6 +462,7 @@ int launch_dw5(const DwArgs& a, cudaStream_t st) {
 // down-sampling access pattern would otherwise recompute every injected row five times)
 template <int KIND>
 __global__ void __launch_bounds__(256) inject_materialize_kernel(SrcDesc sd, int C, float* __restrict__ out, int rows_per_cta) {
+  grid_dep_wait();
   extern __shared__ int jtab[];
   constexpr int V = 4;
   const int b = blockIdx.z;
@@ -501,6 +504,7 @@ template <int KIND>
 __global__ void dw_generic_kernel(SrcDesc sd, int C, int Lout, int ks, int stride,
                                   const float* __restrict__ w, const float* __restrict__ bias,
                                   float* __restrict__ out, int round_out) {
+  grid_dep_wait();
   constexpr int V = 4;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -534,6 +538,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256) dw_strided_kernel(SrcDesc sd, int C, int Lout, int S,
                                                          const float* __restrict__ wT, const float* __restrict__ bias,
                                                          float* __restrict__ out, int round_out) {
+  grid_dep_wait();
   constexpr int V = 4, RO = 8;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -734,6 +739,7 @@ __device__ __forceinline__ void la_body(const LaArgs& a, int b, int ch, int t0, 
 
 template <int LKIND, int GKIND, int V, int GC>
 __global__ void __launch_bounds__(256, GC <= 0 ? 1 : 2) la_combine_kernel(LaArgs a, int rows_per_cta, int gspan) {
+  grid_dep_wait();
   extern __shared__ __align__(16) float la_smem[];
   constexpr int R = 8;
   const int b = blockIdx.z;
@@ -988,6 +994,7 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
 
 template <int LKIND, int CT>
 __global__ void __launch_bounds__(128, 2) la_stream_kernel(LaArgs a, int rows_per_cta) {
+  grid_dep_wait();
   extern __shared__ __align__(16) float la_smem[];
   constexpr int V = 4;
   const int b = blockIdx.z;
@@ -1154,6 +1161,7 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
 
 template <int LKIND, int CT>
 __global__ void __launch_bounds__(128, 3) la_local_stats_kernel(LocalStatsArgs p) {
+  grid_dep_wait();
   extern __shared__ __align__(16) float la_smem[];
   __shared__ double red[64];
   constexpr int V = 4;

@@ -21,6 +21,11 @@ int fail(int code, const char* fmt, ...) {
 
 size_t pit_scratch_floats(int B);
 
+bool g_pdl = [] {
+  const char* e = getenv("TDANET_PDL");
+  return !(e && e[0] == '0');
+}();
+
 // ----------------------------------------------------------------------------- event profiler
 bool g_profile = false;
 thread_local const char* g_tag = nullptr;

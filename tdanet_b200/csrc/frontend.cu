@@ -11,6 +11,7 @@ namespace td {
 // out[b, t, n] = sum_j w_k[n', j] * xp[t*S + j - ks_k/2], xp = zero-padded input of pad_input.
 // The padding is never materialised: xp[p] = wav[p - front_pad] inside [0, T), else 0.
 __global__ void __launch_bounds__(256) encoder_kernel(EncArgs a, int rows_per_cta, int ksmax) {
+  grid_dep_wait();
   extern __shared__ float sm[];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * rows_per_cta;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) bottleneck_kernel(const float* __restrict
                                                          const float* __restrict__ bias,
                                                          float* __restrict__ out, int L0, int Nb, int c,
                                                          int rows_per_cta) {
+  grid_dep_wait();
   extern __shared__ float sm[];
   float* wf = sm;                   // [c][Nb+1]  folded weights (+1: odd stride, no bank conflicts)
   float* bf = wf + c * (Nb + 1);    // [c]
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(256) bottleneck_reg_kernel(const float* __rest
                                                              const float* __restrict__ bias,
                                                              float* __restrict__ out, int L0, int Nb, int c,
                                                              int rows_per_cta) {
+  grid_dep_wait();
   extern __shared__ float sm[];  // [rows][NBR] encoder rows, zero-padded to NBR
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * rows_per_cta;
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ 
                                                       const float* __restrict__ w,
                                                       float* __restrict__ est, int L0, int CI, int K,
                                                       int S, int T, int hops_per_cta) {
+  grid_dep_wait();
   extern __shared__ float ms[];  // [hops_per_cta + 3][CI]
   const int b = blockIdx.z;
   const int h0 = blockIdx.x * hops_per_cta;  // first hop (n / S) of this CTA
@@ -276,6 +280,7 @@ int launch_decoder(const float* masked, const float* w, float* est, int B, int L
 __global__ void concat_kernel(const float* __restrict__ y, const float* __restrict__ mix,
                               const float* __restrict__ cw, const float* __restrict__ cb,
                               const float* __restrict__ slope, float* __restrict__ out, size_t n, int c) {
+  grid_dep_wait();
   const float sl = __ldg(slope);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % c);
@@ -292,6 +297,7 @@ int launch_concat(const float* y, const float* mix, const float* cw, const float
 
 __global__ void mask_apply_kernel(const float* __restrict__ m, const float* __restrict__ enc,
                                   float* __restrict__ masked, size_t n, int CI, int Nb) {
+  grid_dep_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / CI;
     const int col = (int)(i % CI);

@@ -10,6 +10,7 @@ namespace td {
 constexpr int BM = 128, BN = 128, BK = 16;
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a, int tiles_per_item) {
+  grid_dep_wait();
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Ws[2][BK][BN];
   __shared__ double red[64];

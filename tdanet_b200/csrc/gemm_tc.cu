@@ -182,6 +182,7 @@ template <int EPI, bool STATS, bool AB16, bool D16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ CUtensorMap mapW2, GemmArgs a, TcParams p) {
+  grid_dep_wait();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages] x { A 16 KB | W BN*128 B | (W_lo) } then barriers, then the epilogue patches
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -500,6 +501,7 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
 
 // ----------------------------------------------------------------------------- weight preparation
 __global__ void tf32_prepare_kernel(const float* __restrict__ w, float* __restrict__ aux, size_t n, int mode) {
+  grid_dep_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = w[i];
@@ -512,6 +514,7 @@ __global__ void tf32_prepare_kernel(const float* __restrict__ w, float* __restri
 }
 
 __global__ void bf16_prepare_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ aux, size_t n) {
+  grid_dep_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) aux[i] = __float2bfloat16_rn(w[i]);
 }

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(512) pit_item_kernel(const float* __restrict__
                                                        int sdr_type, float* __restrict__ pw_out,
                                                        int32_t* __restrict__ perm_out,
                                                        float* __restrict__ scratch) {
+  grid_dep_wait();
   constexpr int N = NS * NS + 2 * NS;
   __shared__ double sh[N * 32];
   const int b = blockIdx.x;
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(256) pit_finish_kernel(const float* __restrict
                                                          const float* __restrict__ tgt, int B, int T,
                                                          int threshold, const float* __restrict__ scratch,
                                                          float* __restrict__ loss, float* __restrict__ grad) {
+  grid_dep_wait();
   __shared__ double sh[64];
   // batch-level reduction, recomputed by every CTA (B is small)
   double kept_sum = 0.0, kept_cnt = 0.0, all_sum = 0.0;

@@ -9,6 +9,7 @@
 namespace td {
 
 __global__ void sqnorm_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {
+  grid_dep_wait();
   double acc = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = g[i];
@@ -28,6 +29,7 @@ struct AdamArgs {
 };
 
 __global__ void adam_kernel(AdamArgs a) {
+  grid_dep_wait();
   const int t = *a.step + 1;
   // clip_grad_norm_: coef = clamp(max_norm / (total_norm + 1e-6), max = 1)
   float coef = a.grad_scale;
@@ -49,7 +51,10 @@ __global__ void adam_kernel(AdamArgs a) {
   }
 }
 
-__global__ void step_inc_kernel(int32_t* step) { *step += 1; }
+__global__ void step_inc_kernel(int32_t* step) {
+  grid_dep_wait();
+  *step += 1;
+}
 
 }  // namespace td
 

@@ -23,6 +23,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 __global__ void __launch_bounds__(256) wgrad_mma_kernel(const float* __restrict__ G, const float* __restrict__ A,
                                                         float* __restrict__ dW, float* __restrict__ db, int R, int N,
                                                         int K, int rows_per_split) {
+  grid_dep_wait();
   __shared__ __align__(16) float Gs[2][WM_R][WM_S];
   __shared__ __align__(16) float As[2][WM_R][WM_S];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
