@@ -175,7 +175,7 @@ TDANET_API int tdanet_workspace_tensor(const tdanet_config_t* cfg, int batch, in
 TDANET_API int tdanet_latent_lengths(const tdanet_config_t* cfg, int n_samples, int32_t* lengths,
                           int32_t* padded_len, int32_t* rest);
 
-/* ------------------------------------------------------------------ training step (TDANetBest)
+/* ------------------------------------------------------------------ training step (every variant)
  * Replaces the autograd graph of AudioLightningModule.training_step (system/audio_litmodule.py:83-124) and
  * the Trainer's clip + optimiser (audio_train.py:71,187-197; configs/tdanet_lsr2.yml:42-45) for the model
  * path: forward keeping every GlobLN-delimited tensor of every UConvBlock iteration, hand-written backward,
