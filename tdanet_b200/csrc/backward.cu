@@ -169,6 +169,7 @@ static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
     }
   }
   TD_REQUIRE(a.stride == 1 || a.stride == 2, "dw_bwd: stride %d", a.stride);
+  TD_REQUIRE(!a.pool_g || (long)(a.Lin + 1) * (a.pool_Lb + 1) < (1L << 31), "dw_bwd: pooling %d -> %d overflows 32-bit bin arithmetic", a.Lin, a.pool_Lb);
   TD_REQUIRE(a.xkind == SRC_PLAIN || a.xkind == SRC_AFFINE || a.xkind == SRC_AFFINE_PRELU, "dw_bwd: source kind %d", a.xkind);
   TD_REQUIRE(a.xin.L == a.Lin, "dw_bwd: input length %d != %d", a.xin.L, a.Lin);
   const bool extra = a.xkind == SRC_AFFINE_PRELU || a.up_S || a.pool_g || a.dslope;
@@ -223,6 +224,7 @@ static int launch_la_bwd_a(LaBwdArgs& a, int ks, cudaStream_t st) {
 }
 
 static int launch_pool_bwd(const float* g, float* dx, int accumulate, int B, int L, int Lb, int C, cudaStream_t st) {
+  TD_REQUIRE((long)(L + 1) * (Lb + 1) < (1L << 31), "pool_bwd: pooling %d -> %d overflows 32-bit bin arithmetic", L, Lb);
   dim3 grid;
   int threads;
   const int rows = pick_rows(L, C / 4, B, 16);

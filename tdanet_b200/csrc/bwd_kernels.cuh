@@ -246,9 +246,11 @@ __global__ void gln_fwd_apply_kernel(const float* __restrict__ x, NormRef norm, 
 // weight of F.adaptive_avg_pool1d bin j = [floor(j*L/Lb), ceil((j+1)*L/Lb)) for input row t: 1/|bin| if t is in it
 __device__ __forceinline__ float pool_bin_weight(int j, int t, int L, int Lb) {
   if (j >= Lb) return 0.f;
-  const int lo = (int)(((long)j * L) / Lb);
-  const int hi = (int)((((long)j + 1) * L + Lb - 1) / Lb);
-  return (t >= lo && t < hi) ? 1.f / (float)(hi - lo) : 0.f;
+  // 32-bit arithmetic (the launchers require L * Lb < 2^31): a 64-bit division costs ~100 instructions, and this
+  // runs several times per row (it was most of the instructions of the spp_dw backward)
+  const unsigned lo = ((unsigned)j * (unsigned)L) / (unsigned)Lb;
+  const unsigned hi = (((unsigned)j + 1u) * (unsigned)L + (unsigned)Lb - 1u) / (unsigned)Lb;
+  return ((unsigned)t >= lo && (unsigned)t < hi) ? 1.f / (float)(hi - lo) : 0.f;
 }
 
 // ----------------------------------------------------------------------------- depthwise conv backward
@@ -371,7 +373,7 @@ __global__ void dw_bwd_kernel(DwBwdArgs a) {
 #pragma unroll
         for (int q = 0; q < R * STRIDE; ++q) {
           const int ti = min(t * STRIDE + q, Lin - 1);
-          const int jc = (int)(((long)ti * Lb) / Lin);
+          const int jc = (int)(((unsigned)ti * (unsigned)Lb) / (unsigned)Lin);
           const vf<V> g0 = vload<V>(gp + (size_t)jc * C), g1 = vload<V>(gp + (size_t)min(jc + 1, Lb - 1) * C);
           const float w0 = pool_bin_weight(jc, ti, Lin, Lb), w1 = pool_bin_weight(jc + 1, ti, Lin, Lb);
           if (!a.accumulate) O[q] = vzero<V>();
@@ -853,9 +855,9 @@ __global__ void pool_bwd_kernel(const float* __restrict__ g, float* __restrict__
   // only bins jc = floor(t*Lb/L) and jc + 1 can contain t (bins overlap by at most one row)
   auto bin_weight = [&](int j, int t) {
     if (j >= Lb) return 0.f;
-    const int lo = (int)(((long)j * L) / Lb);
-    const int hi = (int)((((long)j + 1) * L + Lb - 1) / Lb);
-    return (t >= lo && t < hi) ? 1.f / (float)(hi - lo) : 0.f;
+    const unsigned lo = ((unsigned)j * (unsigned)L) / (unsigned)Lb;
+    const unsigned hi = (((unsigned)j + 1u) * (unsigned)L + (unsigned)Lb - 1u) / (unsigned)Lb;
+    return ((unsigned)t >= lo && (unsigned)t < hi) ? 1.f / (float)(hi - lo) : 0.f;
   };
   for (int t = t0; t < t1; t += 4) {
     vf<V> g0[4], g1[4], o[4];
@@ -863,7 +865,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ g, float* __restrict__
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // unconditional, clamped loads
       const int tt = t + i < L ? t + i : L - 1;
-      const int jc = (int)(((long)tt * Lb) / L);
+      const int jc = (int)(((unsigned)tt * (unsigned)Lb) / (unsigned)L);
       w0[i] = bin_weight(jc, tt);
       w1[i] = bin_weight(jc + 1, tt);
       g0[i] = vload<V>(gp + (size_t)jc * C);
