@@ -250,7 +250,13 @@ static int launch_att_bwd_d(const float* qkv, const float* dctx, float* P, float
                             int n_head, int group, int time_axis, const uint8_t* amask, float inv_keep, cudaStream_t st) {
   const int n = time_axis ? L : group;
   const int nprob = time_axis ? B : (B / group) * L;
+#ifdef TD_EMU
+  // the warp kernel runs as OS threads with barriers under emulation (seconds per launch): only when asked for
+  static const bool emu_warp = getenv("TD_EMU_WARP_ATT") != nullptr;
+  if (n <= 16 && emu_warp) {
+#else
   if (n <= 16) {
+#endif
     const int warps = nprob * n_head;
     if (n <= 8) TD_LAUNCH_COOP((att_bwd_warp_kernel<D, 8>), cdiv(warps, 4), 128, 0, st, qkv, dctx, dqkv, L, C, n, n_head, group, time_axis, warps, amask, inv_keep);
     else TD_LAUNCH_COOP((att_bwd_warp_kernel<D, 16>), cdiv(warps, 4), 128, 0, st, qkv, dctx, dqkv, L, C, n, n_head, group, time_axis, warps, amask, inv_keep);

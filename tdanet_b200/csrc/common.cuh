@@ -50,17 +50,20 @@ struct Tag {
 #ifdef TD_EMU
 #define TD_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
   do {                                                                                   \
+    emu::Timer _t(#kernel);                                                              \
     emu::launch(dim3(grid), dim3(block), false, [&]() { kernel(__VA_ARGS__); });        \
     td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
   } while (0)
 #define TD_LAUNCH_COOP(kernel, grid, block, smem, stream, ...)                           \
   do {                                                                                   \
+    emu::Timer _t(#kernel);                                                              \
     emu::launch(dim3(grid), dim3(block), true, [&]() { kernel(__VA_ARGS__); });         \
     td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
   } while (0)
 // kernels whose only intra-block communication is a final block reduction (sequential unless TD_EMU_COOP is set)
 #define TD_LAUNCH_RED(kernel, grid, block, smem, stream, ...)                            \
   do {                                                                                   \
+    emu::Timer _t(#kernel);                                                              \
     emu::launch(dim3(grid), dim3(block), emu::coop_reductions, [&]() { kernel(__VA_ARGS__); }); \
     td::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
   } while (0)

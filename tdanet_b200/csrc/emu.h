@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <functional>
 #include <memory>
 #include <thread>
@@ -83,6 +84,18 @@ static inline T shfl_xor(T v, int o) {
   bs->warp_bar->arrive_and_wait();
   return r;
 }
+
+// TD_EMU_TIMING=1: per-launch wall time on stderr (which emulated kernel a slow test spends its time in)
+struct Timer {
+  const char* name;
+  double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+  explicit Timer(const char* n) : name(n), t0(now()) {}
+  ~Timer() {
+    static const bool on = getenv("TD_EMU_TIMING") != nullptr;
+    if (on) { const double dt = now() - t0; if (dt > 0.05) fprintf(stderr, "emu %8.3f s  %s\n", dt, name); }
+  }
+};
 
 template <class F>
 static void launch(dim3 grid, dim3 block, bool coop, F f) {

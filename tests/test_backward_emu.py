@@ -46,11 +46,12 @@ CASES = {
 }
 
 
+# (lengths kept short: the emulation runs the warp-shuffle kernels - attention backward, LayerNorm rows - as real OS
+# threads with barriers, which is what the time of this file goes into; the GPU tests repeat every case at 2x the length)
 @pytest.mark.parametrize("variant,name,B,T", [
-    ("best", "depth4", 2, 1203), ("best", "depth5_odd", 3, 1111), ("best", "depth2_3src", 2, 800), ("best", "depth3", 1, 997),
-    ("fork", "depth4", 2, 1203), ("fork", "depth5_odd", 2, 1111), ("fork", "depth2_3src", 2, 800),
-    ("origin", "depth4", 2, 1203), ("origin", "depth3", 1, 997),
-    ("multres", "multres4", 2, 1203), ("multres", "multres2", 3, 1111)])
+    ("best", "depth4", 2, 643), ("best", "depth5_odd", 3, 587), ("best", "depth2_3src", 2, 331), ("best", "depth3", 1, 517),
+    ("fork", "depth4", 2, 643), ("fork", "depth5_odd", 2, 587), ("fork", "depth2_3src", 2, 331),
+    ("origin", "depth4", 2, 643), ("multres", "multres4", 2, 643), ("multres", "multres2", 3, 587)])
 def test_emulated_backward_matches_autograd(variant, name, B, T):
     kw = CASES[name]
     sd = _model_sd(kw, variant=variant)
@@ -77,9 +78,9 @@ def test_emulated_backward_matches_autograd(variant, name, B, T):
 
 
 @pytest.mark.parametrize("variant,name,B,T,dropout,drop_path", [
-    ("best", "depth4", 3, 1203, 0.1, 0.1), ("best", "depth3", 2, 997, 0.3, 0.0), ("best", "depth4", 4, 1203, 0.0, 0.4),
-    ("fork", "depth4", 3, 1203, 0.2, 0.3), ("origin", "depth4", 2, 1203, 0.1, 0.1),
-    ("multres", "multres4", 2, 1203, 0.2, 0.3), ("multres", "multres2", 3, 1111, 0.1, 0.0)])
+    ("best", "depth4", 3, 643, 0.1, 0.1), ("best", "depth3", 2, 517, 0.3, 0.0), ("best", "depth4", 4, 643, 0.0, 0.4),
+    ("fork", "depth4", 3, 643, 0.2, 0.3), ("origin", "depth4", 2, 643, 0.1, 0.1),
+    ("multres", "multres4", 2, 643, 0.2, 0.3), ("multres", "multres2", 3, 587, 0.1, 0.0)])
 def test_emulated_backward_with_dropout_masks(variant, name, B, T, dropout, drop_path):
     """Train-mode stochastic layers: with the SAME keep-masks in the workspace and in the oracle,
     the emulated backward pass matches autograd of the oracle through nn.Dropout / attention-weight dropout / DropPath."""
@@ -112,3 +113,23 @@ def test_emulated_backward_with_dropout_masks(variant, name, B, T, dropout, drop
         worst = max(worst, rel)
         assert rel < 2e-4, f"{k}: max-rel {rel:.3e} (|ref|max {scale:.3e})"
     print(f"{variant}/{name} dropout {dropout} drop_path {drop_path}: worst max-rel gradient error {worst:.2e}")
+
+
+def test_emulated_warp_attention_backward(monkeypatch):
+    """The one-warp-per-problem attention backward (n <= 16 tokens; what the training batches use on the GPU) under
+    emulation: real OS threads with barriers, so it gets one small case of its own (the other cases emulate the
+    scratch-buffer kernels, which the GPU takes for n > 16)."""
+    import subprocess, sys, os
+    code = ("import sys, torch; sys.path.insert(0, 'tests'); import emu_harness as H;"
+            "from test_backward_emu import _model_sd, _autograd, CASES, SR;"
+            "kw = CASES['depth4']; sd = _model_sd(kw); g = torch.Generator().manual_seed(3);"
+            "wav = torch.randn(3, 1, 331, generator=g) * 0.1; d = torch.randn(3, 2, 331, generator=g);"
+            "masks = H.random_drop_masks(3, H.make_engine(kw, SR).latent_lengths(331)[0][-1], kw['in_channels'], 8, kw['num_blocks'], 0.2, 0.0);"
+            "grads, _, _ = H.emu_backward(sd, wav, d, kw, SR, 'best', 0.2, 0.0, masks);"
+            "ref = _autograd(sd, wav, d, kw, 'best', drop_masks=masks, dropout=0.2, drop_path=0.0);"
+            "worst = max((grads[k].double() - r).abs().max().item() / max(r.abs().max().item(), 1e-12) for k, r in ref.items() if r is not None);"
+            "print('worst', worst); assert worst < 2e-4")
+    env = dict(os.environ, TD_EMU_WARP_ATT="1")   # read once per process by the emulation library: fresh interpreter
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout + r.stderr
