@@ -126,6 +126,35 @@ static inline int pick_rows(int L, int C4, int B, int max_rows) {
   return rows;
 }
 
+// CTAs of `kernel` that can be resident on the device at once (occupancy x SM count); cached per (kernel, block size)
+static long resident_ctas(const void* kernel, int threads) {
+#ifdef TD_EMU
+  (void)kernel; (void)threads;
+  return 1L << 30;
+#else
+  static std::vector<std::pair<std::pair<const void*, int>, long>> cache;
+  for (auto& e : cache)
+    if (e.first.first == kernel && e.first.second == threads) return e.second;
+  int per_sm = 0, dev = 0, sms = 148;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cache.push_back({{kernel, threads}, (long)per_sm * sms});
+  return cache.back().second;
+#endif
+}
+// Rows per thread for the register-heavy streaming backward kernels (2-3 CTAs of 128 threads per SM): `rows` unless
+// the grid would be between one and two waves of resident CTAs - at the training batch of 8 it is 504 CTAs for 296 or
+// 444 slots, and the second, mostly empty wave costs as much as the first.  Then the rows are stretched (to a
+// multiple of `tile`) so that one wave covers the tensor.
+static int fit_wave(int rows, int tile, int L, int ctiles, int B, long slots) {
+  const long ctas = (long)cdiv(L, rows) * ctiles * B;
+  if (ctas <= slots || ctas >= 2 * slots) return rows;
+  const long chunks = slots / ((long)ctiles * B);
+  if (chunks < 1) return rows;
+  return cdiv(cdiv(L, (int)chunks), tile) * tile;
+}
+
 static int launch_gln_bwd_stats(const float* dy, const float* x, const NormRef& norm, float* dgamma, float* dbeta,
                                 double* S, int B, int L, int C, cudaStream_t st) {
   dim3 grid;
@@ -194,13 +223,18 @@ static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
     else return fail(TDANET_EINVAL, "dw_bwd: ks=%d nw=%d", ks, nw);
     return 0;
   }
-  if (key == 511 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, false>), grid, threads, 0, st, a);
-  else if (key == 511) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, true>), grid, threads, 0, st, a);
-  else if (key == 512) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 2, true>), grid, threads, 0, st, a);
-  else if (key == 521 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 2, 1, false>), grid, threads, 0, st, a);
-  else if (key == 111 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<1, 1, 1, false>), grid, threads, 0, st, a);
-  else if (key == 121 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<1, 2, 1, false>), grid, threads, 0, st, a);
+  void (*kfn)(DwBwdArgs) = nullptr;
+  int tile = 4;  // output rows per tile of the variant (bwd_kernels.cuh: R)
+  if (key == 511 && !extra) kfn = dw_bwd_kernel<5, 1, 1, false>;
+  else if (key == 511) kfn = dw_bwd_kernel<5, 1, 1, true>;
+  else if (key == 512) { kfn = dw_bwd_kernel<5, 1, 2, true>; tile = 2; }
+  else if (key == 521 && !extra) { kfn = dw_bwd_kernel<5, 2, 1, false>; tile = 2; }
+  else if (key == 111 && !extra) kfn = dw_bwd_kernel<1, 1, 1, false>;
+  else if (key == 121 && !extra) kfn = dw_bwd_kernel<1, 2, 1, false>;
   else return fail(TDANET_EINVAL, "dw_bwd: ks=%d nw=%d", ks, nw);
+  a.rows_per_thread = fit_wave(a.rows_per_thread, tile, a.Lout, grid.y, a.B, resident_ctas((const void*)kfn, threads));
+  row_grid(a.Lout, a.C / 4, a.B, a.rows_per_thread, grid, threads);
+  TD_LAUNCH_RED(kfn, grid, threads, 0, st, a);
   return 0;
 }
 
@@ -213,13 +247,14 @@ static int launch_la_bwd_a(LaBwdArgs& a, int ks, cudaStream_t st) {
   row_grid(a.Lg, a.C / 4, a.B, grows, grid, threads);
   if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5>), grid, threads, 0, st, a, grows);
   else TD_LAUNCH((la_bwd_g_kernel<1>), grid, threads, 0, st, a, grows);
-  // L pass: chunks of centres covering about 32 local rows per thread
+  // L pass: chunks of centres covering about 32 local rows per thread (one wave of CTAs where that is close, fit_wave)
   int jc = (int)((double)pick_rows(a.loc.L, a.C / 4, a.B, 32) * a.Lg / a.loc.L + 0.5);
   a.jchunk = jc < 1 ? 1 : jc;
+  void (*lfn)(LaBwdArgs) = ks == 5 ? la_bwd_l_kernel<5> : la_bwd_l_kernel<1>;
+  a.jchunk = fit_wave(a.jchunk, 1, a.Lg, cdiv(a.C / 4, threads), a.B, resident_ctas((const void*)lfn, threads));
   dim3 lgrid;
   row_grid(a.Lg, a.C / 4, a.B, a.jchunk, lgrid, threads);
-  if (ks == 5) TD_LAUNCH_RED((la_bwd_l_kernel<5>), lgrid, threads, 0, st, a);
-  else TD_LAUNCH_RED((la_bwd_l_kernel<1>), lgrid, threads, 0, st, a);
+  TD_LAUNCH_RED(lfn, lgrid, threads, 0, st, a);
   return 0;
 }
 
