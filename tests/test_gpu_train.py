@@ -528,3 +528,53 @@ def test_eval_mode_ignores_dropout_and_graph_replays_draw_fresh_masks():
     assert int(rng[1].item()) == off0 + 3
     assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
     assert len({round(v, 6) for v in losses}) == 3, losses     # lr = 0: only the masks differ between the replays
+
+
+def test_train_mode_masks_with_attention_groups():
+    """attn_group = 3 inside a batch of 6 (two reference batches in one launch) in train mode: the attention-weight
+    masks are laid out per (group, time index) problem, DropPath per item; equals the oracle run on each group alone
+    with its slice of the masks."""
+    kw = CASES["depth4"]
+    sd = _model_sd(kw)
+    m = _model(kw, sd).train()
+    m.dropout, m.drop_path = 0.2, 0.2
+    m.gemm_mode = "fp32"
+    m.attn_group = 3
+    B, T, G = 6, 1203, 3
+    wav, d_est = _inputs(kw, B, T)
+    est = m(wav.to(DEV))
+    (est * d_est.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    m.engine.cfg.attn_group = 3          # the workspace names are resolved against the config of the call
+    masks = _oracle_masks(_read_masks(m, B, T, kw["num_blocks"]))
+    Lb = masks[0]["ao"].shape[1]
+    ref_est, ref_grads = [], None
+    for gi in range(B // G):
+        sl = slice(gi * G, (gi + 1) * G)
+        sub = [{"att": mm["att"][gi * Lb * 8:(gi + 1) * Lb * 8], "ao": mm["ao"][sl], "f1": mm["f1"][sl], "f2": mm["f2"][sl],
+                "dp": mm["dp"][:, sl]} for mm in masks]
+        drop = dict(drop_masks=sub, dropout=0.2, drop_path=0.2)
+        with torch.no_grad():
+            ref_est.append(O.forward(sd, wav[sl], O.OracleConfig(sample_rate=SR, **kw, **drop)))
+        g = _autograd(sd, wav[sl], d_est[sl], kw, "best", **drop)
+        ref_grads = g if ref_grads is None else {k: (None if v is None else v + g[k]) for k, v in ref_grads.items()}
+    ref_est = torch.cat(ref_est)
+    err = (est.detach().cpu() - ref_est).abs().max().item() / ref_est.abs().max().item()
+    wmax, wl2, all_l2 = _grad_errors([(k, p.grad) for k, p in m.named_parameters()], ref_grads)
+    print(f"attn_group 3 of 6 with masks: est max-rel {err:.2e}, grad worst max-rel {wmax:.2e}, whole rel-L2 {all_l2:.2e}")
+    assert err < 3e-5 and wmax < 2e-4 and all_l2 < 1e-4
+
+
+def test_multres_training_step_reduces_loss():
+    """TDANetMultRes (configs/tdanet_debug.yml's class) through the fused step: time-axis attention backward,
+    multi-resolution encoder gradients, train-mode masks on; the loss on a fixed batch goes down."""
+    kw = CASES["multres4"]
+    m = _model(kw, _model_sd(kw, variant="multres"), variant="multres").train()
+    m.dropout = m.drop_path = 0.1
+    L = look2hear.losses
+    ts = look2hear.system.TrainingStep(m, L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True), lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    tgt = (torch.randn(4, 2, 2000, generator=g) * 0.1).to(DEV)
+    mix = tgt.sum(1)
+    losses = [ts.step_captured(mix, tgt).item() for _ in range(30)]
+    assert losses[-1] < losses[0] - 0.5, losses
