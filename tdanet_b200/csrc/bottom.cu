@@ -610,10 +610,12 @@ static int launch_attention_mma(const float* qkv, float* ctx, int B, int L, int 
   const int n = time_axis ? L : group;
   const int nprob = time_axis ? B : (B / group) * L;
   const size_t smem = (size_t)4 * 64 * (D + 4) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[16] = {};  // the opt-in to > 48 KB of dynamic shared memory is per device
+  int dev = 0;
+  TD_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16 || !attr_set[dev]) {
     TD_CUDA(cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    if (dev >= 0 && dev < 16) attr_set[dev] = true;
   }
   dim3 grid(nprob, n_head);
   TD_LAUNCH((attention_mma_kernel<D>), grid, 128, smem, st, qkv, ctx, L, C, n, group, time_axis, round_out, amask, inv_keep);
