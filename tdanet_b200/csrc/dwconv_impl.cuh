@@ -371,6 +371,13 @@ __global__ void __launch_bounds__(256) dw5_pool_kernel(DwArgs a, int bins_per_ct
 static void pick_tiling(int B, int L, int ctiles, int R, int* rows_per_cta, int* tiles, long target = 148L * 16,
                         int cap = 64) {
   // aim at `target` CTAs in total, at most `cap` rows per CTA, whole chunks of R rows
+  // (tuning aid: TDANET_TILE_TARGET / TDANET_TILE_CAP override the defaults of the dw5 / dw5_pool launchers)
+  if (target == 148L * 16 && cap == 64) {
+    static const long env_target = getenv("TDANET_TILE_TARGET") ? atol(getenv("TDANET_TILE_TARGET")) : 0;
+    static const int env_cap = getenv("TDANET_TILE_CAP") ? atoi(getenv("TDANET_TILE_CAP")) : 0;
+    if (env_target > 0) target = env_target;
+    if (env_cap > 0) cap = env_cap;
+  }
   long per = ((long)B * L * ctiles + target - 1) / target;
   per = (per + R - 1) / R * R;
   if (per < R) per = R;

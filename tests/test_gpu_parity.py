@@ -335,6 +335,29 @@ def test_attention_over_larger_batches(variant, C, B, group, mode, tol):
     assert max_rel(y, ref) < tol, max_rel(y, ref)
 
 
+def test_pipelined_separation_equals_sequential_calls():
+    """look2hear.system.separate_pipelined: host batches in, host results out, copies overlapped with the forward;
+    bit-identical to model(batch) per batch (graph replay and plain launches), slots of host_outputs reused safely."""
+    import tdanet_b200.look2hear.system as S
+    kw = dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=4, enc_kernel_size=2, num_sources=2)
+    torch.manual_seed(5)
+    m = M.TDANetBest(sample_rate=16000, **kw).eval().to(DEV)
+    g = torch.Generator().manual_seed(6)
+    batches = [(torch.randn(3, 1, 4000, generator=g) * 0.1).pin_memory() for _ in range(5)]
+    for graph in (False, True):
+        m.use_cuda_graph = graph
+        with torch.no_grad():
+            want = [m(b.to(DEV)).cpu() for b in batches]
+        got = S.separate_pipelined(m, batches)
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+        outs = [torch.empty(3, 2, 4000).pin_memory() for _ in range(2)]
+        got2 = S.separate_pipelined(m, batches[:2], outs)
+        assert torch.equal(got2[0], want[0]) and torch.equal(got2[1], want[1]) and got2[0] is outs[0]
+    m.use_cuda_graph = False
+    with pytest.raises(Exception, match="host"):
+        S.separate_pipelined(m, [batches[0].to(DEV)])
+
+
 def test_three_sources():
     kw = dict(out_channels=16, in_channels=32, num_blocks=1, upsampling_depth=4, enc_kernel_size=2, num_sources=3)
     torch.manual_seed(2)
