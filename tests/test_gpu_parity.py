@@ -337,11 +337,12 @@ def test_attention_over_larger_batches(variant, C, B, group, mode, tol):
 
 def test_pipelined_separation_equals_sequential_calls():
     """look2hear.system.separate_pipelined: host batches in, host results out, copies overlapped with the forward;
-    bit-identical to model(batch) per batch (graph replay and plain launches), slots of host_outputs reused safely."""
+    the same results as model(batch) per batch (graph replay and plain launches), slots of host_outputs reused safely."""
     import tdanet_b200.look2hear.system as S
     kw = dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=4, enc_kernel_size=2, num_sources=2)
     torch.manual_seed(5)
     m = M.TDANetBest(sample_rate=16000, **kw).eval().to(DEV)
+    m.gemm_mode = "fp32"     # (with TF32 operands the run-to-run rounding of the sums is amplified to ~1e-4)
     g = torch.Generator().manual_seed(6)
     batches = [(torch.randn(3, 1, 4000, generator=g) * 0.1).pin_memory() for _ in range(5)]
     for graph in (False, True):
@@ -349,10 +350,15 @@ def test_pipelined_separation_equals_sequential_calls():
         with torch.no_grad():
             want = [m(b.to(DEV)).cpu() for b in batches]
         got = S.separate_pipelined(m, batches)
-        assert all(torch.equal(a, b) for a, b in zip(got, want))
+        # (not bit-equal: the GlobLN sums are accumulated with atomics, whose order varies from run to run)
+        errs = [max_rel(a, b) for a, b in zip(got, want)]
+        with torch.no_grad():
+            again = [max_rel(m(b.to(DEV)).cpu(), w) for b, w in zip(batches, want)]   # run-to-run noise of the same call
+        assert max(errs) < 5e-6, (errs, again)
         outs = [torch.empty(3, 2, 4000).pin_memory() for _ in range(2)]
-        got2 = S.separate_pipelined(m, batches[:2], outs)
-        assert torch.equal(got2[0], want[0]) and torch.equal(got2[1], want[1]) and got2[0] is outs[0]
+        got2 = S.separate_pipelined(m, batches[:4], outs)          # slots reused: 0, 1, 0, 1
+        assert got2[0] is outs[0] and got2[2] is outs[0] and got2[3] is outs[1]
+        assert max_rel(got2[2], want[2]) < 5e-6 and max_rel(got2[3], want[3]) < 5e-6
     m.use_cuda_graph = False
     with pytest.raises(Exception, match="host"):
         S.separate_pipelined(m, [batches[0].to(DEV)])
