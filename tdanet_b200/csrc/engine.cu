@@ -441,6 +441,8 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
     g.D = x.at(p.mlogit); g.epi = EPI_BIAS;
     if (int e = launch_gemm_simt(g, st)) return e;
     if (int e = launch_mask_apply(x.at(p.mlogit), x.at(p.enc), x.at(p.masked), B * L0, c->num_sources, Nb, st)) return e;
+  } else if (c->gemm_mode == TDANET_GEMM_TF32 && mask_conv_mma_applies(cc, g.N)) {
+    if (int e = launch_mask_conv_mma(g.A, g.W, g.bias, g.a_slope, g.enc, g.D, B * L0, cc, g.N, Nb, st)) return e;
   } else if (int e = launch_gemm_simt(g, st)) return e;
   return launch_decoder(x.at(p.masked), w->dec_w, est, B, L0, Nb, c->num_sources, K, S, T, st);
 }

@@ -193,6 +193,119 @@ int launch_bottleneck(const float* enc, const NormRef& norm, const float* w, con
   return 0;
 }
 
+// ----------------------------------------------------------------------------- mask_net on the tensor cores
+// masked[r, n] = relu(sum_k prelu(y[r, k]) * W[n, k] + bias[n]) * enc[r, n mod Nb]     (TDANet_best.py:505-509)
+// y [R, K] (K = out_channels), W [N, K] with N = n_src * Nb (66 for the 4 ms encoder: not a tile multiple, which
+// left the CUDA-core GEMM at 9 TFLOP/s, 232 us per forward at B = 64 against ~20 us of HBM time).  TF32 modes only:
+// warp-level mma.sync.m16n8k8, one CTA = four warps x 16 rows per tile of 64 rows, W staged once per CTA
+// (TF32-rounded, rows padded to K + 4 floats), the A tile staged through shared memory with the PReLU applied,
+// NT = ceil(N / 8) accumulator tiles per warp.
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128) mask_conv_mma_kernel(const float* __restrict__ y, const float* __restrict__ w,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ slope_p,
+                                                            const float* __restrict__ enc, float* __restrict__ out,
+                                                            int R, int K, int N, int Nb, int n_tiles) {
+  grid_dep_wait();
+  extern __shared__ float sm[];
+  const int LD = K + 4;
+  float* Ws = sm;                 // [NT*8][LD]
+  float* As = sm + NT * 8 * LD;   // [64][LD]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int K4 = K / 4;
+  for (int i = tid; i < NT * 8 * K4; i += 128) {
+    const int n = i / K4, k = (i % K4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) v = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * K + k));
+    *reinterpret_cast<float4*>(Ws + n * LD + k) = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+  }
+  const float slope = __ldg(slope_p);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int r0 = tile * 64;
+    __syncthreads();  // the previous tile's fragments have been read (first pass: orders the W stores as well)
+    for (int i = tid; i < 64 * K4; i += 128) {
+      const int rr = i / K4, k = (i % K4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + rr < R) v = *reinterpret_cast<const float4*>(y + (size_t)(r0 + rr) * K + k);
+      v.x = tf32_rna(preluf_(v.x, slope)); v.y = tf32_rna(preluf_(v.y, slope));
+      v.z = tf32_rna(preluf_(v.z, slope)); v.w = tf32_rna(preluf_(v.w, slope));
+      *reinterpret_cast<float4*>(As + rr * LD + k) = v;
+    }
+    __syncthreads();
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    const uint32_t* ar = reinterpret_cast<const uint32_t*>(As) + (warp * 16 + g) * LD + t;
+    const uint32_t* wr = reinterpret_cast<const uint32_t*>(Ws) + g * LD + t;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t a[4] = {ar[k0], ar[8 * LD + k0], ar[k0 + 4], ar[8 * LD + k0 + 4]};
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_tf32_m16n8k8(acc[nt], a, wr[nt * 8 * LD + k0], wr[nt * 8 * LD + k0 + 4]);
+    }
+    // epilogue: rows r0 + 16*warp + g (+8), columns 8*nt + 2t, +1
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = r0 + warp * 16 + g + 8 * h;
+      if (r < R) {
+        const float* er = enc + (size_t)r * Nb;
+        float* orow = out + (size_t)r * N;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int c = nt * 8 + 2 * t;
+          if (c < N) {
+            const float v0 = fmaxf(acc[nt][2 * h] + __ldg(bias + c), 0.f) * er[c % Nb];
+            if (c + 1 < N) {
+              const float v1 = fmaxf(acc[nt][2 * h + 1] + __ldg(bias + c + 1), 0.f) * er[(c + 1) % Nb];
+              *reinterpret_cast<float2*>(orow + c) = make_float2(v0, v1);
+            } else {
+              orow[c] = v0;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NT>
+static int launch_mask_conv_mma_t(const float* y, const float* w, const float* bias, const float* slope, const float* enc,
+                                  float* out, int R, int K, int N, int Nb, cudaStream_t st) {
+  const size_t smem = (size_t)(NT * 8 + 64) * (K + 4) * sizeof(float);
+  static bool attr_set[16] = {};
+  int dev = 0;
+  TD_CUDA(cudaGetDevice(&dev));
+  if (smem > 48 * 1024 && (dev < 0 || dev >= 16 || !attr_set[dev])) {
+    TD_CUDA(cudaFuncSetAttribute(mask_conv_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 16) attr_set[dev] = true;
+  }
+  const int tiles = cdiv(R, 64);
+  const int grid = tiles < 148 * 3 ? tiles : 148 * 3;
+  TD_LAUNCH((mask_conv_mma_kernel<NT>), grid, 128, smem, st, y, w, bias, slope, enc, out, R, K, N, Nb, tiles);
+  return 0;
+}
+
+// returns TDANET_EUNSUPPORTED (without setting an error text the caller would report) when the shape is outside
+// what the kernel covers; the caller then takes the CUDA-core GEMM
+bool mask_conv_mma_applies(int K, int N) { return K % 8 == 0 && K <= 256 && N % 2 == 0 && N <= 136; }
+
+int launch_mask_conv_mma(const float* y, const float* w, const float* bias, const float* slope, const float* enc,
+                         float* out, int R, int K, int N, int Nb, cudaStream_t st) {
+  TD_REQUIRE(mask_conv_mma_applies(K, N), "mask_conv_mma: K=%d N=%d", K, N);
+  const int nt = cdiv(N, 8);
+  if (nt <= 5) return launch_mask_conv_mma_t<5>(y, w, bias, slope, enc, out, R, K, N, Nb, st);
+  if (nt <= 9) return launch_mask_conv_mma_t<9>(y, w, bias, slope, enc, out, R, K, N, Nb, st);
+  if (nt <= 13) return launch_mask_conv_mma_t<13>(y, w, bias, slope, enc, out, R, K, N, Nb, st);
+  return launch_mask_conv_mma_t<17>(y, w, bias, slope, enc, out, R, K, N, Nb, st);
+}
+
 // ----------------------------------------------------------------------------- decoder
 // ConvTranspose1d(n_src*Nb -> n_src, k=K, stride=S=K/4, padding=K/2, no bias) followed by the crop
 // [K-S : -(rest+K-S)].  With n the index in the un-cropped output and u = (n + K/2)/S,

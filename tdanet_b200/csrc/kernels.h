@@ -166,6 +166,10 @@ int launch_encoder(const EncArgs& a, cudaStream_t st);
 // x0[b,t,:] = Wb . GlobLN(enc) + bb     enc [B,L0,Nb], out [B,L0,c]
 int launch_bottleneck(const float* enc, const NormRef& norm, const float* w, const float* bias,
                       float* out, int B, int L0, int Nb, int c, cudaStream_t st);
+// mask_net + ReLU mask + encoder product on the tensor cores (TF32 modes, inference): masked [R, N] from y [R, K]
+bool mask_conv_mma_applies(int K, int N);
+int launch_mask_conv_mma(const float* y, const float* w, const float* bias, const float* slope, const float* enc,
+                         float* out, int R, int K, int N, int Nb, cudaStream_t st);
 // decoder ConvTranspose1d + crop: masked [B, L0, n_src*Nb] -> est [B, n_src, T]
 int launch_decoder(const float* masked, const float* w, float* est, int B, int L0, int Nb,
                    int n_src, int K, int S, int T, cudaStream_t st);
