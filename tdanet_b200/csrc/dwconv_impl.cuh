@@ -431,8 +431,12 @@ static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
   return 0;
 }
 
+static bool gstats_stream_applies(const DwArgs& a);
+static int launch_gstats_stream(const DwArgs& a, cudaStream_t st);
+
 int launch_dw5(const DwArgs& a, cudaStream_t st) {
   TD_REQUIRE(a.C % 4 == 0, "dw5: C=%d must be a multiple of 4", a.C);
+  if (gstats_stream_applies(a)) return launch_gstats_stream(a, st);
   if (a.pool_out) {
     TD_REQUIRE(a.nw == 1 && a.out && a.stats && !a.relu && !a.round_out && a.Lb > 0 && a.Lb <= a.Lout,
                "dw5: pooled output needs nw == 1, out, stats and Lb <= Lout");
@@ -1245,6 +1249,138 @@ int launch_la_local_stats(const DwArgs* steps, int n, cudaStream_t st) {
   }
   for (int i = 0; i < n; ++i)
     if (int e = TD_ACT_NS::launch_dw5(steps[i], st)) return e;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- LA global statistics, streaming
+// GlobLN statistics of global_act(x_g) and global_embedding(x_g) (TDANet_best.py:286-289) for a plain x_g
+// (the tensor the previous top-down step just wrote): nothing is written but four sums per item, so the
+// kernel is a pure read.  Same structure as the local-statistics kernel: a thread owns 4 channels and
+// streams its column through a two-stage cp.async ring, few long CTAs (the tap loads and the 4-row
+// prologue are paid once per CTA), four CTAs per SM.
+template <bool EDGE, int CT>
+__device__ __forceinline__ void gstats_stream_body(const DwArgs& a, int b, int ch, int t0, int t1, void* ring,
+                                                   float (&tot1)[2], float (&tot2)[2]) {
+  constexpr int V = 4;
+  const int L = a.src.L;
+  const int C = CT ? CT : a.C;
+  const int colw = CT ? CT : blockDim.x * V;
+  const ACT_T* x = reinterpret_cast<const ACT_T*>(a.src.x) + (size_t)b * L * C + ch;
+  vf<V> wa[5], we[5];
+  load_taps<V>(a.w[0], ch, wa);
+  load_taps<V>(a.w[1], ch, we);
+  vf<V> s1a = vzero<V>(), s2a = vzero<V>(), s1e = vzero<V>(), s2e = vzero<V>();
+
+  auto issue = [&](int k) {
+    const StageCol st = stage_col<SR, 0>(ring, k & 1, colw);
+    const int t = t0 + k * SR;
+#pragma unroll
+    for (int i = 0; i < SR; ++i) {
+      const int row = t + 2 + i;
+      const bool ok = !EDGE || row < L;
+      cp_async_act(st.act + i * colw, x + (ok ? row : 0) * C, ok);
+    }
+  };
+
+  vf<V> xr[SR + 4];
+  const int nchunks = (t1 - t0 + SR - 1) / SR;
+  {
+    const StageCol pre = stage_col<SR, 0>(ring, 1, colw);  // unused until chunk 1 is issued
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 - 2 + i;
+      const bool ok = !EDGE || (t >= 0 && t < L);
+      cp_async_act(pre.act + i * colw, x + (ok ? t : 0) * C, ok);
+    }
+  }
+  issue(0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  {
+    const StageCol pre = stage_col<SR, 0>(ring, 1, colw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 - 2 + i;
+      if (EDGE && (t < 0 || t >= L)) xr[SR + i] = vzero<V>();
+      else xr[SR + i] = alds<V>(pre.act + i * colw);
+    }
+  }
+  for (int k = 0; k < nchunks; ++k) {
+    if (k + 1 < nchunks) issue(k + 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const StageCol st = stage_col<SR, 0>(ring, k & 1, colw);
+    const int t = t0 + k * SR;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xr[i] = xr[SR + i];
+#pragma unroll
+    for (int i = 0; i < SR; ++i) {
+      if (EDGE && t + 2 + i >= L) xr[4 + i] = vzero<V>();
+      else xr[4 + i] = alds<V>(st.act + i * colw);
+    }
+#pragma unroll
+    for (int r = 0; r < SR; ++r) {
+      if (!EDGE || t + r < t1) {
+        const vf<V> ya = conv5<V>(wa, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
+        const vf<V> ye = conv5<V>(we, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
+        s1a = vadd<V>(s1a, ya);
+        s2a = vfma<V>(ya, ya, s2a);
+        s1e = vadd<V>(s1e, ye);
+        s2e = vfma<V>(ye, ye, s2e);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    tot1[0] += s1a[e];
+    tot2[0] += s2a[e];
+    tot1[1] += s1e[e];
+    tot2[1] += s2e[e];
+  }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(128, 4) gstats_stream_kernel(DwArgs a, int rows_per_cta) {
+  grid_dep_wait();
+  extern __shared__ __align__(16) float la_smem[];
+  __shared__ double red[64];
+  constexpr int V = 4;
+  const int b = blockIdx.z;
+  const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const int L = a.src.L;
+  const int t0 = blockIdx.x * rows_per_cta, t1 = min(t0 + rows_per_cta, L);
+  float tot1[2] = {0.f, 0.f}, tot2[2] = {0.f, 0.f};
+  if (ch < a.C) {
+    const bool interior = t0 - 2 >= 0 && t1 + 2 <= L && (t1 - t0) % SR == 0;
+    if (interior) gstats_stream_body<false, CT>(a, b, ch, t0, t1, la_smem, tot1, tot2);
+    else gstats_stream_body<true, CT>(a, b, ch, t0, t1, la_smem, tot1, tot2);
+  }
+  flush_item_stats<2>(a.stats, b, tot1, tot2, red);
+}
+
+static bool gstats_stream_applies(const DwArgs& a) {
+  static const bool off = getenv("TDANET_GSTATS_STREAM") && atoi(getenv("TDANET_GSTATS_STREAM")) == 0;
+  return !off && a.kind == SRC_PLAIN && a.nw == 2 && !a.out && a.stats && !a.chstats && !a.pool_out && a.stride == 1 &&
+         !a.bias[0] && !a.bias[1] && a.Lout == a.src.L && a.C % 4 == 0 && (long)a.src.L * a.C < (1L << 31);
+}
+
+static int launch_gstats_stream(const DwArgs& a, cudaStream_t st) {
+  int threads = a.C / 4;
+  if (threads > 128) threads = 128;
+  if (threads < 32) threads = 32;
+  const int ctiles = cdiv(a.C / 4, threads);
+  // one wave of four CTAs per SM (tuning aid: TDANET_GSTATS_TARGET / TDANET_GSTATS_CAP)
+  static const long target = getenv("TDANET_GSTATS_TARGET") ? atol(getenv("TDANET_GSTATS_TARGET")) : 148L * 4;
+  static const int cap = getenv("TDANET_GSTATS_CAP") ? atoi(getenv("TDANET_GSTATS_CAP")) : 128;
+  int rows, tiles;
+  pick_tiling(a.B, a.src.L, ctiles, SR, &rows, &tiles, target, cap);
+  dim3 grid(tiles, ctiles, a.B);
+  const size_t smem = ring_bytes<SR, 0>(threads);
+  if (a.C == 512 && threads == 128) {
+    TD_LAUNCH((gstats_stream_kernel<512>), grid, threads, smem, st, a, rows);
+  } else {
+    TD_LAUNCH((gstats_stream_kernel<0>), grid, threads, smem, st, a, rows);
+  }
   return 0;
 }
 
