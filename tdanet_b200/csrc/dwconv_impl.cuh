@@ -340,8 +340,8 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
   }
 }
 
-template <int KIND, int S>
-__global__ void __launch_bounds__(256) dw5_pool_kernel(DwArgs a, int bins_per_cta) {
+template <int KIND, int S, int LB>
+__global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(DwArgs a, int bins_per_cta) {
   grid_dep_wait();
   extern __shared__ int2 bins[];  // (lo, hi) of the tile's bins, plus one
   __shared__ double red[64];
@@ -424,10 +424,18 @@ static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
   const int ctiles = cdiv(a.C / 4, threads);
   int rows, tiles;
   pick_tiling(a.B, a.Lout, ctiles, S == 1 ? 8 : 4, &rows, &tiles);
+  // the short scales: a CTA pays its prologue (taps, GlobLN coefficients, bin table) for at least this many rows
+  static const int min_rows = getenv("TDANET_POOL_MINROWS") ? atoi(getenv("TDANET_POOL_MINROWS")) : 8;
+  if (rows < min_rows) rows = min_rows;
   int bpt = (int)(((long)rows * a.Lb + a.Lout / 2) / a.Lout);  // bins per tile ~ rows / (L / Lb)
   if (bpt < 1) bpt = 1;
   dim3 grid(cdiv(a.Lb, bpt), ctiles, a.B);
-  TD_LAUNCH((dw5_pool_kernel<KIND, S>), grid, threads, (size_t)(bpt + 1) * sizeof(int2), st, a, bpt);
+  static const int lb = getenv("TDANET_POOL_LB") ? atoi(getenv("TDANET_POOL_LB")) : 4;  // 4 CTAs of 128 threads per SM (128 registers)
+  if (lb == 4 && threads <= 128) {
+    TD_LAUNCH((dw5_pool_kernel<KIND, S, 4>), grid, threads, (size_t)(bpt + 1) * sizeof(int2), st, a, bpt);
+  } else {
+    TD_LAUNCH((dw5_pool_kernel<KIND, S, 0>), grid, threads, (size_t)(bpt + 1) * sizeof(int2), st, a, bpt);
+  }
   return 0;
 }
 
