@@ -151,6 +151,19 @@ __device__ __forceinline__ vf<V> conv5(const vf<V> (&tap)[5], const vf<V>& x0, c
   return r;
 }
 
+// copy the V=4 channels of one row (16 B fp32 / 8 B bf16) into this thread's shared-memory column
+__device__ __forceinline__ void cp_async_act(ACT_T* dst, const ACT_T* src, bool valid) {
+  if constexpr (sizeof(ACT_T) == 4) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+                 "r"(valid ? 16 : 0)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+                 "r"(valid ? 8 : 0)
+                 : "memory");
+  }
+}
+
 // ----------------------------------------------------------------------------- dw k=5
 template <int KIND, int V, int NW, int S, int R, bool WRITE, bool STATS, bool EDGE>
 __device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0, int t1, const int* jtab, int tab0,
@@ -272,9 +285,11 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
 // and the separate pass that re-read every out_k disappears.  Tiles are whole bins: a tile computes
 // rows [lo(ja), hi(jb-1)) and writes / counts rows [lo(ja), lo(jb)), so every bin is owned by one
 // thread and stored plainly (no atomics, no zero-fill); at most one row per tile is computed twice.
-template <int KIND, int S, bool EDGE>
+// RING: the R*S new input rows of a chunk are prefetched one chunk ahead with cp.async into a two-stage ring of
+// thread-private shared-memory columns (`ringcol`), so loads stay in flight while the current chunk is computed.
+template <int KIND, int S, bool EDGE, bool RING>
 __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, int t0, int tw, int tc, const int2* bins,
-                                              int ja, int nb, float& tot1, float& tot2) {
+                                              int ja, int nb, ACT_T* ringcol, float& tot1, float& tot2) {
   constexpr int V = 4, R = (S == 1) ? 8 : 4;
   Src<KIND, V, EDGE> src;
   src.init(a.src, b, ch, a.C, nullptr, 0);
@@ -287,6 +302,21 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
   float* pool = a.pool_out + ((size_t)b * a.Lb + ja) * a.C + ch;
   constexpr int NR = (R - 1) * S + 5, CARRY = 5 - S;
   vf<V> xr[NR];
+  const int colw = blockDim.x * V;
+  auto issue = [&](int t) {  // the new input rows of the chunk of output rows t .. t+R-1
+    ACT_T* st = ringcol + ((((t - t0) / R) & 1) * (R * S)) * colw;
+    const int base = t * S - 2 + CARRY;
+#pragma unroll
+    for (int i = 0; i < R * S; ++i) {
+      const int row = base + i;
+      const bool ok = !EDGE || (row >= 0 && row < src.L);
+      cp_async_act(st + i * colw, src.x + (ok ? row : 0) * src.C, ok);
+    }
+  };
+  if constexpr (RING) {
+    issue(t0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 #pragma unroll
   for (int i = 0; i < CARRY; ++i) {
     const int t = t0 * S - 2 + i;
@@ -297,8 +327,17 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
 #pragma unroll
     for (int i = 0; i < CARRY; ++i) xr[i] = xr[R * S + i];
     const int base = t * S - 2 + CARRY;
+    if constexpr (RING) {
+      if (t + R < tc) issue(t + R);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      const ACT_T* st = ringcol + ((((t - t0) / R) & 1) * (R * S)) * colw;
 #pragma unroll
-    for (int i = 0; i < R * S; ++i) xr[CARRY + i] = src.load_raw(base + i);
+      for (int i = 0; i < R * S; ++i) xr[CARRY + i] = alds<V>(st + i * colw);
+    } else {
+#pragma unroll
+      for (int i = 0; i < R * S; ++i) xr[CARRY + i] = src.load_raw(base + i);
+    }
 #pragma unroll
     for (int i = 0; i < R * S; ++i) xr[CARRY + i] = src.finalize(xr[CARRY + i], base + i);
 #pragma unroll
@@ -340,12 +379,15 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
   }
 }
 
-template <int KIND, int S, int LB>
+template <int KIND, int S, int LB, bool RING>
 __global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(DwArgs a, int bins_per_cta) {
   grid_dep_wait();
-  extern __shared__ int2 bins[];  // (lo, hi) of the tile's bins, plus one
+  extern __shared__ __align__(16) unsigned char pool_smem[];  // [ring: 2 stages x R*S rows x blockDim.x*4 ACT_T][bins]
   __shared__ double red[64];
   constexpr int V = 4, R = (S == 1) ? 8 : 4;
+  const size_t ring_b = RING ? (size_t)2 * R * S * blockDim.x * V * sizeof(ACT_T) : 0;
+  int2* bins = reinterpret_cast<int2*>(pool_smem + ring_b);  // (lo, hi) of the tile's bins, plus one
+  ACT_T* ringcol = reinterpret_cast<ACT_T*>(pool_smem) + threadIdx.x * V;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const int L = a.Lout, Lb = a.Lb;
@@ -362,8 +404,8 @@ __global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(D
   if (ch < a.C) {
     const int chunks = (tc - t0 + R - 1) / R;
     const bool interior = t0 * S - 2 >= 0 && (t0 + chunks * R - 1) * S + 2 < a.src.L;
-    if (interior) dw5_pool_body<KIND, S, false>(a, b, ch, t0, tw, tc, bins, ja, nb, tot1[0], tot2[0]);
-    else dw5_pool_body<KIND, S, true>(a, b, ch, t0, tw, tc, bins, ja, nb, tot1[0], tot2[0]);
+    if (interior) dw5_pool_body<KIND, S, false, RING>(a, b, ch, t0, tw, tc, bins, ja, nb, ringcol, tot1[0], tot2[0]);
+    else dw5_pool_body<KIND, S, true, RING>(a, b, ch, t0, tw, tc, bins, ja, nb, ringcol, tot1[0], tot2[0]);
   }
   flush_item_stats<1>(a.stats, b, tot1, tot2, red);
 }
@@ -423,7 +465,9 @@ static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
   if (threads < 32) threads = 32;
   const int ctiles = cdiv(a.C / 4, threads);
   int rows, tiles;
-  pick_tiling(a.B, a.Lout, ctiles, S == 1 ? 8 : 4, &rows, &tiles);
+  static const long pool_target = getenv("TDANET_POOL_TARGET") ? atol(getenv("TDANET_POOL_TARGET")) : 148L * 4;
+  static const int pool_cap = getenv("TDANET_POOL_CAP") ? atoi(getenv("TDANET_POOL_CAP")) : 128;
+  pick_tiling(a.B, a.Lout, ctiles, S == 1 ? 8 : 4, &rows, &tiles, pool_target, pool_cap);
   // the short scales: a CTA pays its prologue (taps, GlobLN coefficients, bin table) for at least this many rows
   static const int min_rows = getenv("TDANET_POOL_MINROWS") ? atoi(getenv("TDANET_POOL_MINROWS")) : 8;
   if (rows < min_rows) rows = min_rows;
@@ -431,10 +475,26 @@ static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
   if (bpt < 1) bpt = 1;
   dim3 grid(cdiv(a.Lb, bpt), ctiles, a.B);
   static const int lb = getenv("TDANET_POOL_LB") ? atoi(getenv("TDANET_POOL_LB")) : 4;  // 4 CTAs of 128 threads per SM (128 registers)
-  if (lb == 4 && threads <= 128) {
-    TD_LAUNCH((dw5_pool_kernel<KIND, S, 4>), grid, threads, (size_t)(bpt + 1) * sizeof(int2), st, a, bpt);
+  static const int ring = getenv("TDANET_POOL_RING") ? atoi(getenv("TDANET_POOL_RING")) : 1;
+  constexpr int R = S == 1 ? 8 : 4;
+  const size_t bins_b = (size_t)(bpt + 1) * sizeof(int2);
+  const size_t ring_b = (size_t)2 * R * S * threads * 4 * sizeof(ACT_T);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    attr_set = true;
+  }
+  if (ring && ring_b + bins_b <= 80 * 1024) {
+    if (lb == 4 && threads <= 128) {
+      TD_LAUNCH((dw5_pool_kernel<KIND, S, 4, true>), grid, threads, ring_b + bins_b, st, a, bpt);
+    } else {
+      TD_LAUNCH((dw5_pool_kernel<KIND, S, 0, true>), grid, threads, ring_b + bins_b, st, a, bpt);
+    }
+  } else if (lb == 4 && threads <= 128) {
+    TD_LAUNCH((dw5_pool_kernel<KIND, S, 4, false>), grid, threads, bins_b, st, a, bpt);
   } else {
-    TD_LAUNCH((dw5_pool_kernel<KIND, S, 0>), grid, threads, (size_t)(bpt + 1) * sizeof(int2), st, a, bpt);
+    TD_LAUNCH((dw5_pool_kernel<KIND, S, 0, false>), grid, threads, bins_b, st, a, bpt);
   }
   return 0;
 }
@@ -836,18 +896,6 @@ constexpr int SGR = SGC + 4;      // global rows per chunk (centres + halo)
 constexpr int SGG = 3;            // rows of the injected feature per chunk (ratio to it >= 4)
 constexpr int SAROWS = SR + SGR;  // ACT_T rows per ring stage; SGG fp32 rows follow them
 
-// copy the V=4 channels of one row (16 B fp32 / 8 B bf16) into this thread's shared-memory column
-__device__ __forceinline__ void cp_async_act(ACT_T* dst, const ACT_T* src, bool valid) {
-  if constexpr (sizeof(ACT_T) == 4) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
-                 "r"(valid ? 16 : 0)
-                 : "memory");
-  } else {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
-                 "r"(valid ? 8 : 0)
-                 : "memory");
-  }
-}
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
                "r"(valid ? 16 : 0)
@@ -1215,7 +1263,9 @@ static int launch_la_local_stats_t(LocalStatsArgs& p, cudaStream_t st) {
   long total_rows = 0;
   for (int i = 0; i < p.n; ++i) total_rows += p.step[i].Lout;
   int rows, tiles;
-  pick_tiling(a0.B, (int)total_rows, ctiles, SR, &rows, &tiles);
+  static const long ls_target = getenv("TDANET_LSTATS_TARGET") ? atol(getenv("TDANET_LSTATS_TARGET")) : 148L * 4;
+  static const int ls_cap = getenv("TDANET_LSTATS_CAP") ? atoi(getenv("TDANET_LSTATS_CAP")) : 128;
+  pick_tiling(a0.B, (int)total_rows, ctiles, SR, &rows, &tiles, ls_target, ls_cap);
   p.rows = rows;
   int acc = 0;
   for (int i = 0; i < p.n; ++i) {
