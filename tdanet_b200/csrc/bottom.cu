@@ -63,10 +63,72 @@ __global__ void affine_sum_kernel(PoolArgs a) {
   vstore<V>(a.out + ((size_t)b * a.Lb + j) * a.C + ch, acc);
 }
 
+// The same sum with the LayerNorm + positional encoding that follows it: the CTA holds the whole token row
+// (C / 4 threads), so the two-pass row moments are two block reductions and ln_pe's launch disappears.
+__global__ void affine_sum_ln_kernel(PoolArgs a) {
+  grid_dep_wait();
+  constexpr int V = 4;
+  __shared__ float red[2][32];
+  const int b = blockIdx.z, j = blockIdx.x;
+  const int ch = threadIdx.x * V;
+  const bool live = ch < a.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  vf<V> acc = vzero<V>();
+  if (live) {
+    for (int k = 0; k < a.n; ++k) {
+      vf<V> v = vload<V>(a.x[k] + ((size_t)b * a.Lb + j) * a.C + ch);
+      vf<V> sc, sh;
+      norm_coef<V>(a.norm[k], b, ch, sc, sh);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += fmaf(v[e], sc[e], sh[e]);
+    }
+    vstore<V>(a.out + ((size_t)b * a.Lb + j) * a.C + ch, acc);
+  }
+  float s = live ? (acc[0] + acc[1]) + (acc[2] + acc[3]) : 0.f;
+  s = warp_sum(s);
+  if (lane == 0) red[0][warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < nw; ++i) tot += red[0][i];
+  const float mu = tot / (float)a.C;
+  float q = 0.f;
+  if (live) {
+    const float d0 = acc[0] - mu, d1 = acc[1] - mu, d2 = acc[2] - mu, d3 = acc[3] - mu;
+    q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  q = warp_sum(q);
+  if (lane == 0) red[1][warp] = q;
+  __syncthreads();
+  float qt = 0.f;
+  for (int i = 0; i < nw; ++i) qt += red[1][i];
+  const float rstd = rsqrtf(qt / (float)a.C + kEpsLN);
+  if (!live) return;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_w + ch));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(a.ln_b + ch));
+  const float4 p = __ldg(reinterpret_cast<const float4*>(a.pe + (size_t)j * a.C + ch));
+  float4 o;
+  o.x = (acc[0] - mu) * rstd * g.x + bb.x + p.x;
+  o.y = (acc[1] - mu) * rstd * g.y + bb.y + p.y;
+  o.z = (acc[2] - mu) * rstd * g.z + bb.z + p.z;
+  o.w = (acc[3] - mu) * rstd * g.w + bb.w + p.w;
+  if (a.ln_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+  *reinterpret_cast<float4*>(a.ln_out + ((size_t)b * a.Lb + j) * a.C + ch) = o;
+}
+
+bool launch_affine_sum_fuses_ln(const PoolArgs& a) {
+  static const bool off = getenv("TDANET_FUSE_LN_PE") && atoi(getenv("TDANET_FUSE_LN_PE")) == 0;
+  return !off && a.ln_out && a.ln_w && a.ln_b && a.pe && a.C % 4 == 0 && a.C / 4 <= 256;
+}
+
 int launch_affine_sum(const PoolArgs& a, cudaStream_t st) {
   TD_REQUIRE(a.C % 4 == 0, "affine_sum: C=%d", a.C);
   int threads = a.C / 4 > 256 ? 256 : (a.C / 4 < 32 ? 32 : a.C / 4);
   dim3 grid(a.Lb, cdiv(a.C / 4, threads), a.B);
+  if (launch_affine_sum_fuses_ln(a)) {
+    threads = (threads + 31) / 32 * 32;
+    TD_LAUNCH_COOP(affine_sum_ln_kernel, grid, threads, 0, st, a);
+    return 0;
+  }
   TD_LAUNCH(affine_sum_kernel, grid, threads, 0, st, a);
   return 0;
 }
@@ -463,8 +525,11 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(tf32_rna(x - h));
 }
 
-template <int D>
-__global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
+// RAW: K and V are staged as stored (half the shared memory: four CTAs per SM instead of three, 1008 CTAs of the
+// headline shape in two waves instead of three) and split into TF32 hi / lo when a fragment is gathered - the same
+// values as the pre-split staging, so both forms give identical bits.
+template <int D, bool RAW>
+__global__ void __launch_bounds__(128, RAW ? 4 : 1) attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
                                                             int L, int C, int n, int group, int time_axis,
                                                             int round_out, const uint8_t* __restrict__ amask,
                                                             float inv_keep) {
@@ -472,9 +537,9 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restr
   constexpr int NK = 64, LD = D + 4, KT = D / 8, NT = NK / 8;
   extern __shared__ float smem[];
   float* Khi = smem;
-  float* Klo = Khi + NK * LD;
+  float* Klo = RAW ? Khi : Khi + NK * LD;
   float* Vhi = Klo + NK * LD;
-  float* Vlo = Vhi + NK * LD;
+  float* Vlo = RAW ? Vhi : Vhi + NK * LD;
   const int head = blockIdx.y, prob = blockIdx.x;
   long base, stride;
   if (time_axis) {
@@ -497,13 +562,18 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restr
       kv = *reinterpret_cast<const float4*>(kp);
       vv = *reinterpret_cast<const float4*>(kp + C);
     }
-    uint32_t h[4], l[4];
-    split_tf32(kv.x, h[0], l[0]); split_tf32(kv.y, h[1], l[1]); split_tf32(kv.z, h[2], l[2]); split_tf32(kv.w, h[3], l[3]);
-    *reinterpret_cast<uint4*>(Khi + sidx * LD + i) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(Klo + sidx * LD + i) = make_uint4(l[0], l[1], l[2], l[3]);
-    split_tf32(vv.x, h[0], l[0]); split_tf32(vv.y, h[1], l[1]); split_tf32(vv.z, h[2], l[2]); split_tf32(vv.w, h[3], l[3]);
-    *reinterpret_cast<uint4*>(Vhi + sidx * LD + i) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(Vlo + sidx * LD + i) = make_uint4(l[0], l[1], l[2], l[3]);
+    if constexpr (RAW) {
+      *reinterpret_cast<float4*>(Khi + sidx * LD + i) = kv;
+      *reinterpret_cast<float4*>(Vhi + sidx * LD + i) = vv;
+    } else {
+      uint32_t h[4], l[4];
+      split_tf32(kv.x, h[0], l[0]); split_tf32(kv.y, h[1], l[1]); split_tf32(kv.z, h[2], l[2]); split_tf32(kv.w, h[3], l[3]);
+      *reinterpret_cast<uint4*>(Khi + sidx * LD + i) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(Klo + sidx * LD + i) = make_uint4(l[0], l[1], l[2], l[3]);
+      split_tf32(vv.x, h[0], l[0]); split_tf32(vv.y, h[1], l[1]); split_tf32(vv.z, h[2], l[2]); split_tf32(vv.w, h[3], l[3]);
+      *reinterpret_cast<uint4*>(Vhi + sidx * LD + i) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(Vlo + sidx * LD + i) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
   }
   // ---- Q fragments of this warp's 16 rows (rows g and g + 8), scaled, split
   const int r0 = warp * 16 + g, r1 = r0 + 8;
@@ -533,7 +603,11 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restr
       const uint32_t* kl = reinterpret_cast<const uint32_t*>(Klo) + (nt * 8 + g) * LD + t;
 #pragma unroll
       for (int kt = 0; kt < KT; ++kt) {
-        const uint32_t bh0 = kh[8 * kt], bh1 = kh[8 * kt + 4], bl0 = kl[8 * kt], bl1 = kl[8 * kt + 4];
+        uint32_t bh0 = kh[8 * kt], bh1 = kh[8 * kt + 4], bl0 = kl[8 * kt], bl1 = kl[8 * kt + 4];
+        if constexpr (RAW) {
+          split_tf32(__uint_as_float(bh0), bh0, bl0);
+          split_tf32(__uint_as_float(bh1), bh1, bl1);
+        }
         mma_tf32_16x8x8(S[nt], ql[kt], bh0, bh1);
         mma_tf32_16x8x8(S[nt], qh[kt], bl0, bl1);
         mma_tf32_16x8x8(S[nt], qh[kt], bh0, bh1);
@@ -587,7 +661,11 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restr
       const uint32_t* vl = reinterpret_cast<const uint32_t*>(Vlo) + (j * 8 + 2 * t) * LD + g;
 #pragma unroll
       for (int dt = 0; dt < KT; ++dt) {
-        const uint32_t bh0 = vh[8 * dt], bh1 = vh[LD + 8 * dt], bl0 = vl[8 * dt], bl1 = vl[LD + 8 * dt];
+        uint32_t bh0 = vh[8 * dt], bh1 = vh[LD + 8 * dt], bl0 = vl[8 * dt], bl1 = vl[LD + 8 * dt];
+        if constexpr (RAW) {
+          split_tf32(__uint_as_float(bh0), bh0, bl0);
+          split_tf32(__uint_as_float(bh1), bh1, bl1);
+        }
         mma_tf32_16x8x8(O[dt], pl, bh0, bh1);
         mma_tf32_16x8x8(O[dt], ph, bl0, bl1);
         mma_tf32_16x8x8(O[dt], ph, bh0, bh1);
@@ -609,16 +687,21 @@ static int launch_attention_mma(const float* qkv, float* ctx, int B, int L, int 
                                 int time_axis, int round_out, const uint8_t* amask, float inv_keep, cudaStream_t st) {
   const int n = time_axis ? L : group;
   const int nprob = time_axis ? B : (B / group) * L;
-  const size_t smem = (size_t)4 * 64 * (D + 4) * sizeof(float);
+  static const bool raw = !(getenv("TDANET_ATT_RAW") && atoi(getenv("TDANET_ATT_RAW")) == 0);
+  const size_t smem = (size_t)(raw ? 2 : 4) * 64 * (D + 4) * sizeof(float);
   static bool attr_set[16] = {};  // the opt-in to > 48 KB of dynamic shared memory is per device
   int dev = 0;
   TD_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16 || !attr_set[dev]) {
-    TD_CUDA(cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TD_CUDA(cudaFuncSetAttribute(attention_mma_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * (D + 4) * (int)sizeof(float)));
     if (dev >= 0 && dev < 16) attr_set[dev] = true;
   }
   dim3 grid(nprob, n_head);
-  TD_LAUNCH((attention_mma_kernel<D>), grid, 128, smem, st, qkv, ctx, L, C, n, group, time_axis, round_out, amask, inv_keep);
+  if (raw) {
+    TD_LAUNCH((attention_mma_kernel<D, true>), grid, 128, smem, st, qkv, ctx, L, C, n, group, time_axis, round_out, amask, inv_keep);
+  } else {
+    TD_LAUNCH((attention_mma_kernel<D, false>), grid, 128, smem, st, qkv, ctx, L, C, n, group, time_axis, round_out, amask, inv_keep);
+  }
   return 0;
 }
 

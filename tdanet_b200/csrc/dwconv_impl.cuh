@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(256) inject_materialize_kernel(SrcDesc sd, int
 int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, cudaStream_t st) {  // out: ACT_T
   TD_REQUIRE(C % 4 == 0 && (long)src.L * C < (1L << 31), "inject_materialize: C=%d L=%d", C, src.L);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
-  const int rows = 16;
+  static const int rows = getenv("TDANET_MAT_ROWS") ? atoi(getenv("TDANET_MAT_ROWS")) : 16;
   dim3 grid(cdiv(src.L, rows), cdiv(C / 4, threads), B);
   if (kind == SRC_INJECT_GATE) {
     TD_LAUNCH((inject_materialize_kernel<SRC_INJECT_GATE>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
@@ -1101,7 +1101,9 @@ static int launch_la_stream(const LaArgs& a, cudaStream_t st) {
   if (threads < 32) threads = 32;
   const int ctiles = cdiv(a.C / 4, threads);
   int rows, tiles;
-  pick_tiling(a.B, a.loc.L, ctiles, SR, &rows, &tiles, 148L * 2 * 4, 128);
+  static const long ls_target = getenv("TDANET_LASTREAM_TARGET") ? atol(getenv("TDANET_LASTREAM_TARGET")) : 148L * 2 * 4;
+  static const int ls_cap = getenv("TDANET_LASTREAM_CAP") ? atoi(getenv("TDANET_LASTREAM_CAP")) : 128;
+  pick_tiling(a.B, a.loc.L, ctiles, SR, &rows, &tiles, ls_target, ls_cap);
   dim3 grid(tiles, ctiles, a.B);
   const size_t smem = (size_t)2 * SGC * threads * 4 * sizeof(float) + (size_t)(2 * rows + 4) * sizeof(int) +
                       ring_bytes<SAROWS, SGG>(threads);
@@ -1452,7 +1454,9 @@ static int launch_la_t(const LaArgs& a, cudaStream_t st) {
   if (threads < 32) threads = 32;
   const int ctiles = cdiv(a.C / V, threads);
   int rows, tiles;
-  pick_tiling(a.B, a.loc.L, ctiles, 8, &rows, &tiles);
+  static const long lt_target = getenv("TDANET_LAT_TARGET") ? atol(getenv("TDANET_LAT_TARGET")) : 148L * 16;
+  static const int lt_cap = getenv("TDANET_LAT_CAP") ? atoi(getenv("TDANET_LAT_CAP")) : 64;
+  pick_tiling(a.B, a.loc.L, ctiles, 8, &rows, &tiles, lt_target, lt_cap);
   dim3 grid(tiles, ctiles, a.B);
   // rows of the global tensor one CTA can touch: its rows map to <= rows*scale + 1 centres, + halo
   const int gspan = (int)((double)rows * a.glo.L / a.loc.L) + 16;

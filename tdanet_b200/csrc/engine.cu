@@ -124,7 +124,7 @@ static SrcDesc affine_src(const float* x, int L, const NormRef& norm, const floa
 }
 
 // The bottom-scale block: GA / GlobalAttention (TDANet_best.py:254-264)
-static int global_attention(const Ctx& x) {
+static int global_attention(const Ctx& x, bool ln_pe_done) {
   const tdanet_config_t* c = x.c;
   const tdanet_weights_t* w = x.w;
   const Plan& p = *x.p;
@@ -136,7 +136,8 @@ static int global_attention(const Ctx& x) {
 
   // attn_in_norm + positional encoding
   Tag tag("bottom_misc");
-  if (int e = launch_ln_pe(x.at(p.ga_in), w->ln1_w, w->ln1_b, w->pe, x.at(p.attn_in), B, Lb, C, x.rnd(), x.st)) return e;
+  if (!ln_pe_done)  // else: fused into the kernel that produced ga_in
+    if (int e = launch_ln_pe(x.at(p.ga_in), w->ln1_w, w->ln1_b, w->pe, x.at(p.attn_in), B, Lb, C, x.rnd(), x.st)) return e;
   GemmArgs g{};
   g.A = x.at(p.attn_in); g.W = w->in_proj_w; g.bias = w->in_proj_b; g.D = x.at(p.qkv);
   g.B = B; g.L = Lb; g.N = 3 * C; g.K = C; g.epi = EPI_BIAS;
@@ -223,6 +224,8 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   // global feature at the bottom scale
   PoolArgs pa{};
   pa.n = depth; pa.B = B; pa.C = C; pa.Lb = Lb; pa.out = x.at(p.ga_in);
+  pa.ln_w = w->ln1_w; pa.ln_b = w->ln1_b; pa.pe = w->pe; pa.ln_out = x.at(p.attn_in); pa.ln_round = x.rnd();
+  TD_REQUIRE(w->pe_rows >= Lb, "positional encoding has %d rows, need %d", w->pe_rows, Lb);
   if (c->variant == TDANET_FORK) {
     // conv_pool[depth-1-k](spp[k]): dw (k = 2s+1, stride s = 2^(depth-1-k)) -> 1x1 -> gLN; summed
     for (int k = 0; k < depth; ++k) {
@@ -244,7 +247,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     Tag tp("pool_sum");
     if (int e = launch_affine_sum(pa, x.st)) return e;
   }
-  if (int e = global_attention(x)) return e;
+  if (int e = global_attention(x, launch_affine_sum_fuses_ln(pa))) return e;
 
   // injection of the global feature: never materialised, recomputed on load by the LA kernels
   const int inj_kind = c->variant == TDANET_BEST ? SRC_INJECT_GATE : SRC_INJECT_ADD;

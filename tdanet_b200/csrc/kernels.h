@@ -104,7 +104,15 @@ struct PoolArgs {
   int L[TDANET_MAX_DEPTH];
   int B, C, Lb;
   float* out;
+  // optional fused attn_in_norm + positional encoding (GA, TDANet_best.py:254-256): ln_out = LN_C(out)*ln_w + ln_b + pe[t]
+  // (honoured when a row fits one CTA, C <= 1024; launch_affine_sum_fuses_ln tells)
+  const float* ln_w = nullptr;
+  const float* ln_b = nullptr;
+  const float* pe = nullptr;
+  float* ln_out = nullptr;
+  int ln_round = 0;
 };
+bool launch_affine_sum_fuses_ln(const PoolArgs& a);
 int launch_pool_sum(const PoolArgs& a, cudaStream_t st);
 // fork: out = sum_k affine_k(x_k), all [B, Lb, C]
 int launch_affine_sum(const PoolArgs& a, cudaStream_t st);
