@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(D
   const size_t ring_b = RING ? (size_t)2 * R * S * blockDim.x * V * sizeof(ACT_T) : 0;
   int2* bins = reinterpret_cast<int2*>(pool_smem + ring_b);  // (lo, hi) of the tile's bins, plus one
   ACT_T* ringcol = reinterpret_cast<ACT_T*>(pool_smem) + threadIdx.x * V;
-  const int b = blockIdx.z;
+  const int b = a.rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const int L = a.Lout, Lb = a.Lb;
   const int ja = blockIdx.x * bins_per_cta, jb = min(ja + bins_per_cta, Lb), nb = jb - ja;
@@ -1405,7 +1405,7 @@ __global__ void __launch_bounds__(128, 4) gstats_stream_kernel(DwArgs a, int row
   extern __shared__ __align__(16) float la_smem[];
   __shared__ double red[64];
   constexpr int V = 4;
-  const int b = blockIdx.z;
+  const int b = a.rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const int L = a.src.L;
   const int t0 = blockIdx.x * rows_per_cta, t1 = min(t0 + rows_per_cta, L);

@@ -186,6 +186,17 @@ static int global_attention(const Ctx& x, bool ln_pe_done) {
 }
 
 // One UConvBlock (TDANet_best.py:342-380) including the concat_block that feeds the next one.
+// Item order of the big streaming launches.  A tensor of the two finest scales (132 / 263 MB at B = 64) is larger
+// than the 126 MB L2: a consumer that walks the items in the producer's order finds none of it, one that starts
+// with the item written last finds the tail of it.  So the launches of the chain alternate their direction:
+// proj (first to last) -> spp_dw[0] (last to first) -> spp_dw[1] (first to last) ...; the global statistics of a
+// top-down step and res_conv read what a first-to-last la_stream wrote, last to first.  TDANET_L2_ORDER=0: off.
+// (bit mask, tuning aid: 1 spp_dw, 2 global statistics, 4 res_conv)
+static bool l2_order(int bit) {
+  static const int mask = getenv("TDANET_L2_ORDER") ? atoi(getenv("TDANET_L2_ORDER")) : 1;
+  return (mask & bit) != 0;
+}
+
 static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   const tdanet_config_t* c = x.c;
   const tdanet_weights_t* w = x.w;
@@ -218,6 +229,10 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     d.w[0] = w->spp_dw[k].w; d.bias[0] = w->spp_dw[k].b; d.out = x.at(p.spp[k]);
     d.stats = x.at<double>(p.st_spp[k]);
     d.chstats = c->variant == TDANET_BEST ? x.at(p.st_spp_ch[k]) : nullptr;
+    {
+      static const int spp_mask = getenv("TDANET_SPP_REV") ? atoi(getenv("TDANET_SPP_REV")) : 1;  // scale 0 only (measured: -0.10 ms; further scales, the global statistics and res_conv: neutral or worse)
+      d.rev = l2_order(1) && ((spp_mask >> k) & 1);
+    }
     if (c->variant != TDANET_FORK) { d.pool_out = x.at(p.pool_pw[k]); d.Lb = Lb; }  // pooled raw output P_k
     { Tag t(k == 0 ? "spp_dw0" : "spp_dw_s2"); if (int e = launch_dw5(d, x.st)) return e; }
   }
@@ -337,6 +352,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     DwArgs dg{};
     dg.src = glo; dg.kind = gkind; dg.B = B; dg.C = C; dg.Lout = glo.L; dg.stride = 1; dg.nw = 2; dg.act_bf16 = x.bf();
     dg.w[0] = la.global_act.w; dg.w[1] = la.global_embedding.w; dg.stats = x.at<double>(p.st_la_g[i]);
+    dg.rev = l2_order(2);
     { Tag t("la_stats_global"); if (int e = launch_dw5(dg, x.st)) return e; }
     LaArgs l{};
     l.loc = loc; l.glo = glo; l.lkind = lkind; l.gkind = gkind; l.B = B; l.C = C;
@@ -356,6 +372,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   g.B = B; g.L = p.L[0]; g.N = cc; g.K = C; g.epi = EPI_RESIDUAL;
   g.resid = in; g.mix = x.at(p.x0); g.cw = w->concat_w; g.cb = w->concat_b; g.cslope = w->concat_prelu; g.last = last;
   g.a_bf16 = x.bf();
+  g.rev = l2_order(4);
   Tag tr("gemm_res_conv");
   if (!p.train) return gemm(x, g, p.aux_res);
   // training: keep y = res_conv(expanded) + residual, and apply concat_block in its own launch

@@ -168,6 +168,7 @@ struct TcParams {
   int tiles_n;
   int total;     // tiles in the launch
   int nsplit;    // 1: W only, 2: W then W_lo
+  int rev_b;     // > 0: batch items are visited in the order rev_b-1 .. 0 (rev_b = B)
   uint32_t tmem_cols;
   uint32_t idesc;
 };
@@ -231,7 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
         const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
-        const int b = mt / p.tiles_m, r0 = (mt % p.tiles_m) * TC_BM, n0 = nt * p.BN;
+        const int b = p.rev_b ? p.rev_b - 1 - mt / p.tiles_m : mt / p.tiles_m, r0 = (mt % p.tiles_m) * TC_BM, n0 = nt * p.BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -293,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if constexpr (EPI == 1) cslope = __ldg(a.cslope);
     for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
       const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
-      const int b = mt / p.tiles_m, r0 = (mt % p.tiles_m) * TC_BM, n0 = nt * p.BN;
+      const int b = p.rev_b ? p.rev_b - 1 - mt / p.tiles_m : mt / p.tiles_m, r0 = (mt % p.tiles_m) * TC_BM, n0 = nt * p.BN;
       const int rbase = r0 + quarter * 32;
       const size_t item = (size_t)b * a.L;
       float s1 = 0.f, s2 = 0.f;
@@ -449,6 +450,7 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   p.tiles_m = cdiv(a.L, TC_BM);
   p.tiles_n = a.N / p.BN;
   p.total = a.B * p.tiles_m * p.tiles_n;
+  p.rev_b = a.rev ? a.B : 0;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.BN)) cols <<= 1;
   p.tmem_cols = cols;

@@ -44,6 +44,7 @@ struct DwArgs {
   float* pool_out;  // optional [B, Lb, C]: adaptive-average-pooled raw output (nw == 1, out != null)
   int Lb;
   int act_bf16;     // src.x and out are stored as bf16 (large-activation storage mode), else fp32
+  int rev;          // walk the batch items last to first (L2 reuse of what the producer wrote last; engine.cu)
   int relu;
   int round_out;  // store TF32-rounded values (output only feeds a tensor-core GEMM)
 };
@@ -215,6 +216,7 @@ struct GemmArgs {
   // bf16 activation storage: D is written as bf16 (proj_1x1) / A is read as bf16 (res_conv, kind::f16 MMA
   // against a bf16 copy of W in W_aux)
   int d_bf16, a_bf16;
+  int rev;  // tensor-core path: tiles of the last batch item first (L2 reuse of what the producer wrote last)
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st);
