@@ -540,40 +540,79 @@ int launch_dw5(const DwArgs& a, cudaStream_t st) {
 // y[t] = x_fused[k][t] written out (only for the two small tensors of the first top-down step, whose
 // down-sampling access pattern would otherwise recompute every injected row five times)
 template <int KIND>
-__global__ void __launch_bounds__(256) inject_materialize_kernel(SrcDesc sd, int C, float* __restrict__ out, int rows_per_cta) {
-  grid_dep_wait();
-  extern __shared__ int jtab[];
-  constexpr int V = 4;
+__device__ __forceinline__ void inject_materialize_tile(const SrcDesc& sd, int C, float* __restrict__ out, int tile,
+                                                        int rows_per_cta, int* jtab) {
+  constexpr int V = 4, R = 8;  // 8 rows of loads in flight per thread
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
-  const int t0 = blockIdx.x * rows_per_cta, t1 = min(t0 + rows_per_cta, sd.L);
+  const int t0 = tile * rows_per_cta, t1 = min(t0 + rows_per_cta, sd.L);
   fill_nearest(jtab, rows_per_cta, t0, sd.L, sd.gscale, sd.Lg);
   __syncthreads();
   if (ch >= C) return;
   Src<KIND, V, false> src;
   src.init(sd, b, ch, C, jtab, t0);
   ACT_T* op = reinterpret_cast<ACT_T*>(out) + (size_t)b * sd.L * C + ch;
-  for (int t = t0; t < t1; t += 4) {
-    vf<V> r[4];
+  for (int t = t0; t < t1; t += R) {
+    vf<V> r[R];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = t + i < t1 ? src.load_raw(t + i) : vzero<V>();
+    for (int i = 0; i < R; ++i) r[i] = t + i < t1 ? src.load_raw(t + i) : vzero<V>();
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < R; ++i)
       if (t + i < t1) astore<V>(op + (t + i) * C, src.finalize(r[i], t + i));
   }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) inject_materialize_kernel(SrcDesc sd, int C, float* __restrict__ out, int rows_per_cta) {
+  grid_dep_wait();
+  extern __shared__ int jtab[];
+  inject_materialize_tile<KIND>(sd, C, out, blockIdx.x, rows_per_cta, jtab);
+}
+
+// two tensors in one launch (the two operands of the first top-down step): tiles [0, tiles_a) belong to a
+template <int KIND>
+__global__ void __launch_bounds__(256) inject_materialize2_kernel(SrcDesc sa, float* __restrict__ out_a, int tiles_a,
+                                                                  SrcDesc sb, float* __restrict__ out_b, int C,
+                                                                  int rows_per_cta) {
+  grid_dep_wait();
+  extern __shared__ int jtab[];
+  if ((int)blockIdx.x < tiles_a) inject_materialize_tile<KIND>(sa, C, out_a, blockIdx.x, rows_per_cta, jtab);
+  else inject_materialize_tile<KIND>(sb, C, out_b, blockIdx.x - tiles_a, rows_per_cta, jtab);
+}
+
+static int materialize_rows() {
+  static const int rows = getenv("TDANET_MAT_ROWS") ? atoi(getenv("TDANET_MAT_ROWS")) : 16;
+  return rows;
 }
 
 int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, cudaStream_t st) {  // out: ACT_T
   TD_REQUIRE(C % 4 == 0 && (long)src.L * C < (1L << 31), "inject_materialize: C=%d L=%d", C, src.L);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
-  static const int rows = getenv("TDANET_MAT_ROWS") ? atoi(getenv("TDANET_MAT_ROWS")) : 16;
+  const int rows = materialize_rows();
   dim3 grid(cdiv(src.L, rows), cdiv(C / 4, threads), B);
   if (kind == SRC_INJECT_GATE) {
-    TD_LAUNCH((inject_materialize_kernel<SRC_INJECT_GATE>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
+    TD_LAUNCH_COOP((inject_materialize_kernel<SRC_INJECT_GATE>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
   } else if (kind == SRC_INJECT_ADD) {
-    TD_LAUNCH((inject_materialize_kernel<SRC_INJECT_ADD>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
+    TD_LAUNCH_COOP((inject_materialize_kernel<SRC_INJECT_ADD>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
   } else {
     return fail(TDANET_EINVAL, "inject_materialize: kind %d", kind);
+  }
+  return 0;
+}
+
+int launch_inject_materialize2(const SrcDesc& sa, float* out_a, const SrcDesc& sb, float* out_b, int kind, int B, int C,
+                               cudaStream_t st) {
+  TD_REQUIRE(C % 4 == 0 && (long)sa.L * C < (1L << 31) && (long)sb.L * C < (1L << 31), "inject_materialize2: C=%d", C);
+  int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
+  const int rows = materialize_rows();
+  const int tiles_a = cdiv(sa.L, rows);
+  dim3 grid(tiles_a + cdiv(sb.L, rows), cdiv(C / 4, threads), B);
+  if (kind == SRC_INJECT_GATE) {
+    TD_LAUNCH_COOP((inject_materialize2_kernel<SRC_INJECT_GATE>), grid, threads, rows * sizeof(int), st, sa, out_a, tiles_a, sb, out_b, C, rows);
+  } else if (kind == SRC_INJECT_ADD) {
+    TD_LAUNCH_COOP((inject_materialize2_kernel<SRC_INJECT_ADD>), grid, threads, rows * sizeof(int), st, sa, out_a, tiles_a, sb, out_b, C, rows);
+  } else {
+    return fail(TDANET_EINVAL, "inject_materialize2: kind %d", kind);
   }
   return 0;
 }

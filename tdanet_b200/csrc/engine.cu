@@ -340,8 +340,13 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       // nearest *down*-sampling would re-derive every injected row five times: write the two tensors out once.
       const SrcDesc gsrc = inj_src((i - 1 + depth) % depth);
       Tag t("la_combine_first");
-      if (int e = launch_inject_materialize(loc, inj_kind, B, C, x.at(p.fused_a), x.bf(), x.st)) return e;
-      if (int e = launch_inject_materialize(gsrc, inj_kind, B, C, x.at(p.fused_b), x.bf(), x.st)) return e;
+      static const bool one_launch = !(getenv("TDANET_MAT2") && atoi(getenv("TDANET_MAT2")) == 0);
+      if (one_launch) {
+        if (int e = launch_inject_materialize2(loc, x.at(p.fused_a), gsrc, x.at(p.fused_b), inj_kind, B, C, x.bf(), x.st)) return e;
+      } else {
+        if (int e = launch_inject_materialize(loc, inj_kind, B, C, x.at(p.fused_a), x.bf(), x.st)) return e;
+        if (int e = launch_inject_materialize(gsrc, inj_kind, B, C, x.at(p.fused_b), x.bf(), x.st)) return e;
+      }
       loc = plain_src(x.at(p.fused_a), loc.L);
       glo = plain_src(x.at(p.fused_b), gsrc.L);
       lkind = gkind = SRC_PLAIN;

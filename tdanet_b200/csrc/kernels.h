@@ -60,6 +60,9 @@ int launch_weight_transpose(const float* w, float* wT, int C, int ks, cudaStream
 
 // out[b, t, :] = injected operand (SRC_INJECT_GATE / SRC_INJECT_ADD) written out, [B, src.L, C]
 int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, int act_bf16, cudaStream_t st);
+// two tensors in one launch
+int launch_inject_materialize2(const SrcDesc& sa, float* out_a, const SrcDesc& sb, float* out_b, int kind, int B, int C,
+                               int act_bf16, cudaStream_t st);
 
 // LA combine (TDANet_best.py:277-292 with the three GlobLN folded into coef tables):
 //   out[t] = (cL.s*dw_l(xl)[t] + cL.h) * sigmoid(cA.s*dw_a(xg)[j] + cA.h) + (cE.s*dw_e(xg)[j] + cE.h)
