@@ -285,9 +285,9 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
 // and the separate pass that re-read every out_k disappears.  Tiles are whole bins: a tile computes
 // rows [lo(ja), hi(jb-1)) and writes / counts rows [lo(ja), lo(jb)), so every bin is owned by one
 // thread and stored plainly (no atomics, no zero-fill); at most one row per tile is computed twice.
-// RING: the R*S new input rows of a chunk are prefetched one chunk ahead with cp.async into a two-stage ring of
+// RING (stages, 0 = off): the R*S new input rows of a chunk are prefetched RING-1 chunks ahead with cp.async into a ring of
 // thread-private shared-memory columns (`ringcol`), so loads stay in flight while the current chunk is computed.
-template <int KIND, int S, bool EDGE, bool RING>
+template <int KIND, int S, bool EDGE, int RING>
 __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, int t0, int tw, int tc, const int2* bins,
                                               int ja, int nb, ACT_T* ringcol, float& tot1, float& tot2) {
   constexpr int V = 4, R = (S == 1) ? 8 : 4;
@@ -304,7 +304,7 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
   vf<V> xr[NR];
   const int colw = blockDim.x * V;
   auto issue = [&](int t) {  // the new input rows of the chunk of output rows t .. t+R-1
-    ACT_T* st = ringcol + ((((t - t0) / R) & 1) * (R * S)) * colw;
+    ACT_T* st = ringcol + ((((t - t0) / R) % (RING ? RING : 1)) * (R * S)) * colw;
     const int base = t * S - 2 + CARRY;
 #pragma unroll
     for (int i = 0; i < R * S; ++i) {
@@ -313,9 +313,13 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
       cp_async_act(st + i * colw, src.x + (ok ? row : 0) * src.C, ok);
     }
   };
-  if constexpr (RING) {
+  if constexpr (RING != 0) {
     issue(t0);
     asm volatile("cp.async.commit_group;" ::: "memory");
+    if constexpr (RING == 3) {
+      if (t0 + R < tc) issue(t0 + R);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
   }
 #pragma unroll
   for (int i = 0; i < CARRY; ++i) {
@@ -327,11 +331,12 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
 #pragma unroll
     for (int i = 0; i < CARRY; ++i) xr[i] = xr[R * S + i];
     const int base = t * S - 2 + CARRY;
-    if constexpr (RING) {
-      if (t + R < tc) issue(t + R);
+    if constexpr (RING != 0) {
+      if (t + (RING - 1) * R < tc) issue(t + (RING - 1) * R);
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-      const ACT_T* st = ringcol + ((((t - t0) / R) & 1) * (R * S)) * colw;
+      if constexpr (RING == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else asm volatile("cp.async.wait_group 1;" ::: "memory");
+      const ACT_T* st = ringcol + ((((t - t0) / R) % (RING ? RING : 1)) * (R * S)) * colw;
 #pragma unroll
       for (int i = 0; i < R * S; ++i) xr[CARRY + i] = alds<V>(st + i * colw);
     } else {
@@ -379,13 +384,13 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
   }
 }
 
-template <int KIND, int S, int LB, bool RING>
+template <int KIND, int S, int LB, int RING>
 __global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(DwArgs a, int bins_per_cta) {
   grid_dep_wait();
   extern __shared__ __align__(16) unsigned char pool_smem[];  // [ring: 2 stages x R*S rows x blockDim.x*4 ACT_T][bins]
   __shared__ double red[64];
   constexpr int V = 4, R = (S == 1) ? 8 : 4;
-  const size_t ring_b = RING ? (size_t)2 * R * S * blockDim.x * V * sizeof(ACT_T) : 0;
+  const size_t ring_b = (size_t)RING * R * S * blockDim.x * V * sizeof(ACT_T);
   int2* bins = reinterpret_cast<int2*>(pool_smem + ring_b);  // (lo, hi) of the tile's bins, plus one
   ACT_T* ringcol = reinterpret_cast<ACT_T*>(pool_smem) + threadIdx.x * V;
   const int b = a.rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
@@ -475,27 +480,28 @@ static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
   if (bpt < 1) bpt = 1;
   dim3 grid(cdiv(a.Lb, bpt), ctiles, a.B);
   static const int lb = getenv("TDANET_POOL_LB") ? atoi(getenv("TDANET_POOL_LB")) : 4;  // 4 CTAs of 128 threads per SM (128 registers)
-  static const int ring = getenv("TDANET_POOL_RING") ? atoi(getenv("TDANET_POOL_RING")) : 1;
+  static const int ring_env = getenv("TDANET_POOL_RING") ? atoi(getenv("TDANET_POOL_RING")) : 2;  // stages (0: direct loads)
   constexpr int R = S == 1 ? 8 : 4;
   const size_t bins_b = (size_t)(bpt + 1) * sizeof(int2);
-  const size_t ring_b = (size_t)2 * R * S * threads * 4 * sizeof(ACT_T);
+  int ring = ring_env == 1 ? 2 : ring_env;
+  while (ring > 0 && (size_t)ring * R * S * threads * 4 * sizeof(ACT_T) + bins_b > 100 * 1024) --ring;
+  if (ring == 1) ring = 0;
+  const size_t ring_b = (size_t)ring * R * S * threads * 4 * sizeof(ACT_T);
   static bool attr_set = false;
   if (!attr_set) {
-    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
-  if (ring && ring_b + bins_b <= 80 * 1024) {
-    if (lb == 4 && threads <= 128) {
-      TD_LAUNCH((dw5_pool_kernel<KIND, S, 4, true>), grid, threads, ring_b + bins_b, st, a, bpt);
-    } else {
-      TD_LAUNCH((dw5_pool_kernel<KIND, S, 0, true>), grid, threads, ring_b + bins_b, st, a, bpt);
-    }
-  } else if (lb == 4 && threads <= 128) {
-    TD_LAUNCH((dw5_pool_kernel<KIND, S, 4, false>), grid, threads, bins_b, st, a, bpt);
-  } else {
-    TD_LAUNCH((dw5_pool_kernel<KIND, S, 0, false>), grid, threads, bins_b, st, a, bpt);
-  }
+  const bool lb4 = lb == 4 && threads <= 128;
+#define TD_POOL_LAUNCH(LB_, RING_) \
+  TD_LAUNCH((dw5_pool_kernel<KIND, S, LB_, RING_>), grid, threads, ring_b + bins_b, st, a, bpt)
+  if (ring == 3) { if (lb4) { TD_POOL_LAUNCH(4, 3); } else { TD_POOL_LAUNCH(0, 3); } }
+  else if (ring == 2) { if (lb4) { TD_POOL_LAUNCH(4, 2); } else { TD_POOL_LAUNCH(0, 2); } }
+  else { if (lb4) { TD_POOL_LAUNCH(4, 0); } else { TD_POOL_LAUNCH(0, 0); } }
+#undef TD_POOL_LAUNCH
   return 0;
 }
 
