@@ -446,7 +446,8 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   }
   TcParams p{};
   p.nsplit = (mode == TDANET_GEMM_TF32X3 && !a.a_bf16) ? 2 : 1;
-  p.BN = a.N % 256 == 0 && p.nsplit == 1 ? 256 : (a.N >= 128 ? 128 : a.N);
+  static const int bn_max = getenv("TDANET_GEMM_BN") ? atoi(getenv("TDANET_GEMM_BN")) : 256;  // tuning aid: 128 | 256
+  p.BN = a.N % 256 == 0 && p.nsplit == 1 && bn_max >= 256 ? 256 : (a.N >= 128 ? 128 : a.N);
   p.tiles_m = cdiv(a.L, TC_BM);
   p.tiles_n = a.N / p.BN;
   p.total = a.B * p.tiles_m * p.tiles_n;
