@@ -41,6 +41,120 @@ def workload_name(variant, enc_ms, batch):
             f"(BASELINE.json configs[{1 if enc_ms == 4 else 2}]), random-init weights (seed 0)")
 
 
+def common_config(variant, enc_ms, batch):
+    """The `config` object both arms (ours / reference) print verbatim, so that the driver's same-config check compares
+    like with like; arm-specific knobs go to `impl_config`."""
+    return {"workload": workload_name(variant, enc_ms, batch), "batch_per_gpu": batch, "n_samples": N_SAMPLES}
+
+
+def pin_to_gpu_numa_node(local):
+    """Binds this rank to the cores of its GPU's NUMA node (pinned host buffers allocated afterwards are then
+    first-touched there): at N = 4 / 8 every rank used to sit on node 0 and the pinned H2D / D2H copies of the e2e
+    path lost 5-6 %.  Best effort: any failure leaves the affinity alone."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            return {"numa_node": node, "cores": len(use)}
+    except Exception:
+        pass
+    return None
+
+
+def tf32_peak():
+    """Dense TF32 tensor-core peak measured on this pool's B200 the way MEASURED_PEAKS.json measured bf16
+    (torch.matmul 8192^3 with allow_tf32, best of 10 = burst, back to back for 4 s = sustained):
+    profiles/r02_tf32_peak.json, written by scripts/measure_tf32_peak.py."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_tf32_peak.json")) as f:
+            p = json.load(f)
+        return float(p["tf32_tflops"]), float(p["tf32_tflops_sustained"]), "measured (profiles/r02_tf32_peak.json)"
+    except Exception:
+        return 1125.0, 1125.0, "fallback (half of the nominal dense bf16 2.25 PF)"
+
+
+def gemm_flops(lengths, B, C=512, c=128):
+    """2*M*K*N per forward (16 blocks) of the tcgen05 GEMM roles."""
+    L0, Lb = lengths[0], lengths[-1]
+    per_block = {"gemm_proj": 2 * C * c * L0, "gemm_res_conv": 2 * C * c * L0, "gemm_in_proj": 2 * 3 * C * C * Lb,
+                 "gemm_out_proj": 2 * C * C * Lb, "gemm_fc1": 2 * 2 * C * C * Lb, "gemm_fc2": 2 * 2 * C * C * Lb}
+    return {k: v * B * 16 for k, v in per_block.items()}
+
+
+def eager_gpu_baseline(args, dev, B, steps=3):
+    """"Eager PyTorch on B200" (SURVEY.md section 2a / BASELINE.md section 4): the reference's module graph as stock ATen /
+    cuDNN / cuBLAS calls on this GPU - oracle/tdanet_oracle.py, the restatement pinned to the reference, moved to
+    cuda - TF32 off and on, same weights, same batch.  A measured baseline like cpu_baseline, never the product."""
+    from oracle import tdanet_oracle as O
+    import tdanet_b200.look2hear.models as M
+    kw = model_kwargs(args.enc_ms)
+    torch.manual_seed(0)
+    model = M.get(CLASSES[args.variant])(sample_rate=SR, **kw)
+    sd = {k: v.detach().to(dev) for k, v in model.state_dict().items()}
+    cfg = O.OracleConfig(variant=args.variant, sample_rate=SR, **kw)
+    x = (torch.randn(B, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234)) * 0.1).to(dev)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    out = {"unit": UNIT, "batch": B, "what": "oracle module graph as stock ATen/cuDNN/cuBLAS eager calls on this GPU"}
+    try:
+        for name, flag in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = flag
+            with torch.no_grad():
+                for _ in range(2):
+                    O.forward(sd, x, cfg)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(dev)
+                ev0.record()
+                for _ in range(steps):
+                    O.forward(sd, x, cfg)
+                ev1.record()
+                torch.cuda.synchronize(dev)
+            out[name] = B * (N_SAMPLES / SR) * steps / (ev0.elapsed_time(ev1) / 1e3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del sd, x
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_eager_gpu(args):
+    """`--impl eager_gpu`: the eager-PyTorch-on-B200 arm as its own JSON line."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    e = eager_gpu_baseline(args, dev, args.batch, steps=max(1, args.steps))
+    print(json.dumps({"impl": "eager_gpu", "metric": METRIC, "value": e["tf32"], "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "warmup": 2, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32 (TF32 matmul/cuDNN allowed)", "data": "synthetic",
+                      "config": common_config(args.variant, args.enc_ms, args.batch), "eager_gpu": e}))
+
+
+def write_detail(args, world, obj):
+    """The full record (per-kernel table, every leg's config) goes to a file; stdout carries ONE compact line."""
+    path = args.detail_out or os.path.join(ROOT, "gpurun_out", f"bench_detail_{args.variant}_{args.enc_ms}ms_{args.act_dtype}_{args.scaling}_n{world}.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as f:
+            json.dump(obj, f, indent=1)
+        return os.path.relpath(path, ROOT)
+    except OSError:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -236,6 +350,48 @@ def run_longform_leg(args, dev, rank, world, barrier):
             "stitched_samples": int(out.shape[-1]), "swapped_chunks": int(swap.sum().item())}
 
 
+def run_two_ms_leg(args, dev, rank, world, barrier):
+    """BASELINE.json configs[2]: the 2 ms encoder (latent 4010 .. 251), 64 mixtures split over the GPUs (strong
+    scaling, no collective; every shard attends within itself like a per-shard reference run)."""
+    import torch.distributed as dist
+    import tdanet_b200.look2hear.models as M
+    B = 64 // world
+    torch.manual_seed(0)
+    model = M.get(CLASSES[args.variant])(sample_rate=SR, **model_kwargs(2)).eval().to(dev)
+    model.gemm_mode, model.act_dtype = args.gemm_mode, args.act_dtype
+    eng, weights = model.engine, model._weights()
+    x = (torch.randn(64, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234)) * 0.1)[rank * B:(rank + 1) * B]
+    x = x.squeeze(1).contiguous().to(dev)
+    K = max(5, min(args.steps, 10))
+    with torch.no_grad():
+        for _ in range(3):
+            eng.forward_graphed(weights, x)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            eng.forward_graphed(weights, x)
+        ev1.record()
+        barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    del model, x
+    eng._ws.clear()
+    eng._graphs.clear()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, _ = measured_peaks()
+    model_gb = {"best": 3.859, "fork": 3.892}[args.variant] / (2 if args.act_dtype == "bf16" else 1)
+    value = 64 * 2.0 * K / (ms / 1e3)
+    return {"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / K, "steps": K, "scaling": "strong",
+            "n_gpus": world, "batch_per_gpu": B, "global_batch": 64,
+            "config": {"workload": workload_name(args.variant, 2, B)},
+            "frac_of_survey_roofline": round(value / world / (peak / model_gb * 2.0), 4)}
+
+
 def run_train_leg(args, dev, rank, world, local, barrier):
     """BASELINE.json configs[3]: full training step (forward, PIT SI-SDR loss, backward, gradient all-reduce,
     clip 5.0, Adam) of the 4 ms / 16-block TDANetBest at batch 8 per GPU.  Returns the "train" object of the
@@ -326,8 +482,10 @@ def run_train_leg(args, dev, rank, world, local, barrier):
         "e2e": {"value": K / (ms_e2e / 1e3), "unit": "steps/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": B * 3 * N_SAMPLES * 4, "d2h_bytes_per_step": 4},
         "gpu_launches_per_step": launches, "loss_after": final_loss, "clocks": clk.summary(), "roofline": roofline,
+        # whole-step roofline: SURVEY.md 8(d) - a training step moves 3x the forward's bytes per mixture
+        "step_frac": round((K / (ms / 1e3)) / (peak / (3 * {("best", 4): 1.936, ("best", 2): 3.859, ("fork", 4): 1.952, ("fork", 2): 3.892}[(args.variant, args.enc_ms)] * B)), 4),
         "profiled_ms_per_step": round(sum(k["ms_per_step"] for k in kernels), 3),
-        "kernels": kernels[:16],
+        "kernels": kernels,
     }
     if world == 1 and not args.skip_cpu:
         out["cpu_baseline"] = cpu_train_baseline(args)
@@ -381,26 +539,34 @@ def run_reference(args):
         t0 = time.perf_counter()
         O.forward(sd, x1, cfg)
         t1 = time.perf_counter() - t0
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    bs = int(max(1, min(args.ref_batch, budget // max(t1, 1e-3))))
+    # The step is the full 64-mixture batch of the workload (batch-axis attention makes a smaller batch a different
+    # attention problem); what is bounded is the number of warm-up steps: the run is kept under ~5 minutes.
+    bs = int(max(1, min(args.ref_batch, args.batch)))
+    est_step = t1 * bs * 0.55            # a batch amortises the per-op overhead of the 1-mixture probe
+    warm = args.warmup
+    while warm > 1 and (args.steps + warm) * est_step > 280.0:
+        warm -= 1
+    while bs > 8 and (args.steps + warm) * (t1 * bs * 0.55) > 420.0:
+        bs //= 2
     x = torch.randn(bs, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234)) * 0.1
     with torch.no_grad():
-        for _ in range(args.warmup):
+        for _ in range(warm):
             O.forward(sd, x, cfg)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             O.forward(sd, x, cfg)
         dt = time.perf_counter() - t0
     value = bs * (N_SAMPLES / SR) * args.steps / dt
-    sample = f"{bs} x 2 s mixtures per step (of the {args.batch}-mixture workload), {args.steps} steps"
+    sample = f"{bs} x 2 s mixtures per step (the workload's batch is {args.batch}), {args.steps} steps after {warm} warm-up"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.variant, args.enc_ms, args.batch), "batch_per_step": bs,
-                   "note": "the reference is pure PyTorch and cannot travel to the GPU box (sources may not be "
-                           "copied); this arm times oracle/tdanet_oracle.py, the CPU restatement pinned to the "
-                           "reference by tests/golden, on all host threads"},
+        "config": common_config(args.variant, args.enc_ms, args.batch),
+        "impl_config": {"batch_per_step": bs,
+                        "note": "the reference is pure PyTorch and cannot travel to the GPU box (sources may not be "
+                                "copied); this arm times oracle/tdanet_oracle.py, the CPU restatement pinned to the "
+                                "reference by tests/golden, on all host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -419,6 +585,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -436,14 +603,16 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    B, W, K = args.batch, max(3, args.warmup), args.steps
+    if args.scaling == "strong" and args.batch % world:
+        raise SystemExit(f"--scaling strong: batch {args.batch} does not split over {world} GPUs")
+    B, W, K = (args.batch // world if args.scaling == "strong" else args.batch), max(3, args.warmup), args.steps
     kw = model_kwargs(args.enc_ms)
     torch.manual_seed(0)
     model = M.get(CLASSES[args.variant])(sample_rate=SR, **kw).eval().to(dev)
     model.gemm_mode = args.gemm_mode
     model.act_dtype = args.act_dtype
     eng, weights = model.engine, model._weights()
-    # each rank separates its own shard of the global batch (weak scaling: B mixtures per GPU)
+    # each rank separates its own shard of the global batch (weak: B mixtures per GPU; strong: args.batch / world)
     x_host = (torch.randn(B, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234 + rank)) * 0.1).pin_memory()
     x_dev = x_host.to(dev).squeeze(1).contiguous()
     lengths, _, _ = eng.latent_lengths(N_SAMPLES)
@@ -527,6 +696,16 @@ def run_ours(args):
         model._engine._graphs.clear()
         torch.cuda.empty_cache()
         longform = run_longform_leg(args, dev, rank, world, barrier)
+    two_ms = None
+    if not args.skip_2ms and args.enc_ms == 4 and 64 % world == 0:
+        model._engine._ws.clear()
+        model._engine._graphs.clear()
+        torch.cuda.empty_cache()
+        two_ms = run_two_ms_leg(args, dev, rank, world, barrier)
+    eager = None
+    if rank == 0 and world == 1 and not args.skip_eager:
+        torch.cuda.empty_cache()
+        eager = eager_gpu_baseline(args, dev, B)
     audio_s = world * B * (N_SAMPLES / SR) * K
     value = audio_s / (ms / 1e3)
     e2e = audio_s / (ms_e2e / 1e3)
@@ -534,8 +713,13 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         alg = algorithmic_bytes(args.variant, lengths, B)
-        if args.act_dtype == "bf16":   # per-role byte model below is for fp32 storage
-            alg = {}
+        if args.act_dtype == "bf16":
+            # bf16 storage halves every large activation (the statistics, the 128-channel residual stream and the
+            # bottom-scale tensors stay fp32): the streaming roles move half the bytes of the fp32 model
+            half = ("gemm_proj", "spp_dw0", "spp_dw_s2", "la_stats_local", "la_stats_global", "la_combine", "la_combine_first")
+            alg = {k: (v // 2 if k in half else v) for k, v in alg.items() if k in half}
+        flops = gemm_flops(lengths, B)
+        tf_burst, tf_sust, tf_src = tf32_peak()
         kernels = []
         for p in sorted(prof, key=lambda r: -r["ms"]):
             per_step_ms = p["ms"] / 2
@@ -543,6 +727,10 @@ def run_ours(args):
             if p["kernel"] in alg:
                 row["alg_GB_per_step"] = round(alg[p["kernel"]] / 1e9, 4)
                 row["achieved_GBps"] = round(alg[p["kernel"]] / 1e9 / (per_step_ms / 1e3), 1)
+                row["hbm_frac"] = round(row["achieved_GBps"] / peak, 4)
+            if p["kernel"] in flops:      # the contraction kernels are reported on the tensor axis too
+                row["achieved_TFLOPs"] = round(flops[p["kernel"]] / 1e12 / (per_step_ms / 1e3), 1)
+                row["tensor_frac_of_tf32_sustained"] = round(row["achieved_TFLOPs"] / tf_sust, 4)
             kernels.append(row)
         top = next((r for r in kernels if "achieved_GBps" in r), None)
         prof_total = sum(r["ms_per_step"] for r in kernels)
@@ -556,18 +744,21 @@ def run_ours(args):
         }
         # whole-step roofline against SURVEY.md §8(d)'s byte model (1.936 GB / mixture at 4 ms, fp32)
         model_gb = {("best", 4): 1.936, ("best", 2): 3.859, ("fork", 4): 1.952, ("fork", 2): 3.892}[(args.variant, args.enc_ms)]
+        if args.act_dtype == "bf16":
+            model_gb /= 2
         step_roofline = {"survey_bytes_per_mixture_GB": model_gb, "hbm_roofline_audio_s_per_s": round(peak / model_gb * 2.0, 1),
                          "frac_of_survey_roofline": round(value / world / (peak / model_gb * 2.0), 4)}
         cpu = cpu_baseline(args) if world == 1 and not args.skip_cpu else None
-        out = {
+        dtype = ("bf16 storage, fp32 arithmetic, tf32/bf16 tcgen05 GEMMs" if args.act_dtype == "bf16" else
+                 "f32 (tf32 tcgen05 GEMMs)" if args.gemm_mode != "fp32" else "f32")
+        detail = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("bf16 activation storage, fp32 arithmetic (tf32/bf16 tensor-core GEMMs)" if args.act_dtype == "bf16" else
-                      "f32 (tf32 tensor-core GEMMs, fp32 storage/accumulate)" if args.gemm_mode != "fp32" else "f32"),
-            "data": "synthetic",
-            "config": {"workload": workload_name(args.variant, args.enc_ms, B), "batch_per_gpu": B, "n_samples": N_SAMPLES,
-                       "gemm_mode": args.gemm_mode, "act_dtype": args.act_dtype, "cuda_graph": not args.no_graph,
-                       "l2": "no flush needed: one step streams a 1.7 GB workspace, 13x the 126 MB L2"},
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic",
+            "config": common_config(args.variant, args.enc_ms, B),
+            "impl_config": {"gemm_mode": args.gemm_mode, "act_dtype": args.act_dtype, "cuda_graph": not args.no_graph,
+                            "global_batch": B * world, "numa": numa,
+                            "l2": "no flush needed: one step streams a 1.7 GB workspace, 13x the 126 MB L2"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": B * 2 * N_SAMPLES * 4,
                     "ms_per_step": ms_e2e / K,
                     "api": "look2hear.system.separate_pipelined(model, pinned host batches): every step copies its mixtures "
@@ -579,14 +770,54 @@ def run_ours(args):
             "clocks": clk.summary(),
             "roofline": roofline,
             "step_roofline": step_roofline,
-            "kernels": kernels[:14],
+            "tf32_peak": {"burst_TFLOPs": tf_burst, "sustained_TFLOPs": tf_sust, "source": tf_src},
+            "kernels": kernels,
         }
         if cpu is not None:
-            out["cpu_baseline"] = cpu
+            detail["cpu_baseline"] = cpu
+        if eager is not None:
+            detail["eager_gpu"] = eager
         if train is not None:
-            out["train"] = train
+            detail["train"] = train
         if longform is not None:
-            out["longform"] = longform
+            detail["longform"] = longform
+        if two_ms is not None:
+            detail["two_ms"] = two_ms
+        detail_path = write_detail(args, world, detail)
+        # ---- the ONE line on stdout: every contract key, compact (the driver keeps ~1.5 kB tails)
+        r4 = lambda v: None if v is None else round(float(v), 4)   # noqa: E731
+        r1 = lambda v: None if v is None else round(float(v), 1)   # noqa: E731
+        out = {
+            "metric": METRIC, "value": r1(value), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": r4(ms / K), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic", "config": detail["config"],
+            "e2e": {"value": r1(e2e), "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4,
+                    "d2h_bytes_per_step": B * 2 * N_SAMPLES * 4},
+            "gpu_launches": launches_per_step * K,
+            "clocks": {k: clk.summary()[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "roofline": None if roofline is None else {
+                "bound": "hbm", "kernel": roofline["kernel"], "achieved": roofline["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": roofline["frac"], "traffic": roofline["traffic"], "share": roofline["share_of_step"]},
+            "step_frac": step_roofline["frac_of_survey_roofline"],
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = {"value": r4(cpu["value"]), "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
+                                   "sample": cpu["sample_short"]}
+        if eager is not None:
+            out["eager_gpu"] = {"fp32": r1(eager["fp32"]), "tf32": r1(eager["tf32"]), "unit": UNIT}
+        if train is not None:
+            out["train"] = {"value": r4(train["value"]), "unit": "steps/s", "ms": r4(train["ms_per_step"]),
+                            "e2e": r4(train["e2e"]["value"]), "batch_per_gpu": TRAIN_BATCH,
+                            "frac": None if not train.get("roofline") else train["roofline"]["frac"],
+                            "step_frac": train.get("step_frac")}
+        if longform is not None:
+            out["longform"] = {"value": r1(longform["value"]), "e2e": r1(longform["e2e"]["value"]), "unit": UNIT,
+                               "scaling": "strong"}
+        if two_ms is not None:
+            out["two_ms"] = {"value": r1(two_ms["value"]), "unit": UNIT, "scaling": "strong",
+                             "batch_per_gpu": two_ms["batch_per_gpu"]}
+        if detail_path:
+            out["detail"] = detail_path
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -613,6 +844,7 @@ def cpu_baseline(args):
         O.forward(sd, x[:bs], cfg)
         dt = time.perf_counter() - t0
     return {"value": bs * 2.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample_short": f"1 forward of {bs} of the {args.batch} mixtures, fp32 eager",
             "sample": f"one forward of {bs} x 2 s mixtures (of the {args.batch}-mixture step) after one 1-mixture warm-up, fp32 eager, {cores} threads"}
 
 
@@ -621,7 +853,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager_gpu"])
     ap.add_argument("--variant", default="best", choices=list(CLASSES))
     ap.add_argument("--enc-ms", type=int, default=4, choices=[2, 4])
     ap.add_argument("--batch", type=int, default=64, help="mixtures per GPU per step")
@@ -633,10 +865,17 @@ def main():
     ap.add_argument("--train-only", action="store_true", help="print the training-step leg as the JSON line (profiling aid)")
     ap.add_argument("--skip-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[3])")
     ap.add_argument("--skip-longform", action="store_true", help="skip the long-form leg (BASELINE.json configs[4])")
-    ap.add_argument("--ref-batch", type=int, default=8, help="upper bound of mixtures per step for --impl reference")
+    ap.add_argument("--ref-batch", type=int, default=64, help="upper bound of mixtures per step for --impl reference")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch mixtures per GPU; strong: --batch mixtures split over the GPUs (BASELINE.json configs[2])")
+    ap.add_argument("--skip-eager", action="store_true", help="skip the eager-PyTorch-on-B200 baseline (N=1 only)")
+    ap.add_argument("--skip-2ms", action="store_true", help="skip the strong-scaled 2 ms leg (BASELINE.json configs[2])")
+    ap.add_argument("--detail-out", default="", help="where the full record goes (default gpurun_out/bench_detail_*.json)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "eager_gpu":
+        run_eager_gpu(args)
     else:
         run_ours(args)
 

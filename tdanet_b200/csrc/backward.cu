@@ -750,6 +750,7 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
   int dev = 0;
   TD_CUDA(cudaGetDevice(&dev));
   TD_REQUIRE(dev >= 0 && dev < 16, "device %d", dev);
+  std::lock_guard<std::mutex> enqueue_lock(device_enqueue_mutex(dev));
   x.side = &g_side[dev];
   x.main_st = st;
   if (int e = x.side->init()) return e;

@@ -79,6 +79,8 @@ struct FwdSide {
   }
 };
 static FwdSide g_fside[16];
+static std::mutex g_enqueue_mu[17];
+std::mutex& device_enqueue_mutex(int dev) { return g_enqueue_mu[(dev >= 0 && dev < 16) ? dev : 16]; }
 static thread_local FwdSide* t_fside = nullptr;  // set by forward() for the duration of the call
 
 static int gemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
@@ -399,9 +401,11 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
   TD_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   Ctx x{c, w, &p, (char*)workspace, st};
   const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
+  int cur_dev = 0;
+  TD_CUDA(cudaGetDevice(&cur_dev));
+  std::lock_guard<std::mutex> enqueue_lock(device_enqueue_mutex(cur_dev));
   {
-    int dev = 0;
-    TD_CUDA(cudaGetDevice(&dev));
+    int dev = cur_dev;
     t_fside = nullptr;
     if (dev >= 0 && dev < 16) {
       if (int e = g_fside[dev].init()) return e;

@@ -316,7 +316,9 @@ template <int NS>
 __global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ masked,
                                                       const float* __restrict__ w,
                                                       float* __restrict__ est, int L0, int CI, int K,
-                                                      int S, int T, int hops_per_cta) {
+                                                      int S, int T, int hops_per_cta, int RS) {
+  // RS = phases covered by one pass of the CTA (== S when S <= 64; hops wider than that - the reference's default
+  // enc_kernel_size = 21 ms gives S = 84 - are walked in several passes of RS phases)
   grid_dep_wait();
   extern __shared__ float ms[];  // [hops_per_cta + 3][CI]
   const int b = blockIdx.z;
@@ -328,9 +330,9 @@ __global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ 
     ms[i] = (f >= 0 && f < L0) ? __ldg(masked + ((size_t)b * L0 + f) * CI + i % CI) : 0.f;
   }
   __syncthreads();
-  const int r = threadIdx.x % S;
-  const int qg = threadIdx.x / S;
+  const int qg = threadIdx.x / RS;
   if (qg * 4 >= hops_per_cta) return;
+  for (int r = threadIdx.x % RS; r < S; r += RS) {
   float acc[NS][4];
 #pragma unroll
   for (int o = 0; o < NS; ++o)
@@ -362,27 +364,28 @@ __global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ 
       for (int o = 0; o < NS; ++o) est[((size_t)b * NS + o) * T + n] = acc[o][q];
     }
   }
+  }
 }
 
 int launch_decoder(const float* masked, const float* w, float* est, int B, int L0, int Nb, int n_src,
                    int K, int S, int T, cudaStream_t st) {
   TD_REQUIRE(K == 4 * S, "decoder: window %d must be 4 hops of %d", K, S);
-  TD_REQUIRE(S <= 64, "decoder: hop %d too large", S);
   const int CI = n_src * Nb;
-  int hops = (256 / S) * 4;  // every thread of a 256-thread CTA owns 4 hops of one phase
+  const int RS = S <= 64 ? S : 64;
+  int hops = (256 / RS) * 4;  // every thread of a 256-thread CTA owns 4 hops of one phase (of several when S > 64)
   if (hops > 64) hops = 64;
-  const int threads = S * (hops / 4);
+  const int threads = RS * (hops / 4);
   const size_t smem = (size_t)(hops + 3) * CI * sizeof(float);
   const int total_hops = cdiv(K - S + T, S);
   dim3 grid(cdiv(total_hops, hops), 1, B);
   if (n_src == 2) {
     if (smem > 48 * 1024)
       TD_CUDA(cudaFuncSetAttribute(decoder_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TD_LAUNCH((decoder_kernel<2>), grid, threads, smem, st, masked, w, est, L0, CI, K, S, T, hops);
+    TD_LAUNCH((decoder_kernel<2>), grid, threads, smem, st, masked, w, est, L0, CI, K, S, T, hops, RS);
   } else if (n_src == 3) {
     if (smem > 48 * 1024)
       TD_CUDA(cudaFuncSetAttribute(decoder_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TD_LAUNCH((decoder_kernel<3>), grid, threads, smem, st, masked, w, est, L0, CI, K, S, T, hops);
+    TD_LAUNCH((decoder_kernel<3>), grid, threads, smem, st, masked, w, est, L0, CI, K, S, T, hops, RS);
   } else {
     return fail(TDANET_EUNSUPPORTED, "decoder: num_sources=%d (2 or 3 supported)", n_src);
   }

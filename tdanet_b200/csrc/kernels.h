@@ -2,8 +2,13 @@
 // All tensors are fp32 device pointers, activations channels-last [B, L, C].
 #pragma once
 #include "common.cuh"
+#include <mutex>
 
 namespace td {
+// The side streams / event rings of forward (engine.cu) and backward (backward.cu) are per-device library state; a
+// host thread holds this lock while it enqueues a forward or backward on that device, so two threads cannot
+// interleave their fork / join events (or pull each other's side-stream launches into a stream capture).
+std::mutex& device_enqueue_mutex(int dev);
 
 // ------------------------------------------------------------------ sources (normalise-on-load)
 // How a consumer kernel reads one row of a [B, L, C] activation.

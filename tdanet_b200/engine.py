@@ -46,7 +46,9 @@ class SeparationEngine:
         self._ws: Dict[torch.device, torch.Tensor] = {}
         self._tws: Dict[torch.device, torch.Tensor] = {}   # training workspace (activations of every block)
         self._graphs: Dict[Tuple, Tuple] = {}
-        self._keep = None  # tensors referenced by the packed weight struct
+        self._tws_gen: Dict[torch.device, Tuple] = {}      # what the last forward_train left there (see backward)
+        self._gen = 0
+        self._tws_listeners = []                           # called when a training workspace is reallocated
         self._rng: Dict[torch.device, torch.Tensor] = {}   # device int64[2] = {seed, offset} of the dropout masks
 
     # ------------------------------------------------------------------ configuration
@@ -158,7 +160,10 @@ class SeparationEngine:
         w.concat_prelu = P("sm.concat_block.1.weight")
         w.mask_prelu, w.mask_w, w.mask_b = P("mask_net.0.weight"), P("mask_net.1.weight"), P("mask_net.1.bias")
         w.dec_w = P("decoder.weight")
-        self._keep = (self._keep or []) + keep if optional else keep
+        # The struct holds raw pointers: the tensors must outlive it.  They ride on the struct itself, so whoever owns
+        # the Weights (the model's cached pack, a TrainingStep, one autograd backward) owns their lifetime - nothing
+        # accumulates on the engine.
+        w._keep = keep
         return w
 
     # ------------------------------------------------------------------ workspace
@@ -214,9 +219,24 @@ class SeparationEngine:
     def _train_workspace(self, device, nbytes: int) -> torch.Tensor:
         ws = self._tws.get(device)
         if ws is None or ws.numel() < nbytes:
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.TdanetError("the training workspace would be reallocated during stream capture")
+            ws = None
+            self._tws.pop(device, None)
+            for cb in list(self._tws_listeners):   # captured training graphs hold the old pointer: drop them
+                cb(device)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._tws[device] = ws
         return ws
+
+    def on_train_workspace_realloc(self, callback) -> None:
+        """`callback(device)` runs before the training workspace of `device` is replaced by a larger one
+        (TrainingStep drops its captured CUDA graph there: the graph bakes the workspace pointer in)."""
+        self._tws_listeners.append(callback)
+
+    def _train_signature(self, B: int, T: int, attn_group: int) -> Tuple:
+        c = self.cfg
+        return (B, T, attn_group, c.gemm_mode, c.act_dtype, float(c.dropout), float(c.drop_path))
 
     def train_workspace_tensor(self, name: str, block: int, batch: int, n_samples: int, device) -> torch.Tensor:
         """View of a tensor kept by forward_train for UConvBlock iteration `block` (tests)."""
@@ -254,12 +274,22 @@ class SeparationEngine:
             else:
                 check(lib.tdanet_forward_train(C.byref(self.cfg), C.byref(weights), wav.data_ptr(), B, T, out.data_ptr(),
                                                ws.data_ptr(), ws.numel(), stream))
+            # stamp what now lives in the workspace: backward() refuses anything else (a second
+            # forward_train before the first backward used to hand the first graph the second call's activations)
+            self._gen += 1
+            self._tws_gen[wav.device] = (self._gen, self._train_signature(B, T, attn_group))
         return out
 
+    def train_generation(self, device) -> int:
+        """Id of the forward_train call whose activations the training workspace of `device` holds (0: none)."""
+        return self._tws_gen.get(torch.device(device), (0, None))[0]
+
     def backward(self, weights: Weights, grad_weights: Weights, wav: torch.Tensor, d_est: torch.Tensor,
-                 attn_group: int = 0) -> None:
+                 attn_group: int = 0, generation: Optional[int] = None) -> None:
         """Adds d loss / d theta into the buffers `grad_weights` points at, from d_est = d loss / d est and the
-        workspace the matching forward_train() call left behind."""
+        workspace the matching forward_train() call left behind.  `generation` (train_generation() right after
+        that forward) makes the match explicit: a later forward_train on the same device has overwritten the
+        activations and the call raises instead of returning gradients of the wrong graph."""
         self._check_wav(wav)
         B, T = wav.shape
         if d_est.shape != (B, self.cfg.num_sources, T) or d_est.dtype != torch.float32 or not d_est.is_cuda:
@@ -271,6 +301,15 @@ class SeparationEngine:
             need = self.train_workspace_bytes(B, T)
             if ws is None or ws.numel() < need:
                 raise _lib.TdanetError("backward() without a matching forward_train() on this device")
+            gen, sig = self._tws_gen.get(wav.device, (0, None))
+            if generation is not None and generation != gen:
+                raise _lib.TdanetError(
+                    f"backward() of forward_train call #{generation}, but the training workspace holds call #{gen}: "
+                    "a later model(x) in grad mode overwrote the activations (one forward per backward per device)")
+            if sig != self._train_signature(B, T, attn_group):
+                raise _lib.TdanetError(
+                    f"backward() with (B, T, attn_group, gemm_mode, act_dtype, dropout, drop_path) = "
+                    f"{self._train_signature(B, T, attn_group)} but the workspace was written with {sig}")
             self.cfg.attn_group = attn_group
             stream = torch.cuda.current_stream(wav.device).cuda_stream
             check(lib.tdanet_backward(C.byref(self.cfg), C.byref(weights), C.byref(grad_weights), wav.data_ptr(),

@@ -26,7 +26,12 @@ class _SeparateFn(torch.autograd.Function):
         ctx.model, ctx.names = model, names
         ctx.save_for_backward(wav, *params)
         model._sync_dropout()
-        return model._engine.forward_train(model._weights(), wav, model.attn_group)
+        est = model._engine.forward_train(model._weights(), wav, model.attn_group)
+        # the activations live in the engine's per-device training workspace: remember which call wrote them, so
+        # that backward() raises if another grad-mode forward (or a train()/eval() switch) came in between
+        ctx.generation = model._engine.train_generation(wav.device)
+        ctx.attn_group = model.attn_group
+        return est
 
     @staticmethod
     def backward(ctx, d_est):
@@ -40,7 +45,8 @@ class _SeparateFn(torch.autograd.Function):
             views[n] = flat[off:off + p.numel()].view(p.shape)
             off += s
         gw = model._engine.pack(views, optional=True)
-        model._engine.backward(model._weights(), gw, wav, d_est.contiguous().float(), model.attn_group)
+        model._engine.backward(model._weights(), gw, wav, d_est.contiguous().float(), ctx.attn_group,
+                               generation=ctx.generation)
         dead = model._unused_parameter_names()
         grads = tuple(None if (n in dead or not p.requires_grad) else views[n] for n, p in zip(names, params))
         return (None, None, None) + grads

@@ -87,6 +87,25 @@ class TrainingStep:
         self.sqnorm = torch.zeros(2, dtype=torch.float64, device=dev)
         self._w = self._gw = None
         self._graph = None
+        self._graph_shapes = None
+        model.engine.on_train_workspace_realloc(self._drop_graph)
+        self.broadcast_state()
+
+    def _drop_graph(self, device=None) -> None:
+        """The captured graph bakes the training-workspace pointer in; the engine calls this before it replaces the
+        workspace (a later eager step with a larger batch), so a stale replay can never write to freed memory."""
+        self._graph = None
+        self._graph_shapes = None
+
+    def broadcast_state(self, src: int = 0) -> None:
+        """What DistributedDataParallel's constructor does in the reference run (Lightning DDP, audio_train.py:187-197):
+        every rank starts from rank `src`'s parameters - here also its Adam moments and step counter, so a checkpoint
+        loaded on one rank resumes identically everywhere.  No-op in a single process."""
+        if self._world() <= 1:
+            return
+        for t in (self.params.flat, self.exp_avg, self.exp_avg_sq, self.step_count):
+            dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
+                           group=self.group)
 
     # ------------------------------------------------------------------ pieces
     def _world(self) -> int:
@@ -158,10 +177,12 @@ class TrainingStep:
         self._graph = g
 
     def step_captured(self, mixtures: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        if self._graph is None:
-            self.capture(mixtures, targets)
         if mixtures.ndim == 3:
             mixtures = mixtures.squeeze(1)
+        shapes = (tuple(mixtures.shape), tuple(targets.shape), self.model.training, self.model.attn_group)
+        if self._graph is None or self._graph_shapes != shapes:
+            self.capture(mixtures, targets)       # first call, new batch shape / mode, or the workspace moved
+            self._graph_shapes = shapes
         self._static_mix.copy_(mixtures, non_blocking=True)
         self._static_tgt.copy_(targets, non_blocking=True)
         self._graph.replay()
@@ -200,6 +221,7 @@ class TrainingStep:
             self.load_optimizer_state_dict(ckpt["optimizer_states"][0])
         for s, st in zip(schedulers, ckpt.get("lr_schedulers", [])):
             s.load_state_dict(st)
+        self.broadcast_state()
 
     def grad_norm(self) -> float:
         """Global L2 norm of the gradient of the last step (after the all-reduce, before scaling); syncs."""

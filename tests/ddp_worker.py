@@ -1,7 +1,9 @@
-"""2+-rank check of the batch-sharded training step (run under torch.distributed.run, one rank per GPU):
-the all-reduced gradient equals the single-process gradient of the concatenated batch (attention grouped per
-shard, like reference DDP where every rank attends within its own batch), parameters stay identical across
-ranks after optimiser steps, and the loss goes down."""
+"""2+-rank check of the batch-sharded training step (run under torch.distributed.run, one rank per GPU, by
+tests/test_gpu_ddp.py): every rank builds its model from a DIFFERENT seed - TrainingStep must broadcast rank 0's
+parameters like DistributedDataParallel's constructor does in the reference run (audio_train.py:187-197 never
+seeds) - then the all-reduced gradient equals the single-process gradient of the concatenated batch (attention
+grouped per shard, like reference DDP where every rank attends within its own batch), parameters stay identical
+across ranks after optimiser steps, and the loss goes down."""
 import os
 import sys
 
@@ -21,8 +23,8 @@ def main():
     B, T = 4, 4000
     L = look2hear.losses
 
-    def make():
-        torch.manual_seed(0)
+    def make(seed):
+        torch.manual_seed(seed)
         m = look2hear.models.TDANetBest(sample_rate=8000, **kw).to(dev).train()
         m.gemm_mode = "fp32"
         m.dropout = m.drop_path = 0.0    # the deterministic step: 1-GPU and 2-GPU gradients are comparable
@@ -33,7 +35,12 @@ def main():
     mix_all = tgt_all.sum(1)
     tgt, mix = tgt_all[rank * B:(rank + 1) * B].to(dev), mix_all[rank * B:(rank + 1) * B].to(dev)
     loss_fn = L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True)
-    ts = look2hear.system.TrainingStep(make(), loss_fn, lr=1e-3, clip_grad_norm=5.0)
+    ts = look2hear.system.TrainingStep(make(1000 + rank), loss_fn, lr=1e-3, clip_grad_norm=5.0)
+    # the constructor broadcast rank 0's parameters: every rank now holds the seed-1000 model
+    p0 = ts.params.flat.clone()
+    dist.broadcast(p0, src=0)
+    started_equal = torch.tensor([int(bool((p0 == ts.params.flat).all().item()))], device=dev)
+    dist.all_reduce(started_equal, op=dist.ReduceOp.MIN)
     # ---- gradient of one step against the single-process run on the whole batch
     ts.params.zero_grad()
     loss = ts.forward_backward(mix, tgt)
@@ -44,7 +51,7 @@ def main():
     loss_mean /= world
     ok = True
     if rank == 0:
-        m1 = make()
+        m1 = make(1000)
         m1.attn_group = B                      # every shard attends within itself
         ts1 = look2hear.system.TrainingStep(m1, loss_fn, lr=1e-3, clip_grad_norm=5.0, process_group=None)
         ts1._world = lambda: 1
@@ -53,7 +60,8 @@ def main():
         rel = ((grad_ddp - ts1.params.grad).norm() / ts1.params.grad.norm()).item()
         dl = abs(loss1.item() - loss_mean.item())
         print(f"[ddp_check] world {world}: all-reduced gradient vs single process rel-L2 {rel:.2e}, loss diff {dl:.2e}")
-        ok = ok and rel < 1e-4 and dl < 1e-4
+        print(f"[ddp_check] ranks seeded differently start from rank 0's parameters: {bool(started_equal.item())}")
+        ok = ok and rel < 1e-4 and dl < 1e-4 and bool(started_equal.item())
     # ---- a few optimiser steps: replicas stay bit-identical, loss decreases
     losses = []
     for _ in range(10):

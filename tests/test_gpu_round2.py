@@ -1,0 +1,204 @@
+"""Round-2 regression tests on the GPU: ownership of the training workspace and of packed weight structs, graph
+invalidation, the reference's default encoder window, and the per-utterance metrics CSV."""
+import csv
+import gc
+
+import pytest
+import torch
+
+import tdanet_b200.look2hear as look2hear
+from conftest import max_rel
+from oracle import tdanet_oracle as O
+from tdanet_b200 import _lib
+from test_backward_emu import CASES, SR, _model_sd
+from test_gpu_train import _model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PE = "sm.unet.globalatt.attn.pos_enc.pe"
+
+
+def test_backward_of_an_overwritten_forward_raises():
+    """Two grad-mode model(x) calls before .backward(): the first graph's activations are gone (one training
+    workspace per device), so its backward must raise instead of returning the second call's gradients."""
+    kw = CASES["depth4"]
+    m = _model(kw, _model_sd(kw)).train()
+    g = torch.Generator().manual_seed(2)
+    x1, x2 = (torch.randn(2, 1, 1500, generator=g) * 0.1).to(DEV), (torch.randn(2, 1, 1500, generator=g) * 0.1).to(DEV)
+    y1 = m(x1)
+    y2 = m(x2)
+    with pytest.raises(_lib.TdanetError, match="overwrote"):
+        y1.sum().backward()
+    y2.sum().backward()                         # the latest forward is still consistent
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    # a train()/eval() switch between forward and backward changes the dropout configuration: refused as well
+    m.dropout = m.drop_path = 0.1
+    y3 = m(x1)
+    m.eval()
+    m._sync_dropout()
+    with pytest.raises(_lib.TdanetError, match="workspace was written with"):
+        y3.sum().backward()
+
+
+def test_autograd_path_keeps_no_gradient_buffers():
+    """`loss.backward()` + torch.optim (INTEGRATION.md pattern (a)): the flat gradient buffer of a backward is owned
+    by that backward, not by the engine - memory stays flat over many steps (~9 MB leaked per step)."""
+    kw = CASES["depth4"]
+    m = _model(kw, _model_sd(kw)).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    x = (torch.randn(2, 1, 1500, generator=torch.Generator().manual_seed(4)) * 0.1).to(DEV)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        m(x).pow(2).mean().backward()
+        opt.step()
+
+    for _ in range(3):
+        step()
+    gc.collect()
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_allocated()
+    for _ in range(40):
+        step()
+    gc.collect()
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated() - before < (1 << 20), (before, torch.cuda.memory_allocated())
+    assert not hasattr(m.engine, "_keep")
+
+
+def test_captured_step_survives_a_larger_eager_step():
+    """TrainingStep's CUDA graph bakes the training-workspace pointer in; an eager step with a larger batch
+    reallocates the workspace, after which the captured step must re-capture (not replay into freed memory)."""
+    kw = CASES["depth4"]
+    L = look2hear.losses
+    loss_fn = L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True)
+    g = torch.Generator().manual_seed(8)
+    tgt2 = (torch.randn(2, 2, 2000, generator=g) * 0.1).to(DEV)
+    tgt6 = (torch.randn(6, 2, 2000, generator=g) * 0.1).to(DEV)
+
+    def run(captured):
+        m = _model(kw, _model_sd(kw)).train()
+        m.gemm_mode = "fp32"
+        ts = look2hear.system.TrainingStep(m, loss_fn, lr=1e-3)
+        step2 = ts.step_captured if captured else ts.step
+        out = [step2(tgt2.sum(1), tgt2).item()]
+        g0 = ts._graph
+        out.append(ts.step(tgt6.sum(1), tgt6).item())          # larger batch: the workspace moves
+        if captured:
+            assert ts._graph is None and g0 is not None         # dropped by the engine's realloc hook
+        out.append(step2(tgt2.sum(1), tgt2).item())             # re-captured against the new workspace
+        out.append(step2(tgt2.sum(1), tgt2).item())
+        torch.cuda.synchronize()
+        return out, ts.params.flat.clone()
+
+    (la, pa), (lb, pb) = run(True), run(False)
+    assert all(abs(a - b) < 1e-4 * max(1.0, abs(b)) for a, b in zip(la, lb)), (la, lb)
+    assert (pa - pb).abs().max().item() < 1e-3
+    # a different batch shape through step_captured re-captures instead of replaying the old shape
+    m = _model(kw, _model_sd(kw)).train()
+    ts = look2hear.system.TrainingStep(m, loss_fn, lr=1e-3)
+    a = ts.step_captured(tgt6.sum(1), tgt6)
+    b = ts.step_captured(tgt2.sum(1), tgt2)
+    assert torch.isfinite(a).all() and torch.isfinite(b).all()
+
+
+@pytest.mark.parametrize("variant", ["best", "fork"])
+def test_reference_default_encoder_window(variant):
+    """`TDANetBest()` with the reference's default `enc_kernel_size=21` at 16 kHz: window 336, hop 84, 169 basis
+    signals (TDANet_best.py:403-424) - forward and gradients (the decoder used to reject hops > 64)."""
+    kw = dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4, enc_kernel_size=21, num_sources=2)
+    cls = {"best": "TDANetBest", "fork": "TDANet"}[variant]
+    torch.manual_seed(3)
+    m = getattr(look2hear.models, cls)(sample_rate=16000, **kw)
+    assert m.enc_kernel_size == 336 and m.enc_num_basis == 169
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 1, 9000, generator=g) * 0.1
+    d = torch.randn(3, 2, 9000, generator=g)
+    cfg = O.OracleConfig(variant=variant, sample_rate=16000, **kw)
+    with torch.no_grad():
+        ref = O.forward(sd, x, cfg)
+    m = m.to(DEV).eval()
+    for mode, tol in (("fp32", 5e-5), ("tf32", 1e-3)):
+        m.gemm_mode = mode
+        with torch.no_grad():
+            assert max_rel(m(x.to(DEV)).cpu(), ref) < tol, mode
+    m.gemm_mode = "fp32"
+    m.train()
+    m.dropout = m.drop_path = 0.0
+    (m(x.to(DEV)) * d.to(DEV)).sum().backward()
+    sd64 = {k: v.double().requires_grad_(k != PE) for k, v in sd.items()}
+    (O.forward(sd64, x.double(), cfg) * d.double()).sum().backward()
+    for k, p in m.named_parameters():
+        r = sd64[k].grad
+        if r is None:
+            assert p.grad is None, k
+            continue
+        assert max_rel(p.grad.cpu(), r) < 2e-4, k
+
+
+def test_metrics_tracker_csv_rows_match_the_oracle(tmp_path):
+    """look2hear.metrics.MetricsTracker (metrics/wrapper.py:24-90): one CSV row per utterance + avg / std rows;
+    SI-SNR = -PIT(pairwise_neg_sisdr)(est, clean), SI-SNRi against the mixture repeated for every source."""
+    g = torch.Generator().manual_seed(21)
+    path = tmp_path / "metrics.csv"
+    tracker = look2hear.metrics.MetricsTracker(str(path))
+    want = []
+    for i in range(5):
+        T = 4000 + 333 * i
+        clean = torch.randn(2, T, generator=g) * 0.1
+        mix = clean.sum(0)
+        est = clean.flip(0) * (1.0 + 0.1 * i) + 0.02 * (i + 1) * torch.randn(2, T, generator=g)   # swapped on purpose
+        row = tracker(mix.to(DEV), clean.to(DEV), est.to(DEV), f"utt{i}")
+        s = -O.pit_loss(est.unsqueeze(0).double(), clean.unsqueeze(0).double(), "sisdr", False).item()
+        base = -O.pit_loss(torch.stack([mix, mix]).unsqueeze(0).double(), clean.unsqueeze(0).double(), "sisdr", False).item()
+        want.append((f"utt{i}", s, s - base))
+        assert row["snt_id"] == f"utt{i}"
+    upd = tracker.update()
+    rows_final = tracker.final()
+    with open(path) as f:
+        rows = list(csv.DictReader(f))
+    assert [r["snt_id"] for r in rows] == [w[0] for w in want] + ["avg", "std"]
+    assert list(rows[0].keys()) == ["snt_id", "sdr", "sdr_i", "si-snr", "si-snr_i"]
+    for r, (_, s, si) in zip(rows, want):
+        assert abs(float(r["si-snr"]) - s) < 2e-3 and abs(float(r["si-snr_i"]) - si) < 2e-3, (r, s, si)
+    import numpy as np
+    s_all, si_all = np.array([w[1] for w in want]), np.array([w[2] for w in want])
+    assert abs(float(rows[5]["si-snr"]) - s_all.mean()) < 2e-3 and abs(float(rows[5]["si-snr_i"]) - si_all.mean()) < 2e-3
+    assert abs(float(rows[6]["si-snr"]) - s_all.std()) < 2e-3 and abs(float(rows[6]["si-snr_i"]) - si_all.std()) < 2e-3
+    assert abs(upd["si-snr_i"] - si_all.mean()) < 2e-3
+    assert rows_final[0]["snt_id"] == "avg" and rows_final[1]["snt_id"] == "std"
+
+
+def test_two_host_threads_share_a_device():
+    """Forward calls from two host threads on their own streams (the library's side streams / event rings are
+    per-device state guarded by a lock): both results equal the single-threaded ones."""
+    import threading
+    kw = CASES["depth4"]
+    sd = _model_sd(kw)
+    models = [_model(kw, sd).eval() for _ in range(2)]
+    xs = [(torch.randn(3, 1, 3000, generator=torch.Generator().manual_seed(30 + i)) * 0.1).to(DEV) for i in range(2)]
+    for m in models:
+        m.gemm_mode = "fp32"
+    with torch.no_grad():
+        want = [m(x).clone() for m, x in zip(models, xs)]
+    torch.cuda.synchronize()
+    got, errs = [None, None], []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream(DEV)
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(20):
+                    y = models[i](xs[i])
+                s.synchronize()
+            got[i] = y
+        except Exception as e:       # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for a, b in zip(got, want):
+        assert max_rel(a, b) < 1e-5
