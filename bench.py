@@ -540,22 +540,24 @@ def run_reference(args):
         O.forward(sd, x1, cfg)
         t1 = time.perf_counter() - t0
     # The step is the full 64-mixture batch of the workload (batch-axis attention makes a smaller batch a different
-    # attention problem); what is bounded is the number of warm-up steps: the run is kept under ~5 minutes.
+    # attention problem, and the CPU is ~3x slower per mixture at batch 64 than at batch 8).  What is bounded is the
+    # number of steps: one warm-up step is timed, then as many of the requested steps as fit in ~4 minutes (at least 3).
     bs = int(max(1, min(args.ref_batch, args.batch)))
-    est_step = t1 * bs * 0.55            # a batch amortises the per-op overhead of the 1-mixture probe
-    warm = args.warmup
-    while warm > 1 and (args.steps + warm) * est_step > 280.0:
-        warm -= 1
-    while bs > 8 and (args.steps + warm) * (t1 * bs * 0.55) > 420.0:
-        bs //= 2
     x = torch.randn(bs, 1, N_SAMPLES, generator=torch.Generator().manual_seed(1234)) * 0.1
     with torch.no_grad():
-        for _ in range(warm):
-            O.forward(sd, x, cfg)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        O.forward(sd, x, cfg)
+        t_step = time.perf_counter() - t0
+        warm = 1
+        while warm < args.warmup and (warm + 1 + args.steps) * t_step < 120.0:
+            O.forward(sd, x, cfg)
+            warm += 1
+        steps = int(max(min(3, args.steps), min(args.steps, 240.0 // max(t_step, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(steps):
             O.forward(sd, x, cfg)
         dt = time.perf_counter() - t0
+    requested_steps, args.steps = args.steps, steps
     value = bs * (N_SAMPLES / SR) * args.steps / dt
     sample = f"{bs} x 2 s mixtures per step (the workload's batch is {args.batch}), {args.steps} steps after {warm} warm-up"
     print(json.dumps({
@@ -563,7 +565,7 @@ def run_reference(args):
         "warmup": warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": common_config(args.variant, args.enc_ms, args.batch),
-        "impl_config": {"batch_per_step": bs,
+        "impl_config": {"batch_per_step": bs, "steps_requested": requested_steps,
                         "note": "the reference is pure PyTorch and cannot travel to the GPU box (sources may not be "
                                 "copied); this arm times oracle/tdanet_oracle.py, the CPU restatement pinned to the "
                                 "reference by tests/golden, on all host threads"},

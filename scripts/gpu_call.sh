@@ -1,0 +1,60 @@
+#!/bin/bash
+# One gpurun call of round 2: parity tests, bench, TF32 peak, ncu evidence.  Usage (from the repo root, on the box):
+#   bash scripts/gpu_call.sh <tag> [tests] [bench] [peak] [ncu_gemm] [ncu_list] [ncu_train] [refarm]
+# Every artefact lands in gpurun_out/<tag>_*.
+tag=$1; shift
+out=gpurun_out
+mkdir -p $out
+for what in "$@"; do
+  case $what in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -q -s > $out/${tag}_gpu_tests.log 2>&1
+      echo "tests rc=$? $(tail -1 $out/${tag}_gpu_tests.log)";;
+    tests_new)
+      timeout 1500 python -m pytest tests/test_gpu_headline.py tests/test_gpu_round2.py -m gpu -q -s > $out/${tag}_gpu_tests_new.log 2>&1
+      echo "tests_new rc=$? $(tail -1 $out/${tag}_gpu_tests_new.log)";;
+    bench)
+      timeout 900 python bench.py --steps 20 --warmup 5 --detail-out $out/${tag}_bench_detail.json > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+      echo "bench rc=$?"; cat $out/${tag}_bench.json;;
+    bench_quick)
+      timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu --skip-eager --skip-longform --skip-2ms --detail-out $out/${tag}_benchq_detail.json > $out/${tag}_benchq.json 2> $out/${tag}_benchq.err
+      echo "bench_quick rc=$?"; cat $out/${tag}_benchq.json;;
+    bench_bf16)
+      timeout 600 python bench.py --steps 20 --warmup 5 --act-dtype bf16 --skip-cpu --skip-eager --skip-longform --skip-train --detail-out $out/${tag}_bf16_detail.json > $out/${tag}_bf16.json 2> $out/${tag}_bf16.err
+      echo "bench_bf16 rc=$?"; cat $out/${tag}_bf16.json;;
+    bench_fork)
+      timeout 600 python bench.py --steps 20 --warmup 5 --variant fork --skip-cpu --skip-eager --skip-longform --detail-out $out/${tag}_fork_detail.json > $out/${tag}_fork.json 2> $out/${tag}_fork.err
+      echo "bench_fork rc=$?"; cat $out/${tag}_fork.json;;
+    refarm)
+      timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_refarm.json 2> $out/${tag}_refarm.err
+      echo "refarm rc=$?"; cat $out/${tag}_refarm.json;;
+    peak)
+      python scripts/measure_tf32_peak.py $out/${tag}_tf32_peak.json;;
+    ncu_gemm)
+      # one block's worth of tcgen05 GEMM launches (proj, in_proj, out_proj, fc1, fc2, res_conv), third block
+      cmd="python bench.py --steps 1 --warmup 3 --no-graph --skip-train --skip-longform --skip-cpu --skip-eager --skip-2ms --detail-out $out/${tag}_ncu_dummy.json"
+      $cmd > $out/${tag}_ncu_gemm_plain.log 2>&1 &&
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 12 -c 6 -f -o $out/${tag}_gemm $cmd > $out/${tag}_ncu_gemm.log 2>&1
+      echo "ncu_gemm rc=$?";;
+    ncu_list)
+      cmd="python bench.py --steps 1 --warmup 3 --no-graph --skip-train --skip-longform --skip-cpu --skip-eager --skip-2ms --detail-out $out/${tag}_ncu_dummy.json"
+      $cmd > $out/${tag}_ncu_list_plain.log 2>&1 &&
+      timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1900 -c 480 --csv --log-file $out/${tag}_launches.csv $cmd > $out/${tag}_ncu_list.log 2>&1
+      echo "ncu_list rc=$?";;
+    ncu_train)
+      cmd="python bench.py --train-only --steps 1 --warmup 3 --no-graph --skip-cpu"
+      $cmd > $out/${tag}_ncu_train_plain.log 2>&1 &&
+      timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 8000 -c 2000 --csv --log-file $out/${tag}_train_launches.csv $cmd > $out/${tag}_ncu_train.log 2>&1
+      echo "ncu_train rc=$?";;
+    ab_*)
+      # A/B of an environment knob on the quick bench: ab_NAME=VALUE (e.g. ab_TDANET_LASTREAM_V=2)
+      kv=${what#ab_}
+      env $kv timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu --skip-eager --skip-longform --skip-2ms --detail-out $out/${tag}_${kv}_detail.json > $out/${tag}_${kv}.json 2> $out/${tag}_${kv}.err
+      echo "ab $kv rc=$?"; python scripts/show_line.py $out/${tag}_${kv}.json;;
+    abinf_*)
+      kv=${what#abinf_}
+      env $kv timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu --skip-eager --skip-longform --skip-2ms --skip-train --detail-out $out/${tag}_${kv}_detail.json > $out/${tag}_${kv}.json 2> $out/${tag}_${kv}.err
+      echo "abinf $kv rc=$?"; python scripts/show_line.py $out/${tag}_${kv}.json;;
+    *) echo "unknown step $what";;
+  esac
+done

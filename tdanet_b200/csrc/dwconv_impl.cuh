@@ -953,33 +953,71 @@ __device__ __forceinline__ vf<4> lds4(const float* p) {
   return r;
 }
 
+// the same for V channels per thread: fp32 rows of the global feature (16 / 8 bytes), activation rows (fp32: 16 / 8
+// bytes, bf16: 8 / 4 bytes)
+template <int V>
+__device__ __forceinline__ void cp_async_f32(float* dst, const float* src, bool valid) {
+  if constexpr (V == 4) {
+    cp_async16(dst, src, valid);
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+                 "r"(valid ? 8 : 0)
+                 : "memory");
+  }
+}
+template <int V>
+__device__ __forceinline__ void cp_async_actv(ACT_T* dst, const ACT_T* src, bool valid) {
+  if constexpr (V == 4) {
+    cp_async_act(dst, src, valid);
+  } else if constexpr (sizeof(ACT_T) == 4) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+                 "r"(valid ? 8 : 0)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+                 "r"(valid ? 4 : 0)
+                 : "memory");
+  }
+}
+template <int V>
+__device__ __forceinline__ vf<V> ldsv(const float* p) {
+  if constexpr (V == 4) {
+    return lds4(p);
+  } else {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    vf<V> r;
+    r[0] = t.x; r[1] = t.y;
+    return r;
+  }
+}
+
 // ring stage s of this thread: ACT_T rows, then fp32 rows of the injected feature
 struct StageCol {
   ACT_T* act;
   float* g;
 };
-template <int AROWS, int GROWS>
+template <int AROWS, int GROWS, int V = 4>
 __device__ __forceinline__ StageCol stage_col(void* ring, int s, int colw) {
   // sizes in floats (an ACT_T row of colw elements is colw*sizeof(ACT_T)/4 floats; colw is a multiple of 4)
   const int act_f = AROWS * colw * (int)sizeof(ACT_T) / 4;
   const int stage_f = act_f + GROWS * colw;
   float* base = static_cast<float*>(ring) + s * stage_f;
-  return StageCol{reinterpret_cast<ACT_T*>(base) + threadIdx.x * 4, base + act_f + threadIdx.x * 4};
+  return StageCol{reinterpret_cast<ACT_T*>(base) + threadIdx.x * V, base + act_f + threadIdx.x * V};
 }
 template <int AROWS, int GROWS>
-static size_t ring_bytes(int threads) {
-  return 2 * ((size_t)AROWS * threads * 4 * sizeof(ACT_T) + (size_t)GROWS * threads * 4 * sizeof(float));
+static size_t ring_bytes(int threads, int V = 4) {
+  return 2 * ((size_t)AROWS * threads * V * sizeof(ACT_T) + (size_t)GROWS * threads * V * sizeof(float));
 }
 
 // CT: in_channels when it is the compile-time 512 of every reference configuration (row strides and
 // shared-memory offsets then fold into immediates), 0 = run-time
-template <int LKIND, bool EDGE, int CT>
+template <int LKIND, bool EDGE, int CT, int V>
 __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, int t0, int t1, void* ring,
                                                float* scratch, const int* jc, const int* jl) {
-  constexpr int V = 4;
   const int Ll = a.loc.L, Lg = a.glo.L, Lgg = a.loc.Lg;
   const int C = CT ? CT : a.C;
-  const int colw = CT ? CT : blockDim.x * V;
+  // CT != 0: 128 threads per CTA (the launcher guarantees it), so the column pitch is a compile-time constant too
+  const int colw = CT ? 128 * V : blockDim.x * V;
   const ACT_T* xl = reinterpret_cast<const ACT_T*>(a.loc.x) + (size_t)b * Ll * C + ch;
   const ACT_T* xg = reinterpret_cast<const ACT_T*>(a.glo.x) + (size_t)b * Lg * C + ch;
   const float* gg = a.loc.g + (size_t)b * Lgg * C + ch;
@@ -1000,27 +1038,27 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
   norm_coef<V>(a.nE, b, ch, sE, hE);
 
   auto issue = [&](int k) {
-    const StageCol st = stage_col<SAROWS, SGG>(ring, k & 1, colw);
+    const StageCol st = stage_col<SAROWS, SGG, V>(ring, k & 1, colw);
     const int t = t0 + k * SR;
 #pragma unroll
     for (int i = 0; i < SR; ++i) {
       const int row = t + 2 + i;
       const bool ok = !EDGE || row < Ll;
-      cp_async_act(st.act + i * colw, xl + (ok ? row : 0) * C, ok);
+      cp_async_actv<V>(st.act + i * colw, xl + (ok ? row : 0) * C, ok);
     }
     const int jlo = jc[t - t0];
 #pragma unroll
     for (int i = 0; i < SGR; ++i) {
       const int row = jlo - 2 + i;
       const bool ok = !EDGE || (row >= 0 && row < Lg);
-      cp_async_act(st.act + (SR + i) * colw, xg + (ok ? row : 0) * C, ok);
+      cp_async_actv<V>(st.act + (SR + i) * colw, xg + (ok ? row : 0) * C, ok);
     }
     const int j0 = jl[t - t0 + 4];
 #pragma unroll
     for (int i = 0; i < SGG; ++i) {
       const int row = j0 + i;
       const bool ok = row < Lgg;
-      cp_async16(st.g + i * colw, gg + (ok ? row : 0) * C, ok);
+      cp_async_f32<V>(st.g + i * colw, gg + (ok ? row : 0) * C, ok);
     }
   };
 
@@ -1030,12 +1068,12 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
   const int nchunks = (t1 - t0 + SR - 1) / SR;
   vf<V> gpre[4];
   {
-    const StageCol pre = stage_col<SAROWS, SGG>(ring, 1, colw);  // unused until chunk 1 is issued
+    const StageCol pre = stage_col<SAROWS, SGG, V>(ring, 1, colw);  // unused until chunk 1 is issued
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = t0 - 2 + i;
       const bool ok = !EDGE || (t >= 0 && t < Ll);
-      cp_async_act(pre.act + i * colw, xl + (ok ? t : 0) * C, ok);
+      cp_async_actv<V>(pre.act + i * colw, xl + (ok ? t : 0) * C, ok);
       gpre[i] = vload<V>(gg + jl[i] * C);
     }
   }
@@ -1043,7 +1081,7 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   {
-    const StageCol pre = stage_col<SAROWS, SGG>(ring, 1, colw);
+    const StageCol pre = stage_col<SAROWS, SGG, V>(ring, 1, colw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = t0 - 2 + i;
@@ -1055,7 +1093,7 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
     if (k + 1 < nchunks) issue(k + 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
-    const StageCol st = stage_col<SAROWS, SGG>(ring, k & 1, colw);
+    const StageCol st = stage_col<SAROWS, SGG, V>(ring, k & 1, colw);
     const int t = t0 + k * SR;
     const int jlo = jc[t - t0];
     {
@@ -1087,7 +1125,7 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
         xr[4 + i] = vzero<V>();
       } else {
         const int j = jl[t - t0 + 4 + i];
-        xr[4 + i] = inject(alds<V>(st.act + i * colw), lds4(st.g + (j - j0) * colw), j);
+        xr[4 + i] = inject(alds<V>(st.act + i * colw), ldsv<V>(st.g + (j - j0) * colw), j);
       }
     }
 #pragma unroll
@@ -1095,7 +1133,7 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
       if (!EDGE || t + r < t1) {
         const vf<V> cl = conv5<V>(wl, xr[r], xr[r + 1], xr[r + 2], xr[r + 3], xr[r + 4]);
         const int j = jc[t + r - t0];
-        const vf<V> ga = lds4(mine + (2 * (j - jlo)) * colw), ge = lds4(mine + (2 * (j - jlo) + 1) * colw);
+        const vf<V> ga = ldsv<V>(mine + (2 * (j - jlo)) * colw), ge = ldsv<V>(mine + (2 * (j - jlo) + 1) * colw);
         vf<V> y = vfma<V>(vfma<V>(sL, cl, hL), ga, ge);
         if (a.round_out) vround_tf32<V>(y);
         astore<V>(outp + (t + r) * C, y);
@@ -1104,17 +1142,19 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
   }
 }
 
-template <int LKIND, int CT>
-__global__ void __launch_bounds__(128, 2) la_stream_kernel(LaArgs a, int rows_per_cta) {
+// V = 4: 245 registers, two CTAs of 128 threads per SM (8 warps: every scheduler has two warps to cover the dependent-issue
+// stalls of this arithmetic-heavy loop - issue slots were 38 % busy at 0.65 of the HBM peak).  V = 2: half the
+// per-thread state, four CTAs per SM (16 warps), a CTA covers 256 channels.
+template <int LKIND, int CT, int V>
+__global__ void __launch_bounds__(128, V == 4 ? 2 : 4) la_stream_kernel(LaArgs a, int rows_per_cta) {
   grid_dep_wait();
   extern __shared__ __align__(16) float la_smem[];
-  constexpr int V = 4;
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const int Ll = a.loc.L, Lg = a.glo.L;
   const int t0 = blockIdx.x * rows_per_cta;
   const int t1 = min(t0 + rows_per_cta, Ll);
-  const int colw = CT ? CT : blockDim.x * V;
+  const int colw = CT ? 128 * V : blockDim.x * V;
   // [ring: 2 stages][scratch 2*SGC rows fp32][tables]; plain pointer arithmetic on the __shared__ array so
   // that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
   void* ring = la_smem;
@@ -1128,8 +1168,8 @@ __global__ void __launch_bounds__(128, 2) la_stream_kernel(LaArgs a, int rows_pe
   const int g_first = nearest_src(t0, a.scale, Lg) - 2;
   const int g_last = nearest_src(t1 - 1, a.scale, Lg) + SGR;
   const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0 && g_first >= 0 && g_last < Lg;
-  if (interior) la_stream_body<LKIND, false, CT>(a, b, ch, t0, t1, ring, scratch, jc, jl);
-  else la_stream_body<LKIND, true, CT>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+  if (interior) la_stream_body<LKIND, false, CT, V>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+  else la_stream_body<LKIND, true, CT, V>(a, b, ch, t0, t1, ring, scratch, jc, jl);
 }
 
 // the streaming kernel applies when 8 output rows see <= 5 global centres and <= 3 rows of the
@@ -1139,31 +1179,40 @@ static bool la_stream_applies(const LaArgs& a) {
          7.0 * a.glo.L / a.loc.L <= 3.99 && 7.0 * a.loc.Lg / a.loc.L <= 1.99 && a.C % 4 == 0;
 }
 
-template <int LKIND>
-static int launch_la_stream(const LaArgs& a, cudaStream_t st) {
-  int threads = a.C / 4;
+template <int LKIND, int V>
+static int launch_la_stream_v(const LaArgs& a, cudaStream_t st) {
+  int threads = a.C / V;
   if (threads > 128) threads = 128;
   if (threads < 32) threads = 32;
-  const int ctiles = cdiv(a.C / 4, threads);
+  const int ctiles = cdiv(a.C / V, threads);
   int rows, tiles;
   static const long ls_target = getenv("TDANET_LASTREAM_TARGET") ? atol(getenv("TDANET_LASTREAM_TARGET")) : 148L * 2 * 4;
   static const int ls_cap = getenv("TDANET_LASTREAM_CAP") ? atoi(getenv("TDANET_LASTREAM_CAP")) : 128;
   pick_tiling(a.B, a.loc.L, ctiles, SR, &rows, &tiles, ls_target, ls_cap);
   dim3 grid(tiles, ctiles, a.B);
-  const size_t smem = (size_t)2 * SGC * threads * 4 * sizeof(float) + (size_t)(2 * rows + 4) * sizeof(int) +
-                      ring_bytes<SAROWS, SGG>(threads);
+  const size_t smem = (size_t)2 * SGC * threads * V * sizeof(float) + (size_t)(2 * rows + 4) * sizeof(int) +
+                      ring_bytes<SAROWS, SGG>(threads, V);
   static bool attr_set = false;
   if (!attr_set) {
-    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 0, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 512, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     attr_set = true;
   }
   if (a.C == 512 && threads == 128) {
-    TD_LAUNCH((la_stream_kernel<LKIND, 512>), grid, threads, smem, st, a, rows);
+    TD_LAUNCH((la_stream_kernel<LKIND, 512, V>), grid, threads, smem, st, a, rows);
   } else {
-    TD_LAUNCH((la_stream_kernel<LKIND, 0>), grid, threads, smem, st, a, rows);
+    TD_LAUNCH((la_stream_kernel<LKIND, 0, V>), grid, threads, smem, st, a, rows);
   }
   return 0;
+}
+
+template <int LKIND>
+static int launch_la_stream(const LaArgs& a, cudaStream_t st) {
+  // channels per thread: 2 (four CTAs per SM) unless the channel count has no 2-channel tiling; TDANET_LASTREAM_V=4
+  // selects the two-CTA form for A/B measurements
+  static const int v_knob = getenv("TDANET_LASTREAM_V") ? atoi(getenv("TDANET_LASTREAM_V")) : 4;
+  if (v_knob == 2 && a.C % 2 == 0) return launch_la_stream_v<LKIND, 2>(a, st);
+  return launch_la_stream_v<LKIND, 4>(a, st);
 }
 
 // ----------------------------------------------------------------------------- LA local statistics, one launch

@@ -10,15 +10,19 @@ namespace td {
 // ----------------------------------------------------------------------------- encoder
 // out[b, t, n] = sum_j w_k[n', j] * xp[t*S + j - ks_k/2], xp = zero-padded input of pad_input.
 // The padding is never materialised: xp[p] = wav[p - front_pad] inside [0, T), else 0.
-__global__ void __launch_bounds__(256) encoder_kernel(EncArgs a, int rows_per_cta, int ksmax) {
+// Wide windows (the reference's default enc_kernel_size = 21 ms: K = 336, 169 basis signals = 228 KB of weights) do
+// not fit one CTA's shared memory: blockIdx.y then walks chunks of `chunk` output channels (single-conv encoders only).
+__global__ void __launch_bounds__(256) encoder_kernel(EncArgs a, int rows_per_cta, int ksmax, int chunk) {
   grid_dep_wait();
   extern __shared__ float sm[];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * rows_per_cta;
   const int rows = min(rows_per_cta, a.L0 - t0);
+  const int n_lo = blockIdx.y * chunk;              // first output channel of this CTA
+  const int nc = min(chunk, a.Nb - n_lo);           // == Nb when gridDim.y == 1
   const int span = (rows_per_cta - 1) * a.S + ksmax;
   float* xs = sm;         // [span]
-  float* ws = sm + span;  // per conv: [ch_per_conv][ks_k + 1]
+  float* ws = sm + span;  // per conv: [ch_per_conv][ks_k + 1]  (chunked: [nc][ks + 1] of conv 0)
   const int wstart = t0 * a.S - ksmax / 2;
   const float* wav = a.wav + (size_t)b * a.T;
   for (int i = threadIdx.x; i < span; i += blockDim.x) {
@@ -27,7 +31,12 @@ __global__ void __launch_bounds__(256) encoder_kernel(EncArgs a, int rows_per_ct
     xs[i] = (p >= 0 && p < a.Tp && q >= 0 && q < a.T) ? __ldg(wav + q) : 0.f;
   }
   int woff[TDANET_MAX_ENC];
-  {
+  if (gridDim.y > 1) {
+    const int ks = a.ks[0];
+    woff[0] = 0;
+    const float* w0 = a.w[0] + (size_t)n_lo * ks;
+    for (int i = threadIdx.x; i < nc * ks; i += blockDim.x) ws[(i / ks) * (ks + 1) + (i % ks)] = __ldg(w0 + i);
+  } else {
     int off = 0;
     for (int k = 0; k < a.nconv; ++k) {
       woff[k] = off;
@@ -40,15 +49,15 @@ __global__ void __launch_bounds__(256) encoder_kernel(EncArgs a, int rows_per_ct
   __syncthreads();
   float s1 = 0.f, s2 = 0.f;
   float* out = a.out + ((size_t)b * a.L0 + t0) * a.Nb;
-  for (int idx = threadIdx.x; idx < rows * a.Nb; idx += blockDim.x) {
-    const int r = idx / a.Nb, n = idx % a.Nb;
-    const int k = n / a.ch_per_conv, nn = n % a.ch_per_conv;
+  for (int idx = threadIdx.x; idx < rows * nc; idx += blockDim.x) {
+    const int r = idx / nc, n = idx % nc;            // n: channel inside the chunk
+    const int k = gridDim.y > 1 ? 0 : n / a.ch_per_conv, nn = gridDim.y > 1 ? n : n % a.ch_per_conv;
     const int ks = a.ks[k];
     const float* wr = ws + woff[k] + nn * (ks + 1);
     const float* xr = xs + r * a.S + (ksmax - ks) / 2;
     float acc = 0.f;
     for (int j = 0; j < ks; ++j) acc = fmaf(wr[j], xr[j], acc);
-    out[idx] = acc;
+    out[(size_t)r * a.Nb + n_lo + n] = acc;
     s1 += acc;
     s2 = fmaf(acc, acc, s2);
   }
@@ -69,12 +78,20 @@ int launch_encoder(const EncArgs& a, cudaStream_t st) {
     wfloats += a.ch_per_conv * (a.ks[k] + 1);
   }
   const int rows = 32;
-  const size_t smem = ((size_t)(rows - 1) * a.S + ksmax + wfloats) * sizeof(float);
+  const size_t xfloats = (size_t)(rows - 1) * a.S + ksmax;
+  size_t smem = (xfloats + wfloats) * sizeof(float);
+  int chunk = a.Nb, ychunks = 1;
+  if (smem > 96 * 1024 && a.nconv == 1) {   // chunks of output channels, about 64 KB of weights each
+    chunk = (int)((64 * 1024 / sizeof(float)) / (size_t)(ksmax + 1));
+    if (chunk < 1) chunk = 1;
+    ychunks = cdiv(a.Nb, chunk);
+    smem = (xfloats + (size_t)chunk * (ksmax + 1)) * sizeof(float);
+  }
   TD_REQUIRE(smem <= 200 * 1024, "encoder: %zu bytes of shared memory needed", smem);
   if (smem > 48 * 1024)
     TD_CUDA(cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(a.L0, rows), 1, a.B);
-  TD_LAUNCH(encoder_kernel, grid, 256, smem, st, a, rows, ksmax);
+  dim3 grid(cdiv(a.L0, rows), ychunks, a.B);
+  TD_LAUNCH(encoder_kernel, grid, 256, smem, st, a, rows, ksmax, chunk);
   return 0;
 }
 

@@ -175,6 +175,8 @@ class TrainingStep:
             self.params.zero_grad()
             self._static_loss = self.forward_backward(self._static_mix, self._static_tgt)
         self._graph = g
+        self._graph_shapes = (tuple(self._static_mix.shape), tuple(self._static_tgt.shape), self.model.training,
+                              self.model.attn_group)
 
     def step_captured(self, mixtures: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         if mixtures.ndim == 3:
@@ -182,7 +184,6 @@ class TrainingStep:
         shapes = (tuple(mixtures.shape), tuple(targets.shape), self.model.training, self.model.attn_group)
         if self._graph is None or self._graph_shapes != shapes:
             self.capture(mixtures, targets)       # first call, new batch shape / mode, or the workspace moved
-            self._graph_shapes = shapes
         self._static_mix.copy_(mixtures, non_blocking=True)
         self._static_tgt.copy_(targets, non_blocking=True)
         self._graph.replay()
