@@ -55,6 +55,14 @@ for what in "$@"; do
       kv=${what#abinf_}
       env $kv timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu --skip-eager --skip-longform --skip-2ms --skip-train --detail-out $out/${tag}_${kv}_detail.json > $out/${tag}_${kv}.json 2> $out/${tag}_${kv}.err
       echo "abinf $kv rc=$?"; python scripts/show_line.py $out/${tag}_${kv}.json;;
+    abtrain_*)
+      kv=${what#abtrain_}
+      env $kv timeout 600 python bench.py --train-only --steps 30 --warmup 5 --skip-cpu > $out/${tag}_train_${kv}.json 2> $out/${tag}_train_${kv}.err
+      echo "abtrain $kv rc=$?"; python -c "
+import json,sys
+d=json.loads(open('$out/${tag}_train_${kv}.json').read().strip().splitlines()[-1])
+print('train', d['value'], 'steps/s', d['ms_per_step'], 'ms; e2e', d['e2e']['value'], 'launches', d['gpu_launches_per_step'], 'step_frac', d.get('step_frac'))
+";;
     *) echo "unknown step $what";;
   esac
 done

@@ -79,8 +79,7 @@ struct FwdSide {
   }
 };
 static FwdSide g_fside[16];
-static std::mutex g_enqueue_mu[17];
-std::mutex& device_enqueue_mutex(int dev) { return g_enqueue_mu[(dev >= 0 && dev < 16) ? dev : 16]; }
+
 static thread_local FwdSide* t_fside = nullptr;  // set by forward() for the duration of the call
 
 static int gemm(const Ctx& x, GemmArgs& g, size_t aux_off) {

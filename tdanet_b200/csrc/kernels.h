@@ -8,7 +8,10 @@ namespace td {
 // The side streams / event rings of forward (engine.cu) and backward (backward.cu) are per-device library state; a
 // host thread holds this lock while it enqueues a forward or backward on that device, so two threads cannot
 // interleave their fork / join events (or pull each other's side-stream launches into a stream capture).
-std::mutex& device_enqueue_mutex(int dev);
+inline std::mutex& device_enqueue_mutex(int dev) {
+  static std::mutex mu[17];
+  return mu[(dev >= 0 && dev < 16) ? dev : 16];
+}
 
 // ------------------------------------------------------------------ sources (normalise-on-load)
 // How a consumer kernel reads one row of a [B, L, C] activation.

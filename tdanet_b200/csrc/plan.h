@@ -69,7 +69,8 @@ struct Plan {
       g_exp[TDANET_MAX_DEPTH];
   // LA backward temporaries, TDANET_LA_TEMP_SETS sets: the top-down steps alternate between sets 0 / 1 so that the
   // local-branch kernels of step i (side stream) overlap step i+1; the loc_glo_fus chain (side stream) owns set 2
-  size_t t_dloc[3], t_rawa[3], t_dact[3], t_demb[3], t_rawb[3], t_rawe[3];
+  size_t t_dloc[4], t_rawa[4], t_dact[4], t_demb[4], t_rawb[4], t_rawe[4];  // sets 0/1: top-down steps, 2/3: loc_glo_fus chains
+  size_t g_ga_out2;  // second accumulator of the global feature's gradient (the two loc_glo_fus streams), summed at the join
   size_t g_ga_out, g_fc2, g_ffn, g_fc1, g_ga_mid, g_attn_out, g_ctx, g_qkv, g_attn_in, g_ga_in;
   size_t att_p, att_ds, ln_rows;
   // replicated accumulators of the depthwise weight / bias gradients: [REP_COUNT][rep_floats]
@@ -320,7 +321,7 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     const int Lg = i == depth - 2 ? p.L[first_step_partner(depth)] : p.L[i + 1];
     Lg_max = Lg > Lg_max ? Lg : Lg_max;
   }
-  for (int s = 0; s < 3; ++s) {
+  for (int s = 0; s < 4; ++s) {
     p.t_dloc[s] = p.act(nullptr, L0, C);
     p.t_rawa[s] = p.act(nullptr, L0, C);
     p.t_dact[s] = p.act(nullptr, Lg_max, C);
@@ -329,6 +330,7 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     p.t_rawe[s] = p.act(nullptr, Lg_max, C);
   }
   p.g_ga_out = p.act("g_ga_out", Lb, C);
+  p.g_ga_out2 = p.act(nullptr, Lb, C);
   p.g_fc2 = p.act("g_fc2", Lb, C);
   p.g_ffn = p.act("g_ffn", Lb, 2 * C);
   p.g_fc1 = p.act("g_fc1", Lb, 2 * C);
