@@ -102,6 +102,7 @@ struct BCtx : Ctx {
   const tdanet_weights_t* g;  // gradient buffers, same layout as the weights
   std::vector<RepEntry>* reps;  // replicated accumulators handed out so far (shared by the per-block copies)
   SideStreams* side;
+  cudaEvent_t* w_pending;       // the previous block's weight-gradient GEMMs (stream `w`), not yet joined
   cudaStream_t main_st;         // the caller's stream (x.st is the stream launches currently go to)
   int tset = 0;                 // LA temporary set in use
   BCtx on(cudaStream_t s, int set) const { BCtx y = *this; y.st = s; y.tset = set; return y; }
@@ -653,6 +654,12 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
     float* d_glo = first ? x.at(p.g_fused[gi]) : x.at(p.g_exp[i + 1]);
     // this step's passes overwrite temporary set i % 2: the local branch of step i - 2 must have read it
     if (i >= 2) TD_CUDA(cudaStreamWaitEvent(x.st, local_done[i - 2], 0));
+    // ... and set 0 holds the G operand of the previous block's proj weight gradient, which is still running on `w`
+    // (joining it at the end of that block stalled the main stream for the ~17 us the wgrad outlasts dgrad_proj)
+    if (i == 0 && x.w_pending && *x.w_pending) {
+      TD_CUDA(cudaStreamWaitEvent(x.st, *x.w_pending, 0));
+      *x.w_pending = nullptr;
+    }
     // the first step adds into g_fused[gi], which the side stream wrote in step gi
     if (first && fused_written[gi]) TD_CUDA(cudaStreamWaitEvent(x.st, local_done[gi], 0));
     if (int e = la_backward(x.on(x.st, i & 1), 5, la, gw->last_layer[i], bplain(x.at(p.fused[i]), p.L[i]), SRC_PLAIN, glo, Lg,
@@ -760,11 +767,21 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
   { Tag t("bwd_gln_apply");
     if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_proj), x.at(p.proj), n_proj, x.at<double>(p.bs_proj)),
                                      x.at(p.t_dloc[0]), 0, B, L0, C, x.st)) return e; }  // LA temporaries are free by now
+  // every weight gradient enqueued so far is joined at the end of this block (they finished long ago); only the proj
+  // one, enqueued next, may outlast the block
+  cudaEvent_t w_before_proj = x.side->events[x.side->next++ % x.side->events.size()];
+  TD_CUDA(cudaEventRecord(w_before_proj, x.side->w));
   { Tag t("wgrad_proj"); if (int e = wgrad_side(x, x.at(p.t_dloc[0]), in, x.gp(gw->proj.w), x.gp(gw->proj.b), R0, C, cc)) return e; }
   Tag t("dgrad_proj");
   if (int e = dgrad(x, x.at(p.t_dloc[0]), p.wt_proj, p.auxt_proj, d_in, L0, cc, C, d_y)) return e;
-  // the weight-gradient GEMMs of this block must be done before the next block (or the caller) reuses their operands
-  return x.side->order(x.side->w, x.st);
+  // the weight-gradient GEMMs of this block must be done before the next block (or the caller) reuses their operands:
+  // the next block waits for this event before its first write to the LA temporaries, backward() after the last block
+  if (!x.w_pending) return x.side->order(x.side->w, x.st);
+  TD_CUDA(cudaStreamWaitEvent(x.st, w_before_proj, 0));
+  cudaEvent_t ev = x.side->events[x.side->next++ % x.side->events.size()];
+  TD_CUDA(cudaEventRecord(ev, x.side->w));
+  *x.w_pending = ev;
+  return 0;
 }
 
 static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const tdanet_weights_t* gw, const float* wav,
@@ -812,9 +829,12 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
   }
   // Recurrent, backwards: g_u[cur] holds d loss / d y_blk
   int cur = 0;
+  cudaEvent_t w_pending = nullptr;
+  static const bool defer_w = !(getenv("TDANET_WGRAD_JOIN") && atoi(getenv("TDANET_WGRAD_JOIN")) == 1);
   for (int blk = nb - 1; blk >= 0; --blk) {
     BCtx xb = x;
     xb.blk = blk;
+    xb.w_pending = defer_w ? &w_pending : nullptr;
     const float* in = blk == 0 ? x.at(p.x0) : xb.at(p.bin);
     if (int e = uconv_block_backward(xb, in, x.at(p.g_u[cur]), x.at(p.g_u[cur ^ 1]))) return e;
     cur ^= 1;  // g_u[cur] = d loss / d in_blk
@@ -830,6 +850,7 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
       cur ^= 1;  // g_u[cur] = d loss / d y_{blk-1}
     }
   }
+  if (w_pending) TD_CUDA(cudaStreamWaitEvent(st, w_pending, 0));  // the last block's weight gradients
   Tag t("bwd_frontend");
   // d x0 = d in_0 + the mixture path of every concat_block
   {

@@ -27,6 +27,7 @@ constexpr int TC_BK = 32;  // fp32 elements = one 128-byte swizzle row
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 constexpr int TC_PATCH = 32 * 36;  // floats per epilogue warp: 32 rows x (32 + 4 pad) columns
+constexpr int TC_TPATCH = 2 * 32 * 32;  // TMA-store epilogue: two 32 x 32 boxes (4 KB each, 1024-byte aligned) per warp
 
 // ----------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,6 +87,19 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA store of a [32 rows x 32 fp32] box (128-byte swizzled in shared memory) into the 3-D output map; rows / columns
+// past the tensor are clipped by the hardware.  Bulk-group completion is tracked per issuing thread.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// full completion: the writes of every bulk group of this thread have been performed (not just its smem reads)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -171,6 +185,7 @@ struct TcParams {
   int rev_b;     // > 0: batch items are visited in the order rev_b-1 .. 0 (rev_b = B)
   uint32_t tmem_cols;
   uint32_t idesc;
+  int tma_store;  // EPI 0, fp32 output, BN % 32 == 0: the epilogue stores 32 x 32 boxes through TMA (mapD)
 };
 
 // EPI: 0 = D = acc + bias                                   (proj_1x1, in/out_proj, fc1, fc2, pw_conv)
@@ -182,7 +197,7 @@ struct TcParams {
 template <int EPI, bool STATS, bool AB16, bool D16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-               const __grid_constant__ CUtensorMap mapW2, GemmArgs a, TcParams p) {
+               const __grid_constant__ CUtensorMap mapW2, const __grid_constant__ CUtensorMap mapD, GemmArgs a, TcParams p) {
   grid_dep_wait();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages] x { A 16 KB | W BN*128 B | (W_lo) } then barriers, then the epilogue patches
@@ -196,7 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* acc_full = bars + 2 * p.stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* patches = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  // (TMA-store epilogue: the boxes must sit on 1024-byte boundaries for the 128-byte swizzle)
+  float* patches = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + (p.tma_store ? 1024 : 256));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int BKE = AB16 ? 2 * TC_BK : TC_BK;  // elements per 128-byte K-block
@@ -292,6 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int N = a.N;
     float cslope = 0.f;
     if constexpr (EPI == 1) cslope = __ldg(a.cslope);
+    int tbuf = 0;  // TMA-store epilogue: which of the warp's two boxes the next chunk goes to (alternates across tiles too)
     for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
       const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
       const int b = p.rev_b ? p.rev_b - 1 - mt / p.tiles_m : mt / p.tiles_m, r0 = (mt % p.tiles_m) * TC_BM, n0 = nt * p.BN;
@@ -301,6 +318,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(acc_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+      if constexpr (EPI == 0 && !D16) {
+        if (p.tma_store) {
+          // thread = row: bias and statistics in registers, the 32 x 32 box goes to shared memory in the 128-byte
+          // swizzled layout (16-byte chunk j of row r at chunk j ^ (r & 7): conflict-free for the row-per-thread
+          // writes) and one lane hands it to TMA; two boxes per warp so the next chunk never waits for the store
+          float* tp = patches + (warp - 2) * TC_TPATCH;
+          const bool row_ok = rbase + lane < a.L;
+          // (a quarter that lies past the end of the item has nothing to store; it must not touch the boxes either:
+          // staging without committing a group would break the "at most one group pending = the other box" invariant
+          // of the wait below - observed as a data race at the last row tile of L = 2010 / 4010)
+          for (int c0 = half * 32; c0 < p.BN && rbase < a.L; c0 += 64) {
+            float v[32];
+            tc_ld32(taddr + c0, v);
+            if (a.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(a.bias + n0 + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(bp + j);
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+            }
+            if constexpr (STATS) {
+              if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  s1 += v[j];
+                  s2 = fmaf(v[j], v[j], s2);
+                }
+              }
+            }
+            if (lane == 0) tma_store_wait_read<1>();  // the store that read this box two chunks ago
+            __syncwarp();
+            float* box = tp + tbuf * (32 * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(box + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_async_shared();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&mapD, box, n0 + c0, rbase, b);
+              tma_store_commit();
+            }
+            tbuf ^= 1;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + acc);
+          if constexpr (STATS) {
+            const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
+            if (lane == 0) {
+              atomicAdd(a.stats + 2 * b, d1);
+              atomicAdd(a.stats + 2 * b + 1, d2);
+            }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+      }
       for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
         float v[32];
         const int ncol = min(32, p.BN - c0);  // BN is a multiple of 16
@@ -374,6 +450,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  }
+  if constexpr (EPI == 0 && !D16) {
+    // the stores must have been performed (not only have read their boxes) before this CTA gives up its shared memory
+    // and signals completion to a programmatically dependent kernel
+    if (p.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -461,13 +542,16 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   while (cols < (uint32_t)(2 * p.BN)) cols <<= 1;
   p.tmem_cols = cols;
   p.idesc = make_idesc(TC_BM, p.BN, a.a_bf16 != 0);
+  static const bool tma_store_on = !(getenv("TDANET_GEMM_TMA_STORE") && atoi(getenv("TDANET_GEMM_TMA_STORE")) == 0);
+  p.tma_store = tma_store_on && a.epi != EPI_RESIDUAL && !a.d_bf16 && !a.a_bf16 && p.BN % 32 == 0;
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 4 + (size_t)p.BN * TC_BK * 4 * p.nsplit;
-  const size_t budget = 184 * 1024;
+  const size_t epi_bytes = p.tma_store ? 1024 + TC_EPI_WARPS * TC_TPATCH * sizeof(float) : 256 + TC_EPI_WARPS * TC_PATCH * sizeof(float);
+  const size_t budget = 226 * 1024 - 1024 - epi_bytes;
   int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(TDANET_EUNSUPPORTED, "gemm_tc: tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + 256 + TC_EPI_WARPS * TC_PATCH * sizeof(float);
+  const size_t smem = 1024 + stages * stage_bytes + epi_bytes;
 
   CUtensorMap mapA, mapW, mapW2;
   const uint64_t dA[3] = {(uint64_t)a.K, (uint64_t)a.L, (uint64_t)a.B};
@@ -480,6 +564,12 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   // bf16 operands: the bf16 copy.
   if (int e = encode_map(&mapW, p.nsplit == 2 ? a.W : a.W_aux, 2, dW, bW, a.a_bf16)) return e;
   if (int e = encode_map(&mapW2, a.W_aux, 2, dW, bW, a.a_bf16)) return e;
+  CUtensorMap mapD = mapA;   // (a valid map even when the TMA-store epilogue is off)
+  if (p.tma_store) {
+    const uint64_t dD[3] = {(uint64_t)a.N, (uint64_t)a.L, (uint64_t)a.B};
+    const uint32_t bD[3] = {32, 32, 1};
+    if (int e = encode_map(&mapD, a.D, 3, dD, bD, false)) return e;
+  }
 
   const int grid = p.total < num_sms ? p.total : num_sms;
   const int epi = a.epi == EPI_RESIDUAL ? (a.last ? 2 : 1) : 0;
@@ -490,7 +580,7 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
       TD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<E, S, AB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    TD_LAUNCH((gemm_tc_kernel<E, S, AB, DB>), grid, TC_THREADS, smem, st, mapA, mapW, mapW2, a, p);             \
+    TD_LAUNCH((gemm_tc_kernel<E, S, AB, DB>), grid, TC_THREADS, smem, st, mapA, mapW, mapW2, mapD, a, p);             \
   } while (0)
   if (a.d_bf16) {
     TD_REQUIRE(epi == 0 && a.stats && !a.a_bf16, "gemm_tc: bf16 output is implemented for the statistics epilogue only");
