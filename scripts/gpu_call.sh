@@ -57,10 +57,11 @@ for what in "$@"; do
       echo "abinf $kv rc=$?"; python scripts/show_line.py $out/${tag}_${kv}.json;;
     abtrain_*)
       kv=${what#abtrain_}
-      env $kv timeout 600 python bench.py --train-only --steps 30 --warmup 5 --skip-cpu > $out/${tag}_train_${kv}.json 2> $out/${tag}_train_${kv}.err
+      fn=$(echo "$kv" | tr '/' '_')
+      env $kv timeout 600 python bench.py --train-only --steps 30 --warmup 5 --skip-cpu > $out/${tag}_train_${fn}.json 2> $out/${tag}_train_${fn}.err
       echo "abtrain $kv rc=$?"; python -c "
 import json,sys
-d=json.loads(open('$out/${tag}_train_${kv}.json').read().strip().splitlines()[-1])
+d=json.loads(open('$out/${tag}_train_${fn}.json').read().strip().splitlines()[-1])
 print('train', d['value'], 'steps/s', d['ms_per_step'], 'ms; e2e', d['e2e']['value'], 'launches', d['gpu_launches_per_step'], 'step_frac', d.get('step_frac'))
 ";;
     *) echo "unknown step $what";;

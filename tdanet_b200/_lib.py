@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtdanet_b200.so")
+LIB_PATH = os.environ.get("TDANET_LIB") or os.path.join(_HERE, "lib", "libtdanet_b200.so")   # TDANET_LIB: experiment builds
 
 MAX_DEPTH = 8
 MAX_ENC = 4

@@ -120,13 +120,18 @@ struct BCtx : Ctx {
 };
 
 // ----------------------------------------------------------------------------- launchers
+#ifdef TD_BWD_MINB
+constexpr int kRowGridMaxThreads = 128;   // the experiment's launch bounds are for 128-thread CTAs
+#else
+constexpr int kRowGridMaxThreads = 256;
+#endif
 static inline void row_grid(int L, int C4, int B, int rows, dim3& grid, int& threads) {
-  threads = C4 > 256 ? 256 : (C4 < 32 ? 32 : C4);
+  threads = C4 > kRowGridMaxThreads ? kRowGridMaxThreads : (C4 < 32 ? 32 : C4);
   grid = dim3(cdiv(L, rows), cdiv(C4, threads), B);
 }
 // rows per thread (a multiple of the 4-row tile): as many as `max_rows`, but keep at least two CTAs per SM
 static inline int pick_rows(int L, int C4, int B, int max_rows) {
-  const int threads = C4 > 256 ? 256 : (C4 < 32 ? 32 : C4);
+  const int threads = C4 > kRowGridMaxThreads ? kRowGridMaxThreads : (C4 < 32 ? 32 : C4);
   int rows = max_rows;
   while (rows > 4 && (long)cdiv(L, rows) * cdiv(C4, threads) * B < 2 * 148) rows >>= 1;
   return rows;

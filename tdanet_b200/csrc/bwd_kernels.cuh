@@ -295,8 +295,13 @@ struct DwBwdArgs {
 // the plain variants (LA branches) stay lean in registers.
 // V = 4 channels per thread, or 2 for small launches (training batches): twice the warps at about half the registers,
 // where the kernel is bound by latency at low occupancy rather than by bytes (rows are still read as whole sectors).
+#ifdef TD_BWD_MINB   // experiment: force >= TD_BWD_MINB CTAs of 128 threads per SM on the streaming backward kernels
+#define TD_BWD_BOUNDS __launch_bounds__(128, TD_BWD_MINB)
+#else
+#define TD_BWD_BOUNDS
+#endif
 template <int KS, int NW, int STRIDE, bool EXTRA, int V = 4>
-__global__ void dw_bwd_kernel(DwBwdArgs a) {
+__global__ void TD_BWD_BOUNDS dw_bwd_kernel(DwBwdArgs a) {
   grid_dep_wait();
   // output rows per tile: 4, or 2 where the windows are wide (two convs, or stride 2 with its 2x input rows)
   constexpr int PAD = (KS - 1) / 2, R = (NW == 2 && KS == 5) || STRIDE == 2 ? 2 : 4;
@@ -598,7 +603,7 @@ __global__ void la_bwd_g_kernel(LaBwdArgs a, int rows_per_thread) {
 }
 
 template <int KS>
-__global__ void la_bwd_l_kernel(LaBwdArgs a) {
+__global__ void TD_BWD_BOUNDS la_bwd_l_kernel(LaBwdArgs a) {
   grid_dep_wait();
   constexpr int V = 4, PAD = (KS - 1) / 2, R = 4, W = R + 2 * PAD;
   const int b = blockIdx.z;

@@ -1146,7 +1146,10 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
 // stalls of this arithmetic-heavy loop - issue slots were 38 % busy at 0.65 of the HBM peak).  V = 2: half the
 // per-thread state, four CTAs per SM (16 warps), a CTA covers 256 channels.
 template <int LKIND, int CT, int V>
-__global__ void __launch_bounds__(128, V == 4 ? 2 : 4) la_stream_kernel(LaArgs a, int rows_per_cta) {
+#ifndef TD_LASTREAM_MINB
+#define TD_LASTREAM_MINB 2
+#endif
+__global__ void __launch_bounds__(128, V == 4 ? TD_LASTREAM_MINB : 4) la_stream_kernel(LaArgs a, int rows_per_cta) {
   grid_dep_wait();
   extern __shared__ __align__(16) float la_smem[];
   const int b = blockIdx.z;
