@@ -37,8 +37,8 @@ def model_kwargs(enc_ms):
 
 
 def workload_name(variant, enc_ms, batch):
-    return (f"{CLASSES[variant]} {enc_ms} ms encoder, 16 blocks, inference, batch {batch} x 2 s @16 kHz per GPU "
-            f"(BASELINE.json configs[{1 if enc_ms == 4 else 2}]), random-init weights (seed 0)")
+    return (f"{CLASSES[variant]} {enc_ms} ms/16 blocks, inference, {batch} x 2 s @16 kHz per GPU "
+            f"(BASELINE.json configs[{1 if enc_ms == 4 else 2}]), seed-0 init")
 
 
 def common_config(variant, enc_ms, batch):
@@ -751,8 +751,8 @@ def run_ours(args):
         step_roofline = {"survey_bytes_per_mixture_GB": model_gb, "hbm_roofline_audio_s_per_s": round(peak / model_gb * 2.0, 1),
                          "frac_of_survey_roofline": round(value / world / (peak / model_gb * 2.0), 4)}
         cpu = cpu_baseline(args) if world == 1 and not args.skip_cpu else None
-        dtype = ("bf16 storage, fp32 arithmetic, tf32/bf16 tcgen05 GEMMs" if args.act_dtype == "bf16" else
-                 "f32 (tf32 tcgen05 GEMMs)" if args.gemm_mode != "fp32" else "f32")
+        dtype = ("bf16 storage, f32 arithmetic" if args.act_dtype == "bf16" else
+                 "f32 (tf32 GEMMs)" if args.gemm_mode != "fp32" else "f32")
         detail = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -806,18 +806,16 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": r4(cpu["value"]), "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
                                    "sample": cpu["sample_short"]}
         if eager is not None:
-            out["eager_gpu"] = {"fp32": r1(eager["fp32"]), "tf32": r1(eager["tf32"]), "unit": UNIT}
+            out["eager_gpu"] = {"fp32": r1(eager["fp32"]), "tf32": r1(eager["tf32"])}
         if train is not None:
-            out["train"] = {"value": r4(train["value"]), "unit": "steps/s", "ms": r4(train["ms_per_step"]),
-                            "e2e": r4(train["e2e"]["value"]), "batch_per_gpu": TRAIN_BATCH,
+            out["train"] = {"value": round(train["value"], 2), "unit": "steps/s", "ms": round(train["ms_per_step"], 3),
+                            "e2e": round(train["e2e"]["value"], 2), "batch_per_gpu": TRAIN_BATCH,
                             "frac": None if not train.get("roofline") else train["roofline"]["frac"],
                             "step_frac": train.get("step_frac")}
         if longform is not None:
-            out["longform"] = {"value": r1(longform["value"]), "e2e": r1(longform["e2e"]["value"]), "unit": UNIT,
-                               "scaling": "strong"}
+            out["longform"] = {"value": r1(longform["value"]), "e2e": r1(longform["e2e"]["value"]), "scaling": "strong"}
         if two_ms is not None:
-            out["two_ms"] = {"value": r1(two_ms["value"]), "unit": UNIT, "scaling": "strong",
-                             "batch_per_gpu": two_ms["batch_per_gpu"]}
+            out["two_ms"] = {"value": r1(two_ms["value"]), "scaling": "strong", "batch_per_gpu": two_ms["batch_per_gpu"]}
         if detail_path:
             out["detail"] = detail_path
         print(json.dumps(out))

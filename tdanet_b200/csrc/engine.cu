@@ -140,9 +140,25 @@ static int global_attention(const Ctx& x, bool ln_pe_done) {
   if (!ln_pe_done)  // else: fused into the kernel that produced ga_in
     if (int e = launch_ln_pe(x.at(p.ga_in), w->ln1_w, w->ln1_b, w->pe, x.at(p.attn_in), B, Lb, C, x.rnd(), x.st)) return e;
   GemmArgs g{};
+  // Every item attends alone (attention group 1: the chunk-at-a-time long-form loop, audio_test_css.py:110-111, and
+  // any B = 1 call): the softmax over a single key is exactly 1, so the attention output IS the value row - only the
+  // V third of in_proj is computed, straight into the context buffer, and the attention launch disappears.
+  const bool single_key = group == 1 && !time_axis && !p.train;
   g.A = x.at(p.attn_in); g.W = w->in_proj_w; g.bias = w->in_proj_b; g.D = x.at(p.qkv);
   g.B = B; g.L = Lb; g.N = 3 * C; g.K = C; g.epi = EPI_BIAS;
-  { Tag t("gemm_in_proj"); if (int e = gemm(x, g, p.aux_in)) return e; }
+  if (single_key) {
+    g.W = w->in_proj_w + (size_t)2 * C * C; g.bias = w->in_proj_b + 2 * C; g.D = x.at(p.attn_ctx); g.N = C;
+    Tag t("gemm_in_proj");
+    if (x.c->gemm_mode == TDANET_GEMM_FP32) {
+      if (int e = launch_gemm_simt(g, x.st)) return e;
+    } else {
+      g.W_aux = x.at(p.aux_in) + (size_t)2 * C * C;   // the same rows of the prepared (TF32) copy
+      if (int e = launch_gemm_tc(g, x.c->gemm_mode, x.st)) return e;
+    }
+  } else {
+    Tag t("gemm_in_proj");
+    if (int e = gemm(x, g, p.aux_in)) return e;
+  }
   // training-mode multipliers (nn.Dropout / DropPath keep-masks drawn by launch_dropout_masks): null in eval
   const float ik = p.drop_elem ? 1.f / (1.f - c->dropout) : 1.f, ikp = p.drop_item ? 1.f / (1.f - c->drop_path) : 1.f;
   const uint8_t* m_att = p.drop_elem ? x.at<uint8_t>(p.m_att) : nullptr;
@@ -150,8 +166,10 @@ static int global_attention(const Ctx& x, bool ln_pe_done) {
   const uint8_t* m_f1 = p.drop_elem ? x.at<uint8_t>(p.m_f1) : nullptr;
   const uint8_t* m_f2 = p.drop_elem ? x.at<uint8_t>(p.m_f2) : nullptr;
   const uint8_t* m_dp = p.drop_item ? x.at<uint8_t>(p.m_dp) : nullptr;
-  { Tag t("attention");
-  if (int e = launch_attention(x.at(p.qkv), x.at(p.attn_ctx), B, Lb, C, c->n_head, group, time_axis, x.rnd(), m_att, ik, x.st)) return e; }
+  if (!single_key) {
+    Tag t("attention");
+    if (int e = launch_attention(x.at(p.qkv), x.at(p.attn_ctx), B, Lb, C, c->n_head, group, time_axis, x.rnd(), m_att, ik, x.st)) return e;
+  }
   g = GemmArgs{};
   g.A = x.at(p.attn_ctx); g.W = w->out_proj_w; g.bias = w->out_proj_b; g.D = x.at(p.attn_out);
   g.B = B; g.L = Lb; g.N = C; g.K = C; g.epi = EPI_BIAS;
