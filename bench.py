@@ -403,6 +403,7 @@ def run_train_leg(args, dev, rank, world, local, barrier):
     torch.manual_seed(0)
     model = getattr(look2hear.models, CLASSES[args.variant])(sample_rate=SR, **model_kwargs(args.enc_ms)).to(dev).train()
     model.gemm_mode = args.gemm_mode
+    model.act_dtype = args.act_dtype     # bf16: the large activations kept for the backward pass are stored as bf16
     L = look2hear.losses
     ts = look2hear.system.TrainingStep(model, L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True),
                                        lr=1e-3, clip_grad_norm=5.0)
@@ -477,6 +478,7 @@ def run_train_leg(args, dev, rank, world, local, barrier):
                                f"backward, gradient all-reduce, clip 5.0, Adam), batch {B} x 2 s per GPU "
                                "(BASELINE.json configs[3]), train mode: dropout 0.1 / DropPath 0.1 like the reference (Philox keep-masks drawn on the device every step)",
                    "dropout": model.dropout, "drop_path": model.drop_path, "batch_per_gpu": B, "global_batch": B * world, "gemm_mode": args.gemm_mode,
+                   "act_dtype": args.act_dtype,
                    "cuda_graph": not args.no_graph},
         "samples_per_second": world * B * K / (ms / 1e3),
         "e2e": {"value": K / (ms_e2e / 1e3), "unit": "steps/s", "ms_per_step": ms_e2e / K,

@@ -55,6 +55,13 @@ for what in "$@"; do
       kv=${what#abinf_}
       env $kv timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu --skip-eager --skip-longform --skip-2ms --skip-train --detail-out $out/${tag}_${kv}_detail.json > $out/${tag}_${kv}.json 2> $out/${tag}_${kv}.err
       echo "abinf $kv rc=$?"; python scripts/show_line.py $out/${tag}_${kv}.json;;
+    train_bf16)
+      timeout 600 python bench.py --train-only --steps 30 --warmup 5 --skip-cpu --act-dtype bf16 > $out/${tag}_train_bf16.json 2> $out/${tag}_train_bf16.err
+      echo "train_bf16 rc=$?"; python -c "
+import json
+d=json.loads(open('$out/${tag}_train_bf16.json').read().strip().splitlines()[-1])
+print('train bf16', d['value'], 'steps/s', d['ms_per_step'], 'ms; e2e', d['e2e']['value'], 'loss_after', d['loss_after'])
+";;
     abtrain_*)
       kv=${what#abtrain_}
       fn=$(echo "$kv" | tr '/' '_')

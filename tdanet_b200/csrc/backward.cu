@@ -166,19 +166,25 @@ static int fit_wave(int rows, int tile, int L, int ctiles, int B, long slots) {
   return cdiv(cdiv(L, (int)chunks), tile) * tile;
 }
 
-static int launch_gln_bwd_stats(const float* dy, const float* x, const NormRef& norm, float* dgamma, float* dbeta,
+static int launch_gln_bwd_stats_t(int x_bf16, const float* dy, const float* x, const NormRef& norm, float* dgamma, float* dbeta,
                                 double* S, int B, int L, int C, cudaStream_t st) {
   dim3 grid;
   int threads;
   const int rows = pick_rows(L, C % 4 == 0 ? C / 4 : C, B, 32);
   if (C % 4 == 0) {
     row_grid(L, C / 4, B, rows, grid, threads);
-    TD_LAUNCH_RED((gln_bwd_stats_kernel<4>), grid, threads, 0, st, dy, x, norm, dgamma, dbeta, S, L, C, rows);
+    if (x_bf16) TD_LAUNCH_RED((gln_bwd_stats_kernel<4, true>), grid, threads, 0, st, dy, x, norm, dgamma, dbeta, S, L, C, rows, x_bf16);
+    else TD_LAUNCH_RED((gln_bwd_stats_kernel<4>), grid, threads, 0, st, dy, x, norm, dgamma, dbeta, S, L, C, rows, x_bf16);
   } else {
     row_grid(L, C, B, rows, grid, threads);
-    TD_LAUNCH_RED((gln_bwd_stats_kernel<1>), grid, threads, 0, st, dy, x, norm, dgamma, dbeta, S, L, C, rows);
+    TD_LAUNCH_RED((gln_bwd_stats_kernel<1>), grid, threads, 0, st, dy, x, norm, dgamma, dbeta, S, L, C, rows, x_bf16);
   }
   return 0;
+}
+
+static int launch_gln_bwd_stats(const float* dy, const float* x, const NormRef& norm, float* dgamma, float* dbeta,
+                                double* S, int B, int L, int C, cudaStream_t st) {
+  return launch_gln_bwd_stats_t(0, dy, x, norm, dgamma, dbeta, S, B, L, C, st);
 }
 
 static int launch_gln_bwd_apply(const GradSrc& g, float* out, int accumulate, int B, int L, int C, cudaStream_t st) {
@@ -187,7 +193,8 @@ static int launch_gln_bwd_apply(const GradSrc& g, float* out, int accumulate, in
   const int rows = pick_rows(L, C % 4 == 0 ? C / 4 : C, B, 16);
   if (C % 4 == 0) {
     row_grid(L, C / 4, B, rows, grid, threads);
-    TD_LAUNCH((gln_bwd_apply_kernel<4>), grid, threads, 0, st, g, out, accumulate, L, C, rows);
+    if (g.x_bf16) TD_LAUNCH((gln_bwd_apply_kernel<4, true>), grid, threads, 0, st, g, out, accumulate, L, C, rows);
+    else TD_LAUNCH((gln_bwd_apply_kernel<4>), grid, threads, 0, st, g, out, accumulate, L, C, rows);
   } else {
     row_grid(L, C, B, rows, grid, threads);
     TD_LAUNCH((gln_bwd_apply_kernel<1>), grid, threads, 0, st, g, out, accumulate, L, C, rows);
@@ -222,7 +229,7 @@ static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
   // launches).  Measured on B200 at the training shape (B = 8, 2016 warps per launch): V = 2 is SLOWER (bwd_spp_dw0
   // 0.81 -> 1.30 ms per step, bwd_la_dw 5.20 -> 5.35): the kernels are not occupancy-bound there.
   const long warps4 = (long)grid.x * grid.y * grid.z * (threads / 32);
-  if (warps4 < 148L && a.C % 2 == 0) {
+  if (warps4 < 148L && a.C % 2 == 0 && !(a.xin.bf16 || a.g[0].x_bf16 || (nw == 2 && a.g[1].x_bf16))) {
     a.rows_per_thread = pick_rows(a.Lout, a.C / 2, a.B, 32);
     row_grid(a.Lout, a.C / 2, a.B, a.rows_per_thread, grid, threads);
     if (key == 511 && !extra) TD_LAUNCH_RED((dw_bwd_kernel<5, 1, 1, false, 2>), grid, threads, 0, st, a);
@@ -236,7 +243,26 @@ static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
   }
   void (*kfn)(DwBwdArgs) = nullptr;
   int tile = 4;  // output rows per tile of the variant (bwd_kernels.cuh: R)
-  if (key == 511 && !extra) kfn = dw_bwd_kernel<5, 1, 1, false>;
+  // act_dtype bf16: which operands are stored activations in bf16 is a compile-time property of the instantiation.
+  // The combinations the sweep produces: conv input only (LA / loc_glo_fus branches: the gradient sources read fp32
+  // temporaries) and both (the spp_dw chain); everything at the bottom scale is fp32.
+  const bool xbf = a.xin.bf16 != 0;
+  const bool gbf = a.g[0].x_bf16 != 0;
+  TD_REQUIRE(nw == 1 || (a.g[1].x_bf16 != 0) == gbf, "dw_bwd: mixed storage of the gradient sources");
+  if (xbf && !gbf) {
+    if (key == 511 && !extra) kfn = dw_bwd_kernel<5, 1, 1, false, 4, false, true>;
+    else if (key == 521 && !extra) { kfn = dw_bwd_kernel<5, 2, 1, false, 4, false, true>; tile = 2; }
+    else if (key == 111 && !extra) kfn = dw_bwd_kernel<1, 1, 1, false, 4, false, true>;
+    else if (key == 121 && !extra) kfn = dw_bwd_kernel<1, 2, 1, false, 4, false, true>;
+    else return fail(TDANET_EINVAL, "dw_bwd (bf16 input): ks=%d nw=%d extra=%d", ks, nw, (int)extra);
+  } else if (xbf && gbf) {
+    if (key == 511) kfn = dw_bwd_kernel<5, 1, 1, true, 4, true, true>;
+    else if (key == 512) { kfn = dw_bwd_kernel<5, 1, 2, true, 4, true, true>; tile = 2; }
+    else return fail(TDANET_EINVAL, "dw_bwd (bf16 input and sources): ks=%d nw=%d", ks, nw);
+  } else if (gbf) {
+    return fail(TDANET_EINVAL, "dw_bwd: bf16 gradient sources with an fp32 input");
+  }
+  else if (key == 511 && !extra) kfn = dw_bwd_kernel<5, 1, 1, false>;
   else if (key == 511) kfn = dw_bwd_kernel<5, 1, 1, true>;
   else if (key == 512) { kfn = dw_bwd_kernel<5, 1, 2, true>; tile = 2; }
   else if (key == 521 && !extra) { kfn = dw_bwd_kernel<5, 2, 1, false>; tile = 2; }
@@ -256,12 +282,16 @@ static int launch_la_bwd_a(LaBwdArgs& a, int ks, cudaStream_t st) {
   int threads;
   const int grows = pick_rows(a.Lg, a.C / 4, a.B, 16);  // global rows per thread of the G and F passes
   row_grid(a.Lg, a.C / 4, a.B, grows, grid, threads);
-  if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5>), grid, threads, 0, st, a, grows);
+  if (a.glo_bf16) {
+    if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5, true>), grid, threads, 0, st, a, grows);
+    else TD_LAUNCH((la_bwd_g_kernel<1, true>), grid, threads, 0, st, a, grows);
+  } else if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5>), grid, threads, 0, st, a, grows);
   else TD_LAUNCH((la_bwd_g_kernel<1>), grid, threads, 0, st, a, grows);
   // L pass: chunks of centres covering about 32 local rows per thread (one wave of CTAs where that is close, fit_wave)
   int jc = (int)((double)pick_rows(a.loc.L, a.C / 4, a.B, 32) * a.Lg / a.loc.L + 0.5);
   a.jchunk = jc < 1 ? 1 : jc;
-  void (*lfn)(LaBwdArgs) = ks == 5 ? la_bwd_l_kernel<5> : la_bwd_l_kernel<1>;
+  void (*lfn)(LaBwdArgs) = a.loc.bf16 ? (ks == 5 ? la_bwd_l_kernel<5, true> : la_bwd_l_kernel<1, true>)
+                                      : (ks == 5 ? la_bwd_l_kernel<5> : la_bwd_l_kernel<1>);
   a.jchunk = fit_wave(a.jchunk, 1, a.Lg, cdiv(a.C / 4, threads), a.B, resident_ctas((const void*)lfn, threads));
   dim3 lgrid;
   row_grid(a.Lg, a.C / 4, a.B, a.jchunk, lgrid, threads);
@@ -386,19 +416,20 @@ static int launch_framed_wgrad(const float* M, const float* sig, float* dW, int 
 }
 
 // ----------------------------------------------------------------------------- orchestration
-static GradSrc gln_grad(const float* dy, const float* x, const NormRef& n, const double* S) {
+// `bf16`: x is one of the large stored activations and act_dtype is bf16 (everything else the sweep reads is fp32)
+static GradSrc gln_grad(const float* dy, const float* x, const NormRef& n, const double* S, int bf16 = 0) {
   GradSrc g{};
-  g.dy = dy; g.x = x; g.norm = n; g.S = S; g.kind = G_GLN;
+  g.dy = dy; g.x = x; g.norm = n; g.S = S; g.kind = G_GLN; g.x_bf16 = bf16;
   return g;
 }
-static SrcDesc bplain(const float* x, int L) {
+static SrcDesc bplain(const float* x, int L, int bf16 = 0) {
   SrcDesc s{};
-  s.x = x; s.L = L;
+  s.x = x; s.L = L; s.bf16 = bf16;
   return s;
 }
-static SrcDesc baffine(const float* x, int L, const NormRef& n, const float* slope = nullptr) {
+static SrcDesc baffine(const float* x, int L, const NormRef& n, const float* slope = nullptr, int bf16 = 0) {
   SrcDesc s{};
-  s.x = x; s.L = L; s.norm = n; s.slope = slope;
+  s.x = x; s.L = L; s.norm = n; s.slope = slope; s.bf16 = bf16;
   return s;
 }
 
@@ -426,6 +457,13 @@ static int prepare_transposed(const BCtx& x) {
   return 0;
 }
 
+static int launch_bf16_to_f32(const float* src, float* dst, size_t n, cudaStream_t st) {
+  TD_REQUIRE(n % 4 == 0, "bf16_to_f32: n=%zu", n);
+  const size_t n4 = n / 4;
+  TD_LAUNCH(bf16_to_f32_kernel, (unsigned)((n4 + 255) / 256 > 8192 ? 8192 : (n4 + 255) / 256), 256, 0, st, src, dst, n4);
+  return 0;
+}
+
 // weight gradient on the side stream `w`: it waits for everything the main stream has enqueued so far (its operands)
 // and is joined back at the end of the block (uconv_block_backward) before any operand buffer is reused
 static int wgrad_side(const BCtx& x, const float* G, const float* A, float* dW, float* db, int R, int N, int K) {
@@ -449,11 +487,11 @@ static int dgrad(const BCtx& x, const float* A, size_t wt, size_t aux, float* D,
 static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdanet_la_t& gla, const SrcDesc& loc, int lkind,
                        const float* glo, int Lg, const NormRef& nL, const NormRef& nA, const NormRef& nE,
                        const size_t bs[3], const float* dout, float* d_loc_in, int acc_loc, float* d_glo_in, int acc_glo,
-                       cudaStream_t local_st = nullptr) {
+                       cudaStream_t local_st = nullptr, int glo_bf16 = 0) {
   const Plan& p = *x.p;
   const int B = p.B, C = x.c->in_channels, Ll = loc.L;
   LaBwdArgs a{};
-  a.loc = loc; a.lkind = lkind; a.glo = glo; a.Lg = Lg; a.B = B; a.C = C;
+  a.loc = loc; a.lkind = lkind; a.glo = glo; a.glo_bf16 = glo_bf16; a.Lg = Lg; a.B = B; a.C = C;
   a.wl = la.local_embedding.w; a.wa = la.global_act.w; a.we = la.global_embedding.w;
   a.nL = nL; a.nA = nA; a.nE = nE; a.dout = dout; a.scale = nearest_scale(Lg, Ll);
   const int ts = x.tset;
@@ -480,7 +518,7 @@ static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdane
   d.g[1] = gln_grad(a.d_emb, a.raw_e, nE, a.S[2]);
   d.w[0] = la.global_act.w; d.dw[0] = x.gp(gla.global_act.w);
   d.w[1] = la.global_embedding.w; d.dw[1] = x.gp(gla.global_embedding.w);
-  d.xin = bplain(glo, Lg); d.xkind = SRC_PLAIN; d.B = B; d.C = C; d.Lin = Lg; d.Lout = Lg; d.stride = 1;
+  d.xin = bplain(glo, Lg, glo_bf16); d.xkind = SRC_PLAIN; d.B = B; d.C = C; d.Lin = Lg; d.Lout = Lg; d.stride = 1;
   d.dx = d_glo_in; d.accumulate = acc_glo;
   return launch_dw_bwd(x, d, ks, 2);
 }
@@ -593,12 +631,28 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
   const Plan& p = *x.p;
   const int B = p.B, C = c->in_channels, cc = c->out_channels, depth = c->depth, Lb = p.Lb, L0 = p.L[0];
   const int R0 = B * L0;
+  const int abf = x.bf() ? 1 : 0;   // the large stored activations (proj, spp, x_fused, expanded) are bf16
+  cudaEvent_t wres_done = nullptr;
   TD_CUDA(cudaMemsetAsync(x.at<char>(p.bs_begin), 0, p.bs_end - p.bs_begin, x.st));
   auto spp_norm = [&](int k) {
     return norm_ref(x, p.st_spp[k], 2, (double)p.L[k] * C, w->spp_dw[k].gamma, w->spp_dw[k].beta);
   };
   // ---- res_conv
-  { Tag t("wgrad_res_conv"); if (int e = wgrad_side(x, d_y, x.at(p.expanded[0]), x.gp(gw->res_w), x.gp(gw->res_b), R0, cc, C)) return e; }
+  {
+    Tag t("wgrad_res_conv");
+    const float* a_op = x.at(p.expanded[0]);
+    if (abf) {
+      // the weight-gradient kernel reads fp32 rows: widen expanded[0] into a free LA temporary (set 1 is untouched
+      // until the second top-down step, which waits for this weight gradient below)
+      if (int e = launch_bf16_to_f32(x.at(p.expanded[0]), x.at(p.t_rawa[1]), (size_t)R0 * C, x.st)) return e;
+      a_op = x.at(p.t_rawa[1]);
+    }
+    if (int e = wgrad_side(x, d_y, a_op, x.gp(gw->res_w), x.gp(gw->res_b), R0, cc, C)) return e;
+    if (abf) {
+      wres_done = x.side->events[x.side->next++ % x.side->events.size()];
+      TD_CUDA(cudaEventRecord(wres_done, x.side->w));
+    }
+  }
   { Tag t("dgrad_res_conv"); if (int e = dgrad(x, d_y, p.wt_res, p.auxt_res, x.at(p.g_exp[0]), L0, C, cc, nullptr)) return e; }
   // ---- top-down fusion, in the reverse of the forward order.  Main stream: passes G/L/F and the global-branch
   // depthwise backward of every step (the chain g_exp[i] -> g_exp[i+1]).  Side stream `l`: the local-branch depthwise
@@ -637,7 +691,7 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
     const NormRef nL = norm_ref(x, p.st_lgf[k], 6, (double)p.L[k] * C, la.local_embedding.gamma, la.local_embedding.beta);
     const NormRef nA = norm_ref(x, p.st_lgf[k] + 2 * sizeof(double), 6, (double)Lb * C, la.global_act.gamma, la.global_act.beta);
     const NormRef nE = norm_ref(x, p.st_lgf[k] + 4 * sizeof(double), 6, (double)Lb * C, la.global_embedding.gamma, la.global_embedding.beta);
-    if (int e = la_backward(x.on(sf, 2 + q), 1, la, gw->loc_glo_fus[k], baffine(x.at(p.spp[k]), p.L[k], spp_norm(k)), SRC_AFFINE,
+    if (int e = la_backward(x.on(sf, 2 + q), 1, la, gw->loc_glo_fus[k], baffine(x.at(p.spp[k]), p.L[k], spp_norm(k), nullptr, abf), SRC_AFFINE,
                             x.at(p.ga_out), Lb, nL, nA, nE, p.bs_lgf[k], x.at(p.g_fused[k]), x.at(p.g_spp[k]), 0,
                             g_out, ga_out_written[q])) return e;
     spp_written[k] = true;
@@ -667,9 +721,10 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
     }
     // the first step adds into g_fused[gi], which the side stream wrote in step gi
     if (first && fused_written[gi]) TD_CUDA(cudaStreamWaitEvent(x.st, local_done[gi], 0));
-    if (int e = la_backward(x.on(x.st, i & 1), 5, la, gw->last_layer[i], bplain(x.at(p.fused[i]), p.L[i]), SRC_PLAIN, glo, Lg,
+    if (i == 1 && wres_done) TD_CUDA(cudaStreamWaitEvent(x.st, wres_done, 0));  // t_rawa[1] held res_conv's fp32 operand
+    if (int e = la_backward(x.on(x.st, i & 1), 5, la, gw->last_layer[i], bplain(x.at(p.fused[i]), p.L[i], abf), SRC_PLAIN, glo, Lg,
                             nL, nA, nE, p.bs_la[i], x.at(p.g_exp[i]), x.at(p.g_fused[i]), fused_written[i], d_glo,
-                            first ? (int)fused_written[gi] : 0, sl)) return e;
+                            first ? (int)fused_written[gi] : 0, sl, abf)) return e;
     fused_written[i] = true;
     if (first) fused_written[gi] = true;
     local_done[i] = x.side->events[x.side->next++ % x.side->events.size()];
@@ -727,8 +782,10 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
       int wrows = 4;
       while (wrows < Lb && (long)cdiv(C / 4, threads) * (ks + 1) * B * cdiv(Lb, wrows * 2) >= 4 * 148) wrows *= 2;
       dim3 wgrid(cdiv(C / 4, threads), ks + 1, B * cdiv(Lb, wrows));
-      TD_LAUNCH(dwg_bwd_weight_kernel, wgrid, threads, 0, x.st, x.at(p.g_pool_dw), baffine(x.at(p.spp[k]), p.L[k], spp_norm(k)),
-                (int)SRC_AFFINE, x.gp(gq.dw_w), x.gp(gq.dw_b), B, Lb, C, ks, s, wrows);
+      if (abf) TD_LAUNCH((dwg_bwd_weight_kernel<true>), wgrid, threads, 0, x.st, x.at(p.g_pool_dw), baffine(x.at(p.spp[k]), p.L[k], spp_norm(k), nullptr, abf),
+                         (int)SRC_AFFINE, x.gp(gq.dw_w), x.gp(gq.dw_b), B, Lb, C, ks, s, wrows);
+      else TD_LAUNCH((dwg_bwd_weight_kernel<false>), wgrid, threads, 0, x.st, x.at(p.g_pool_dw), baffine(x.at(p.spp[k]), p.L[k], spp_norm(k)),
+                     (int)SRC_AFFINE, x.gp(gq.dw_w), x.gp(gq.dw_b), B, Lb, C, ks, s, wrows);
     }
   } else {
     // ---- ga_in = sum_k avgpool(gLN(spp_k)): the coarsest scale (identity bins) here, the others inside the spp_dw
@@ -745,20 +802,20 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
     const NormRef nk = spp_norm(k);
     if (k == depth - 1) {
       Tag t("bwd_gln_stats");
-      if (int e = launch_gln_bwd_stats(x.at(p.g_spp[k]), x.at(p.spp[k]), nk, x.gp(gw->spp_dw[k].gamma),
+      if (int e = launch_gln_bwd_stats_t(abf, x.at(p.g_spp[k]), x.at(p.spp[k]), nk, x.gp(gw->spp_dw[k].gamma),
                                        x.gp(gw->spp_dw[k].beta), x.at<double>(p.bs_spp[k]), B, p.L[k], C, x.st)) return e;
     }
     DwBwdArgs d{};
-    d.g[0] = gln_grad(x.at(p.g_spp[k]), x.at(p.spp[k]), nk, x.at<double>(p.bs_spp[k]));
+    d.g[0] = gln_grad(x.at(p.g_spp[k]), x.at(p.spp[k]), nk, x.at<double>(p.bs_spp[k]), abf);
     d.w[0] = w->spp_dw[k].w; d.dw[0] = x.gp(gw->spp_dw[k].w); d.db[0] = x.gp(gw->spp_dw[k].b);
     d.B = B; d.C = C; d.Lout = p.L[k];
     if (k == 0) {
-      d.xin = baffine(x.at(p.proj), L0, n_proj, w->proj_prelu);
+      d.xin = baffine(x.at(p.proj), L0, n_proj, w->proj_prelu, abf);
       d.xkind = SRC_AFFINE_PRELU; d.Lin = L0; d.stride = 1; d.dx = x.at(p.g_proj); d.accumulate = 0;
       d.dslope = x.gp(gw->proj_prelu);
       d.up_dgamma = x.gp(gw->proj.gamma); d.up_dbeta = x.gp(gw->proj.beta); d.up_S = x.at<double>(p.bs_proj);
     } else {
-      d.xin = baffine(x.at(p.spp[k - 1]), p.L[k - 1], spp_norm(k - 1));
+      d.xin = baffine(x.at(p.spp[k - 1]), p.L[k - 1], spp_norm(k - 1), nullptr, abf);
       d.xkind = SRC_AFFINE; d.Lin = p.L[k - 1]; d.stride = 2; d.dx = x.at(p.g_spp[k - 1]);
       d.accumulate = spp_written[k - 1];  // the loc_glo_fus local branch wrote it (every scale but a dead last one)
       if (c->variant != TDANET_FORK) { d.pool_g = x.at(p.g_ga_in); d.pool_Lb = Lb; }
@@ -770,7 +827,7 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
   }
   // ---- proj_1x1 (its GlobLN sums were accumulated by the spp_dw[0] backward)
   { Tag t("bwd_gln_apply");
-    if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_proj), x.at(p.proj), n_proj, x.at<double>(p.bs_proj)),
+    if (int e = launch_gln_bwd_apply(gln_grad(x.at(p.g_proj), x.at(p.proj), n_proj, x.at<double>(p.bs_proj), abf),
                                      x.at(p.t_dloc[0]), 0, B, L0, C, x.st)) return e; }  // LA temporaries are free by now
   // every weight gradient enqueued so far is joined at the end of this block (they finished long ago); only the proj
   // one, enqueued next, may outlast the block

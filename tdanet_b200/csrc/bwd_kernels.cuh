@@ -35,19 +35,25 @@ struct GradSrc {
   NormRef norm;     // G_GLN: forward statistics + gamma
   const double* S;  // G_GLN: [B, 2]
   int kind;
+  int x_bf16;       // x is a stored activation in bf16 (training with act_dtype bf16); dy is always fp32
 };
 
-template <int V>
+// BF: `x` is a stored activation in bf16 (act_dtype bf16) - a compile-time property of the instantiation, chosen by
+// the launcher from the x_bf16 / bf16 flags of the sources; the fp32 instantiations carry no trace of it.
+template <int V, bool BF = false>
 struct GradLoad {
   vf<V> gr;
   float r, mur, k1, k2;
   const float* dy;
-  const float* x;
-  int kind;
+  const float* x;   // start of the tensor (typed access: act_vload)
+  size_t x0;        // element offset of (item b, channel ch)
+  int kind, xbf;
   __device__ __forceinline__ void init(const GradSrc& g, int b, int ch, size_t item_elems) {
     kind = g.kind;
     dy = g.dy + (size_t)b * item_elems + ch;
-    x = (g.x ? g.x : g.dy) + (size_t)b * item_elems + ch;  // always loadable: loads are issued unconditionally
+    x = g.x ? g.x : g.dy;  // always loadable: loads are issued unconditionally
+    xbf = g.x ? g.x_bf16 : 0;
+    x0 = (size_t)b * item_elems + ch;
     r = 1.f; mur = 0.f; k1 = 0.f; k2 = 0.f;
     gr = vzero<V>();
     if (kind == G_GLN) {
@@ -63,7 +69,7 @@ struct GradLoad {
   // off: row * C.  Branch-free (selects on the uniform `kind`) so that callers can issue many loads back to back.
   __device__ __forceinline__ vf<V> load(size_t off) const {
     vf<V> d = vload<V>(dy + off);
-    const vf<V> xv = vload<V>(x + off);
+    const vf<V> xv = act_vload_t<V, BF>(x, x0 + off);
 #pragma unroll
     for (int e = 0; e < V; ++e) {
       const float xh = fmaf(xv[e], r, -mur);
@@ -85,15 +91,18 @@ struct GradLoad {
 };
 
 // forward value of a conv input row (normalise-on-load): PLAIN, AFFINE, AFFINE_PRELU
-template <int V>
+template <int V, bool BF = false>
 struct FwdLoad {
   vf<V> sc, sh, gam;
   float slope, r, mur;
-  const float* x;
-  int kind;
+  const float* x;   // start of the tensor (typed access: act_vload)
+  size_t x0;        // element offset of (item b, channel ch)
+  int kind, xbf;
   __device__ __forceinline__ void init(const SrcDesc& s, int kind_, int b, int ch, int C) {
     kind = kind_;
-    x = s.x + (size_t)b * s.L * C + ch;
+    x = s.x;
+    xbf = s.bf16;
+    x0 = (size_t)b * s.L * C + ch;
     slope = 1.f; r = 1.f; mur = 0.f;
 #pragma unroll
     for (int e = 0; e < V; ++e) { sc[e] = 1.f; sh[e] = 0.f; gam[e] = 0.f; }
@@ -106,7 +115,7 @@ struct FwdLoad {
   }
   // pre-activation value (GlobLN output; the raw value for PLAIN: sc = 1, sh = 0)
   __device__ __forceinline__ vf<V> pre(size_t off) const {
-    vf<V> v = vload<V>(x + off);
+    vf<V> v = act_vload_t<V, BF>(x, x0 + off);
 #pragma unroll
     for (int e = 0; e < V; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
     return v;
@@ -114,7 +123,7 @@ struct FwdLoad {
   // raw stored value of a row clamped into [0, L)
   __device__ __forceinline__ vf<V> raw_row(int row, int L, int C) const {
     const int rc = row < 0 ? 0 : (row >= L ? L - 1 : row);
-    return vload<V>(x + (size_t)rc * C);
+    return act_vload_t<V, BF>(x, x0 + (size_t)rc * C);
   }
   // GlobLN output from a raw value; rows outside [0, L) are the conv's zero padding
   __device__ __forceinline__ vf<V> pre_of(const vf<V>& raw, int row, int L) const {
@@ -149,10 +158,10 @@ struct FwdLoad {
 
 // ----------------------------------------------------------------------------- GlobLN backward
 // statistics pass: dgamma_c += sum dy*xhat, dbeta_c += sum dy, S[b] += (sum gamma*dy, sum gamma*dy*xhat)
-template <int V>
+template <int V, bool BF = false>
 __global__ void gln_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, NormRef norm,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     double* __restrict__ S, int L, int C, int rows_per_thread) {
+                                     double* __restrict__ S, int L, int C, int rows_per_thread, int x_bf16) {
   grid_dep_wait();
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -171,7 +180,7 @@ __global__ void gln_bwd_stats_kernel(const float* __restrict__ dy, const float* 
       for (int i = 0; i < 4; ++i) {  // unconditional, clamped; rows past t1 contribute zero
         const size_t off = ((size_t)b * L + (t + i < L ? t + i : L - 1)) * C + ch;
         d[i] = vload<V>(dy + off);
-        xv[i] = vload<V>(x + off);
+        xv[i] = act_vload_t<V, BF>(x, off);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -197,7 +206,7 @@ __global__ void gln_bwd_stats_kernel(const float* __restrict__ dy, const float* 
 }
 
 // out = dX formed on load (out must not alias g.dy: the source is read through the read-only path); accumulate: out += dX
-template <int V>
+template <int V, bool BF = false>
 __global__ void gln_bwd_apply_kernel(GradSrc g, float* __restrict__ out, int accumulate, int L, int C,
                                      int rows_per_thread) {
   grid_dep_wait();
@@ -205,7 +214,7 @@ __global__ void gln_bwd_apply_kernel(GradSrc g, float* __restrict__ out, int acc
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   if (ch >= C) return;
   const int t0 = blockIdx.x * rows_per_thread, t1 = min(t0 + rows_per_thread, L);
-  GradLoad<V> gl;
+  GradLoad<V, BF> gl;
   gl.init(g, b, ch, (size_t)L * C);
   float* op = out + (size_t)b * L * C + ch;
   for (int t = t0; t < t1; t += 4) {
@@ -300,7 +309,8 @@ struct DwBwdArgs {
 #else
 #define TD_BWD_BOUNDS
 #endif
-template <int KS, int NW, int STRIDE, bool EXTRA, int V = 4>
+// GBF / XBF: the raw GlobLN inputs of the gradient sources (g[*].x) / the conv input (xin) are bf16 activations
+template <int KS, int NW, int STRIDE, bool EXTRA, int V = 4, bool GBF = false, bool XBF = false>
 __global__ void TD_BWD_BOUNDS dw_bwd_kernel(DwBwdArgs a) {
   grid_dep_wait();
   // output rows per tile: 4, or 2 where the windows are wide (two convs, or stride 2 with its 2x input rows)
@@ -318,7 +328,7 @@ __global__ void TD_BWD_BOUNDS dw_bwd_kernel(DwBwdArgs a) {
     const int C = a.C, Lin = a.Lin, Lout = a.Lout;
     const int o0 = blockIdx.x * a.rows_per_thread, o1 = min(o0 + a.rows_per_thread, Lout);
     const int i1 = o1 == Lout ? Lin : min(o1 * STRIDE, Lin);
-    GradLoad<V> gl[NW];
+    GradLoad<V, GBF> gl[NW];
     float w[NW][KS][V];
 #pragma unroll
     for (int g = 0; g < NW; ++g) {
@@ -328,7 +338,7 @@ __global__ void TD_BWD_BOUNDS dw_bwd_kernel(DwBwdArgs a) {
 #pragma unroll
         for (int k = 0; k < KS; ++k) w[g][k][e] = __ldg(a.w[g] + (size_t)(ch + e) * KS + k);
     }
-    FwdLoad<V> fx;
+    FwdLoad<V, XBF> fx;
     fx.init(a.xin, a.xkind, b, ch, C);
     const bool prelu = EXTRA && a.xkind == SRC_AFFINE_PRELU;
     float* dxp = a.dx + (size_t)b * Lin * C + ch;
@@ -521,6 +531,7 @@ struct LaBwdArgs {
   SrcDesc loc;
   int lkind;         // SRC_PLAIN (x_fused) or SRC_AFFINE (GlobLN(spp_dw[k]) for loc_glo_fus)
   const float* glo;  // [B, Lg, C]
+  int glo_bf16;      // glo is a stored activation in bf16
   int Lg, B, C;
   const float *wl, *wa, *we;
   NormRef nL, nA, nE;
@@ -549,7 +560,7 @@ __device__ __forceinline__ int first_local_row(int j, float scale, int Ll, int L
 //   L  over the local rows  : raw_a = dw_l(xl), d_loc = dout * gate[j], GlobLN_L sums; a thread owns whole centres,
 //                             so when it leaves centre j it writes d_act[j] = (sum dout*loc) * gate*(1-gate),
 //                             d_emb[j] = sum dout and adds them to the GlobLN_A / GlobLN_E sums
-template <int KS>
+template <int KS, bool BF = false>
 __global__ void la_bwd_g_kernel(LaBwdArgs a, int rows_per_thread) {
   grid_dep_wait();
   constexpr int V = 4, PAD = (KS - 1) / 2, R = 4, W = R + 2 * PAD;
@@ -566,11 +577,10 @@ __global__ void la_bwd_g_kernel(LaBwdArgs a, int rows_per_thread) {
       wa[k][e] = __ldg(a.wa + (size_t)(ch + e) * KS + k);
       we[k][e] = __ldg(a.we + (size_t)(ch + e) * KS + k);
     }
-  const float* gp = a.glo + (size_t)b * Lg * C + ch;
   const size_t goff = (size_t)b * Lg * C + ch;
   auto loadg = [&](int row) {
     const int rc = row < 0 ? 0 : (row >= Lg ? Lg - 1 : row);
-    vf<V> v = vload<V>(gp + (size_t)rc * C);
+    vf<V> v = act_vload_t<V, BF>(a.glo, goff + (size_t)rc * C);
     const bool ok = row == rc;
 #pragma unroll
     for (int e = 0; e < V; ++e) v[e] = ok ? v[e] : 0.f;
@@ -602,7 +612,7 @@ __global__ void la_bwd_g_kernel(LaBwdArgs a, int rows_per_thread) {
   }
 }
 
-template <int KS>
+template <int KS, bool BF = false>
 __global__ void TD_BWD_BOUNDS la_bwd_l_kernel(LaBwdArgs a) {
   grid_dep_wait();
   constexpr int V = 4, PAD = (KS - 1) / 2, R = 4, W = R + 2 * PAD;
@@ -627,7 +637,7 @@ __global__ void TD_BWD_BOUNDS la_bwd_l_kernel(LaBwdArgs a) {
     norm_moments(a.nA, b, rA, murA);
     norm_moments(a.nE, b, rE, murE);
     const vf<V> gL = vload<V>(a.nL.gamma + ch), gA = vload<V>(a.nA.gamma + ch), gE = vload<V>(a.nE.gamma + ch);
-    FwdLoad<V> fl;
+    FwdLoad<V, BF> fl;
     fl.init(a.loc, a.lkind, b, ch, C);
     const float* dop = a.dout + (size_t)b * Ll * C + ch;
     float* dlp = a.d_loc + (size_t)b * Ll * C + ch;
@@ -806,6 +816,7 @@ __global__ void dwg_bwd_data_kernel(const float* __restrict__ G, const float* __
 // blocks for the bias), blockIdx.z = item * chunks + chunk.  Rows in tiles of 4 with every load issued before use.
 // (The first version walked all B * Lout rows in one thread per (tap, 4 channels): 34 CTAs, ~0.5 ms per launch,
 // 50.8 of the 68.7 ms of a fork training step.)
+template <bool BF = false>
 __global__ void dwg_bwd_weight_kernel(const float* __restrict__ G, SrcDesc xin, int xkind, float* __restrict__ dw,
                                       float* __restrict__ db, int B, int Lout, int C, int ks, int stride,
                                       int rows_per_cta) {
@@ -819,7 +830,7 @@ __global__ void dwg_bwd_weight_kernel(const float* __restrict__ G, SrcDesc xin, 
   const int to1 = min(to0 + rows_per_cta, Lout);
   const int pad = (ks - 1) / 2, Lin = xin.L;
   vf<V> acc = vzero<V>();
-  FwdLoad<V> fx;
+  FwdLoad<V, BF> fx;
   fx.init(xin, xkind, b, ch, C);
   const float* gp = G + (size_t)b * Lout * C + ch;
   for (int to = to0; to < to1; to += 4) {
@@ -1327,6 +1338,13 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
   if (idx >= (size_t)N * K) return;
   const int k = (int)(idx / N), n = (int)(idx % N);
   Wt[idx] = W[(size_t)n * K + k];
+}
+
+// bf16 -> fp32 copy of a stored activation (the fp32 operand of res_conv's weight gradient in bf16 training)
+__global__ void bf16_to_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n4) {
+  grid_dep_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    vstore<4>(dst + 4 * i, act_vload<4>(src, 4 * i, 1));
 }
 
 // dst = a + b

@@ -245,6 +245,38 @@ __device__ __forceinline__ void astore(__nv_bfloat16* __restrict__ p, const vf<V
 
 #endif  // !TD_EMU
 
+// Run-time typed read of a stored activation (the backward kernels are compiled once; which of their inputs were
+// stored as bf16 is a launch argument): `base` is the start of the tensor, `off` an ELEMENT offset.  Written so that
+// the CPU emulation build (emu.h) can execute it.
+template <int V>
+__device__ __forceinline__ vf<V> act_vload(const float* __restrict__ base, size_t off, int bf16) {
+  if (!bf16) return vload<V>(base + off);
+  const uint16_t* p = reinterpret_cast<const uint16_t*>(base) + off;
+  vf<V> r;
+#ifdef TD_EMU
+  for (int e = 0; e < V; ++e) r.v[e] = __uint_as_float((uint32_t)p[e] << 16);
+#else
+  if constexpr (V == 4) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    r.v[0] = __uint_as_float(t.x << 16); r.v[1] = __uint_as_float(t.x & 0xffff0000u);
+    r.v[2] = __uint_as_float(t.y << 16); r.v[3] = __uint_as_float(t.y & 0xffff0000u);
+  } else if constexpr (V == 2) {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    r.v[0] = __uint_as_float(t << 16); r.v[1] = __uint_as_float(t & 0xffff0000u);
+  } else {
+    r.v[0] = __uint_as_float((uint32_t)__ldg(p) << 16);
+  }
+#endif
+  return r;
+}
+
+// compile-time typed form
+template <int V, bool BF>
+__device__ __forceinline__ vf<V> act_vload_t(const float* __restrict__ base, size_t off) {
+  if constexpr (BF) return act_vload<V>(base, off, 1);
+  else return vload<V>(base + off);
+}
+
 // fire-and-forget vector reduction into global memory (red.global.add.v{2,4}.f32 on sm_90+)
 template <int V>
 __device__ __forceinline__ void vred_add(float* p, const vf<V>& r) {

@@ -313,7 +313,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     Tag t("fused_materialize");
     for (int k = 0; k < depth; ++k)
       if (fused_live[k])
-        if (int e = launch_inject_materialize(inj_src(k), inj_kind, B, C, x.at(p.fused[k]), 0, x.st)) return e;
+        if (int e = launch_inject_materialize(inj_src(k), inj_kind, B, C, x.at(p.fused[k]), x.bf(), x.st)) return e;
   }
   // statistics of the local branch of every top-down step: independent of the chain below, so they run on the side
   // stream - the coarse scales first (one launch; the first steps of the chain need them), then the finest scale,

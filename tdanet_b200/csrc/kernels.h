@@ -32,6 +32,7 @@ struct SrcDesc {
   const float* g;      // injected global feature [B, Lg, C] or nullptr
   int Lg;
   float gscale;        // fl32(Lg / L)
+  int bf16;            // backward kernels only: x is stored as bf16 (the forward kernels know it at compile time)
 };
 
 // ------------------------------------------------------------------ dwconv.cu

@@ -89,6 +89,14 @@ struct Plan {
     if (name) named.push_back({name, o, {B, L_, C_}, 4});
     return o;
   }
+  // one of the LARGE activations (proj_1x1 output, spp_dw outputs, expanded, materialised x_fused): stored as bf16 in
+  // the first half of its fp32-sized buffer when act_dtype is bf16
+  size_t big(const char* name, int64_t L_, int64_t C_) {
+    size_t o = take((size_t)B * L_ * C_ * sizeof(float));
+    if (name) named.push_back({name, o, {B, L_, C_}, act_bf16 ? 2 : 4});
+    return o;
+  }
+  bool act_bf16 = false;
   size_t dstat(const char* name, int n) {
     size_t o = take((size_t)B * n * 2 * sizeof(double));
     if (name) named.push_back({name, o, {B, n, 2}, 8});
@@ -132,8 +140,9 @@ static inline int check_config(const tdanet_config_t* c) {
 // What the training path supports in this build (everything else raises instead of falling back).
 static inline int check_train_config(const tdanet_config_t* c) {
   if (int e = check_config(c)) return e;
-  if (c->act_dtype != TDANET_ACT_F32)
-    return fail(TDANET_EUNSUPPORTED, "training step: activations are kept in fp32 (act_dtype fp32)");
+  // act_dtype bf16: the large activations a forward keeps for the backward pass (proj, spp_dw outputs, x_fused,
+  // expanded) are stored as bf16; arithmetic, statistics, gradients and parameters stay fp32 ("precision: 16" of
+  // configs/tdanet.yml:41 in this implementation's terms)
   TD_REQUIRE(c->dropout >= 0.f && c->dropout < 1.f && c->drop_path >= 0.f && c->drop_path < 1.f,
              "dropout %g / drop_path %g outside [0, 1)", (double)c->dropout, (double)c->drop_path);
   return 0;
@@ -149,6 +158,7 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
   p.B = B;
   p.T = T;
   p.train = train;
+  p.act_bf16 = c->act_dtype == TDANET_ACT_BF16;
   // pad_input (TDANet_best.py:465-479)
   p.rest = K - (S + T % K) % K;
   p.Tp = T + p.rest + 2 * (K - S);
@@ -194,14 +204,14 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
 
   // ---- block arena
   p.blk_begin = p.bytes;
-  p.proj = p.act("proj", L0, C);
+  p.proj = p.big("proj", L0, C);
   for (int k = 0; k < depth; ++k) {
     snprintf(nm, sizeof nm, "spp%d", k);
-    p.spp[k] = p.act(nm, p.L[k], C);
+    p.spp[k] = p.big(nm, p.L[k], C);
   }
   for (int k = 0; k < depth - 1; ++k) {
     snprintf(nm, sizeof nm, "expanded%d", k);
-    p.expanded[k] = p.act(nm, p.L[k], C);
+    p.expanded[k] = p.big(nm, p.L[k], C);
   }
   p.ga_in = p.act("ga_in", Lb, C);
   p.attn_in = p.act("attn_in", Lb, C);
@@ -227,7 +237,7 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     p.y = p.act("y", L0, cc);
     for (int k = 0; k < depth; ++k) {
       snprintf(nm, sizeof nm, "fused%d", k);
-      p.fused[k] = p.act(nm, p.L[k], C);
+      p.fused[k] = p.big(nm, p.L[k], C);
     }
     p.fused_a = p.fused[depth - 2];
     p.fused_b = p.fused[first_step_partner(depth)];

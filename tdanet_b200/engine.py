@@ -245,7 +245,7 @@ class SeparationEngine:
                                                         C.byref(off), C.byref(dims), C.byref(es)))
         ws = self._tws[torch.device(device)]
         n = dims[0] * dims[1] * dims[2]
-        dt = {1: torch.uint8, 4: torch.float32, 8: torch.float64}[es.value]
+        dt = {1: torch.uint8, 2: torch.bfloat16, 4: torch.float32, 8: torch.float64}[es.value]
         return ws[off.value: off.value + es.value * n].view(dt).view(dims[0], dims[1], dims[2])
 
     def _check_wav(self, wav):

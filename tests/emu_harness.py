@@ -70,12 +70,12 @@ def _check(lib, code):
         raise RuntimeError(f"emu error {code}: {lib.tdanet_last_error().decode()}")
 
 
-def make_engine(kw, sample_rate, gemm_mode="fp32", variant="best"):
+def make_engine(kw, sample_rate, gemm_mode="fp32", variant="best", act_dtype="fp32"):
     K = kw["enc_kernel_size"] * sample_rate // 1000
     multres = variant == "multres"
     return SeparationEngine(variant, kw["out_channels"], kw["in_channels"], kw["num_blocks"], kw["upsampling_depth"],
                             K, kw["out_channels"] if multres else K // 2 + 1, kw["num_sources"],
-                            enc_convs=kw.get("kernels", 4) if multres else 1, gemm_mode=gemm_mode)
+                            enc_convs=kw.get("kernels", 4) if multres else 1, gemm_mode=gemm_mode, act_dtype=act_dtype)
 
 
 class Workspace:
@@ -98,13 +98,16 @@ class Workspace:
         _check(self.lib, self.lib.tdanet_train_workspace_tensor(C.byref(self.cfg), self.B, self.T, name.encode(), block,
                                                                 C.byref(off), C.byref(dims), C.byref(es)))
         n = dims[0] * dims[1] * dims[2]
-        dt = {1: np.uint8, 4: np.float32, 8: np.float64}[es.value]
+        dt = {1: np.uint8, 2: np.uint16, 4: np.float32, 8: np.float64}[es.value]   # 2: bf16 bits
         raw = self.buf[self.base + off.value: self.base + off.value + n * es.value]
         return raw.view(dt).reshape(dims[0], dims[1], dims[2])
 
     def put(self, name, t, block=0):
         v = self.view(name, block)
-        a = t.detach().cpu().numpy()
+        if v.dtype == np.uint16:   # a large activation stored as bf16 (round to nearest even, like the forward kernels)
+            a = t.detach().cpu().float().to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+        else:
+            a = t.detach().cpu().numpy()
         assert a.shape == v.shape, (name, a.shape, v.shape)
         v[...] = a
 
@@ -198,12 +201,14 @@ def fill_workspace(ws: Workspace, taps, kw, variant="best", drop_masks=None):
         ws.put("ga_out", _cl(t("ga.out")), b)
 
 
-def emu_backward(sd, wav, d_est, kw, sample_rate, variant="best", dropout=0.0, drop_path=0.0, drop_masks=None):
+def emu_backward(sd, wav, d_est, kw, sample_rate, variant="best", dropout=0.0, drop_path=0.0, drop_masks=None,
+                 act_dtype="fp32"):
     """Gradients of sum(est * d_est) w.r.t. every parameter, computed by the emulated CUDA backward pass.
     Returns (grads dict keyed like the state_dict, oracle output).  drop_masks: explicit keep-masks of a train-mode
     step (OracleConfig.drop_masks), written into the workspace where the forward pass would have drawn them."""
     lib = load_emu()
-    eng = make_engine(kw, sample_rate, variant=variant)
+    # (bf16 storage needs a tensor-core gemm_mode in the configuration check; the emulated GEMMs are exact either way)
+    eng = make_engine(kw, sample_rate, variant=variant, act_dtype=act_dtype, gemm_mode="tf32" if act_dtype == "bf16" else "fp32")
     eng.set_dropout(dropout, drop_path)
     okw = {k: v for k, v in kw.items() if k != "feat_len"}
     cfg = O.OracleConfig(variant=variant, sample_rate=sample_rate, taps={}, tap_all=True, drop_masks=drop_masks,

@@ -133,3 +133,39 @@ def test_emulated_warp_attention_backward(monkeypatch):
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("variant", ["best", "fork"])
+def test_emulated_backward_with_bf16_stored_activations(variant):
+    """act_dtype bf16 in training: the large activations a forward keeps (proj, spp_dw outputs, x_fused, expanded) are
+    stored as bf16 and the backward kernels read them through run-time typed loads.  The workspace is filled from the
+    oracle's taps rounded to bf16, so the gradients are those of the exact model evaluated at activations that are off
+    by up to 2^-9 relative: close to autograd (a loose bound), different from the fp32-storage run (the path is live),
+    and the workspace reports 2-byte elements for exactly those tensors."""
+    kw = dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4, enc_kernel_size=4, num_sources=2)
+    sd = _model_sd(kw, variant=variant)
+    g = torch.Generator().manual_seed(7)
+    B, T = 2, 643
+    wav = torch.randn(B, 1, T, generator=g) * 0.1
+    d_est = torch.randn(B, 2, T, generator=g)
+    g16, _, ws16 = H.emu_backward(sd, wav, d_est, kw, SR, variant, act_dtype="bf16")
+    g32, _, ws32 = H.emu_backward(sd, wav, d_est, kw, SR, variant)
+    import numpy as np
+    for name in ("proj", "spp0", "spp3", "fused0", "expanded1"):
+        assert ws16.view(name).dtype == np.uint16 and ws32.view(name).dtype == np.float32, name
+    for name in ("x0", "y", "ga_out", "fc1", "qkv"):
+        assert ws16.view(name).dtype == np.float32, name
+    ref = _autograd(sd, wav, d_est, kw, variant)
+    num = den = diff = 0.0
+    for k, r in ref.items():
+        if r is None:
+            assert g16[k].abs().max().item() == 0.0, k
+            continue
+        num += (g16[k].double() - r).pow(2).sum().item()
+        diff += (g16[k].double() - g32[k].double()).pow(2).sum().item()
+        den += r.pow(2).sum().item()
+        assert torch.isfinite(g16[k]).all(), k
+    rel, rel_vs_fp32 = (num / den) ** 0.5, (diff / den) ** 0.5
+    print(f"{variant} bf16 storage: whole-gradient rel-L2 vs fp64 autograd {rel:.2e}, vs the fp32-storage run {rel_vs_fp32:.2e}")
+    assert rel < 3e-2, rel
+    assert rel_vs_fp32 > 1e-5, rel_vs_fp32

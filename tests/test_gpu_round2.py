@@ -202,3 +202,65 @@ def test_two_host_threads_share_a_device():
     assert not errs, errs
     for a, b in zip(got, want):
         assert max_rel(a, b) < 1e-5
+
+
+# ----------------------------------------------------------------------------- bf16 activation storage in training
+@pytest.mark.parametrize("variant", ["best", "fork"])
+def test_bf16_storage_training_gradients(variant):
+    """`act_dtype = "bf16"` in training (the reference trains with `precision: 16`, configs/tdanet.yml:41): the large
+    activations a forward keeps for the backward pass (proj, spp_dw outputs, x_fused, expanded) are stored as bf16,
+    arithmetic / statistics / gradients / parameters stay fp32.  Output by the bf16-mode SI-SNR acceptance, gradients
+    against fp64 autograd of the oracle (bf16 storage + TF32 GEMMs: a few 1e-3 of the whole gradient), and the
+    workspace really holds 2-byte elements."""
+    from test_gpu_parity import _bf16_checks
+    kw = dict(out_channels=32, in_channels=64, num_blocks=3, upsampling_depth=5, enc_kernel_size=4, num_sources=2)
+    cls = {"best": "TDANetBest", "fork": "TDANet"}[variant]
+    torch.manual_seed(11)
+    m = getattr(look2hear.models, cls)(sample_rate=16000, **kw)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    B, T = 3, 6000
+    x = torch.randn(B, 1, T, generator=g) * 0.1
+    d = torch.randn(B, 2, T, generator=g)
+    cfg = O.OracleConfig(variant=variant, sample_rate=16000, **kw)
+    sd64 = {k: v.double().requires_grad_(k != PE) for k, v in sd.items()}
+    ref_est = O.forward(sd64, x.double(), cfg)
+    (ref_est * d.double()).sum().backward()
+    m = m.to(DEV).train()
+    m.dropout = m.drop_path = 0.0
+    m.act_dtype = "bf16"
+    est = m(x.to(DEV))
+    (est * d.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    _bf16_checks(est.detach().cpu(), ref_est.detach().float(), 5)
+    assert m.engine.train_workspace_tensor("proj", 0, B, T, DEV).dtype == torch.bfloat16
+    assert m.engine.train_workspace_tensor("fused0", 1, B, T, DEV).dtype == torch.bfloat16
+    assert m.engine.train_workspace_tensor("y", 0, B, T, DEV).dtype == torch.float32
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        r = sd64[k].grad
+        if r is None:
+            assert p.grad is None, k
+            continue
+        assert torch.isfinite(p.grad).all(), k
+        num += (p.grad.cpu().double() - r).pow(2).sum().item()
+        den += r.pow(2).sum().item()
+    rel = (num / den) ** 0.5
+    print(f"{variant} bf16-storage training: whole-gradient rel-L2 vs fp64 autograd {rel:.2e}")
+    # a 32 / 64-channel model averages its GlobLN statistics over few elements, so the bf16 rounding of the forward's
+    # stored tensors shows more than at the benchmarked width (test_gpu_headline: 2e-2 bound at 128 / 512 channels)
+    assert rel < 8e-2, rel
+
+
+def test_bf16_storage_training_step_reduces_loss():
+    kw = dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4, enc_kernel_size=4, num_sources=2)
+    torch.manual_seed(1)
+    m = look2hear.models.TDANetBest(sample_rate=8000, **kw).to(DEV).train()
+    m.act_dtype = "bf16"
+    L = look2hear.losses
+    ts = look2hear.system.TrainingStep(m, L.PITLossWrapper(L.pairwise_neg_sisdr, threshold_byloss=True), lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    tgt = (torch.randn(4, 2, 2000, generator=g) * 0.1).to(DEV)
+    mix = tgt.sum(1)
+    losses = [ts.step_captured(mix, tgt).item() for _ in range(30)]
+    assert losses[-1] < losses[0] - 0.5, losses
