@@ -115,6 +115,65 @@ __global__ void affine_sum_ln_kernel(PoolArgs a) {
   *reinterpret_cast<float4*>(a.ln_out + ((size_t)b * a.Lb + j) * a.C + ch) = o;
 }
 
+// One WARP per token row (C a multiple of 128, <= 1024): a lane owns the channel quads lane*4 + 128*q, the row moments
+// are warp shuffles - no block barrier, four rows per 128-thread CTA, and the loads of the n pooled tensors of a row
+// are all in flight before the first is used.  (The CTA-per-row form above: 8,064 CTAs of two block reductions each,
+// 34 us per launch at B = 64.)
+template <int Q>
+__global__ void __launch_bounds__(128) affine_sum_ln_warp_kernel(PoolArgs a, int rows) {
+  grid_dep_wait();
+  constexpr int V = 4;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = row / a.Lb, j = row % a.Lb;
+  const size_t roff = (size_t)row * a.C;
+  vf<V> acc[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc[q] = vzero<V>();
+  for (int k = 0; k < a.n; ++k) {
+    vf<V> v[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) v[q] = vload<V>(a.x[k] + roff + lane * 4 + 128 * q);
+    float r, mur;
+    norm_moments(a.norm[k], b, r, mur);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const vf<V> g = vload<V>(a.norm[k].gamma + lane * 4 + 128 * q), be = vload<V>(a.norm[k].beta + lane * 4 + 128 * q);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[q][e] += fmaf(v[q][e], g[e] * r, fmaf(-g[e], mur, be[e]));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    vstore<V>(a.out + roff + lane * 4 + 128 * q, acc[q]);
+    s += (acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]);
+  }
+  const float mu = warp_sum(s) / (float)a.C;
+  float qq = 0.f;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const float d0 = acc[q][0] - mu, d1 = acc[q][1] - mu, d2 = acc[q][2] - mu, d3 = acc[q][3] - mu;
+    qq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  const float rstd = rsqrtf(warp_sum(qq) / (float)a.C + kEpsLN);
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int c = lane * 4 + 128 * q;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_w + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(a.ln_b + c));
+    const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pe + (size_t)j * a.C + c));
+    float4 o;
+    o.x = (acc[q][0] - mu) * rstd * g.x + bb.x + pe.x;
+    o.y = (acc[q][1] - mu) * rstd * g.y + bb.y + pe.y;
+    o.z = (acc[q][2] - mu) * rstd * g.z + bb.z + pe.z;
+    o.w = (acc[q][3] - mu) * rstd * g.w + bb.w + pe.w;
+    if (a.ln_round) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+    *reinterpret_cast<float4*>(a.ln_out + roff + c) = o;
+  }
+}
+
 bool launch_affine_sum_fuses_ln(const PoolArgs& a) {
   static const bool off = getenv("TDANET_FUSE_LN_PE") && atoi(getenv("TDANET_FUSE_LN_PE")) == 0;
   return !off && a.ln_out && a.ln_w && a.ln_b && a.pe && a.C % 4 == 0 && a.C / 4 <= 256;
@@ -125,6 +184,16 @@ int launch_affine_sum(const PoolArgs& a, cudaStream_t st) {
   int threads = a.C / 4 > 256 ? 256 : (a.C / 4 < 32 ? 32 : a.C / 4);
   dim3 grid(a.Lb, cdiv(a.C / 4, threads), a.B);
   if (launch_affine_sum_fuses_ln(a)) {
+    static const bool warp_rows = !(getenv("TDANET_POOLSUM_WARP") && atoi(getenv("TDANET_POOLSUM_WARP")) == 0);
+    const int rows = a.B * a.Lb;
+    if (warp_rows && a.C % 128 == 0 && a.C <= 1024) {
+      const int q = a.C / 128;
+      const unsigned g = (unsigned)cdiv(rows, 4);
+      if (q == 4) { TD_LAUNCH((affine_sum_ln_warp_kernel<4>), g, 128, 0, st, a, rows); return 0; }
+      if (q == 2) { TD_LAUNCH((affine_sum_ln_warp_kernel<2>), g, 128, 0, st, a, rows); return 0; }
+      if (q == 1) { TD_LAUNCH((affine_sum_ln_warp_kernel<1>), g, 128, 0, st, a, rows); return 0; }
+      if (q == 8) { TD_LAUNCH((affine_sum_ln_warp_kernel<8>), g, 128, 0, st, a, rows); return 0; }
+    }
     threads = (threads + 31) / 32 * 32;
     TD_LAUNCH_COOP(affine_sum_ln_kernel, grid, threads, 0, st, a);
     return 0;

@@ -8,9 +8,10 @@ namespace td {
   int launch_dw5(const DwArgs& a, cudaStream_t st);                                                           \
   int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int ks, int stride, const float* w, \
                         const float* wT, const float* bias, float* out, int round_out, cudaStream_t st);      \
-  int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, cudaStream_t st);     \
+  int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, const float* wa,      \
+                                const float* we, double* stats, cudaStream_t st);                             \
   int launch_inject_materialize2(const SrcDesc& sa, float* out_a, const SrcDesc& sb, float* out_b, int kind, int B, \
-                                 int C, cudaStream_t st);                                                     \
+                                 int C, const float* wa, const float* we, double* stats, cudaStream_t st);    \
   int launch_la_combine(const LaArgs& a, cudaStream_t st);                                                    \
   int launch_la_local_stats(const DwArgs* steps, int n, cudaStream_t st);                                     \
   }
@@ -26,14 +27,15 @@ int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int 
   return act_bf16 ? act_bf16::launch_dw_generic(src, kind, B, C, Lout, ks, stride, w, wT, bias, out, round_out, st)
                   : act_f32::launch_dw_generic(src, kind, B, C, Lout, ks, stride, w, wT, bias, out, round_out, st);
 }
-int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, int act_bf16, cudaStream_t st) {
-  return act_bf16 ? act_bf16::launch_inject_materialize(src, kind, B, C, out, st)
-                  : act_f32::launch_inject_materialize(src, kind, B, C, out, st);
+int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, int act_bf16, cudaStream_t st,
+                              const float* wa, const float* we, double* stats) {
+  return act_bf16 ? act_bf16::launch_inject_materialize(src, kind, B, C, out, wa, we, stats, st)
+                  : act_f32::launch_inject_materialize(src, kind, B, C, out, wa, we, stats, st);
 }
 int launch_inject_materialize2(const SrcDesc& sa, float* out_a, const SrcDesc& sb, float* out_b, int kind, int B, int C,
-                               int act_bf16, cudaStream_t st) {
-  return act_bf16 ? act_bf16::launch_inject_materialize2(sa, out_a, sb, out_b, kind, B, C, st)
-                  : act_f32::launch_inject_materialize2(sa, out_a, sb, out_b, kind, B, C, st);
+                               int act_bf16, cudaStream_t st, const float* wa, const float* we, double* stats) {
+  return act_bf16 ? act_bf16::launch_inject_materialize2(sa, out_a, sb, out_b, kind, B, C, wa, we, stats, st)
+                  : act_f32::launch_inject_materialize2(sa, out_a, sb, out_b, kind, B, C, wa, we, stats, st);
 }
 int launch_la_combine(const LaArgs& a, cudaStream_t st) {
   return a.act_bf16 ? act_bf16::launch_la_combine(a, st) : act_f32::launch_la_combine(a, st);

@@ -545,61 +545,119 @@ int launch_dw5(const DwArgs& a, cudaStream_t st) {
 // ----------------------------------------------------------------------------- materialise an injected operand
 // y[t] = x_fused[k][t] written out (only for the two small tensors of the first top-down step, whose
 // down-sampling access pattern would otherwise recompute every injected row five times)
-template <int KIND>
+// Optional: the GlobLN statistics of two 5-tap depthwise convolutions of the tensor being written (global_act /
+// global_embedding of the first top-down step, whose "global" operand this is): the CTA finalises two halo rows on
+// either side of its range and slides a 5-row window over what it writes, so the separate statistics pass over the
+// materialised tensor (one launch per block) disappears.
+struct MatStats {
+  const float* wa;   // [C,1,5] or null: no statistics
+  const float* we;
+  double* stats;     // [B, 2, 2]
+};
+
+template <int KIND, bool STATS>
 __device__ __forceinline__ void inject_materialize_tile(const SrcDesc& sd, int C, float* __restrict__ out, int tile,
-                                                        int rows_per_cta, int* jtab) {
+                                                        int rows_per_cta, int* jtab, const MatStats& ms) {
   constexpr int V = 4, R = 8;  // 8 rows of loads in flight per thread
+  constexpr int H = STATS ? 2 : 0;  // halo rows finalised (not stored) on either side
+  __shared__ double red[STATS ? 64 : 1];
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const int t0 = tile * rows_per_cta, t1 = min(t0 + rows_per_cta, sd.L);
-  fill_nearest(jtab, rows_per_cta, t0, sd.L, sd.gscale, sd.Lg);
+  fill_nearest(jtab, rows_per_cta + 2 * H, t0 - H, sd.L, sd.gscale, sd.Lg);
   __syncthreads();
-  if (ch >= C) return;
-  Src<KIND, V, false> src;
-  src.init(sd, b, ch, C, jtab, t0);
-  ACT_T* op = reinterpret_cast<ACT_T*>(out) + (size_t)b * sd.L * C + ch;
-  for (int t = t0; t < t1; t += R) {
-    vf<V> r[R];
+  float tot1[2] = {0.f, 0.f}, tot2[2] = {0.f, 0.f};
+  if (ch < C) {
+    Src<KIND, V, false> src;
+    src.init(sd, b, ch, C, jtab, t0 - H);
+    ACT_T* op = reinterpret_cast<ACT_T*>(out) + (size_t)b * sd.L * C + ch;
+    vf<V> wa[5], we[5], win[5], s1a = vzero<V>(), s2a = vzero<V>(), s1e = vzero<V>(), s2e = vzero<V>();
+    if constexpr (STATS) {
+      load_taps<V>(ms.wa, ch, wa);
+      load_taps<V>(ms.we, ch, we);
 #pragma unroll
-    for (int i = 0; i < R; ++i) r[i] = t + i < t1 ? src.load_raw(t + i) : vzero<V>();
+      for (int i = 0; i < 5; ++i) win[i] = vzero<V>();
+    }
+    for (int t = t0 - H; t < t1 + H; t += R) {
+      vf<V> r[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-      if (t + i < t1) astore<V>(op + (t + i) * C, src.finalize(r[i], t + i));
+      for (int i = 0; i < R; ++i) {
+        const int row = t + i;
+        r[i] = (row < t1 + H && row >= 0 && row < sd.L) ? src.load_raw(row) : vzero<V>();
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int row = t + i;
+        if (row < t1 + H) {
+          const bool inside = row >= 0 && row < sd.L;   // rows outside the tensor are the convolutions' zero padding
+          const vf<V> f = inside ? src.finalize(r[i], row) : vzero<V>();
+          if (row >= t0 && row < t1) astore<V>(op + row * C, f);
+          if constexpr (STATS) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) win[j] = win[j + 1];
+            win[4] = f;
+            const int c = row - 2;   // the window now holds rows c-2 .. c+2
+            if (c >= t0 && c < t1) {
+              const vf<V> ya = conv5<V>(wa, win[0], win[1], win[2], win[3], win[4]);
+              const vf<V> ye = conv5<V>(we, win[0], win[1], win[2], win[3], win[4]);
+              s1a = vadd<V>(s1a, ya); s2a = vfma<V>(ya, ya, s2a);
+              s1e = vadd<V>(s1e, ye); s2e = vfma<V>(ye, ye, s2e);
+            }
+          }
+        }
+      }
+    }
+    if constexpr (STATS) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        tot1[0] += s1a[e]; tot2[0] += s2a[e];
+        tot1[1] += s1e[e]; tot2[1] += s2e[e];
+      }
+    }
   }
+  if constexpr (STATS) flush_item_stats<2>(ms.stats, b, tot1, tot2, red);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(256) inject_materialize_kernel(SrcDesc sd, int C, float* __restrict__ out, int rows_per_cta) {
+template <int KIND, bool STATS>
+__global__ void __launch_bounds__(256) inject_materialize_kernel(SrcDesc sd, int C, float* __restrict__ out, int rows_per_cta,
+                                                                 MatStats ms) {
   grid_dep_wait();
   extern __shared__ int jtab[];
-  inject_materialize_tile<KIND>(sd, C, out, blockIdx.x, rows_per_cta, jtab);
+  inject_materialize_tile<KIND, STATS>(sd, C, out, blockIdx.x, rows_per_cta, jtab, ms);
 }
 
-// two tensors in one launch (the two operands of the first top-down step): tiles [0, tiles_a) belong to a
-template <int KIND>
+// two tensors in one launch (the two operands of the first top-down step): tiles [0, tiles_a) belong to a; the
+// statistics (if any) are those of tensor b, the step's "global" operand
+template <int KIND, bool STATS>
 __global__ void __launch_bounds__(256) inject_materialize2_kernel(SrcDesc sa, float* __restrict__ out_a, int tiles_a,
                                                                   SrcDesc sb, float* __restrict__ out_b, int C,
-                                                                  int rows_per_cta) {
+                                                                  int rows_per_cta, MatStats ms) {
   grid_dep_wait();
   extern __shared__ int jtab[];
-  if ((int)blockIdx.x < tiles_a) inject_materialize_tile<KIND>(sa, C, out_a, blockIdx.x, rows_per_cta, jtab);
-  else inject_materialize_tile<KIND>(sb, C, out_b, blockIdx.x - tiles_a, rows_per_cta, jtab);
+  if ((int)blockIdx.x < tiles_a) inject_materialize_tile<KIND, false>(sa, C, out_a, blockIdx.x, rows_per_cta, jtab, ms);
+  else inject_materialize_tile<KIND, STATS>(sb, C, out_b, blockIdx.x - tiles_a, rows_per_cta, jtab, ms);
 }
 
-static int materialize_rows() {
+static int materialize_rows(bool stats) {
   static const int rows = getenv("TDANET_MAT_ROWS") ? atoi(getenv("TDANET_MAT_ROWS")) : 16;
-  return rows;
+  return stats ? 2 * rows : rows;   // longer ranges where every CTA pays four halo rows
 }
 
-int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, cudaStream_t st) {  // out: ACT_T
+int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, const float* wa, const float* we,
+                              double* stats, cudaStream_t st) {  // out: ACT_T
   TD_REQUIRE(C % 4 == 0 && (long)src.L * C < (1L << 31), "inject_materialize: C=%d L=%d", C, src.L);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
-  const int rows = materialize_rows();
+  const bool with_stats = stats != nullptr;
+  const int rows = materialize_rows(with_stats);
+  const MatStats ms{wa, we, stats};
   dim3 grid(cdiv(src.L, rows), cdiv(C / 4, threads), B);
+  const size_t smem = (rows + 4) * sizeof(int);
   if (kind == SRC_INJECT_GATE) {
-    TD_LAUNCH_COOP((inject_materialize_kernel<SRC_INJECT_GATE>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
+    if (with_stats) TD_LAUNCH_COOP((inject_materialize_kernel<SRC_INJECT_GATE, true>), grid, threads, smem, st, src, C, out, rows, ms);
+    else TD_LAUNCH_COOP((inject_materialize_kernel<SRC_INJECT_GATE, false>), grid, threads, smem, st, src, C, out, rows, ms);
   } else if (kind == SRC_INJECT_ADD) {
-    TD_LAUNCH_COOP((inject_materialize_kernel<SRC_INJECT_ADD>), grid, threads, rows * sizeof(int), st, src, C, out, rows);
+    if (with_stats) TD_LAUNCH_COOP((inject_materialize_kernel<SRC_INJECT_ADD, true>), grid, threads, smem, st, src, C, out, rows, ms);
+    else TD_LAUNCH_COOP((inject_materialize_kernel<SRC_INJECT_ADD, false>), grid, threads, smem, st, src, C, out, rows, ms);
   } else {
     return fail(TDANET_EINVAL, "inject_materialize: kind %d", kind);
   }
@@ -607,16 +665,21 @@ int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float*
 }
 
 int launch_inject_materialize2(const SrcDesc& sa, float* out_a, const SrcDesc& sb, float* out_b, int kind, int B, int C,
-                               cudaStream_t st) {
+                               const float* wa, const float* we, double* stats, cudaStream_t st) {
   TD_REQUIRE(C % 4 == 0 && (long)sa.L * C < (1L << 31) && (long)sb.L * C < (1L << 31), "inject_materialize2: C=%d", C);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
-  const int rows = materialize_rows();
+  const bool with_stats = stats != nullptr;
+  const int rows = materialize_rows(with_stats);
+  const MatStats ms{wa, we, stats};
   const int tiles_a = cdiv(sa.L, rows);
   dim3 grid(tiles_a + cdiv(sb.L, rows), cdiv(C / 4, threads), B);
+  const size_t smem = (rows + 4) * sizeof(int);
   if (kind == SRC_INJECT_GATE) {
-    TD_LAUNCH_COOP((inject_materialize2_kernel<SRC_INJECT_GATE>), grid, threads, rows * sizeof(int), st, sa, out_a, tiles_a, sb, out_b, C, rows);
+    if (with_stats) TD_LAUNCH_COOP((inject_materialize2_kernel<SRC_INJECT_GATE, true>), grid, threads, smem, st, sa, out_a, tiles_a, sb, out_b, C, rows, ms);
+    else TD_LAUNCH_COOP((inject_materialize2_kernel<SRC_INJECT_GATE, false>), grid, threads, smem, st, sa, out_a, tiles_a, sb, out_b, C, rows, ms);
   } else if (kind == SRC_INJECT_ADD) {
-    TD_LAUNCH_COOP((inject_materialize2_kernel<SRC_INJECT_ADD>), grid, threads, rows * sizeof(int), st, sa, out_a, tiles_a, sb, out_b, C, rows);
+    if (with_stats) TD_LAUNCH_COOP((inject_materialize2_kernel<SRC_INJECT_ADD, true>), grid, threads, smem, st, sa, out_a, tiles_a, sb, out_b, C, rows, ms);
+    else TD_LAUNCH_COOP((inject_materialize2_kernel<SRC_INJECT_ADD, false>), grid, threads, smem, st, sa, out_a, tiles_a, sb, out_b, C, rows, ms);
   } else {
     return fail(TDANET_EINVAL, "inject_materialize2: kind %d", kind);
   }

@@ -113,6 +113,15 @@ static int prepare_weights(const Ctx& x) {
   return 0;
 }
 
+// The global-branch statistics of the first top-down step computed by the kernel that materialises its operand.
+// Measured on B200: at the training batch of 8 it removes a launch from a launch-bound chain (52.6 -> 53.5 steps/s);
+// at B = 64 the fused kernel is 47 us slower per block than the 20 us statistics launch it replaces (17.96 -> 18.40 ms
+// per inference step), so inference keeps the separate launch.  TDANET_FIRST_STATS=0 / 1 forces either form.
+static bool first_stats_fused(bool train) {
+  static const int knob = getenv("TDANET_FIRST_STATS") ? atoi(getenv("TDANET_FIRST_STATS")) : -1;
+  return knob < 0 ? train : knob != 0;
+}
+
 static SrcDesc plain_src(const float* x, int L) {
   SrcDesc s{};
   s.x = x; s.L = L;
@@ -311,9 +320,17 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     for (int k = 0; k < depth - 1; ++k) fused_live[k] = true;
     fused_live[first_step_partner(depth)] = true;
     Tag t("fused_materialize");
+    const int gi = first_step_partner(depth);
     for (int k = 0; k < depth; ++k)
-      if (fused_live[k])
-        if (int e = launch_inject_materialize(inj_src(k), inj_kind, B, C, x.at(p.fused[k]), x.bf(), x.st)) return e;
+      if (fused_live[k]) {
+        // x_fused[gi] is the "global" operand of the first top-down step: its global-branch GlobLN statistics ride
+        // in the kernel that writes it (no statistics launch for that step)
+        const bool st = k == gi && first_stats_fused(true);
+        const tdanet_la_t& la0 = w->last_layer[depth - 2];
+        if (int e = launch_inject_materialize(inj_src(k), inj_kind, B, C, x.at(p.fused[k]), x.bf(), x.st,
+                                              st ? la0.global_act.w : nullptr, st ? la0.global_embedding.w : nullptr,
+                                              st ? x.at<double>(p.st_la_g[depth - 2]) : nullptr)) return e;
+      }
   }
   // statistics of the local branch of every top-down step: independent of the chain below, so they run on the side
   // stream - the coarse scales first (one launch; the first steps of the chain need them), then the finest scale,
@@ -344,6 +361,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     }
   }
   // top-down fusion: last_layer[i](x_fused[i], i == depth-2 ? x_fused[i-1] : expanded)
+  bool first_global_stats_done = p.train && first_stats_fused(true);   // training: done by fused_materialize above
   for (int i = depth - 2; i >= 0; --i) {
     const tdanet_la_t& la = w->last_layer[i];
     SrcDesc loc = inj_src(i), glo;
@@ -361,7 +379,11 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       Tag t("la_combine_first");
       static const bool one_launch = !(getenv("TDANET_MAT2") && atoi(getenv("TDANET_MAT2")) == 0);
       if (one_launch) {
-        if (int e = launch_inject_materialize2(loc, x.at(p.fused_a), gsrc, x.at(p.fused_b), inj_kind, B, C, x.bf(), x.st)) return e;
+        const bool st = first_stats_fused(false);
+        if (int e = launch_inject_materialize2(loc, x.at(p.fused_a), gsrc, x.at(p.fused_b), inj_kind, B, C, x.bf(), x.st,
+                                               st ? la.global_act.w : nullptr, st ? la.global_embedding.w : nullptr,
+                                               st ? x.at<double>(p.st_la_g[i]) : nullptr)) return e;
+        first_global_stats_done = st;
       } else {
         if (int e = launch_inject_materialize(loc, inj_kind, B, C, x.at(p.fused_a), x.bf(), x.st)) return e;
         if (int e = launch_inject_materialize(gsrc, inj_kind, B, C, x.at(p.fused_b), x.bf(), x.st)) return e;
@@ -377,7 +399,10 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     dg.src = glo; dg.kind = gkind; dg.B = B; dg.C = C; dg.Lout = glo.L; dg.stride = 1; dg.nw = 2; dg.act_bf16 = x.bf();
     dg.w[0] = la.global_act.w; dg.w[1] = la.global_embedding.w; dg.stats = x.at<double>(p.st_la_g[i]);
     dg.rev = l2_order(2);
-    { Tag t("la_stats_global"); if (int e = launch_dw5(dg, x.st)) return e; }
+    if (!(i == depth - 2 && first_global_stats_done)) {
+      Tag t("la_stats_global");
+      if (int e = launch_dw5(dg, x.st)) return e;
+    }
     LaArgs l{};
     l.loc = loc; l.glo = glo; l.lkind = lkind; l.gkind = gkind; l.B = B; l.C = C;
     l.wl = la.local_embedding.w; l.wa = la.global_act.w; l.we = la.global_embedding.w;

@@ -67,11 +67,15 @@ int launch_dw_generic(const SrcDesc& src, int kind, int B, int C, int Lout, int 
 // wT[k, c] = w[c, k]   (coef.cu)
 int launch_weight_transpose(const float* w, float* wT, int C, int ks, cudaStream_t st);
 
-// out[b, t, :] = injected operand (SRC_INJECT_GATE / SRC_INJECT_ADD) written out, [B, src.L, C]
-int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, int act_bf16, cudaStream_t st);
-// two tensors in one launch
+// out[b, t, :] = injected operand (SRC_INJECT_GATE / SRC_INJECT_ADD) written out, [B, src.L, C].
+// stats != null: also the GlobLN statistics [B, 2, 2] (double, accumulated) of the two 5-tap depthwise convolutions
+// wa / we of the tensor written (zero padding) - what launch_dw5 with nw = 2 and no output would compute from it.
+int launch_inject_materialize(const SrcDesc& src, int kind, int B, int C, float* out, int act_bf16, cudaStream_t st,
+                              const float* wa = nullptr, const float* we = nullptr, double* stats = nullptr);
+// two tensors in one launch (the statistics are those of tensor b)
 int launch_inject_materialize2(const SrcDesc& sa, float* out_a, const SrcDesc& sb, float* out_b, int kind, int B, int C,
-                               int act_bf16, cudaStream_t st);
+                               int act_bf16, cudaStream_t st, const float* wa = nullptr, const float* we = nullptr,
+                               double* stats = nullptr);
 
 // LA combine (TDANet_best.py:277-292 with the three GlobLN folded into coef tables):
 //   out[t] = (cL.s*dw_l(xl)[t] + cL.h) * sigmoid(cA.s*dw_a(xg)[j] + cA.h) + (cE.s*dw_e(xg)[j] + cE.h)
