@@ -801,7 +801,8 @@ def run_ours(args):
             "clocks": {k: clk.summary()[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "roofline": None if roofline is None else {
                 "bound": "hbm", "kernel": roofline["kernel"], "achieved": roofline["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": roofline["frac"], "traffic": roofline["traffic"], "share": roofline["share_of_step"]},
+                "frac": roofline["frac"], "traffic": roofline["traffic"] if args.act_dtype == "fp32" else None,
+                "share": roofline["share_of_step"]},
             "step_frac": step_roofline["frac_of_survey_roofline"],
         }
         if cpu is not None:

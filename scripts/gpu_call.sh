@@ -62,6 +62,15 @@ import json
 d=json.loads(open('$out/${tag}_train_bf16.json').read().strip().splitlines()[-1])
 print('train bf16', d['value'], 'steps/s', d['ms_per_step'], 'ms; e2e', d['e2e']['value'], 'loss_after', d['loss_after'])
 ";;
+    abfork_*)
+      kv=${what#abfork_}
+      fn=$(echo "$kv" | tr '/' '_')
+      env $kv timeout 600 python bench.py --train-only --variant fork --steps 30 --warmup 5 --skip-cpu > $out/${tag}_forktrain_${fn}.json 2> $out/${tag}_forktrain_${fn}.err
+      echo "abfork $kv rc=$?"; python -c "
+import json
+d=json.loads(open('$out/${tag}_forktrain_${fn}.json').read().strip().splitlines()[-1])
+print('fork train', d['value'], 'steps/s', d['ms_per_step'], 'ms')
+";;
     abtrain_*)
       kv=${what#abtrain_}
       fn=$(echo "$kv" | tr '/' '_')

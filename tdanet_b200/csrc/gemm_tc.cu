@@ -530,10 +530,13 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   static const int bn_max = getenv("TDANET_GEMM_BN") ? atoi(getenv("TDANET_GEMM_BN")) : 256;  // tuning aid: 128 | 256
   p.BN = a.N % 256 == 0 && p.nsplit == 1 && bn_max >= 256 ? 256 : (a.N >= 128 ? 128 : a.N);
   p.tiles_m = cdiv(a.L, TC_BM);
-  // Small launches (the bottom-scale GEMMs of a training batch of 8: 8 row tiles) would occupy 16-48 of the 148 SMs
-  // with 256-column tiles, and a CTA's time is what it pulls through its SM's L2 port (~60 GB/s: A tile + W tile per
-  // K sweep) - so narrower tiles on more SMs, down to 32 columns, until at least half the SMs have a tile.
-  static const int bn_min = getenv("TDANET_GEMM_BN_MIN") ? atoi(getenv("TDANET_GEMM_BN_MIN")) : 32;
+  // Tile width by launch size (TDANET_GEMM_BN_MIN=32 ...): the bottom-scale GEMMs of a training batch of 8 have 8 row
+  // tiles, i.e. 16-48 CTAs at 256 columns, and a CTA's time is what it pulls through its SM's L2 port (~60 GB/s), so
+  // narrower tiles on more SMs shorten the launch itself.  Measured on the whole training step it is a loss, though:
+  // TDANetBest +1 % (noise), the fork TDANet 44.0 -> 39.2 steps/s - a persistent CTA takes its SM's whole shared
+  // memory, so a 128-CTA GEMM on the main stream evicts the side-stream kernels (weight gradients, loc_glo_fus /
+  // conv_pool chains) that a 16-CTA launch lets run beside it.  Off by default (minimum = 256 columns).
+  static const int bn_min = getenv("TDANET_GEMM_BN_MIN") ? atoi(getenv("TDANET_GEMM_BN_MIN")) : 256;
   while (p.BN > bn_min && p.BN % 32 == 0 && (long)a.B * p.tiles_m * (a.N / p.BN) * 2 < num_sms) p.BN /= 2;
   p.tiles_n = a.N / p.BN;
   p.total = a.B * p.tiles_m * p.tiles_n;
