@@ -578,7 +578,17 @@ __device__ __forceinline__ void inject_materialize_tile(const SrcDesc& sd, int C
 #pragma unroll
       for (int i = 0; i < 5; ++i) win[i] = vzero<V>();
     }
-    for (int t = t0 - H; t < t1 + H; t += R) {
+    if constexpr (!STATS) {   // the plain copy: every row of the range is inside the tensor
+      for (int t = t0; t < t1; t += R) {
+        vf<V> r[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) r[i] = t + i < t1 ? src.load_raw(t + i) : vzero<V>();
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          if (t + i < t1) astore<V>(op + (t + i) * C, src.finalize(r[i], t + i));
+      }
+    }
+    for (int t = t0 - H; STATS && t < t1 + H; t += R) {
       vf<V> r[R];
 #pragma unroll
       for (int i = 0; i < R; ++i) {
