@@ -74,7 +74,7 @@ static int bgemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
 // Dependencies are cudaEventRecord / cudaStreamWaitEvent pairs, which stream capture turns into graph edges, so a
 // captured training step keeps the concurrency.
 struct SideStreams {
-  cudaStream_t w = nullptr, l = nullptr, f[2] = {nullptr, nullptr};
+  cudaStream_t w = nullptr, l = nullptr, f[2] = {nullptr, nullptr}, g = nullptr;
   std::vector<cudaEvent_t> events;
   size_t next = 0;
   int init() {
@@ -83,6 +83,7 @@ struct SideStreams {
     TD_CUDA(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking));
     TD_CUDA(cudaStreamCreateWithFlags(&f[0], cudaStreamNonBlocking));
     TD_CUDA(cudaStreamCreateWithFlags(&f[1], cudaStreamNonBlocking));
+    TD_CUDA(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
     events.resize(512);
     for (auto& e : events) TD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return 0;
@@ -275,14 +276,30 @@ static int launch_dw_bwd(const BCtx& x, DwBwdArgs& a, int ks, int nw) {
   return 0;
 }
 
-static int launch_la_bwd_a(LaBwdArgs& a, int ks, cudaStream_t st) {
+// pass G alone (raw_b / raw_e = the global-branch conv outputs: forward quantities, independent of any gradient)
+static int launch_la_bwd_g(LaBwdArgs& a, int ks, cudaStream_t st) {
+  dim3 grid;
+  int threads;
+  const int grows = pick_rows(a.Lg, a.C / 4, a.B, 16);
+  row_grid(a.Lg, a.C / 4, a.B, grows, grid, threads);
+  if (a.glo_bf16) {
+    if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5, true>), grid, threads, 0, st, a, grows);
+    else TD_LAUNCH((la_bwd_g_kernel<1, true>), grid, threads, 0, st, a, grows);
+  } else if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5>), grid, threads, 0, st, a, grows);
+  else TD_LAUNCH((la_bwd_g_kernel<1>), grid, threads, 0, st, a, grows);
+  return 0;
+}
+
+static int launch_la_bwd_a(LaBwdArgs& a, int ks, cudaStream_t st, bool g_done = false) {
   TD_REQUIRE(a.C % 4 == 0, "la_bwd: C=%d", a.C);
   TD_REQUIRE(ks == 5 || ks == 1, "la_bwd: ks=%d", ks);
   dim3 grid;
   int threads;
   const int grows = pick_rows(a.Lg, a.C / 4, a.B, 16);  // global rows per thread of the G and F passes
   row_grid(a.Lg, a.C / 4, a.B, grows, grid, threads);
-  if (a.glo_bf16) {
+  if (g_done) {
+    // raw_b / raw_e were computed ahead of the chain (uconv_block_backward: stream `g`)
+  } else if (a.glo_bf16) {
     if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5, true>), grid, threads, 0, st, a, grows);
     else TD_LAUNCH((la_bwd_g_kernel<1, true>), grid, threads, 0, st, a, grows);
   } else if (ks == 5) TD_LAUNCH((la_bwd_g_kernel<5>), grid, threads, 0, st, a, grows);
@@ -487,7 +504,7 @@ static int dgrad(const BCtx& x, const float* A, size_t wt, size_t aux, float* D,
 static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdanet_la_t& gla, const SrcDesc& loc, int lkind,
                        const float* glo, int Lg, const NormRef& nL, const NormRef& nA, const NormRef& nE,
                        const size_t bs[3], const float* dout, float* d_loc_in, int acc_loc, float* d_glo_in, int acc_glo,
-                       cudaStream_t local_st = nullptr, int glo_bf16 = 0) {
+                       cudaStream_t local_st = nullptr, int glo_bf16 = 0, float* pre_rawb = nullptr, float* pre_rawe = nullptr) {
   const Plan& p = *x.p;
   const int B = p.B, C = x.c->in_channels, Ll = loc.L;
   LaBwdArgs a{};
@@ -497,11 +514,12 @@ static int la_backward(const BCtx& x, int ks, const tdanet_la_t& la, const tdane
   const int ts = x.tset;
   a.d_loc = x.at(p.t_dloc[ts]); a.raw_a = x.at(p.t_rawa[ts]);
   a.d_act = x.at(p.t_dact[ts]); a.d_emb = x.at(p.t_demb[ts]); a.raw_b = x.at(p.t_rawb[ts]); a.raw_e = x.at(p.t_rawe[ts]);
+  if (pre_rawb) { a.raw_b = pre_rawb; a.raw_e = pre_rawe; }   // pass G already done into per-step buffers
   a.dgamma[0] = x.gp(gla.local_embedding.gamma); a.dbeta[0] = x.gp(gla.local_embedding.beta);
   a.dgamma[1] = x.gp(gla.global_act.gamma); a.dbeta[1] = x.gp(gla.global_act.beta);
   a.dgamma[2] = x.gp(gla.global_embedding.gamma); a.dbeta[2] = x.gp(gla.global_embedding.beta);
   for (int i = 0; i < 3; ++i) a.S[i] = x.at<double>(bs[i]);
-  { Tag t(ks == 5 ? "bwd_la_a" : "bwd_lgf_a"); if (int e = launch_la_bwd_a(a, ks, x.st)) return e; }
+  { Tag t(ks == 5 ? "bwd_la_a" : "bwd_lgf_a"); if (int e = launch_la_bwd_a(a, ks, x.st, pre_rawb != nullptr)) return e; }
   Tag t(ks == 5 ? "bwd_la_dw" : "bwd_lgf_dw");
   DwBwdArgs d{};
   d.g[0] = gln_grad(a.d_loc, a.raw_a, nL, a.S[0]);
@@ -702,11 +720,34 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
     if (int e = x.side->order(x.st, x.side->f[0])) return e;
     if (int e = x.side->order(x.st, x.side->f[1])) return e;
   }
+  // Pass G of every top-down step (raw_b / raw_e = the global-branch conv outputs of the step's "global" operand) reads
+  // forward tensors only: all of them run ahead of the chain on stream `g`, into per-step buffers, instead of as the
+  // first launch of every step on the critical path (12 + 10 + 8 + 9 us per block at B = 8).
+  // Measured neutral (52.6 vs 52.5 steps/s: the join at the end of the top-down phase waits for the loc_glo_fus streams,
+  // not for the main chain), so it stays off; TDANET_LA_G_AHEAD=1 enables it.
+  static const bool g_ahead = getenv("TDANET_LA_G_AHEAD") && atoi(getenv("TDANET_LA_G_AHEAD")) == 1;
+  cudaEvent_t g_done[TDANET_MAX_DEPTH] = {};
+  if (g_ahead) {
+    if (int e = x.side->order(x.st, x.side->g)) return e;
+    for (int i = 0; i <= depth - 2; ++i) {
+      const bool first = i == depth - 2;
+      LaBwdArgs ga{};
+      ga.glo = first ? x.at(p.fused[gi]) : x.at(p.expanded[i + 1]);
+      ga.glo_bf16 = abf; ga.Lg = first ? p.L[gi] : p.L[i + 1]; ga.B = B; ga.C = C;
+      ga.wa = w->last_layer[i].global_act.w; ga.we = w->last_layer[i].global_embedding.w;
+      ga.raw_b = x.at(p.t_rawb_step[i]); ga.raw_e = x.at(p.t_rawe_step[i]);
+      Tag t("bwd_la_a");
+      if (int e = launch_la_bwd_g(ga, 5, x.side->g)) return e;
+      g_done[i] = x.side->events[x.side->next++ % x.side->events.size()];
+      TD_CUDA(cudaEventRecord(g_done[i], x.side->g));
+    }
+  }
   for (int i = 0; i <= depth - 2; ++i) {
     const tdanet_la_t& la = w->last_layer[i];
     const bool first = i == depth - 2;  // the first forward step: its "global" input is x_fused[gi]
     const int Lg = first ? p.L[gi] : p.L[i + 1];
     const float* glo = first ? x.at(p.fused[gi]) : x.at(p.expanded[i + 1]);
+    if (g_ahead) TD_CUDA(cudaStreamWaitEvent(x.st, g_done[i], 0));
     const NormRef nL = norm_ref(x, p.st_la_l[i], 2, (double)p.L[i] * C, la.local_embedding.gamma, la.local_embedding.beta);
     const NormRef nA = norm_ref(x, p.st_la_g[i], 4, (double)Lg * C, la.global_act.gamma, la.global_act.beta);
     const NormRef nE = norm_ref(x, p.st_la_g[i] + 2 * sizeof(double), 4, (double)Lg * C, la.global_embedding.gamma, la.global_embedding.beta);
@@ -724,7 +765,8 @@ static int uconv_block_backward(const BCtx& x, const float* in, const float* d_y
     if (i == 1 && wres_done) TD_CUDA(cudaStreamWaitEvent(x.st, wres_done, 0));  // t_rawa[1] held res_conv's fp32 operand
     if (int e = la_backward(x.on(x.st, i & 1), 5, la, gw->last_layer[i], bplain(x.at(p.fused[i]), p.L[i], abf), SRC_PLAIN, glo, Lg,
                             nL, nA, nE, p.bs_la[i], x.at(p.g_exp[i]), x.at(p.g_fused[i]), fused_written[i], d_glo,
-                            first ? (int)fused_written[gi] : 0, sl, abf)) return e;
+                            first ? (int)fused_written[gi] : 0, sl, abf,
+                            g_ahead ? x.at(p.t_rawb_step[i]) : nullptr, g_ahead ? x.at(p.t_rawe_step[i]) : nullptr)) return e;
     fused_written[i] = true;
     if (first) fused_written[gi] = true;
     local_done[i] = x.side->events[x.side->next++ % x.side->events.size()];

@@ -70,6 +70,8 @@ struct Plan {
   // LA backward temporaries, TDANET_LA_TEMP_SETS sets: the top-down steps alternate between sets 0 / 1 so that the
   // local-branch kernels of step i (side stream) overlap step i+1; the loc_glo_fus chain (side stream) owns set 2
   size_t t_dloc[4], t_rawa[4], t_dact[4], t_demb[4], t_rawb[4], t_rawe[4];  // sets 0/1: top-down steps, 2/3: loc_glo_fus chains
+  // per top-down step: raw conv outputs of the global branch (pass G of the LA backward), computed ahead of the chain
+  size_t t_rawb_step[TDANET_MAX_DEPTH], t_rawe_step[TDANET_MAX_DEPTH];
   size_t g_ga_out2;  // second accumulator of the global feature's gradient (the two loc_glo_fus streams), summed at the join
   size_t g_ga_out, g_fc2, g_ffn, g_fc1, g_ga_mid, g_attn_out, g_ctx, g_qkv, g_attn_in, g_ga_in;
   size_t att_p, att_ds, ln_rows;
@@ -338,6 +340,11 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
     p.t_demb[s] = p.act(nullptr, Lg_max, C);
     p.t_rawb[s] = p.act(nullptr, Lg_max, C);
     p.t_rawe[s] = p.act(nullptr, Lg_max, C);
+  }
+  for (int i = 0; i < depth - 1; ++i) {
+    const int Lg = i == depth - 2 ? p.L[first_step_partner(depth)] : p.L[i + 1];
+    p.t_rawb_step[i] = p.act(nullptr, Lg, C);
+    p.t_rawe_step[i] = p.act(nullptr, Lg, C);
   }
   p.g_ga_out = p.act("g_ga_out", Lb, C);
   p.g_ga_out2 = p.act(nullptr, Lb, C);

@@ -50,11 +50,13 @@ def main():
     dist.all_reduce(loss_mean, op=dist.ReduceOp.SUM)
     loss_mean /= world
     ok = True
+    solo = dist.new_group(ranks=[0])           # (collective: every rank calls it) a one-rank group for the reference run
     if rank == 0:
         m1 = make(1000)
         m1.attn_group = B                      # every shard attends within itself
-        ts1 = look2hear.system.TrainingStep(m1, loss_fn, lr=1e-3, clip_grad_norm=5.0, process_group=None)
-        ts1._world = lambda: 1
+        # a single-process TrainingStep beside the distributed one: its group has one member, so its constructor
+        # broadcast and its gradient all-reduce are no-ops (with the default group rank 0 would wait for rank 1 forever)
+        ts1 = look2hear.system.TrainingStep(m1, loss_fn, lr=1e-3, clip_grad_norm=5.0, process_group=solo)
         ts1.params.zero_grad()
         loss1 = ts1.forward_backward(mix_all.to(dev), tgt_all.to(dev))
         rel = ((grad_ddp - ts1.params.grad).norm() / ts1.params.grad.norm()).item()

@@ -25,6 +25,15 @@ def _free_port():
 def test_two_rank_training_step_matches_single_process():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "ddp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    print(r.stdout[-3000:], r.stderr[-3000:])
-    assert r.returncode == 0 and "[ddp_check] PASS" in r.stdout
+    # own process group + kill of the whole group on a timeout: a hung rank must not survive the test and keep a
+    # spinning NCCL kernel on the GPU under whatever runs next
+    import signal
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=300)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("ddp_worker timed out (killed):\n" + out[-2000:] + err[-2000:])
+    print(out[-3000:], err[-3000:])
+    assert proc.returncode == 0 and "[ddp_check] PASS" in out
