@@ -67,9 +67,30 @@ def pin_to_gpu_numa_node(local):
                 cpus.update(range(int(a), int(b or a) + 1))
         allowed = os.sched_getaffinity(0)
         use = cpus & allowed
-        if use:
+        if len(use) >= 4:
             os.sched_setaffinity(0, use)
-            return {"numa_node": node, "cores": len(use)}
+            return {"numa_node": node, "cores": len(use), "how": "sysfs"}
+    except Exception:
+        pass
+    try:
+        # containers often hide the PCI devices' numa_node (-1): the driver's own table still has the affinity
+        import re
+        txt = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        txt = re.sub(r"\x1b\[[0-9;]*m", "", txt)
+        lines = [ln for ln in txt.splitlines() if ln.strip()]
+        head = [t.strip() for t in lines[0].split("\t")]
+        col = head.index("CPU Affinity")
+        row = next(ln for ln in lines[1:] if ln.split("\t")[0].strip() == f"GPU{local}")
+        spec = [t.strip() for t in row.split("\t")][col]   # (the header's first cell is empty: columns line up)
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if len(use) >= 4 and use != allowed:
+            os.sched_setaffinity(0, use)
+            return {"cpu_affinity": spec, "cores": len(use), "how": "nvidia-smi topo"}
     except Exception:
         pass
     return None

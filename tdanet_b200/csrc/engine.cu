@@ -85,6 +85,7 @@ static thread_local FwdSide* t_fside = nullptr;  // set by forward() for the dur
 static int gemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
   if (x.c->gemm_mode == TDANET_GEMM_FP32) return launch_gemm_simt(g, x.st);
   g.W_aux = x.at(aux_off);
+  g.narrow = !x.p->train;   // inference: the main stream has the SMs to itself while a GEMM runs
   return launch_gemm_tc(g, x.c->gemm_mode, x.st);
 }
 
@@ -162,6 +163,7 @@ static int global_attention(const Ctx& x, bool ln_pe_done) {
       if (int e = launch_gemm_simt(g, x.st)) return e;
     } else {
       g.W_aux = x.at(p.aux_in) + (size_t)2 * C * C;   // the same rows of the prepared (TF32) copy
+      g.narrow = 1;
       if (int e = launch_gemm_tc(g, x.c->gemm_mode, x.st)) return e;
     }
   } else {

@@ -536,7 +536,10 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   // TDANetBest +1 % (noise), the fork TDANet 44.0 -> 39.2 steps/s - a persistent CTA takes its SM's whole shared
   // memory, so a 128-CTA GEMM on the main stream evicts the side-stream kernels (weight gradients, loc_glo_fus /
   // conv_pool chains) that a 16-CTA launch lets run beside it.  Off by default (minimum = 256 columns).
-  static const int bn_min = getenv("TDANET_GEMM_BN_MIN") ? atoi(getenv("TDANET_GEMM_BN_MIN")) : 256;
+  // The inference forward has no such neighbours while its bottom-scale GEMMs run (GemmArgs::narrow): there a small
+  // launch (a 64-mixture job split over 8 GPUs: 8 row tiles) takes the narrow tiles.
+  static const int bn_env = getenv("TDANET_GEMM_BN_MIN") ? atoi(getenv("TDANET_GEMM_BN_MIN")) : 0;
+  const int bn_min = bn_env > 0 ? bn_env : (a.narrow ? 32 : 256);
   while (p.BN > bn_min && p.BN % 32 == 0 && (long)a.B * p.tiles_m * (a.N / p.BN) * 2 < num_sms) p.BN /= 2;
   p.tiles_n = a.N / p.BN;
   p.total = a.B * p.tiles_m * p.tiles_n;

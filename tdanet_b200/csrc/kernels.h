@@ -233,6 +233,7 @@ struct GemmArgs {
   // against a bf16 copy of W in W_aux)
   int d_bf16, a_bf16;
   int rev;  // tensor-core path: tiles of the last batch item first (L2 reuse of what the producer wrote last)
+  int narrow;  // tensor-core path: nothing else competes for the SMs (inference forward): narrow tiles for small launches
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st);
