@@ -315,29 +315,37 @@ class SeparationEngine:
             check(lib.tdanet_backward(C.byref(self.cfg), C.byref(weights), C.byref(grad_weights), wav.data_ptr(),
                                       d_est.data_ptr(), B, T, ws.data_ptr(), ws.numel(), stream))
 
+    def graph_slot(self, weights: Weights, B: int, T: int, device, attn_group: int = 0, slot: int = 0,
+                   example: Optional[torch.Tensor] = None):
+        """(graph, static_in [B, T], static_out [B, n_src, T]) of the captured forward for this shape; one capture per
+        (shape, modes, weights, slot).  Slots are independent input / output buffers over the same workspace - a
+        pipeline alternates two of them so that it can copy into / out of the buffers of one step while the other
+        step's replay runs (look2hear.system.separate_pipelined), with no staging copies."""
+        device = torch.device(device)
+        key = (device, B, T, attn_group, self.cfg.gemm_mode, self.cfg.act_dtype, C.addressof(weights), slot)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = torch.zeros(B, T, dtype=torch.float32, device=device) if example is None else example.clone()
+            static_out = torch.empty(B, self.cfg.num_sources, T, dtype=torch.float32, device=device)
+            s = torch.cuda.Stream(device)
+            s.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(s):   # warm-up outside capture (function attributes, workspace)
+                self.forward(weights, static_in, attn_group, out=static_out)
+            torch.cuda.current_stream(device).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.forward(weights, static_in, attn_group, out=static_out)
+            entry = (g, static_in, static_out, self._ws[device])
+            self._graphs[key] = entry
+        return entry[0], entry[1], entry[2]
+
     def forward_graphed(self, weights: Weights, wav: torch.Tensor, attn_group: int = 0) -> torch.Tensor:
         """Same as forward() but replays one captured CUDA graph per (B, T, group, weights) key.
 
         The returned tensor is the graph's static output buffer: it is overwritten by the next call.
         """
         B, T = wav.shape
-        key = (wav.device, B, T, attn_group, self.cfg.gemm_mode, self.cfg.act_dtype, C.addressof(weights))
-        entry = self._graphs.get(key)
-        if entry is None:
-            static_in = torch.empty_like(wav)
-            static_out = torch.empty(B, self.cfg.num_sources, T, dtype=torch.float32, device=wav.device)
-            static_in.copy_(wav)
-            s = torch.cuda.Stream(wav.device)
-            s.wait_stream(torch.cuda.current_stream(wav.device))
-            with torch.cuda.stream(s):   # warm-up outside capture (function attributes, workspace)
-                self.forward(weights, static_in, attn_group, out=static_out)
-            torch.cuda.current_stream(wav.device).wait_stream(s)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.forward(weights, static_in, attn_group, out=static_out)
-            entry = (g, static_in, static_out, self._ws[wav.device])
-            self._graphs[key] = entry
-        g, static_in, static_out, _ = entry
+        g, static_in, static_out = self.graph_slot(weights, B, T, wav.device, attn_group, 0, example=wav)
         static_in.copy_(wav)
         g.replay()
         return static_out

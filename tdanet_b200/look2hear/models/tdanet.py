@@ -137,6 +137,12 @@ class _TDANetCommon(BaseModel):
             self._packed_sig = sig
         return self._packed
 
+    def graph_slot(self, batch: int, n_samples: int, slot: int = 0):
+        """(graph, static_in [B, T], static_out [B, n_src, T]) of this model's captured inference forward (see
+        SeparationEngine.graph_slot); used by look2hear.system.separate_pipelined."""
+        dev = next(self.parameters()).device
+        return self._engine.graph_slot(self._weights(), batch, n_samples, dev, self.attn_group, slot)
+
     def pad_input(self, input, window, stride):
         """Kept for API parity (TDANet_best.py:465-479); the CUDA encoder folds this padding into its
         indexing and never materialises it."""
