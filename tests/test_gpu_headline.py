@@ -128,7 +128,7 @@ def test_four_ms_shards_match_oracle(B):
 # eager PyTorch TF32 on B200, same model / seed / batch (worst per-tensor max-rel, whole-gradient rel-L2), as measured
 # by this test on the box and committed in profiles/r02_tf32_grad_eager.json; used only if the live measurement
 # cannot run
-EAGER_TF32_MEASURED = (1e-3, 1e-3)
+EAGER_TF32_MEASURED = (1.61e-2, 1.92e-3)
 
 
 def _grad_table(named, ref):
