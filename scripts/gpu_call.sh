@@ -7,6 +7,11 @@ out=gpurun_out
 mkdir -p $out
 for what in "$@"; do
   case $what in
+    smoke)
+      # a hung kernel must not eat the call: stop here when the tiny forward does not come back
+      timeout -k 5 240 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1
+      rc=$?; echo "smoke rc=$rc $(tail -2 $out/${tag}_smoke.log)"
+      if [ $rc -ne 0 ]; then exit $rc; fi;;
     tests)
       timeout 1500 python -m pytest tests -m gpu -q -s > $out/${tag}_gpu_tests.log 2>&1
       echo "tests rc=$? $(tail -1 $out/${tag}_gpu_tests.log)";;
@@ -36,6 +41,13 @@ for what in "$@"; do
       $cmd > $out/${tag}_ncu_gemm_plain.log 2>&1 &&
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 12 -c 6 -f -o $out/${tag}_gemm $cmd > $out/${tag}_ncu_gemm.log 2>&1
       echo "ncu_gemm rc=$?";;
+    ncuk_*)
+      # ncu --set full of the launches whose name matches a regex (third block on): ncuk_<regex>[:skip[:count]]
+      spec=${what#ncuk_}; rx=${spec%%:*}; rest=${spec#*:}; skip=12; cnt=6
+      if [ "$rest" != "$spec" ]; then skip=${rest%%:*}; c2=${rest#*:}; if [ "$c2" != "$rest" ]; then cnt=$c2; fi; fi
+      cmd="python bench.py --steps 1 --warmup 3 --no-graph --skip-train --skip-longform --skip-cpu --skip-eager --skip-2ms --detail-out $out/${tag}_ncu_dummy.json"
+      timeout -k 5 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -f -o $out/${tag}_k_${rx} $cmd > $out/${tag}_ncuk_${rx}.log 2>&1
+      echo "ncuk $rx rc=$?";;
     ncu_list)
       cmd="python bench.py --steps 1 --warmup 3 --no-graph --skip-train --skip-longform --skip-cpu --skip-eager --skip-2ms --detail-out $out/${tag}_ncu_dummy.json"
       $cmd > $out/${tag}_ncu_list_plain.log 2>&1 &&

@@ -164,6 +164,120 @@ __device__ __forceinline__ void cp_async_act(ACT_T* dst, const ACT_T* src, bool 
   }
 }
 
+// ----------------------------------------------------------------------------- bulk (TMA 1-D) staging
+// A CTA of 128 threads x 4 channels covers all 512 channels of its rows, so the rows of a chunk are ONE contiguous
+// range of global memory and a ring stage [row][512] is its image: one elected thread fills a stage with three
+// cp.async.bulk copies that complete on an mbarrier, instead of every thread issuing 20 cp.async of its own
+// (~150 of the ~1000 instructions a chunk of la_stream_kernel costs per thread were address arithmetic and copies).
+// full[s]: the stage has landed (transaction bytes); empty[s]: one arrival per warp after its last read of the stage.
+__device__ __forceinline__ uint32_t sb_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sb_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sb_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sb_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sb_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool sb_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(sb_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void sb_wait(uint64_t* bar, uint32_t parity) {
+  while (!sb_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void sb_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_u32(dst)),
+               "l"(src), "r"(bytes), "r"(sb_u32(bar))
+               : "memory");
+}
+
+// Two-stage ring protocol of the streaming kernels.  In the LA kernels stage 1 has one extra phase at the start: the
+// four rows ahead of the CTA's first chunk are parked in it while chunk 0 lands in stage 0.
+struct SbRing {
+  uint64_t* full;   // [2]
+  uint64_t* empty;  // [2]
+  // the copying thread: stage k & 1 may be overwritten with chunk k (PARK: stage 1 began with the parked rows)
+  template <bool PARK = true>
+  __device__ __forceinline__ void acquire(int k) const {
+    const int s = k & 1, u = k >> 1;
+    sb_wait(empty + s, (PARK && s) ? (u & 1) : ((u & 1) ^ 1));
+  }
+  __device__ __forceinline__ void wait_full(int k) const { sb_wait(full + (k & 1), (k >> 1) & 1); }
+  // every warp, after its last read of stage s
+  __device__ __forceinline__ void release(int s) const {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) sb_arrive(empty + s);
+  }
+};
+// thread 0 of a CTA of `nwarps` warps; the caller synchronises the CTA afterwards
+__device__ __forceinline__ SbRing sb_ring_init(uint64_t* bars, int nwarps) {
+  if (threadIdx.x == 0) {
+    sb_init(bars + 0, 1); sb_init(bars + 1, 1);            // full: the copying thread's arrive.expect_tx
+    sb_init(bars + 2, nwarps); sb_init(bars + 3, nwarps);  // empty: one arrival per warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  return SbRing{bars, bars + 2};
+}
+// The same protocol with `ns` stages (2 .. SB_MAX_STAGES) and a prefetch distance of ns - 1 chunks: what limits these
+// streaming kernels is the number of bytes in flight per SM (bandwidth x latency, ~90 KB per SM at 6.4 TB/s), and with
+// bulk copies a deeper ring costs shared memory only - no registers, no instructions.  PARK: the rows ahead of the
+// CTA's first chunk are parked in the last stage, which therefore starts with one extra phase.
+constexpr int SB_MAX_STAGES = 4;
+struct SbCursor {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void next(int ns) {
+    if (++stage == ns) { stage = 0; phase ^= 1; }
+  }
+};
+struct SbRingN {
+  uint64_t* full;   // [ns]
+  uint64_t* empty;  // [ns]
+  int ns;
+  template <bool PARK>
+  __device__ __forceinline__ void acquire(const SbCursor& c) const {   // the copying thread
+    sb_wait(empty + c.stage, (PARK && c.stage == ns - 1) ? c.phase : (c.phase ^ 1));
+  }
+  __device__ __forceinline__ void wait_full(const SbCursor& c) const { sb_wait(full + c.stage, c.phase); }
+  __device__ __forceinline__ void release(int stage) const {          // every warp, after its last read of the stage
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) sb_arrive(empty + stage);
+  }
+};
+__device__ __forceinline__ SbRingN sb_ringn_init(uint64_t* bars, int ns, int nwarps) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ns; ++s) { sb_init(bars + s, 1); sb_init(bars + ns + s, nwarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  return SbRingN{bars, bars + ns, ns};
+}
+constexpr size_t SB_BAR_BYTES = 2 * SB_MAX_STAGES * sizeof(uint64_t);
+// stages of the bulk rings of the two statistics kernels (TDANET_BULK_STAGES).  Measured on B200 (B = 64): deeper
+// rings are SLOWER - 2 / 3 / 4 stages: 17.59 / 18.16 / 18.78 ms per step, every streaming role slower - so more
+// bytes in flight is not what these kernels lack; 2 is the default.  spp_dw keeps two stages unconditionally.
+static inline int bulk_stages() {
+  static const int n = getenv("TDANET_BULK_STAGES") ? atoi(getenv("TDANET_BULK_STAGES")) : 2;
+  return n < 2 ? 2 : (n > SB_MAX_STAGES ? SB_MAX_STAGES : n);
+}
+// which streaming kernels stage their rows with cp.async.bulk (bit mask: 1 la_stream, 2 local statistics, 4 global
+// statistics, 8 spp_dw); TDANET_BULK=0 restores the per-thread cp.async rings everywhere (A/B measurements)
+static inline int bulk_mask() {
+  static const int m = getenv("TDANET_BULK") ? atoi(getenv("TDANET_BULK")) : 15;
+  return m;
+}
+
 // ----------------------------------------------------------------------------- dw k=5
 template <int KIND, int V, int NW, int S, int R, bool WRITE, bool STATS, bool EDGE>
 __device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0, int t1, const int* jtab, int tab0,
@@ -287,9 +401,11 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
 // thread and stored plainly (no atomics, no zero-fill); at most one row per tile is computed twice.
 // RING (stages, 0 = off): the R*S new input rows of a chunk are prefetched RING-1 chunks ahead with cp.async into a ring of
 // thread-private shared-memory columns (`ringcol`), so loads stay in flight while the current chunk is computed.
-template <int KIND, int S, bool EDGE, int RING>
+template <int KIND, int S, bool EDGE, int RING, bool BULK = false>
 __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, int t0, int tw, int tc, const int2* bins,
-                                              int ja, int nb, ACT_T* ringcol, float& tot1, float& tot2) {
+                                              int ja, int nb, ACT_T* ringcol, float& tot1, float& tot2,
+                                              SbRingN rb = SbRingN{}) {
+  static_assert(!BULK || (!EDGE && RING == 2), "bulk staging: interior CTAs (RING: any non-zero value, rb.ns stages)");
   constexpr int V = 4, R = (S == 1) ? 8 : 4;
   Src<KIND, V, EDGE> src;
   src.init(a.src, b, ch, a.C, nullptr, 0);
@@ -303,9 +419,20 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
   constexpr int NR = (R - 1) * S + 5, CARRY = 5 - S;
   vf<V> xr[NR];
   const int colw = blockDim.x * V;
+  SbCursor pc, cc;  // BULK: producer (thread 0) / consumer positions in the ring
   auto issue = [&](int t) {  // the new input rows of the chunk of output rows t .. t+R-1
-    ACT_T* st = ringcol + ((((t - t0) / R) % (RING ? RING : 1)) * (R * S)) * colw;
     const int base = t * S - 2 + CARRY;
+    if constexpr (BULK) {  // the CTA covers all 512 channels: the chunk's rows are one contiguous range
+      if (threadIdx.x == 0) {
+        rb.acquire<false>(pc);
+        constexpr uint32_t bytes = R * S * 512 * sizeof(ACT_T);
+        sb_expect_tx(rb.full + pc.stage, bytes);
+        sb_bulk_g2s(ringcol + (pc.stage * (R * S)) * colw, src.x + (size_t)base * src.C, bytes, rb.full + pc.stage);
+        pc.next(rb.ns);
+      }
+      return;
+    }
+    ACT_T* st = ringcol + ((((t - t0) / R) % (RING ? RING : 1)) * (R * S)) * colw;
 #pragma unroll
     for (int i = 0; i < R * S; ++i) {
       const int row = base + i;
@@ -313,7 +440,10 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
       cp_async_act(st + i * colw, src.x + (ok ? row : 0) * src.C, ok);
     }
   };
-  if constexpr (RING != 0) {
+  if constexpr (BULK) {
+    for (int k = 0; k < rb.ns - 1; ++k)
+      if (t0 + k * R < tc) issue(t0 + k * R);
+  } else if constexpr (RING != 0) {
     issue(t0);
     asm volatile("cp.async.commit_group;" ::: "memory");
     if constexpr (RING == 3) {
@@ -331,7 +461,15 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
 #pragma unroll
     for (int i = 0; i < CARRY; ++i) xr[i] = xr[R * S + i];
     const int base = t * S - 2 + CARRY;
-    if constexpr (RING != 0) {
+    if constexpr (BULK) {
+      if (t + (rb.ns - 1) * R < tc) issue(t + (rb.ns - 1) * R);
+      rb.wait_full(cc);
+      const ACT_T* st = ringcol + (cc.stage * (R * S)) * colw;
+#pragma unroll
+      for (int i = 0; i < R * S; ++i) xr[CARRY + i] = alds<V>(st + i * colw);
+      rb.release(cc.stage);
+      cc.next(rb.ns);
+    } else if constexpr (RING != 0) {
       if (t + (RING - 1) * R < tc) issue(t + (RING - 1) * R);
       asm volatile("cp.async.commit_group;" ::: "memory");
       if constexpr (RING == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
@@ -384,13 +522,13 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
   }
 }
 
-template <int KIND, int S, int LB, int RING>
-__global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(DwArgs a, int bins_per_cta) {
-  grid_dep_wait();
-  extern __shared__ __align__(16) unsigned char pool_smem[];  // [ring: 2 stages x R*S rows x blockDim.x*4 ACT_T][bins]
+template <int KIND, int S, int LB, int RING, bool BULK = false>
+__global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(DwArgs a, int bins_per_cta, int ns) {
+  // [ring: RING (BULK: ns) stages x R*S rows x blockDim.x*4 ACT_T][bins][BULK: full[ns], empty[ns] mbarriers]
+  extern __shared__ __align__(16) unsigned char pool_smem[];
   __shared__ double red[64];
   constexpr int V = 4, R = (S == 1) ? 8 : 4;
-  const size_t ring_b = (size_t)RING * R * S * blockDim.x * V * sizeof(ACT_T);
+  const size_t ring_b = (size_t)(BULK ? ns : RING) * R * S * blockDim.x * V * sizeof(ACT_T);
   int2* bins = reinterpret_cast<int2*>(pool_smem + ring_b);  // (lo, hi) of the tile's bins, plus one
   ACT_T* ringcol = reinterpret_cast<ACT_T*>(pool_smem) + threadIdx.x * V;
   const int b = a.rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
@@ -401,7 +539,10 @@ __global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(D
     const long j = ja + i;
     bins[i] = make_int2((int)((j * L) / Lb), (int)(((j + 1) * L + Lb - 1) / Lb));
   }
+  SbRingN rb{};
+  if constexpr (BULK) rb = sb_ringn_init(reinterpret_cast<uint64_t*>(bins + bins_per_cta + 1), ns, blockDim.x / 32);
   __syncthreads();
+  grid_dep_wait();   // the bin table does not depend on the previous kernel
   const int t0 = bins[0].x;
   const int tw = jb < Lb ? bins[nb].x : L;  // rows written / counted by this tile
   const int tc = bins[nb - 1].y;            // rows computed (the last bin may reach one row further)
@@ -409,7 +550,7 @@ __global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(D
   if (ch < a.C) {
     const int chunks = (tc - t0 + R - 1) / R;
     const bool interior = t0 * S - 2 >= 0 && (t0 + chunks * R - 1) * S + 2 < a.src.L;
-    if (interior) dw5_pool_body<KIND, S, false, RING>(a, b, ch, t0, tw, tc, bins, ja, nb, ringcol, tot1[0], tot2[0]);
+    if (interior) dw5_pool_body<KIND, S, false, RING, BULK>(a, b, ch, t0, tw, tc, bins, ja, nb, ringcol, tot1[0], tot2[0], rb);
     else dw5_pool_body<KIND, S, true, RING>(a, b, ch, t0, tw, tc, bins, ja, nb, ringcol, tot1[0], tot2[0]);
   }
   flush_item_stats<1>(a.stats, b, tot1, tot2, red);
@@ -493,11 +634,19 @@ static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
     TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
   const bool lb4 = lb == 4 && threads <= 128;
+  if (ring == 2 && lb4 && a.C == 512 && threads == 128 && (bulk_mask() & 8)) {
+    // two stages: with three the B = 64 parity tests failed intermittently (1e-3 instead of 1e-6; the statistics
+    // kernels pass with three) and the launch was slower anyway, so the depth is not a knob here
+    const int ns = 2;
+    TD_LAUNCH((dw5_pool_kernel<KIND, S, 4, 2, true>), grid, threads, ring_b / 2 * ns + bins_b + SB_BAR_BYTES, st, a, bpt, ns);
+    return 0;
+  }
 #define TD_POOL_LAUNCH(LB_, RING_) \
-  TD_LAUNCH((dw5_pool_kernel<KIND, S, LB_, RING_>), grid, threads, ring_b + bins_b, st, a, bpt)
+  TD_LAUNCH((dw5_pool_kernel<KIND, S, LB_, RING_>), grid, threads, ring_b + bins_b, st, a, bpt, 0)
   if (ring == 3) { if (lb4) { TD_POOL_LAUNCH(4, 3); } else { TD_POOL_LAUNCH(0, 3); } }
   else if (ring == 2) { if (lb4) { TD_POOL_LAUNCH(4, 2); } else { TD_POOL_LAUNCH(0, 2); } }
   else { if (lb4) { TD_POOL_LAUNCH(4, 0); } else { TD_POOL_LAUNCH(0, 0); } }
@@ -1084,13 +1233,17 @@ static size_t ring_bytes(int threads, int V = 4) {
 
 // CT: in_channels when it is the compile-time 512 of every reference configuration (row strides and
 // shared-memory offsets then fold into immediates), 0 = run-time
-template <int LKIND, bool EDGE, int CT, int V>
+// BULK (interior CTAs of the 512-channel, 4-channels-per-thread form): stages filled by cp.async.bulk, see above
+// NT: threads per CTA of the CT != 0 forms (128; 256 for the two-channels-per-thread bulk form, whose CTA of 8 warps
+// still covers all 512 channels)
+template <int LKIND, bool EDGE, int CT, int V, bool BULK = false, int NT = 128>
 __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, int t0, int t1, void* ring,
-                                               float* scratch, const int* jc, const int* jl) {
+                                               float* scratch, const int* jc, const int* jl, SbRing rb = SbRing{}) {
+  static_assert(!BULK || (!EDGE && CT == 512 && NT * V == 512), "bulk staging: interior CTAs covering all 512 channels");
   const int Ll = a.loc.L, Lg = a.glo.L, Lgg = a.loc.Lg;
   const int C = CT ? CT : a.C;
-  // CT != 0: 128 threads per CTA (the launcher guarantees it), so the column pitch is a compile-time constant too
-  const int colw = CT ? 128 * V : blockDim.x * V;
+  // CT != 0: NT threads per CTA (the launcher guarantees it), so the column pitch is a compile-time constant too
+  const int colw = CT ? NT * V : blockDim.x * V;
   const ACT_T* xl = reinterpret_cast<const ACT_T*>(a.loc.x) + (size_t)b * Ll * C + ch;
   const ACT_T* xg = reinterpret_cast<const ACT_T*>(a.glo.x) + (size_t)b * Lg * C + ch;
   const float* gg = a.loc.g + (size_t)b * Lgg * C + ch;
@@ -1113,6 +1266,24 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
   auto issue = [&](int k) {
     const StageCol st = stage_col<SAROWS, SGG, V>(ring, k & 1, colw);
     const int t = t0 + k * SR;
+    if constexpr (BULK) {
+      // thread 0 (channel 0: its pointers are the row bases) copies the three row ranges of the chunk
+      if (threadIdx.x == 0) {
+        uint64_t* full = rb.full;
+        const int s = k & 1;
+        rb.acquire(k);
+        const int jlo = jc[t - t0], j0 = jl[t - t0 + 4];
+        const int ngg = min(SGG, Lgg - j0);
+        constexpr uint32_t rowb = 512 * sizeof(ACT_T);
+        sb_expect_tx(full + s, (SR + SGR) * rowb + ngg * 2048u + (k == 0 ? 4 * rowb : 0u));
+        sb_bulk_g2s(st.act, xl + (size_t)(t + 2) * C, SR * rowb, full + s);
+        sb_bulk_g2s(st.act + SR * colw, xg + (size_t)(jlo - 2) * C, SGR * rowb, full + s);
+        sb_bulk_g2s(st.g, gg + (size_t)j0 * C, ngg * 2048u, full + s);
+        if (k == 0)  // rows t0-2 .. t0+1, parked in the other stage
+          sb_bulk_g2s(stage_col<SAROWS, SGG, V>(ring, 1, colw).act, xl + (size_t)(t0 - 2) * C, 4 * rowb, full);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < SR; ++i) {
       const int row = t + 2 + i;
@@ -1146,13 +1317,17 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
     for (int i = 0; i < 4; ++i) {
       const int t = t0 - 2 + i;
       const bool ok = !EDGE || (t >= 0 && t < Ll);
-      cp_async_actv<V>(pre.act + i * colw, xl + (ok ? t : 0) * C, ok);
+      if constexpr (!BULK) cp_async_actv<V>(pre.act + i * colw, xl + (ok ? t : 0) * C, ok);
       gpre[i] = vload<V>(gg + jl[i] * C);
     }
   }
   issue(0);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if constexpr (BULK) {
+    rb.wait_full(0);
+  } else {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
   {
     const StageCol pre = stage_col<SAROWS, SGG, V>(ring, 1, colw);
 #pragma unroll
@@ -1161,11 +1336,16 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
       if (EDGE && (t < 0 || t >= Ll)) xr[SR + i] = vzero<V>();
       else xr[SR + i] = inject(alds<V>(pre.act + i * colw), gpre[i], jl[i]);
     }
+    if constexpr (BULK) rb.release(1);  // the parked rows are consumed: stage 1 may be filled
   }
   for (int k = 0; k < nchunks; ++k) {
     if (k + 1 < nchunks) issue(k + 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    if constexpr (BULK) {
+      if (k > 0) rb.wait_full(k);   // chunk 0 was awaited with the prologue rows
+    } else {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    }
     const StageCol st = stage_col<SAROWS, SGG, V>(ring, k & 1, colw);
     const int t = t0 + k * SR;
     const int jlo = jc[t - t0];
@@ -1201,6 +1381,7 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
         xr[4 + i] = inject(alds<V>(st.act + i * colw), ldsv<V>(st.g + (j - j0) * colw), j);
       }
     }
+    if constexpr (BULK) rb.release(k & 1);  // last read of this stage by this warp
 #pragma unroll
     for (int r = 0; r < SR; ++r) {
       if (!EDGE || t + r < t1) {
@@ -1218,34 +1399,46 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
 // V = 4: 245 registers, two CTAs of 128 threads per SM (8 warps: every scheduler has two warps to cover the dependent-issue
 // stalls of this arithmetic-heavy loop - issue slots were 38 % busy at 0.65 of the HBM peak).  V = 2: half the
 // per-thread state, four CTAs per SM (16 warps), a CTA covers 256 channels.
-template <int LKIND, int CT, int V>
+// BULK, V = 2: 256 threads (8 warps) per CTA, two CTAs per SM at <= 128 registers: the 16 warps per SM of the
+// two-channel form without its doubled copy / address overhead (one thread stages the rows for the whole CTA).
+template <int LKIND, int CT, int V, bool BULK = false>
 #ifndef TD_LASTREAM_MINB
 #define TD_LASTREAM_MINB 2
 #endif
-__global__ void __launch_bounds__(128, V == 4 ? TD_LASTREAM_MINB : 4) la_stream_kernel(LaArgs a, int rows_per_cta) {
-  grid_dep_wait();
+__global__ void __launch_bounds__(BULK && V == 2 ? 256 : 128, V == 4 ? TD_LASTREAM_MINB : (BULK ? 2 : 4))
+la_stream_kernel(LaArgs a, int rows_per_cta) {
+  constexpr int NT = BULK && V == 2 ? 256 : 128;
   extern __shared__ __align__(16) float la_smem[];
   const int b = blockIdx.z;
   const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   const int Ll = a.loc.L, Lg = a.glo.L;
   const int t0 = blockIdx.x * rows_per_cta;
   const int t1 = min(t0 + rows_per_cta, Ll);
-  const int colw = CT ? 128 * V : blockDim.x * V;
-  // [ring: 2 stages][scratch 2*SGC rows fp32][tables]; plain pointer arithmetic on the __shared__ array so
-  // that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
+  const int colw = CT ? NT * V : blockDim.x * V;
+  // [ring: 2 stages][scratch 2*SGC rows fp32][tables][BULK: full[2], empty[2] mbarriers]; plain pointer arithmetic on
+  // the __shared__ array so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
   void* ring = la_smem;
   float* scratch = la_smem + 2 * ((SAROWS * colw * sizeof(ACT_T)) / sizeof(float) + SGG * colw);
   int* jc = reinterpret_cast<int*>(scratch + 2 * SGC * colw);
   int* jl = jc + rows_per_cta;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(jl + rows_per_cta + 4);  // rows_per_cta is a multiple of 8: 16-byte aligned
   fill_nearest(jc, rows_per_cta, t0, Ll, a.scale, Lg);
   fill_nearest(jl, rows_per_cta + 4, t0 - 2, Ll, a.loc.gscale, a.loc.Lg);
+  SbRing rb{};
+  if constexpr (BULK) rb = sb_ring_init(bars, NT / 32);
   __syncthreads();
+  grid_dep_wait();   // everything above is independent of the previous kernel's output
   if (ch >= a.C) return;
   const int g_first = nearest_src(t0, a.scale, Lg) - 2;
   const int g_last = nearest_src(t1 - 1, a.scale, Lg) + SGR;
   const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0 && g_first >= 0 && g_last < Lg;
-  if (interior) la_stream_body<LKIND, false, CT, V>(a, b, ch, t0, t1, ring, scratch, jc, jl);
-  else la_stream_body<LKIND, true, CT, V>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+  if constexpr (BULK) {
+    if (interior) la_stream_body<LKIND, false, CT, V, true, NT>(a, b, ch, t0, t1, ring, scratch, jc, jl, rb);
+    else la_stream_body<LKIND, true, CT, V, false, NT>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+  } else {
+    if (interior) la_stream_body<LKIND, false, CT, V>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+    else la_stream_body<LKIND, true, CT, V>(a, b, ch, t0, t1, ring, scratch, jc, jl);
+  }
 }
 
 // the streaming kernel applies when 8 output rows see <= 5 global centres and <= 3 rows of the
@@ -1257,8 +1450,9 @@ static bool la_stream_applies(const LaArgs& a) {
 
 template <int LKIND, int V>
 static int launch_la_stream_v(const LaArgs& a, cudaStream_t st) {
+  const bool bulk = (bulk_mask() & 1) != 0 && a.C == 512;
   int threads = a.C / V;
-  if (threads > 128) threads = 128;
+  if (threads > 128 && !(bulk && V == 2)) threads = 128;   // bulk, V = 2: one CTA of 256 threads covers the 512 channels
   if (threads < 32) threads = 32;
   const int ctiles = cdiv(a.C / V, threads);
   int rows, tiles;
@@ -1267,14 +1461,17 @@ static int launch_la_stream_v(const LaArgs& a, cudaStream_t st) {
   pick_tiling(a.B, a.loc.L, ctiles, SR, &rows, &tiles, ls_target, ls_cap);
   dim3 grid(tiles, ctiles, a.B);
   const size_t smem = (size_t)2 * SGC * threads * V * sizeof(float) + (size_t)(2 * rows + 4) * sizeof(int) +
-                      ring_bytes<SAROWS, SGG>(threads, V);
+                      ring_bytes<SAROWS, SGG>(threads, V) + 4 * sizeof(uint64_t);
   static bool attr_set = false;
   if (!attr_set) {
     TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 0, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 512, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 512, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     attr_set = true;
   }
-  if (a.C == 512 && threads == 128) {
+  if (bulk && threads * V == 512) {
+    TD_LAUNCH((la_stream_kernel<LKIND, 512, V, true>), grid, threads, smem, st, a, rows);
+  } else if (a.C == 512 && threads == 128) {
     TD_LAUNCH((la_stream_kernel<LKIND, 512, V>), grid, threads, smem, st, a, rows);
   } else {
     TD_LAUNCH((la_stream_kernel<LKIND, 0, V>), grid, threads, smem, st, a, rows);
@@ -1304,11 +1501,13 @@ struct LocalStatsArgs {
   DwArgs step[TDANET_MAX_DEPTH];
   int tile_end[TDANET_MAX_DEPTH];  // exclusive prefix sum of tiles per step
   int rows;                        // rows per CTA (same for every step)
+  int ns;                          // stages of the bulk ring
 };
 
-template <int LKIND, bool EDGE, int CT>
+template <int LKIND, bool EDGE, int CT, bool BULK = false>
 __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch, int t0, int t1, void* ring,
-                                                  const int* jl, float& tot1, float& tot2) {
+                                                  const int* jl, float& tot1, float& tot2, SbRingN rb = SbRingN{}) {
+  static_assert(!BULK || (!EDGE && CT == 512), "bulk staging: interior CTAs covering all 512 channels");
   constexpr int V = 4;
   const int Ll = a.src.L, Lgg = a.src.Lg;
   const int C = CT ? CT : a.C;
@@ -1321,9 +1520,27 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
   load_taps<V>(a.w[0], ch, wl);
   vf<V> s1 = vzero<V>(), s2 = vzero<V>();
 
+  SbCursor pc, cc;  // BULK: producer (thread 0) / consumer positions in the ring
   auto issue = [&](int k) {
-    const StageCol st = stage_col<SR, SSG>(ring, k & 1, colw);
     const int t = t0 + k * SR;
+    if constexpr (BULK) {
+      if (threadIdx.x == 0) {
+        const StageCol st = stage_col<SR, SSG>(ring, pc.stage, colw);
+        uint64_t* full = rb.full + pc.stage;
+        rb.acquire<true>(pc);
+        const int j0 = jl[t - t0 + 4];
+        const int ngg = min(SSG, Lgg - j0);
+        constexpr uint32_t rowb = 512 * sizeof(ACT_T);
+        sb_expect_tx(full, SR * rowb + ngg * 2048u + (k == 0 ? 4 * rowb : 0u));
+        sb_bulk_g2s(st.act, xl + (size_t)(t + 2) * C, SR * rowb, full);
+        sb_bulk_g2s(st.g, gg + (size_t)j0 * C, ngg * 2048u, full);
+        if (k == 0)  // rows t0-2 .. t0+1, parked in the last stage
+          sb_bulk_g2s(stage_col<SR, SSG>(ring, rb.ns - 1, colw).act, xl + (size_t)(t0 - 2) * C, 4 * rowb, full);
+        pc.next(rb.ns);
+      }
+      return;
+    }
+    const StageCol st = stage_col<SR, SSG>(ring, k & 1, colw);
 #pragma unroll
     for (int i = 0; i < SR; ++i) {
       const int row = t + 2 + i;
@@ -1343,32 +1560,44 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
   const int nchunks = (t1 - t0 + SR - 1) / SR;
   vf<V> gpre[4];
   {
-    const StageCol pre = stage_col<SR, SSG>(ring, 1, colw);  // unused until chunk 1 is issued
+    const StageCol pre = stage_col<SR, SSG>(ring, BULK ? rb.ns - 1 : 1, colw);  // unused until that stage's first chunk
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = t0 - 2 + i;
       const bool ok = !EDGE || (t >= 0 && t < Ll);
-      cp_async_act(pre.act + i * colw, xl + (ok ? t : 0) * C, ok);
+      if constexpr (!BULK) cp_async_act(pre.act + i * colw, xl + (ok ? t : 0) * C, ok);
       gpre[i] = vload<V>(gg + jl[i] * C);
     }
   }
   issue(0);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if constexpr (BULK) {
+    for (int k = 1; k < rb.ns - 1; ++k)
+      if (k < nchunks) issue(k);
+    rb.wait_full(cc);   // chunk 0 and the parked rows
+  } else {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
   {
-    const StageCol pre = stage_col<SR, SSG>(ring, 1, colw);
+    const StageCol pre = stage_col<SR, SSG>(ring, BULK ? rb.ns - 1 : 1, colw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = t0 - 2 + i;
       if (EDGE && (t < 0 || t >= Ll)) xr[SR + i] = vzero<V>();
       else xr[SR + i] = inj.apply(alds<V>(pre.act + i * colw), gpre[i], jl[i]);
     }
+    if constexpr (BULK) rb.release(rb.ns - 1);
   }
   for (int k = 0; k < nchunks; ++k) {
-    if (k + 1 < nchunks) issue(k + 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    const StageCol st = stage_col<SR, SSG>(ring, k & 1, colw);
+    if constexpr (BULK) {
+      if (k + rb.ns - 1 < nchunks) issue(k + rb.ns - 1);
+      rb.wait_full(cc);
+    } else {
+      if (k + 1 < nchunks) issue(k + 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    }
+    const StageCol st = stage_col<SR, SSG>(ring, BULK ? cc.stage : (k & 1), colw);
     const int t = t0 + k * SR;
 #pragma unroll
     for (int i = 0; i < 4; ++i) xr[i] = xr[SR + i];
@@ -1381,6 +1610,10 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
         const int j = jl[t - t0 + 4 + i];
         xr[4 + i] = inj.apply(alds<V>(st.act + i * colw), lds4(st.g + (j - j0) * colw), j);
       }
+    }
+    if constexpr (BULK) {
+      rb.release(cc.stage);
+      cc.next(rb.ns);
     }
 #pragma unroll
     for (int r = 0; r < SR; ++r) {
@@ -1398,9 +1631,8 @@ __device__ __forceinline__ void stats_stream_body(const DwArgs& a, int b, int ch
   }
 }
 
-template <int LKIND, int CT>
+template <int LKIND, int CT, bool BULK = false>
 __global__ void __launch_bounds__(128, 3) la_local_stats_kernel(LocalStatsArgs p) {
-  grid_dep_wait();
   extern __shared__ __align__(16) float la_smem[];
   __shared__ double red[64];
   constexpr int V = 4;
@@ -1413,13 +1645,16 @@ __global__ void __launch_bounds__(128, 3) la_local_stats_kernel(LocalStatsArgs p
   const int Ll = loc.src.L;
   const int t0 = tile * p.rows, t1 = min(t0 + p.rows, Ll);
   void* ring = la_smem;
-  int* jl = reinterpret_cast<int*>(la_smem + 2 * ((SR * blockDim.x * V * sizeof(ACT_T)) / sizeof(float) + SSG * blockDim.x * V));
+  int* jl = reinterpret_cast<int*>(la_smem + (BULK ? p.ns : 2) * ((SR * blockDim.x * V * sizeof(ACT_T)) / sizeof(float) + SSG * blockDim.x * V));
   fill_nearest(jl, p.rows + 4, t0 - 2, Ll, loc.src.gscale, loc.src.Lg);
+  SbRingN rb{};
+  if constexpr (BULK) rb = sb_ringn_init(reinterpret_cast<uint64_t*>(jl + p.rows + 4), p.ns, 4);  // rows: a multiple of 8
   __syncthreads();
+  grid_dep_wait();   // the index table does not depend on the previous kernel
   float tot1[1] = {0.f}, tot2[1] = {0.f};
   if (ch < loc.C) {
     const bool interior = t0 - 2 >= 0 && t1 + 2 <= Ll && (t1 - t0) % SR == 0;
-    if (interior) stats_stream_body<LKIND, false, CT>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
+    if (interior) stats_stream_body<LKIND, false, CT, BULK>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0], rb);
     else stats_stream_body<LKIND, true, CT>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
   }
   flush_item_stats<1>(loc.stats, b, tot1, tot2, red);
@@ -1445,14 +1680,20 @@ static int launch_la_local_stats_t(LocalStatsArgs& p, cudaStream_t st) {
     p.tile_end[i] = acc;
   }
   dim3 grid(acc, ctiles, a0.B);
-  const size_t smem = ring_bytes<SR, SSG>(threads) + (size_t)(rows + 4) * sizeof(int);
+  const bool bulk = a0.C == 512 && threads == 128 && (bulk_mask() & 2);
+  // three CTAs of two stages or two CTAs of up to four stages per SM: the bytes in flight decide (see SbRingN)
+  p.ns = bulk ? bulk_stages() : 2;
+  const size_t smem = ring_bytes<SR, SSG>(threads) / 2 * p.ns + (size_t)(rows + 4) * sizeof(int) + SB_BAR_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
     TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     attr_set = true;
   }
-  if (a0.C == 512 && threads == 128) {
+  if (bulk) {
+    TD_LAUNCH((la_local_stats_kernel<LKIND, 512, true>), grid, threads, smem, st, p);
+  } else if (a0.C == 512 && threads == 128) {
     TD_LAUNCH((la_local_stats_kernel<LKIND, 512>), grid, threads, smem, st, p);
   } else {
     TD_LAUNCH((la_local_stats_kernel<LKIND, 0>), grid, threads, smem, st, p);
@@ -1488,9 +1729,10 @@ int launch_la_local_stats(const DwArgs* steps, int n, cudaStream_t st) {
 // kernel is a pure read.  Same structure as the local-statistics kernel: a thread owns 4 channels and
 // streams its column through a two-stage cp.async ring, few long CTAs (the tap loads and the 4-row
 // prologue are paid once per CTA), four CTAs per SM.
-template <bool EDGE, int CT>
+template <bool EDGE, int CT, bool BULK = false>
 __device__ __forceinline__ void gstats_stream_body(const DwArgs& a, int b, int ch, int t0, int t1, void* ring,
-                                                   float (&tot1)[2], float (&tot2)[2]) {
+                                                   float (&tot1)[2], float (&tot2)[2], SbRingN rb = SbRingN{}) {
+  static_assert(!BULK || (!EDGE && CT == 512), "bulk staging: interior CTAs covering all 512 channels");
   constexpr int V = 4;
   const int L = a.src.L;
   const int C = CT ? CT : a.C;
@@ -1501,9 +1743,24 @@ __device__ __forceinline__ void gstats_stream_body(const DwArgs& a, int b, int c
   load_taps<V>(a.w[1], ch, we);
   vf<V> s1a = vzero<V>(), s2a = vzero<V>(), s1e = vzero<V>(), s2e = vzero<V>();
 
+  SbCursor pc, cc;  // BULK: producer (thread 0) / consumer positions in the ring
   auto issue = [&](int k) {
-    const StageCol st = stage_col<SR, 0>(ring, k & 1, colw);
     const int t = t0 + k * SR;
+    if constexpr (BULK) {
+      if (threadIdx.x == 0) {
+        const StageCol st = stage_col<SR, 0>(ring, pc.stage, colw);
+        uint64_t* full = rb.full + pc.stage;
+        rb.acquire<true>(pc);
+        constexpr uint32_t rowb = 512 * sizeof(ACT_T);
+        sb_expect_tx(full, SR * rowb + (k == 0 ? 4 * rowb : 0u));
+        sb_bulk_g2s(st.act, x + (size_t)(t + 2) * C, SR * rowb, full);
+        if (k == 0)  // rows t0-2 .. t0+1, parked in the last stage
+          sb_bulk_g2s(stage_col<SR, 0>(ring, rb.ns - 1, colw).act, x + (size_t)(t0 - 2) * C, 4 * rowb, full);
+        pc.next(rb.ns);
+      }
+      return;
+    }
+    const StageCol st = stage_col<SR, 0>(ring, k & 1, colw);
 #pragma unroll
     for (int i = 0; i < SR; ++i) {
       const int row = t + 2 + i;
@@ -1515,31 +1772,43 @@ __device__ __forceinline__ void gstats_stream_body(const DwArgs& a, int b, int c
   vf<V> xr[SR + 4];
   const int nchunks = (t1 - t0 + SR - 1) / SR;
   {
-    const StageCol pre = stage_col<SR, 0>(ring, 1, colw);  // unused until chunk 1 is issued
+    const StageCol pre = stage_col<SR, 0>(ring, BULK ? rb.ns - 1 : 1, colw);  // unused until that stage's first chunk
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = t0 - 2 + i;
       const bool ok = !EDGE || (t >= 0 && t < L);
-      cp_async_act(pre.act + i * colw, x + (ok ? t : 0) * C, ok);
+      if constexpr (!BULK) cp_async_act(pre.act + i * colw, x + (ok ? t : 0) * C, ok);
     }
   }
   issue(0);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if constexpr (BULK) {
+    for (int k = 1; k < rb.ns - 1; ++k)
+      if (k < nchunks) issue(k);
+    rb.wait_full(cc);   // chunk 0 and the parked rows
+  } else {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
   {
-    const StageCol pre = stage_col<SR, 0>(ring, 1, colw);
+    const StageCol pre = stage_col<SR, 0>(ring, BULK ? rb.ns - 1 : 1, colw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = t0 - 2 + i;
       if (EDGE && (t < 0 || t >= L)) xr[SR + i] = vzero<V>();
       else xr[SR + i] = alds<V>(pre.act + i * colw);
     }
+    if constexpr (BULK) rb.release(rb.ns - 1);
   }
   for (int k = 0; k < nchunks; ++k) {
-    if (k + 1 < nchunks) issue(k + 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    const StageCol st = stage_col<SR, 0>(ring, k & 1, colw);
+    if constexpr (BULK) {
+      if (k + rb.ns - 1 < nchunks) issue(k + rb.ns - 1);
+      rb.wait_full(cc);
+    } else {
+      if (k + 1 < nchunks) issue(k + 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    }
+    const StageCol st = stage_col<SR, 0>(ring, BULK ? cc.stage : (k & 1), colw);
     const int t = t0 + k * SR;
 #pragma unroll
     for (int i = 0; i < 4; ++i) xr[i] = xr[SR + i];
@@ -1547,6 +1816,10 @@ __device__ __forceinline__ void gstats_stream_body(const DwArgs& a, int b, int c
     for (int i = 0; i < SR; ++i) {
       if (EDGE && t + 2 + i >= L) xr[4 + i] = vzero<V>();
       else xr[4 + i] = alds<V>(st.act + i * colw);
+    }
+    if constexpr (BULK) {
+      rb.release(cc.stage);
+      cc.next(rb.ns);
     }
 #pragma unroll
     for (int r = 0; r < SR; ++r) {
@@ -1569,10 +1842,15 @@ __device__ __forceinline__ void gstats_stream_body(const DwArgs& a, int b, int c
   }
 }
 
-template <int CT>
-__global__ void __launch_bounds__(128, 4) gstats_stream_kernel(DwArgs a, int rows_per_cta) {
-  grid_dep_wait();
+template <int CT, bool BULK = false>
+__global__ void __launch_bounds__(128, 4) gstats_stream_kernel(DwArgs a, int rows_per_cta, int ns) {
   extern __shared__ __align__(16) float la_smem[];
+  SbRingN rb{};
+  if constexpr (BULK) {  // the barriers follow the ring (ns stages of SR rows of 512 channels)
+    rb = sb_ringn_init(reinterpret_cast<uint64_t*>(la_smem + ns * (SR * 512 * sizeof(ACT_T)) / sizeof(float)), ns, 4);
+    __syncthreads();
+  }
+  grid_dep_wait();
   __shared__ double red[64];
   constexpr int V = 4;
   const int b = a.rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
@@ -1582,7 +1860,7 @@ __global__ void __launch_bounds__(128, 4) gstats_stream_kernel(DwArgs a, int row
   float tot1[2] = {0.f, 0.f}, tot2[2] = {0.f, 0.f};
   if (ch < a.C) {
     const bool interior = t0 - 2 >= 0 && t1 + 2 <= L && (t1 - t0) % SR == 0;
-    if (interior) gstats_stream_body<false, CT>(a, b, ch, t0, t1, la_smem, tot1, tot2);
+    if (interior) gstats_stream_body<false, CT, BULK>(a, b, ch, t0, t1, la_smem, tot1, tot2, rb);
     else gstats_stream_body<true, CT>(a, b, ch, t0, t1, la_smem, tot1, tot2);
   }
   flush_item_stats<2>(a.stats, b, tot1, tot2, red);
@@ -1605,11 +1883,20 @@ static int launch_gstats_stream(const DwArgs& a, cudaStream_t st) {
   int rows, tiles;
   pick_tiling(a.B, a.src.L, ctiles, SR, &rows, &tiles, target, cap);
   dim3 grid(tiles, ctiles, a.B);
-  const size_t smem = ring_bytes<SR, 0>(threads);
-  if (a.C == 512 && threads == 128) {
-    TD_LAUNCH((gstats_stream_kernel<512>), grid, threads, smem, st, a, rows);
+  const bool bulk = a.C == 512 && threads == 128 && (bulk_mask() & 4);
+  const int ns = bulk ? bulk_stages() : 2;
+  const size_t smem = ring_bytes<SR, 0>(threads) / 2 * ns + SB_BAR_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TD_CUDA(cudaFuncSetAttribute(gstats_stream_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  if (bulk) {
+    TD_LAUNCH((gstats_stream_kernel<512, true>), grid, threads, smem, st, a, rows, ns);
+  } else if (a.C == 512 && threads == 128) {
+    TD_LAUNCH((gstats_stream_kernel<512>), grid, threads, smem, st, a, rows, 2);
   } else {
-    TD_LAUNCH((gstats_stream_kernel<0>), grid, threads, smem, st, a, rows);
+    TD_LAUNCH((gstats_stream_kernel<0>), grid, threads, smem, st, a, rows, 2);
   }
   return 0;
 }
