@@ -1,0 +1,54 @@
+"""The streaming kernels have two ways of staging their rows in shared memory (round 2): cp.async.bulk by one thread of
+the CTA onto an mbarrier ring (512-channel models, the default) and per-thread cp.async rings (every other channel
+count, and TDANET_BULK=0).  Both evaluate the same expressions in the same order, so the outputs of one model under
+the two forms must agree to the run-to-run noise of the GlobLN statistics (double atomics).  The knob is read once per
+process, hence the subprocesses.  Kernels: csrc/dwconv_impl.cuh (SbRing / SbRingN, la_stream_kernel, la_local_stats_kernel,
+gstats_stream_kernel, dw5_pool_kernel); reference: look2hear/models/TDANet_best.py:266-292,342-380."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_CHILD = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+import tdanet_b200.look2hear as look2hear
+torch.manual_seed(0)
+cls = getattr(look2hear.models, {cls!r})
+m = cls(sample_rate=16000, out_channels=128, in_channels=512, num_blocks=3, upsampling_depth=5, enc_kernel_size=4,
+        num_sources=2).eval().to("cuda:0")
+m.gemm_mode = "fp32" if {act!r} == "fp32" else "tf32"    # bf16 storage needs a tensor-core GEMM mode
+m.act_dtype = {act!r}
+x = (torch.randn(5, 1, 24000, generator=torch.Generator().manual_seed(7)) * 0.1).to("cuda:0")
+with torch.no_grad():
+    y = m(x).float().cpu()
+torch.save(y, {out!r})
+"""
+
+
+def _run(tmp_path, tag, env, cls="TDANetBest", act="fp32"):
+    out = str(tmp_path / f"{tag}.pt")
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", _CHILD.format(root=ROOT, cls=cls, act=act, out=out)], env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return torch.load(out)
+
+
+@pytest.mark.parametrize("cls,act", [("TDANetBest", "fp32"), ("TDANet", "fp32"), ("TDANetBest", "bf16")])
+def test_bulk_and_per_thread_staging_agree(tmp_path, cls, act):
+    ref = _run(tmp_path, "bulk", {"TDANET_BULK": "15"}, cls, act)
+    assert torch.isfinite(ref).all() and ref.abs().max() > 0
+    tol = 2e-5 if act == "fp32" else 2e-2     # bf16 storage: a statistic that moves by 1e-7 can flip a rounding
+    # none; for the headline model also each kernel family alone
+    for mask in (("0", "1", "2", "4", "8") if (cls, act) == ("TDANetBest", "fp32") else ("0",)):
+        y = _run(tmp_path, f"mask{mask}", {"TDANET_BULK": mask}, cls, act)
+        err = ((y - ref).abs().max() / ref.abs().max()).item()
+        assert err < tol, (cls, act, mask, err)
+
