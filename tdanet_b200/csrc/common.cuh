@@ -84,6 +84,24 @@ struct Tag {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// The opt-in to more than 48 KB of dynamic shared memory (cudaFuncSetAttribute) is per DEVICE: a call site keeps one
+// of these as a function-local static and sets its attributes whenever it reports the first use on the current device
+// (a process may drive several GPUs, e.g. a model moved from cuda:0 to cuda:1).
+struct PerDeviceOnce {
+  bool done[16] = {};
+  bool operator()() {
+#ifdef TD_EMU
+    return false;
+#else
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 16) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+#endif
+  }
+};
+
 // Programmatic dependent launch: every kernel of this library begins with grid_dep_wait() (griddepcontrol.wait: block
 // until the previous kernel of the stream has completed and its writes are visible) and is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled - launch latency, parameter and

@@ -628,14 +628,13 @@ static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
   while (ring > 0 && (size_t)ring * R * S * threads * 4 * sizeof(ACT_T) + bins_b > 100 * 1024) --ring;
   if (ring == 1) ring = 0;
   const size_t ring_b = (size_t)ring * R * S * threads * 4 * sizeof(ACT_T);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce first_use;
+  if (first_use()) {
     TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     TD_CUDA(cudaFuncSetAttribute(dw5_pool_kernel<KIND, S, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
   }
   const bool lb4 = lb == 4 && threads <= 128;
   if (ring == 2 && lb4 && a.C == 512 && threads == 128 && (bulk_mask() & 8)) {
@@ -1462,12 +1461,11 @@ static int launch_la_stream_v(const LaArgs& a, cudaStream_t st) {
   dim3 grid(tiles, ctiles, a.B);
   const size_t smem = (size_t)2 * SGC * threads * V * sizeof(float) + (size_t)(2 * rows + 4) * sizeof(int) +
                       ring_bytes<SAROWS, SGG>(threads, V) + 4 * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce first_use;
+  if (first_use()) {
     TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 0, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 512, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     TD_CUDA(cudaFuncSetAttribute(la_stream_kernel<LKIND, 512, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    attr_set = true;
   }
   if (bulk && threads * V == 512) {
     TD_LAUNCH((la_stream_kernel<LKIND, 512, V, true>), grid, threads, smem, st, a, rows);
@@ -1684,12 +1682,11 @@ static int launch_la_local_stats_t(LocalStatsArgs& p, cudaStream_t st) {
   // three CTAs of two stages or two CTAs of up to four stages per SM: the bytes in flight decide (see SbRingN)
   p.ns = bulk ? bulk_stages() : 2;
   const size_t smem = ring_bytes<SR, SSG>(threads) / 2 * p.ns + (size_t)(rows + 4) * sizeof(int) + SB_BAR_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce first_use;
+  if (first_use()) {
     TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     TD_CUDA(cudaFuncSetAttribute(la_local_stats_kernel<LKIND, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    attr_set = true;
   }
   if (bulk) {
     TD_LAUNCH((la_local_stats_kernel<LKIND, 512, true>), grid, threads, smem, st, p);
@@ -1886,10 +1883,9 @@ static int launch_gstats_stream(const DwArgs& a, cudaStream_t st) {
   const bool bulk = a.C == 512 && threads == 128 && (bulk_mask() & 4);
   const int ns = bulk ? bulk_stages() : 2;
   const size_t smem = ring_bytes<SR, 0>(threads) / 2 * ns + SB_BAR_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce first_use;
+  if (first_use()) {
     TD_CUDA(cudaFuncSetAttribute(gstats_stream_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
   }
   if (bulk) {
     TD_LAUNCH((gstats_stream_kernel<512, true>), grid, threads, smem, st, a, rows, ns);

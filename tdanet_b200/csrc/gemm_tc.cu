@@ -581,10 +581,9 @@ int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st) {
   const int epi = a.epi == EPI_RESIDUAL ? (a.last ? 2 : 1) : 0;
 #define TD_TC_LAUNCH(E, S, AB, DB)                                                                             \
   do {                                                                                                         \
-    static bool attr_set = false;                                                                              \
-    if (!attr_set) {                                                                                           \
+    static PerDeviceOnce first_use;                                                                            \
+    if (first_use()) {                                                                                         \
       TD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<E, S, AB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr_set = true;                                                                                         \
     }                                                                                                          \
     TD_LAUNCH((gemm_tc_kernel<E, S, AB, DB>), grid, TC_THREADS, smem, st, mapA, mapW, mapW2, mapD, a, p);             \
   } while (0)

@@ -52,3 +52,27 @@ def test_bulk_and_per_thread_staging_agree(tmp_path, cls, act):
         err = ((y - ref).abs().max() / ref.abs().max()).item()
         assert err < tol, (cls, act, mask, err)
 
+
+
+def test_second_device_in_the_same_process():
+    """The opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: a process that has run the
+    512-channel kernels on cuda:0 must be able to run them on cuda:1 (csrc/common.cuh: PerDeviceOnce)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import tdanet_b200.look2hear as look2hear
+    torch.manual_seed(0)
+    kw = dict(sample_rate=16000, out_channels=128, in_channels=512, num_blocks=2, upsampling_depth=5, enc_kernel_size=4,
+              num_sources=2)
+    m0 = look2hear.models.TDANetBest(**kw).eval()
+    sd = {k: v.clone() for k, v in m0.state_dict().items()}
+    x = torch.randn(3, 1, 16000, generator=torch.Generator().manual_seed(3)) * 0.1
+    ys = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = look2hear.models.TDANetBest(**kw).eval()
+        m.load_state_dict(sd)
+        m = m.to(dev)
+        m.gemm_mode = "tf32"
+        with torch.no_grad():
+            ys.append(m(x.to(dev)).float().cpu())
+    assert torch.isfinite(ys[1]).all()
+    assert ((ys[0] - ys[1]).abs().max() / ys[0].abs().max()).item() < 1e-3
