@@ -1400,6 +1400,8 @@ __device__ __forceinline__ void la_stream_body(const LaArgs& a, int b, int ch, i
 // per-thread state, four CTAs per SM (16 warps), a CTA covers 256 channels.
 // BULK, V = 2: 256 threads (8 warps) per CTA, two CTAs per SM at <= 128 registers: the 16 warps per SM of the
 // two-channel form without its doubled copy / address overhead (one thread stages the rows for the whole CTA).
+// Measured: the same duration as V = 4 (143 vs 139 us for the 661 MB launch: 38 % more instructions at 47 % instead of
+// 34 % issue-slot use, profiles/r03_ncu_la_stream_bulk.txt), so V = 4 stays the default.
 template <int LKIND, int CT, int V, bool BULK = false>
 #ifndef TD_LASTREAM_MINB
 #define TD_LASTREAM_MINB 2
@@ -1479,8 +1481,8 @@ static int launch_la_stream_v(const LaArgs& a, cudaStream_t st) {
 
 template <int LKIND>
 static int launch_la_stream(const LaArgs& a, cudaStream_t st) {
-  // channels per thread: 2 (four CTAs per SM) unless the channel count has no 2-channel tiling; TDANET_LASTREAM_V=4
-  // selects the two-CTA form for A/B measurements
+  // channels per thread: 4 (two CTAs of 128 threads per SM).  TDANET_LASTREAM_V=2 selects the two-channel form for A/B
+  // measurements (bulk-staged: 256 threads per CTA; measured on B200: 17.60 instead of 17.39 ms per step)
   static const int v_knob = getenv("TDANET_LASTREAM_V") ? atoi(getenv("TDANET_LASTREAM_V")) : 4;
   if (v_knob == 2 && a.C % 2 == 0) return launch_la_stream_v<LKIND, 2>(a, st);
   return launch_la_stream_v<LKIND, 4>(a, st);
