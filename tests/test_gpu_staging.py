@@ -76,3 +76,28 @@ def test_second_device_in_the_same_process():
             ys.append(m(x.to(dev)).float().cpu())
     assert torch.isfinite(ys[1]).all()
     assert ((ys[0] - ys[1]).abs().max() / ys[0].abs().max()).item() < 1e-3
+
+
+@pytest.mark.parametrize("cls,variant", [("TDANetBest", "best"), ("TDANet", "fork")])
+@pytest.mark.parametrize("enc_ms,T", [(4, 640), (4, 3333), (4, 12345), (4, 40001), (2, 9001)])
+def test_bulk_staged_kernels_on_ragged_lengths(cls, variant, enc_ms, T):
+    """512-channel models (the bulk-staged kernels) on lengths that are no multiple of the window, the hop or any tile:
+    tensors of a few rows (every CTA an edge CTA), one interior chunk between two edges, the long case with many
+    interior CTAs per item, the 2 ms encoder; batch 1 and 3, against the oracle in fp32."""
+    import tdanet_b200.look2hear as look2hear
+    from conftest import max_rel
+    from oracle import tdanet_oracle as O
+    kw = dict(out_channels=128, in_channels=512, num_blocks=2, upsampling_depth=5, enc_kernel_size=enc_ms, num_sources=2)
+    torch.manual_seed(T)
+    m = getattr(look2hear.models, cls)(sample_rate=16000, **kw).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = O.OracleConfig(variant=variant, sample_rate=16000, **kw)
+    m = m.to("cuda:0")
+    m.gemm_mode = "fp32"
+    for B in (1, 3):
+        x = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(T + B)) * 0.1
+        with torch.no_grad():
+            ref = O.forward(sd, x, cfg)
+            y = m(x.to("cuda:0")).cpu()
+        assert y.shape == ref.shape == (B, 2, T)
+        assert max_rel(y, ref) < 5e-5, (cls, enc_ms, T, B)
