@@ -922,13 +922,18 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
       const size_t n = (size_t)R0 * CI;
       TD_LAUNCH(dec_bwd_data_naive_kernel, (unsigned)((n + 127) / 128), 128, 0, st, d_est, w->dec_w, x.at(p.g_masked), B, L0, CI, NS, K, S, T, K - S);
     }
-    if (int e = launch_framed_wgrad(x.at(p.masked), d_est, x.gp(gw->dec_w), B, L0, CI, NS, K, S, T, K - S, CI, st)) return e;
+    // the two weight gradients of the back end (decoder basis: ~150 us of latency-bound launch; mask conv) read only
+    // inputs of the call / g_masked and nothing else writes their outputs: they ride on the weight-gradient stream,
+    // which the first block's event (or join) brings back long before g_masked is reused as d_nenc below
+    if (int e = x.side->order(st, x.side->w)) return e;
+    if (int e = launch_framed_wgrad(x.at(p.masked), d_est, x.gp(gw->dec_w), B, L0, CI, NS, K, S, T, K - S, CI, x.side->w)) return e;
     // masked = relu(m) * enc
     const size_t ne = (size_t)R0 * Nb;
     TD_LAUNCH(mask_bwd_kernel, (unsigned)((ne + 255) / 256), 256, 0, st, x.at(p.g_masked), x.at(p.mlogit), x.at(p.enc), x.at(p.g_enc), R0, NS, Nb);
     // m = mask_conv(prelu(y_last)) + bias
     const float* y_last = x.at_blk(p.y, nb - 1);
-    if (int e = launch_wgrad(x.at(p.g_masked), y_last, x.gp(gw->mask_w), x.gp(gw->mask_b), R0, CI, cc, w->mask_prelu, st)) return e;
+    if (int e = x.side->order(st, x.side->w)) return e;
+    if (int e = launch_wgrad(x.at(p.g_masked), y_last, x.gp(gw->mask_w), x.gp(gw->mask_b), R0, CI, cc, w->mask_prelu, x.side->w)) return e;
     if (int e = launch_small_dgrad(x.at(p.g_masked), w->mask_w, x.at(p.g_u[0]), R0, CI, cc, y_last, w->mask_prelu, x.gp(gw->mask_prelu), st)) return e;
   }
   // Recurrent, backwards: g_u[cur] holds d loss / d y_blk
