@@ -317,14 +317,21 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   }
   // training: every live x_fused[k] is kept for the backward pass (the top-down steps below still recompute it on
   // load, like inference: the streaming kernels are the fast path; both evaluate the same expression)
-  bool fused_live[TDANET_MAX_DEPTH] = {};
+  bool fused_live[TDANET_MAX_DEPTH] = {}, fused_deferred[TDANET_MAX_DEPTH] = {};
+  cudaEvent_t fused_ready = nullptr;
   if (p.train) {
     for (int k = 0; k < depth - 1; ++k) fused_live[k] = true;
     fused_live[first_step_partner(depth)] = true;
     Tag t("fused_materialize");
     const int gi = first_step_partner(depth);
+    // only the two operands of the first top-down step are read by this forward; the others (the two finest scales,
+    // most of the bytes) are kept for the backward pass alone and are written on the side stream, after the local
+    // statistics (TDANET_MAT_SIDE=0: everything on the caller's stream, round 2 first session)
+    static const bool mat_side = !(getenv("TDANET_MAT_SIDE") && atoi(getenv("TDANET_MAT_SIDE")) == 0);
+    const bool side_ok = mat_side && t_fside != nullptr && depth >= 3;
     for (int k = 0; k < depth; ++k)
       if (fused_live[k]) {
+        if (side_ok && k != gi && k != depth - 2) { fused_deferred[k] = true; continue; }
         // x_fused[gi] is the "global" operand of the first top-down step: its global-branch GlobLN statistics ride
         // in the kernel that writes it (no statistics launch for that step)
         const bool st = k == gi && first_stats_fused(true);
@@ -360,6 +367,17 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       cudaEvent_t e0 = fs->events[fs->next++ % fs->events.size()];
       TD_CUDA(cudaEventRecord(e0, fs->s));
       local_ready[0] = e0;
+      bool any = false;
+      for (int k = 0; k < depth; ++k)
+        if (fused_deferred[k]) {
+          Tag tm("fused_materialize");
+          if (int e = launch_inject_materialize(inj_src(k), inj_kind, B, C, x.at(p.fused[k]), x.bf(), fs->s)) return e;
+          any = true;
+        }
+      if (any) {
+        fused_ready = fs->events[fs->next++ % fs->events.size()];
+        TD_CUDA(cudaEventRecord(fused_ready, fs->s));
+      }
     }
   }
   // top-down fusion: last_layer[i](x_fused[i], i == depth-2 ? x_fused[i-1] : expanded)
@@ -417,6 +435,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     if (local_ready[i]) TD_CUDA(cudaStreamWaitEvent(x.st, local_ready[i], 0));  // st_la_l[i] (side stream)
     { Tag t(i == depth - 2 ? "la_combine_first" : "la_combine"); if (int e = launch_la_combine(l, x.st)) return e; }
   }
+  if (fused_ready) TD_CUDA(cudaStreamWaitEvent(x.st, fused_ready, 0));  // the side stream's x_fused[k] (long done)
   // res_conv + residual (+ concat_block for the next iteration)
   g = GemmArgs{};
   g.A = x.at(p.expanded[0]); g.W = w->res_w; g.bias = w->res_b; g.D = out;
