@@ -424,7 +424,7 @@ static int launch_framed_wgrad(const float* M, const float* sig, float* dW, int 
                                int S, int T, int shift, int m_stride, cudaStream_t st) {
   TD_REQUIRE(K <= 1024, "framed_wgrad: window %d", K);
   const int R = B * L0;
-  int splits = cdiv(1184, CI * NO);
+  int splits = cdiv(148 * 24, CI * NO);   // CTAs of K (64) threads: ~24 per SM, ~150 rows each at the training batch
   const int rps = cdiv(R, splits);
   splits = cdiv(R, rps);
   dim3 grid(CI * NO, splits);
@@ -908,7 +908,15 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
   const int K = c->enc_kernel, S = c->enc_stride, Nb = c->n_basis, cc = c->out_channels, L0 = p.L[0];
   const int NS = c->num_sources, CI = NS * Nb, R0 = B * L0, nb = c->num_blocks;
 
-  if (int e = prepare_transposed(x)) return e;
+  // the transposed weight copies of the data-gradient GEMMs (12 short launches) are first needed by the res_conv
+  // data gradient of the last block: they are prepared on the weight-gradient stream while the back end below runs
+  cudaEvent_t wt_ready = nullptr;
+  {
+    if (int e = x.side->order(st, x.side->w)) return e;
+    if (int e = prepare_transposed(x.on(x.side->w, 0))) return e;
+    wt_ready = x.side->events[x.side->next++ % x.side->events.size()];
+    TD_CUDA(cudaEventRecord(wt_ready, x.side->w));
+  }
   TD_CUDA(cudaMemsetAsync(x.at<char>(p.bs_enc), 0, (size_t)B * 2 * sizeof(double), st));
   TD_CUDA(cudaMemsetAsync(x.at<char>(p.g_x0), 0, (size_t)R0 * cc * sizeof(float), st));
   {
@@ -936,6 +944,7 @@ static int backward(const tdanet_config_t* c, const tdanet_weights_t* w, const t
     if (int e = launch_wgrad(x.at(p.g_masked), y_last, x.gp(gw->mask_w), x.gp(gw->mask_b), R0, CI, cc, w->mask_prelu, x.side->w)) return e;
     if (int e = launch_small_dgrad(x.at(p.g_masked), w->mask_w, x.at(p.g_u[0]), R0, CI, cc, y_last, w->mask_prelu, x.gp(gw->mask_prelu), st)) return e;
   }
+  TD_CUDA(cudaStreamWaitEvent(st, wt_ready, 0));
   // Recurrent, backwards: g_u[cur] holds d loss / d y_blk
   int cur = 0;
   cudaEvent_t w_pending = nullptr;

@@ -1498,7 +1498,21 @@ __global__ void framed_wgrad_kernel(const float* __restrict__ M, const float* __
   const int R = B * L0;
   const int r0 = blockIdx.y * rows_per_split, r1 = min(r0 + rows_per_split, R);
   float acc = 0.f;
-  for (int r = r0; r < r1; ++r) {
+  // four rows per trip: their eight loads are independent of the accumulation chain and go out together (the plain
+  // loop paid one L2 round trip per row: 148 us for the encoder basis at B = 8); the sum keeps its order
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    float mv[4], sv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = (r + q) / L0, l = (r + q) % L0;
+      mv[q] = M[(size_t)(r + q) * m_stride + ci];
+      sv[q] = framed_sig(sig + ((size_t)b * NO + o) * T, l * S + j - K / 2, shift, T);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc = fmaf(mv[q], sv[q], acc);
+  }
+  for (; r < r1; ++r) {
     const int b = r / L0, l = r % L0;
     const float mv = M[(size_t)r * m_stride + ci];
     acc = fmaf(mv, framed_sig(sig + ((size_t)b * NO + o) * T, l * S + j - K / 2, shift, T), acc);
