@@ -50,6 +50,7 @@ class SeparationEngine:
         self._gen = 0
         self._tws_listeners = []                           # called when a training workspace is reallocated
         self._rng: Dict[torch.device, torch.Tensor] = {}   # device int64[2] = {seed, offset} of the dropout masks
+        self._pack_seq = 0                                 # id of the last pack(): the graph cache is keyed on it
 
     # ------------------------------------------------------------------ configuration
     @property
@@ -164,7 +165,22 @@ class SeparationEngine:
         # the Weights (the model's cached pack, a TrainingStep, one autograd backward) owns their lifetime - nothing
         # accumulates on the engine.
         w._keep = keep
+        # Captured graphs bake these pointers in.  They are cached per pack id, not per struct address: a struct
+        # garbage-collected after a re-pack can hand its address to a later one, and a graph of the freed storage
+        # must never be replayed for it.
+        self._pack_seq += 1
+        w._pack_id = self._pack_seq
         return w
+
+    def drop_graphs(self, weights: Optional[Weights] = None) -> None:
+        """Forgets the captured forwards of `weights` (all of them when None); the model calls this when it re-packs
+        its parameters after their storage moved."""
+        if weights is None:
+            self._graphs.clear()
+            return
+        pid = getattr(weights, "_pack_id", None)
+        for key in [k for k in self._graphs if k[6] == pid]:
+            del self._graphs[key]
 
     # ------------------------------------------------------------------ workspace
     def workspace_bytes(self, batch: int, n_samples: int) -> int:
@@ -322,7 +338,11 @@ class SeparationEngine:
         pipeline alternates two of them so that it can copy into / out of the buffers of one step while the other
         step's replay runs (look2hear.system.separate_pipelined), with no staging copies."""
         device = torch.device(device)
-        key = (device, B, T, attn_group, self.cfg.gemm_mode, self.cfg.act_dtype, C.addressof(weights), slot)
+        pack_id = getattr(weights, "_pack_id", None)
+        if pack_id is None:                  # a struct filled by hand: give it an id of its own
+            self._pack_seq += 1
+            pack_id = weights._pack_id = self._pack_seq
+        key = (device, B, T, attn_group, self.cfg.gemm_mode, self.cfg.act_dtype, pack_id, slot)
         entry = self._graphs.get(key)
         if entry is None:
             static_in = torch.zeros(B, T, dtype=torch.float32, device=device) if example is None else example.clone()

@@ -133,6 +133,8 @@ class _TDANetCommon(BaseModel):
         sd = {k: v for k, v in self.state_dict(keep_vars=True).items()}
         sig = tuple(t.data_ptr() for t in sd.values())
         if getattr(self, "_packed_sig", None) != sig:
+            if getattr(self, "_packed", None) is not None:
+                self._engine.drop_graphs(self._packed)     # captured forwards of the old storage
             self._packed = self._engine.pack({k: v.detach() for k, v in sd.items()})
             self._packed_sig = sig
         return self._packed

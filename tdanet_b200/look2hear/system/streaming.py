@@ -101,6 +101,7 @@ def _separate_pipelined_graphed(model, host_batches, host_outputs, dev):
                 if ev_free[slot] is not None:
                     s_in.wait_event(ev_free[slot])
                 sin.copy_(h2, non_blocking=True)
+                sin.record_stream(s_in)   # a larger batch later re-captures and drops these buffers mid-copy
                 ev_in[slot].record(s_in)
             cur.wait_event(ev_in[slot])
             if ev_drained[slot] is not None:
@@ -118,6 +119,7 @@ def _separate_pipelined_graphed(model, host_batches, host_outputs, dev):
                 else:
                     k, ho = None, torch.empty(B, n_src, T, dtype=torch.float32).pin_memory()
                 ho.copy_(sout, non_blocking=True)
+                sout.record_stream(s_out)
                 ev_drained[slot] = torch.cuda.Event()
                 ev_drained[slot].record(s_out)
                 if k is not None:

@@ -19,6 +19,7 @@ gives the deterministic step the parity tests compare with autograd of the oracl
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -88,7 +89,10 @@ class TrainingStep:
         self._w = self._gw = None
         self._graph = None
         self._graph_shapes = None
-        model.engine.on_train_workspace_realloc(self._drop_graph)
+        # weakly: the engine outlives this object (a second TrainingStep for the same model must not keep the first
+        # one's flat buffers and graph alive through the listener list)
+        drop = weakref.WeakMethod(self._drop_graph)
+        model.engine.on_train_workspace_realloc(lambda device, _drop=drop: (_drop() or (lambda d: None))(device))
         self.broadcast_state()
 
     def _drop_graph(self, device=None) -> None:
@@ -175,13 +179,19 @@ class TrainingStep:
             self.params.zero_grad()
             self._static_loss = self.forward_backward(self._static_mix, self._static_tgt)
         self._graph = g
-        self._graph_shapes = (tuple(self._static_mix.shape), tuple(self._static_tgt.shape), self.model.training,
-                              self.model.attn_group)
+        self._graph_shapes = self._graph_key(self._static_mix, self._static_tgt)
+
+    def _graph_key(self, mixtures: torch.Tensor, targets: torch.Tensor):
+        """Everything the captured step bakes in besides the buffers: shapes and the modes the library reads from
+        the configuration at enqueue time."""
+        m = self.model
+        return (tuple(mixtures.shape), tuple(targets.shape), m.training, m.attn_group, m.gemm_mode, m.act_dtype,
+                float(m.dropout), float(m.drop_path), self.loss.loss_func.sdr_type, bool(self.loss.threshold_byloss))
 
     def step_captured(self, mixtures: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         if mixtures.ndim == 3:
             mixtures = mixtures.squeeze(1)
-        shapes = (tuple(mixtures.shape), tuple(targets.shape), self.model.training, self.model.attn_group)
+        shapes = self._graph_key(mixtures, targets)
         if self._graph is None or self._graph_shapes != shapes:
             self.capture(mixtures, targets)       # first call, new batch shape / mode, or the workspace moved
         self._static_mix.copy_(mixtures, non_blocking=True)

@@ -292,3 +292,58 @@ def test_graph_pipeline_with_ragged_batches():
         y1 = m(batches[0].to(DEV))
         y2 = m(batches[1].to(DEV))
     assert y1.data_ptr() != y2.data_ptr() and max_rel(y1.cpu(), want[0]) < 5e-6
+
+
+def test_graphs_follow_the_packed_weights_not_their_address():
+    """The captured forwards are cached per pack of the parameters.  After the storage moves twice (a struct freed
+    by the first re-pack can hand its address to the third pack) the graph mode must still read the live parameters,
+    and the graphs of the dropped pack must be gone."""
+    kw = dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=4, enc_kernel_size=2, num_sources=2)
+    torch.manual_seed(11)
+    m = look2hear.models.TDANetBest(sample_rate=16000, **kw).eval().to(DEV)
+    m.gemm_mode = "fp32"
+    x = (torch.randn(2, 1, 3000, generator=torch.Generator().manual_seed(12)) * 0.1).to(DEV)
+    m.use_cuda_graph = True
+    with torch.no_grad():
+        m(x)
+        ids = set()
+        for scale in (1.5, 0.5, 2.0):
+            for p in m.parameters():            # new storage for every parameter, different values
+                p.data = (p.data * scale).clone()
+            gc.collect()
+            y_graph = m(x)
+            ids.add(m._weights()._pack_id)
+            assert {k[6] for k in m.engine._graphs} == {m._weights()._pack_id}
+            m.use_cuda_graph = False
+            y_eager = m(x)
+            m.use_cuda_graph = True
+            assert max_rel(y_graph.cpu(), y_eager.cpu()) < 5e-6
+    assert len(ids) == 3
+
+
+def test_training_step_listener_does_not_keep_a_dropped_step_alive():
+    """The engine calls back into TrainingStep when the training workspace is reallocated; that hook is weak, so a
+    TrainingStep that went out of scope frees its flat buffers, and the call-back of a dead step is a no-op."""
+    import weakref
+    import tdanet_b200.look2hear.system as S
+    kw = CASES["depth4"]
+    m = _model(kw, _model_sd(kw)).train()
+    m.dropout = m.drop_path = 0.0
+    loss = look2hear.losses.PITLossWrapper(look2hear.losses.pairwise_neg_sisdr, threshold_byloss=False)
+    g = torch.Generator().manual_seed(3)
+    tgt = (torch.randn(2, 2, 1500, generator=g) * 0.1).to(DEV)
+    ts = S.TrainingStep(m, loss, lr=1e-3)
+    ts.step_captured(tgt.sum(1), tgt)
+    ref = weakref.ref(ts)
+    del ts
+    gc.collect()
+    assert ref() is None
+    ts2 = S.TrainingStep(m, loss, lr=1e-3)
+    big = (torch.randn(4, 2, 3000, generator=g) * 0.1).to(DEV)
+    l1 = ts2.step_captured(big.sum(1), big)     # larger batch: workspace reallocated, every listener called
+    assert torch.isfinite(l1).all()
+    # a mode the captured step bakes in changes: re-captured, not replayed
+    key = ts2._graph_shapes
+    m.gemm_mode = "fp32"
+    ts2.step_captured(big.sum(1), big)
+    assert ts2._graph_shapes != key
