@@ -153,6 +153,16 @@ TDANET_API int tdanet_profile_enable(int on);
 TDANET_API int tdanet_profile_dump(char* out, size_t cap);
 /* 0 if device `dev` can run the library (compute capability 10.x) */
 TDANET_API int tdanet_device_supported(int dev);
+/* Deterministic statistics (process-wide, off by default; TDANET_DETERMINISTIC=1 in the environment turns it on at
+ * load).  The GlobLN sums of tdanet_forward are accumulated across thread blocks with floating-point atomics, so two
+ * runs of the same call differ by ~1e-7 (fp32 GEMMs) / up to ~1e-4 (TF32: a sum that moves in its last bit can flip
+ * a TF32 rounding) - inside the parity tolerance, but in the way when bisecting a regression.  With the mode on every
+ * such sum is accumulated exactly (integer atomics on a fixed-point pair per statistic) and tdanet_forward is
+ * bit-reproducible run to run, at the cost of one small launch per producer of a statistic.  The mode enlarges the
+ * inference workspace: set it BEFORE tdanet_workspace_bytes.  Training calls (tdanet_forward_train*, tdanet_backward:
+ * their weight-gradient accumulation is atomic as well) are not affected. */
+TDANET_API int tdanet_set_deterministic(int on);
+TDANET_API int tdanet_get_deterministic(void);
 
 /* ------------------------------------------------------------------ model forward
  * Replaces TDANet*.forward(input_wav) (TDANet_best.py:482-521, TDANet.py:869-909,

@@ -92,6 +92,9 @@ import json,sys
 d=json.loads(open('$out/${tag}_train_${fn}.json').read().strip().splitlines()[-1])
 print('train', d['value'], 'steps/s', d['ms_per_step'], 'ms; e2e', d['e2e']['value'], 'launches', d['gpu_launches_per_step'], 'step_frac', d.get('step_frac'))
 ";;
+    det)
+      timeout 300 python scripts/det_probe.py $out/${tag}_deterministic.json > $out/${tag}_det.log 2>&1
+      echo "det rc=$? $(tail -1 $out/${tag}_det.log | cut -c1-600)";;
     *) echo "unknown step $what";;
   esac
 done

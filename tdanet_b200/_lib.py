@@ -77,6 +77,8 @@ _SIGNATURES = {
     "tdanet_last_error": (C.c_char_p, []),
     "tdanet_launch_count": (C.c_uint64, []),
     "tdanet_device_supported": (C.c_int, [C.c_int]),
+    "tdanet_set_deterministic": (C.c_int, [C.c_int]),
+    "tdanet_get_deterministic": (C.c_int, []),
     "tdanet_profile_enable": (C.c_int, [C.c_int]),
     "tdanet_profile_dump": (C.c_int, [C.c_char_p, C.c_size_t]),
     "tdanet_workspace_bytes": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
@@ -138,6 +140,16 @@ def check(code: int) -> None:
     if code != 0:
         msg = load().tdanet_last_error().decode(errors="replace")
         raise TdanetError(f"tdanet_b200 error {code}: {msg}")
+
+
+def set_deterministic(on: bool) -> None:
+    """Process-wide: exact (order-independent) accumulation of the GlobLN statistics of the inference forward, so
+    that two runs of the same call return the same bits (include/tdanet_b200.h: tdanet_set_deterministic)."""
+    check(load().tdanet_set_deterministic(int(bool(on))))
+
+
+def deterministic() -> bool:
+    return bool(load().tdanet_get_deterministic())
 
 
 def launch_count() -> int:

@@ -328,7 +328,8 @@ int launch_ln_residual(const float* a, const float* xin, const float* resid, con
 template <bool RES, bool STATS, bool DROP = false>
 __global__ void affine_kernel(const float* __restrict__ x, NormRef norm,
                               const float* __restrict__ resid, float* __restrict__ y,
-                              float* __restrict__ chstats, int L, int C, int rows_per_cta, DropRef drop) {
+                              float* __restrict__ chstats, int L, int C, int rows_per_cta, DropRef drop,
+                              DetRef det) {
   grid_dep_wait();
   constexpr int V = 4;
   const int b = blockIdx.z;
@@ -368,29 +369,30 @@ __global__ void affine_kernel(const float* __restrict__ x, NormRef norm,
   }
   if constexpr (STATS) {
     float* sp = chstats + (size_t)b * 2 * C + ch;
-    vred_add<V>(sp, s1);
-    vred_add<V>(sp + C, s2);
+    vstat_add<V>(det, sp, s1);
+    vstat_add<V>(det, sp + C, s2);
   }
 }
 
 int launch_affine_residual(const float* x, const NormRef& norm, const float* resid, float* y,
-                           float* chstats, const DropRef& drop, int B, int L, int C, cudaStream_t st) {
+                           float* chstats, const DropRef& drop, int B, int L, int C, cudaStream_t st,
+                           const DetRef& det) {
   TD_REQUIRE(C % 4 == 0, "affine_residual: C=%d", C);
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
   const int rows = 8;
   dim3 grid(cdiv(L, rows), cdiv(C / 4, threads), B);
   if (drop.mask || drop.item_mask) {
     if (chstats) {
-      TD_LAUNCH((affine_kernel<true, true, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, drop);
+      TD_LAUNCH((affine_kernel<true, true, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, drop, det);
     } else {
-      TD_LAUNCH((affine_kernel<true, false, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, drop);
+      TD_LAUNCH((affine_kernel<true, false, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, drop, det);
     }
     return 0;
   }
   if (chstats) {
-    TD_LAUNCH((affine_kernel<true, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, DropRef{});
+    TD_LAUNCH((affine_kernel<true, true>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, DropRef{}, det);
   } else {
-    TD_LAUNCH((affine_kernel<true, false>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, DropRef{});
+    TD_LAUNCH((affine_kernel<true, false>), grid, threads, 0, st, x, norm, resid, y, chstats, L, C, rows, DropRef{}, det);
   }
   return 0;
 }
@@ -400,7 +402,7 @@ int launch_affine(const float* x, const NormRef& norm, float* y, int B, int L, i
   int threads = C / 4 > 256 ? 256 : (C / 4 < 32 ? 32 : C / 4);
   const int rows = 16;
   dim3 grid(cdiv(L, rows), cdiv(C / 4, threads), B);
-  TD_LAUNCH((affine_kernel<false, false>), grid, threads, 0, st, x, norm, nullptr, y, nullptr, L, C, rows, DropRef{});
+  TD_LAUNCH((affine_kernel<false, false>), grid, threads, 0, st, x, norm, nullptr, y, nullptr, L, C, rows, DropRef{}, DetRef{});
   return 0;
 }
 

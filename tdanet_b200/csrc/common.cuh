@@ -313,6 +313,61 @@ __device__ __forceinline__ void vred_add(float* p, const vf<V>& r) {
 #endif
 }
 
+// ----------------------------------------------------------------------------- deterministic statistics
+// The GlobLN sums are accumulated across CTAs with floating-point atomics, so two runs of one forward differ in the
+// last bits (the order of the adds).  The deterministic mode (tdanet_set_deterministic / TDANET_DETERMINISTIC=1,
+// inference) makes every such add EXACT instead: a partial v is split into two integers, hi = floor(v * 2^8) and
+// lo = trunc((v * 2^8 - hi) * 2^48), which are added to a pair of 64-bit words with integer atomics - integer
+// addition is associative, so the pair is independent of the order - and a small kernel (det_finalize_kernel,
+// engine.cu) writes hi * 2^-8 + lo * 2^-56 into the slot the consumers read, before they run.  Range |sum| < 2^54,
+// resolution 2^-56 per partial, up to 2^15 partials per slot; a non-finite partial saturates (the mode is for
+// bisecting, not for diagnosing NaNs).  The pair of a slot at byte offset o of the statistics arena `base` lives at
+// shadow + 4 * o: a float slot owns 16 bytes there, a double slot 32 (the first 16 used).
+struct DetRef {
+  const char* base = nullptr;  // null: off (plain floating-point atomics)
+  char* shadow = nullptr;
+};
+#ifndef TD_EMU
+__device__ __forceinline__ void det_add(const DetRef& d, const void* slot, double v) {
+  unsigned long long* s =
+      reinterpret_cast<unsigned long long*>(d.shadow + 4 * (reinterpret_cast<const char*>(slot) - d.base));
+  double sc = v * 256.0;
+  if (!(sc < 4.6e18)) sc = 4.6e18;     // also catches NaN
+  if (sc < -4.6e18) sc = -4.6e18;
+  const double fl = floor(sc);
+  const long long hi = (long long)fl;
+  const unsigned long long lo = (unsigned long long)((sc - fl) * 281474976710656.0);  // 2^48
+  atomicAdd(s, (unsigned long long)hi);
+  atomicAdd(s + 1, lo);
+}
+__device__ __forceinline__ double det_value(const unsigned long long* s) {
+  return (double)(long long)s[0] * 0.00390625 + (double)s[1] * 1.3877787807814457e-17;  // 2^-8, 2^-56
+}
+#endif
+// dst[0] += a, dst[1] += b (one thread per CTA calls it)
+__device__ __forceinline__ void stat_add2(const DetRef& d, double* dst, double a, double b) {
+#ifndef TD_EMU
+  if (d.base) {
+    det_add(d, dst, a);
+    det_add(d, dst + 1, b);
+    return;
+  }
+#endif
+  atomicAdd(dst, a);
+  atomicAdd(dst + 1, b);
+}
+template <int V>
+__device__ __forceinline__ void vstat_add(const DetRef& d, float* p, const vf<V>& r) {
+#ifndef TD_EMU
+  if (d.base) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) det_add(d, p + e, (double)r.v[e]);
+    return;
+  }
+#endif
+  vred_add<V>(p, r);
+}
+
 // round-to-nearest (ties away) to TF32: what producers of GEMM-only operands store in TF32 mode so
 // that the tensor core's truncation of the low 13 mantissa bits is exact
 __device__ __forceinline__ float tf32_rna(float x) {

@@ -337,8 +337,8 @@ __device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0,
     for (int i = 0; i < NW; ++i) {
       if (a.chstats) {
         float* sp = a.chstats + ((size_t)(b * NW + i) * 2) * a.C + ch;
-        vred_add<V>(sp, s1[i]);
-        vred_add<V>(sp + a.C, s2[i]);
+        vstat_add<V>(a.det, sp, s1[i]);
+        vstat_add<V>(a.det, sp + a.C, s2[i]);
       }
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -352,15 +352,12 @@ __device__ __forceinline__ void dw5_body(const DwArgs& a, int b, int ch, int t0,
 // per-item totals: block reduction, then one pair of double atomics per CTA
 template <int NW>
 __device__ __forceinline__ void flush_item_stats(double* stats, int b, const float (&tot1)[NW], const float (&tot2)[NW],
-                                                 double* red) {
+                                                 double* red, const DetRef& det = DetRef{}) {
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
     double d1 = tot1[i], d2 = tot2[i];
     block_sum2(d1, d2, red);
-    if (threadIdx.x == 0) {
-      atomicAdd(stats + ((size_t)b * NW + i) * 2, d1);
-      atomicAdd(stats + ((size_t)b * NW + i) * 2 + 1, d2);
-    }
+    if (threadIdx.x == 0) stat_add2(det, stats + ((size_t)b * NW + i) * 2, d1, d2);
   }
 }
 
@@ -388,7 +385,7 @@ __global__ void __launch_bounds__(256) dw5_kernel(DwArgs a, int rows_per_cta) {
     if (interior) dw5_body<KIND, V, NW, S, R, WRITE, STATS, false>(a, b, ch, t0, t1, jtab, in_first, tot1, tot2);
     else dw5_body<KIND, V, NW, S, R, WRITE, STATS, true>(a, b, ch, t0, t1, jtab, in_first, tot1, tot2);
   }
-  if constexpr (STATS) flush_item_stats<NW>(a.stats, b, tot1, tot2, red);
+  if constexpr (STATS) flush_item_stats<NW>(a.stats, b, tot1, tot2, red, a.det);
 }
 
 // ----------------------------------------------------------------------------- dw k=5 with fused pooling
@@ -512,8 +509,8 @@ __device__ __forceinline__ void dw5_pool_body(const DwArgs& a, int b, int ch, in
   }
   if (a.chstats) {
     float* sp = a.chstats + ((size_t)b * 2) * a.C + ch;
-    vred_add<V>(sp, s1);
-    vred_add<V>(sp + a.C, s2);
+    vstat_add<V>(a.det, sp, s1);
+    vstat_add<V>(a.det, sp + a.C, s2);
   }
 #pragma unroll
   for (int e = 0; e < V; ++e) {
@@ -553,7 +550,7 @@ __global__ void __launch_bounds__(LB ? 128 : 256, LB ? LB : 1) dw5_pool_kernel(D
     if (interior) dw5_pool_body<KIND, S, false, RING, BULK>(a, b, ch, t0, tw, tc, bins, ja, nb, ringcol, tot1[0], tot2[0], rb);
     else dw5_pool_body<KIND, S, true, RING>(a, b, ch, t0, tw, tc, bins, ja, nb, ringcol, tot1[0], tot2[0]);
   }
-  flush_item_stats<1>(a.stats, b, tot1, tot2, red);
+  flush_item_stats<1>(a.stats, b, tot1, tot2, red, a.det);
 }
 
 static void pick_tiling(int B, int L, int ctiles, int R, int* rows_per_cta, int* tiles, long target = 148L * 16,
@@ -1671,7 +1668,7 @@ __global__ void __launch_bounds__(128, 3) la_local_stats_kernel(LocalStatsArgs p
     if (interior) stats_stream_body<LKIND, false, CT, BULK>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0], rb);
     else stats_stream_body<LKIND, true, CT>(loc, b, ch, t0, t1, ring, jl, tot1[0], tot2[0]);
   }
-  flush_item_stats<1>(loc.stats, b, tot1, tot2, red);
+  flush_item_stats<1>(loc.stats, b, tot1, tot2, red, loc.det);
 }
 
 template <int LKIND>
@@ -1876,7 +1873,7 @@ __global__ void __launch_bounds__(128, 4) gstats_stream_kernel(DwArgs a, int row
     if (interior) gstats_stream_body<false, CT, BULK>(a, b, ch, t0, t1, la_smem, tot1, tot2, rb);
     else gstats_stream_body<true, CT>(a, b, ch, t0, t1, la_smem, tot1, tot2);
   }
-  flush_item_stats<2>(a.stats, b, tot1, tot2, red);
+  flush_item_stats<2>(a.stats, b, tot1, tot2, red, a.det);
 }
 
 static bool gstats_stream_applies(const DwArgs& a) {

@@ -82,11 +82,49 @@ static FwdSide g_fside[16];
 
 static thread_local FwdSide* t_fside = nullptr;  // set by forward() for the duration of the call
 
+// Deterministic mode (DetRef, common.cuh): the producers of a statistic accumulate it exactly in integer pairs; this
+// kernel, enqueued right behind the producer on the producer's stream, writes the value into the slots the consumers
+// read (n values of `elem` bytes from `slots`: double sums per item, or float sums per channel).
+__global__ void det_finalize_kernel(DetRef d, char* slots, int n, int elem) {
+  grid_dep_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  char* slot = slots + (size_t)i * elem;
+  const double v = det_value(reinterpret_cast<const unsigned long long*>(d.shadow + 4 * (slot - d.base)));
+  if (elem == 8) *reinterpret_cast<double*>(slot) = v;
+  else *reinterpret_cast<float*>(slot) = (float)v;
+}
+static int det_finalize(const DetRef& d, void* slots, size_t n, int elem, cudaStream_t st) {
+  if (!d.base || !slots || n == 0) return 0;
+  TD_LAUNCH(det_finalize_kernel, dim3((unsigned)((n + 255) / 256)), 256, 0, st, d, reinterpret_cast<char*>(slots), (int)n, elem);
+  return 0;
+}
+
 static int gemm(const Ctx& x, GemmArgs& g, size_t aux_off) {
-  if (x.c->gemm_mode == TDANET_GEMM_FP32) return launch_gemm_simt(g, x.st);
-  g.W_aux = x.at(aux_off);
-  g.narrow = !x.p->train;   // inference: the main stream has the SMs to itself while a GEMM runs
-  return launch_gemm_tc(g, x.c->gemm_mode, x.st);
+  if (g.stats) g.det = x.det();
+  if (x.c->gemm_mode == TDANET_GEMM_FP32) {
+    if (int e = launch_gemm_simt(g, x.st)) return e;
+  } else {
+    g.W_aux = x.at(aux_off);
+    g.narrow = !x.p->train;   // inference: the main stream has the SMs to itself while a GEMM runs
+    if (int e = launch_gemm_tc(g, x.c->gemm_mode, x.st)) return e;
+  }
+  return g.stats ? det_finalize(g.det, g.stats, (size_t)g.B * 2, 8, x.st) : 0;
+}
+
+// launch_dw5 with the statistics of its output (per item, optionally per channel) made exact in deterministic mode
+static int dw5_stats(const Ctx& x, DwArgs& d, cudaStream_t st) {
+  d.det = x.det();
+  if (int e = launch_dw5(d, st)) return e;
+  if (int e = det_finalize(d.det, d.stats, (size_t)d.B * d.nw * 2, 8, st)) return e;
+  return det_finalize(d.det, d.chstats, (size_t)d.B * d.nw * 2 * d.C, 4, st);
+}
+static int la_local_stats(const Ctx& x, DwArgs* steps, int n, cudaStream_t st) {
+  for (int i = 0; i < n; ++i) steps[i].det = x.det();
+  if (int e = launch_la_local_stats(steps, n, st)) return e;
+  for (int i = 0; i < n; ++i)
+    if (int e = det_finalize(steps[i].det, steps[i].stats, (size_t)steps[i].B * 2, 8, st)) return e;
+  return 0;
 }
 
 static int prepare_weights(const Ctx& x) {
@@ -209,10 +247,12 @@ static int global_attention(const Ctx& x, bool ln_pe_done) {
   g.B = B; g.L = Lb; g.N = C; g.K = 2 * C; g.epi = EPI_BIAS; g.stats = x.at<double>(p.st_fc2);
   { Tag t("gemm_fc2"); if (int e = gemm(x, g, p.aux_fc2)) return e; }
   // global_f = x + gLN(fc2); BEST also needs its per-channel sums for the closed-form loc_glo_fus
-  return launch_affine_residual(x.at(p.fc2), norm_ref(x, p.st_fc2, 2, (double)Lb * C, w->fc2.gamma, w->fc2.beta),
+  if (int e = launch_affine_residual(x.at(p.fc2), norm_ref(x, p.st_fc2, 2, (double)Lb * C, w->fc2.gamma, w->fc2.beta),
                                 x.at(p.ga_mid), x.at(p.ga_out),
                                 c->variant == TDANET_BEST ? x.at(p.st_g) : nullptr,
-                                DropRef{m_f2, ik, m_dp ? m_dp + B : nullptr, ikp}, B, Lb, C, x.st);
+                                DropRef{m_f2, ik, m_dp ? m_dp + B : nullptr, ikp}, B, Lb, C, x.st, x.det()))
+    return e;
+  return c->variant == TDANET_BEST ? det_finalize(x.det(), x.at(p.st_g), (size_t)B * 2 * C, 4, x.st) : 0;
 }
 
 // One UConvBlock (TDANet_best.py:342-380) including the concat_block that feeds the next one.
@@ -233,6 +273,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
   const Plan& p = *x.p;
   const int B = p.B, C = c->in_channels, cc = c->out_channels, depth = c->depth, Lb = p.Lb;
   TD_CUDA(cudaMemsetAsync(x.at<char>(p.st_proj), 0, p.stats_end - p.st_proj, x.st));
+  if (p.det) TD_CUDA(cudaMemsetAsync(x.ws + p.det_shadow, 0, 4 * (p.stats_end - p.stats_begin), x.st));
 
   // proj_1x1: 1x1 conv c -> C (+bias); GlobLN + PReLU are applied by the consumer on load
   GemmArgs g{};
@@ -264,7 +305,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       d.rev = l2_order(1) && ((spp_mask >> k) & 1);
     }
     if (c->variant != TDANET_FORK) { d.pool_out = x.at(p.pool_pw[k]); d.Lb = Lb; }  // pooled raw output P_k
-    { Tag t(k == 0 ? "spp_dw0" : "spp_dw_s2"); if (int e = launch_dw5(d, x.st)) return e; }
+    { Tag t(k == 0 ? "spp_dw0" : "spp_dw_s2"); if (int e = dw5_stats(x, d, x.st)) return e; }
   }
   // global feature at the bottom scale
   PoolArgs pa{};
@@ -356,14 +397,14 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     Tag t("la_stats_local");
     FwdSide* fs = t_fside;
     if (fs == nullptr || depth < 3) {
-      if (int e = launch_la_local_stats(dl, depth - 1, x.st)) return e;
+      if (int e = la_local_stats(x, dl, depth - 1, x.st)) return e;
     } else {
       if (int e = fs->order(x.st, fs->s)) return e;
-      if (int e = launch_la_local_stats(dl + 1, depth - 2, fs->s)) return e;  // scales 1 .. depth-2
+      if (int e = la_local_stats(x, dl + 1, depth - 2, fs->s)) return e;  // scales 1 .. depth-2
       cudaEvent_t ec = fs->events[fs->next++ % fs->events.size()];
       TD_CUDA(cudaEventRecord(ec, fs->s));
       for (int i = 1; i < depth - 1; ++i) local_ready[i] = ec;
-      if (int e = launch_la_local_stats(dl, 1, fs->s)) return e;              // scale 0
+      if (int e = la_local_stats(x, dl, 1, fs->s)) return e;              // scale 0
       cudaEvent_t e0 = fs->events[fs->next++ % fs->events.size()];
       TD_CUDA(cudaEventRecord(e0, fs->s));
       local_ready[0] = e0;
@@ -399,7 +440,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
       Tag t("la_combine_first");
       static const bool one_launch = !(getenv("TDANET_MAT2") && atoi(getenv("TDANET_MAT2")) == 0);
       if (one_launch) {
-        const bool st = first_stats_fused(false);
+        const bool st = first_stats_fused(false) && !p.det;  // its statistics are not on the exact path
         if (int e = launch_inject_materialize2(loc, x.at(p.fused_a), gsrc, x.at(p.fused_b), inj_kind, B, C, x.bf(), x.st,
                                                st ? la.global_act.w : nullptr, st ? la.global_embedding.w : nullptr,
                                                st ? x.at<double>(p.st_la_g[i]) : nullptr)) return e;
@@ -421,7 +462,7 @@ static int uconv_block(const Ctx& x, const float* in, float* out, bool last) {
     dg.rev = l2_order(2);
     if (!(i == depth - 2 && first_global_stats_done)) {
       Tag t("la_stats_global");
-      if (int e = launch_dw5(dg, x.st)) return e;
+      if (int e = dw5_stats(x, dg, x.st)) return e;
     }
     LaArgs l{};
     l.loc = loc; l.glo = glo; l.lkind = lkind; l.gkind = gkind; l.B = B; l.C = C;
@@ -477,6 +518,7 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
   }
 
   TD_CUDA(cudaMemsetAsync(x.ws + p.st_enc, 0, (size_t)B * 2 * sizeof(double), st));
+  if (p.det) TD_CUDA(cudaMemsetAsync(x.ws + p.det_enc_shadow, 0, 4 * (size_t)B * 2 * sizeof(double), st));
   Tag tag("frontend");
   if (int e = prepare_weights(x)) return e;
   // encoder (+ pad_input folded into the indexing) and its GlobLN statistics
@@ -485,7 +527,9 @@ static int forward(const tdanet_config_t* c, const tdanet_weights_t* w, const fl
   ea.nconv = c->enc_convs; ea.ch_per_conv = Nb / c->enc_convs; ea.Nb = Nb; ea.L0 = L0;
   for (int k = 0; k < c->enc_convs; ++k) { ea.w[k] = w->enc_w[k]; ea.ks[k] = (k + 1) * K; }
   ea.out = x.at(p.enc); ea.stats = x.at<double>(p.st_enc);
+  ea.det = x.det_enc();
   if (int e = launch_encoder(ea, st)) return e;
+  if (int e = det_finalize(ea.det, ea.stats, (size_t)B * 2, 8, st)) return e;
   const NormRef enc_norm = norm_ref(x, p.st_enc, 2, (double)L0 * Nb, w->ln_gamma, w->ln_beta);
   if (c->variant == TDANET_MULTRES) {
     if (int e = launch_affine(x.at(p.enc), enc_norm, x.at(p.x0), B, L0, Nb, st)) return e;
@@ -557,6 +601,13 @@ int tdanet_abi_sizes(size_t* config_bytes, size_t* weights_bytes) {
 const char* tdanet_last_error(void) { return g_err; }
 
 uint64_t tdanet_launch_count(void) { return g_launches.load(); }
+
+int tdanet_set_deterministic(int on) {
+  det_mode() = on != 0;
+  return 0;
+}
+
+int tdanet_get_deterministic(void) { return det_mode(); }
 
 int tdanet_device_supported(int dev) {
   cudaDeviceProp prop;

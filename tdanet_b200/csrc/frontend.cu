@@ -64,10 +64,7 @@ __global__ void __launch_bounds__(256) encoder_kernel(EncArgs a, int rows_per_ct
   __shared__ double red[64];
   double d1 = s1, d2 = s2;
   block_sum2(d1, d2, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(a.stats + 2 * b, d1);
-    atomicAdd(a.stats + 2 * b + 1, d2);
-  }
+  if (threadIdx.x == 0) stat_add2(a.det, a.stats + 2 * b, d1, d2);
 }
 
 int launch_encoder(const EncArgs& a, cudaStream_t st) {

@@ -104,10 +104,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a, int tiles_pe
   if (a.stats) {
     double d1 = s1, d2 = s2;
     block_sum2(d1, d2, red);
-    if (tid == 0) {
-      atomicAdd(a.stats + 2 * b, d1);
-      atomicAdd(a.stats + 2 * b + 1, d2);
-    }
+    if (tid == 0) stat_add2(a.det, a.stats + 2 * b, d1, d2);
   }
 }
 

@@ -368,10 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (lane == 0) mbar_arrive(acc_empty + acc);
           if constexpr (STATS) {
             const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
-            if (lane == 0) {
-              atomicAdd(a.stats + 2 * b, d1);
-              atomicAdd(a.stats + 2 * b + 1, d2);
-            }
+            if (lane == 0) stat_add2(a.det, a.stats + 2 * b, d1, d2);
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
@@ -443,10 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (lane == 0) mbar_arrive(acc_empty + acc);
       if constexpr (STATS) {
         const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
-        if (lane == 0) {
-          atomicAdd(a.stats + 2 * b, d1);
-          atomicAdd(a.stats + 2 * b + 1, d2);
-        }
+        if (lane == 0) stat_add2(a.det, a.stats + 2 * b, d1, d2);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -56,6 +56,7 @@ struct DwArgs {
   int rev;          // walk the batch items last to first (L2 reuse of what the producer wrote last; engine.cu)
   int relu;
   int round_out;  // store TF32-rounded values (output only feeds a tensor-core GEMM)
+  DetRef det;     // deterministic mode: where the sums of stats / chstats are accumulated exactly (common.cuh)
 };
 int launch_dw5(const DwArgs& a, cudaStream_t st);
 
@@ -156,7 +157,8 @@ int launch_ln_residual(const float* a, const float* xin, const float* resid, con
                        const float* b, float* y, int mode, const DropRef& drop, int B, int L, int C, cudaStream_t st);
 // y = resid + f_b * m * GlobLN(x) (m, f_b: multipliers of `drop`); optional per-channel stats of y -> [B,2,C]
 int launch_affine_residual(const float* x, const NormRef& norm, const float* resid, float* y,
-                           float* chstats, const DropRef& drop, int B, int L, int C, cudaStream_t st);
+                           float* chstats, const DropRef& drop, int B, int L, int C, cudaStream_t st,
+                           const DetRef& det = DetRef{});
 // ------------------------------------------------------------------ dropout.cu (training only)
 struct MaskRegion {
   size_t off;      // byte offset inside one iteration's block arena
@@ -186,6 +188,7 @@ struct EncArgs {
   int ch_per_conv, Nb, L0;
   float* out;     // [B, L0, Nb]
   double* stats;  // [B,2]
+  DetRef det;     // deterministic mode (common.cuh)
 };
 int launch_encoder(const EncArgs& a, cudaStream_t st);
 // x0[b,t,:] = Wb . GlobLN(enc) + bb     enc [B,L0,Nb], out [B,L0,c]
@@ -234,6 +237,7 @@ struct GemmArgs {
   int d_bf16, a_bf16;
   int rev;  // tensor-core path: tiles of the last batch item first (L2 reuse of what the producer wrote last)
   int narrow;  // tensor-core path: nothing else competes for the SMs (inference forward): narrow tiles for small launches
+  DetRef det;  // deterministic mode: where the sums of `stats` are accumulated exactly (common.cuh)
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& a, int mode, cudaStream_t st);

@@ -43,6 +43,10 @@ struct Plan {
   size_t inj_coef[TDANET_MAX_DEPTH];
   // statistics arena (zeroed once per block)
   size_t stats_begin, stats_end;
+  // deterministic mode (inference, det_mode()): the integer pairs the sums are accumulated in (DetRef, common.cuh),
+  // 4 bytes of shadow per byte of the statistics arena / of st_enc
+  bool det = false;
+  size_t det_shadow = 0, det_enc_shadow = 0;
   // per-item sum / sum of squares in double: [B,2] ([B,2,2] for st_la_g: global_act, global_embedding)
   size_t st_proj, st_fc1, st_fc2, st_pool[TDANET_MAX_DEPTH], st_spp[TDANET_MAX_DEPTH],
       st_la_l[TDANET_MAX_DEPTH], st_la_g[TDANET_MAX_DEPTH];
@@ -109,6 +113,17 @@ struct Plan {
     return (off >= blk_begin && off < blk_begin + blk_stride) ? off + (size_t)blk * blk_stride : off;
   }
 };
+
+// Process-wide switch of the deterministic-statistics mode (tdanet_set_deterministic; TDANET_DETERMINISTIC=1 in the
+// environment turns it on from the start).  It changes the inference workspace size, so a caller sets it before
+// sizing a workspace, not between tdanet_workspace_bytes and tdanet_forward.
+inline int& det_mode() {
+  static int mode = [] {
+    const char* e = getenv("TDANET_DETERMINISTIC");
+    return (e && e[0] != '0' && e[0] != 0) ? 1 : 0;
+  }();
+  return mode;
+}
 
 static inline int check_config(const tdanet_config_t* c) {
   TD_REQUIRE(c != nullptr, "config is NULL");
@@ -307,6 +322,11 @@ static inline int make_plan(const tdanet_config_t* c, int B, int T, Plan& p, boo
   // "block_out" aliases the u buffer the last block writes
   p.named.push_back({"block_out", p.u[(c->num_blocks - 1) & 1], {B, L0, cc}, 4});
   p.named.push_back({"u", p.u[(c->num_blocks & 1)], {B, L0, cc}, 4});
+  if (!train && det_mode()) {
+    p.det = true;
+    p.det_shadow = p.take(4 * (p.stats_end - p.stats_begin));
+    p.det_enc_shadow = p.take(4 * (size_t)B * 2 * sizeof(double));
+  }
   if (!train) return 0;
 
   // ---- gradient arena (reused by every iteration of the backward sweep)
@@ -409,6 +429,9 @@ struct Ctx {
   T* at(size_t off) const { return reinterpret_cast<T*>(ws + p->blk_off(off, blk)); }
   template <class T = float>
   T* at_blk(size_t off, int b) const { return reinterpret_cast<T*>(ws + p->blk_off(off, b)); }
+  // deterministic mode: the exact accumulators of the statistics arena / of the encoder's statistics
+  DetRef det() const { return p->det ? DetRef{ws + p->stats_begin, ws + p->det_shadow} : DetRef{}; }
+  DetRef det_enc() const { return p->det ? DetRef{ws + p->st_enc, ws + p->det_enc_shadow} : DetRef{}; }
 };
 
 static inline NormRef norm_ref(const Ctx& x, size_t stats_off, int item_stride, double count, const float* gamma,

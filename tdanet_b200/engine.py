@@ -342,7 +342,7 @@ class SeparationEngine:
         if pack_id is None:                  # a struct filled by hand: give it an id of its own
             self._pack_seq += 1
             pack_id = weights._pack_id = self._pack_seq
-        key = (device, B, T, attn_group, self.cfg.gemm_mode, self.cfg.act_dtype, pack_id, slot)
+        key = (device, B, T, attn_group, self.cfg.gemm_mode, self.cfg.act_dtype, pack_id, slot, _lib.deterministic())
         entry = self._graphs.get(key)
         if entry is None:
             static_in = torch.zeros(B, T, dtype=torch.float32, device=device) if example is None else example.clone()

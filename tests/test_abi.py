@@ -74,3 +74,22 @@ def test_headline_shapes():
     assert eng.latent_lengths(32000) == ([2010, 1005, 503, 252, 126], 32144, 48)
     eng2 = SeparationEngine("best", 128, 512, 16, 5, 32, 17, 2)
     assert eng2.latent_lengths(32000)[0] == [4010, 2005, 1003, 502, 251]
+
+
+def test_deterministic_mode_switch_and_workspace():
+    """tdanet_set_deterministic is process-wide, off by default, and enlarges the inference workspace by four bytes
+    per byte of GlobLN statistics (the exact accumulators) - the training workspace is not affected."""
+    eng = SeparationEngine("best", 128, 512, 16, 5, 64, 33, 2)
+    assert not _lib.deterministic()
+    plain, train = eng.workspace_bytes(64, 32000), eng.train_workspace_bytes(2, 8000)
+    _lib.set_deterministic(True)
+    try:
+        assert _lib.deterministic()
+        det = eng.workspace_bytes(64, 32000)
+        # per block: 3 + 4*depth + depth(la_g counts double) item sums [B,2] double, (depth + 1) channel tables [B,2,C]
+        stats = 64 * 2 * 512 * 4 * 6
+        assert plain + 4 * stats < det < plain + 4 * stats + (1 << 20)
+        assert eng.train_workspace_bytes(2, 8000) == train
+    finally:
+        _lib.set_deterministic(False)
+    assert eng.workspace_bytes(64, 32000) == plain

@@ -1,0 +1,93 @@
+"""The deterministic-statistics mode (include/tdanet_b200.h: tdanet_set_deterministic): every GlobLN sum of the
+inference forward is accumulated exactly (integer atomics on a fixed-point pair), so two runs of the same call return
+the same bits; the result still matches the oracle / the reference goldens inside the usual tolerances.
+Run on the B200 box: python -m pytest tests -m gpu."""
+import pytest
+import torch
+
+import tdanet_b200.look2hear as look2hear
+from conftest import CLASSES, load_golden, max_rel, oracle_cfg
+from oracle import tdanet_oracle as O
+from tdanet_b200 import _lib
+from test_gpu_parity import build_from_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture
+def deterministic():
+    _lib.set_deterministic(True)
+    try:
+        yield
+    finally:
+        _lib.set_deterministic(False)
+
+
+def _runs(m, x, n=4):
+    outs = []
+    with torch.no_grad():
+        for _ in range(n):
+            outs.append(m(x).clone())
+    torch.cuda.synchronize()
+    return outs
+
+
+@pytest.mark.parametrize("variant", list(CLASSES))
+@pytest.mark.parametrize("mode,tol", [("fp32", 3e-5), ("tf32", 1e-3)])
+def test_small_models_are_bit_reproducible_and_match_the_golden(deterministic, variant, mode, tol):
+    g = load_golden(f"{variant}_small")
+    m = build_from_golden(variant, g)
+    m.gemm_mode = mode
+    x = torch.from_numpy(g["x"]).to(DEV)
+    outs = _runs(m, x)
+    assert all(torch.equal(outs[0], o) for o in outs[1:]), "deterministic mode: runs differ"
+    assert max_rel(outs[0].cpu(), torch.from_numpy(g["y"])) < tol
+    # the default mode computes the same thing up to the order of its atomic adds
+    _lib.set_deterministic(False)
+    with torch.no_grad():
+        y = m(x)
+    assert max_rel(y.cpu(), outs[0].cpu()) < (5e-6 if mode == "fp32" else 1e-3)
+
+
+@pytest.mark.parametrize("variant,act", [("best", "fp32"), ("best", "bf16"), ("fork", "fp32")])
+def test_wide_model_ragged_batch_is_bit_reproducible(deterministic, variant, act):
+    """512 channels (the bulk-staged streaming kernels, the tcgen05 GEMMs with the statistics epilogue), a ragged
+    length, batch 5, 3 blocks; also as a CUDA graph and with bf16 activation storage."""
+    kw = dict(out_channels=128, in_channels=512, num_blocks=3, upsampling_depth=5, enc_kernel_size=4, num_sources=2)
+    torch.manual_seed(21)
+    m = getattr(look2hear.models, CLASSES[variant])(sample_rate=16000, **kw).eval()
+    x = torch.randn(5, 1, 20011, generator=torch.Generator().manual_seed(22)) * 0.1
+    with torch.no_grad():
+        ref = O.forward({k: v for k, v in m.state_dict().items()}, x, oracle_cfg(variant, kw, 16000))
+    m = m.to(DEV)
+    m.gemm_mode = "tf32"
+    m.act_dtype = act
+    xd = x.to(DEV)
+    outs = _runs(m, xd)
+    assert all(torch.equal(outs[0], o) for o in outs[1:]), "deterministic mode: runs differ"
+    if act == "fp32":
+        assert max_rel(outs[0].cpu(), ref) < 1e-3
+    m.use_cuda_graph = True
+    graphed = _runs(m, xd, 3)
+    assert all(torch.equal(outs[0], o) for o in graphed), "deterministic mode: graph replays differ from eager runs"
+    # switching the mode off re-captures (the graph cache is keyed on it) and still agrees within the atomics' noise
+    _lib.set_deterministic(False)
+    with torch.no_grad():
+        y = m(xd)
+    assert max_rel(y.cpu(), outs[0].cpu()) < (1e-3 if act == "fp32" else 2e-2)
+
+
+def test_headline_shape_is_bit_reproducible(deterministic):
+    """BASELINE.json configs[1] (TDANetBest 4 ms, 16 blocks, 64 x 2 s, TF32): two runs, same bits."""
+    torch.manual_seed(0)
+    m = look2hear.models.TDANetBest(out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=5,
+                                    enc_kernel_size=4, num_sources=2, sample_rate=16000).eval().to(DEV)
+    x = (torch.randn(64, 1, 32000, generator=torch.Generator().manual_seed(1)) * 0.1).to(DEV)
+    outs = _runs(m, x, 3)
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    assert torch.isfinite(outs[0]).all()
+    _lib.set_deterministic(False)
+    with torch.no_grad():
+        y = m(x)
+    assert max_rel(y.cpu(), outs[0].cpu()) < 1e-3
