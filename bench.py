@@ -782,6 +782,7 @@ def run_ours(args):
             "dtype": dtype, "data": "synthetic",
             "config": common_config(args.variant, args.enc_ms, B),
             "impl_config": {"gemm_mode": args.gemm_mode, "act_dtype": args.act_dtype, "cuda_graph": not args.no_graph,
+                            "deterministic_statistics": bool(getattr(args, "deterministic", False)),
                             "global_batch": B * world, "numa": numa,
                             "l2": "no flush needed: one step streams a 1.7 GB workspace, 13x the 126 MB L2"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": B * 2 * N_SAMPLES * 4,
@@ -895,7 +896,12 @@ def main():
     ap.add_argument("--skip-eager", action="store_true", help="skip the eager-PyTorch-on-B200 baseline (N=1 only)")
     ap.add_argument("--skip-2ms", action="store_true", help="skip the strong-scaled 2 ms leg (BASELINE.json configs[2])")
     ap.add_argument("--detail-out", default="", help="where the full record goes (default gpurun_out/bench_detail_*.json)")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="our arm with the deterministic-statistics mode on (bit-reproducible inference; measures its cost)")
     args = ap.parse_args()
+    if args.deterministic and args.impl == "ours":
+        from tdanet_b200 import _lib
+        _lib.set_deterministic(True)
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "eager_gpu":

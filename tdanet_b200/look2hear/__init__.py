@@ -5,3 +5,4 @@ kwargs, forward signatures and state_dict keys, so `import tdan
 look2hear` is the whole migration for code that only touches this path.
 """
 from . import losses, metrics, models, system  # noqa: F401
+from .._lib import deterministic, set_deterministic  # noqa: F401  (bit-reproducible inference: exact GlobLN sums)
