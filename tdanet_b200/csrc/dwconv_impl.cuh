@@ -203,6 +203,14 @@ __device__ __forceinline__ void sb_bulk_g2s(void* dst, const void* src, uint32_t
                : "memory");
 }
 
+// The stages are read with ordinary ld.shared (generic proxy) and refilled by cp.async.bulk (async proxy).  The
+// mbarrier hand-over alone does not order the two proxies: without this fence the refill of a stage could overtake the
+// last reads of it - found with the deterministic-statistics mode as 2 deviating forwards in 16,000 (256 bytes of one
+// staged row from the NEXT fill of the stage; profiles/r04_bulk_ring_race.txt).  Every thread fences its own reads
+// before its warp signals the stage empty (the pattern of CUTLASS's TMA-load epilogues: fence_view_async_shared()
+// ahead of consumer_release).
+__device__ __forceinline__ void sb_fence_reads() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Two-stage ring protocol of the streaming kernels.  In the LA kernels stage 1 has one extra phase at the start: the
 // four rows ahead of the CTA's first chunk are parked in it while chunk 0 lands in stage 0.
 struct SbRing {
@@ -217,6 +225,7 @@ struct SbRing {
   __device__ __forceinline__ void wait_full(int k) const { sb_wait(full + (k & 1), (k >> 1) & 1); }
   // every warp, after its last read of stage s
   __device__ __forceinline__ void release(int s) const {
+    sb_fence_reads();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) sb_arrive(empty + s);
   }
@@ -252,6 +261,7 @@ struct SbRingN {
   }
   __device__ __forceinline__ void wait_full(const SbCursor& c) const { sb_wait(full + c.stage, c.phase); }
   __device__ __forceinline__ void release(int stage) const {          // every warp, after its last read of the stage
+    sb_fence_reads();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) sb_arrive(empty + stage);
   }
