@@ -276,7 +276,8 @@ __device__ __forceinline__ SbRingN sb_ringn_init(uint64_t* bars, int ns, int nwa
 constexpr size_t SB_BAR_BYTES = 2 * SB_MAX_STAGES * sizeof(uint64_t);
 // stages of the bulk rings of the two statistics kernels (TDANET_BULK_STAGES).  Measured on B200 (B = 64): deeper
 // rings are SLOWER - 2 / 3 / 4 stages: 17.59 / 18.16 / 18.78 ms per step, every streaming role slower - so more
-// bytes in flight is not what these kernels lack; 2 is the default.  spp_dw keeps two stages unconditionally.
+// bytes in flight is not what these kernels lack; 2 is the default.  spp_dw keeps two stages unconditionally
+// (slower with three; its intermittent parity failures at three stages predate sb_fence_reads()).
 static inline int bulk_stages() {
   static const int n = getenv("TDANET_BULK_STAGES") ? atoi(getenv("TDANET_BULK_STAGES")) : 2;
   return n < 2 ? 2 : (n > SB_MAX_STAGES ? SB_MAX_STAGES : n);
@@ -645,8 +646,9 @@ static int launch_dw5_pool_t(const DwArgs& a, cudaStream_t st) {
   }
   const bool lb4 = lb == 4 && threads <= 128;
   if (ring == 2 && lb4 && a.C == 512 && threads == 128 && (bulk_mask() & 8)) {
-    // two stages: with three the B = 64 parity tests failed intermittently (1e-3 instead of 1e-6; the statistics
-    // kernels pass with three) and the launch was slower anyway, so the depth is not a knob here
+    // two stages: three were slower, so the depth is not a knob here.  (With three the B = 64 parity tests also failed
+    // intermittently at 1e-3 in the second session - in hindsight the proxy race sb_fence_reads() closes, which a
+    // deeper ring makes likelier; not re-measured since.)
     const int ns = 2;
     TD_LAUNCH((dw5_pool_kernel<KIND, S, 4, 2, true>), grid, threads, ring_b / 2 * ns + bins_b + SB_BAR_BYTES, st, a, bpt, ns);
     return 0;
