@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call of round 2: parity tests, bench, TF32 peak, ncu evidence.  Usage (from the repo root, on the box):
-#   bash scripts/gpu_call.sh <tag> [tests] [bench] [peak] [ncu_gemm] [ncu_list] [ncu_train] [refarm]
+#   bash scripts/gpu_call.sh <tag> [tests] [bench] [peak] [ncu_gemm] [ncu_list] [ncu_train] [refarm] [det] [hunt_24000]
 # Every artefact lands in gpurun_out/<tag>_*.
 tag=$1; shift
 out=gpurun_out
@@ -95,6 +95,14 @@ print('train', d['value'], 'steps/s', d['ms_per_step'], 'ms; e2e', d['e2e']['val
     det)
       timeout 300 python scripts/det_probe.py $out/${tag}_deterministic.json > $out/${tag}_det.log 2>&1
       echo "det rc=$? $(tail -1 $out/${tag}_det.log | cut -c1-600)";;
+    hunt_*)
+      # rare run-to-run deviations with exact statistics: hunt_<runs> back-to-back 1-block forwards (scripts/det_hunt.py),
+      # then the element-wise form on a third as many (scripts/det_hunt2.py); profiles/r04_bulk_ring_race.txt
+      n=${what#hunt_}
+      timeout 300 python scripts/det_hunt.py --blocks 1 --runs $n --out $out/${tag}_hunt_b1.json > $out/${tag}_hunt.log 2>&1
+      echo "hunt rc=$? $(tail -1 $out/${tag}_hunt.log | cut -c1-600)"
+      timeout 300 python scripts/det_hunt2.py --runs $((n / 3)) --out $out/${tag}_hunt2.json > $out/${tag}_hunt2.log 2>&1
+      echo "hunt2 rc=$? $(tail -1 $out/${tag}_hunt2.log | cut -c1-600)";;
     *) echo "unknown step $what";;
   esac
 done

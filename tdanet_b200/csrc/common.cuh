@@ -327,7 +327,6 @@ struct DetRef {
   const char* base = nullptr;  // null: off (plain floating-point atomics)
   char* shadow = nullptr;
 };
-#ifndef TD_EMU
 __device__ __forceinline__ void det_add(const DetRef& d, const void* slot, double v) {
   unsigned long long* s =
       reinterpret_cast<unsigned long long*>(d.shadow + 4 * (reinterpret_cast<const char*>(slot) - d.base));
@@ -343,28 +342,23 @@ __device__ __forceinline__ void det_add(const DetRef& d, const void* slot, doubl
 __device__ __forceinline__ double det_value(const unsigned long long* s) {
   return (double)(long long)s[0] * 0.00390625 + (double)s[1] * 1.3877787807814457e-17;  // 2^-8, 2^-56
 }
-#endif
 // dst[0] += a, dst[1] += b (one thread per CTA calls it)
 __device__ __forceinline__ void stat_add2(const DetRef& d, double* dst, double a, double b) {
-#ifndef TD_EMU
   if (d.base) {
     det_add(d, dst, a);
     det_add(d, dst + 1, b);
     return;
   }
-#endif
   atomicAdd(dst, a);
   atomicAdd(dst + 1, b);
 }
 template <int V>
 __device__ __forceinline__ void vstat_add(const DetRef& d, float* p, const vf<V>& r) {
-#ifndef TD_EMU
   if (d.base) {
 #pragma unroll
     for (int e = 0; e < V; ++e) det_add(d, p + e, (double)r.v[e]);
     return;
   }
-#endif
   vred_add<V>(p, r);
 }
 

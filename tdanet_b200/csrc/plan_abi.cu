@@ -58,4 +58,22 @@ int tdanet_train_workspace_tensor(const tdanet_config_t* cfg, int batch, int n_s
   return find_named(p, name, block, byte_offset, dims, elem_bytes);
 }
 
+#ifdef TD_EMU
+// Test hook of the CPU emulation build (tests/test_deterministic_emu.py): the fixed-point accumulation of the
+// deterministic-statistics mode (common.cuh: det_add / det_value) applied to v[order[0]], v[order[1]], ... into the
+// pair of a double slot and of a float slot; returns what det_finalize_kernel would write.
+int tdanet_emu_det_sum(const double* v, const int32_t* order, int n, double* as_double, float* as_float) {
+  alignas(16) char slots[16] = {};          // [0, 8): a double slot, [8, 12): a float slot
+  alignas(16) unsigned long long shadow[8] = {};
+  const DetRef d{slots, reinterpret_cast<char*>(shadow)};
+  for (int i = 0; i < n; ++i) {
+    det_add(d, slots, v[order[i]]);
+    det_add(d, slots + 8, (double)(float)v[order[i]]);
+  }
+  if (as_double) *as_double = det_value(shadow);
+  if (as_float) *as_float = (float)det_value(shadow + 4);
+  return 0;
+}
+#endif
+
 }  // extern "C"
